@@ -1,0 +1,462 @@
+///////////////////////////////////////////////////////////////////////////////
+///
+///	\file    ref_dump.cpp
+///
+///	Dump-hook driver for the parity oracle.  TEST INFRASTRUCTURE ONLY.
+///
+///	Links the UNMODIFIED reference objects (oracle/_ref/libtempestref.a) and
+///	calls the reference plugin methods one at a time (all public:
+///	HorizontalDynamics.h:57-167, VerticalDynamics.h:53-126, Grid.h:228,548-566,
+///	TimestepScheme.h:55-117), writing the raw arrays after every operation to
+///	one binary file that tests/ read with tests/refdump.py.
+///
+///	usage: ref_dump --case (sw2|jw|bubble) --out FILE --npatch N
+///	                --script "op;op;..."  [reference command-line flags]
+///
+///	script ops (instances are the reference's state-instance indices):
+///	  dump:TAG              write every state/tracer instance of every patch
+///	  hexp:IN,OUT,DT        HorizontalDynamics::StepExplicit
+///	  vexp:IN,OUT,DT        VerticalDynamics::StepExplicit
+///	  vimp:IN,OUT,DT        VerticalDynamics::StepImplicit
+///	  dss:INST              Grid::PostProcessSubstage(INST, State) (+Tracers)
+///	  hasc:IN,OUT,WORK,DT   HorizontalDynamics::StepAfterSubCycle
+///	  copy:SRC,DST          Grid::CopyData (State and Tracers)
+///	  lincomb:DST,c0,c1,..  Grid::LinearCombineData (State and Tracers)
+///	  step:N                N calls of TimestepScheme::Step (first = first call)
+///	  checksum:TAG          Grid::Checksum of instance 0 -> record
+///
+///	The test-case classes live in the reference's driver sources next to a
+///	main(); they are included (not copied) with main renamed.
+///
+///////////////////////////////////////////////////////////////////////////////
+
+#define main SWTest2_reference_main
+#include "shallowwater_sphere/SWTest2.cpp"
+#undef main
+#define main BaroclinicWaveJW_reference_main
+#include "nonhydro_sphere/BaroclinicWaveJWTest.cpp"
+#undef main
+#define main ThermalBubble_reference_main
+#include "nonhydro_xz/ThermalBubbleCartesianTest.cpp"
+#undef main
+
+#include "GridCSGLL.h"
+#include "GridCartesianGLL.h"
+#include "GridPatchGLL.h"
+#include "HorizontalDynamicsFEM.h"
+#include "VerticalDynamicsFEM.h"
+
+#include <cstdio>
+#include <cstdint>
+#include <sstream>
+#include <vector>
+#include <string>
+
+///////////////////////////////////////////////////////////////////////////////
+
+static FILE * g_fp = NULL;
+
+static void WriteRecord(
+	const std::string & strName,
+	int iType, // 0 = double, 1 = int32
+	const std::vector<uint64_t> & vecDims,
+	const void * pData
+) {
+	uint32_t nName = strName.size();
+	uint32_t nType = iType;
+	uint32_t nDim = vecDims.size();
+	fwrite(&nName, 4, 1, g_fp);
+	fwrite(strName.c_str(), 1, nName, g_fp);
+	fwrite(&nType, 4, 1, g_fp);
+	fwrite(&nDim, 4, 1, g_fp);
+	uint64_t nTotal = 1;
+	for (size_t d = 0; d < vecDims.size(); d++) {
+		fwrite(&(vecDims[d]), 8, 1, g_fp);
+		nTotal *= vecDims[d];
+	}
+	fwrite(pData, (iType == 0) ? 8 : 4, nTotal, g_fp);
+}
+
+static void WriteScalarD(const std::string & strName, double d) {
+	std::vector<uint64_t> dims(1, 1);
+	WriteRecord(strName, 0, dims, &d);
+}
+
+static void WriteScalarI(const std::string & strName, int i) {
+	std::vector<uint64_t> dims(1, 1);
+	WriteRecord(strName, 1, dims, &i);
+}
+
+static void Write1D(const std::string & strName, const DataArray1D<double> & a) {
+	std::vector<uint64_t> dims(1, a.GetRows());
+	WriteRecord(strName, 0, dims, &(a[0]));
+}
+
+static void Write1I(const std::string & strName, const DataArray1D<int> & a) {
+	std::vector<uint64_t> dims(1, a.GetRows());
+	WriteRecord(strName, 1, dims, &(a[0]));
+}
+
+static void Write2D(const std::string & strName, const DataArray2D<double> & a) {
+	std::vector<uint64_t> dims(2);
+	dims[0] = a.GetRows(); dims[1] = a.GetColumns();
+	if (dims[0] * dims[1] == 0) return;
+	WriteRecord(strName, 0, dims, &(a[0][0]));
+}
+
+static void Write3D(const std::string & strName, const DataArray3D<double> & a) {
+	std::vector<uint64_t> dims(3);
+	dims[0] = a.GetSize(0); dims[1] = a.GetSize(1); dims[2] = a.GetSize(2);
+	if (dims[0] * dims[1] * dims[2] == 0) return;
+	WriteRecord(strName, 0, dims, &(a[0][0][0]));
+}
+
+static void Write4D(const std::string & strName, const DataArray4D<double> & a) {
+	std::vector<uint64_t> dims(4);
+	dims[0] = a.GetSize(0); dims[1] = a.GetSize(1);
+	dims[2] = a.GetSize(2); dims[3] = a.GetSize(3);
+	if (dims[0] * dims[1] * dims[2] * dims[3] == 0) return;
+	WriteRecord(strName, 0, dims, &(a[0][0][0][0]));
+}
+
+static void WriteOp(const std::string & strName, const LinearColumnOperator & op) {
+	if (op.GetCoeffs().GetRows() == 0) return;
+	Write2D(strName + ".coeff", op.GetCoeffs());
+	Write1I(strName + ".begin", op.GetIxBegin());
+	Write1I(strName + ".end", op.GetIxEnd());
+}
+
+static std::string P(int n, const char * sz) {
+	char buf[64];
+	snprintf(buf, 64, "patch%d.", n);
+	return std::string(buf) + sz;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+static void DumpGeometry(Model & model) {
+	GridGLL * pGrid = dynamic_cast<GridGLL*>(model.GetGrid());
+	const PhysicalConstants & phys = model.GetPhysicalConstants();
+	const EquationSet & eqn = model.GetEquationSet();
+
+	WriteScalarI("grid.npatch", pGrid->GetActivePatchCount());
+	WriteScalarI("grid.np", pGrid->GetHorizontalOrder());
+	WriteScalarI("grid.vertorder", pGrid->GetVerticalOrder());
+	WriteScalarI("grid.nlev", pGrid->GetRElements());
+	WriteScalarI("grid.ncomp", eqn.GetComponents());
+	WriteScalarI("grid.ntracers", eqn.GetTracers());
+	WriteScalarI("grid.eqntype", (int)eqn.GetType());
+	WriteScalarI("grid.ninstances", model.GetComponentDataInstances());
+	WriteScalarI("grid.ntracerinstances", model.GetTracerDataInstances());
+	WriteScalarI("grid.xz", pGrid->GetIsCartesianXZ() ? 1 : 0);
+	WriteScalarI("grid.iscartesian",
+		(dynamic_cast<GridCartesianGLL*>(pGrid) != NULL) ? 1 : 0);
+	WriteScalarD("grid.ztop", pGrid->GetZtop());
+	WriteScalarD("grid.reflength", pGrid->GetReferenceLength());
+	{
+		DataArray1D<int> loc(eqn.GetComponents());
+		for (int c = 0; c < eqn.GetComponents(); c++) {
+			loc[c] = (pGrid->GetVarLocation(c) == DataLocation_REdge) ? 1 : 0;
+		}
+		Write1I("grid.varloc", loc);
+	}
+	Write1D("grid.retalevels", pGrid->GetREtaLevels());
+	Write1D("grid.retainterfaces", pGrid->GetREtaInterfaces());
+
+	WriteScalarD("phys.g", phys.GetG());
+	WriteScalarD("phys.R", phys.GetR());
+	WriteScalarD("phys.cp", phys.GetCp());
+	WriteScalarD("phys.cv", phys.GetCv());
+	WriteScalarD("phys.p0", phys.GetP0());
+	WriteScalarD("phys.omega", phys.GetOmega());
+	WriteScalarD("phys.radius", phys.GetEarthRadius());
+
+	Write2D("table.dxbasis1d", pGrid->GetDxBasis1D());
+	Write2D("table.stiffness1d", pGrid->GetStiffness1D());
+	Write1D("table.gllweights1d", pGrid->GetGLLWeights1D());
+
+	WriteOp("op.interp_n2e", pGrid->GetOpInterpNodeToREdge());
+	WriteOp("op.interp_e2n", pGrid->GetOpInterpREdgeToNode());
+	WriteOp("op.diff_n2n", pGrid->GetOpDiffNodeToNode());
+	WriteOp("op.diff_n2e", pGrid->GetOpDiffNodeToREdge());
+	WriteOp("op.diff_e2n", pGrid->GetOpDiffREdgeToNode());
+	WriteOp("op.diff_e2e", pGrid->GetOpDiffREdgeToREdge());
+	WriteOp("op.diffdiff_n2n", pGrid->GetOpDiffDiffNodeToNode());
+	WriteOp("op.diffdiff_e2e", pGrid->GetOpDiffDiffREdgeToREdge());
+	WriteOp("op.penalty_left", pGrid->GetOpPenaltyNodeToNode().GetLeftOp());
+	WriteOp("op.penalty_right", pGrid->GetOpPenaltyNodeToNode().GetRightOp());
+
+	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+		GridPatchGLL * pPatch =
+			dynamic_cast<GridPatchGLL*>(pGrid->GetActivePatch(n));
+		const PatchBox & box = pPatch->GetPatchBox();
+
+		WriteScalarI(P(n, "index"), pPatch->GetPatchIndex());
+		WriteScalarI(P(n, "panel"), box.GetPanel());
+		WriteScalarI(P(n, "halo"), box.GetHaloElements());
+		WriteScalarI(P(n, "nelem_a"), pPatch->GetElementCountA());
+		WriteScalarI(P(n, "nelem_b"), pPatch->GetElementCountB());
+		WriteScalarI(P(n, "a_global_begin"), box.GetAGlobalInteriorBegin());
+		WriteScalarI(P(n, "b_global_begin"), box.GetBGlobalInteriorBegin());
+		WriteScalarD(P(n, "delta_a"), pPatch->GetElementDeltaA());
+		WriteScalarD(P(n, "delta_b"), pPatch->GetElementDeltaB());
+		{
+			DataArray1D<int> nb(8);
+			for (int d = 0; d < 8; d++) {
+				nb[d] = pPatch->GetNeighborPanel((Direction)d);
+			}
+			Write1I(P(n, "neighbor_panels"), nb);
+		}
+		Write1D(P(n, "anode"), pPatch->GetANodes());
+		Write1D(P(n, "bnode"), pPatch->GetBNodes());
+		Write2D(P(n, "lon"), pPatch->GetLongitude());
+		Write2D(P(n, "lat"), pPatch->GetLatitude());
+		Write2D(P(n, "jacobian2d"), pPatch->GetJacobian2D());
+		Write3D(P(n, "contrametric2da"), pPatch->GetContraMetric2DA());
+		Write3D(P(n, "contrametric2db"), pPatch->GetContraMetric2DB());
+		Write2D(P(n, "coriolis"), pPatch->GetCoriolisF());
+		Write2D(P(n, "topography"), pPatch->GetTopography());
+		Write3D(P(n, "jacobian"), pPatch->GetJacobian());
+		Write3D(P(n, "jacobianredge"), pPatch->GetJacobianREdge());
+		Write4D(P(n, "contrametrica"), pPatch->GetContraMetricA());
+		Write4D(P(n, "contrametricb"), pPatch->GetContraMetricB());
+		Write4D(P(n, "contrametricxi"), pPatch->GetContraMetricXi());
+		Write4D(P(n, "contrametricaredge"), pPatch->GetContraMetricAREdge());
+		Write4D(P(n, "contrametricbredge"), pPatch->GetContraMetricBREdge());
+		Write4D(P(n, "contrametricxiredge"), pPatch->GetContraMetricXiREdge());
+		Write4D(P(n, "derivrnode"), pPatch->GetDerivRNode());
+		Write4D(P(n, "derivrredge"), pPatch->GetDerivRREdge());
+		Write3D(P(n, "elementareanode"), pPatch->GetElementAreaNode());
+		Write3D(P(n, "elementarearedge"), pPatch->GetElementAreaREdge());
+		Write3D(P(n, "zlevels"), pPatch->GetZLevels());
+		Write3D(P(n, "zinterfaces"), pPatch->GetZInterfaces());
+		Write3D(P(n, "rayleighnode"), pPatch->GetRayleighStrength(DataLocation_Node));
+		Write3D(P(n, "rayleighredge"), pPatch->GetRayleighStrength(DataLocation_REdge));
+		Write4D(P(n, "refstatenode"), pPatch->GetReferenceState(DataLocation_Node));
+		Write4D(P(n, "refstateredge"), pPatch->GetReferenceState(DataLocation_REdge));
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+static void DumpState(Model & model, const std::string & strTag) {
+	Grid * pGrid = model.GetGrid();
+	const EquationSet & eqn = model.GetEquationSet();
+	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+		GridPatch * pPatch = pGrid->GetActivePatch(n);
+		for (int m = 0; m < model.GetComponentDataInstances(); m++) {
+			char buf[128];
+			snprintf(buf, 128, "%s.patch%d.inst%d.", strTag.c_str(), n, m);
+			Write4D(std::string(buf) + "node",
+				pPatch->GetDataState(m, DataLocation_Node));
+			Write4D(std::string(buf) + "redge",
+				pPatch->GetDataState(m, DataLocation_REdge));
+		}
+		if (eqn.GetTracers() != 0) {
+			for (int m = 0; m < model.GetTracerDataInstances(); m++) {
+				char buf[128];
+				snprintf(buf, 128, "%s.patch%d.inst%d.", strTag.c_str(), n, m);
+				Write4D(std::string(buf) + "tracers",
+					pPatch->GetDataTracers(m));
+			}
+		}
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+static std::vector<std::string> Split(const std::string & s, char c) {
+	std::vector<std::string> out;
+	std::stringstream ss(s);
+	std::string item;
+	while (std::getline(ss, item, c)) {
+		if (item.size() != 0) out.push_back(item);
+	}
+	return out;
+}
+
+static void RunScript(Model & model, const std::string & strScript) {
+	Grid * pGrid = model.GetGrid();
+	const EquationSet & eqn = model.GetEquationSet();
+	HorizontalDynamics * pH = model.GetHorizontalDynamics();
+	VerticalDynamics * pV = model.GetVerticalDynamics();
+	TimestepScheme * pT = model.GetTimestepScheme();
+
+	Time time = model.GetStartTime();
+	bool fFirst = true;
+
+	std::vector<std::string> vecOps = Split(strScript, ';');
+	for (size_t o = 0; o < vecOps.size(); o++) {
+		std::vector<std::string> kv = Split(vecOps[o], ':');
+		const std::string & op = kv[0];
+		std::vector<std::string> a;
+		if (kv.size() > 1) a = Split(kv[1], ',');
+
+		if (op == "dump") {
+			DumpState(model, a[0]);
+		} else if (op == "hexp") {
+			pH->StepExplicit(atoi(a[0].c_str()), atoi(a[1].c_str()), time, atof(a[2].c_str()));
+		} else if (op == "vexp") {
+			pV->StepExplicit(atoi(a[0].c_str()), atoi(a[1].c_str()), time, atof(a[2].c_str()));
+		} else if (op == "vimp") {
+			pV->StepImplicit(atoi(a[0].c_str()), atoi(a[1].c_str()), time, atof(a[2].c_str()));
+		} else if (op == "dss") {
+			pGrid->PostProcessSubstage(atoi(a[0].c_str()), DataType_State);
+			pGrid->PostProcessSubstage(atoi(a[0].c_str()), DataType_Tracers);
+		} else if (op == "hasc") {
+			pH->StepAfterSubCycle(
+				atoi(a[0].c_str()), atoi(a[1].c_str()), atoi(a[2].c_str()),
+				time, atof(a[3].c_str()));
+		} else if (op == "copy") {
+			pGrid->CopyData(atoi(a[0].c_str()), atoi(a[1].c_str()), DataType_State);
+			pGrid->CopyData(atoi(a[0].c_str()), atoi(a[1].c_str()), DataType_Tracers);
+		} else if (op == "lincomb") {
+			DataArray1D<double> dCoeff(model.GetComponentDataInstances());
+			for (size_t i = 1; i < a.size(); i++) {
+				dCoeff[i-1] = atof(a[i].c_str());
+			}
+			pGrid->LinearCombineData(dCoeff, atoi(a[0].c_str()), DataType_State);
+			pGrid->LinearCombineData(dCoeff, atoi(a[0].c_str()), DataType_Tracers);
+		} else if (op == "step") {
+			int nSteps = atoi(a[0].c_str());
+			double dDeltaT = model.GetDeltaT().GetSeconds();
+			for (int s = 0; s < nSteps; s++) {
+				pT->Step(fFirst, false, time, dDeltaT);
+				fFirst = false;
+				time += model.GetDeltaT();
+			}
+		} else if (op == "checksum") {
+			DataArray1D<double> dSums;
+			pGrid->Checksum(DataType_State, dSums, 0, ChecksumType_Sum);
+			Write1D(a[0] + ".checksum", dSums);
+		} else {
+			_EXCEPTION1("ref_dump: unknown op \"%s\"", op.c_str());
+		}
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+int main(int argc, char ** argv) {
+
+	TempestInitialize(&argc, &argv);
+
+try {
+	std::string strCase;
+	std::string strOut;
+	std::string strScript;
+	int nPatch;
+	double dZtop;
+	std::string strPert;
+	double dU0, dH0, dAlpha;
+
+	BeginTempestCommandLine("RefDump");
+		SetDefaultResolution(4);
+		SetDefaultLevels(1);
+		SetDefaultOutputDeltaT("200s");
+		SetDefaultDeltaT("200s");
+		SetDefaultEndTime("0s");
+		SetDefaultHorizontalOrder(4);
+		SetDefaultVerticalOrder(1);
+
+		CommandLineString(strCase, "case", "sw2");
+		CommandLineString(strOut, "out", "ref_dump.bin");
+		CommandLineString(strScript, "script", "dump:ic");
+		CommandLineInt(nPatch, "npatch", 6);
+		CommandLineDouble(dZtop, "ztop", 30000.0);
+		CommandLineString(strPert, "pert", "Exp");
+		CommandLineDouble(dU0, "u0", 38.61068277);
+		CommandLineDouble(dH0, "h0", 2998.104995);
+		CommandLineDouble(dAlpha, "alpha", 0.0);
+
+		ParseCommandLine(argc, argv);
+	EndTempestCommandLine(argv)
+
+	g_fp = fopen(strOut.c_str(), "wb");
+	if (g_fp == NULL) {
+		_EXCEPTION1("Cannot open \"%s\"", strOut.c_str());
+	}
+	fwrite("TB2DUMP1", 1, 8, g_fp);
+
+	Model * pModel;
+	TestCase * pTest;
+
+	if (strCase == "sw2") {
+		pModel = new Model(EquationSet::ShallowWaterEquations);
+		pTest = new ShallowWaterTestCase2(dH0, dU0, dAlpha);
+	} else if (strCase == "jw") {
+		pModel = new Model(EquationSet::PrimitiveNonhydrostaticEquations);
+		STLStringHelper::ToLower(strPert);
+		pTest = new BaroclinicWaveJWTest(
+			dAlpha, dZtop,
+			(strPert == "exp") ?
+				BaroclinicWaveJWTest::PerturbationType_Exp :
+				BaroclinicWaveJWTest::PerturbationType_None);
+	} else if (strCase == "bubble") {
+		pModel = new Model(EquationSet::PrimitiveNonhydrostaticEquations);
+		pTest = new ThermalBubbleCartesianTest(
+			300.0, 0.5, 250.0, 500.0, 350.0, 3.14159265);
+	} else {
+		_EXCEPTIONT("--case must be sw2, jw or bubble");
+	}
+	Model & model = (*pModel);
+
+	if (strCase == "bubble") {
+		ThermalBubbleCartesianTest * pBubble =
+			dynamic_cast<ThermalBubbleCartesianTest*>(pTest);
+		TempestSetupCartesianModel(
+			model, pBubble->m_dGDim, 0.0, pBubble->m_iLatBC, true);
+		const double XL = std::abs(pBubble->m_dGDim[1] - pBubble->m_dGDim[0]);
+		model.GetGrid()->SetReferenceLength((XL < 110000.0) ? XL : 110000.0);
+
+	} else {
+		// Same sequence as _TempestSetupCubedSphereModel
+		// (TempestInitialize.h:476-586) with an explicit patch count.
+		model.SetDeltaT(_tempestvars.timeDeltaT);
+		model.SetEndTime(_tempestvars.timeEndTime);
+		_TempestSetupMethodOfLines(model, _tempestvars);
+
+		GridCSGLL * pGrid = new GridCSGLL(model);
+		pGrid->DefineParameters();
+		pGrid->SetParameters(
+			_tempestvars.nLevels,
+			nPatch,
+			_tempestvars.nResolutionX,
+			4,
+			_tempestvars.nHorizontalOrder,
+			_tempestvars.nVerticalOrder,
+			Grid::VerticalDiscretization_FiniteElement,
+			Grid::VerticalStaggering_Lorenz);
+		pGrid->InitializeDataLocal();
+		model.SetGrid(pGrid, nPatch);
+		_TempestSetupOutputManagers(model, _tempestvars);
+	}
+
+	model.SetTestCase(pTest);
+
+	// With end time == start time Model::Go runs exactly its head
+	// (Model.cpp:347-366: EvaluateGeometricTerms, ApplyBoundaryConditions,
+	// Initialize of scheme / horizontal / vertical dynamics) and returns
+	// before the first output and the step loop.
+	model.Go();
+
+	WriteScalarD("run.dt", model.GetDeltaT().GetSeconds());
+	WriteScalarI("run.hypervisorder", _tempestvars.nHyperviscosityOrder);
+	WriteScalarI("run.nohypervis", _tempestvars.fNoHyperviscosity ? 1 : 0);
+	WriteScalarD("run.nu_scalar", _tempestvars.dNuScalar);
+	WriteScalarD("run.nu_div", _tempestvars.dNuDiv);
+	WriteScalarD("run.nu_vort", _tempestvars.dNuVort);
+
+	DumpGeometry(model);
+	RunScript(model, strScript);
+
+	fclose(g_fp);
+	delete pModel;
+
+} catch(Exception & e) {
+	std::cout << e.ToString() << std::endl;
+	return 1;
+}
+	TempestDeinitialize();
+	return 0;
+}
