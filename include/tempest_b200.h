@@ -1,0 +1,275 @@
+/*
+ * tempest_b200.h - C ABI of the B200-native Tempest dynamical-core hot path.
+ *
+ * The library (libtempest_b200.so, hand-written FP64 CUDA for sm_100a) is the
+ * drop-in for the reference's per-timestep path between Model.cpp:420
+ * (m_pTimestepScheme->Step) and its return.  Every entry point below cites the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *  - every function returns 0 on success, non-zero on failure;
+ *    tb200_last_error() returns the message (the C++ shells turn it into the
+ *    reference's Exception, src/base/Exception.h:25-49);
+ *  - one caller thread per context (the reference is single threaded per rank);
+ *  - HOST arrays use the reference layout: state [c][iA][iB][k], k fastest,
+ *    with the one-node halo (src/base/DataArray4D.h:507-530,
+ *    src/atm/GridPatch.cpp:341-357); the device layout is private.
+ *  - "instance" is the reference's state-instance index
+ *    (TimestepScheme::GetComponentDataInstances, TimestepScheme.h:55-63).
+ */
+#ifndef TEMPEST_B200_H
+#define TEMPEST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb200_ctx tb200_ctx;
+
+#define TB200_MAX_COMPONENTS 8
+
+/* EquationSet::Type (src/atm/EquationSet.h) */
+#define TB200_EQN_SHALLOW_WATER 1
+#define TB200_EQN_PRIMITIVE_NONHYDRO 2
+
+/* DataType selector (src/atm/DataType.h): bit mask */
+#define TB200_DATA_STATE 1
+#define TB200_DATA_TRACERS 2
+
+/* Vertical column operators of GridGLL (src/atm/GridGLL.h:357-448) */
+enum tb200_column_op {
+	TB200_OP_INTERP_N2E = 0,   /* m_opInterpNodeToREdge  */
+	TB200_OP_INTERP_E2N = 1,   /* m_opInterpREdgeToNode  */
+	TB200_OP_DIFF_N2N = 2,     /* m_opDiffNodeToNode     */
+	TB200_OP_DIFF_N2E = 3,     /* m_opDiffNodeToREdge    */
+	TB200_OP_DIFF_E2N = 4,     /* m_opDiffREdgeToNode    */
+	TB200_OP_DIFF_E2E = 5,     /* m_opDiffREdgeToREdge   */
+	TB200_OP_DIFFDIFF_N2N = 6, /* m_opDiffDiffNodeToNode */
+	TB200_OP_DIFFDIFF_E2E = 7, /* m_opDiffDiffREdgeToREdge */
+	TB200_OP_PENALTY_LEFT = 8, /* m_opPenaltyNodeToNode.GetLeftOp()  */
+	TB200_OP_PENALTY_RIGHT = 9,/* m_opPenaltyNodeToNode.GetRightOp() */
+	TB200_OP_COUNT = 10
+};
+
+/* Time schemes (src/atm/TimestepScheme*.cpp) */
+enum tb200_scheme {
+	TB200_SCHEME_STRANG_KGU35 = 0, /* TimestepSchemeStrang (default)   */
+	TB200_SCHEME_ARS343 = 1,       /* TimestepSchemeARS343             */
+	TB200_SCHEME_ARS232 = 2,       /* TimestepSchemeARS232             */
+	TB200_SCHEME_ARS222 = 3,       /* TimestepSchemeARS222             */
+	TB200_SCHEME_ARS443 = 4,       /* TimestepSchemeARS443             */
+	TB200_SCHEME_STRANG_RK4 = 5,
+	TB200_SCHEME_STRANG_SSP3 = 6,
+	TB200_SCHEME_STRANG_FE = 7
+};
+
+/*
+ * Static configuration: what Model, EquationSet, GridGLL, PhysicalConstants
+ * and the HorizontalDynamicsFEM / VerticalDynamicsFEM constructors hold
+ * (src/atm/TempestInitialize.h:112-144,185-409; PhysicalConstants.h).
+ */
+typedef struct {
+	int np;              /* GridGLL::GetHorizontalOrder (nodes per element edge) */
+	int nlev;            /* Grid::GetRElements                                   */
+	int vertical_order;  /* GridGLL::GetVerticalOrder                            */
+	int ncomp;           /* EquationSet::GetComponents (3 SW, 5 nonhydro)        */
+	int ntracers;        /* EquationSet::GetTracers                              */
+	int ninstances;      /* Model::GetComponentDataInstances                     */
+	int eqn_type;        /* TB200_EQN_*                                          */
+	int cartesian_xz;    /* GridGLL::GetIsCartesianXZ                            */
+	int comp_on_redge[TB200_MAX_COMPONENTS]; /* Grid::GetVarLocation == REdge   */
+	int device;          /* CUDA device ordinal (-1: current device)             */
+	/* PhysicalConstants */
+	double g, R, cp, cv, p0, omega, earth_radius;
+	double ztop;             /* Grid::GetZtop             */
+	double ref_length;       /* Grid::GetReferenceLength  */
+	/* HorizontalDynamicsFEM ctor (HorizontalDynamicsFEM.cpp:44-73) */
+	int hypervis_order;      /* 0 (--nohypervis), 2 or 4 */
+	double nu_scalar, nu_div, nu_vort;
+	/* VerticalDynamicsFEM ctor (VerticalDynamicsFEM.cpp:53-78) */
+	int fully_explicit;      /* --explicitvertical */
+	/* TimestepSchemeStrang off-centering (TimestepSchemeStrang.h:53) */
+	double off_centering;
+} tb200_config;
+
+/* Host pointers to one patch's geometric arrays in the reference layout
+ * (allocated in GridPatch::InitializeDataLocal, GridPatch.cpp:102-285).
+ * W_A x W_B include the halo.  Pointers that a configuration does not need
+ * (all 3-D arrays for shallow water) may be NULL. */
+typedef struct {
+	const double * jacobian2d;         /* [W_A][W_B]         GetJacobian2D         */
+	const double * contrametric2da;    /* [W_A][W_B][2]      GetContraMetric2DA    */
+	const double * contrametric2db;    /* [W_A][W_B][2]      GetContraMetric2DB    */
+	const double * coriolis;           /* [W_A][W_B]         GetCoriolisF          */
+	const double * topography;         /* [W_A][W_B]         GetTopography         */
+	const double * jacobian;           /* [W_A][W_B][L]      GetJacobian           */
+	const double * jacobian_redge;     /* [W_A][W_B][L+1]    GetJacobianREdge      */
+	const double * contrametrica;      /* [W_A][W_B][L][3]   GetContraMetricA      */
+	const double * contrametricb;      /* [W_A][W_B][L][3]   GetContraMetricB      */
+	const double * contrametricxi;     /* [W_A][W_B][L][3]   GetContraMetricXi     */
+	const double * contrametrica_redge;/* [W_A][W_B][L+1][3] GetContraMetricAREdge */
+	const double * contrametricb_redge;/* [W_A][W_B][L+1][3] GetContraMetricBREdge */
+	const double * contrametricxi_redge;/*[W_A][W_B][L+1][3] GetContraMetricXiREdge*/
+	const double * derivr_node;        /* [W_A][W_B][L][3]   GetDerivRNode         */
+	const double * derivr_redge;       /* [W_A][W_B][L+1][3] GetDerivRREdge        */
+} tb200_geometry;
+
+/* ---- lifetime ----------------------------------------------------------- */
+
+/* Replaces the constructors of HorizontalDynamicsFEM / VerticalDynamicsFEM /
+ * TimestepScheme* (TempestInitialize.h:185-409). */
+int tb200_create(const tb200_config * cfg, tb200_ctx ** out);
+int tb200_destroy(tb200_ctx * ctx);
+const char * tb200_last_error(const tb200_ctx * ctx);
+const char * tb200_version(void);
+
+/* Launch all work on this CUDA stream (a cudaStream_t passed as void*). */
+int tb200_set_stream(tb200_ctx * ctx, void * cuda_stream);
+/* Block until all queued work is complete (FunctionTimer groups). */
+int tb200_sync(tb200_ctx * ctx);
+/* tb200_sync + report deferred device-side failures of the column solve
+ * ("Solution failed" / "Inversion failure", VerticalDynamicsFEM.cpp:1461-1481). */
+int tb200_check_errors(tb200_ctx * ctx);
+
+/* ---- grid description (Grid::NewPatch / GridPatchGLL ctor) --------------- */
+
+/* Register one patch of the global grid (GridPatch.h:331 index, PatchBox.h:74
+ * panel, GridPatchGLL.h:94 element spacing) and the rank that owns it
+ * (Grid::DistributePatches, Grid.cpp:1038-1062).  EVERY patch of the grid is
+ * registered on every rank; only patches with owner_rank == this rank hold
+ * data.  Patches must be added before tb200_commit_layout.  halo is
+ * PatchBox::GetHaloElements (1) and only describes the HOST arrays. */
+int tb200_add_patch(tb200_ctx * ctx, int patch_index, int panel,
+                    int nelem_a, int nelem_b, int halo,
+                    double delta_a, double delta_b, int owner_rank);
+/* Allocate device storage for every state instance and the geometry. */
+int tb200_commit_layout(tb200_ctx * ctx);
+
+/* GridGLL::GetDxBasis1D / GetStiffness1D / GetGLLWeights1D
+ * (GridGLL.cpp:101-180); [np][np], [np][np], [np]. */
+int tb200_set_tables(tb200_ctx * ctx, const double * dx_basis,
+                     const double * stiffness, const double * gll_weights);
+/* LinearColumnOperator coefficient table + per-row band
+ * (LinearColumnOperator.h:62-236): coeff[nout][nin], begin[nout], end[nout]. */
+int tb200_set_column_op(tb200_ctx * ctx, int op, int nout, int nin,
+                        const double * coeff, const int * begin, const int * end);
+/* Upload one patch's metric terms (GridPatchCSGLL::EvaluateGeometricTerms,
+ * GridPatchCSGLL.cpp:295-574 / GridPatchCartesianGLL.cpp:197-460 outputs). */
+int tb200_upload_geometry(tb200_ctx * ctx, int patch_index, const tb200_geometry * g);
+
+/*
+ * Connectivity.  The reference finds coincident nodes through its exchange
+ * buffer topology (Grid.cpp:1066-1573, Connectivity.cpp:47-744); here the host
+ * names them: node_ids[W_Aint][W_Bint] (interior nodes only, no halo) gives
+ * every element-local node a global id, equal ids are one physical node.
+ * Direct stiffness summation averages over equal ids
+ * (GridCSGLL::ApplyDSS, GridCSGLL.cpp:435-781).
+ */
+int tb200_set_node_ids(tb200_ctx * ctx, int patch_index, const int64_t * node_ids);
+/* (ids are supplied for every patch of the grid, local or not, so that each
+ * rank can derive the same send/receive slot order without communication) */
+/* Nodes on a panel seam: covector re-basing of (u_alpha,u_beta) from a source
+ * panel to this node's panel (CubedSphereTrans::CoVecPanelTrans,
+ * CubedSphereTrans.h:1751-2275; GridPatchCSGLL::TransformHaloVelocities,
+ * GridPatchCSGLL.cpp:1783-1924).  For n seam nodes: ia[n], ib[n] (interior
+ * indices), src_panel[n], m[n][4] row-major 2x2 so that
+ * (ua,ub)_this = M (ua,ub)_src. */
+int tb200_set_seam_transforms(tb200_ctx * ctx, int patch_index, int n,
+                              const int * ia, const int * ib,
+                              const int * src_panel, const double * m);
+/* Build the device-side averaging groups from the ids above. */
+int tb200_build_connectivity(tb200_ctx * ctx);
+
+/* ---- state movement (DataContainer / DataArray4D seam) -------- */
+
+/* Host (reference layout, halo included) -> device instance.  node/redge are
+ * GridPatch::GetDataState(inst, DataLocation_Node / _REdge), tracers is
+ * GetDataTracers(inst); NULL skips.  Only the components located at the array
+ * (Grid.cpp:281-287) are transferred. */
+int tb200_upload_state(tb200_ctx * ctx, int patch_index, int inst,
+                       const double * node, const double * redge,
+                       const double * tracers);
+/* Device instance -> host; also fills the derived slots the reference keeps
+ * (W on nodes, U,V on interfaces: HorizontalDynamicsFEM.cpp:817-831) when
+ * fill_derived != 0.  Halo entries are left untouched. */
+int tb200_download_state(tb200_ctx * ctx, int patch_index, int inst,
+                         double * node, double * redge, double * tracers,
+                         int fill_derived);
+
+/* ---- Grid::CopyData / LinearCombineData / ZeroData (Grid.cpp:1585-1632,
+ *      GridPatch.cpp:1402-1553) ------------------------------------------- */
+int tb200_copy(tb200_ctx * ctx, int src, int dst, int data_mask);
+int tb200_lincomb(tb200_ctx * ctx, const double * coeff, int ncoeff, int dst,
+                  int data_mask);
+int tb200_zero(tb200_ctx * ctx, int inst, int data_mask);
+
+/* ---- dynamics plugins ---------------------------------------------------- */
+
+/* HorizontalDynamicsFEM::StepExplicit (HorizontalDynamicsFEM.cpp:1787-1863):
+ * StepShallowWater (:321-647) or StepNonhydrostaticPrimitive (:701-1783). */
+int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt);
+/* VerticalDynamicsFEM::StepExplicit (VerticalDynamicsFEM.cpp:616-1159). */
+int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt);
+/* Both of the above in one pass over the state (same results). */
+int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double dt);
+/* VerticalDynamicsFEM::StepImplicit (VerticalDynamicsFEM.cpp:1230-1638). */
+int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt);
+/* GridGLL::PostProcessSubstage -> ApplyDSS (GridGLL.cpp:571-583,
+ * GridCSGLL.cpp:435-781, GridCartesianGLL.cpp:508-654). */
+int tb200_dss(tb200_ctx * ctx, int inst, int data_mask);
+/* HorizontalDynamicsFEM::StepAfterSubCycle (HorizontalDynamicsFEM.cpp:2637-2726):
+ * scalar + vector hyperdiffusion, DSS, Rayleigh friction. */
+int tb200_h_step_after_subcycle(tb200_ctx * ctx, int in, int out, int work, double dt);
+/* VerticalDynamics::FilterNegativeTracers + HorizontalDynamicsFEM one
+ * (VerticalDynamicsFEM.cpp:4286-4347, HorizontalDynamicsFEM.cpp:213-317). */
+int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst);
+
+/* TimestepScheme::Step (TimestepSchemeStrang.cpp:450-674,
+ * TimestepSchemeARS343.cpp:146-235, ...): one full time step on the device. */
+int tb200_scheme_instances(int scheme);
+int tb200_step(tb200_ctx * ctx, int scheme, int first_step, int last_step, double dt);
+
+/* ---- diagnostics (Grid::Checksum, GridPatch.cpp:744-835) ----------------- */
+/* Area-weighted sum of every component of an instance over the local patches;
+ * sums[ncomp].  element_area_* in the reference layout are supplied once. */
+int tb200_upload_element_area(tb200_ctx * ctx, int patch_index,
+                              const double * area_node, const double * area_redge);
+int tb200_checksum(tb200_ctx * ctx, int inst, double * sums);
+
+/* ---- multi-GPU halo traffic (Grid::Exchange, Grid.cpp:627-685) ----------- */
+/* Patches are partitioned over ranks (one process per GPU).  Per exchange the
+ * library packs the local nodes that other ranks share into a device send
+ * buffer ordered [destination rank][slot][row], calls the callback - which
+ * must move send_counts[r] doubles to rank r and receive recv_counts[r]
+ * doubles from rank r into recvbuf (same ordering), enqueued on the stream of
+ * tb200_set_stream, e.g. one NCCL all-to-all - and then averages.
+ * Must be called before tb200_add_patch. */
+typedef int (*tb200_exchange_fn)(void * user, double * sendbuf, double * recvbuf,
+                                 const int64_t * send_counts,
+                                 const int64_t * recv_counts, int nranks);
+int tb200_set_exchange(tb200_ctx * ctx, int rank, int nranks,
+                       tb200_exchange_fn fn, void * user);
+/* Nodes sent to / received from each rank per exchange (after
+ * tb200_build_connectivity); arrays of nranks entries. */
+int tb200_exchange_counts(tb200_ctx * ctx, int64_t * send_nodes, int64_t * recv_nodes);
+
+/* ---- introspection for tests and the bench -------------------------------- */
+/* Number of kernels this context has launched since creation. */
+int64_t tb200_launch_count(const tb200_ctx * ctx);
+/* Total columns (element-local nodes incl. duplicates) held by this context. */
+int64_t tb200_column_count(const tb200_ctx * ctx);
+/* Direct banded solve used by the implicit step, exposed for pinning against
+ * LAPACK dgbsv (src/base/LinearAlgebra.cpp:156-202): ncols independent systems,
+ * ab[ncols][n][ldab] in the reference's row-major band storage, b[ncols][n]
+ * overwritten with the solution.  Runs on the device. */
+int tb200_test_band_solve(tb200_ctx * ctx, int ncols, int n, int kl, int ku,
+                          const double * ab, double * b);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,1264 @@
+// C ABI of libtempest_b200 (see include/tempest_b200.h).
+//
+// Host-side plumbing only: context, layout, uploads, connectivity, dispatch.
+// All arithmetic on model data happens in the kernels of tb200_kernels.cuh,
+// tb200_dss.cuh and tb200_column.cuh; there is no CPU fallback.
+
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <unordered_map>
+
+#include "tb200_ctx.h"
+#include "tb200_kernels.cuh"
+#include "tb200_dss.cuh"
+#include "tb200_column.cuh"
+
+#define TB_CHECK(ctx, call) \
+	do { \
+		cudaError_t e__ = (call); \
+		if (e__ != cudaSuccess) { \
+			(ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__); \
+			return 1; \
+		} \
+	} while (0)
+
+#define TB_FAIL(ctx, msg) \
+	do { (ctx)->err = (msg); return 1; } while (0)
+
+#define TB_KERNEL_CHECK(ctx) \
+	do { \
+		(ctx)->launches++; \
+		cudaError_t e__ = cudaGetLastError(); \
+		if (e__ != cudaSuccess) { \
+			(ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__); \
+			return 1; \
+		} \
+	} while (0)
+
+static const int kItems = 8;   // (element, level) pairs per block in the slab kernels
+
+template <typename T>
+static int dalloc(tb200_ctx * ctx, T ** p, size_t count) {
+	void * q = 0;
+	cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+	if (e != cudaSuccess) {
+		ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+		return 1;
+	}
+	ctx->allocs.push_back(q);
+	*p = (T *)q;
+	return 0;
+}
+
+template <typename T>
+static int dupload(tb200_ctx * ctx, T ** p, const std::vector<T> & v) {
+	if (dalloc(ctx, p, v.size())) return 1;
+	if (v.size() != 0) {
+		TB_CHECK(ctx, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+	}
+	return 0;
+}
+
+static PatchInfo * find_patch(tb200_ctx * ctx, int patch_index) {
+	std::map<int, int>::iterator it = ctx->patch_pos.find(patch_index);
+	if (it == ctx->patch_pos.end()) return 0;
+	return &ctx->patches[it->second];
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+extern "C" const char * tb200_version(void) {
+#ifdef TB200_EMU
+	return "tempest-b200 0.1 (host emulation build - tests only)";
+#else
+	return "tempest-b200 0.1 (CUDA sm_100a)";
+#endif
+}
+
+extern "C" const char * tb200_last_error(const tb200_ctx * ctx) {
+	return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int tb200_create(const tb200_config * cfg, tb200_ctx ** out) {
+	if (cfg == 0 || out == 0) return 1;
+	tb200_ctx * ctx = new tb200_ctx();
+	*out = ctx;
+	ctx->cfg = *cfg;
+	if (cfg->np != 4) {
+		TB_FAIL(ctx, "only np = 4 kernels are instantiated in this build");
+	}
+	if (cfg->nlev < 1 || cfg->ncomp < 1 || cfg->ncomp > TB_MAXC) {
+		TB_FAIL(ctx, "invalid nlev / ncomp");
+	}
+	if (cfg->ninstances < 1 || cfg->ninstances > TB_MAXINST) {
+		TB_FAIL(ctx, "invalid ninstances");
+	}
+	if (cfg->eqn_type == TB200_EQN_SHALLOW_WATER) {
+		if (cfg->ncomp != 3) TB_FAIL(ctx, "shallow water needs 3 components");
+	} else if (cfg->eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
+		if (cfg->ncomp != 5) TB_FAIL(ctx, "nonhydrostatic needs 5 components");
+		// Lorenz staggering only (reference default --vstagger LOR)
+		const int want[5] = {0, 0, 0, 1, 0};
+		for (int c = 0; c < 5; c++) {
+			if ((cfg->comp_on_redge[c] != 0) != (want[c] != 0)) {
+				TB_FAIL(ctx, "only Lorenz staggering (W on interfaces) is supported");
+			}
+		}
+	} else {
+		TB_FAIL(ctx, "unsupported equation set");
+	}
+#ifndef TB200_EMU
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		TB_FAIL(ctx, "no CUDA device: libtempest_b200 has no CPU fallback");
+	}
+#endif
+	if (cfg->device >= 0) {
+		TB_CHECK(ctx, cudaSetDevice(cfg->device));
+	}
+
+	DevLayout & lay = ctx->lay;
+	memset(&lay, 0, sizeof(lay));
+	lay.np = cfg->np;
+	lay.nn = cfg->np * cfg->np;
+	lay.nlev = cfg->nlev;
+	lay.ncomp = cfg->ncomp;
+	lay.ntr = cfg->ntracers;
+	int row = 0;
+	for (int c = 0; c < cfg->ncomp; c++) {
+		lay.rowoff[c] = row;
+		lay.onedge[c] = cfg->comp_on_redge[c] ? 1 : 0;
+		lay.rowlev[c] = cfg->nlev + lay.onedge[c];
+		row += lay.rowlev[c];
+	}
+	lay.nrows_state = row;
+	lay.troff = row;
+	lay.nrows = row + cfg->ntracers * cfg->nlev;
+
+	ctx->phys.g = cfg->g;
+	ctx->phys.R = cfg->R;
+	ctx->phys.cp = cfg->cp;
+	ctx->phys.cv = cfg->cv;
+	ctx->phys.p0 = cfg->p0;
+	ctx->phys.exner_c1 = cfg->R / (cfg->cp - cfg->R);
+	ctx->phys.exner_c2 = cfg->R / cfg->p0;
+
+	// m_nJacobianFOffD (VerticalDynamicsFEM.cpp:188-201, FE discretisation)
+	switch (cfg->vertical_order) {
+		case 1: ctx->offd = 4; break;
+		case 2: ctx->offd = 9; break;
+		case 3: ctx->offd = 15; break;
+		case 4: ctx->offd = 22; break;
+		case 5: ctx->offd = 30; break;
+		default: TB_FAIL(ctx, "unsupported vertical order");
+	}
+	memset(&ctx->ops, 0, sizeof(ctx->ops));
+	memset(&ctx->geom, 0, sizeof(ctx->geom));
+	memset(&ctx->tables, 0, sizeof(ctx->tables));
+	return 0;
+}
+
+extern "C" int tb200_destroy(tb200_ctx * ctx) {
+	if (ctx == 0) return 0;
+	cudaDeviceSynchronize();
+	for (size_t i = 0; i < ctx->allocs.size(); i++) {
+		cudaFree(ctx->allocs[i]);
+	}
+	delete ctx;
+	return 0;
+}
+
+extern "C" int tb200_set_stream(tb200_ctx * ctx, void * s) {
+	ctx->stream = (cudaStream_t)s;
+	return 0;
+}
+
+extern "C" int tb200_sync(tb200_ctx * ctx) {
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+extern "C" int64_t tb200_launch_count(const tb200_ctx * ctx) {
+	return ctx->launches;
+}
+
+extern "C" int64_t tb200_column_count(const tb200_ctx * ctx) {
+	return (int64_t)ctx->lay.nelem * ctx->lay.nn;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+extern "C" int tb200_set_exchange(
+	tb200_ctx * ctx, int rank, int nranks, tb200_exchange_fn fn, void * user
+) {
+	if (ctx->patches.size() != 0) {
+		TB_FAIL(ctx, "tb200_set_exchange must precede tb200_add_patch");
+	}
+	if (nranks < 1 || rank < 0 || rank >= nranks) TB_FAIL(ctx, "invalid rank");
+	if (nranks > 1 && fn == 0) TB_FAIL(ctx, "exchange callback required");
+	ctx->rank = rank;
+	ctx->nranks = nranks;
+	ctx->exch_fn = fn;
+	ctx->exch_user = user;
+	return 0;
+}
+
+extern "C" int tb200_add_patch(
+	tb200_ctx * ctx, int patch_index, int panel, int nelem_a, int nelem_b,
+	int halo, double delta_a, double delta_b, int owner_rank
+) {
+	if (ctx->committed) TB_FAIL(ctx, "layout already committed");
+	if (ctx->patch_pos.count(patch_index)) TB_FAIL(ctx, "duplicate patch index");
+	if (owner_rank < 0 || owner_rank >= ctx->nranks) TB_FAIL(ctx, "invalid owner rank");
+	PatchInfo p;
+	p.index = patch_index;
+	p.panel = panel;
+	p.nea = nelem_a;
+	p.neb = nelem_b;
+	p.halo = halo;
+	p.owner = owner_rank;
+	p.da = delta_a;
+	p.db = delta_b;
+	p.elem0 = -1;
+	ctx->patch_pos[patch_index] = (int)ctx->patches.size();
+	ctx->patches.push_back(p);
+	return 0;
+}
+
+extern "C" int tb200_commit_layout(tb200_ctx * ctx) {
+	if (ctx->committed) TB_FAIL(ctx, "layout already committed");
+	DevLayout & lay = ctx->lay;
+	const int np = lay.np, nn = lay.nn, L = lay.nlev;
+
+	long long nelem = 0;
+	size_t stage = 0;
+	for (size_t p = 0; p < ctx->patches.size(); p++) {
+		PatchInfo & pi = ctx->patches[p];
+		if (pi.owner != ctx->rank) continue;
+		pi.elem0 = nelem;
+		nelem += (long long)pi.nea * pi.neb;
+		const size_t wa = pi.nea * np + 2 * pi.halo;
+		const size_t wb = pi.neb * np + 2 * pi.halo;
+		const size_t ncmax = std::max(std::max(lay.ncomp, lay.ntr), 3);
+		stage = std::max(stage, wa * wb * (size_t)(L + 1) * ncmax);
+	}
+	if (nelem == 0) TB_FAIL(ctx, "no local patches");
+	if (nelem * nn >= (1ll << 30)) TB_FAIL(ctx, "too many local nodes for 32-bit node addresses");
+	lay.nelem = nelem;
+
+	const size_t inst_doubles = (size_t)nelem * lay.nrows * nn;
+	ctx->inst.resize(ctx->cfg.ninstances);
+	for (int m = 0; m < ctx->cfg.ninstances; m++) {
+		if (dalloc(ctx, &ctx->inst[m], inst_doubles)) return 1;
+		TB_CHECK(ctx, cudaMemset(ctx->inst[m], 0, inst_doubles * sizeof(double)));
+	}
+	ctx->stage_doubles = stage;
+	if (dalloc(ctx, &ctx->d_stage, stage)) return 1;
+	if (dalloc(ctx, &ctx->d_rowmap, 64)) return 1;
+
+	// per-element spacing and viscosity scaling
+	// (HorizontalDynamicsFEM.cpp:1970-1975: nu * (deltaA / ref)^3.2)
+	std::vector<double> ida(nelem), idb(nelem), nus(nelem);
+	for (size_t p = 0; p < ctx->patches.size(); p++) {
+		const PatchInfo & pi = ctx->patches[p];
+		if (pi.elem0 < 0) continue;
+		for (long long q = 0; q < (long long)pi.nea * pi.neb; q++) {
+			ida[pi.elem0 + q] = 1.0 / pi.da;
+			idb[pi.elem0 + q] = 1.0 / pi.db;
+			nus[pi.elem0 + q] = (ctx->cfg.ref_length != 0.0)
+				? pow(pi.da / ctx->cfg.ref_length, 3.2) : 1.0;
+		}
+	}
+	if (dupload(ctx, &ctx->d_inv_da, ida)) return 1;
+	if (dupload(ctx, &ctx->d_inv_db, idb)) return 1;
+	if (dupload(ctx, &ctx->d_nu_scale, nus)) return 1;
+
+	for (int q = 0; q < 7; q++) {
+		if (dalloc(ctx, &ctx->g2d[q], (size_t)nelem * nn)) return 1;
+		TB_CHECK(ctx, cudaMemset(ctx->g2d[q], 0, (size_t)nelem * nn * sizeof(double)));
+	}
+	const bool need3d = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO);
+	// the level / interface Jacobians are needed by every equation set
+	// (scalar hyperdiffusion, HorizontalDynamicsFEM.cpp:1913-1916)
+	for (int q = 0; q < (need3d ? 13 : 1); q++) {
+		if (dalloc(ctx, &ctx->g3n[q], (size_t)nelem * L * nn)) return 1;
+		if (dalloc(ctx, &ctx->g3e[q], (size_t)nelem * (L + 1) * nn)) return 1;
+	}
+	DevGeom & g = ctx->geom;
+	g.inv_da = ctx->d_inv_da; g.inv_db = ctx->d_inv_db; g.nu_scale = ctx->d_nu_scale;
+	g.j2d = ctx->g2d[0]; g.a0 = ctx->g2d[1]; g.a1 = ctx->g2d[2];
+	g.b0 = ctx->g2d[3]; g.b1 = ctx->g2d[4]; g.f = ctx->g2d[5]; g.zs = ctx->g2d[6];
+	g.jac = ctx->g3n[0];
+	g.jace = ctx->g3e[0];
+	for (int m = 0; m < 3; m++) {
+		g.ca[m] = ctx->g3n[1 + m]; g.cb[m] = ctx->g3n[4 + m];
+		g.cx[m] = ctx->g3n[7 + m]; g.dr[m] = ctx->g3n[10 + m];
+		g.cae[m] = ctx->g3e[1 + m]; g.cbe[m] = ctx->g3e[4 + m];
+		g.cxe[m] = ctx->g3e[7 + m]; g.dre[m] = ctx->g3e[10 + m];
+	}
+	if (dalloc(ctx, &ctx->d_sums, 64)) return 1;
+	if (dalloc(ctx, &ctx->d_info, 4)) return 1;
+	TB_CHECK(ctx, cudaMemset(ctx->d_info, 0, 4 * sizeof(int)));
+
+	// unique columns of the implicit solve and the duplicates that receive
+	// a copy (VerticalDynamicsFEM.cpp:1315-1334, 1544-1633)
+	if (need3d) {
+		std::vector<int> cn, cd;
+		for (size_t p = 0; p < ctx->patches.size(); p++) {
+			const PatchInfo & pi = ctx->patches[p];
+			if (pi.elem0 < 0) continue;
+			for (int a = 0; a < pi.nea; a++)
+			for (int b = 0; b < pi.neb; b++) {
+				const int iEnd = (a == pi.nea - 1) ? np : np - 1;
+				const int jEnd = (b == pi.neb - 1) ? np : np - 1;
+				for (int i = 0; i < iEnd; i++)
+				for (int j = 0; j < jEnd; j++) {
+					const long long e = pi.elem0 + (long long)a * pi.neb + b;
+					cn.push_back((int)(e * nn + i * np + j));
+					int d[3] = {-1, -1, -1};
+					int nd = 0;
+					const bool da_ = (i == 0 && a > 0);
+					const bool db_ = (j == 0 && b > 0);
+					if (da_) {
+						const long long e2 = pi.elem0 + (long long)(a - 1) * pi.neb + b;
+						d[nd++] = (int)(e2 * nn + (np - 1) * np + j);
+					}
+					if (db_) {
+						const long long e2 = pi.elem0 + (long long)a * pi.neb + (b - 1);
+						d[nd++] = (int)(e2 * nn + i * np + (np - 1));
+					}
+					if (da_ && db_) {
+						const long long e2 = pi.elem0 + (long long)(a - 1) * pi.neb + (b - 1);
+						d[nd++] = (int)(e2 * nn + (np - 1) * np + (np - 1));
+					}
+					cd.push_back(d[0]); cd.push_back(d[1]); cd.push_back(d[2]);
+				}
+			}
+		}
+		ctx->ncols = (int)cn.size();
+		if (dupload(ctx, &ctx->d_col_node, cn)) return 1;
+		if (dupload(ctx, &ctx->d_col_dups, cd)) return 1;
+		ctx->ws_cols = std::min(ctx->ncols, 1 << 16);
+		const size_t wsd = (size_t)tb_column_ws_entries(L, ctx->offd) * ctx->ws_cols;
+		if (dalloc(ctx, &ctx->d_ws, wsd)) return 1;
+	}
+	ctx->committed = true;
+	return 0;
+}
+
+extern "C" int tb200_set_tables(
+	tb200_ctx * ctx, const double * dx, const double * st, const double * w
+) {
+	const int np = ctx->lay.np;
+	for (int q = 0; q < np * np; q++) {
+		ctx->tables.dx[q] = dx[q];
+		ctx->tables.st[q] = st[q];
+	}
+	(void)w;
+	return 0;
+}
+
+extern "C" int tb200_set_column_op(
+	tb200_ctx * ctx, int op, int nout, int nin,
+	const double * coeff, const int * begin, const int * end
+) {
+	if (op < 0 || op >= TB_NOPS) TB_FAIL(ctx, "invalid column operator id");
+	HostOp & h = ctx->hops[op];
+	h.nout = nout;
+	h.nin = nin;
+	h.begin.assign(nout, 0);
+	h.end.assign(nout, 0);
+	int width = 1;
+	for (int k = 0; k < nout; k++) {
+		int b = std::max(begin[k], 0);
+		int e = std::min(end[k], nin);
+		if (e < b) e = b;
+		h.begin[k] = b;
+		h.end[k] = e;
+		width = std::max(width, e - b);
+	}
+	h.width = width;
+	h.coeff.assign((size_t)nout * width, 0.0);
+	for (int k = 0; k < nout; k++) {
+		for (int l = h.begin[k]; l < h.end[k]; l++) {
+			h.coeff[(size_t)k * width + (l - h.begin[k])] = coeff[(size_t)k * nin + l];
+		}
+	}
+	if (dupload(ctx, &h.d_coeff, h.coeff)) return 1;
+	if (dupload(ctx, &h.d_begin, h.begin)) return 1;
+	if (dupload(ctx, &h.d_end, h.end)) return 1;
+	DevOp & d = ctx->ops.op[op];
+	d.coeff = h.d_coeff;
+	d.begin = h.d_begin;
+	d.end = h.d_end;
+	d.width = width;
+	d.nout = nout;
+	d.nin = nin;
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+static int upload_geom_array(
+	tb200_ctx * ctx, const PatchInfo & pi, const double * host,
+	int nlev, int nm, double * d0, double * d1, double * d2
+) {
+	if (host == 0) return 0;
+	const int np = ctx->lay.np;
+	const size_t wa = pi.nea * np + 2 * pi.halo;
+	const size_t wb = pi.neb * np + 2 * pi.halo;
+	const size_t count = wa * wb * nlev * nm;
+	if (count > ctx->stage_doubles) TB_FAIL(ctx, "staging buffer too small");
+	TB_CHECK(ctx, cudaMemcpyAsync(ctx->d_stage, host, count * sizeof(double),
+		cudaMemcpyHostToDevice, ctx->stream));
+	GeomDst dst;
+	dst.p[0] = d0; dst.p[1] = d1; dst.p[2] = d2;
+	auto kfn = k_transpose_geom;
+	TB_LAUNCH_FLAT(kfn, dim3(pi.nea * pi.neb), dim3(256), 0, ctx->stream,
+		np, ctx->lay.nn, pi.elem0, pi.nea, pi.neb, pi.halo,
+		(const double *)ctx->d_stage, nlev, nm, dst);
+	TB_KERNEL_CHECK(ctx);
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+extern "C" int tb200_upload_geometry(
+	tb200_ctx * ctx, int patch_index, const tb200_geometry * gh
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	const int L = ctx->lay.nlev;
+	double ** g2 = ctx->g2d;
+	double ** gn = ctx->g3n;
+	double ** ge = ctx->g3e;
+	if (upload_geom_array(ctx, *pi, gh->jacobian2d, 1, 1, g2[0], 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, gh->contrametric2da, 1, 2, g2[1], g2[2], 0)) return 1;
+	if (upload_geom_array(ctx, *pi, gh->contrametric2db, 1, 2, g2[3], g2[4], 0)) return 1;
+	if (upload_geom_array(ctx, *pi, gh->coriolis, 1, 1, g2[5], 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, gh->topography, 1, 1, g2[6], 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, gh->jacobian, L, 1, gn[0], 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, gh->jacobian_redge, L + 1, 1, ge[0], 0, 0)) return 1;
+	if (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
+		if (upload_geom_array(ctx, *pi, gh->contrametrica, L, 3, gn[1], gn[2], gn[3])) return 1;
+		if (upload_geom_array(ctx, *pi, gh->contrametricb, L, 3, gn[4], gn[5], gn[6])) return 1;
+		if (upload_geom_array(ctx, *pi, gh->contrametricxi, L, 3, gn[7], gn[8], gn[9])) return 1;
+		if (upload_geom_array(ctx, *pi, gh->derivr_node, L, 3, gn[10], gn[11], gn[12])) return 1;
+		if (upload_geom_array(ctx, *pi, gh->contrametrica_redge, L + 1, 3, ge[1], ge[2], ge[3])) return 1;
+		if (upload_geom_array(ctx, *pi, gh->contrametricb_redge, L + 1, 3, ge[4], ge[5], ge[6])) return 1;
+		if (upload_geom_array(ctx, *pi, gh->contrametricxi_redge, L + 1, 3, ge[7], ge[8], ge[9])) return 1;
+		if (upload_geom_array(ctx, *pi, gh->derivr_redge, L + 1, 3, ge[10], ge[11], ge[12])) return 1;
+	}
+	return 0;
+}
+
+extern "C" int tb200_upload_element_area(
+	tb200_ctx * ctx, int patch_index, const double * area_node, const double * area_redge
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	const int L = ctx->lay.nlev;
+	const size_t nn = ctx->lay.nn;
+	if (ctx->d_area_node == 0) {
+		if (dalloc(ctx, &ctx->d_area_node, (size_t)ctx->lay.nelem * L * nn)) return 1;
+		if (dalloc(ctx, &ctx->d_area_redge, (size_t)ctx->lay.nelem * (L + 1) * nn)) return 1;
+	}
+	if (upload_geom_array(ctx, *pi, area_node, L, 1, ctx->d_area_node, 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, area_redge, L + 1, 1, ctx->d_area_redge, 0, 0)) return 1;
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// State movement
+
+static int move_state_array(
+	tb200_ctx * ctx, const PatchInfo & pi, int inst, double * host,
+	int ncomp_host, int host_nlev, const std::vector<int> & rowmap, bool to_device
+) {
+	if (host == 0) return 0;
+	const int np = ctx->lay.np, nn = ctx->lay.nn;
+	const size_t wa = pi.nea * np + 2 * pi.halo;
+	const size_t wb = pi.neb * np + 2 * pi.halo;
+	const size_t slice = wa * wb * host_nlev;
+	if (slice * ncomp_host > ctx->stage_doubles) TB_FAIL(ctx, "staging buffer too small");
+	TB_CHECK(ctx, cudaMemcpyAsync(ctx->d_rowmap, rowmap.data(), ncomp_host * sizeof(int),
+		cudaMemcpyHostToDevice, ctx->stream));
+	const size_t smem = (size_t)host_nlev * (nn + 1) * sizeof(double);
+	if (to_device) {
+		for (int c = 0; c < ncomp_host; c++) {
+			if (rowmap[c] < 0) continue;
+			TB_CHECK(ctx, cudaMemcpyAsync(ctx->d_stage + c * slice, host + c * slice,
+				slice * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		}
+		auto kfn = k_transpose_state<true>;
+		TB_LAUNCH(kfn, dim3(pi.nea * pi.neb), dim3(256), smem, ctx->stream,
+			ctx->lay, ctx->inst[inst], ctx->d_stage, pi.elem0, pi.nea, pi.neb, pi.halo,
+			0, ncomp_host, host_nlev, 0, (const int *)ctx->d_rowmap);
+		TB_KERNEL_CHECK(ctx);
+		TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	} else {
+		auto kfn = k_transpose_state<false>;
+		TB_LAUNCH(kfn, dim3(pi.nea * pi.neb), dim3(256), smem, ctx->stream,
+			ctx->lay, ctx->inst[inst], ctx->d_stage, pi.elem0, pi.nea, pi.neb, pi.halo,
+			0, ncomp_host, host_nlev, 0, (const int *)ctx->d_rowmap);
+		TB_KERNEL_CHECK(ctx);
+	}
+	return 0;
+}
+
+// copy the interior of component slices from the staged array back to the host
+static int stage_to_host(
+	tb200_ctx * ctx, const PatchInfo & pi, double * host, int host_nlev,
+	const std::vector<int> & comps
+) {
+	const int np = ctx->lay.np;
+	const size_t wa = pi.nea * np + 2 * pi.halo;
+	const size_t wb = pi.neb * np + 2 * pi.halo;
+	const size_t slice = wa * wb * host_nlev;
+	// rows iA in the interior are contiguous runs of wb*host_nlev doubles;
+	// copy interior rows only so that halo entries on the host are untouched
+	// in alpha; beta halos inside a row are restored from a saved copy.
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	std::vector<double> tmp(slice);
+	for (size_t q = 0; q < comps.size(); q++) {
+		const int c = comps[q];
+		TB_CHECK(ctx, cudaMemcpy(tmp.data(), ctx->d_stage + c * slice,
+			slice * sizeof(double), cudaMemcpyDeviceToHost));
+		for (size_t ia = pi.halo; ia < wa - pi.halo; ia++) {
+			const size_t off = (ia * wb + pi.halo) * host_nlev;
+			memcpy(host + c * slice + off, tmp.data() + off,
+				(wb - 2 * pi.halo) * host_nlev * sizeof(double));
+		}
+	}
+	return 0;
+}
+
+extern "C" int tb200_upload_state(
+	tb200_ctx * ctx, int patch_index, int inst,
+	const double * node, const double * redge, const double * tracers
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid instance");
+	const DevLayout & lay = ctx->lay;
+	std::vector<int> rm(lay.ncomp);
+	for (int c = 0; c < lay.ncomp; c++) rm[c] = lay.onedge[c] ? -1 : lay.rowoff[c];
+	if (move_state_array(ctx, *pi, inst, (double *)node, lay.ncomp, lay.nlev, rm, true)) return 1;
+	bool anyedge = false;
+	for (int c = 0; c < lay.ncomp; c++) {
+		rm[c] = lay.onedge[c] ? lay.rowoff[c] : -1;
+		anyedge = anyedge || lay.onedge[c];
+	}
+	if (anyedge) {
+		if (move_state_array(ctx, *pi, inst, (double *)redge, lay.ncomp, lay.nlev + 1, rm, true)) return 1;
+	}
+	if (lay.ntr > 0 && tracers != 0) {
+		std::vector<int> rt(lay.ntr);
+		for (int q = 0; q < lay.ntr; q++) rt[q] = lay.troff + q * lay.nlev;
+		if (move_state_array(ctx, *pi, inst, (double *)tracers, lay.ntr, lay.nlev, rt, true)) return 1;
+	}
+	return 0;
+}
+
+extern "C" int tb200_download_state(
+	tb200_ctx * ctx, int patch_index, int inst,
+	double * node, double * redge, double * tracers, int fill_derived
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid instance");
+	const DevLayout & lay = ctx->lay;
+	const bool nh = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO);
+	std::vector<int> rm(lay.ncomp), comps;
+	if (node != 0) {
+		comps.clear();
+		for (int c = 0; c < lay.ncomp; c++) {
+			rm[c] = lay.onedge[c] ? -1 : lay.rowoff[c];
+			if (!lay.onedge[c]) comps.push_back(c);
+		}
+		if (move_state_array(ctx, *pi, inst, node, lay.ncomp, lay.nlev, rm, false)) return 1;
+		if (fill_derived && nh) {
+			auto kfn = k_fill_derived;
+			TB_LAUNCH_FLAT(kfn, dim3(pi->nea * pi->neb), dim3(256), 0, ctx->stream,
+				lay, ctx->ops, (const double *)ctx->inst[inst], ctx->d_stage,
+				pi->elem0, pi->nea, pi->neb, pi->halo, 3, 3, 1, lay.nlev);
+			TB_KERNEL_CHECK(ctx);
+			comps.push_back(3);
+		}
+		if (stage_to_host(ctx, *pi, node, lay.nlev, comps)) return 1;
+	}
+	bool anyedge = false;
+	for (int c = 0; c < lay.ncomp; c++) anyedge = anyedge || lay.onedge[c];
+	if (redge != 0 && anyedge) {
+		comps.clear();
+		for (int c = 0; c < lay.ncomp; c++) {
+			rm[c] = lay.onedge[c] ? lay.rowoff[c] : -1;
+			if (lay.onedge[c]) comps.push_back(c);
+		}
+		if (move_state_array(ctx, *pi, inst, redge, lay.ncomp, lay.nlev + 1, rm, false)) return 1;
+		if (fill_derived && nh) {
+			for (int c = 0; c < 2; c++) {
+				auto kfn = k_fill_derived;
+				TB_LAUNCH_FLAT(kfn, dim3(pi->nea * pi->neb), dim3(256), 0, ctx->stream,
+					lay, ctx->ops, (const double *)ctx->inst[inst], ctx->d_stage,
+					pi->elem0, pi->nea, pi->neb, pi->halo, c, c, 0, lay.nlev + 1);
+				TB_KERNEL_CHECK(ctx);
+				comps.push_back(c);
+			}
+		}
+		if (stage_to_host(ctx, *pi, redge, lay.nlev + 1, comps)) return 1;
+	}
+	if (lay.ntr > 0 && tracers != 0) {
+		std::vector<int> rt(lay.ntr);
+		comps.clear();
+		for (int q = 0; q < lay.ntr; q++) {
+			rt[q] = lay.troff + q * lay.nlev;
+			comps.push_back(q);
+		}
+		if (move_state_array(ctx, *pi, inst, tracers, lay.ntr, lay.nlev, rt, false)) return 1;
+		if (stage_to_host(ctx, *pi, tracers, lay.nlev, comps)) return 1;
+	}
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Copy / LinearCombine / Zero
+
+static void mask_rows(const tb200_ctx * ctx, int mask, int & row0, int & row1) {
+	const DevLayout & lay = ctx->lay;
+	row0 = (mask & TB200_DATA_STATE) ? 0 : lay.nrows_state;
+	row1 = (mask & TB200_DATA_TRACERS) ? lay.nrows : lay.nrows_state;
+}
+
+static int launch_combine(tb200_ctx * ctx, const CombineArgs & ca, int dst, int row0, int row1) {
+	if (row1 <= row0) return 0;
+	const DevLayout & lay = ctx->lay;
+	const long long total = lay.nelem * (long long)(row1 - row0) * lay.nn;
+	const int block = 256;
+	long long nb = (total + block - 1) / block;
+	if (nb > 148 * 16) nb = 148 * 16;
+	auto kfn = k_lincomb;
+	TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(block), 0, ctx->stream,
+		lay, ca, ctx->inst[dst], row0, row1);
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
+extern "C" int tb200_copy(tb200_ctx * ctx, int src, int dst, int mask) {
+	const int ni = (int)ctx->inst.size();
+	if (src < 0 || src >= ni || dst < 0 || dst >= ni) TB_FAIL(ctx, "Invalid index in CopyData.");
+	if (src == dst) return 0;
+	int row0, row1;
+	mask_rows(ctx, mask, row0, row1);
+	if (row1 <= row0) return 0;
+	if (row0 == 0 && row1 == ctx->lay.nrows) {
+		const size_t bytes = (size_t)ctx->lay.nelem * ctx->lay.nrows * ctx->lay.nn * sizeof(double);
+		TB_CHECK(ctx, cudaMemcpyAsync(ctx->inst[dst], ctx->inst[src], bytes,
+			cudaMemcpyDeviceToDevice, ctx->stream));
+		return 0;
+	}
+	CombineArgs ca;
+	memset(&ca, 0, sizeof(ca));
+	ca.nsrc = 1;
+	ca.src[0] = ctx->inst[src];
+	ca.coeff[0] = 1.0;
+	ca.scale_dst = 0;
+	return launch_combine(ctx, ca, dst, row0, row1);
+}
+
+extern "C" int tb200_lincomb(
+	tb200_ctx * ctx, const double * coeff, int ncoeff, int dst, int mask
+) {
+	const int ni = (int)ctx->inst.size();
+	if (dst < 0 || dst >= ni) TB_FAIL(ctx, "Invalid ixDest index in LinearCombineData.");
+	if (dst >= ncoeff) TB_FAIL(ctx, "Destination index out of coefficient bounds");
+	if (ncoeff > ni) TB_FAIL(ctx, "Too many elements in coefficient vector.");
+	CombineArgs ca;
+	memset(&ca, 0, sizeof(ca));
+	ca.cdst = coeff[dst];
+	ca.scale_dst = (coeff[dst] == 0.0) ? 0 : 1;
+	for (int m = 0; m < ncoeff; m++) {
+		if (m == dst || coeff[m] == 0.0) continue;
+		ca.src[ca.nsrc] = ctx->inst[m];
+		ca.coeff[ca.nsrc] = coeff[m];
+		ca.nsrc++;
+	}
+	int row0, row1;
+	mask_rows(ctx, mask, row0, row1);
+	return launch_combine(ctx, ca, dst, row0, row1);
+}
+
+extern "C" int tb200_zero(tb200_ctx * ctx, int inst, int mask) {
+	const int ni = (int)ctx->inst.size();
+	if (inst < 0 || inst >= ni) TB_FAIL(ctx, "Invalid ixData index in ZeroData.");
+	CombineArgs ca;
+	memset(&ca, 0, sizeof(ca));
+	int row0, row1;
+	mask_rows(ctx, mask, row0, row1);
+	return launch_combine(ctx, ca, inst, row0, row1);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Dynamics
+
+static int check_ops(tb200_ctx * ctx) {
+	for (int q = 0; q < TB_NOPS; q++) {
+		if (q == 5 || q == 6) continue;   // not used by the hot path
+		if (ctx->ops.op[q].coeff == 0) TB_FAIL(ctx, "vertical column operators not set");
+	}
+	return 0;
+}
+
+static int nh_launch(tb200_ctx * ctx, int in, int out, double dt, bool do_h, bool do_v) {
+	const DevLayout & lay = ctx->lay;
+	if (check_ops(ctx)) return 1;
+	NHArgs a;
+	a.dt = dt;
+	a.xz = ctx->cfg.cartesian_xz;
+	a.fe_nodes = ctx->cfg.vertical_order;
+	int KB = 256 / lay.nn;
+	if (KB > lay.nlev) KB = lay.nlev;
+	const size_t smem = tb_nh_smem_doubles(lay.nlev, lay.nn, KB) * sizeof(double);
+	const dim3 grid((unsigned)lay.nelem), block(KB * lay.nn);
+	if (do_h && do_v) {
+		auto kfn = k_nh_explicit<4, true, true>;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
+			ctx->ops, ctx->phys, a, (const double *)ctx->inst[in], ctx->inst[out], KB);
+	} else if (do_h) {
+		auto kfn = k_nh_explicit<4, true, false>;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
+			ctx->ops, ctx->phys, a, (const double *)ctx->inst[in], ctx->inst[out], KB);
+	} else {
+		auto kfn = k_nh_explicit<4, false, true>;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
+			ctx->ops, ctx->phys, a, (const double *)ctx->inst[in], ctx->inst[out], KB);
+	}
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
+static int check_inst2(tb200_ctx * ctx, int in, int out) {
+	const int ni = (int)ctx->inst.size();
+	if (in < 0 || in >= ni || out < 0 || out >= ni) TB_FAIL(ctx, "invalid state instance");
+	return 0;
+}
+
+extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
+	if (check_inst2(ctx, in, out)) return 1;
+	// HorizontalDynamicsFEM.cpp:1793
+	if (in == out) TB_FAIL(ctx, "HorizontalDynamics Step must have iDataInitial != iDataUpdate");
+	const DevLayout & lay = ctx->lay;
+	if (ctx->cfg.eqn_type == TB200_EQN_SHALLOW_WATER) {
+		const long long nitems = lay.nelem * lay.nlev;
+		auto kfn = k_sw_explicit<4, kItems>;
+		TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
+			ctx->stream, lay, ctx->geom, ctx->tables,
+			(const double *)ctx->inst[in], ctx->inst[out], dt, ctx->cfg.g);
+		TB_KERNEL_CHECK(ctx);
+	} else {
+		if (nh_launch(ctx, in, out, dt, true, false)) return 1;
+	}
+	return tb200_filter_negative_tracers(ctx, out);
+}
+
+extern "C" int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
+	if (check_inst2(ctx, in, out)) return 1;
+	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || ctx->lay.nlev == 1) {
+		return 0;   // VerticalDynamicsStub (TempestInitialize.h:362-364)
+	}
+	if (ctx->cfg.fully_explicit) TB_FAIL(ctx, "--explicitvertical is not supported");
+	return nh_launch(ctx, in, out, dt, false, true);
+}
+
+extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
+	if (check_inst2(ctx, in, out)) return 1;
+	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || ctx->lay.nlev == 1) {
+		return tb200_h_step_explicit(ctx, in, out, dt);
+	}
+	if (in == out) TB_FAIL(ctx, "HorizontalDynamics Step must have iDataInitial != iDataUpdate");
+	if (ctx->lay.ntr > 0) {
+		// the tracer filter sits between the two plugins in the reference
+		if (tb200_h_step_explicit(ctx, in, out, dt)) return 1;
+		return tb200_v_step_explicit(ctx, in, out, dt);
+	}
+	return nh_launch(ctx, in, out, dt, true, true);
+}
+
+extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt) {
+	if (check_inst2(ctx, in, out)) return 1;
+	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || ctx->lay.nlev == 1) return 0;
+	if (ctx->cfg.fully_explicit) return 0;   // VerticalDynamicsFEM.cpp:1240-1242
+	if (check_ops(ctx)) return 1;
+	if (ctx->lay.ntr > 0) TB_FAIL(ctx, "implicit tracer transport is not implemented yet");
+	const DevLayout & lay = ctx->lay;
+	ColumnArgs ca;
+	ca.col_node = ctx->d_col_node;
+	ca.col_dups = ctx->d_col_dups;
+	ca.ws = ctx->d_ws;
+	ca.ws_stride = ctx->ws_cols;
+	ca.dt = dt;
+	ca.offd = ctx->offd;
+	ca.fe_nodes = ctx->cfg.vertical_order;
+	// m_dUpwindCoeff (VerticalDynamicsFEM.cpp:520-521)
+	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
+	ca.info = ctx->d_info;
+	for (int c0 = 0; c0 < ctx->ncols; c0 += ctx->ws_cols) {
+		ca.col0 = c0;
+		ca.ncols = std::min(ctx->ws_cols, ctx->ncols - c0);
+		const int block = 64;
+		auto kfn = k_column_implicit;
+		TB_LAUNCH_FLAT(kfn, dim3((ca.ncols + block - 1) / block), dim3(block), 0, ctx->stream,
+			lay, ctx->geom, ctx->ops, ctx->phys, ca,
+			(const double *)ctx->inst[in], ctx->inst[out]);
+		TB_KERNEL_CHECK(ctx);
+	}
+	return 0;
+}
+
+// Deferred error of the column solve ("Solution failed" / "Inversion failure",
+// VerticalDynamicsFEM.cpp:1461-1481); checked at tb200_sync-like points.
+static int check_column_info(tb200_ctx * ctx) {
+	if (ctx->d_info == 0) return 0;
+	int info = 0;
+	TB_CHECK(ctx, cudaMemcpy(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost));
+	if (info != 0) {
+		char buf[128];
+		snprintf(buf, 128, "Inversion failure in column %d", info - 1);
+		int zero = 0;
+		cudaMemcpy(ctx->d_info, &zero, sizeof(int), cudaMemcpyHostToDevice);
+		TB_FAIL(ctx, buf);
+	}
+	return 0;
+}
+
+extern "C" int tb200_check_errors(tb200_ctx * ctx) {
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	return check_column_info(ctx);
+}
+
+extern "C" int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst) {
+	if (ctx->lay.ntr == 0) return 0;
+	(void)inst;
+	TB_FAIL(ctx, "FilterNegativeTracers is not implemented yet");
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// DSS
+
+static int ensure_buffers(tb200_ctx * ctx, size_t rows) {
+	if (ctx->nranks == 1 || rows <= ctx->buf_rows) return 0;
+	if (dalloc(ctx, &ctx->d_sendbuf, (size_t)ctx->nsend_total * rows)) return 1;
+	if (dalloc(ctx, &ctx->d_recvbuf, (size_t)ctx->nrecv_total * rows)) return 1;
+	ctx->buf_rows = rows;
+	return 0;
+}
+
+static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state) {
+	if (row1 <= row0) return 0;
+	const DevLayout & lay = ctx->lay;
+	const int nsel = row1 - row0;
+	if (ctx->nranks > 1) {
+		if (ensure_buffers(ctx, (size_t)std::max(lay.nrows_state, lay.nrows - lay.nrows_state))) return 1;
+		if (ctx->nsend_total > 0) {
+			const long long total = (long long)ctx->nsend_total * nsel;
+			long long nb = (total + 255) / 256;
+			if (nb > 148 * 8) nb = 148 * 8;
+			auto kfn = k_dss_pack;
+			TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(256), 0, ctx->stream,
+				lay, (const int *)ctx->d_send_nodes, ctx->nsend_total,
+				(const double *)ctx->inst[inst], ctx->d_sendbuf, row0, nsel);
+			TB_KERNEL_CHECK(ctx);
+		}
+		std::vector<int64_t> sc(ctx->nranks), rc(ctx->nranks);
+		for (int r = 0; r < ctx->nranks; r++) {
+			sc[r] = ctx->send_count[r] * nsel;
+			rc[r] = ctx->recv_count[r] * nsel;
+		}
+		if (ctx->exch_fn(ctx->exch_user, ctx->d_sendbuf, ctx->d_recvbuf,
+				sc.data(), rc.data(), ctx->nranks) != 0) {
+			TB_FAIL(ctx, "exchange callback failed");
+		}
+	}
+	if (ctx->ngroups == 0) return 0;
+	DssArgs a;
+	a.members = ctx->d_members;
+	a.flags = ctx->d_flags;
+	a.ngroups = ctx->ngroups;
+	a.nlocal = (int)(lay.nelem * lay.nn);
+	a.recv = ctx->d_recvbuf;
+	a.row0 = row0;
+	a.row1 = row1;
+	a.uv_row0 = is_state ? lay.rowoff[0] : -1;
+	a.uv_row1 = is_state ? (lay.rowoff[1] + lay.rowlev[1]) : -1;
+	a.nsel = nsel;
+	a.sel_row0 = row0;
+	{
+		const int block = 128;
+		int gy = std::min(nsel, 32);
+		auto kfn = k_dss_scalar;
+		TB_LAUNCH_FLAT(kfn, dim3((ctx->ngroups + block - 1) / block, gy), dim3(block), 0,
+			ctx->stream, lay, a, ctx->inst[inst]);
+		TB_KERNEL_CHECK(ctx);
+	}
+	if (is_state && ctx->nseam > 0) {
+		SeamArgs sa;
+		sa.group = ctx->d_seam_group;
+		sa.mats = ctx->d_seam_mats;
+		sa.nseam = ctx->nseam;
+		sa.nlev_u = lay.rowlev[0];
+		const int total = sa.nseam * sa.nlev_u;
+		auto kfn = k_dss_seam_vector;
+		TB_LAUNCH_FLAT(kfn, dim3((total + 127) / 128), dim3(128), 0, ctx->stream,
+			lay, a, sa, ctx->inst[inst]);
+		TB_KERNEL_CHECK(ctx);
+	}
+	return 0;
+}
+
+extern "C" int tb200_dss(tb200_ctx * ctx, int inst, int mask) {
+	if (!ctx->connectivity_built) TB_FAIL(ctx, "connectivity not built");
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid state instance");
+	const DevLayout & lay = ctx->lay;
+	if (mask & TB200_DATA_STATE) {
+		if (dss_rows(ctx, inst, 0, lay.nrows_state, true)) return 1;
+	}
+	if ((mask & TB200_DATA_TRACERS) && lay.ntr > 0) {
+		if (dss_rows(ctx, inst, lay.nrows_state, lay.nrows, false)) return 1;
+	}
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Hyperdiffusion (HorizontalDynamicsFEM::StepAfterSubCycle, :2637-2726)
+
+static int hyper_scalar(tb200_ctx * ctx, int in, int out, double dt, double nu, bool scale) {
+	const DevLayout & lay = ctx->lay;
+	HyperRows hr;
+	memset(&hr, 0, sizeof(hr));
+	int nsel = 0;
+	// components 2.. of the state (:1983-1993), then every tracer
+	for (int c = 2; c < lay.ncomp; c++) {
+		hr.row0[hr.nranges] = lay.rowoff[c];
+		hr.row1[hr.nranges] = lay.rowoff[c] + lay.rowlev[c];
+		hr.onedge[hr.nranges] = lay.onedge[c];
+		nsel += lay.rowlev[c];
+		hr.nranges++;
+	}
+	if (lay.ntr > 0) {
+		hr.row0[hr.nranges] = lay.troff;
+		hr.row1[hr.nranges] = lay.nrows;
+		hr.onedge[hr.nranges] = 0;
+		nsel += lay.ntr * lay.nlev;
+		hr.nranges++;
+	}
+	const long long nitems = lay.nelem * nsel;
+	auto kfn = k_hyper_scalar<4, kItems>;
+	TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
+		ctx->stream, lay, ctx->geom, ctx->tables, hr, nsel,
+		(const double *)ctx->inst[in], ctx->inst[out], dt, nu, scale ? 1 : 0);
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
+static int hyper_vector(
+	tb200_ctx * ctx, int in, int out, double dt, double nud, double nuv, bool scale
+) {
+	const DevLayout & lay = ctx->lay;
+	const long long nitems = lay.nelem * lay.nlev;
+	auto kfn = k_hyper_vector<4, kItems>;
+	TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
+		ctx->stream, lay, ctx->geom, ctx->tables,
+		(const double *)ctx->inst[in], ctx->inst[out], dt, nud, nuv, scale ? 1 : 0,
+		ctx->cfg.cartesian_xz);
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
+extern "C" int tb200_h_step_after_subcycle(
+	tb200_ctx * ctx, int in, int out, int work, double dt
+) {
+	const int ni = (int)ctx->inst.size();
+	if (in < 0 || in >= ni || out < 0 || out >= ni || work < 0 || work >= ni) {
+		TB_FAIL(ctx, "invalid state instance");
+	}
+	if (in == work) TB_FAIL(ctx, "Invalid indices -- initial and working data must be distinct");
+	if (out == work) TB_FAIL(ctx, "Invalid indices -- working and update data must be distinct");
+	const tb200_config & c = ctx->cfg;
+	const int all = TB200_DATA_STATE | TB200_DATA_TRACERS;
+	if (tb200_copy(ctx, in, out, all)) return 1;
+	if ((c.nu_scalar == 0.0) && (c.nu_div == 0.0) && (c.nu_vort == 0.0)) {
+	} else if (c.hypervis_order == 0) {
+	} else if (c.hypervis_order == 2) {
+		if (hyper_scalar(ctx, in, out, dt, c.nu_scalar, false)) return 1;
+		if (hyper_vector(ctx, in, out, -dt, c.nu_div, c.nu_vort, false)) return 1;
+		if (tb200_filter_negative_tracers(ctx, out)) return 1;
+		if (tb200_dss(ctx, out, all)) return 1;
+	} else if (c.hypervis_order == 4) {
+		if (tb200_zero(ctx, work, all)) return 1;
+		if (hyper_scalar(ctx, in, work, 1.0, 1.0, false)) return 1;
+		if (hyper_vector(ctx, in, work, 1.0, 1.0, 1.0, false)) return 1;
+		if (tb200_dss(ctx, work, all)) return 1;
+		if (hyper_scalar(ctx, work, out, -dt, c.nu_scalar, true)) return 1;
+		if (hyper_vector(ctx, work, out, -dt, c.nu_div, c.nu_vort, true)) return 1;
+		if (tb200_filter_negative_tracers(ctx, out)) return 1;
+		if (tb200_dss(ctx, out, all)) return 1;
+	} else {
+		TB_FAIL(ctx, "Invalid viscosity order");
+	}
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Connectivity
+
+extern "C" int tb200_set_node_ids(tb200_ctx * ctx, int patch_index, const int64_t * ids) {
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0) TB_FAIL(ctx, "unknown patch");
+	const size_t n = (size_t)pi->nea * ctx->lay.np * pi->neb * ctx->lay.np;
+	pi->ids.assign(ids, ids + n);
+	return 0;
+}
+
+extern "C" int tb200_set_seam_transforms(
+	tb200_ctx * ctx, int patch_index, int n, const int * ia, const int * ib,
+	const int * src_panel, const double * m
+) {
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0) TB_FAIL(ctx, "unknown patch");
+	pi->seams.clear();
+	for (int q = 0; q < n; q++) {
+		SeamEntry s;
+		s.ia = ia[q];
+		s.ib = ib[q];
+		s.src_panel = src_panel[q];
+		for (int r = 0; r < 4; r++) s.m[r] = m[4 * q + r];
+		pi->seams.push_back(s);
+	}
+	return 0;
+}
+
+struct Member {
+	int ppos;       // position of the patch in ctx->patches
+	int ia, ib;
+	long long addr; // local node address, -1 when remote
+};
+
+static bool member_less(const tb200_ctx * ctx, const Member & x, const Member & y) {
+	const int px = ctx->patches[x.ppos].index, py = ctx->patches[y.ppos].index;
+	if (px != py) return px < py;
+	if (x.ib != y.ib) return x.ib < y.ib;
+	return x.ia < y.ia;
+}
+
+extern "C" int tb200_build_connectivity(tb200_ctx * ctx) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	const int np = ctx->lay.np, nn = ctx->lay.nn;
+
+	// collect the boundary nodes of every element of every patch by id
+	std::unordered_map<int64_t, std::vector<Member> > byid;
+	for (size_t p = 0; p < ctx->patches.size(); p++) {
+		const PatchInfo & pi = ctx->patches[p];
+		const int wbi = pi.neb * np;
+		if (pi.ids.size() != (size_t)pi.nea * np * wbi) {
+			TB_FAIL(ctx, "node ids missing for a patch");
+		}
+		for (int a = 0; a < pi.nea; a++)
+		for (int b = 0; b < pi.neb; b++)
+		for (int i = 0; i < np; i++)
+		for (int j = 0; j < np; j++) {
+			if (i != 0 && i != np - 1 && j != 0 && j != np - 1) continue;
+			Member m;
+			m.ppos = (int)p;
+			m.ia = a * np + i;
+			m.ib = b * np + j;
+			m.addr = (pi.elem0 >= 0)
+				? (pi.elem0 + (long long)a * pi.neb + b) * nn + i * np + j : -1;
+			byid[pi.ids[(size_t)m.ia * wbi + m.ib]].push_back(m);
+		}
+	}
+
+	const int nlocal = (int)(ctx->lay.nelem * nn);
+	// exchange lists: for the ordered pair (src rank -> dst rank) the nodes of
+	// src that share an id with a node of dst, in (patch, ib, ia) order.
+	// send_lists[d] = my nodes sent to d; recv_index[(s, patch, ia, ib)] = slot.
+	std::vector<std::vector<Member> > send_lists(ctx->nranks), recv_lists(ctx->nranks);
+
+	struct Group { std::vector<Member> mem; bool seam; };
+	std::vector<Group> groups;
+
+	for (std::unordered_map<int64_t, std::vector<Member> >::iterator it = byid.begin();
+	     it != byid.end(); ++it
+	) {
+		std::vector<Member> & mem = it->second;
+		if (mem.size() < 2) continue;
+		if (mem.size() > 4) TB_FAIL(ctx, "node shared by more than four elements");
+		bool anylocal = false, anyremote = false, seam = false;
+		for (size_t q = 0; q < mem.size(); q++) {
+			if (mem[q].addr >= 0) anylocal = true; else anyremote = true;
+			if (ctx->patches[mem[q].ppos].panel != ctx->patches[mem[0].ppos].panel) seam = true;
+		}
+		if (!anylocal) continue;
+		std::sort(mem.begin(), mem.end(),
+			[ctx](const Member & x, const Member & y) { return member_less(ctx, x, y); });
+		if (anyremote) {
+			for (size_t q = 0; q < mem.size(); q++) {
+				const int owner = ctx->patches[mem[q].ppos].owner;
+				if (owner == ctx->rank) {
+					// this node goes to every other rank present in the group
+					std::vector<int> seen;
+					for (size_t r = 0; r < mem.size(); r++) {
+						const int o2 = ctx->patches[mem[r].ppos].owner;
+						if (o2 != ctx->rank && std::find(seen.begin(), seen.end(), o2) == seen.end()) {
+							seen.push_back(o2);
+							send_lists[o2].push_back(mem[q]);
+						}
+					}
+				} else {
+					recv_lists[owner].push_back(mem[q]);
+				}
+			}
+		}
+		Group gr;
+		gr.mem = mem;
+		gr.seam = seam;
+		groups.push_back(gr);
+	}
+
+	// deterministic slot order on both sides
+	std::vector<int> send_nodes;
+	ctx->send_count.assign(ctx->nranks, 0);
+	ctx->recv_count.assign(ctx->nranks, 0);
+	std::map<std::pair<int, std::pair<int, int> >, int> recv_slot;  // (patch index,(ia,ib)) -> slot
+	int slot = 0;
+	for (int r = 0; r < ctx->nranks; r++) {
+		std::vector<Member> & sl = send_lists[r];
+		std::sort(sl.begin(), sl.end(),
+			[ctx](const Member & x, const Member & y) { return member_less(ctx, x, y); });
+		// a node can be listed once per group only, groups are disjoint: no duplicates
+		for (size_t q = 0; q < sl.size(); q++) send_nodes.push_back((int)sl[q].addr);
+		ctx->send_count[r] = (int64_t)sl.size();
+		std::vector<Member> & rl = recv_lists[r];
+		std::sort(rl.begin(), rl.end(),
+			[ctx](const Member & x, const Member & y) { return member_less(ctx, x, y); });
+		for (size_t q = 0; q < rl.size(); q++) {
+			recv_slot[std::make_pair(ctx->patches[rl[q].ppos].index,
+				std::make_pair(rl[q].ia, rl[q].ib))] = slot++;
+		}
+		ctx->recv_count[r] = (int64_t)rl.size();
+	}
+	ctx->nsend_total = (int)send_nodes.size();
+	ctx->nrecv_total = slot;
+	if (dupload(ctx, &ctx->d_send_nodes, send_nodes)) return 1;
+
+	// order groups by their first local member for memory locality
+	std::sort(groups.begin(), groups.end(), [](const Group & x, const Group & y) {
+		long long ax = -1, ay = -1;
+		for (size_t q = 0; q < x.mem.size(); q++) if (x.mem[q].addr >= 0) { ax = x.mem[q].addr; break; }
+		for (size_t q = 0; q < y.mem.size(); q++) if (y.mem[q].addr >= 0) { ay = y.mem[q].addr; break; }
+		return ax < ay;
+	});
+
+	std::vector<int> members(groups.size() * 4, -1), flags(groups.size(), 0);
+	std::vector<int> seam_group;
+	std::vector<double> seam_mats;
+	for (size_t gi = 0; gi < groups.size(); gi++) {
+		const Group & gr = groups[gi];
+		for (size_t q = 0; q < gr.mem.size(); q++) {
+			const Member & m = gr.mem[q];
+			if (m.addr >= 0) {
+				members[gi * 4 + q] = (int)m.addr;
+			} else {
+				members[gi * 4 + q] = nlocal + recv_slot[std::make_pair(
+					ctx->patches[m.ppos].index, std::make_pair(m.ia, m.ib))];
+			}
+		}
+		if (!gr.seam) continue;
+		flags[gi] = 1;
+		seam_group.push_back((int)gi);
+		const size_t base = seam_mats.size();
+		seam_mats.resize(base + 64, 0.0);
+		for (size_t t = 0; t < gr.mem.size(); t++) {
+			const PatchInfo & pt = ctx->patches[gr.mem[t].ppos];
+			for (size_t s = 0; s < gr.mem.size(); s++) {
+				const PatchInfo & ps = ctx->patches[gr.mem[s].ppos];
+				double * M = &seam_mats[base + (t * 4 + s) * 4];
+				if (ps.panel == pt.panel) {
+					M[0] = 1.0; M[1] = 0.0; M[2] = 0.0; M[3] = 1.0;
+					continue;
+				}
+				if (gr.mem[t].addr < 0) continue;   // remote targets are not written
+				bool found = false;
+				for (size_t q = 0; q < pt.seams.size(); q++) {
+					const SeamEntry & se = pt.seams[q];
+					if (se.ia == gr.mem[t].ia && se.ib == gr.mem[t].ib && se.src_panel == ps.panel) {
+						for (int r = 0; r < 4; r++) M[r] = se.m[r];
+						found = true;
+						break;
+					}
+				}
+				if (!found) TB_FAIL(ctx, "missing seam transform for a panel-boundary node");
+			}
+		}
+	}
+	ctx->ngroups = (int)groups.size();
+	ctx->nseam = (int)seam_group.size();
+	if (dupload(ctx, &ctx->d_members, members)) return 1;
+	if (dupload(ctx, &ctx->d_flags, flags)) return 1;
+	if (dupload(ctx, &ctx->d_seam_group, seam_group)) return 1;
+	if (dupload(ctx, &ctx->d_seam_mats, seam_mats)) return 1;
+	ctx->connectivity_built = true;
+	return 0;
+}
+
+extern "C" int tb200_exchange_counts(
+	tb200_ctx * ctx, int64_t * send_nodes, int64_t * recv_nodes
+) {
+	for (int r = 0; r < ctx->nranks; r++) {
+		send_nodes[r] = ctx->send_count.size() ? ctx->send_count[r] : 0;
+		recv_nodes[r] = ctx->recv_count.size() ? ctx->recv_count[r] : 0;
+	}
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Band solve test hook
+
+extern "C" int tb200_test_band_solve(
+	tb200_ctx * ctx, int ncols, int n, int kl, int ku, const double * ab, double * b
+) {
+	const int ldab = 2 * kl + ku + 1;
+	// host [col][n][ldab] -> device [(j*ldab + r)][col]
+	std::vector<double> hab((size_t)ncols * n * ldab), hb((size_t)ncols * n);
+	for (int c = 0; c < ncols; c++) {
+		for (int q = 0; q < n * ldab; q++) hab[(size_t)q * ncols + c] = ab[(size_t)c * n * ldab + q];
+		for (int q = 0; q < n; q++) hb[(size_t)q * ncols + c] = b[(size_t)c * n + q];
+	}
+	double * dab = 0;
+	double * db = 0;
+	if (dupload(ctx, &dab, hab)) return 1;
+	if (dupload(ctx, &db, hb)) return 1;
+	auto kfn = k_band_solve;
+	TB_LAUNCH_FLAT(kfn, dim3((ncols + 63) / 64), dim3(64), 0, ctx->stream,
+		ncols, n, kl, ku, dab, db, ctx->d_info);
+	TB_KERNEL_CHECK(ctx);
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	TB_CHECK(ctx, cudaMemcpy(hb.data(), db, hb.size() * sizeof(double), cudaMemcpyDeviceToHost));
+	for (int c = 0; c < ncols; c++) {
+		for (int q = 0; q < n; q++) b[(size_t)c * n + q] = hb[(size_t)q * ncols + c];
+	}
+	return check_column_info(ctx);
+}

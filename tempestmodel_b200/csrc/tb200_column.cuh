@@ -1,0 +1,524 @@
+// Vertically implicit column solve (FP64): one thread per unique column.
+//
+// Restates VerticalDynamicsFEM::StepImplicit and its helpers for the
+// configuration the reference compiles (src/atm/Defines.h: USE_DIRECTSOLVE,
+// USE_JACOBIAN_DIAGONAL, FORMULATION_RHOTHETA_PI; VerticalDynamicsFEM.cpp:36-46
+// upwinding on rho-theta, w, rho; Clark-form implicit vertical advection of w)
+// under Lorenz staggering:
+//   SetupReferenceColumn   VerticalDynamicsFEM.cpp:1643-1835
+//   PrepareColumn          :1839-2179
+//   BuildF                 :2183-2780
+//   BuildJacobianF_LOR_RhoTheta_Pi + _Diffusion   :2977-3187, :2784-2973
+//   LAPACK dgbsv (dgbtf2 + dgbtrs, partial pivoting)  LinearAlgebra.cpp:156-202
+//   x = x0 - J^{-1} F and scatter to duplicates   :1483-1633
+//
+// All per-column work arrays live in a global workspace laid out
+// [entry][column] so that the threads of a warp (adjacent columns) touch
+// consecutive addresses.
+#ifndef TB200_COLUMN_CUH
+#define TB200_COLUMN_CUH
+
+#include "tb200_platform.h"
+#include "tb200_device.h"
+#include "tb200_kernels.cuh"
+
+struct ColumnArgs {
+	const int * col_node;   // [ncols] local node address (e*NN+n) solved
+	const int * col_dups;   // [ncols][3] duplicates receiving a copy, -1 unused
+	int ncols;              // columns in this launch
+	int col0;               // first column of this launch
+	double * ws;            // workspace [entries][ws_stride]
+	int ws_stride;
+	double dt;
+	int offd;               // m_nJacobianFOffD (kl = ku)
+	int fe_nodes;           // nodes per vertical finite element
+	double upwind_coeff;    // m_dUpwindCoeff
+	int * info;             // device flag: first failing column + 1
+};
+
+// number of workspace entries per column
+__host__ __device__ inline int tb_column_ws_entries(int L, int offd) {
+	const int n = 3 * (L + 1);
+	return 24 * (L + 1) + 2 * n + n * (3 * offd + 1);
+}
+
+// Banded LU with partial pivoting and solve, nrhs = 1: LAPACK dgbsv =
+// dgbtf2 + dgbtrs('N').  ab(r, j) is band row r (0-based, 0..ldab-1) of
+// column j: the reference's row-major [n][ldab] array handed to Fortran as
+// AB(ldab, n) (LinearAlgebra.cpp:156-202).  Strided accessors.
+template <typename AB, typename BV>
+__device__ inline int tb_dgbsv(int n, int kl, int ku, AB ab, BV b) {
+	const int kv = ku + kl;
+	int info = 0;
+	// zero the fill-in part of the first superdiagonal columns
+	for (int j = ku + 1; j < ((kv < n) ? kv : n); j++) {
+		for (int i = kv - j; i < kl; i++) {
+			ab(i, j) = 0.0;
+		}
+	}
+	int ju = 0;
+	for (int j = 0; j < n; j++) {
+		if (j + kv < n) {
+			for (int i = 0; i < kl; i++) {
+				ab(i, j + kv) = 0.0;
+			}
+		}
+		const int km = (kl < n - 1 - j) ? kl : (n - 1 - j);
+		// idamax
+		int jp = 0;
+		double amax = fabs(ab(kv, j));
+		for (int i = 1; i <= km; i++) {
+			const double v = fabs(ab(kv + i, j));
+			if (v > amax) {
+				amax = v;
+				jp = i;
+			}
+		}
+		const int piv = jp + j;
+		if (ab(kv + jp, j) != 0.0) {
+			int cand = j + ku + jp;
+			if (cand > n - 1) cand = n - 1;
+			if (cand > ju) ju = cand;
+			if (jp != 0) {
+				for (int c = 0; c <= ju - j; c++) {
+					const double tmp = ab(kv + jp - c, j + c);
+					ab(kv + jp - c, j + c) = ab(kv - c, j + c);
+					ab(kv - c, j + c) = tmp;
+				}
+			}
+			if (km > 0) {
+				const double r = 1.0 / ab(kv, j);
+				for (int i = 1; i <= km; i++) {
+					ab(kv + i, j) *= r;
+				}
+				for (int c = 1; c <= ju - j; c++) {
+					const double y = ab(kv - c, j + c);
+					if (y != 0.0) {
+						for (int i = 1; i <= km; i++) {
+							ab(kv + i - c, j + c) -= ab(kv + i, j) * y;
+						}
+					}
+				}
+			}
+		} else if (info == 0) {
+			info = j + 1;
+		}
+		// forward substitution of dgbtrs fused in (same arithmetic)
+		if (j < n - 1) {
+			if (piv != j) {
+				const double tmp = b(piv);
+				b(piv) = b(j);
+				b(j) = tmp;
+			}
+			const double bj = b(j);
+			for (int i = 1; i <= km; i++) {
+				b(j + i) -= ab(kv + i, j) * bj;
+			}
+		}
+	}
+	if (info != 0) return info;
+	// dtbsv upper, no transpose, non-unit, bandwidth kv
+	for (int j = n - 1; j >= 0; j--) {
+		if (b(j) != 0.0) {
+			b(j) = b(j) / ab(kv, j);
+			const double temp = b(j);
+			const int lo = (j - kv > 0) ? (j - kv) : 0;
+			for (int i = j - 1; i >= lo; i--) {
+				b(i) -= temp * ab(kv - (j - i), j);
+			}
+		}
+	}
+	return 0;
+}
+
+struct WsAcc {
+	double * p;
+	int stride;
+	__device__ __forceinline__ double & operator()(int i) const {
+		return p[(size_t)i * stride];
+	}
+};
+
+struct WsBand {
+	double * p;
+	int stride;
+	int ldab;
+	__device__ __forceinline__ double & operator()(int r, int j) const {
+		return p[(size_t)(j * ldab + r) * stride];
+	}
+};
+
+// Standalone batched band solve (pinning against LAPACK)
+__global__ void k_band_solve(
+	int ncols, int n, int kl, int ku, double * ab, double * b, int * info
+) {
+	const int tcol = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tcol >= ncols) return;
+	const int ldab = 2 * kl + ku + 1;
+	WsBand A = {ab + tcol, ncols, ldab};
+	WsAcc B = {b + tcol, ncols};
+	const int r = tb_dgbsv(n, kl, ku, A, B);
+	if (r != 0) atomicMax(info, r);
+}
+
+// apply a column operator to a workspace column
+__device__ __forceinline__ double tb_ws_apply(const DevOp & op, const WsAcc & in, int k) {
+	double o = 0.0;
+	const int b = op.begin[k];
+	const int e = op.end[k];
+	const double * c = op.coeff + (size_t)k * op.width;
+	for (int l = b; l < e; l++) {
+		o += c[l - b] * in(l);
+	}
+	return o;
+}
+
+__device__ __forceinline__ double tb_op_coeff(const DevOp & op, int k, int l) {
+	return op.coeff[(size_t)k * op.width + (l - op.begin[k])];
+}
+
+__global__ void k_column_implicit(
+	DevLayout lay, DevGeom g, DevOps ops, DevPhys ph, ColumnArgs ca,
+	const double * __restrict__ in, double * __restrict__ out
+) {
+	const int tcol = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tcol >= ca.ncols) return;
+
+	const int UIx = 0, VIx = 1, PIx = 2, WIx = 3, RIx = 4;
+	const int FP = 0, FW = 1, FR = 2;
+	const int NN = lay.nn;
+	const int L = lay.nlev;
+	const int n = 3 * (L + 1);
+	const int offd = ca.offd;
+	const int ldab = 3 * offd + 1;
+
+	const int node = ca.col_node[ca.col0 + tcol];
+	const long long e = node / NN;
+	const int nd = node % NN;
+	const size_t ebase = (size_t)e * lay.nrows * NN;
+	const size_t g3 = (size_t)e * L * NN + nd;
+	const size_t g3e = (size_t)e * (L + 1) * NN + nd;
+
+	// workspace carve-up
+	double * w0 = ca.ws + tcol;
+	const int S = ca.ws_stride;
+	int cur = 0;
+#define TB_WS(name, len) WsAcc name = {w0 + (size_t)cur * S, S}; cur += (len)
+	TB_WS(snU, L + 1); TB_WS(snV, L + 1); TB_WS(snP, L + 1); TB_WS(snW, L + 1); TB_WS(snR, L + 1);
+	TB_WS(seU, L + 1); TB_WS(seV, L + 1); TB_WS(seW, L + 1); TB_WS(seR, L + 1); TB_WS(seP, L + 1);
+	TB_WS(exn, L + 1); TB_WS(dPe, L + 1); TB_WS(xdn, L + 1); TB_WS(xde, L + 1);
+	TB_WS(mfe, L + 1); TB_WS(dmfn, L + 1); TB_WS(pfe, L + 1); TB_WS(dpfn, L + 1);
+	TB_WS(ken, L + 1); TB_WS(dkee, L + 1); TB_WS(dUa, L + 1); TB_WS(dUb, L + 1);
+	TB_WS(ddW, L + 1); TB_WS(aux, L + 1);
+	TB_WS(x0, n); TB_WS(F, n);
+#undef TB_WS
+	WsBand DG = {w0 + (size_t)cur * S, S, ldab};
+
+	const DevOp & opInterpN2E = ops.op[0];
+	const DevOp & opInterpE2N = ops.op[1];
+	const DevOp & opDiffN2E = ops.op[3];
+	const DevOp & opDiffE2N = ops.op[4];
+	const DevOp & opDDE2E = ops.op[7];
+	const DevOp & opPenL = ops.op[8];
+	const DevOp & opPenR = ops.op[9];
+
+	const double * inU = in + ebase + (size_t)lay.rowoff[UIx] * NN + nd;
+	const double * inV = in + ebase + (size_t)lay.rowoff[VIx] * NN + nd;
+	const double * inP = in + ebase + (size_t)lay.rowoff[PIx] * NN + nd;
+	const double * inW = in + ebase + (size_t)lay.rowoff[WIx] * NN + nd;
+	const double * inR = in + ebase + (size_t)lay.rowoff[RIx] * NN + nd;
+
+	// ---- SetupReferenceColumn (:1643-1835) --------------------------------
+	for (int k = 0; k < L; k++) {
+		snU(k) = inU[(size_t)k * NN];
+		snV(k) = inV[(size_t)k * NN];
+	}
+	for (int k = 0; k <= L; k++) {
+		seU(k) = tb_ws_apply(opInterpN2E, snU, k);
+		seV(k) = tb_ws_apply(opInterpN2E, snV, k);
+		dUa(k) = tb_ws_apply(opDiffN2E, snU, k);
+		dUb(k) = tb_ws_apply(opDiffN2E, snV, k);
+	}
+	for (int q = 0; q < n; q++) {
+		x0(q) = 0.0;
+	}
+	for (int k = 0; k < L; k++) {
+		x0(3 * k + FP) = inP[(size_t)k * NN];
+		x0(3 * k + FR) = inR[(size_t)k * NN];
+	}
+	for (int k = 0; k <= L; k++) {
+		x0(3 * k + FW) = inW[(size_t)k * NN];
+	}
+
+	// ---- PrepareColumn (:1839-2179) ----------------------------------------
+	for (int k = 0; k < L; k++) {
+		snP(k) = x0(3 * k + FP);
+		seW(k) = x0(3 * k + FW);
+		snR(k) = x0(3 * k + FR);
+	}
+	seW(L) = x0(3 * L + FW);
+	for (int k = 0; k < L; k++) {
+		snW(k) = tb_ws_apply(opInterpE2N, seW, k);
+	}
+	for (int k = 0; k <= L; k++) {
+		seR(k) = tb_ws_apply(opInterpN2E, snR, k);
+		seP(k) = tb_ws_apply(opInterpN2E, snP, k);
+	}
+	for (int k = 0; k < L; k++) {
+		exn(k) = ph.cp * exp(ph.exner_c1 * log(ph.exner_c2 * snP(k)));
+	}
+	for (int k = 0; k <= L; k++) {
+		dPe(k) = tb_ws_apply(opDiffN2E, exn, k);
+	}
+	for (int k = 0; k < L; k++) {
+		const size_t o = g3 + (size_t)k * NN;
+		xdn(k) = g.cx[0][o] * snU(k) + g.cx[1][o] * snV(k) + g.cx[2][o] * snW(k);
+	}
+	for (int k = 1; k < L; k++) {
+		const size_t o = g3e + (size_t)k * NN;
+		xde(k) = g.cxe[0][o] * seU(k) + g.cxe[1][o] * seV(k) + g.cxe[2][o] * seW(k);
+	}
+	xde(0) = 0.0;
+	xde(L) = 0.0;
+	// second derivative of w for interface upwinding (:2091-2102)
+	for (int k = 0; k <= L; k++) {
+		ddW(k) = tb_ws_apply(opDDE2E, seW, k);
+	}
+
+	// ---- BuildF (:2183-2780) -------------------------------------------------
+	for (int q = 0; q < n; q++) {
+		F(q) = 0.0;
+	}
+	mfe(0) = 0.0; mfe(L) = 0.0; pfe(0) = 0.0; pfe(L) = 0.0;
+	for (int k = 1; k < L; k++) {
+		const double je = g.jace[g3e + (size_t)k * NN];
+		mfe(k) = je * seR(k) * xde(k);
+		pfe(k) = je * seP(k) * xde(k);
+	}
+	for (int k = 0; k < L; k++) {
+		const double invj = 1.0 / g.jac[g3 + (size_t)k * NN];
+		dmfn(k) = tb_ws_apply(opDiffE2N, mfe, k);
+		dpfn(k) = tb_ws_apply(opDiffE2N, pfe, k);
+		F(3 * k + FR) = dmfn(k) * invj;
+		F(3 * k + FP) += dpfn(k) * invj;
+	}
+	// kinetic energy on levels (:2433-2467)
+	for (int k = 0; k < L; k++) {
+		const size_t o = g3 + (size_t)k * NN;
+		const double dCovUa = snU(k), dCovUb = snV(k), dCovUx = snW(k);
+		const double dConUa = g.ca[0][o] * dCovUa + g.ca[1][o] * dCovUb + g.ca[2][o] * dCovUx;
+		const double dConUb = g.cb[0][o] * dCovUa + g.cb[1][o] * dCovUb + g.cb[2][o] * dCovUx;
+		const double dConUx = g.cx[0][o] * dCovUa + g.cx[1][o] * dCovUb + g.cx[2][o] * dCovUx;
+		ken(k) = 0.5 * (dConUa * dCovUa + dConUb * dCovUb + dConUx * dCovUx);
+	}
+	for (int k = 0; k <= L; k++) {
+		dkee(k) = tb_ws_apply(opDiffN2E, ken, k);
+	}
+	// vertical velocity on interfaces (:2533-2589)
+	for (int k = 1; k < L; k++) {
+		const size_t o = g3e + (size_t)k * NN;
+		const double dPressureGradientForce = dPe(k) * seP(k) / seR(k);
+		double f = dPressureGradientForce;
+		f += ph.g * g.dre[2][o];
+		const double dCovUa = seU(k), dCovUb = seV(k), dCovUx = seW(k);
+		const double dConUa = g.cae[0][o] * dCovUa + g.cae[1][o] * dCovUb + g.cae[2][o] * dCovUx;
+		const double dConUb = g.cbe[0][o] * dCovUa + g.cbe[1][o] * dCovUb + g.cbe[2][o] * dCovUx;
+		const double dCurlTerm = -dConUa * dUa(k) - dConUb * dUb(k);
+		f += (dkee(k) + dCurlTerm);
+		F(3 * k + FW) = f;
+	}
+	// vertical upwinding (:2640-2713)
+	const int vo = ca.fe_nodes;
+	const int nfe = L / vo;
+	for (int c = 2; c < 5; c++) {
+		if (c == WIx) {
+			ddW(0) = 0.0;
+			ddW(L) = 0.0;
+			for (int k = 0; k <= L; k++) {
+				F(3 * k + FW) -= ca.upwind_coeff * fabs(xde(k)) * ddW(k);
+			}
+		} else {
+			const WsAcc & sn = (c == PIx) ? snP : snR;
+			const int fc = (c == PIx) ? FP : FR;
+			for (int k = 0; k < L; k++) {
+				aux(k) = 0.0;
+			}
+			for (int a = 0; a < nfe - 1; a++) {
+				const double wgt = fabs(xde((a + 1) * vo));
+				for (int ii = 0; ii < vo; ii++) {
+					const int k = a * vo + ii;
+					aux(k) += tb_ws_apply(opPenL, sn, k) * wgt;
+				}
+			}
+			for (int a = 1; a < nfe; a++) {
+				const double wgt = fabs(xde(a * vo));
+				for (int ii = 0; ii < vo; ii++) {
+					const int k = a * vo + ii;
+					aux(k) += tb_ws_apply(opPenR, sn, k) * wgt;
+				}
+			}
+			for (int k = 0; k < L; k++) {
+				F(3 * k + fc) -= aux(k);
+			}
+		}
+	}
+	F(3 * 0 + FW) = 0.0;
+	F(3 * L + FW) = 0.0;
+
+	// ---- BuildJacobianF_LOR_RhoTheta_Pi (:2977-3187) -------------------------
+	for (int j = 0; j < n; j++) {
+		for (int r = 0; r < ldab; r++) {
+			DG(r, j) = 0.0;
+		}
+	}
+	// MatFIx(c0,k0,c1,k1): column 3*k0+c0, row 3*k1+c1 (VerticalDynamicsFEM.h:110-119)
+#define TB_MAT(c0, k0, c1, k1) \
+	DG(2 * offd + (3 * (k1) + (c1)) - (3 * (k0) + (c0)), 3 * (k0) + (c0))
+
+	const double dInvDeltaT = 1.0 / ca.dt;
+
+	for (int k = 0; k < L; k++) {
+		const double invj = 1.0 / g.jac[g3 + (size_t)k * NN];
+		for (int m = opDiffE2N.begin[k]; m < opDiffE2N.end[k]; m++) {
+			const double je = g.jace[g3e + (size_t)m * NN];
+			const double dm = tb_op_coeff(opDiffE2N, k, m);
+			if ((m != 0) && (m != L)) {
+				const double dMassFluxCoeff =
+					dm * je * invj * g.cxe[2][g3e + (size_t)m * NN];
+				TB_MAT(FW, m, FP, k) += dMassFluxCoeff * seP(m);
+				TB_MAT(FW, m, FR, k) += dMassFluxCoeff * seR(m);
+			}
+			for (int q = opInterpN2E.begin[m]; q < opInterpN2E.end[m]; q++) {
+				const double dCoeffVerticalFlux =
+					dm * je * invj * tb_op_coeff(opInterpN2E, m, q) * xde(m);
+				TB_MAT(FR, q, FR, k) += dCoeffVerticalFlux;
+				TB_MAT(FP, q, FP, k) += dCoeffVerticalFlux;
+			}
+		}
+	}
+	for (int k = 1; k < L; k++) {
+		const double dRHSWCoeffA = seP(k) * ph.R / (seR(k) * ph.cv);
+		for (int m = opDiffN2E.begin[k]; m < opDiffN2E.end[k]; m++) {
+			TB_MAT(FP, m, FW, k) +=
+				dRHSWCoeffA * tb_op_coeff(opDiffN2E, k, m) * exn(m) / snP(m);
+		}
+		const double dRHSWCoeffB = 1.0 / (seR(k) * seR(k)) * dPe(k);
+		for (int q = opInterpN2E.begin[k]; q < opInterpN2E.end[k]; q++) {
+			const double dRHSWCoeffC = dRHSWCoeffB * tb_op_coeff(opInterpN2E, k, q);
+			TB_MAT(FP, q, FW, k) += dRHSWCoeffC * seR(k);
+			TB_MAT(FR, q, FW, k) += -dRHSWCoeffC * seP(k);
+		}
+	}
+	// dW_k/dW_m (Clark form)
+	for (int k = 1; k < L; k++) {
+		for (int l = opDiffN2E.begin[k]; l < opDiffN2E.end[k]; l++) {
+			for (int m = opInterpE2N.begin[l]; m < opInterpE2N.end[l]; m++) {
+				TB_MAT(FW, m, FW, k) +=
+					tb_op_coeff(opInterpE2N, l, m) * tb_op_coeff(opDiffN2E, k, l) * xdn(l);
+			}
+		}
+	}
+	// ---- BuildJacobianF_Diffusion (:2784-2973) -------------------------------
+	for (int c = 2; c < 5; c++) {
+		if (c == WIx) {
+			for (int k = 0; k <= L; k++) {
+				double dSignWeight;
+				const double cx2 = g.cxe[2][g3e + (size_t)k * NN];
+				if (xde(k) > 0.0) {
+					dSignWeight = 1.0 * cx2;
+				} else if (xde(k) < 0.0) {
+					dSignWeight = -1.0 * cx2;
+				} else {
+					dSignWeight = 0.0;
+				}
+				TB_MAT(FW, k, FW, k) -= ca.upwind_coeff * dSignWeight * ddW(k);
+			}
+			for (int k = 0; k <= L; k++) {
+				for (int q = opDDE2E.begin[k]; q < opDDE2E.end[k]; q++) {
+					TB_MAT(FW, q, FW, k) -=
+						ca.upwind_coeff * fabs(xde(k)) * tb_op_coeff(opDDE2E, k, q);
+				}
+			}
+		} else {
+			const WsAcc & sn = (c == PIx) ? snP : snR;
+			const int fc = (c == PIx) ? FP : FR;
+			for (int a = 1; a < nfe; a++) {
+				const int ke = a * vo;
+				const double xd = xde(ke);
+				const double dWeight = fabs(xd);
+				const double cx2 = g.cxe[2][g3e + (size_t)ke * NN];
+				double dSignWeight;
+				if (xd > 0.0) {
+					dSignWeight = 1.0 * cx2;
+				} else if (xd < 0.0) {
+					dSignWeight = -1.0 * cx2;
+				} else {
+					dSignWeight = 0.0;
+				}
+				const int kLeftBegin = (a - 1) * vo;
+				const int kLeftEnd = a * vo;
+				const int kRightBegin = a * vo;
+				const int kRightEnd = (a + 1) * vo;
+				for (int k = kLeftBegin; k < kLeftEnd; k++) {
+					for (int q = opPenL.begin[k]; q < opPenL.end[k]; q++) {
+						TB_MAT(FW, kLeftEnd, fc, k) -=
+							dSignWeight * tb_op_coeff(opPenL, k, q) * sn(q);
+					}
+				}
+				for (int k = kRightBegin; k < kRightEnd; k++) {
+					for (int q = opPenR.begin[k]; q < opPenR.end[k]; q++) {
+						TB_MAT(FW, kRightBegin, fc, k) -=
+							dSignWeight * tb_op_coeff(opPenR, k, q) * sn(q);
+					}
+				}
+				for (int k = kLeftBegin; k < kLeftEnd; k++) {
+					for (int q = opPenL.begin[k]; q < opPenL.end[k]; q++) {
+						TB_MAT(fc, q, fc, k) -= dWeight * tb_op_coeff(opPenL, k, q);
+					}
+				}
+				for (int k = kRightBegin; k < kRightEnd; k++) {
+					for (int q = opPenR.begin[k]; q < opPenR.end[k]; q++) {
+						TB_MAT(fc, q, fc, k) -= dWeight * tb_op_coeff(opPenR, k, q);
+					}
+				}
+			}
+		}
+	}
+	// identity components (:3172-3176)
+	for (int k = 0; k <= L; k++) {
+		TB_MAT(FP, k, FP, k) += dInvDeltaT;
+		TB_MAT(FW, k, FW, k) += dInvDeltaT;
+		TB_MAT(FR, k, FR, k) += dInvDeltaT;
+	}
+#undef TB_MAT
+
+	// ---- direct solve and update (:1457-1536) -------------------------------
+	const int r = tb_dgbsv(n, offd, offd, DG, F);
+	if (r != 0 || !(F(0) == F(0))) {
+		atomicMax(ca.info, ca.col0 + tcol + 1);
+	}
+
+	const int * dups = ca.col_dups + (size_t)(ca.col0 + tcol) * 3;
+	for (int q = -1; q < 3; q++) {
+		int tgt = node;
+		if (q >= 0) {
+			tgt = dups[q];
+			if (tgt < 0) continue;
+		}
+		const long long te = tgt / NN;
+		const int tn = tgt % NN;
+		const size_t tb = (size_t)te * lay.nrows * NN + tn;
+		double * oP = out + tb + (size_t)lay.rowoff[PIx] * NN;
+		double * oW = out + tb + (size_t)lay.rowoff[WIx] * NN;
+		double * oR = out + tb + (size_t)lay.rowoff[RIx] * NN;
+		for (int k = 0; k < L; k++) {
+			oP[(size_t)k * NN] = x0(3 * k + FP) - F(3 * k + FP);
+			oR[(size_t)k * NN] = x0(3 * k + FR) - F(3 * k + FR);
+		}
+		for (int k = 0; k <= L; k++) {
+			oW[(size_t)k * NN] = x0(3 * k + FW) - F(3 * k + FW);
+		}
+	}
+}
+
+#endif

@@ -1,0 +1,110 @@
+// Host-side context of the library (private).
+#ifndef TB200_CTX_H
+#define TB200_CTX_H
+
+#include <string>
+#include <vector>
+#include <map>
+#include <cstdint>
+
+#include "tb200_platform.h"
+#include "tb200_device.h"
+#include "../../include/tempest_b200.h"
+
+struct SeamEntry {
+	int ia, ib, src_panel;
+	double m[4];
+};
+
+struct PatchInfo {
+	int index, panel, nea, neb, halo, owner;
+	double da, db;
+	long long elem0;           // first local element, -1 when owned elsewhere
+	std::vector<int64_t> ids;  // [nea*np][neb*np] global node ids
+	std::vector<SeamEntry> seams;
+};
+
+struct HostOp {
+	int nout, nin, width;
+	std::vector<double> coeff;   // [nout][width]
+	std::vector<int> begin, end;
+	double * d_coeff;
+	int * d_begin;
+	int * d_end;
+	HostOp() : nout(0), nin(0), width(0), d_coeff(0), d_begin(0), d_end(0) {}
+};
+
+struct tb200_ctx {
+	tb200_config cfg;
+	std::string err;
+	cudaStream_t stream;
+	bool committed;
+	bool connectivity_built;
+
+	std::vector<PatchInfo> patches;
+	std::map<int, int> patch_pos;     // patch index -> position in patches
+
+	DevLayout lay;
+	DevTables tables;
+	DevOps ops;
+	DevGeom geom;
+	DevPhys phys;
+	HostOp hops[TB_NOPS];
+
+	std::vector<double *> inst;       // device state instances
+	std::vector<void *> allocs;       // everything to cudaFree
+
+	// staging for host <-> device layout conversion
+	double * d_stage;
+	size_t stage_doubles;
+	int * d_rowmap;
+
+	// mutable geometry arrays (device), same pointers as in geom
+	double * d_inv_da; double * d_inv_db; double * d_nu_scale;
+	double * g2d[7];
+	double * g3n[13];
+	double * g3e[13];
+	double * d_area_node;             // [e][L][NN] element area (checksum)
+	double * d_area_redge;            // [e][L+1][NN]
+	double * d_sums;
+
+	// averaging groups
+	int ngroups;
+	int * d_members; int * d_flags;
+	int nseam;
+	int * d_seam_group; double * d_seam_mats;
+	// multi-rank exchange
+	int rank, nranks;
+	tb200_exchange_fn exch_fn;
+	void * exch_user;
+	int nsend_total, nrecv_total;
+	std::vector<int64_t> send_count, recv_count;   // nodes per peer
+	int * d_send_nodes;
+	double * d_sendbuf; double * d_recvbuf;
+	size_t buf_rows;                  // rows per slot the buffers are sized for
+
+	// implicit column solve
+	int ncols;
+	int * d_col_node; int * d_col_dups;
+	double * d_ws; int ws_cols; int * d_info;
+	int offd;
+
+	int64_t launches;
+
+	tb200_ctx() :
+		stream(0), committed(false), connectivity_built(false),
+		d_stage(0), stage_doubles(0), d_rowmap(0),
+		d_inv_da(0), d_inv_db(0), d_nu_scale(0),
+		d_area_node(0), d_area_redge(0), d_sums(0),
+		ngroups(0), d_members(0), d_flags(0), nseam(0), d_seam_group(0),
+		d_seam_mats(0), rank(0), nranks(1), exch_fn(0), exch_user(0),
+		nsend_total(0), nrecv_total(0), d_send_nodes(0), d_sendbuf(0),
+		d_recvbuf(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0),
+		d_ws(0), ws_cols(0), d_info(0), offd(4), launches(0)
+	{
+		for (int i = 0; i < 7; i++) g2d[i] = 0;
+		for (int i = 0; i < 13; i++) { g3n[i] = 0; g3e[i] = 0; }
+	}
+};
+
+#endif

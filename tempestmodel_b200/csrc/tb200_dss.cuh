@@ -1,0 +1,159 @@
+// Direct stiffness summation and halo traffic.
+//
+// The reference copies one-node strips into patch halos (Grid::Exchange,
+// Grid.cpp:627-685; ExchangeBuffer::Pack/Unpack, Connectivity.cpp:47-744),
+// re-bases halo velocities at panel seams
+// (GridPatchCSGLL::TransformHaloVelocities, GridPatchCSGLL.cpp:1783-1924) and
+// then averages duplicates pairwise in alpha, then beta, with a 3-way average
+// at cube corners (GridCSGLL::ApplyDSS, GridCSGLL.cpp:435-781).  The net
+// effect on every physical node is the mean of its duplicates expressed in
+// the owner's basis.  The device has no halo: each physical node shared by
+// 2..4 element-local nodes is one *averaging group*; a thread gathers the
+// members, averages them in the reference's association order
+// (alpha pairs first, then beta) and scatters the result to the local members.
+// Members owned by other ranks are read from the receive buffer that the
+// exchange filled from the peers' packed send buffers.
+#ifndef TB200_DSS_CUH
+#define TB200_DSS_CUH
+
+#include "tb200_platform.h"
+#include "tb200_device.h"
+
+struct DssArgs {
+	const int * members;      // [ngroups][4], -1 = unused; >= nlocal: remote slot
+	const int * flags;        // [ngroups] bit0: group spans a panel seam
+	int ngroups;
+	int nlocal;               // number of local element nodes (nelem * NN)
+	const double * recv;      // [slot][nsel]
+	int row0, row1;           // rows averaged
+	int uv_row0, uv_row1;     // rows of (U,V) skipped for seam groups (vector path)
+	int nsel;                 // rows per remote slot in this exchange
+	int sel_row0;             // first row carried by the exchange
+};
+
+__device__ __forceinline__ double tb_dss_load(
+	const DevLayout & lay, const DssArgs & a, const double * data, int m, int r
+) {
+	if (m < a.nlocal) {
+		const int e = m / lay.nn;
+		const int n = m % lay.nn;
+		return data[((size_t)e * lay.nrows + r) * lay.nn + n];
+	}
+	return a.recv[(size_t)(m - a.nlocal) * a.nsel + (r - a.sel_row0)];
+}
+
+__global__ void k_dss_scalar(DevLayout lay, DssArgs a, double * data) {
+	const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (gidx >= a.ngroups) return;
+	const int m0 = a.members[4 * gidx + 0];
+	const int m1 = a.members[4 * gidx + 1];
+	const int m2 = a.members[4 * gidx + 2];
+	const int m3 = a.members[4 * gidx + 3];
+	const bool seam = (a.flags[gidx] & 1) != 0;
+	for (int r = a.row0 + blockIdx.y; r < a.row1; r += gridDim.y) {
+		if (seam && r >= a.uv_row0 && r < a.uv_row1) continue;
+		const double v0 = tb_dss_load(lay, a, data, m0, r);
+		const double v1 = tb_dss_load(lay, a, data, m1, r);
+		double avg;
+		if (m2 < 0) {
+			avg = 0.5 * (v0 + v1);
+		} else if (m3 < 0) {
+			const double v2 = tb_dss_load(lay, a, data, m2, r);
+			avg = (1.0 / 3.0) * (v0 + v1 + v2);
+		} else {
+			const double v2 = tb_dss_load(lay, a, data, m2, r);
+			const double v3 = tb_dss_load(lay, a, data, m3, r);
+			avg = 0.5 * (0.5 * (v0 + v1) + 0.5 * (v2 + v3));
+		}
+		const int ms[4] = {m0, m1, m2, m3};
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const int m = ms[q];
+			if (m >= 0 && m < a.nlocal) {
+				const int e = m / lay.nn;
+				const int n = m % lay.nn;
+				data[((size_t)e * lay.nrows + r) * lay.nn + n] = avg;
+			}
+		}
+	}
+}
+
+// Seam groups: (u_alpha, u_beta) of every member is re-based into each local
+// target's panel with the 2x2 matrix mats[sg][t][s] (identity when t and s are
+// on the same panel), restating CubedSphereTrans::CoVecPanelTrans
+// (CubedSphereTrans.h:1751-2275).
+struct SeamArgs {
+	const int * group;        // [nseam] index into the group list
+	const double * mats;      // [nseam][4][4][4]
+	int nseam;
+	int nlev_u;               // levels of U (and V)
+};
+
+__global__ void k_dss_seam_vector(DevLayout lay, DssArgs a, SeamArgs sa, double * data) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= sa.nseam * sa.nlev_u) return;
+	const int sg = idx / sa.nlev_u;
+	const int k = idx % sa.nlev_u;
+	const int gidx = sa.group[sg];
+	int ms[4];
+	double u[4], v[4];
+	int cnt = 0;
+	for (int q = 0; q < 4; q++) {
+		ms[q] = a.members[4 * gidx + q];
+		if (ms[q] >= 0) {
+			u[q] = tb_dss_load(lay, a, data, ms[q], a.uv_row0 + k);
+			v[q] = tb_dss_load(lay, a, data, ms[q], a.uv_row0 + sa.nlev_u + k);
+			cnt++;
+		} else {
+			u[q] = 0.0;
+			v[q] = 0.0;
+		}
+	}
+	const double * M = sa.mats + (size_t)sg * 64;
+	for (int tq = 0; tq < 4; tq++) {
+		const int m = ms[tq];
+		if (m < 0 || m >= a.nlocal) continue;
+		double tu[4], tv[4];
+		for (int s = 0; s < 4; s++) {
+			const double * mm = M + (tq * 4 + s) * 4;
+			tu[s] = mm[0] * u[s] + mm[1] * v[s];
+			tv[s] = mm[2] * u[s] + mm[3] * v[s];
+		}
+		double au, av;
+		if (cnt == 2) {
+			au = 0.5 * (tu[0] + tu[1]);
+			av = 0.5 * (tv[0] + tv[1]);
+		} else if (cnt == 3) {
+			au = (1.0 / 3.0) * (tu[0] + tu[1] + tu[2]);
+			av = (1.0 / 3.0) * (tv[0] + tv[1] + tv[2]);
+		} else {
+			au = 0.5 * (0.5 * (tu[0] + tu[1]) + 0.5 * (tu[2] + tu[3]));
+			av = 0.5 * (0.5 * (tv[0] + tv[1]) + 0.5 * (tv[2] + tv[3]));
+		}
+		const int e = m / lay.nn;
+		const int n = m % lay.nn;
+		data[((size_t)e * lay.nrows + a.uv_row0 + k) * lay.nn + n] = au;
+		data[((size_t)e * lay.nrows + a.uv_row0 + sa.nlev_u + k) * lay.nn + n] = av;
+	}
+}
+
+// Pack the local nodes other ranks need: send[slot][nsel] (Grid::Exchange
+// pack step, GridPatch.cpp:1292-1340).
+__global__ void k_dss_pack(
+	DevLayout lay, const int * send_nodes, int nsend,
+	const double * data, double * send, int row0, int nsel
+) {
+	const long long total = (long long)nsend * nsel;
+	for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	     idx < total; idx += (long long)gridDim.x * blockDim.x
+	) {
+		const int slot = (int)(idx / nsel);
+		const int r = (int)(idx % nsel);
+		const int m = send_nodes[slot];
+		const int e = m / lay.nn;
+		const int n = m % lay.nn;
+		send[idx] = data[((size_t)e * lay.nrows + row0 + r) * lay.nn + n];
+	}
+}
+
+#endif

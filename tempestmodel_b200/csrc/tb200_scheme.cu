@@ -1,0 +1,283 @@
+// TimestepScheme::Step on the device, and Grid::Checksum.
+//
+// Stage sequencing of the reference's time schemes: every Grid::CopyData /
+// LinearCombineData / StepExplicit / StepImplicit / PostProcessSubstage call
+// of the reference becomes the matching C-ABI call on device-resident state
+// instances, in the same order with the same coefficients.
+//   TimestepSchemeStrang::Step   reference TimestepSchemeStrang.cpp:450-674
+//   TimestepSchemeARS343::Step   reference TimestepSchemeARS343.cpp:146-235
+
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+#include "tb200_ctx.h"
+
+#define TB_FAIL(ctx, msg) \
+	do { (ctx)->err = (msg); return 1; } while (0)
+
+#define TB_CHECK(ctx, call) \
+	do { \
+		cudaError_t e__ = (call); \
+		if (e__ != cudaSuccess) { \
+			(ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__); \
+			return 1; \
+		} \
+	} while (0)
+
+#define TRY(call) do { if ((call) != 0) return 1; } while (0)
+
+static const int ALL = TB200_DATA_STATE | TB200_DATA_TRACERS;
+
+extern "C" int tb200_scheme_instances(int scheme) {
+	switch (scheme) {
+		case TB200_SCHEME_STRANG_KGU35:
+		case TB200_SCHEME_STRANG_RK4:
+		case TB200_SCHEME_STRANG_SSP3:
+		case TB200_SCHEME_STRANG_FE:
+			return 5;   // TimestepSchemeStrang.h:61-70
+		case TB200_SCHEME_ARS343:
+			return 7;   // TimestepSchemeARS343.h:49-58
+		default:
+			return -1;
+	}
+}
+
+// One explicit substage: H.StepExplicit, V.StepExplicit, DSS of state and
+// tracers (e.g. TimestepSchemeStrang.cpp:548-553).
+static int substage(tb200_ctx * ctx, int in, int out, double dt) {
+	TRY(tb200_hv_step_explicit(ctx, in, out, dt));
+	TRY(tb200_dss(ctx, out, ALL));
+	return 0;
+}
+
+static int lincomb(tb200_ctx * ctx, const std::vector<double> & c, int dst) {
+	return tb200_lincomb(ctx, c.data(), (int)c.size(), dst, ALL);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double dt) {
+	const double offc = ctx->cfg.off_centering;
+	const double half = 0.5 * dt;
+
+	// :470-482
+	if (first) {
+		TRY(tb200_v_step_implicit(ctx, 0, 0, half));
+	} else {
+		const std::vector<double> carry = {1.0, 1.0};
+		TRY(lincomb(ctx, carry, 0));
+		TRY(tb200_filter_negative_tracers(ctx, 0));
+	}
+
+	if (scheme == TB200_SCHEME_STRANG_FE) {
+		// :485-492
+		TRY(tb200_copy(ctx, 0, 4, ALL));
+		TRY(substage(ctx, 0, 4, dt));
+
+	} else if (scheme == TB200_SCHEME_STRANG_RK4) {
+		// :495-522
+		TRY(tb200_copy(ctx, 0, 1, ALL));
+		TRY(substage(ctx, 0, 1, half));
+		TRY(tb200_copy(ctx, 0, 2, ALL));
+		TRY(substage(ctx, 1, 2, half));
+		TRY(tb200_copy(ctx, 0, 3, ALL));
+		TRY(substage(ctx, 2, 3, dt));
+		const std::vector<double> rk4 = {-1.0 / 3.0, 1.0 / 3.0, 2.0 / 3.0, 1.0 / 3.0, 0.0};
+		TRY(lincomb(ctx, rk4, 4));
+		TRY(substage(ctx, 3, 4, dt / 6.0));
+
+	} else if (scheme == TB200_SCHEME_STRANG_SSP3) {
+		// :525-546
+		TRY(tb200_copy(ctx, 0, 1, ALL));
+		TRY(substage(ctx, 0, 1, dt));
+		const std::vector<double> a = {3.0 / 4.0, 1.0 / 4.0, 0.0};
+		TRY(lincomb(ctx, a, 2));
+		TRY(substage(ctx, 1, 2, 0.25 * dt));
+		const std::vector<double> b = {1.0 / 3.0, 0.0, 2.0 / 3.0, 0.0, 0.0};
+		TRY(lincomb(ctx, b, 4));
+		TRY(substage(ctx, 2, 4, (2.0 / 3.0) * dt));
+
+	} else {
+		// Kinnmark-Gray-Ullrich (3,5), :548-585
+		TRY(tb200_copy(ctx, 0, 1, ALL));
+		TRY(substage(ctx, 0, 1, dt / 5.0));
+		TRY(tb200_copy(ctx, 0, 2, ALL));
+		TRY(substage(ctx, 1, 2, dt / 5.0));
+		TRY(tb200_copy(ctx, 0, 3, ALL));
+		TRY(substage(ctx, 2, 3, dt / 3.0));
+		TRY(tb200_copy(ctx, 0, 2, ALL));
+		TRY(substage(ctx, 3, 2, 2.0 * dt / 3.0));
+		const std::vector<double> kgu = {-1.0 / 4.0, 5.0 / 4.0, 0.0, 0.0, 0.0};
+		TRY(lincomb(ctx, kgu, 4));
+		TRY(substage(ctx, 2, 4, 3.0 * dt / 4.0));
+	}
+
+	// hyperdiffusion, :638-641
+	TRY(tb200_copy(ctx, 4, 1, ALL));
+	TRY(tb200_h_step_after_subcycle(ctx, 4, 1, 2, dt));
+
+	// vertical step, :644-657
+	const double dOffCenterDeltaT = 0.5 * (1.0 + offc) * dt;
+	TRY(tb200_copy(ctx, 1, 0, ALL));
+	TRY(tb200_v_step_implicit(ctx, 0, 0, dOffCenterDeltaT));
+	const std::vector<double> oc = {(2.0 - offc) / 2.0, offc / 2.0};
+	TRY(lincomb(ctx, oc, 0));
+	if (!last) {
+		const std::vector<double> fin = {+1.0, -1.0};
+		TRY(lincomb(ctx, fin, 1));
+	}
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// ARS(3,4,3) of Ascher, Ruuth & Spiteri (1997): tableau and the stage
+// combinations that express each new stage base through stored instances
+// (reference TimestepSchemeARS343.cpp:30-141).
+
+struct ARS343Coefficients {
+	double diag_exp[4];
+	double diag_imp[4];
+	std::vector<double> u2, u3, u4;
+};
+
+static ARS343Coefficients ars343_coefficients() {
+	ARS343Coefficients k;
+	const double gam = 0.4358665215084590;
+	const double b1 = -1.5 * gam * gam + 4.0 * gam - 0.25;
+	const double b2 = 1.5 * gam * gam - 5.0 * gam + 1.25;
+	const double a42 = 0.5529291480359398;
+	const double a43 = 0.5529291480359398;
+	const double a31 =
+		(1.0 - 4.5 * gam + 1.5 * gam * gam) * a42
+		+ (2.75 - 10.5 * gam + 3.75 * gam * gam) * a43
+		- 3.5 + 13 * gam - 4.5 * gam * gam;
+	const double a32 =
+		(-1.0 + 4.5 * gam - 1.5 * gam * gam) * a42
+		+ (-2.75 + 10.5 * gam - 3.75 * gam * gam) * a43
+		+ 4.0 - 12.5 * gam + 4.5 * gam * gam;
+	const double a41 = 1.0 - a42 - a43;
+	// rows = stages 1..4, columns = earlier stages
+	const double I[4][4] = {
+		{gam, 0., 0., 0.},
+		{0.5 * (1.0 - gam), gam, 0., 0.},
+		{b1, b2, gam, 0.},
+		{b1, b2, gam, 0.}};
+	const double E[4][4] = {
+		{gam, 0., 0., 0.},
+		{a31, a32, 0., 0.},
+		{a41, a42, a43, 0.},
+		{0., b1, b2, gam}};
+	for (int s = 0; s < 4; s++) {
+		k.diag_exp[s] = E[s][s];
+		k.diag_imp[s] = I[s][s];
+	}
+	// raw combination of stage row r (1..3): instance 0 carries u^n, the pair
+	// (2j+1, 2j+2) carries the explicit / implicit result of stage j
+	std::vector<double> raw[4];
+	for (int r = 1; r < 4; r++) {
+		raw[r].assign(7, 0.0);
+		raw[r][0] = 1.0 - E[r][0] / E[0][0];
+		for (int j = 0; j < r; j++) {
+			raw[r][2 * j + 1] = E[r][j] / E[j][j] - I[r][j] / I[j][j];
+			raw[r][2 * j + 2] = I[r][j] / I[j][j];
+		}
+	}
+	// the explicit increment of a stage j >= 1 is measured from that stage's
+	// own base, itself a combination of earlier instances: fold it back
+	k.u2 = raw[1];
+	k.u3 = raw[2];
+	k.u4 = raw[3];
+	const double c37 = -E[2][1] / E[1][1];
+	for (int q = 0; q < 3; q++) k.u3[q] += c37 * k.u2[q];
+	const double c47 = -E[3][1] / E[1][1];
+	const double c48 = -E[3][2] / E[2][2];
+	for (int q = 0; q < 3; q++) k.u4[q] += c47 * k.u2[q] + c48 * k.u3[q];
+	for (int q = 3; q < 5; q++) k.u4[q] += c48 * k.u3[q];
+	return k;
+}
+
+static int step_ars343(tb200_ctx * ctx, int first, int last, double dt) {
+	(void)first;
+	(void)last;
+	static const ARS343Coefficients k = ars343_coefficients();
+	// :161-234
+	TRY(tb200_copy(ctx, 0, 1, ALL));
+	TRY(substage(ctx, 0, 1, k.diag_exp[0] * dt));
+	TRY(tb200_copy(ctx, 1, 2, ALL));
+	TRY(tb200_v_step_implicit(ctx, 2, 2, k.diag_imp[0] * dt));
+
+	TRY(lincomb(ctx, k.u2, 3));
+	TRY(substage(ctx, 2, 3, k.diag_exp[1] * dt));
+	TRY(tb200_copy(ctx, 3, 4, ALL));
+	TRY(tb200_v_step_implicit(ctx, 4, 4, k.diag_imp[1] * dt));
+
+	TRY(lincomb(ctx, k.u3, 5));
+	TRY(substage(ctx, 4, 5, k.diag_exp[2] * dt));
+	TRY(tb200_copy(ctx, 5, 6, ALL));
+	TRY(tb200_v_step_implicit(ctx, 6, 6, k.diag_imp[2] * dt));
+
+	TRY(lincomb(ctx, k.u4, 1));
+	TRY(substage(ctx, 6, 1, k.diag_exp[3] * dt));
+
+	TRY(tb200_copy(ctx, 1, 0, ALL));
+	TRY(tb200_h_step_after_subcycle(ctx, 1, 0, 2, dt));
+	return 0;
+}
+
+extern "C" int tb200_step(tb200_ctx * ctx, int scheme, int first, int last, double dt) {
+	const int need = tb200_scheme_instances(scheme);
+	if (need < 0) TB_FAIL(ctx, "time scheme not implemented");
+	if ((int)ctx->inst.size() < need) TB_FAIL(ctx, "not enough state instances for this scheme");
+	if (scheme == TB200_SCHEME_ARS343) {
+		return step_ars343(ctx, first, last, dt);
+	}
+	return step_strang(ctx, scheme, first, last, dt);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Grid::Checksum, ChecksumType_Sum (reference GridPatch.cpp:744-835,
+// Grid.cpp:460-524): area-weighted sum of every component.
+
+__global__ void k_checksum(
+	DevLayout lay, const double * data, const double * area_node,
+	const double * area_redge, double * sums
+) {
+	__shared__ double red[256];
+	const int c = blockIdx.y;
+	const int nn = lay.nn;
+	const int nl = lay.rowlev[c];
+	const double * area = lay.onedge[c] ? area_redge : area_node;
+	const long long per_e = (long long)nl * nn;
+	const long long total = lay.nelem * per_e;
+	double acc = 0.0;
+	for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	     idx < total; idx += (long long)gridDim.x * blockDim.x
+	) {
+		const long long e = idx / per_e;
+		const long long r = idx % per_e;
+		acc += data[((size_t)e * lay.nrows + lay.rowoff[c]) * nn + r] * area[(size_t)e * per_e + r];
+	}
+	red[threadIdx.x] = acc;
+	__syncthreads();
+	for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+		if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) atomicAdd(&sums[c], red[0]);
+}
+
+extern "C" int tb200_checksum(tb200_ctx * ctx, int inst, double * sums) {
+	if (ctx->d_area_node == 0) TB_FAIL(ctx, "element areas not uploaded");
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid state instance");
+	TB_CHECK(ctx, cudaMemsetAsync(ctx->d_sums, 0, 64 * sizeof(double), ctx->stream));
+	auto kfn = k_checksum;
+	TB_LAUNCH(kfn, dim3(148, ctx->lay.ncomp), dim3(256), 0, ctx->stream,
+		ctx->lay, (const double *)ctx->inst[inst], (const double *)ctx->d_area_node,
+		(const double *)ctx->d_area_redge, ctx->d_sums);
+	ctx->launches++;
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	TB_CHECK(ctx, cudaMemcpy(sums, ctx->d_sums, ctx->lay.ncomp * sizeof(double),
+		cudaMemcpyDeviceToHost));
+	return 0;
+}

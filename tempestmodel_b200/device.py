@@ -1,0 +1,216 @@
+"""Thin object wrapper over the C ABI (include/tempest_b200.h).
+
+Every method is one C-ABI call; arrays are numpy float64/int32/int64 in the
+reference's host layout.  Errors of the library are raised as
+:class:`TempestError` carrying ``tb200_last_error`` (the C++ shells raise the
+reference's ``Exception`` at the same places, src/base/Exception.h:25-49).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (DATA_ALL, DATA_STATE, DATA_TRACERS, EQN_PRIMITIVE_NONHYDRO,
+                   EQN_SHALLOW_WATER, OP_NAMES, SCHEMES)
+
+
+class TempestError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class DeviceContext:
+    """One tb200_ctx: the device-resident dynamical core of one rank."""
+
+    def __init__(self, library=None, **cfg):
+        self.lib = _lib.load(library)
+        c = _lib.Config()
+        onedge = cfg.pop("comp_on_redge", [0] * 8)
+        for k, v in cfg.items():
+            if not hasattr(c, k):
+                raise TypeError("unknown configuration field %r" % k)
+            setattr(c, k, v)
+        for i, v in enumerate(onedge):
+            c.comp_on_redge[i] = int(v)
+        self.cfg = c
+        self._h = ctypes.c_void_p()
+        rc = self.lib.tb200_create(ctypes.byref(c), ctypes.byref(self._h))
+        if rc != 0:
+            msg = self.lib.tb200_last_error(self._h).decode()
+            self.lib.tb200_destroy(self._h)
+            self._h = None
+            raise TempestError(msg)
+        self._keep = []
+        self.patches = {}
+
+    # -- plumbing ---------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise TempestError(self.lib.tb200_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.tb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.tb200_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._ck(self.lib.tb200_sync(self._h))
+
+    def check_errors(self):
+        self._ck(self.lib.tb200_check_errors(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.tb200_launch_count(self._h))
+
+    @property
+    def column_count(self):
+        return int(self.lib.tb200_column_count(self._h))
+
+    # -- grid -----------------------------------------------------------------
+    def set_exchange(self, rank, nranks, fn):
+        cb = _lib.EXCHANGE_FN(fn) if fn is not None else _lib.EXCHANGE_FN()
+        self._keep.append(cb)
+        self._ck(self.lib.tb200_set_exchange(self._h, rank, nranks, cb, None))
+
+    def add_patch(self, index, panel, nelem_a, nelem_b, halo, delta_a, delta_b,
+                  owner_rank=0):
+        self._ck(self.lib.tb200_add_patch(self._h, index, panel, nelem_a,
+                                          nelem_b, halo, delta_a, delta_b,
+                                          owner_rank))
+        self.patches[index] = dict(panel=panel, nelem_a=nelem_a,
+                                   nelem_b=nelem_b, halo=halo, owner=owner_rank)
+
+    def commit_layout(self):
+        self._ck(self.lib.tb200_commit_layout(self._h))
+
+    def set_tables(self, dx_basis, stiffness, gll_weights):
+        dx, st, w = _f64(dx_basis), _f64(stiffness), _f64(gll_weights)
+        self._ck(self.lib.tb200_set_tables(self._h, _ptr(dx), _ptr(st), _ptr(w)))
+
+    def set_column_op(self, op, coeff, begin, end):
+        if isinstance(op, str):
+            op = OP_NAMES.index(op)
+        coeff = _f64(coeff)
+        begin = np.ascontiguousarray(begin, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        self._ck(self.lib.tb200_set_column_op(
+            self._h, op, coeff.shape[0], coeff.shape[1], _ptr(coeff),
+            _ptr(begin), _ptr(end)))
+
+    def upload_geometry(self, patch, **arrays):
+        g = _lib.Geometry()
+        keep = []
+        for name in _lib.GEOMETRY_FIELDS:
+            a = _f64(arrays.get(name))
+            keep.append(a)
+            setattr(g, name, None if a is None else a.ctypes.data)
+        self._ck(self.lib.tb200_upload_geometry(self._h, patch, ctypes.byref(g)))
+
+    def upload_element_area(self, patch, area_node, area_redge):
+        a, b = _f64(area_node), _f64(area_redge)
+        self._ck(self.lib.tb200_upload_element_area(self._h, patch, _ptr(a), _ptr(b)))
+
+    def set_node_ids(self, patch, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self._ck(self.lib.tb200_set_node_ids(self._h, patch, _ptr(ids)))
+
+    def set_seam_transforms(self, patch, ia, ib, src_panel, mats):
+        ia = np.ascontiguousarray(ia, dtype=np.int32)
+        ib = np.ascontiguousarray(ib, dtype=np.int32)
+        sp = np.ascontiguousarray(src_panel, dtype=np.int32)
+        m = _f64(mats)
+        self._ck(self.lib.tb200_set_seam_transforms(
+            self._h, patch, len(ia), _ptr(ia), _ptr(ib), _ptr(sp), _ptr(m)))
+
+    def build_connectivity(self):
+        self._ck(self.lib.tb200_build_connectivity(self._h))
+
+    def exchange_counts(self, nranks):
+        s = np.zeros(nranks, dtype=np.int64)
+        r = np.zeros(nranks, dtype=np.int64)
+        self._ck(self.lib.tb200_exchange_counts(self._h, _ptr(s), _ptr(r)))
+        return s, r
+
+    # -- state ------------------------------------------------------------------
+    def upload_state(self, patch, inst, node=None, redge=None, tracers=None):
+        n, e, t = _f64(node), _f64(redge), _f64(tracers)
+        self._ck(self.lib.tb200_upload_state(self._h, patch, inst, _ptr(n),
+                                             _ptr(e), _ptr(t)))
+
+    def download_state(self, patch, inst, node=None, redge=None, tracers=None,
+                       fill_derived=True):
+        for a in (node, redge, tracers):
+            if a is not None:
+                assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.tb200_download_state(
+            self._h, patch, inst, _ptr(node), _ptr(redge), _ptr(tracers),
+            1 if fill_derived else 0))
+
+    def copy(self, src, dst, mask=DATA_ALL):
+        self._ck(self.lib.tb200_copy(self._h, src, dst, mask))
+
+    def lincomb(self, coeff, dst, mask=DATA_ALL):
+        c = _f64(coeff)
+        self._ck(self.lib.tb200_lincomb(self._h, _ptr(c), len(c), dst, mask))
+
+    def zero(self, inst, mask=DATA_ALL):
+        self._ck(self.lib.tb200_zero(self._h, inst, mask))
+
+    # -- dynamics ---------------------------------------------------------------
+    def h_step_explicit(self, i_in, i_out, dt):
+        self._ck(self.lib.tb200_h_step_explicit(self._h, i_in, i_out, dt))
+
+    def v_step_explicit(self, i_in, i_out, dt):
+        self._ck(self.lib.tb200_v_step_explicit(self._h, i_in, i_out, dt))
+
+    def hv_step_explicit(self, i_in, i_out, dt):
+        self._ck(self.lib.tb200_hv_step_explicit(self._h, i_in, i_out, dt))
+
+    def v_step_implicit(self, i_in, i_out, dt):
+        self._ck(self.lib.tb200_v_step_implicit(self._h, i_in, i_out, dt))
+
+    def dss(self, inst, mask=DATA_ALL):
+        self._ck(self.lib.tb200_dss(self._h, inst, mask))
+
+    def h_step_after_subcycle(self, i_in, i_out, i_work, dt):
+        self._ck(self.lib.tb200_h_step_after_subcycle(self._h, i_in, i_out,
+                                                      i_work, dt))
+
+    def step(self, scheme, first, last, dt):
+        if isinstance(scheme, str):
+            scheme = SCHEMES[scheme.lower()]
+        self._ck(self.lib.tb200_step(self._h, scheme, int(first), int(last), dt))
+
+    def checksum(self, inst):
+        s = np.zeros(self.cfg.ncomp, dtype=np.float64)
+        self._ck(self.lib.tb200_checksum(self._h, inst, _ptr(s)))
+        return s
+
+    def test_band_solve(self, ab, b, kl, ku):
+        ab = np.ascontiguousarray(ab, dtype=np.float64)
+        x = np.array(b, dtype=np.float64, order="C", copy=True)
+        ncols, n, _ = ab.shape
+        self._ck(self.lib.tb200_test_band_solve(self._h, ncols, n, kl, ku,
+                                                _ptr(ab), _ptr(x)))
+        return x
+
+
+__all__ = ["DeviceContext", "TempestError", "DATA_ALL", "DATA_STATE",
+           "DATA_TRACERS", "EQN_SHALLOW_WATER", "EQN_PRIMITIVE_NONHYDRO"]
