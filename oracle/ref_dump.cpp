@@ -14,7 +14,7 @@
 ///	                --script "op;op;..."  [reference command-line flags]
 ///
 ///	script ops (instances are the reference's state-instance indices):
-///	  dump:TAG              write every state/tracer instance of every patch
+///	  dump:TAG[,I,J..]      write every (or the listed) state/tracer instance
 ///	  hexp:IN,OUT,DT        HorizontalDynamics::StepExplicit
 ///	  vexp:IN,OUT,DT        VerticalDynamics::StepExplicit
 ///	  vimp:IN,OUT,DT        VerticalDynamics::StepImplicit
@@ -239,12 +239,15 @@ static void DumpGeometry(Model & model) {
 
 ///////////////////////////////////////////////////////////////////////////////
 
-static void DumpState(Model & model, const std::string & strTag) {
+static void DumpState(
+	Model & model, const std::string & strTag, int iOnly = -1
+) {
 	Grid * pGrid = model.GetGrid();
 	const EquationSet & eqn = model.GetEquationSet();
 	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
 		GridPatch * pPatch = pGrid->GetActivePatch(n);
 		for (int m = 0; m < model.GetComponentDataInstances(); m++) {
+			if ((iOnly >= 0) && (m != iOnly)) continue;
 			char buf[128];
 			snprintf(buf, 128, "%s.patch%d.inst%d.", strTag.c_str(), n, m);
 			Write4D(std::string(buf) + "node",
@@ -254,6 +257,7 @@ static void DumpState(Model & model, const std::string & strTag) {
 		}
 		if (eqn.GetTracers() != 0) {
 			for (int m = 0; m < model.GetTracerDataInstances(); m++) {
+				if ((iOnly >= 0) && (m != iOnly)) continue;
 				char buf[128];
 				snprintf(buf, 128, "%s.patch%d.inst%d.", strTag.c_str(), n, m);
 				Write4D(std::string(buf) + "tracers",
@@ -293,7 +297,13 @@ static void RunScript(Model & model, const std::string & strScript) {
 		if (kv.size() > 1) a = Split(kv[1], ',');
 
 		if (op == "dump") {
-			DumpState(model, a[0]);
+			if (a.size() > 1) {
+				for (size_t i = 1; i < a.size(); i++) {
+					DumpState(model, a[0], atoi(a[i].c_str()));
+				}
+			} else {
+				DumpState(model, a[0]);
+			}
 		} else if (op == "hexp") {
 			pH->StepExplicit(atoi(a[0].c_str()), atoi(a[1].c_str()), time, atof(a[2].c_str()));
 		} else if (op == "vexp") {

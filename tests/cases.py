@@ -1,0 +1,62 @@
+"""Golden cases: reference runs through oracle/_ref/ref_dump whose outputs are
+committed under tests/golden/ (regenerate with `python tests/make_golden.py`
+in a container that has /root/reference; the GPU box only reads the files)."""
+import os
+
+import numpy as np
+
+import refdump
+
+GOLDEN = refdump.GOLDEN
+
+KGU = "-0.25,1.25,0,0,0"
+
+CASES = {
+    # shallow water, Williamson 2 (reduced to ne=2)
+    "sw2_ne2": dict(
+        case="sw2", flags=["--resolution", "2"],
+        script=";".join([
+            "dump:ic,0", "copy:0,1", "hexp:0,1,100", "dump:h1,1", "dss:1", "dump:dss,1",
+            "copy:1,4", "hasc:4,1,2,200", "dump:hasc,1,2",
+            "lincomb:3,0.25,1.5,0,0.5,-1", "dump:lc,3",
+            "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
+            "step:2", "dump:st,0,1", "checksum:cs"])),
+    # nonhydrostatic, Jablonowski-Williamson (config 3, reduced)
+    "jw_ne2_l6": dict(
+        case="jw", flags=["--resolution", "2", "--levels", "6"],
+        script=";".join([
+            "dump:ic,0", "copy:0,1", "hexp:0,1,50", "dump:h1,1", "vexp:0,1,50",
+            "dump:v1,1", "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,30",
+            "dump:vi,2", "hasc:1,3,4,200", "dump:hasc,3,4"])),
+    "jw_ne2_l6_strang": dict(
+        case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s"],
+        script="dump:ic,0;step:2;dump:st,0,1;checksum:cs"),
+    "jw_ne2_l6_ars343": dict(
+        case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s",
+                          "--timescheme", "ars343"],
+        script="dump:ic,0;step:2;dump:st,0;checksum:cs"),
+}
+
+
+def golden_path(name):
+    return os.path.join(GOLDEN, name + ".npz")
+
+
+def load_case(name):
+    """Golden dump of a case: the committed file, else a fresh reference run."""
+    path = golden_path(name)
+    if os.path.exists(path):
+        with np.load(path) as z:
+            return {k: z[k] for k in z.files}
+    if not refdump.have_ref_dump():
+        raise FileNotFoundError("golden file %s missing and oracle/_ref/ref_dump not built" % path)
+    c = CASES[name]
+    return refdump.run_ref_dump("/tmp/tb200_%s.bin" % name, c["case"], c["script"], c["flags"])
+
+
+def write_golden(name):
+    c = CASES[name]
+    d = refdump.run_ref_dump("/tmp/tb200_%s.bin" % name, c["case"], c["script"], c["flags"])
+    os.makedirs(GOLDEN, exist_ok=True)
+    np.savez_compressed(golden_path(name), **d)
+    return golden_path(name)

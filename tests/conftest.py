@@ -1,0 +1,41 @@
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+
+
+def _cuda_available():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def emu_library():
+    """Host emulation build of the kernel sources (tests only)."""
+    path = os.path.join(HERE, "emu", "libtb200_emu.so")
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tempestmodel_b200", "csrc"), "emu"])
+    return path
+
+
+@pytest.fixture(scope="session")
+def cuda_library():
+    """The product library; GPU tests fail loudly when it is missing."""
+    from tempestmodel_b200 import PRODUCT_LIBRARY
+    assert os.path.exists(PRODUCT_LIBRARY), "libtempest_b200.so missing: run __graft_entry__.build()"
+    assert _cuda_available(), "no CUDA device"
+    return PRODUCT_LIBRARY

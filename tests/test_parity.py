@@ -1,0 +1,171 @@
+"""Parity of the device path with the unmodified reference (oracle/_ref) on
+the committed golden cases.  Each check runs twice from the same body:
+ - backend "emu"  (not gpu): the kernel sources compiled for the host through
+   tests/emu/cuda_emu.h - kernel logic, indexing, connectivity;
+ - backend "cuda" (gpu): the product library libtempest_b200.so on the B200,
+   called through the C ABI.
+
+Tolerances (FP64): the north star asks per-stage tendencies to agree within
+1e-12 relative; every explicit stage is held to 1e-12 of the largest tendency
+of the component.  The implicit column solve goes through a different LAPACK
+build than the reference's (OpenBLAS, FMA kernels), so it is held to 1e-10 of
+the largest change of the component; multi-step states to 1e-10 of the field.
+"""
+import numpy as np
+import pytest
+
+import cases
+import dumpctx
+
+BACKENDS = [pytest.param("emu"), pytest.param("cuda", marks=pytest.mark.gpu)]
+
+TOL_STAGE = 1e-12
+TOL_IMPLICIT = 1e-10
+TOL_DSS = 1e-14
+TOL_STATE = 1e-10
+
+
+@pytest.fixture(params=BACKENDS)
+def library(request):
+    if request.param == "emu":
+        return request.getfixturevalue("emu_library")
+    return request.getfixturevalue("cuda_library")
+
+
+def tendency_errors(ctx, d, inst, tag, before_tag, before_inst, node, redge=(),
+                    scale=None):
+    """max |dev - ref| / max |ref - ref_before| per component.  `scale`
+    = (tag, inst) takes the normalising tendency from another record (the
+    element-wise tendencies before DSS: for balanced flows they cancel to
+    rounding noise once averaged)."""
+    got = dumpctx.download(ctx, d, inst)
+    out = {}
+    for loc, comps in (("node", node), ("redge", redge)):
+        for c in comps:
+            num = den = 0.0
+            for n in ctx.local_patches:
+                ref = dumpctx.interior(d["%s.patch%d.inst%d.%s" % (tag, n, inst, loc)])[c]
+                sc = ref if scale is None else dumpctx.interior(
+                    d["%s.patch%d.inst%d.%s" % (scale[0], n, scale[1], loc)])[c]
+                bef = dumpctx.interior(d["%s.patch%d.inst%d.%s" % (before_tag, n, before_inst, loc)])[c]
+                dev = dumpctx.interior(got[n][0 if loc == "node" else 1])[c]
+                num = max(num, np.abs(dev - ref).max())
+                den = max(den, np.abs(sc - bef).max())
+            out[(loc, c)] = num / den if den > 0 else num
+    return out
+
+
+def assert_below(errs, tol):
+    bad = {k: v for k, v in errs.items() if not (v <= tol)}
+    assert not bad, "parity errors above %g: %r" % (tol, bad)
+
+
+def test_shallow_water_stages(library):
+    d = cases.load_case("sw2_ne2")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    # upload / download round trip is exact
+    assert_below(dumpctx.compare(ctx, d, 0, "ic", [0, 1, 2]), 0.0)
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 100.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2]), TOL_STAGE)
+    ctx.dss(1)
+    # DSS acts on the state (velocities are re-based with 2x2 matrices at
+    # seams): rounding is relative to the field, not to its tendency
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2]), TOL_DSS)
+    assert_below(tendency_errors(ctx, d, 1, "dss", "ic", 0, [0, 1, 2],
+                                 scale=("h1", 1)), 1e-10)
+    ctx.copy(1, 4)
+    ctx.h_step_after_subcycle(4, 1, 2, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 1, "hasc", [0, 1, 2]), 1e-13)
+    assert_below(dumpctx.compare(ctx, d, 2, "hasc", [0, 1, 2]), 1e-12)
+    ctx.lincomb([0.25, 1.5, 0, 0.5, -1], 3)
+    assert_below(dumpctx.compare(ctx, d, 3, "lc", [0, 1, 2]), 1e-14)
+    ctx.close()
+
+
+def test_shallow_water_steps(library):
+    d = cases.load_case("sw2_ne2")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, 5):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2]), TOL_STATE)
+    cs = ctx.checksum(0)
+    # V sums to rounding noise of the U-sized terms: absolute tolerance
+    assert np.allclose(cs, d["cs.checksum"], rtol=1e-12,
+                       atol=1e-12 * np.abs(d["cs.checksum"]).max())
+    ctx.close()
+
+
+def test_nonhydro_stages(library):
+    d = cases.load_case("jw_ne2_l6")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    assert_below(dumpctx.compare(ctx, d, 0, "ic", [0, 1, 2, 4], [3]), 0.0)
+    ctx.copy(0, 1)
+    # HorizontalDynamicsFEM::StepExplicit
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    # VerticalDynamicsFEM::StepExplicit on top of it
+    ctx.v_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    # the fused pass gives the same answer as the two plugin calls
+    ctx.copy(0, 3)
+    ctx.hv_step_explicit(0, 3, 50.0)
+    a = dumpctx.download(ctx, d, 1)
+    b = dumpctx.download(ctx, d, 3)
+    for n in ctx.local_patches:
+        assert np.array_equal(a[n][0], b[n][0]) and np.array_equal(a[n][1], b[n][1])
+    # DSS incl. covector re-basing at panel seams
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    assert_below(tendency_errors(ctx, d, 1, "dss", "ic", 0, [0, 1, 2, 4], [3],
+                                 scale=("v1", 1)), 1e-10)
+    # VerticalDynamicsFEM::StepImplicit
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3]), TOL_IMPLICIT)
+    assert_below(dumpctx.compare(ctx, d, 2, "vi", [0, 1, 2, 4], [3]), 1e-12)
+    # StepAfterSubCycle (order-4 hyperdiffusion + 2 DSS)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    assert_below(dumpctx.compare(ctx, d, 4, "hasc", [0, 1, 2, 4], [3]), 1e-11)
+    ctx.close()
+
+
+@pytest.mark.parametrize("scheme", ["strang", "ars343"])
+def test_nonhydro_steps(library, scheme):
+    d = cases.load_case("jw_ne2_l6_%s" % scheme)
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step(scheme, True, False, 200.0)
+    ctx.step(scheme, False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    cs = ctx.checksum(0)
+    ref = d["cs.checksum"]
+    # mass (rho) and rho-theta checksums match the reference
+    assert abs(cs[4] - ref[4]) <= 1e-13 * abs(ref[4])
+    assert abs(cs[2] - ref[2]) <= 1e-13 * abs(ref[2])
+    ctx.close()
+
+
+def test_error_conventions(library):
+    """Argument errors surface with the reference's messages."""
+    from tempestmodel_b200 import TempestError
+    d = cases.load_case("sw2_ne2")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    with pytest.raises(TempestError, match="iDataInitial != iDataUpdate"):
+        ctx.h_step_explicit(1, 1, 1.0)
+    with pytest.raises(TempestError, match="must be distinct"):
+        ctx.h_step_after_subcycle(0, 1, 1, 1.0)
+    with pytest.raises(TempestError, match="Invalid"):
+        ctx.copy(0, 99)
+    ctx.close()
