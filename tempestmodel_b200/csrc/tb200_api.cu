@@ -781,6 +781,7 @@ extern "C" int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 		return 0;   // VerticalDynamicsStub (TempestInitialize.h:362-364)
 	}
 	if (ctx->cfg.fully_explicit) TB_FAIL(ctx, "--explicitvertical is not supported");
+	if (in == out) TB_FAIL(ctx, "VerticalDynamics StepExplicit must have iDataInitial != iDataUpdate");
 	return nh_launch(ctx, in, out, dt, false, true);
 }
 
@@ -1241,6 +1242,10 @@ extern "C" int tb200_test_band_solve(
 	tb200_ctx * ctx, int ncols, int n, int kl, int ku, const double * ab, double * b
 ) {
 	const int ldab = 2 * kl + ku + 1;
+	if (ctx->d_info == 0) {
+		if (dalloc(ctx, &ctx->d_info, 4)) return 1;
+		TB_CHECK(ctx, cudaMemset(ctx->d_info, 0, 4 * sizeof(int)));
+	}
 	// host [col][n][ldab] -> device [(j*ldab + r)][col]
 	std::vector<double> hab((size_t)ncols * n * ldab), hb((size_t)ncols * n);
 	for (int c = 0; c < ncols; c++) {

@@ -179,7 +179,7 @@ __device__ __forceinline__ double tb_op_coeff(const DevOp & op, int k, int l) {
 
 __global__ void k_column_implicit(
 	DevLayout lay, DevGeom g, DevOps ops, DevPhys ph, ColumnArgs ca,
-	const double * __restrict__ in, double * __restrict__ out
+	const double * in, double * out   // may alias: StepImplicit(i, i, ...)
 ) {
 	const int tcol = blockIdx.x * blockDim.x + threadIdx.x;
 	if (tcol >= ca.ncols) return;

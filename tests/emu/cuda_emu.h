@@ -247,7 +247,9 @@ inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int * d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int * n) { *n = 1; return cudaSuccess; }
-inline cudaError_t cudaMalloc(void ** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? cudaSuccess : cudaErrorEmu; }
+// fresh device memory is NOT zero: poison it (NaN pattern) so that reads of
+// never-written entries show up in the emulated tests
+inline cudaError_t cudaMalloc(void ** p, size_t n) { *p = malloc(n ? n : 1); if (*p) memset(*p, 0xFF, n ? n : 1); return *p ? cudaSuccess : cudaErrorEmu; }
 inline cudaError_t cudaFree(void * p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMallocHost(void ** p, size_t n) { *p = malloc(n ? n : 1); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void * p) { free(p); return cudaSuccess; }
