@@ -268,6 +268,13 @@ int64_t tb200_column_count(const tb200_ctx * ctx);
 int tb200_test_band_solve(tb200_ctx * ctx, int ncols, int n, int kl, int ku,
                           const double * ab, double * b);
 
+/* Debugging aid (cf. USE_JACOBIAN_DEBUG / BootstrapJacobian,
+ * VerticalDynamicsFEM.cpp:1163-1226): assemble F and the banded Jacobian of
+ * the implicit solve for instance `in` without solving and return the work
+ * arrays of unique column `col` (24 arrays of nlev+1, x0, F, band matrix). */
+int tb200_debug_column_assembly(tb200_ctx * ctx, int in, double dt, int col,
+                                double * ws_out, int nentries);
+
 #ifdef __cplusplus
 }
 #endif

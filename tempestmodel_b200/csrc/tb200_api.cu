@@ -817,6 +817,7 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 	// m_dUpwindCoeff (VerticalDynamicsFEM.cpp:520-521)
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
+	ca.assemble_only = 0;
 	for (int c0 = 0; c0 < ctx->ncols; c0 += ctx->ws_cols) {
 		ca.col0 = c0;
 		ca.ncols = std::min(ctx->ws_cols, ctx->ncols - c0);
@@ -826,6 +827,46 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 			lay, ctx->geom, ctx->ops, ctx->phys, ca,
 			(const double *)ctx->inst[in], ctx->inst[out]);
 		TB_KERNEL_CHECK(ctx);
+	}
+	return 0;
+}
+
+// Debugging aid: assemble F and the banded Jacobian of the first launch chunk
+// without solving and copy the workspace of one column back
+// (cf. USE_JACOBIAN_DEBUG / BootstrapJacobian, VerticalDynamicsFEM.cpp:1163-1226).
+extern "C" int tb200_debug_column_assembly(
+	tb200_ctx * ctx, int in, double dt, int col, double * ws_out, int nentries
+) {
+	// nentries < 0: also run the band solve (F then holds the Newton update)
+	const int mode = (nentries < 0) ? 2 : 1;
+	if (nentries < 0) nentries = -nentries;
+	if (check_ops(ctx)) return 1;
+	const DevLayout & lay = ctx->lay;
+	ColumnArgs ca;
+	ca.col_node = ctx->d_col_node;
+	ca.col_dups = ctx->d_col_dups;
+	ca.ws = ctx->d_ws;
+	ca.ws_stride = ctx->ws_cols;
+	ca.dt = dt;
+	ca.offd = ctx->offd;
+	ca.fe_nodes = ctx->cfg.vertical_order;
+	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
+	ca.info = ctx->d_info;
+	ca.assemble_only = mode;
+	ca.col0 = 0;
+	ca.ncols = std::min(ctx->ws_cols, ctx->ncols);
+	if (col < 0 || col >= ca.ncols) TB_FAIL(ctx, "column out of range");
+	auto kfn = k_column_implicit;
+	TB_LAUNCH_FLAT(kfn, dim3((ca.ncols + 63) / 64), dim3(64), 0, ctx->stream,
+		lay, ctx->geom, ctx->ops, ctx->phys, ca,
+		(const double *)ctx->inst[in], ctx->inst[in]);
+	TB_KERNEL_CHECK(ctx);
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	const int total = tb_column_ws_entries(lay.nlev, ctx->offd);
+	std::vector<double> all((size_t)total * ctx->ws_cols);
+	TB_CHECK(ctx, cudaMemcpy(all.data(), ctx->d_ws, all.size() * sizeof(double), cudaMemcpyDeviceToHost));
+	for (int q = 0; q < nentries && q < total; q++) {
+		ws_out[q] = all[(size_t)q * ctx->ws_cols + col];
 	}
 	return 0;
 }

@@ -34,6 +34,7 @@ struct ColumnArgs {
 	int fe_nodes;           // nodes per vertical finite element
 	double upwind_coeff;    // m_dUpwindCoeff
 	int * info;             // device flag: first failing column + 1
+	int assemble_only;      // debugging: stop before the solve
 };
 
 // number of workspace entries per column
@@ -492,11 +493,15 @@ __global__ void k_column_implicit(
 	}
 #undef TB_MAT
 
+	if (ca.assemble_only == 1) return;
+
 	// ---- direct solve and update (:1457-1536) -------------------------------
 	const int r = tb_dgbsv(n, offd, offd, DG, F);
 	if (r != 0 || !(F(0) == F(0))) {
 		atomicMax(ca.info, ca.col0 + tcol + 1);
 	}
+
+	if (ca.assemble_only == 2) return;
 
 	const int * dups = ca.col_dups + (size_t)(ca.col0 + tcol) * 3;
 	for (int q = -1; q < 3; q++) {

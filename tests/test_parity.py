@@ -33,7 +33,7 @@ def library(request):
 
 
 def tendency_errors(ctx, d, inst, tag, before_tag, before_inst, node, redge=(),
-                    scale=None):
+                    scale=None, skip_poles=False):
     """max |dev - ref| / max |ref - ref_before| per component.  `scale`
     = (tag, inst) takes the normalising tendency from another record (the
     element-wise tendencies before DSS: for balanced flows they cancel to
@@ -49,6 +49,9 @@ def tendency_errors(ctx, d, inst, tag, before_tag, before_inst, node, redge=(),
                     d["%s.patch%d.inst%d.%s" % (scale[0], n, scale[1], loc)])[c]
                 bef = dumpctx.interior(d["%s.patch%d.inst%d.%s" % (before_tag, n, before_inst, loc)])[c]
                 dev = dumpctx.interior(got[n][0 if loc == "node" else 1])[c]
+                if skip_poles:
+                    m = dumpctx.pole_mask(d, n)
+                    ref, sc, bef, dev = ref[m], sc[m], bef[m], dev[m]
                 num = max(num, np.abs(dev - ref).max())
                 den = max(den, np.abs(sc - bef).max())
             out[(loc, c)] = num / den if den > 0 else num
@@ -125,12 +128,18 @@ def test_nonhydro_stages(library):
     assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
     assert_below(tendency_errors(ctx, d, 1, "dss", "ic", 0, [0, 1, 2, 4], [3],
                                  scale=("v1", 1)), 1e-10)
-    # VerticalDynamicsFEM::StepImplicit
+    # VerticalDynamicsFEM::StepImplicit.  The two pole columns are left out:
+    # there u = v = w = 0, xi-dot is pure rounding noise and the reference's
+    # Jacobian carries sign(xi-dot) (VerticalDynamicsFEM.cpp:2876-2884), so the
+    # Newton update of those columns flips with the last bit of the input -
+    # for the reference itself as much as for the device.
     ctx.copy(1, 2)
     ctx.v_step_implicit(2, 2, 30.0)
     ctx.check_errors()
-    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3]), TOL_IMPLICIT)
-    assert_below(dumpctx.compare(ctx, d, 2, "vi", [0, 1, 2, 4], [3]), 1e-12)
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=True), TOL_IMPLICIT)
+    assert_below(dumpctx.compare(ctx, d, 2, "vi", [0, 1, 2, 4], [3],
+                                 skip_poles=True), 1e-12)
     # StepAfterSubCycle (order-4 hyperdiffusion + 2 DSS)
     ctx.h_step_after_subcycle(1, 3, 4, 200.0)
     assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
