@@ -24,6 +24,7 @@
 ///	  lincomb:DST,c0,c1,..  Grid::LinearCombineData (State and Tracers)
 ///	  step:N                N calls of TimestepScheme::Step (first = first call)
 ///	  checksum:TAG          Grid::Checksum of instance 0 -> record
+///	  addw:INST,AMP         test data: add a smooth non-zero W on interfaces
 ///
 ///	The test-case classes live in the reference's driver sources next to a
 ///	main(); they are included (not copied) with main renamed.
@@ -303,6 +304,32 @@ static void RunScript(Model & model, const std::string & strScript) {
 				}
 			} else {
 				DumpState(model, a[0]);
+			}
+		} else if (op == "addw") {
+			// Test-data helper: add a smooth, everywhere non-zero vertical
+			// velocity to interior interfaces of one instance so that xi-dot
+			// is nowhere rounding noise (the reference's Jacobian carries
+			// sign(xi-dot), VerticalDynamicsFEM.cpp:2876-2884, which makes
+			// columns of exactly zero wind - JW equator and poles - flip
+			// with the last bit of their input).
+			const int iInst = atoi(a[0].c_str());
+			const double dAmp = atof(a[1].c_str());
+			const int nL = pGrid->GetRElements();
+			for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+				GridPatch * pPatch = pGrid->GetActivePatch(n);
+				DataArray4D<double> & dataREdge =
+					pPatch->GetDataState(iInst, DataLocation_REdge);
+				const DataArray2D<double> & dLon = pPatch->GetLongitude();
+				const DataArray2D<double> & dLat = pPatch->GetLatitude();
+				for (int i = 0; i < dataREdge.GetSize(1); i++) {
+				for (int j = 0; j < dataREdge.GetSize(2); j++) {
+				for (int k = 1; k < nL; k++) {
+					dataREdge(3,i,j,k) += dAmp
+						* (1.0 + 0.5 * sin(dLon(i,j)) * cos(dLat(i,j)))
+						* sin(M_PI * static_cast<double>(k) / static_cast<double>(nL));
+				}
+				}
+				}
 			}
 		} else if (op == "hexp") {
 			pH->StepExplicit(atoi(a[0].c_str()), atoi(a[1].c_str()), time, atof(a[2].c_str()));
