@@ -25,6 +25,7 @@
 ///	  step:N                N calls of TimestepScheme::Step (first = first call)
 ///	  checksum:TAG          Grid::Checksum of instance 0 -> record
 ///	  addw:INST,AMP         test data: add a smooth non-zero W on interfaces
+///	  perturb:INST,EPS      test data: relative pseudo-random noise of size EPS
 ///
 ///	The test-case classes live in the reference's driver sources next to a
 ///	main(); they are included (not copied) with main renamed.
@@ -329,6 +330,27 @@ static void RunScript(Model & model, const std::string & strScript) {
 						* sin(M_PI * static_cast<double>(k) / static_cast<double>(nL));
 				}
 				}
+				}
+			}
+		} else if (op == "perturb") {
+			// Test-data helper: multiply every state value of one instance by
+			// (1 + EPS * r), r a fixed pseudo-random sequence in [-1,1]; used to
+			// measure the reference's own sensitivity to last-bit changes.
+			const int iInst = atoi(a[0].c_str());
+			const double dEps = atof(a[1].c_str());
+			unsigned long long u = 88172645463325252ull;
+			for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+				GridPatch * pPatch = pGrid->GetActivePatch(n);
+				for (int l = 0; l < 2; l++) {
+					DataArray4D<double> & data = pPatch->GetDataState(
+						iInst, (l == 0) ? DataLocation_Node : DataLocation_REdge);
+					double * p = &(data(0,0,0,0));
+					const size_t nTotal = data.GetTotalSize();
+					for (size_t q = 0; q < nTotal; q++) {
+						u ^= u << 13; u ^= u >> 7; u ^= u << 17;
+						const double r = 2.0 * (double)(u >> 11) / 9007199254740992.0 - 1.0;
+						p[q] *= (1.0 + dEps * r);
+					}
 				}
 			}
 		} else if (op == "hexp") {

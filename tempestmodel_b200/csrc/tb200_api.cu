@@ -474,6 +474,30 @@ extern "C" int tb200_upload_element_area(
 ///////////////////////////////////////////////////////////////////////////////
 // State movement
 
+// Interior of one component slice <-> staging copy: (wa-2) rows of
+// (wb-2)*nlev contiguous doubles, pitch wb*nlev; halo entries are not touched
+// on either side.
+static int copy_interior(
+	tb200_ctx * ctx, const PatchInfo & pi, double * host, size_t comp,
+	int host_nlev, bool to_device
+) {
+	const int np = ctx->lay.np;
+	const size_t wa = pi.nea * np + 2 * pi.halo;
+	const size_t wb = pi.neb * np + 2 * pi.halo;
+	const size_t slice = wa * wb * host_nlev;
+	const size_t pitch = wb * host_nlev * sizeof(double);
+	const size_t width = (wb - 2 * pi.halo) * host_nlev * sizeof(double);
+	const size_t off = comp * slice + ((size_t)pi.halo * wb + pi.halo) * host_nlev;
+	if (to_device) {
+		TB_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_stage + off, pitch, host + off, pitch,
+			width, wa - 2 * pi.halo, cudaMemcpyHostToDevice, ctx->stream));
+	} else {
+		TB_CHECK(ctx, cudaMemcpy2DAsync(host + off, pitch, ctx->d_stage + off, pitch,
+			width, wa - 2 * pi.halo, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	return 0;
+}
+
 static int move_state_array(
 	tb200_ctx * ctx, const PatchInfo & pi, int inst, double * host,
 	int ncomp_host, int host_nlev, const std::vector<int> & rowmap, bool to_device
@@ -484,14 +508,15 @@ static int move_state_array(
 	const size_t wb = pi.neb * np + 2 * pi.halo;
 	const size_t slice = wa * wb * host_nlev;
 	if (slice * ncomp_host > ctx->stage_doubles) TB_FAIL(ctx, "staging buffer too small");
+	// the previous user of the staging buffer / row map must be done
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
 	TB_CHECK(ctx, cudaMemcpyAsync(ctx->d_rowmap, rowmap.data(), ncomp_host * sizeof(int),
 		cudaMemcpyHostToDevice, ctx->stream));
 	const size_t smem = (size_t)host_nlev * (nn + 1) * sizeof(double);
 	if (to_device) {
 		for (int c = 0; c < ncomp_host; c++) {
 			if (rowmap[c] < 0) continue;
-			TB_CHECK(ctx, cudaMemcpyAsync(ctx->d_stage + c * slice, host + c * slice,
-				slice * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+			if (copy_interior(ctx, pi, host, c, host_nlev, true)) return 1;
 		}
 		auto kfn = k_transpose_state<true>;
 		TB_LAUNCH(kfn, dim3(pi.nea * pi.neb), dim3(256), smem, ctx->stream,
@@ -514,25 +539,10 @@ static int stage_to_host(
 	tb200_ctx * ctx, const PatchInfo & pi, double * host, int host_nlev,
 	const std::vector<int> & comps
 ) {
-	const int np = ctx->lay.np;
-	const size_t wa = pi.nea * np + 2 * pi.halo;
-	const size_t wb = pi.neb * np + 2 * pi.halo;
-	const size_t slice = wa * wb * host_nlev;
-	// rows iA in the interior are contiguous runs of wb*host_nlev doubles;
-	// copy interior rows only so that halo entries on the host are untouched
-	// in alpha; beta halos inside a row are restored from a saved copy.
-	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-	std::vector<double> tmp(slice);
 	for (size_t q = 0; q < comps.size(); q++) {
-		const int c = comps[q];
-		TB_CHECK(ctx, cudaMemcpy(tmp.data(), ctx->d_stage + c * slice,
-			slice * sizeof(double), cudaMemcpyDeviceToHost));
-		for (size_t ia = pi.halo; ia < wa - pi.halo; ia++) {
-			const size_t off = (ia * wb + pi.halo) * host_nlev;
-			memcpy(host + c * slice + off, tmp.data() + off,
-				(wb - 2 * pi.halo) * host_nlev * sizeof(double));
-		}
+		if (copy_interior(ctx, pi, host, comps[q], host_nlev, false)) return 1;
 	}
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
 	return 0;
 }
 

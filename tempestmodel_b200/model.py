@@ -1,0 +1,148 @@
+"""Model driver mirroring the reference's Model / TempestInitialize setup path
+(reference src/atm/Model.{h,cpp}, src/atm/TempestInitialize.h:185-586):
+owns the grid, the test case and the device context, and advances the state
+with TimestepScheme::Step entirely on the device.
+"""
+import math
+
+import numpy as np
+
+from . import grid as G
+from ._lib import (DATA_ALL, EQN_PRIMITIVE_NONHYDRO, EQN_SHALLOW_WATER,
+                   OP_NAMES, SCHEMES)
+from .device import DeviceContext
+
+SCHEME_INSTANCES = {"strang": 5, "strang/kgu35": 5, "strang/rk4": 5,
+                    "strang/rk3": 5, "strang/fe": 5, "ars343": 7}
+
+
+class Model:
+    """model = Model(grid, test); model.initialize(); model.step(n)."""
+
+    def __init__(self, grid, test, timescheme="strang", dt=200.0,
+                 hypervis_order=4, nu_scalar=1.0e15, nu_div=1.0e15,
+                 nu_vort=1.0e15, no_hypervis=False, off_centering=0.0,
+                 library=None, device=-1, rank=0, nranks=1, owners=None,
+                 exchange=None):
+        self.grid = grid
+        self.test = test
+        self.timescheme = timescheme.lower()
+        if self.timescheme not in SCHEME_INSTANCES:
+            raise ValueError("Invalid --timescheme %r" % timescheme)
+        self.dt = float(dt)
+        self.rank, self.nranks = rank, nranks
+        npatch = len(grid.patches)
+        self.owners = list(owners) if owners is not None else [0] * npatch
+        self.local = [p for p in grid.patches if self.owners[p.index] == rank]
+        sw = (test.equation_set == "shallow_water")
+        self.ncomp = 3 if sw else 5
+        onedge = [0] * 8
+        if not sw:
+            onedge[3] = 1                       # Lorenz staggering: W on interfaces
+        if no_hypervis:
+            hypervis_order, nu_scalar, nu_div, nu_vort = 0, 0.0, 0.0, 0.0
+        ph = grid.phys
+        self.ctx = DeviceContext(
+            library=library, np=grid.np, nlev=grid.nlev,
+            vertical_order=grid.vertical_order, ncomp=self.ncomp, ntracers=0,
+            ninstances=SCHEME_INSTANCES[self.timescheme],
+            eqn_type=EQN_SHALLOW_WATER if sw else EQN_PRIMITIVE_NONHYDRO,
+            cartesian_xz=0, comp_on_redge=onedge, device=device,
+            g=ph.g, R=ph.R, cp=ph.cp, cv=ph.cv, p0=ph.p0, omega=ph.omega,
+            earth_radius=ph.earth_radius, ztop=grid.ztop,
+            ref_length=grid.reference_length, hypervis_order=hypervis_order,
+            nu_scalar=nu_scalar, nu_div=nu_div, nu_vort=nu_vort,
+            fully_explicit=0, off_centering=off_centering)
+        if nranks > 1:
+            self.ctx.set_exchange(rank, nranks, exchange)
+        self.steps_taken = 0
+        self._host = {}
+
+    # -- setup (Model::SetGrid, SetTestCase and the head of Model::Go) ---------
+    def initialize(self, upload_state=True):
+        g, ctx = self.grid, self.ctx
+        for p in g.patches:
+            ctx.add_patch(p.index, p.panel, p.nea, p.neb, p.halo, p.delta,
+                          p.delta, self.owners[p.index])
+        ctx.commit_layout()
+        ctx.set_tables(g.dx, g.stiffness, g.gll_weights)
+        for i, name in enumerate(OP_NAMES):
+            if name in g.ops:
+                c, b, e = g.ops[name]
+                ctx.set_column_op(i, c, b, e)
+        g.evaluate_topography(self.test)
+        for p in g.patches:
+            ctx.set_node_ids(p.index, p.node_ids())
+        for p in self.local:
+            geo = p.evaluate_geometric_terms(p._zs, p._dazs, p._dbzs)
+            ctx.upload_geometry(p.index, **geo)
+            ctx.upload_element_area(p.index, p.area_node, p.area_redge)
+            ctx.set_seam_transforms(p.index, *p.seam_transforms())
+            if upload_state:
+                node, redge = self.evaluate_test_case(p)
+                self._host[p.index] = (node, redge)
+                ctx.upload_state(p.index, 0, node, redge, None)
+        ctx.build_connectivity()
+        return self
+
+    def evaluate_test_case(self, p):
+        """GridPatchCSGLL::EvaluateTestCase (GridPatchCSGLL.cpp:578-920) for
+        one patch: pointwise state on levels (and w on interfaces), zonal /
+        meridional wind converted to covariant components."""
+        g, ph, test = self.grid, self.grid.phys, self.test
+        L = g.nlev
+        node = np.zeros((self.ncomp, p.wa, p.wb, L))
+        redge = np.zeros((self.ncomp, p.wa, p.wb, L + 1))
+        lon, lat = p.lon[:, :, None], p.lat[:, :, None]
+        if test.equation_set == "shallow_water":
+            z = np.zeros((1, 1, L))
+        else:
+            zs = p._zs[:, :, None]
+            z = zs + g.reta_levels[None, None, :] * (g.ztop - zs)
+        st = test.evaluate_pointwise_state(ph, z, lon, lat)
+        st = [np.broadcast_to(s, np.broadcast(z, lon).shape) for s in st]
+        ua, ub = G.covec_abp_from_rll(p.XX[:, :, None], p.YY[:, :, None], p.panel,
+                                      st[0] * ph.earth_radius, st[1] * ph.earth_radius)
+        node[0, 1:-1, 1:-1] = ua
+        node[1, 1:-1, 1:-1] = ub
+        if test.equation_set == "shallow_water":
+            node[2, 1:-1, 1:-1] = st[2]
+        else:
+            # EquationSet::ConvertComponents (EquationSet.cpp:153-155): theta -> rho theta
+            node[2, 1:-1, 1:-1] = st[2] * st[4]
+            node[4, 1:-1, 1:-1] = st[4]
+            # w on interfaces: zero for the test cases here (dState[3] = 0)
+        return node, redge
+
+    # -- the step loop (Model::Go, Model.cpp:395-518) ------------------------------
+    def step(self, nsteps=1, last=False):
+        for s in range(nsteps):
+            first = (self.steps_taken == 0)
+            is_last = last and (s == nsteps - 1)
+            self.ctx.step(SCHEMES[self.timescheme], first, is_last, self.dt)
+            self.steps_taken += 1
+
+    def download_state(self, inst=0):
+        out = {}
+        L = self.grid.nlev
+        for p in self.local:
+            node = np.zeros((self.ncomp, p.wa, p.wb, L))
+            redge = np.zeros((self.ncomp, p.wa, p.wb, L + 1))
+            self.ctx.download_state(p.index, inst, node, redge, None, True)
+            out[p.index] = (node, redge)
+        return out
+
+    def checksum(self, inst=0):
+        return self.ctx.checksum(inst)
+
+    @property
+    def column_count(self):
+        return self.ctx.column_count
+
+    def simulated_days_per_day(self, seconds_per_step):
+        return self.dt / seconds_per_step
+
+
+def default_dt(ne):
+    """Driver default 200 s at ne = 20, scaled with resolution."""
+    return 200.0 * 20.0 / ne

@@ -1,0 +1,34 @@
+"""Patch decomposition over ranks: the golden Strang case on 2 ranks (3 patches
+each) must reproduce the single-rank reference state.  CPU: gloo + emulation
+library; GPU (needs 2 devices): nccl + product library."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _run(backend, nproc=2, port=29611):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(HERE, "_multirank_worker.py"),
+           backend, "jw_ne2_l6_strang", "strang"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert "MULTIRANK worst=" in res.stdout, res.stdout[-3000:]
+    return res.stdout
+
+
+def test_two_ranks_gloo(emu_library):
+    _run("gloo")
+
+
+@pytest.mark.gpu
+def test_two_ranks_nccl(cuda_library):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("nccl", port=29612)

@@ -42,7 +42,7 @@ def tendency_errors(ctx, d, inst, tag, before_tag, before_inst, node, redge=(),
     out = {}
     for loc, comps in (("node", node), ("redge", redge)):
         for c in comps:
-            num = den = 0.0
+            num = den = mag = 0.0
             for n in ctx.local_patches:
                 ref = dumpctx.interior(d["%s.patch%d.inst%d.%s" % (tag, n, inst, loc)])[c]
                 sc = ref if scale is None else dumpctx.interior(
@@ -54,6 +54,10 @@ def tendency_errors(ctx, d, inst, tag, before_tag, before_inst, node, redge=(),
                     ref, sc, bef, dev = ref[m], sc[m], bef[m], dev[m]
                 num = max(num, np.abs(dev - ref).max())
                 den = max(den, np.abs(sc - bef).max())
+                mag = max(mag, np.abs(ref).max())
+            # the updated field is stored rounded to its own precision: allow
+            # two units in the last place of the field on top of the tendency
+            num = max(0.0, num - 2.0 * np.finfo(float).eps * mag)
             out[(loc, c)] = num / den if den > 0 else num
     return out
 
