@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the dynamical-core timestep hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --steps K --warmup W    (reference CPU arm)
+
+A "step" is one full TimestepScheme::Step (default strang / KGU35 + hyper-
+diffusion + implicit column solve) of the Jablonowski-Williamson baroclinic
+wave on the cubed sphere, synthetic closed-form initial conditions.  The
+metric is column-steps/s over all GPUs (columns = 6 ne^2 np^2 element-local
+columns); simulated days per wall day is reported beside it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "column-steps/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ne", type=int, default=120)
+    ap.add_argument("--levels", type=int, default=30)
+    ap.add_argument("--timescheme", default="strang")
+    ap.add_argument("--ref-ne", type=int, default=12,
+                    help="resolution of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference (oracle/_ref) timed on
+# the host.  The reference is one thread per MPI rank and the image has no MPI
+# runtime, so this is a 1-core number.
+
+def run_reference(ne, levels, steps, dt, timescheme):
+    exe = os.path.join(ROOT, "oracle", "_ref", "BaroclinicWaveJWTest")
+    if not os.path.exists(exe):
+        return None
+    end = dt * steps
+    cmd = [exe, "--resolution", str(ne), "--levels", str(levels), "--dt", "%ds" % dt,
+           "--endtime", "%ds" % end, "--ztop", "30000", "--pert", "Exp",
+           "--timescheme", timescheme, "--output_none"]
+    t0 = time.time()
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=3600)
+    wall = time.time() - t0
+    loop_us = None
+    count = None
+    for line in res.stdout.splitlines():
+        if line.startswith("Time [Loop]:"):
+            # Time [Loop]: avg [min, max] (count)   microseconds, Model.cpp:640-643
+            parts = line.replace("[", " ").replace("]", " ").replace(",", " ") \
+                .replace("(", " ").replace(")", " ").split()
+            loop_us = float(parts[3])
+            count = int(parts[-1])
+    if loop_us is None:
+        return None
+    cols = 6 * ne * ne * 16
+    return dict(seconds_per_step=loop_us * 1e-6, steps=count, columns=cols,
+                value=cols / (loop_us * 1e-6), wall=wall)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dt = int(round(200.0 * 20.0 / args.ref_ne))
+    steps = max(1, min(args.steps, 3))
+    r = run_reference(args.ref_ne, args.levels, steps + min(args.warmup, 1), dt, args.timescheme)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/BaroclinicWaveJWTest not built"}))
+        return
+    sample = ("unmodified reference BaroclinicWaveJWTest ne=%d L=%d %s, %d steps, "
+              "FunctionTimer 'Loop' average (column-steps/s is per column, the "
+              "sample is the ne=%d workload scaled down)"
+              % (args.ref_ne, args.levels, args.timescheme, r["steps"], args.ne))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "column-steps/s",
+        "n_gpus": 0, "steps": r["steps"], "warmup": 0,
+        "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "JW baroclinic wave ne=%d L%d np=4 %s (CPU sample ne=%d)"
+                   % (args.ne, args.levels, args.timescheme, args.ref_ne)},
+        "sim_days_per_day": dt / r["seconds_per_step"],
+        "cpu_baseline": {"value": r["value"], "unit": "column-steps/s", "cores": 1,
+                         "kind": "reference", "sample": sample},
+        "e2e": {"value": r["value"], "unit": "column-steps/s",
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop:
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                     "--format=csv,noheader,nounits"],
+                    stdout=subprocess.PIPE, text=True, timeout=10).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append((float(f[0]), float(f[1])))
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        s = sorted(x[0] for x in self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.samples[0][1],
+                "reasons": sorted(self.reasons)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from tempestmodel_b200 import grid as G
+    from tempestmodel_b200 import testcases as TC
+    from tempestmodel_b200.model import Model
+    from tempestmodel_b200.parallel import Exchange, assign_patches
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: tempestmodel_b200 has no CPU fallback")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl")
+    n_gpus = world
+
+    ne, L = args.ne, args.levels
+    dt = 200.0 * 20.0 / ne
+    npatch = 6 if world == 1 else 24
+    while npatch % world != 0 or ne % int(round((npatch // 6) ** 0.5)) != 0:
+        npatch += 6
+    owners = assign_patches(npatch, world)
+    t_setup = time.time()
+    grid = G.GridCSGLL(ne, L, npatch=npatch, ztop=30000.0)
+    ex = Exchange(cuda=True) if world > 1 else None
+    model = Model(grid, TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"),
+                  timescheme=args.timescheme, dt=dt, device=local_rank,
+                  rank=rank, nranks=world, owners=owners, exchange=ex)
+    ctx = model.ctx
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    model.device_setup = True
+    model.initialize()
+    ctx.sync()
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # pinned host copies of instance 0 (reference layout) for the end-to-end leg
+    host = {}
+    h2d = d2h = 0
+    if not args.no_e2e:
+        for p in model.local:
+            node, redge = model._host[p.index]
+            pn = torch.empty(node.shape, dtype=torch.float64).pin_memory()
+            pe = torch.empty(redge.shape, dtype=torch.float64).pin_memory()
+            pn.numpy()[...] = node
+            pe.numpy()[...] = redge
+            host[p.index] = (pn.numpy(), pe.numpy())
+            interior = (p.wa - 2) * (p.wb - 2)
+            # U,V,rho-theta,rho on levels + W on interfaces
+            h2d += interior * (4 * L + (L + 1)) * 8
+            d2h += interior * (4 * L + (L + 1)) * 8
+    model._host = {}
+
+    # ---- warm-up ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        model.step(1)
+    ctx.check_errors()
+
+    # ---- timed region: device-resident steps ---------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    model.step(args.steps)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    ctx.check_errors()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    sampler.stop = True
+    sampler.join(timeout=5)
+
+    columns = 6 * ne * ne * grid.np * grid.np
+    sec_per_step = ms * 1e-3 / args.steps
+    value = columns / sec_per_step
+
+    # ---- dominant kernel: fused explicit stage (H + V explicit) ----------------
+    nk = 10
+    k0 = torch.cuda.Event(enable_timing=True)
+    k1 = torch.cuda.Event(enable_timing=True)
+    ctx.hv_step_explicit(2, 3, 1e-9)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(nk):
+        ctx.hv_step_explicit(2, 3, 1e-9)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / nk
+    local_nodes = ctx.column_count * L
+    # algorithmic bytes of one explicit stage pass with one source instance
+    # ((n_src + 1) * S * 8 B per node, S = 5)
+    alg_bytes = local_nodes * (1 + 1) * 5 * 8
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_nh_explicit<4,true,true>",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "bytes_per_node": 80,
+                "step_algorithmic_bytes": columns * L * 35.5 * 5 * 8,
+                "step_frac": columns * L * 35.5 * 5 * 8 / sec_per_step / 1e9 / peak / n_gpus}
+
+    # ---- end to end: host buffers in, host buffers out, every step ------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            for p in model.local:
+                pn, pe = host[p.index]
+                ctx.upload_state(p.index, 0, pn, pe, None)
+            model.step(1)
+            for p in model.local:
+                pn, pe = host[p.index]
+                ctx.download_state(p.index, 0, pn, pe, None, False)
+        e2e_step()
+        ksteps = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        te = (time.perf_counter() - t0) / ksteps
+        tt = torch.tensor([te], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        hb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(hb)
+        e2e = {"value": columns / tt.item(), "unit": "column-steps/s",
+               "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()),
+               "ms_per_step": tt.item() * 1e3}
+        ctx.check_errors()
+
+    # ---- CPU baseline: the unmodified reference on this host, bounded sample --
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rdt = int(round(200.0 * 20.0 / args.ref_ne))
+        r = run_reference(args.ref_ne, L, 2, rdt, args.timescheme)
+        if r is not None:
+            cpu = {"value": r["value"], "unit": "column-steps/s", "cores": 1,
+                   "kind": "reference",
+                   "sample": "unmodified reference BaroclinicWaveJWTest ne=%d L=%d %s, "
+                             "%d steps, FunctionTimer 'Loop' average; single rank "
+                             "(no MPI runtime in the image)"
+                             % (args.ref_ne, L, args.timescheme, r["steps"]),
+                   "ms_per_step": r["seconds_per_step"] * 1e3}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "column-steps/s",
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "JW baroclinic wave ne=%d L%d np=4 %s dt=%gs, %d patches"
+                                   % (ne, L, args.timescheme, dt, npatch),
+                       "l2": "state per instance %.2f GB >> 126 MB L2"
+                             % (ctx.column_count * (5 * L + 1) * 8 / 1e9)},
+            "sim_days_per_day": dt / sec_per_step,
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "setup_seconds": t_setup,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@ class Model:
             self.ctx.set_exchange(rank, nranks, exchange)
         self.steps_taken = 0
         self._host = {}
+        self.device_setup = False
 
     # -- setup (Model::SetGrid, SetTestCase and the head of Model::Go) ---------
     def initialize(self, upload_state=True):
@@ -99,7 +100,16 @@ class Model:
         else:
             zs = p._zs[:, :, None]
             z = zs + g.reta_levels[None, None, :] * (g.ztop - zs)
-        st = test.evaluate_pointwise_state(ph, z, lon, lat)
+        if self.device_setup:
+            # large grids: evaluate the closed-form state on the GPU (torch is
+            # plumbing here; same formulas as the numpy path)
+            import torch
+            from .testcases import _Torch
+            dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+            st = test.evaluate_pointwise_state(ph, dev(z), dev(lon), dev(lat), _Torch())
+            st = [s.cpu().numpy() for s in st]
+        else:
+            st = test.evaluate_pointwise_state(ph, z, lon, lat)
         st = [np.broadcast_to(s, np.broadcast(z, lon).shape) for s in st]
         ua, ub = G.covec_abp_from_rll(p.XX[:, :, None], p.YY[:, :, None], p.panel,
                                       st[0] * ph.earth_radius, st[1] * ph.earth_radius)

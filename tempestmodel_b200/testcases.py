@@ -14,6 +14,66 @@ import math
 import numpy as np
 
 
+class _Numpy:
+    """array namespace used by the closed-form initial conditions; a torch
+    twin (below) evaluates the same formulas on the GPU for large grids."""
+    where = staticmethod(np.where)
+    sin = staticmethod(np.sin)
+    cos = staticmethod(np.cos)
+    tan = staticmethod(np.tan)
+    log = staticmethod(np.log)
+    exp = staticmethod(np.exp)
+    sqrt = staticmethod(np.sqrt)
+    abs = staticmethod(np.abs)
+    arccos = staticmethod(np.arccos)
+    zeros_like = staticmethod(np.zeros_like)
+
+    @staticmethod
+    def clip(a, lo, hi):
+        return np.clip(a, lo, hi)
+
+    @staticmethod
+    def full_like_broadcast(a, b, value):
+        return np.full(np.broadcast(a, b).shape, value)
+
+    @staticmethod
+    def broadcast_to(a, shape):
+        return np.broadcast_to(a, shape)
+
+    @staticmethod
+    def all(a):
+        return bool(np.all(a))
+
+    @staticmethod
+    def zeros_bool(shape):
+        return np.zeros(shape, dtype=bool)
+
+
+class _Torch:
+    def __init__(self):
+        import torch
+        self.t = torch
+        for name in ("where", "sin", "cos", "tan", "log", "exp", "sqrt", "abs",
+                     "arccos", "zeros_like", "broadcast_to"):
+            setattr(self, name, getattr(torch, name))
+
+    def clip(self, a, lo, hi):
+        return self.t.clamp(a, lo, hi)
+
+    def full_like_broadcast(self, a, b, value):
+        shape = self.t.broadcast_shapes(a.shape, b.shape)
+        return self.t.full(shape, value, dtype=self.t.float64, device=a.device)
+
+    def all(self, a):
+        return bool(a.all().item())
+
+    def zeros_bool(self, shape):
+        return self.t.zeros(shape, dtype=self.t.bool, device="cuda")
+
+
+NUMPY = _Numpy()
+
+
 class ShallowWaterTestCase2:
     """Williamson et al. (1992) test 2: steady geostrophic flow."""
 
@@ -26,13 +86,13 @@ class ShallowWaterTestCase2:
     def evaluate_topography(self, phys, lon, lat):
         return np.zeros_like(lon)
 
-    def evaluate_pointwise_state(self, phys, z, lon, lat):
-        lat = np.where(np.abs(lat - 0.5 * math.pi) < 1.0e-12, lat - 1.0e-12, lat)
-        lat = np.where(np.abs(lat + 0.5 * math.pi) < 1.0e-12, lat + 1.0e-12, lat)
+    def evaluate_pointwise_state(self, phys, z, lon, lat, xp=NUMPY):
+        lat = xp.where(xp.abs(lat - 0.5 * math.pi) < 1.0e-12, lat - 1.0e-12, lat)
+        lat = xp.where(xp.abs(lat + 0.5 * math.pi) < 1.0e-12, lat + 1.0e-12, lat)
         a = self.alpha
-        u = self.u0 * np.cos(lat) * (math.cos(a) + np.cos(lon) * np.tan(lat) * math.sin(a))
-        v = -self.u0 * np.sin(lon) * math.sin(a)
-        htrig = -np.cos(lon) * np.cos(lat) * math.sin(a) + np.sin(lat) * math.cos(a)
+        u = self.u0 * xp.cos(lat) * (math.cos(a) + xp.cos(lon) * xp.tan(lat) * math.sin(a))
+        v = -self.u0 * xp.sin(lon) * math.sin(a) + 0.0 * lat
+        htrig = -xp.cos(lon) * xp.cos(lat) * math.sin(a) + xp.sin(lat) * math.cos(a)
         h = self.h0 - (phys.earth_radius * phys.omega + 0.5 * self.u0) \
             * self.u0 * htrig * htrig / phys.g
         return [u, v, h]
@@ -58,86 +118,88 @@ class BaroclinicWaveJWTest:
         self.pert_lat = 2.0 * math.pi / 9.0
         self.pert_r = 0.1
 
-    def _profiles(self, phys, aux_eta, lat):
-        s = np.sin(lat)
+    def _profiles(self, phys, aux_eta, lat, xp=NUMPY):
+        s = xp.sin(lat)
         s2 = s * s
         s6 = s2 * s2 * s2
-        c = np.cos(lat)
+        c = xp.cos(lat)
         c2 = c * c
         c3 = c2 * c
-        p1 = self.u0 * np.cos(aux_eta) ** 1.5 * (-2.0 * s6 * (c2 + 1.0 / 3.0) + 10.0 / 63.0)
+        p1 = self.u0 * xp.cos(aux_eta) ** 1.5 * (-2.0 * s6 * (c2 + 1.0 / 3.0) + 10.0 / 63.0)
         p2 = phys.earth_radius * phys.omega * (8.0 / 5.0 * c3 * (s2 + 2.0 / 3.0) - 0.25 * math.pi)
         return p1, p2
 
     def evaluate_topography(self, phys, lon, lat):
         aux = 0.5 * math.pi * (1.0 - self.eta0)
-        p1, p2 = self._profiles(phys, aux, lat)
+        p1, p2 = self._profiles(phys, np.float64(aux), lat)
         return self.u0 * math.cos(aux) ** 1.5 * (p1 + p2) / phys.g
 
-    def geopotential_temperature(self, phys, eta, lat):
+    def geopotential_temperature(self, phys, eta, lat, xp=NUMPY):
         aux = 0.5 * math.pi * (eta - self.eta0)
         expo = phys.R * self.lapse_rate / phys.g
         tavg = self.t0 * eta ** expo
         strat = eta < self.tropopause_eta
         te = self.tropopause_eta
-        tavg = tavg + np.where(strat, self.delta_t * np.maximum(te - eta, 0.0) ** 5.0, 0.0)
-        p1, p2 = self._profiles(phys, aux, lat)
+        zero = xp.zeros_like(eta)
+        tavg = tavg + xp.where(strat, self.delta_t * xp.clip(te - eta, 0.0, 1.0e30) ** 5.0, zero)
+        p1, p2 = self._profiles(phys, aux, lat, xp)
         temp = 2.0 * p1 + p2
         temp = tavg + 0.75 * eta * math.pi * self.u0 / phys.R \
-            * np.sin(aux) * np.sqrt(np.cos(aux)) * temp
+            * xp.sin(aux) * xp.sqrt(xp.cos(aux)) * temp
         gavg = self.t0 * phys.g / self.lapse_rate * (1.0 - eta ** expo)
-        es = np.where(strat, eta, te)
+        es = xp.where(strat, eta, zero + te)
         corr = phys.R * self.delta_t * (
-            (np.log(es / te) + 137.0 / 60.0) * te ** 5
+            (xp.log(es / te) + 137.0 / 60.0) * te ** 5
             - 5.0 * te ** 4 * es + 5.0 * te ** 3 * es ** 2
             - (10.0 / 3.0) * te ** 2 * es ** 3 + 5.0 / 4.0 * te * es ** 4
             - 1.0 / 5.0 * es ** 5)
-        gavg = gavg - np.where(strat, corr, 0.0)
-        geo = gavg + self.u0 * np.cos(aux) ** 1.5 * (p1 + p2)
+        gavg = gavg - xp.where(strat, corr, zero)
+        geo = gavg + self.u0 * xp.cos(aux) ** 1.5 * (p1 + p2)
         return geo, temp
 
-    def eta_from_rll(self, phys, z, lat):
+    def eta_from_rll(self, phys, z, lat, xp=NUMPY):
         """Newton iteration of EtaFromRLL (:297-345)."""
-        eta = np.full(np.broadcast(z, lat).shape, 1.0e-7)
-        lat = np.broadcast_to(lat, eta.shape)
-        z = np.broadcast_to(z, eta.shape)
-        done = np.zeros(eta.shape, dtype=bool)
+        eta = xp.full_like_broadcast(z, lat, 1.0e-7)
+        lat = xp.broadcast_to(lat, eta.shape)
+        z = xp.broadcast_to(z, eta.shape)
+        done = xp.zeros_bool(eta.shape)
         geo = temp = None
         for _ in range(25):
-            geo, temp = self.geopotential_temperature(phys, eta, lat)
+            geo, temp = self.geopotential_temperature(phys, eta, lat, xp)
             f = -phys.g * z + geo
             df = -phys.R / eta * temp
             new = eta - f / df
-            conv = np.abs(eta - new) < 1.0e-13
-            eta = np.where(done, eta, new)
+            conv = xp.abs(eta - new) < 1.0e-13
+            eta = xp.where(done, eta, new)
             done = done | conv
-            if done.all():
+            if xp.all(done):
                 break
-        if not done.all():
+        if not xp.all(done):
             raise RuntimeError("Maximum number of iterations exceeded.")
         # the reference returns geopotential / temperature of the last
         # evaluated iterate
         return eta, temp
 
-    def evaluate_reference_state(self, phys, z, lon, lat):
-        eta, temp = self.eta_from_rll(phys, z, lat)
-        ulon = self.u0 * np.cos(0.5 * math.pi * (eta - self.eta0)) ** 1.5 \
-            * np.sin(2.0 * lat) * np.sin(2.0 * lat)
+    def evaluate_reference_state(self, phys, z, lon, lat, xp=NUMPY):
+        eta, temp = self.eta_from_rll(phys, z, lat, xp)
+        ulon = self.u0 * xp.cos(0.5 * math.pi * (eta - self.eta0)) ** 1.5 \
+            * xp.sin(2.0 * lat) * xp.sin(2.0 * lat)
         p = phys.p0 * eta
         rho = p / (phys.R * temp)
-        rhotheta = phys.rho_theta_from_pressure(p)
-        zero = np.zeros_like(ulon)
+        # PhysicalConstants::RhoThetaFromPressure (PhysicalConstants.h:389-391)
+        rhotheta = xp.exp(xp.log(p / phys.pressure_scaling) / phys.gamma)
+        zero = xp.zeros_like(ulon)
         return [ulon, zero, rhotheta / rho, zero, rho]
 
-    def evaluate_pointwise_state(self, phys, z, lon, lat):
-        st = self.evaluate_reference_state(phys, z, lon, lat)
+    def evaluate_pointwise_state(self, phys, z, lon, lat, xp=NUMPY):
+        st = self.evaluate_reference_state(phys, z, lon, lat, xp)
         if self.perturbation == "exp":
-            lonb = np.broadcast_to(lon, st[0].shape)
-            latb = np.broadcast_to(lat, st[0].shape)
-            r = np.arccos(np.clip(
-                math.sin(self.pert_lat) * np.sin(latb)
-                + math.cos(self.pert_lat) * np.cos(latb) * np.cos(lonb - self.pert_lon),
+            lonb = xp.broadcast_to(lon, st[0].shape)
+            latb = xp.broadcast_to(lat, st[0].shape)
+            r = xp.arccos(xp.clip(
+                math.sin(self.pert_lat) * xp.sin(latb)
+                + math.cos(self.pert_lat) * xp.cos(latb) * xp.cos(lonb - self.pert_lon),
                 -1.0, 1.0))
             r = r / self.pert_r
-            st[0] = st[0] + np.where(r < 1.0, self.up * np.exp(-r * r), 0.0)
+            st[0] = st[0] + xp.where(r < 1.0, self.up * xp.exp(-r * r), xp.zeros_like(r))
         return st
