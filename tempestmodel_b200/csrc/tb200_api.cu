@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 #include <unordered_map>
@@ -828,6 +829,40 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
 	ca.assemble_only = 0;
+
+	// one warp per column with all work arrays in shared memory, unless the
+	// column is too tall for it (or TB200_COLUMN_KERNEL=thread asks for the
+	// thread-per-column implementation)
+	const size_t warp_bytes =
+		(size_t)tb_column_warp_smem_doubles(lay.nlev, ctx->offd) * sizeof(double);
+	const size_t sm_budget = 227 * 1024;
+	int wpb = 0;
+	{
+		int best = 0;
+		for (int w = 1; w <= 8; w++) {
+			const size_t blk = warp_bytes * w + 1024;
+			if (blk > sm_budget) break;
+			const int per_sm = (int)(sm_budget / blk) * w;
+			if (per_sm > best) { best = per_sm; wpb = w; }
+		}
+	}
+	const char * force = getenv("TB200_COLUMN_KERNEL");
+	if (force != 0 && strcmp(force, "thread") == 0) wpb = 0;
+
+	if (wpb > 0) {
+		ca.col0 = 0;
+		ca.ncols = ctx->ncols;
+		const size_t smem = warp_bytes * wpb;
+		auto kfn = k_column_implicit_warp;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		TB_LAUNCH(kfn, dim3((ca.ncols + wpb - 1) / wpb), dim3(32 * wpb), smem, ctx->stream,
+			lay, ctx->geom, ctx->ops, ctx->phys, ca,
+			(const double *)ctx->inst[in], ctx->inst[out], (int)(warp_bytes / sizeof(double)));
+		TB_KERNEL_CHECK(ctx);
+		return 0;
+	}
 	for (int c0 = 0; c0 < ctx->ncols; c0 += ctx->ws_cols) {
 		ca.col0 = c0;
 		ca.ncols = std::min(ctx->ws_cols, ctx->ncols - c0);

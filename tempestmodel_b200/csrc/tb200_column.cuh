@@ -526,4 +526,414 @@ __global__ void k_column_implicit(
 	}
 }
 
+
+///////////////////////////////////////////////////////////////////////////////
+// One warp per column, all work arrays in shared memory.
+//
+// Same arithmetic as k_column_implicit (which stays as the reference
+// implementation of the solve on the device and as the fallback for columns
+// too tall for shared memory); here lane k assembles the rows of level k, and
+// the band LU runs warp-wide: pivot search by shuffle reduction, the rank-1
+// update of the (kl x kl+ku) trailing block one entry per lane.  Every
+// Jacobian entry is accumulated by a single lane in the reference's statement
+// order, so the matrix is identical to the one the thread-per-column kernel
+// (and the reference) build.
+
+__host__ __device__ inline int tb_column_warp_smem_doubles(int L, int offd) {
+	const int n = 3 * (L + 1);
+	const int lp = L + 2;
+	return 21 * lp + n + n * (3 * offd + 1) + 8;
+}
+
+struct SmAcc {
+	double * p;
+	__device__ __forceinline__ double & operator()(int i) const { return p[i]; }
+};
+
+struct SmBand {
+	double * p;
+	int ldab;
+	__device__ __forceinline__ double & operator()(int r, int j) const {
+		return p[j * ldab + r];
+	}
+};
+
+__device__ __forceinline__ double tb_sm_apply(const DevOp & op, const SmAcc & in, int k) {
+	double o = 0.0;
+	const int b = op.begin[k];
+	const int e = op.end[k];
+	const double * c = op.coeff + (size_t)k * op.width;
+	for (int l = b; l < e; l++) {
+		o += c[l - b] * in(l);
+	}
+	return o;
+}
+
+__global__ void k_column_implicit_warp(
+	DevLayout lay, DevGeom g, DevOps ops, DevPhys ph, ColumnArgs ca,
+	const double * in, double * out, int smem_per_warp
+) {
+	TB_DYN_SMEM(double, smem_all);
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const int wpb = blockDim.x >> 5;
+	const int tcol = blockIdx.x * wpb + warp;
+	if (tcol >= ca.ncols) return;      // whole warp leaves together
+	const unsigned FULL = 0xffffffffu;
+
+	const int UIx = 0, VIx = 1, PIx = 2, WIx = 3, RIx = 4;
+	const int FP = 0, FW = 1, FR = 2;
+	const int NN = lay.nn;
+	const int L = lay.nlev;
+	const int n = 3 * (L + 1);
+	const int offd = ca.offd;
+	const int ldab = 3 * offd + 1;
+	const int lp = L + 2;
+
+	const int node = ca.col_node[ca.col0 + tcol];
+	const long long e = node / NN;
+	const int nd = node % NN;
+	const size_t ebase = (size_t)e * lay.nrows * NN;
+	const size_t g3 = (size_t)e * L * NN + nd;
+	const size_t g3e = (size_t)e * (L + 1) * NN + nd;
+
+	double * w0 = smem_all + (size_t)warp * smem_per_warp;
+	int cur = 0;
+#define TB_SM(name) SmAcc name = {w0 + cur}; cur += lp
+	TB_SM(snU); TB_SM(snV); TB_SM(snP); TB_SM(snW); TB_SM(snR);
+	TB_SM(seU); TB_SM(seV); TB_SM(seW); TB_SM(seR); TB_SM(seP);
+	TB_SM(exn); TB_SM(dPe); TB_SM(xdn); TB_SM(xde); TB_SM(mfe); TB_SM(pfe);
+	TB_SM(ken); TB_SM(dkee); TB_SM(dUa); TB_SM(dUb); TB_SM(ddW);
+#undef TB_SM
+	SmAcc F = {w0 + cur}; cur += n;
+	SmBand DG = {w0 + cur, ldab};
+
+	const DevOp & opInterpN2E = ops.op[0];
+	const DevOp & opInterpE2N = ops.op[1];
+	const DevOp & opDiffN2E = ops.op[3];
+	const DevOp & opDiffE2N = ops.op[4];
+	const DevOp & opDDE2E = ops.op[7];
+	const DevOp & opPenL = ops.op[8];
+	const DevOp & opPenR = ops.op[9];
+
+	const double * inU = in + ebase + (size_t)lay.rowoff[UIx] * NN + nd;
+	const double * inV = in + ebase + (size_t)lay.rowoff[VIx] * NN + nd;
+	const double * inP = in + ebase + (size_t)lay.rowoff[PIx] * NN + nd;
+	const double * inW = in + ebase + (size_t)lay.rowoff[WIx] * NN + nd;
+	const double * inR = in + ebase + (size_t)lay.rowoff[RIx] * NN + nd;
+
+	// ---- SetupReferenceColumn / PrepareColumn ---------------------------------
+	for (int k = lane; k <= L; k += 32) {
+		if (k < L) {
+			snU(k) = inU[(size_t)k * NN];
+			snV(k) = inV[(size_t)k * NN];
+			snP(k) = inP[(size_t)k * NN];
+			snR(k) = inR[(size_t)k * NN];
+		}
+		seW(k) = inW[(size_t)k * NN];
+	}
+	__syncwarp();
+	for (int k = lane; k <= L; k += 32) {
+		seU(k) = tb_sm_apply(opInterpN2E, snU, k);
+		seV(k) = tb_sm_apply(opInterpN2E, snV, k);
+		dUa(k) = tb_sm_apply(opDiffN2E, snU, k);
+		dUb(k) = tb_sm_apply(opDiffN2E, snV, k);
+		seR(k) = tb_sm_apply(opInterpN2E, snR, k);
+		seP(k) = tb_sm_apply(opInterpN2E, snP, k);
+		double d2 = tb_sm_apply(opDDE2E, seW, k);
+		if (k == 0 || k == L) d2 = 0.0;      // BuildF :2676-2679
+		ddW(k) = d2;
+		if (k < L) {
+			snW(k) = tb_sm_apply(opInterpE2N, seW, k);
+			exn(k) = ph.cp * exp(ph.exner_c1 * log(ph.exner_c2 * snP(k)));
+		}
+	}
+	__syncwarp();
+	for (int k = lane; k <= L; k += 32) {
+		dPe(k) = tb_sm_apply(opDiffN2E, exn, k);
+		if (k < L) {
+			const size_t o = g3 + (size_t)k * NN;
+			const double dCovUa = snU(k), dCovUb = snV(k), dCovUx = snW(k);
+			const double cx0 = g.cx[0][o], cx1 = g.cx[1][o], cx2 = g.cx[2][o];
+			xdn(k) = cx0 * dCovUa + cx1 * dCovUb + cx2 * dCovUx;
+			const double dConUa = g.ca[0][o] * dCovUa + g.ca[1][o] * dCovUb + g.ca[2][o] * dCovUx;
+			const double dConUb = g.cb[0][o] * dCovUa + g.cb[1][o] * dCovUb + g.cb[2][o] * dCovUx;
+			const double dConUx = cx0 * dCovUa + cx1 * dCovUb + cx2 * dCovUx;
+			ken(k) = 0.5 * (dConUa * dCovUa + dConUb * dCovUb + dConUx * dCovUx);
+		}
+		double xd = 0.0;
+		if (k >= 1 && k < L) {
+			const size_t o = g3e + (size_t)k * NN;
+			xd = g.cxe[0][o] * seU(k) + g.cxe[1][o] * seV(k) + g.cxe[2][o] * seW(k);
+		}
+		xde(k) = xd;
+		double mf = 0.0, pf = 0.0;
+		if (k >= 1 && k < L) {
+			const double je = g.jace[g3e + (size_t)k * NN];
+			mf = je * seR(k) * xd;
+			pf = je * seP(k) * xd;
+		}
+		mfe(k) = mf;
+		pfe(k) = pf;
+	}
+	__syncwarp();
+	for (int k = lane; k <= L; k += 32) {
+		dkee(k) = tb_sm_apply(opDiffN2E, ken, k);
+	}
+	for (int q = lane; q < n * ldab; q += 32) {
+		DG.p[q] = 0.0;
+	}
+	__syncwarp();
+
+	const int vo = ca.fe_nodes;
+	const int nfe = L / vo;
+	const double dInvDeltaT = 1.0 / ca.dt;
+#define TB_MAT(c0, k0, c1, k1) \
+	DG(2 * offd + (3 * (k1) + (c1)) - (3 * (k0) + (c0)), 3 * (k0) + (c0))
+
+	// ---- BuildF and the Jacobian rows of level k --------------------------------
+	for (int k = lane; k <= L; k += 32) {
+		double fP = 0.0, fW = 0.0, fR = 0.0;
+		if (k < L) {
+			const double invj = 1.0 / g.jac[g3 + (size_t)k * NN];
+			const double dmfn = tb_sm_apply(opDiffE2N, mfe, k);
+			const double dpfn = tb_sm_apply(opDiffE2N, pfe, k);
+			fR = dmfn * invj;
+			fP += dpfn * invj;
+			// upwind penalty of rho-theta and rho (BuildF :2687-2713)
+			const int a = k / vo;
+			for (int c = 0; c < 2; c++) {
+				const SmAcc & sn = (c == 0) ? snP : snR;
+				double aux = 0.0;
+				if (a <= nfe - 2) {
+					aux += tb_sm_apply(opPenL, sn, k) * fabs(xde((a + 1) * vo));
+				}
+				if (a >= 1) {
+					aux += tb_sm_apply(opPenR, sn, k) * fabs(xde(a * vo));
+				}
+				if (c == 0) fP -= aux; else fR -= aux;
+			}
+			// Jacobian: conservative flux terms (:3059-3091)
+			for (int m = opDiffE2N.begin[k]; m < opDiffE2N.end[k]; m++) {
+				const double je = g.jace[g3e + (size_t)m * NN];
+				const double dm = tb_op_coeff(opDiffE2N, k, m);
+				if ((m != 0) && (m != L)) {
+					const double dMassFluxCoeff =
+						dm * je * invj * g.cxe[2][g3e + (size_t)m * NN];
+					TB_MAT(FW, m, FP, k) += dMassFluxCoeff * seP(m);
+					TB_MAT(FW, m, FR, k) += dMassFluxCoeff * seR(m);
+				}
+				for (int q = opInterpN2E.begin[m]; q < opInterpN2E.end[m]; q++) {
+					const double dCoeffVerticalFlux =
+						dm * je * invj * tb_op_coeff(opInterpN2E, m, q) * xde(m);
+					TB_MAT(FR, q, FR, k) += dCoeffVerticalFlux;
+					TB_MAT(FP, q, FP, k) += dCoeffVerticalFlux;
+				}
+			}
+		}
+		if (k >= 1 && k < L) {
+			const size_t o = g3e + (size_t)k * NN;
+			const double dPressureGradientForce = dPe(k) * seP(k) / seR(k);
+			double f = dPressureGradientForce;
+			f += ph.g * g.dre[2][o];
+			const double dCovUa = seU(k), dCovUb = seV(k), dCovUx = seW(k);
+			const double dConUa = g.cae[0][o] * dCovUa + g.cae[1][o] * dCovUb + g.cae[2][o] * dCovUx;
+			const double dConUb = g.cbe[0][o] * dCovUa + g.cbe[1][o] * dCovUb + g.cbe[2][o] * dCovUx;
+			const double dCurlTerm = -dConUa * dUa(k) - dConUb * dUb(k);
+			f += (dkee(k) + dCurlTerm);
+			fW = f;
+			// Jacobian rows of w (:3094-3140)
+			const double dRHSWCoeffA = seP(k) * ph.R / (seR(k) * ph.cv);
+			for (int m = opDiffN2E.begin[k]; m < opDiffN2E.end[k]; m++) {
+				TB_MAT(FP, m, FW, k) +=
+					dRHSWCoeffA * tb_op_coeff(opDiffN2E, k, m) * exn(m) / snP(m);
+			}
+			const double dRHSWCoeffB = 1.0 / (seR(k) * seR(k)) * dPe(k);
+			for (int q = opInterpN2E.begin[k]; q < opInterpN2E.end[k]; q++) {
+				const double dRHSWCoeffC = dRHSWCoeffB * tb_op_coeff(opInterpN2E, k, q);
+				TB_MAT(FP, q, FW, k) += dRHSWCoeffC * seR(k);
+				TB_MAT(FR, q, FW, k) += -dRHSWCoeffC * seP(k);
+			}
+			for (int l = opDiffN2E.begin[k]; l < opDiffN2E.end[k]; l++) {
+				for (int m = opInterpE2N.begin[l]; m < opInterpE2N.end[l]; m++) {
+					TB_MAT(FW, m, FW, k) +=
+						tb_op_coeff(opInterpE2N, l, m) * tb_op_coeff(opDiffN2E, k, l) * xdn(l);
+				}
+			}
+		}
+		// upwinding of w on interfaces: F (:2676-2686), Jacobian (:2870-2897)
+		{
+			fW -= ca.upwind_coeff * fabs(xde(k)) * ddW(k);
+			double dSignWeight;
+			const double cx2 = g.cxe[2][g3e + (size_t)k * NN];
+			if (xde(k) > 0.0) {
+				dSignWeight = 1.0 * cx2;
+			} else if (xde(k) < 0.0) {
+				dSignWeight = -1.0 * cx2;
+			} else {
+				dSignWeight = 0.0;
+			}
+			TB_MAT(FW, k, FW, k) -= ca.upwind_coeff * dSignWeight * ddW(k);
+			for (int q = opDDE2E.begin[k]; q < opDDE2E.end[k]; q++) {
+				TB_MAT(FW, q, FW, k) -=
+					ca.upwind_coeff * fabs(xde(k)) * tb_op_coeff(opDDE2E, k, q);
+			}
+		}
+		// upwind penalty of rho-theta and rho: Jacobian (:2899-2968); a row in
+		// finite element a receives its "right" terms (iteration a of the
+		// reference loop) before its "left" terms (iteration a + 1)
+		if (k < L) {
+			const int a = k / vo;
+			for (int c = 0; c < 2; c++) {
+				const SmAcc & sn = (c == 0) ? snP : snR;
+				const int fc = (c == 0) ? FP : FR;
+				for (int side = 0; side < 2; side++) {
+					const bool right = (side == 0);
+					if (right && a < 1) continue;
+					if (!right && a > nfe - 2) continue;
+					const int ke = right ? (a * vo) : ((a + 1) * vo);
+					const DevOp & op = right ? opPenR : opPenL;
+					const double xd = xde(ke);
+					const double dWeight = fabs(xd);
+					const double cx2 = g.cxe[2][g3e + (size_t)ke * NN];
+					double dSignWeight;
+					if (xd > 0.0) {
+						dSignWeight = 1.0 * cx2;
+					} else if (xd < 0.0) {
+						dSignWeight = -1.0 * cx2;
+					} else {
+						dSignWeight = 0.0;
+					}
+					for (int q = op.begin[k]; q < op.end[k]; q++) {
+						TB_MAT(FW, ke, fc, k) -= dSignWeight * tb_op_coeff(op, k, q) * sn(q);
+					}
+					for (int q = op.begin[k]; q < op.end[k]; q++) {
+						TB_MAT(fc, q, fc, k) -= dWeight * tb_op_coeff(op, k, q);
+					}
+				}
+			}
+		}
+		if (k == 0 || k == L) fW = 0.0;      // :2747-2758
+		TB_MAT(FP, k, FP, k) += dInvDeltaT;
+		TB_MAT(FW, k, FW, k) += dInvDeltaT;
+		TB_MAT(FR, k, FR, k) += dInvDeltaT;
+		F(3 * k + FP) = fP;
+		F(3 * k + FW) = fW;
+		F(3 * k + FR) = fR;
+	}
+#undef TB_MAT
+	__syncwarp();
+
+	// ---- dgbsv: dgbtf2 with the forward substitution fused in, warp-wide ------
+	const int kl = offd, ku = offd, kv = 2 * offd;
+	int info = 0;
+	int ju = 0;
+	for (int j = 0; j < n; j++) {
+		const int km = (kl < n - 1 - j) ? kl : (n - 1 - j);
+		// idamax over rows j..j+km (first maximum)
+		double v = -1.0;
+		int jp = 0;
+		for (int i = lane; i <= km; i += 32) {
+			const double a = fabs(DG(kv + i, j));
+			if (a > v) { v = a; jp = i; }
+		}
+		for (int off = 16; off > 0; off >>= 1) {
+			const double ov = __shfl_down_sync(FULL, v, off);
+			const int oi = __shfl_down_sync(FULL, jp, off);
+			if (ov > v || (ov == v && oi < jp)) { v = ov; jp = oi; }
+		}
+		jp = __shfl_sync(FULL, jp, 0);
+		const int piv = jp + j;
+		const double pv = DG(kv + jp, j);
+		if (pv != 0.0) {
+			int cand = j + ku + jp;
+			if (cand > n - 1) cand = n - 1;
+			if (cand > ju) ju = cand;
+			if (jp != 0) {
+				for (int c = lane; c <= ju - j; c += 32) {
+					const double tmp = DG(kv + jp - c, j + c);
+					DG(kv + jp - c, j + c) = DG(kv - c, j + c);
+					DG(kv - c, j + c) = tmp;
+				}
+			}
+			__syncwarp();
+			if (km > 0) {
+				const double r = 1.0 / DG(kv, j);
+				__syncwarp();
+				for (int i = 1 + lane; i <= km; i += 32) {
+					DG(kv + i, j) *= r;
+				}
+				__syncwarp();
+				const int nc = ju - j;
+				for (int q = lane; q < km * nc; q += 32) {
+					const int i = 1 + q / nc;
+					const int c = 1 + q % nc;
+					const double y = DG(kv - c, j + c);
+					if (y != 0.0) {
+						DG(kv + i - c, j + c) -= DG(kv + i, j) * y;
+					}
+				}
+			}
+		} else if (info == 0) {
+			info = j + 1;
+		}
+		if (j < n - 1) {
+			if (lane == 0 && piv != j) {
+				const double tmp = F(piv);
+				F(piv) = F(j);
+				F(j) = tmp;
+			}
+			__syncwarp();
+			const double bj = F(j);
+			for (int i = 1 + lane; i <= km; i += 32) {
+				F(j + i) -= DG(kv + i, j) * bj;
+			}
+		}
+		__syncwarp();
+	}
+	if (info == 0) {
+		// dtbsv: upper, no transpose, non-unit diagonal, bandwidth kv
+		for (int j = n - 1; j >= 0; j--) {
+			const double bj = F(j);
+			if (bj != 0.0) {
+				const double temp = bj / DG(kv, j);
+				__syncwarp();
+				if (lane == 0) F(j) = temp;
+				const int lo = (j - kv > 0) ? (j - kv) : 0;
+				for (int i = j - 1 - lane; i >= lo; i -= 32) {
+					F(i) -= temp * DG(kv - (j - i), j);
+				}
+			}
+			__syncwarp();
+		}
+	}
+	if (info != 0 || !(F(0) == F(0))) {
+		if (lane == 0) atomicMax(ca.info, ca.col0 + tcol + 1);
+	}
+	if (ca.assemble_only) return;
+
+	// ---- x = x0 - delta, scattered to the column and its duplicates ------------
+	const int * dups = ca.col_dups + (size_t)(ca.col0 + tcol) * 3;
+	for (int q = -1; q < 3; q++) {
+		int tgt = node;
+		if (q >= 0) {
+			tgt = dups[q];
+			if (tgt < 0) continue;
+		}
+		const long long te = tgt / NN;
+		const int tn = tgt % NN;
+		const size_t tb = (size_t)te * lay.nrows * NN + tn;
+		double * oP = out + tb + (size_t)lay.rowoff[PIx] * NN;
+		double * oW = out + tb + (size_t)lay.rowoff[WIx] * NN;
+		double * oR = out + tb + (size_t)lay.rowoff[RIx] * NN;
+		for (int k = lane; k <= L; k += 32) {
+			if (k < L) {
+				oP[(size_t)k * NN] = snP(k) - F(3 * k + FP);
+				oR[(size_t)k * NN] = snR(k) - F(3 * k + FR);
+			}
+			oW[(size_t)k * NN] = seW(k) - F(3 * k + FW);
+		}
+	}
+}
+
 #endif

@@ -219,6 +219,13 @@ inline double __shfl_down_sync(unsigned m, double v, unsigned delta, int width =
 	return __shfl_sync(m, v, (int)((l + delta < (unsigned)width) ? l + delta : l), width);
 }
 
+inline int __shfl_sync(unsigned m, int v, int src, int width = 32) {
+	return (int)__shfl_sync(m, (double)v, src, width);
+}
+inline int __shfl_down_sync(unsigned m, int v, unsigned delta, int width = 32) {
+	return (int)__shfl_down_sync(m, (double)v, delta, width);
+}
+
 inline double __ldg(const double * p) { return *p; }
 inline int __ldg(const int * p) { return *p; }
 inline double atomicAdd(double * p, double v) { double o = *p; *p += v; return o; }
