@@ -341,7 +341,7 @@ extern "C" int tb200_commit_layout(tb200_ctx * ctx) {
 		ctx->ncols = (int)cn.size();
 		if (dupload(ctx, &ctx->d_col_node, cn)) return 1;
 		if (dupload(ctx, &ctx->d_col_dups, cd)) return 1;
-		ctx->ws_cols = std::min(ctx->ncols, 1 << 16);
+		ctx->ws_cols = std::min(ctx->ncols, 1 << 17);
 		const size_t wsd = (size_t)tb_column_ws_entries(L, ctx->offd) * ctx->ws_cols;
 		if (dalloc(ctx, &ctx->d_ws, wsd)) return 1;
 	}
@@ -846,8 +846,29 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 			if (per_sm > best) { best = per_sm; wpb = w; }
 		}
 	}
+	// default: thread per column with a sliding band window in shared memory
+	// (vertical order 1); TB200_COLUMN_KERNEL = thread | warp | window overrides
 	const char * force = getenv("TB200_COLUMN_KERNEL");
-	if (force != 0 && strcmp(force, "thread") == 0) wpb = 0;
+	bool use_window = (ctx->offd == TBW_KL);
+	if (force != 0 && strcmp(force, "thread") == 0) { wpb = 0; use_window = false; }
+	if (force != 0 && strcmp(force, "warp") == 0) use_window = false;
+	if (force == 0 || strcmp(force, "warp") != 0) { if (use_window) wpb = 0; }
+	if (use_window) {
+		const size_t smem = tb_column_window_smem_bytes();
+		auto kfn = k_column_implicit_window;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		for (int c0 = 0; c0 < ctx->ncols; c0 += ctx->ws_cols) {
+			ca.col0 = c0;
+			ca.ncols = std::min(ctx->ws_cols, ctx->ncols - c0);
+			TB_LAUNCH_FLAT(kfn, dim3((ca.ncols + TBW_THREADS - 1) / TBW_THREADS), dim3(TBW_THREADS),
+				smem, ctx->stream, lay, ctx->geom, ctx->ops, ctx->phys, ca,
+				(const double *)ctx->inst[in], ctx->inst[out]);
+			TB_KERNEL_CHECK(ctx);
+		}
+		return 0;
+	}
 
 	if (wpb > 0) {
 		ca.col0 = 0;

@@ -936,4 +936,453 @@ __global__ void k_column_implicit_warp(
 	}
 }
 
+
+///////////////////////////////////////////////////////////////////////////////
+// One thread per column with a sliding band window in shared memory
+// (vertical order 1: kl = ku = 4).
+//
+// The banded Jacobian is never materialised.  Rows are generated level by
+// level straight from the state and the metric terms (every derived column
+// quantity is recomputed from its definition when needed), enter a ring of
+// TBW_COLS band columns held in shared memory as [entry][thread], and leave it
+// as finished columns of U, which - with the forward-substituted right-hand
+// side - stream to a global scratch laid out [entry][column] for the
+// back substitution.  The elimination is LAPACK's dgbtf2 step for step
+// (same pivot search, row interchange, reciprocal scaling and rank-1 update)
+// and the back substitution is dtbsv; each Jacobian entry is accumulated in
+// the reference's statement order, so the arithmetic matches
+// k_column_implicit.  Per column the global traffic is the inputs
+// (~6 kB) plus 10 n doubles written and read once (~15 kB at L = 30) instead
+// of several passes over a 17 kB work area.
+
+#define TBW_KL 4
+#define TBW_KV 8
+#define TBW_LDAB 13
+#define TBW_COLS 12
+#define TBW_FRING 8
+#define TBW_THREADS 64
+
+__host__ __device__ inline size_t tb_column_window_smem_bytes() {
+	return (size_t)(TBW_COLS * TBW_LDAB + TBW_FRING) * TBW_THREADS * sizeof(double);
+}
+// scratch doubles per column: U columns (9 n) + right-hand side (n)
+__host__ __device__ inline int tb_column_window_scratch(int L) {
+	return 10 * 3 * (L + 1);
+}
+
+__global__ void __launch_bounds__(TBW_THREADS)
+k_column_implicit_window(
+	DevLayout lay, DevGeom g, DevOps ops, DevPhys ph, ColumnArgs ca,
+	const double * in, double * out   // may alias
+) {
+	TB_DYN_SMEM(double, sm);
+	const int t = threadIdx.x;
+	const int tcol = blockIdx.x * TBW_THREADS + t;
+	if (tcol >= ca.ncols) return;
+
+	const int UIx = 0, VIx = 1, PIx = 2, WIx = 3, RIx = 4;
+	const int FP = 0, FW = 1, FR = 2;
+	const int NN = lay.nn;
+	const int L = lay.nlev;
+	const int n = 3 * (L + 1);
+	const int kl = TBW_KL, kv = TBW_KV;
+
+	const int node = ca.col_node[ca.col0 + tcol];
+	const long long e = node / NN;
+	const int nd = node % NN;
+	const size_t ebase = (size_t)e * lay.nrows * NN;
+	const size_t g3 = (size_t)e * L * NN + nd;
+	const size_t g3e = (size_t)e * (L + 1) * NN + nd;
+
+	double * win = sm + t;
+	double * fr = sm + (size_t)TBW_COLS * TBW_LDAB * TBW_THREADS + t;
+	// A(i, c): band row kv + i - c of ring column c
+#define WIN(i, c) win[(((c) % TBW_COLS) * TBW_LDAB + (kv + (i) - (c))) * TBW_THREADS]
+#define WINB(r, c) win[(((c) % TBW_COLS) * TBW_LDAB + (r)) * TBW_THREADS]
+#define FRING(i) fr[((i) % TBW_FRING) * TBW_THREADS]
+	// scratch: U column j -> entries [9 j, 9 j + 9), right-hand side -> 9 n + j
+	double * sc = ca.ws + tcol;
+	const size_t S = (size_t)ca.ws_stride;
+
+	const DevOp & opInterpN2E = ops.op[0];
+	const DevOp & opInterpE2N = ops.op[1];
+	const DevOp & opDiffN2E = ops.op[3];
+	const DevOp & opDiffE2N = ops.op[4];
+	const DevOp & opDDE2E = ops.op[7];
+	const DevOp & opPenL = ops.op[8];
+	const DevOp & opPenR = ops.op[9];
+
+	const double * inU = in + ebase + (size_t)lay.rowoff[UIx] * NN + nd;
+	const double * inV = in + ebase + (size_t)lay.rowoff[VIx] * NN + nd;
+	const double * inP = in + ebase + (size_t)lay.rowoff[PIx] * NN + nd;
+	const double * inW = in + ebase + (size_t)lay.rowoff[WIx] * NN + nd;
+	const double * inR = in + ebase + (size_t)lay.rowoff[RIx] * NN + nd;
+
+	// ---- column quantities, recomputed from their definitions ----------------
+	// (PrepareColumn, VerticalDynamicsFEM.cpp:1839-2179)
+	auto seU = [&](int m) { return tb_col_apply(opInterpN2E, inU, NN, m); };
+	auto seV = [&](int m) { return tb_col_apply(opInterpN2E, inV, NN, m); };
+	auto seP = [&](int m) { return tb_col_apply(opInterpN2E, inP, NN, m); };
+	auto seR = [&](int m) { return tb_col_apply(opInterpN2E, inR, NN, m); };
+	auto snW = [&](int l) { return tb_col_apply(opInterpE2N, inW, NN, l); };
+	auto exn = [&](int l) {
+		return ph.cp * exp(ph.exner_c1 * log(ph.exner_c2 * inP[(size_t)l * NN]));
+	};
+	auto xde = [&](int m) {
+		if (m <= 0 || m >= L) return 0.0;
+		const size_t o = g3e + (size_t)m * NN;
+		return g.cxe[0][o] * seU(m) + g.cxe[1][o] * seV(m) + g.cxe[2][o] * inW[(size_t)m * NN];
+	};
+	auto xdn = [&](int l) {
+		const size_t o = g3 + (size_t)l * NN;
+		return g.cx[0][o] * inU[(size_t)l * NN] + g.cx[1][o] * inV[(size_t)l * NN]
+			+ g.cx[2][o] * snW(l);
+	};
+	auto ken = [&](int l) {
+		const size_t o = g3 + (size_t)l * NN;
+		const double dCovUa = inU[(size_t)l * NN], dCovUb = inV[(size_t)l * NN];
+		const double dCovUx = snW(l);
+		const double cx0 = g.cx[0][o], cx1 = g.cx[1][o], cx2 = g.cx[2][o];
+		const double dConUa = g.ca[0][o] * dCovUa + g.ca[1][o] * dCovUb + g.ca[2][o] * dCovUx;
+		const double dConUb = g.cb[0][o] * dCovUa + g.cb[1][o] * dCovUb + g.cb[2][o] * dCovUx;
+		const double dConUx = cx0 * dCovUa + cx1 * dCovUb + cx2 * dCovUx;
+		return 0.5 * (dConUa * dCovUa + dConUb * dCovUb + dConUx * dCovUx);
+	};
+	auto ddW = [&](int m) {
+		if (m <= 0 || m >= L) return 0.0;
+		return tb_col_apply(opDDE2E, inW, NN, m);
+	};
+
+	const int vo = ca.fe_nodes;
+	const int nfe = L / vo;
+	const double dInvDeltaT = 1.0 / ca.dt;
+
+	// zero the ring
+	for (int q = 0; q < TBW_COLS * TBW_LDAB; q++) {
+		win[(size_t)q * TBW_THREADS] = 0.0;
+	}
+
+	// exn / ken of the two levels around the current interface are reused
+	int cache_l = -1000;
+	double exn_a = 0.0, exn_b = 0.0, ken_a = 0.0, ken_b = 0.0;   // levels cache_l, cache_l+1
+	double xde_k = 0.0, xde_kp1 = 0.0;
+
+	// ---- rows of level k into the window (BuildF + Jacobian) -------------------
+	auto assemble_level = [&](int k) {
+		// sliding caches: interface quantities at k and k+1, level quantities at k-1, k
+		xde_k = (k == 0) ? 0.0 : xde_kp1;
+		xde_kp1 = xde(k + 1);
+		if (k < L) {
+			if (cache_l == k - 1 && k >= 1) {
+				exn_a = exn_b; ken_a = ken_b;
+			} else if (k >= 1) {
+				exn_a = exn(k - 1); ken_a = ken(k - 1);
+			}
+			exn_b = exn(k); ken_b = ken(k);
+			cache_l = k;
+		}
+		auto exn_at = [&](int l) {
+			if (l == cache_l - 1 && l >= 0) return exn_a;
+			if (l == cache_l) return exn_b;
+			return exn(l);
+		};
+		auto ken_at = [&](int l) {
+			if (l == cache_l - 1 && l >= 0) return ken_a;
+			if (l == cache_l) return ken_b;
+			return ken(l);
+		};
+		auto xde_at = [&](int m) {
+			if (m == k) return xde_k;
+			if (m == k + 1) return xde_kp1;
+			return xde(m);
+		};
+		auto mfe = [&](int m) {
+			if (m <= 0 || m >= L) return 0.0;
+			return g.jace[g3e + (size_t)m * NN] * seR(m) * xde_at(m);
+		};
+		auto pfe = [&](int m) {
+			if (m <= 0 || m >= L) return 0.0;
+			return g.jace[g3e + (size_t)m * NN] * seP(m) * xde_at(m);
+		};
+
+		double fP = 0.0, fW = 0.0, fR = 0.0;
+		const int rP = 3 * k + FP, rW = 3 * k + FW, rR = 3 * k + FR;
+		if (k < L) {
+			const double invj = 1.0 / g.jac[g3 + (size_t)k * NN];
+			double dmfn = 0.0, dpfn = 0.0;
+			for (int m = opDiffE2N.begin[k]; m < opDiffE2N.end[k]; m++) {
+				const double c = tb_op_coeff(opDiffE2N, k, m);
+				dmfn += c * mfe(m);
+				dpfn += c * pfe(m);
+			}
+			fR = dmfn * invj;
+			fP += dpfn * invj;
+			const int a = k / vo;
+			for (int cc = 0; cc < 2; cc++) {
+				const double * sn = (cc == 0) ? inP : inR;
+				double aux = 0.0;
+				if (a <= nfe - 2) {
+					aux += tb_col_apply(opPenL, sn, NN, k) * fabs(xde_at((a + 1) * vo));
+				}
+				if (a >= 1) {
+					aux += tb_col_apply(opPenR, sn, NN, k) * fabs(xde_at(a * vo));
+				}
+				if (cc == 0) fP -= aux; else fR -= aux;
+			}
+			for (int m = opDiffE2N.begin[k]; m < opDiffE2N.end[k]; m++) {
+				const double je = g.jace[g3e + (size_t)m * NN];
+				const double dm = tb_op_coeff(opDiffE2N, k, m);
+				if ((m != 0) && (m != L)) {
+					const double dMassFluxCoeff =
+						dm * je * invj * g.cxe[2][g3e + (size_t)m * NN];
+					WIN(rP, 3 * m + FW) += dMassFluxCoeff * seP(m);
+					WIN(rR, 3 * m + FW) += dMassFluxCoeff * seR(m);
+				}
+				for (int q = opInterpN2E.begin[m]; q < opInterpN2E.end[m]; q++) {
+					const double dCoeffVerticalFlux =
+						dm * je * invj * tb_op_coeff(opInterpN2E, m, q) * xde_at(m);
+					WIN(rR, 3 * q + FR) += dCoeffVerticalFlux;
+					WIN(rP, 3 * q + FP) += dCoeffVerticalFlux;
+				}
+			}
+		}
+		if (k >= 1 && k < L) {
+			const size_t o = g3e + (size_t)k * NN;
+			double dPe = 0.0, dkee = 0.0;
+			for (int l = opDiffN2E.begin[k]; l < opDiffN2E.end[k]; l++) {
+				const double c = tb_op_coeff(opDiffN2E, k, l);
+				if (c != 0.0) {
+					dPe += c * exn_at(l);
+					dkee += c * ken_at(l);
+				}
+			}
+			const double sePk = seP(k), seRk = seR(k);
+			const double dPressureGradientForce = dPe * sePk / seRk;
+			double f = dPressureGradientForce;
+			f += ph.g * g.dre[2][o];
+			const double dCovUa = seU(k), dCovUb = seV(k), dCovUx = inW[(size_t)k * NN];
+			const double dConUa = g.cae[0][o] * dCovUa + g.cae[1][o] * dCovUb + g.cae[2][o] * dCovUx;
+			const double dConUb = g.cbe[0][o] * dCovUa + g.cbe[1][o] * dCovUb + g.cbe[2][o] * dCovUx;
+			const double dUa = tb_col_apply(opDiffN2E, inU, NN, k);
+			const double dUb = tb_col_apply(opDiffN2E, inV, NN, k);
+			const double dCurlTerm = -dConUa * dUa - dConUb * dUb;
+			f += (dkee + dCurlTerm);
+			fW = f;
+			const double dRHSWCoeffA = sePk * ph.R / (seRk * ph.cv);
+			for (int m = opDiffN2E.begin[k]; m < opDiffN2E.end[k]; m++) {
+				const double c = tb_op_coeff(opDiffN2E, k, m);
+				if (c != 0.0) {
+					WIN(rW, 3 * m + FP) += dRHSWCoeffA * c * exn_at(m) / inP[(size_t)m * NN];
+				}
+			}
+			const double dRHSWCoeffB = 1.0 / (seRk * seRk) * dPe;
+			for (int q = opInterpN2E.begin[k]; q < opInterpN2E.end[k]; q++) {
+				const double dRHSWCoeffC = dRHSWCoeffB * tb_op_coeff(opInterpN2E, k, q);
+				WIN(rW, 3 * q + FP) += dRHSWCoeffC * seRk;
+				WIN(rW, 3 * q + FR) += -dRHSWCoeffC * sePk;
+			}
+			for (int l = opDiffN2E.begin[k]; l < opDiffN2E.end[k]; l++) {
+				const double cl = tb_op_coeff(opDiffN2E, k, l);
+				if (cl == 0.0) continue;
+				const double xn = xdn(l);
+				for (int m = opInterpE2N.begin[l]; m < opInterpE2N.end[l]; m++) {
+					WIN(rW, 3 * m + FW) += tb_op_coeff(opInterpE2N, l, m) * cl * xn;
+				}
+			}
+		}
+		{
+			const double d2 = ddW(k);
+			fW -= ca.upwind_coeff * fabs(xde_k) * d2;
+			double dSignWeight;
+			const double cx2 = g.cxe[2][g3e + (size_t)k * NN];
+			if (xde_k > 0.0) {
+				dSignWeight = 1.0 * cx2;
+			} else if (xde_k < 0.0) {
+				dSignWeight = -1.0 * cx2;
+			} else {
+				dSignWeight = 0.0;
+			}
+			WIN(rW, rW) -= ca.upwind_coeff * dSignWeight * d2;
+			for (int q = opDDE2E.begin[k]; q < opDDE2E.end[k]; q++) {
+				WIN(rW, 3 * q + FW) -=
+					ca.upwind_coeff * fabs(xde_k) * tb_op_coeff(opDDE2E, k, q);
+			}
+		}
+		if (k < L) {
+			const int a = k / vo;
+			for (int cc = 0; cc < 2; cc++) {
+				const double * sn = (cc == 0) ? inP : inR;
+				const int fc = (cc == 0) ? FP : FR;
+				const int rr = 3 * k + fc;
+				for (int side = 0; side < 2; side++) {
+					const bool right = (side == 0);
+					if (right && a < 1) continue;
+					if (!right && a > nfe - 2) continue;
+					const int ke = right ? (a * vo) : ((a + 1) * vo);
+					const DevOp & op = right ? opPenR : opPenL;
+					const double xd = xde_at(ke);
+					const double dWeight = fabs(xd);
+					const double cx2 = g.cxe[2][g3e + (size_t)ke * NN];
+					double dSignWeight;
+					if (xd > 0.0) {
+						dSignWeight = 1.0 * cx2;
+					} else if (xd < 0.0) {
+						dSignWeight = -1.0 * cx2;
+					} else {
+						dSignWeight = 0.0;
+					}
+					for (int q = op.begin[k]; q < op.end[k]; q++) {
+						WIN(rr, 3 * ke + FW) -=
+							dSignWeight * tb_op_coeff(op, k, q) * sn[(size_t)q * NN];
+					}
+					for (int q = op.begin[k]; q < op.end[k]; q++) {
+						WIN(rr, 3 * q + fc) -= dWeight * tb_op_coeff(op, k, q);
+					}
+				}
+			}
+		}
+		if (k == 0 || k == L) fW = 0.0;
+		WIN(rP, rP) += dInvDeltaT;
+		WIN(rW, rW) += dInvDeltaT;
+		WIN(rR, rR) += dInvDeltaT;
+		FRING(rP) = fP;
+		FRING(rW) = fW;
+		FRING(rR) = fR;
+	};
+
+	// ---- dgbtf2 + forward substitution over the sliding window ------------------
+	int info = 0;
+	int ju = 0;
+	int next_level = 0;
+	for (int j = 0; j < n; j++) {
+		while (next_level <= L && 3 * next_level <= j + kl) {
+			assemble_level(next_level);
+			next_level++;
+		}
+		const int km = (kl < n - 1 - j) ? kl : (n - 1 - j);
+		int jp = 0;
+		double amax = fabs(WINB(kv, j));
+		for (int i = 1; i <= km; i++) {
+			const double v = fabs(WINB(kv + i, j));
+			if (v > amax) { amax = v; jp = i; }
+		}
+		const int piv = jp + j;
+		if (WINB(kv + jp, j) != 0.0) {
+			int cand = j + kl + jp;      // ku == kl
+			if (cand > n - 1) cand = n - 1;
+			if (cand > ju) ju = cand;
+			if (jp != 0) {
+				for (int c = 0; c <= ju - j; c++) {
+					const double tmp = WINB(kv + jp - c, j + c);
+					WINB(kv + jp - c, j + c) = WINB(kv - c, j + c);
+					WINB(kv - c, j + c) = tmp;
+				}
+			}
+			if (km > 0) {
+				const double r = 1.0 / WINB(kv, j);
+				double mult[TBW_KL + 1];
+#pragma unroll
+				for (int i = 1; i <= TBW_KL; i++) {
+					if (i <= km) {
+						mult[i] = WINB(kv + i, j) * r;
+					} else {
+						mult[i] = 0.0;
+					}
+				}
+				for (int c = 1; c <= ju - j; c++) {
+					const double y = WINB(kv - c, j + c);
+					if (y != 0.0) {
+#pragma unroll
+						for (int i = 1; i <= TBW_KL; i++) {
+							if (i <= km) {
+								WINB(kv + i - c, j + c) -= mult[i] * y;
+							}
+						}
+					}
+				}
+				if (j < n - 1) {
+					if (piv != j) {
+						const double tmp = FRING(piv);
+						FRING(piv) = FRING(j);
+						FRING(j) = tmp;
+					}
+					const double bj = FRING(j);
+#pragma unroll
+					for (int i = 1; i <= TBW_KL; i++) {
+						if (i <= km) {
+							FRING(j + i) -= mult[i] * bj;
+						}
+					}
+				}
+			}
+		} else {
+			if (info == 0) info = j + 1;
+			if (j < n - 1 && piv != j) {
+				const double tmp = FRING(piv);
+				FRING(piv) = FRING(j);
+				FRING(j) = tmp;
+			}
+		}
+		// column j of U and entry j of the right-hand side are final
+#pragma unroll
+		for (int r = 0; r <= TBW_KV; r++) {
+			sc[(size_t)(9 * j + r) * S] = WINB(r, j);
+		}
+		sc[(size_t)(9 * n + j) * S] = FRING(j);
+		// the slot now belongs to column j + TBW_COLS: start it out as zero
+		// (this also is dgbtf2's zeroing of the fill-in rows)
+#pragma unroll
+		for (int r = 0; r < TBW_LDAB; r++) {
+			WINB(r, j) = 0.0;
+		}
+	}
+	if (info != 0) {
+		atomicMax(ca.info, ca.col0 + tcol + 1);
+		return;
+	}
+	if (ca.assemble_only) return;
+
+	// ---- dtbsv (upper, non-unit) with x = x0 - delta scattered as it appears ----
+	const int * dups = ca.col_dups + (size_t)(ca.col0 + tcol) * 3;
+	const int d0 = dups[0], d1 = dups[1], d2 = dups[2];
+	// right-hand side ring (entries j-9..j live): reuse the now free window
+	double * br = win;   // br[(i % 16) * TBW_THREADS]
+#define BR(i) br[((i) & 15) * TBW_THREADS]
+	for (int i = n - 1; i >= n - 1 - kv && i >= 0; i--) {
+		BR(i) = sc[(size_t)(9 * n + i) * S];
+	}
+	bool nan_seen = false;
+	for (int j = n - 1; j >= 0; j--) {
+		double xj = BR(j);
+		if (xj != 0.0) {
+			xj = xj / sc[(size_t)(9 * j + kv) * S];
+			const int lo = (j - kv > 0) ? (j - kv) : 0;
+			for (int i = j - 1; i >= lo; i--) {
+				BR(i) -= xj * sc[(size_t)(9 * j + kv - (j - i)) * S];
+			}
+		}
+		if (j - kv - 1 >= 0) {
+			BR(j - kv - 1) = sc[(size_t)(9 * n + (j - kv - 1)) * S];
+		}
+		if (j == 0 && !(xj == xj)) nan_seen = true;
+		// delta_j known: write the updated unknown
+		const int k = j / 3;
+		const int c = j - 3 * k;
+		if (c == FW || k < L) {
+			const int rowoff = (c == FP) ? lay.rowoff[PIx] : ((c == FW) ? lay.rowoff[WIx] : lay.rowoff[RIx]);
+			const double x0 = in[ebase + (size_t)(rowoff + k) * NN + nd];
+			const double xnew = x0 - xj;
+			out[ebase + (size_t)(rowoff + k) * NN + nd] = xnew;
+			if (d0 >= 0) out[((size_t)(d0 / NN) * lay.nrows + rowoff + k) * NN + (d0 % NN)] = xnew;
+			if (d1 >= 0) out[((size_t)(d1 / NN) * lay.nrows + rowoff + k) * NN + (d1 % NN)] = xnew;
+			if (d2 >= 0) out[((size_t)(d2 / NN) * lay.nrows + rowoff + k) * NN + (d2 % NN)] = xnew;
+		}
+	}
+	if (nan_seen) atomicMax(ca.info, ca.col0 + tcol + 1);
+#undef BR
+#undef WIN
+#undef WINB
+#undef FRING
+}
+
 #endif
