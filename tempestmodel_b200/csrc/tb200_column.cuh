@@ -1018,29 +1018,81 @@ k_column_implicit_window(
 	const double * inW = in + ebase + (size_t)lay.rowoff[WIx] * NN + nd;
 	const double * inR = in + ebase + (size_t)lay.rowoff[RIx] * NN + nd;
 
-	// ---- column quantities, recomputed from their definitions ----------------
-	// (PrepareColumn, VerticalDynamicsFEM.cpp:1839-2179)
-	auto seU = [&](int m) { return tb_col_apply(opInterpN2E, inU, NN, m); };
-	auto seV = [&](int m) { return tb_col_apply(opInterpN2E, inV, NN, m); };
-	auto seP = [&](int m) { return tb_col_apply(opInterpN2E, inP, NN, m); };
-	auto seR = [&](int m) { return tb_col_apply(opInterpN2E, inR, NN, m); };
-	auto snW = [&](int l) { return tb_col_apply(opInterpE2N, inW, NN, l); };
-	auto exn = [&](int l) {
-		return ph.cp * exp(ph.exner_c1 * log(ph.exner_c2 * inP[(size_t)l * NN]));
+	// ---- column quantities (PrepareColumn, VerticalDynamicsFEM.cpp:1839-2179) --
+	// Inputs are held in a register window that slides with the level being
+	// assembled (levels kcur-2..kcur+1, interfaces kcur-1..kcur+1): each state
+	// value is loaded from global memory once.  Anything outside the window
+	// (never the case for order-1 operators) falls back to a global load.
+	int kcur = 0;
+	double Uw0 = 0.0, Uw1 = 0.0, Uw2 = 0.0, Uw3 = 0.0;
+	double Vw0 = 0.0, Vw1 = 0.0, Vw2 = 0.0, Vw3 = 0.0;
+	double Pw0 = 0.0, Pw1 = 0.0, Pw2 = 0.0, Pw3 = 0.0;
+	double Rw0 = 0.0, Rw1 = 0.0, Rw2 = 0.0, Rw3 = 0.0;
+	double Ww0 = 0.0, Ww1 = 0.0, Ww2 = 0.0;
+	auto getU = [&](int l) {
+		const int d = l - (kcur - 2);
+		return (d == 0) ? Uw0 : (d == 1) ? Uw1 : (d == 2) ? Uw2 : (d == 3) ? Uw3 : inU[(size_t)l * NN];
 	};
-	auto xde = [&](int m) {
-		if (m <= 0 || m >= L) return 0.0;
-		const size_t o = g3e + (size_t)m * NN;
-		return g.cxe[0][o] * seU(m) + g.cxe[1][o] * seV(m) + g.cxe[2][o] * inW[(size_t)m * NN];
+	auto getV = [&](int l) {
+		const int d = l - (kcur - 2);
+		return (d == 0) ? Vw0 : (d == 1) ? Vw1 : (d == 2) ? Vw2 : (d == 3) ? Vw3 : inV[(size_t)l * NN];
+	};
+	auto getP = [&](int l) {
+		const int d = l - (kcur - 2);
+		return (d == 0) ? Pw0 : (d == 1) ? Pw1 : (d == 2) ? Pw2 : (d == 3) ? Pw3 : inP[(size_t)l * NN];
+	};
+	auto getR = [&](int l) {
+		const int d = l - (kcur - 2);
+		return (d == 0) ? Rw0 : (d == 1) ? Rw1 : (d == 2) ? Rw2 : (d == 3) ? Rw3 : inR[(size_t)l * NN];
+	};
+	auto getW = [&](int m) {
+		const int d = m - (kcur - 1);
+		return (d == 0) ? Ww0 : (d == 1) ? Ww1 : (d == 2) ? Ww2 : inW[(size_t)m * NN];
+	};
+	auto slide = [&](int k) {
+		// window for level k; called with k = 0, 1, 2, ... in order
+		kcur = k;
+		if (k == 0) {
+			Uw2 = inU[0]; Vw2 = inV[0]; Pw2 = inP[0]; Rw2 = inR[0];
+			if (L > 1) {
+				Uw3 = inU[NN]; Vw3 = inV[NN]; Pw3 = inP[NN]; Rw3 = inR[NN];
+			}
+			Ww1 = inW[0];
+			Ww2 = inW[NN];
+		} else {
+			Uw0 = Uw1; Uw1 = Uw2; Uw2 = Uw3;
+			Vw0 = Vw1; Vw1 = Vw2; Vw2 = Vw3;
+			Pw0 = Pw1; Pw1 = Pw2; Pw2 = Pw3;
+			Rw0 = Rw1; Rw1 = Rw2; Rw2 = Rw3;
+			if (k + 1 < L) {
+				const size_t o = (size_t)(k + 1) * NN;
+				Uw3 = inU[o]; Vw3 = inV[o]; Pw3 = inP[o]; Rw3 = inR[o];
+			}
+			Ww0 = Ww1; Ww1 = Ww2;
+			if (k + 1 <= L) Ww2 = inW[(size_t)(k + 1) * NN];
+		}
+	};
+#define TB_APPLY(op, m, get) ([&]() { \
+		double o_ = 0.0; \
+		const int b_ = (op).begin[m], e_ = (op).end[m]; \
+		const double * c_ = (op).coeff + (size_t)(m) * (op).width; \
+		for (int l_ = b_; l_ < e_; l_++) o_ += c_[l_ - b_] * get(l_); \
+		return o_; }())
+	auto seU = [&](int m) { return TB_APPLY(opInterpN2E, m, getU); };
+	auto seV = [&](int m) { return TB_APPLY(opInterpN2E, m, getV); };
+	auto seP = [&](int m) { return TB_APPLY(opInterpN2E, m, getP); };
+	auto seR = [&](int m) { return TB_APPLY(opInterpN2E, m, getR); };
+	auto snW = [&](int l) { return TB_APPLY(opInterpE2N, l, getW); };
+	auto exn = [&](int l) {
+		return ph.cp * exp(ph.exner_c1 * log(ph.exner_c2 * getP(l)));
 	};
 	auto xdn = [&](int l) {
 		const size_t o = g3 + (size_t)l * NN;
-		return g.cx[0][o] * inU[(size_t)l * NN] + g.cx[1][o] * inV[(size_t)l * NN]
-			+ g.cx[2][o] * snW(l);
+		return g.cx[0][o] * getU(l) + g.cx[1][o] * getV(l) + g.cx[2][o] * snW(l);
 	};
 	auto ken = [&](int l) {
 		const size_t o = g3 + (size_t)l * NN;
-		const double dCovUa = inU[(size_t)l * NN], dCovUb = inV[(size_t)l * NN];
+		const double dCovUa = getU(l), dCovUb = getV(l);
 		const double dCovUx = snW(l);
 		const double cx0 = g.cx[0][o], cx1 = g.cx[1][o], cx2 = g.cx[2][o];
 		const double dConUa = g.ca[0][o] * dCovUa + g.ca[1][o] * dCovUb + g.ca[2][o] * dCovUx;
@@ -1050,7 +1102,41 @@ k_column_implicit_window(
 	};
 	auto ddW = [&](int m) {
 		if (m <= 0 || m >= L) return 0.0;
-		return tb_col_apply(opDDE2E, inW, NN, m);
+		return TB_APPLY(opDDE2E, m, getW);
+	};
+	// interface metrics of the interface above the current level are reused
+	// as those of the current interface one level later
+	double cxe0_k = 0.0, cxe1_k = 0.0, cxe2_k = 0.0, jace_k = 0.0;
+	double cxe0_p = 0.0, cxe1_p = 0.0, cxe2_p = 0.0, jace_p = 0.0;
+	auto load_edge_metrics = [&](int k) {
+		if (k == 0) {
+			cxe0_k = g.cxe[0][g3e]; cxe1_k = g.cxe[1][g3e]; cxe2_k = g.cxe[2][g3e];
+			jace_k = g.jace[g3e];
+		} else {
+			cxe0_k = cxe0_p; cxe1_k = cxe1_p; cxe2_k = cxe2_p; jace_k = jace_p;
+		}
+		if (k + 1 <= L) {
+			const size_t o = g3e + (size_t)(k + 1) * NN;
+			cxe0_p = g.cxe[0][o]; cxe1_p = g.cxe[1][o]; cxe2_p = g.cxe[2][o];
+			jace_p = g.jace[o];
+		}
+	};
+	auto cxe2_at = [&](int m) {
+		return (m == kcur) ? cxe2_k : (m == kcur + 1) ? cxe2_p : g.cxe[2][g3e + (size_t)m * NN];
+	};
+	auto jace_at = [&](int m) {
+		return (m == kcur) ? jace_k : (m == kcur + 1) ? jace_p : g.jace[g3e + (size_t)m * NN];
+	};
+	auto xde = [&](int m) {
+		if (m <= 0 || m >= L) return 0.0;
+		double c0, c1, c2;
+		if (m == kcur) { c0 = cxe0_k; c1 = cxe1_k; c2 = cxe2_k; }
+		else if (m == kcur + 1) { c0 = cxe0_p; c1 = cxe1_p; c2 = cxe2_p; }
+		else {
+			const size_t o = g3e + (size_t)m * NN;
+			c0 = g.cxe[0][o]; c1 = g.cxe[1][o]; c2 = g.cxe[2][o];
+		}
+		return c0 * seU(m) + c1 * seV(m) + c2 * getW(m);
 	};
 
 	const int vo = ca.fe_nodes;
@@ -1064,23 +1150,32 @@ k_column_implicit_window(
 
 	// exn / ken of the two levels around the current interface are reused
 	int cache_l = -1000;
-	double exn_a = 0.0, exn_b = 0.0, ken_a = 0.0, ken_b = 0.0;   // levels cache_l, cache_l+1
+	double exn_a = 0.0, exn_b = 0.0, ken_a = 0.0, ken_b = 0.0;   // levels cache_l-1, cache_l
+	double xdn_a = 0.0, xdn_b = 0.0;
 	double xde_k = 0.0, xde_kp1 = 0.0;
 
 	// ---- rows of level k into the window (BuildF + Jacobian) -------------------
 	auto assemble_level = [&](int k) {
-		// sliding caches: interface quantities at k and k+1, level quantities at k-1, k
+		// slide the input window, then the caches: interface quantities at k
+		// and k+1, level quantities at k-1 and k
+		slide(k);
+		load_edge_metrics(k);
 		xde_k = (k == 0) ? 0.0 : xde_kp1;
 		xde_kp1 = xde(k + 1);
 		if (k < L) {
 			if (cache_l == k - 1 && k >= 1) {
-				exn_a = exn_b; ken_a = ken_b;
+				exn_a = exn_b; ken_a = ken_b; xdn_a = xdn_b;
 			} else if (k >= 1) {
-				exn_a = exn(k - 1); ken_a = ken(k - 1);
+				exn_a = exn(k - 1); ken_a = ken(k - 1); xdn_a = xdn(k - 1);
 			}
-			exn_b = exn(k); ken_b = ken(k);
+			exn_b = exn(k); ken_b = ken(k); xdn_b = xdn(k);
 			cache_l = k;
 		}
+		auto xdn_at = [&](int l) {
+			if (l == cache_l - 1 && l >= 0) return xdn_a;
+			if (l == cache_l) return xdn_b;
+			return xdn(l);
+		};
 		auto exn_at = [&](int l) {
 			if (l == cache_l - 1 && l >= 0) return exn_a;
 			if (l == cache_l) return exn_b;
@@ -1098,11 +1193,11 @@ k_column_implicit_window(
 		};
 		auto mfe = [&](int m) {
 			if (m <= 0 || m >= L) return 0.0;
-			return g.jace[g3e + (size_t)m * NN] * seR(m) * xde_at(m);
+			return jace_at(m) * seR(m) * xde_at(m);
 		};
 		auto pfe = [&](int m) {
 			if (m <= 0 || m >= L) return 0.0;
-			return g.jace[g3e + (size_t)m * NN] * seP(m) * xde_at(m);
+			return jace_at(m) * seP(m) * xde_at(m);
 		};
 
 		double fP = 0.0, fW = 0.0, fR = 0.0;
@@ -1119,22 +1214,23 @@ k_column_implicit_window(
 			fP += dpfn * invj;
 			const int a = k / vo;
 			for (int cc = 0; cc < 2; cc++) {
-				const double * sn = (cc == 0) ? inP : inR;
 				double aux = 0.0;
 				if (a <= nfe - 2) {
-					aux += tb_col_apply(opPenL, sn, NN, k) * fabs(xde_at((a + 1) * vo));
+					const double pl = (cc == 0) ? TB_APPLY(opPenL, k, getP) : TB_APPLY(opPenL, k, getR);
+					aux += pl * fabs(xde_at((a + 1) * vo));
 				}
 				if (a >= 1) {
-					aux += tb_col_apply(opPenR, sn, NN, k) * fabs(xde_at(a * vo));
+					const double pr = (cc == 0) ? TB_APPLY(opPenR, k, getP) : TB_APPLY(opPenR, k, getR);
+					aux += pr * fabs(xde_at(a * vo));
 				}
 				if (cc == 0) fP -= aux; else fR -= aux;
 			}
 			for (int m = opDiffE2N.begin[k]; m < opDiffE2N.end[k]; m++) {
-				const double je = g.jace[g3e + (size_t)m * NN];
+				const double je = jace_at(m);
 				const double dm = tb_op_coeff(opDiffE2N, k, m);
 				if ((m != 0) && (m != L)) {
 					const double dMassFluxCoeff =
-						dm * je * invj * g.cxe[2][g3e + (size_t)m * NN];
+						dm * je * invj * cxe2_at(m);
 					WIN(rP, 3 * m + FW) += dMassFluxCoeff * seP(m);
 					WIN(rR, 3 * m + FW) += dMassFluxCoeff * seR(m);
 				}
@@ -1160,11 +1256,11 @@ k_column_implicit_window(
 			const double dPressureGradientForce = dPe * sePk / seRk;
 			double f = dPressureGradientForce;
 			f += ph.g * g.dre[2][o];
-			const double dCovUa = seU(k), dCovUb = seV(k), dCovUx = inW[(size_t)k * NN];
+			const double dCovUa = seU(k), dCovUb = seV(k), dCovUx = getW(k);
 			const double dConUa = g.cae[0][o] * dCovUa + g.cae[1][o] * dCovUb + g.cae[2][o] * dCovUx;
 			const double dConUb = g.cbe[0][o] * dCovUa + g.cbe[1][o] * dCovUb + g.cbe[2][o] * dCovUx;
-			const double dUa = tb_col_apply(opDiffN2E, inU, NN, k);
-			const double dUb = tb_col_apply(opDiffN2E, inV, NN, k);
+			const double dUa = TB_APPLY(opDiffN2E, k, getU);
+			const double dUb = TB_APPLY(opDiffN2E, k, getV);
 			const double dCurlTerm = -dConUa * dUa - dConUb * dUb;
 			f += (dkee + dCurlTerm);
 			fW = f;
@@ -1172,7 +1268,7 @@ k_column_implicit_window(
 			for (int m = opDiffN2E.begin[k]; m < opDiffN2E.end[k]; m++) {
 				const double c = tb_op_coeff(opDiffN2E, k, m);
 				if (c != 0.0) {
-					WIN(rW, 3 * m + FP) += dRHSWCoeffA * c * exn_at(m) / inP[(size_t)m * NN];
+					WIN(rW, 3 * m + FP) += dRHSWCoeffA * c * exn_at(m) / getP(m);
 				}
 			}
 			const double dRHSWCoeffB = 1.0 / (seRk * seRk) * dPe;
@@ -1184,7 +1280,7 @@ k_column_implicit_window(
 			for (int l = opDiffN2E.begin[k]; l < opDiffN2E.end[k]; l++) {
 				const double cl = tb_op_coeff(opDiffN2E, k, l);
 				if (cl == 0.0) continue;
-				const double xn = xdn(l);
+				const double xn = xdn_at(l);
 				for (int m = opInterpE2N.begin[l]; m < opInterpE2N.end[l]; m++) {
 					WIN(rW, 3 * m + FW) += tb_op_coeff(opInterpE2N, l, m) * cl * xn;
 				}
@@ -1194,7 +1290,7 @@ k_column_implicit_window(
 			const double d2 = ddW(k);
 			fW -= ca.upwind_coeff * fabs(xde_k) * d2;
 			double dSignWeight;
-			const double cx2 = g.cxe[2][g3e + (size_t)k * NN];
+			const double cx2 = cxe2_k;
 			if (xde_k > 0.0) {
 				dSignWeight = 1.0 * cx2;
 			} else if (xde_k < 0.0) {
@@ -1211,7 +1307,6 @@ k_column_implicit_window(
 		if (k < L) {
 			const int a = k / vo;
 			for (int cc = 0; cc < 2; cc++) {
-				const double * sn = (cc == 0) ? inP : inR;
 				const int fc = (cc == 0) ? FP : FR;
 				const int rr = 3 * k + fc;
 				for (int side = 0; side < 2; side++) {
@@ -1222,7 +1317,7 @@ k_column_implicit_window(
 					const DevOp & op = right ? opPenR : opPenL;
 					const double xd = xde_at(ke);
 					const double dWeight = fabs(xd);
-					const double cx2 = g.cxe[2][g3e + (size_t)ke * NN];
+					const double cx2 = cxe2_at(ke);
 					double dSignWeight;
 					if (xd > 0.0) {
 						dSignWeight = 1.0 * cx2;
@@ -1233,7 +1328,7 @@ k_column_implicit_window(
 					}
 					for (int q = op.begin[k]; q < op.end[k]; q++) {
 						WIN(rr, 3 * ke + FW) -=
-							dSignWeight * tb_op_coeff(op, k, q) * sn[(size_t)q * NN];
+							dSignWeight * tb_op_coeff(op, k, q) * ((cc == 0) ? getP(q) : getR(q));
 					}
 					for (int q = op.begin[k]; q < op.end[k]; q++) {
 						WIN(rr, 3 * q + fc) -= dWeight * tb_op_coeff(op, k, q);
