@@ -938,34 +938,33 @@ __global__ void k_column_implicit_warp(
 
 
 ///////////////////////////////////////////////////////////////////////////////
-// One thread per column with a sliding band window in shared memory
+// One thread per column, register-resident elimination block
 // (vertical order 1: kl = ku = 4).
 //
 // The banded Jacobian is never materialised.  Rows are generated level by
-// level straight from the state and the metric terms (every derived column
-// quantity is recomputed from its definition when needed), enter a ring of
-// TBW_COLS band columns held in shared memory as [entry][thread], and leave it
-// as finished columns of U, which - with the forward-substituted right-hand
-// side - stream to a global scratch laid out [entry][column] for the
-// back substitution.  The elimination is LAPACK's dgbtf2 step for step
-// (same pivot search, row interchange, reciprocal scaling and rank-1 update)
-// and the back substitution is dtbsv; each Jacobian entry is accumulated in
-// the reference's statement order, so the arithmetic matches
-// k_column_implicit.  Per column the global traffic is the inputs
-// (~6 kB) plus 10 n doubles written and read once (~15 kB at L = 30) instead
-// of several passes over a 17 kB work area.
+// level straight from the state and the metric terms (inputs in a sliding
+// register window, each loaded once; three rows of a level are staged in
+// shared memory) and enter a 5 x 9 block of registers that holds rows
+// j..j+4, columns j..j+8 of the partially eliminated matrix - all LAPACK's
+// dgbtf2 touches at step j.  After the step the finished row j of U and the
+// forward-substituted right-hand side stream to a global scratch laid out
+// [entry][column]; the block shifts by one row and column and the next row
+// enters.  The elimination is dgbtf2 step for step (same pivot search, row
+// interchange, reciprocal scaling, rank-1 update), the back substitution
+// subtracts in dtbsv's order, and every Jacobian entry is accumulated in the
+// reference's statement order, so the arithmetic matches k_column_implicit.
+// Per column the global traffic is the inputs (~6 kB) plus 10 n doubles
+// written and read once (~15 kB at L = 30).
 
 #define TBW_KL 4
 #define TBW_KV 8
-#define TBW_LDAB 13
-#define TBW_COLS 12
-#define TBW_FRING 8
-#define TBW_THREADS 64
+#define TBW_THREADS 128
+#define TBW_STG 30     // staged doubles per thread: 3 rows x 9 band entries + 3 F
 
 __host__ __device__ inline size_t tb_column_window_smem_bytes() {
-	return (size_t)(TBW_COLS * TBW_LDAB + TBW_FRING) * TBW_THREADS * sizeof(double);
+	return (size_t)TBW_STG * TBW_THREADS * sizeof(double);
 }
-// scratch doubles per column: U columns (9 n) + right-hand side (n)
+// scratch doubles per column: rows of U (9 n) + right-hand side (n)
 __host__ __device__ inline int tb_column_window_scratch(int L) {
 	return 10 * 3 * (L + 1);
 }
@@ -994,13 +993,12 @@ k_column_implicit_window(
 	const size_t g3 = (size_t)e * L * NN + nd;
 	const size_t g3e = (size_t)e * (L + 1) * NN + nd;
 
-	double * win = sm + t;
-	double * fr = sm + (size_t)TBW_COLS * TBW_LDAB * TBW_THREADS + t;
-	// A(i, c): band row kv + i - c of ring column c
-#define WIN(i, c) win[(((c) % TBW_COLS) * TBW_LDAB + (kv + (i) - (c))) * TBW_THREADS]
-#define WINB(r, c) win[(((c) % TBW_COLS) * TBW_LDAB + (r)) * TBW_THREADS]
-#define FRING(i) fr[((i) % TBW_FRING) * TBW_THREADS]
-	// scratch: U column j -> entries [9 j, 9 j + 9), right-hand side -> 9 n + j
+	double * stg = sm + t;
+	// staged rows of the level being generated: A(i, c), i in 3k..3k+2,
+	// band entry c - i + 4 in 0..8
+#define WIN(i, c) stg[(((i) - 3 * kcur) * 9 + ((c) - (i) + 4)) * TBW_THREADS]
+#define FRING(i) stg[(27 + (i) - 3 * kcur) * TBW_THREADS]
+	// scratch: U row j -> entries [9 j, 9 j + 9), right-hand side -> 9 n + j
 	double * sc = ca.ws + tcol;
 	const size_t S = (size_t)ca.ws_stride;
 
@@ -1143,10 +1141,6 @@ k_column_implicit_window(
 	const int nfe = L / vo;
 	const double dInvDeltaT = 1.0 / ca.dt;
 
-	// zero the ring
-	for (int q = 0; q < TBW_COLS * TBW_LDAB; q++) {
-		win[(size_t)q * TBW_THREADS] = 0.0;
-	}
 
 	// exn / ken of the two levels around the current interface are reused
 	int cache_l = -1000;
@@ -1160,6 +1154,10 @@ k_column_implicit_window(
 		// and k+1, level quantities at k-1 and k
 		slide(k);
 		load_edge_metrics(k);
+#pragma unroll
+		for (int q = 0; q < 27; q++) {
+			stg[q * TBW_THREADS] = 0.0;
+		}
 		xde_k = (k == 0) ? 0.0 : xde_kp1;
 		xde_kp1 = xde(k + 1);
 		if (k < L) {
@@ -1345,90 +1343,118 @@ k_column_implicit_window(
 		FRING(rR) = fR;
 	};
 
-	// ---- dgbtf2 + forward substitution over the sliding window ------------------
+	// ---- dgbtf2 + forward substitution on the register block -------------------
+	// B[r][c] = A(j + r, j + c), bb[r] = b(j + r)
+	double B[5][9];
+	double bb[5];
+#pragma unroll
+	for (int r = 0; r < 5; r++) {
+#pragma unroll
+		for (int c = 0; c < 9; c++) B[r][c] = 0.0;
+		bb[r] = 0.0;
+	}
+	// rows 0..4 (levels 0 and 1)
+	assemble_level(0);
+#pragma unroll
+	for (int r = 0; r < 3; r++) {
+#pragma unroll
+		for (int c = 0; c < 9; c++) {
+			// row r holds columns r-4..r+4: column c is band entry c - r + 4
+			if (c - r + 4 >= 0 && c - r + 4 <= 8) B[r][c] = stg[(r * 9 + (c - r + 4)) * TBW_THREADS];
+		}
+		bb[r] = stg[(27 + r) * TBW_THREADS];
+	}
+	if (L >= 1) {
+		assemble_level(1);
+#pragma unroll
+		for (int r = 3; r < 5; r++) {
+#pragma unroll
+			for (int c = 0; c < 9; c++) {
+				if (c - r + 4 >= 0 && c - r + 4 <= 8) {
+					B[r][c] = stg[((r - 3) * 9 + (c - r + 4)) * TBW_THREADS];
+				}
+			}
+			bb[r] = stg[(27 + r - 3) * TBW_THREADS];
+		}
+	}
 	int info = 0;
-	int ju = 0;
-	int next_level = 0;
 	for (int j = 0; j < n; j++) {
-		while (next_level <= L && 3 * next_level <= j + kl) {
-			assemble_level(next_level);
-			next_level++;
-		}
 		const int km = (kl < n - 1 - j) ? kl : (n - 1 - j);
+		// idamax over rows j..j+km (first maximum)
 		int jp = 0;
-		double amax = fabs(WINB(kv, j));
-		for (int i = 1; i <= km; i++) {
-			const double v = fabs(WINB(kv + i, j));
-			if (v > amax) { amax = v; jp = i; }
+		double amax = fabs(B[0][0]);
+#pragma unroll
+		for (int r = 1; r < 5; r++) {
+			const double v = fabs(B[r][0]);
+			if (r <= km && v > amax) { amax = v; jp = r; }
 		}
-		const int piv = jp + j;
-		if (WINB(kv + jp, j) != 0.0) {
-			int cand = j + kl + jp;      // ku == kl
-			if (cand > n - 1) cand = n - 1;
-			if (cand > ju) ju = cand;
-			if (jp != 0) {
-				for (int c = 0; c <= ju - j; c++) {
-					const double tmp = WINB(kv + jp - c, j + c);
-					WINB(kv + jp - c, j + c) = WINB(kv - c, j + c);
-					WINB(kv - c, j + c) = tmp;
-				}
+		// interchange rows j and j + jp (entries beyond ju are zero in both)
+		if (jp != 0) {
+#pragma unroll
+			for (int c = 0; c < 9; c++) {
+				const double t0 = B[0][c];
+				const double s0 = (jp == 1) ? B[1][c] : (jp == 2) ? B[2][c] : (jp == 3) ? B[3][c] : B[4][c];
+				B[0][c] = s0;
+				if (jp == 1) B[1][c] = t0;
+				if (jp == 2) B[2][c] = t0;
+				if (jp == 3) B[3][c] = t0;
+				if (jp == 4) B[4][c] = t0;
 			}
+			if (j < n - 1) {
+				const double t0 = bb[0];
+				const double s0 = (jp == 1) ? bb[1] : (jp == 2) ? bb[2] : (jp == 3) ? bb[3] : bb[4];
+				bb[0] = s0;
+				if (jp == 1) bb[1] = t0;
+				if (jp == 2) bb[2] = t0;
+				if (jp == 3) bb[3] = t0;
+				if (jp == 4) bb[4] = t0;
+			}
+		}
+		if (B[0][0] != 0.0) {
 			if (km > 0) {
-				const double r = 1.0 / WINB(kv, j);
-				double mult[TBW_KL + 1];
+				const double rcp = 1.0 / B[0][0];
+				const double bj = bb[0];
 #pragma unroll
-				for (int i = 1; i <= TBW_KL; i++) {
-					if (i <= km) {
-						mult[i] = WINB(kv + i, j) * r;
-					} else {
-						mult[i] = 0.0;
-					}
-				}
-				for (int c = 1; c <= ju - j; c++) {
-					const double y = WINB(kv - c, j + c);
-					if (y != 0.0) {
+				for (int r = 1; r < 5; r++) {
+					if (r <= km) {
+						const double mult = B[r][0] * rcp;
 #pragma unroll
-						for (int i = 1; i <= TBW_KL; i++) {
-							if (i <= km) {
-								WINB(kv + i - c, j + c) -= mult[i] * y;
-							}
+						for (int c = 1; c < 9; c++) {
+							const double y = B[0][c];
+							if (y != 0.0) B[r][c] -= mult * y;
 						}
-					}
-				}
-				if (j < n - 1) {
-					if (piv != j) {
-						const double tmp = FRING(piv);
-						FRING(piv) = FRING(j);
-						FRING(j) = tmp;
-					}
-					const double bj = FRING(j);
-#pragma unroll
-					for (int i = 1; i <= TBW_KL; i++) {
-						if (i <= km) {
-							FRING(j + i) -= mult[i] * bj;
-						}
+						bb[r] -= mult * bj;
 					}
 				}
 			}
+		} else if (info == 0) {
+			info = j + 1;
+		}
+		// row j of U and entry j of the right-hand side are final
+#pragma unroll
+		for (int c = 0; c < 9; c++) {
+			sc[(size_t)(9 * j + c) * S] = B[0][c];
+		}
+		sc[(size_t)(9 * n + j) * S] = bb[0];
+		// shift the block; row j + 5 enters
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+#pragma unroll
+			for (int c = 0; c < 8; c++) B[r][c] = B[r + 1][c + 1];
+			B[r][8] = 0.0;
+			bb[r] = bb[r + 1];
+		}
+		const int inew = j + 5;
+		if (inew < n) {
+			if (inew % 3 == 0) assemble_level(inew / 3);
+			const int rl = inew % 3;
+#pragma unroll
+			for (int c = 0; c < 9; c++) B[4][c] = stg[(rl * 9 + c) * TBW_THREADS];
+			bb[4] = stg[(27 + rl) * TBW_THREADS];
 		} else {
-			if (info == 0) info = j + 1;
-			if (j < n - 1 && piv != j) {
-				const double tmp = FRING(piv);
-				FRING(piv) = FRING(j);
-				FRING(j) = tmp;
-			}
-		}
-		// column j of U and entry j of the right-hand side are final
 #pragma unroll
-		for (int r = 0; r <= TBW_KV; r++) {
-			sc[(size_t)(9 * j + r) * S] = WINB(r, j);
-		}
-		sc[(size_t)(9 * n + j) * S] = FRING(j);
-		// the slot now belongs to column j + TBW_COLS: start it out as zero
-		// (this also is dgbtf2's zeroing of the fill-in rows)
-#pragma unroll
-		for (int r = 0; r < TBW_LDAB; r++) {
-			WINB(r, j) = 0.0;
+			for (int c = 0; c < 9; c++) B[4][c] = 0.0;
+			bb[4] = 0.0;
 		}
 	}
 	if (info != 0) {
@@ -1437,34 +1463,31 @@ k_column_implicit_window(
 	}
 	if (ca.assemble_only) return;
 
-	// ---- dtbsv (upper, non-unit) with x = x0 - delta scattered as it appears ----
+	// ---- back substitution in dtbsv's order; x = x0 - delta is scattered as
+	//      each unknown appears ------------------------------------------------
 	const int * dups = ca.col_dups + (size_t)(ca.col0 + tcol) * 3;
 	const int d0 = dups[0], d1 = dups[1], d2 = dups[2];
-	// right-hand side ring (entries j-9..j live): reuse the now free window
-	double * br = win;   // br[(i % 16) * TBW_THREADS]
-#define BR(i) br[((i) & 15) * TBW_THREADS]
-	for (int i = n - 1; i >= n - 1 - kv && i >= 0; i--) {
-		BR(i) = sc[(size_t)(9 * n + i) * S];
-	}
+	double xr[8];      // x(j+1) .. x(j+8)
+#pragma unroll
+	for (int c = 0; c < 8; c++) xr[c] = 0.0;
 	bool nan_seen = false;
 	for (int j = n - 1; j >= 0; j--) {
-		double xj = BR(j);
-		if (xj != 0.0) {
-			xj = xj / sc[(size_t)(9 * j + kv) * S];
-			const int lo = (j - kv > 0) ? (j - kv) : 0;
-			for (int i = j - 1; i >= lo; i--) {
-				BR(i) -= xj * sc[(size_t)(9 * j + kv - (j - i)) * S];
-			}
+		double acc = sc[(size_t)(9 * n + j) * S];
+#pragma unroll
+		for (int c = 8; c >= 1; c--) {
+			const double xc = xr[c - 1];
+			if (xc != 0.0) acc -= xc * sc[(size_t)(9 * j + c) * S];
 		}
-		if (j - kv - 1 >= 0) {
-			BR(j - kv - 1) = sc[(size_t)(9 * n + (j - kv - 1)) * S];
-		}
+		double xj = acc;
+		if (xj != 0.0) xj = xj / sc[(size_t)(9 * j) * S];
+#pragma unroll
+		for (int c = 7; c >= 1; c--) xr[c] = xr[c - 1];
+		xr[0] = xj;
 		if (j == 0 && !(xj == xj)) nan_seen = true;
-		// delta_j known: write the updated unknown
 		const int k = j / 3;
-		const int c = j - 3 * k;
-		if (c == FW || k < L) {
-			const int rowoff = (c == FP) ? lay.rowoff[PIx] : ((c == FW) ? lay.rowoff[WIx] : lay.rowoff[RIx]);
+		const int c3 = j - 3 * k;
+		if (c3 == FW || k < L) {
+			const int rowoff = (c3 == FP) ? lay.rowoff[PIx] : ((c3 == FW) ? lay.rowoff[WIx] : lay.rowoff[RIx]);
 			const double x0 = in[ebase + (size_t)(rowoff + k) * NN + nd];
 			const double xnew = x0 - xj;
 			out[ebase + (size_t)(rowoff + k) * NN + nd] = xnew;
@@ -1474,9 +1497,7 @@ k_column_implicit_window(
 		}
 	}
 	if (nan_seen) atomicMax(ca.info, ca.col0 + tcol + 1);
-#undef BR
 #undef WIN
-#undef WINB
 #undef FRING
 }
 
