@@ -1,0 +1,435 @@
+///////////////////////////////////////////////////////////////////////////////
+///
+///	\file    TempestB200.cpp
+///
+///	Reference-side binding of libtempest_b200 (see TempestB200.h).
+///
+///////////////////////////////////////////////////////////////////////////////
+
+#include "TempestB200.h"
+
+#include "GridCSGLL.h"
+#include "CubedSphereTrans.h"
+#include "EquationSet.h"
+#include "PhysicalConstants.h"
+#include "Exception.h"
+
+#include <map>
+#include <cmath>
+#include <cstring>
+
+///////////////////////////////////////////////////////////////////////////////
+
+static std::map<Model *, B200Bridge *> g_mapBridges;
+
+B200Bridge & B200Bridge::Get(Model & model) {
+	std::map<Model *, B200Bridge *>::iterator it = g_mapBridges.find(&model);
+	if (it == g_mapBridges.end()) {
+		B200Bridge * p = new B200Bridge(model);
+		g_mapBridges[&model] = p;
+		return *p;
+	}
+	return *(it->second);
+}
+
+B200Bridge::B200Bridge(Model & model) :
+	m_model(model),
+	m_pCtx(NULL),
+	m_fInitialized(false),
+	m_nHypervisOrder(0),
+	m_dNuScalar(0.0),
+	m_dNuDiv(0.0),
+	m_dNuVort(0.0)
+{ }
+
+void B200Bridge::SetHyperviscosity(
+	int nOrder, double dNuScalar, double dNuDiv, double dNuVort
+) {
+	m_nHypervisOrder = nOrder;
+	m_dNuScalar = dNuScalar;
+	m_dNuDiv = dNuDiv;
+	m_dNuVort = dNuVort;
+}
+
+void B200Bridge::Check(int iResult) {
+	if (iResult != 0) {
+		_EXCEPTION1("tempest_b200: %s", tb200_last_error(m_pCtx));
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Global node ids: the integer point of the cube surface a GLL node sits on
+// (panel orientation of CubedSphereTrans::XYZFromXYP, CubedSphereTrans.cpp:25-83).
+
+static void LatticePoint(int p, long s, long t, long n, long & x, long & y, long & z) {
+	switch (p) {
+		case 0: x = n; y = s; z = t; break;
+		case 1: x = -s; y = n; z = t; break;
+		case 2: x = -n; y = -s; z = t; break;
+		case 3: x = s; y = -n; z = t; break;
+		case 4: x = -t; y = s; z = n; break;
+		default: x = t; y = s; z = -n; break;
+	}
+}
+
+static long UniqueIndex(long g, int np) {
+	return (g / np) * (np - 1) + (g % np);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+void B200Bridge::Initialize() {
+	if (m_fInitialized) {
+		return;
+	}
+	GridGLL * pGrid = dynamic_cast<GridGLL *>(m_model.GetGrid());
+	if (pGrid == NULL) {
+		_EXCEPTIONT("tempest_b200 requires a GridGLL");
+	}
+	GridCSGLL * pGridCS = dynamic_cast<GridCSGLL *>(pGrid);
+	if (pGridCS == NULL) {
+		_EXCEPTIONT("tempest_b200: only the cubed-sphere grid is bound so far");
+	}
+	const EquationSet & eqn = m_model.GetEquationSet();
+	const PhysicalConstants & phys = m_model.GetPhysicalConstants();
+
+	tb200_config cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.np = pGrid->GetHorizontalOrder();
+	cfg.nlev = pGrid->GetRElements();
+	cfg.vertical_order = pGrid->GetVerticalOrder();
+	cfg.ncomp = eqn.GetComponents();
+	cfg.ntracers = eqn.GetTracers();
+	cfg.ninstances = m_model.GetComponentDataInstances();
+	cfg.eqn_type =
+		(eqn.GetType() == EquationSet::ShallowWaterEquations)
+			? TB200_EQN_SHALLOW_WATER : TB200_EQN_PRIMITIVE_NONHYDRO;
+	cfg.cartesian_xz = pGrid->GetIsCartesianXZ() ? 1 : 0;
+	for (int c = 0; c < cfg.ncomp; c++) {
+		cfg.comp_on_redge[c] =
+			(pGrid->GetVarLocation(c) == DataLocation_REdge) ? 1 : 0;
+	}
+	cfg.device = -1;
+	cfg.g = phys.GetG();
+	cfg.R = phys.GetR();
+	cfg.cp = phys.GetCp();
+	cfg.cv = phys.GetCv();
+	cfg.p0 = phys.GetP0();
+	cfg.omega = phys.GetOmega();
+	cfg.earth_radius = phys.GetEarthRadius();
+	cfg.ztop = pGrid->GetZtop();
+	cfg.ref_length = pGrid->GetReferenceLength();
+	cfg.hypervis_order = m_nHypervisOrder;
+	cfg.nu_scalar = m_dNuScalar;
+	cfg.nu_div = m_dNuDiv;
+	cfg.nu_vort = m_dNuVort;
+	cfg.fully_explicit = 0;
+	cfg.off_centering = 0.0;
+
+	int iResult = tb200_create(&cfg, &m_pCtx);
+	Check(iResult);
+
+	const int np = cfg.np;
+	const int ne = pGrid->GetABaseResolution();
+	const long nLattice = (long)(np - 1) * ne;
+
+	// Patches (all on this rank: single-rank MPI build)
+	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+		GridPatchGLL * pPatch =
+			dynamic_cast<GridPatchGLL *>(pGrid->GetActivePatch(n));
+		const PatchBox & box = pPatch->GetPatchBox();
+		Check(tb200_add_patch(
+			m_pCtx, pPatch->GetPatchIndex(), box.GetPanel(),
+			pPatch->GetElementCountA(), pPatch->GetElementCountB(),
+			box.GetHaloElements(),
+			pPatch->GetElementDeltaA(), pPatch->GetElementDeltaB(), 0));
+	}
+	Check(tb200_commit_layout(m_pCtx));
+
+	// Tables and vertical column operators, from the host objects
+	Check(tb200_set_tables(
+		m_pCtx,
+		&(pGrid->GetDxBasis1D()[0][0]),
+		&(pGrid->GetStiffness1D()[0][0]),
+		&(pGrid->GetGLLWeights1D()[0])));
+
+	if (cfg.nlev > 1) {
+		const LinearColumnOperator * apOps[TB200_OP_COUNT] = {
+			&(pGrid->GetOpInterpNodeToREdge()),
+			&(pGrid->GetOpInterpREdgeToNode()),
+			&(pGrid->GetOpDiffNodeToNode()),
+			&(pGrid->GetOpDiffNodeToREdge()),
+			&(pGrid->GetOpDiffREdgeToNode()),
+			&(pGrid->GetOpDiffREdgeToREdge()),
+			&(pGrid->GetOpDiffDiffNodeToNode()),
+			&(pGrid->GetOpDiffDiffREdgeToREdge()),
+			&(pGrid->GetOpPenaltyNodeToNode().GetLeftOp()),
+			&(pGrid->GetOpPenaltyNodeToNode().GetRightOp())};
+		for (int o = 0; o < TB200_OP_COUNT; o++) {
+			const DataArray2D<double> & dCoeff = apOps[o]->GetCoeffs();
+			if (dCoeff.GetRows() == 0) {
+				continue;
+			}
+			Check(tb200_set_column_op(
+				m_pCtx, o, dCoeff.GetRows(), dCoeff.GetColumns(),
+				&(dCoeff[0][0]),
+				&(apOps[o]->GetIxBegin()[0]),
+				&(apOps[o]->GetIxEnd()[0])));
+		}
+	}
+
+	// Geometry, node ids, seam transforms per patch
+	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+		GridPatchGLL * pPatch =
+			dynamic_cast<GridPatchGLL *>(pGrid->GetActivePatch(n));
+		const PatchBox & box = pPatch->GetPatchBox();
+		const int ixPatch = pPatch->GetPatchIndex();
+		const int nPanel = box.GetPanel();
+		const int nHalo = box.GetHaloElements();
+
+		tb200_geometry geo;
+		memset(&geo, 0, sizeof(geo));
+		geo.jacobian2d = &(pPatch->GetJacobian2D()[0][0]);
+		geo.contrametric2da = &(pPatch->GetContraMetric2DA()[0][0][0]);
+		geo.contrametric2db = &(pPatch->GetContraMetric2DB()[0][0][0]);
+		geo.coriolis = &(pPatch->GetCoriolisF()[0][0]);
+		geo.topography = &(pPatch->GetTopography()[0][0]);
+		geo.jacobian = &(pPatch->GetJacobian()[0][0][0]);
+		geo.jacobian_redge = &(pPatch->GetJacobianREdge()[0][0][0]);
+		if (cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
+			geo.contrametrica = &(pPatch->GetContraMetricA()[0][0][0][0]);
+			geo.contrametricb = &(pPatch->GetContraMetricB()[0][0][0][0]);
+			geo.contrametricxi = &(pPatch->GetContraMetricXi()[0][0][0][0]);
+			geo.contrametrica_redge = &(pPatch->GetContraMetricAREdge()[0][0][0][0]);
+			geo.contrametricb_redge = &(pPatch->GetContraMetricBREdge()[0][0][0][0]);
+			geo.contrametricxi_redge = &(pPatch->GetContraMetricXiREdge()[0][0][0][0]);
+			geo.derivr_node = &(pPatch->GetDerivRNode()[0][0][0][0]);
+			geo.derivr_redge = &(pPatch->GetDerivRREdge()[0][0][0][0]);
+		}
+		Check(tb200_upload_geometry(m_pCtx, ixPatch, &geo));
+
+		const int nWA = box.GetAInteriorWidth();
+		const int nWB = box.GetBInteriorWidth();
+		const long gA0 = box.GetAGlobalInteriorBegin();
+		const long gB0 = box.GetBGlobalInteriorBegin();
+
+		std::vector<int64_t> vecIds((size_t)nWA * nWB);
+		std::vector<int> vecIa, vecIb, vecSrc;
+		std::vector<double> vecM;
+		const long m = 2 * nLattice + 1;
+		for (int i = 0; i < nWA; i++) {
+		for (int j = 0; j < nWB; j++) {
+			const long s = 2 * UniqueIndex(gA0 + i, np) - nLattice;
+			const long t = 2 * UniqueIndex(gB0 + j, np) - nLattice;
+			long x, y, z;
+			LatticePoint(nPanel, s, t, nLattice, x, y, z);
+			vecIds[(size_t)i * nWB + j] =
+				((x + nLattice) * m + (y + nLattice)) * m + (z + nLattice);
+
+			// Nodes on a panel edge: covector re-basing from every other
+			// panel containing the point, with the reference's own formulas
+			// (CubedSphereTrans::CoVecPanelTrans, CubedSphereTrans.h:1751)
+			if ((labs(s) != nLattice) && (labs(t) != nLattice)) {
+				continue;
+			}
+			const bool fOn[6] = {
+				x == nLattice, y == nLattice, x == -nLattice,
+				y == -nLattice, z == nLattice, z == -nLattice};
+			const double dX = tan(pPatch->GetANode(i + nHalo));
+			const double dY = tan(pPatch->GetBNode(j + nHalo));
+			for (int q = 0; q < 6; q++) {
+				if ((!fOn[q]) || (q == nPanel)) {
+					continue;
+				}
+				double dM[4];
+				for (int u = 0; u < 2; u++) {
+					double dA = (u == 0) ? 1.0 : 0.0;
+					double dB = (u == 0) ? 0.0 : 1.0;
+					CubedSphereTrans::CoVecPanelTrans(q, nPanel, dA, dB, dX, dY);
+					dM[0 + u] = dA;
+					dM[2 + u] = dB;
+				}
+				vecIa.push_back(i);
+				vecIb.push_back(j);
+				vecSrc.push_back(q);
+				for (int u = 0; u < 4; u++) {
+					vecM.push_back(dM[u]);
+				}
+			}
+		}
+		}
+		Check(tb200_set_node_ids(m_pCtx, ixPatch, &(vecIds[0])));
+		Check(tb200_set_seam_transforms(
+			m_pCtx, ixPatch, (int)vecIa.size(),
+			vecIa.empty() ? NULL : &(vecIa[0]),
+			vecIb.empty() ? NULL : &(vecIb[0]),
+			vecSrc.empty() ? NULL : &(vecSrc[0]),
+			vecM.empty() ? NULL : &(vecM[0])));
+	}
+	Check(tb200_build_connectivity(m_pCtx));
+	m_fInitialized = true;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+void B200Bridge::Upload(int iInstance) {
+	Grid * pGrid = m_model.GetGrid();
+	const bool fTracers = (m_model.GetEquationSet().GetTracers() != 0);
+	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+		GridPatch * pPatch = pGrid->GetActivePatch(n);
+		Check(tb200_upload_state(
+			m_pCtx, pPatch->GetPatchIndex(), iInstance,
+			&(pPatch->GetDataState(iInstance, DataLocation_Node)[0][0][0][0]),
+			&(pPatch->GetDataState(iInstance, DataLocation_REdge)[0][0][0][0]),
+			fTracers ? &(pPatch->GetDataTracers(iInstance)[0][0][0][0]) : NULL));
+	}
+}
+
+void B200Bridge::Download(int iInstance) {
+	Grid * pGrid = m_model.GetGrid();
+	const bool fTracers = (m_model.GetEquationSet().GetTracers() != 0);
+	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+		GridPatch * pPatch = pGrid->GetActivePatch(n);
+		Check(tb200_download_state(
+			m_pCtx, pPatch->GetPatchIndex(), iInstance,
+			&(pPatch->GetDataState(iInstance, DataLocation_Node)[0][0][0][0]),
+			&(pPatch->GetDataState(iInstance, DataLocation_REdge)[0][0][0][0]),
+			fTracers ? &(pPatch->GetDataTracers(iInstance)[0][0][0][0]) : NULL,
+			1));
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// HorizontalDynamicsB200
+
+HorizontalDynamicsB200::HorizontalDynamicsB200(
+	Model & model,
+	int nHorizontalOrder,
+	int nHyperviscosityOrder,
+	double dNuScalar,
+	double dNuDiv,
+	double dNuVort,
+	double dInstepNuDiv
+) :
+	HorizontalDynamics(model)
+{
+	B200Bridge::Get(model).SetHyperviscosity(
+		nHyperviscosityOrder, dNuScalar, dNuDiv, dNuVort);
+}
+
+void HorizontalDynamicsB200::Initialize() {
+	B200Bridge::Get(m_model).Initialize();
+}
+
+void HorizontalDynamicsB200::StepExplicit(
+	int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT
+) {
+	// Used under one of the reference's own TimestepSchemes the state lives
+	// on the host between plugin calls: move both instances across.
+	B200Bridge & b = B200Bridge::Get(m_model);
+	b.Upload(iDataInitial);
+	b.Upload(iDataUpdate);
+	b.Check(tb200_h_step_explicit(b.Ctx(), iDataInitial, iDataUpdate, dDeltaT));
+	// the reference leaves W on levels and U,V on interfaces in the input
+	// instance (HorizontalDynamicsFEM.cpp:817-831); download refreshes them
+	b.Download(iDataInitial);
+	b.Download(iDataUpdate);
+}
+
+void HorizontalDynamicsB200::StepAfterSubCycle(
+	int iDataInitial, int iDataUpdate, int iDataWorking,
+	const Time & time, double dDeltaT
+) {
+	B200Bridge & b = B200Bridge::Get(m_model);
+	b.Upload(iDataInitial);
+	b.Check(tb200_h_step_after_subcycle(
+		b.Ctx(), iDataInitial, iDataUpdate, iDataWorking, dDeltaT));
+	b.Download(iDataUpdate);
+	b.Download(iDataWorking);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// VerticalDynamicsB200
+
+VerticalDynamicsB200::VerticalDynamicsB200(
+	Model & model,
+	int nHorizontalOrder,
+	int nVerticalOrder,
+	int nHypervisOrder,
+	bool fFullyExplicit,
+	bool fUseReferenceState,
+	bool fForceMassFluxOnLevels
+) :
+	VerticalDynamics(model)
+{
+	if (fFullyExplicit) {
+		_EXCEPTIONT("tempest_b200: --explicitvertical is not supported");
+	}
+}
+
+void VerticalDynamicsB200::Initialize() {
+	B200Bridge::Get(m_model).Initialize();
+}
+
+void VerticalDynamicsB200::StepExplicit(
+	int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT
+) {
+	B200Bridge & b = B200Bridge::Get(m_model);
+	b.Upload(iDataInitial);
+	b.Upload(iDataUpdate);
+	b.Check(tb200_v_step_explicit(b.Ctx(), iDataInitial, iDataUpdate, dDeltaT));
+	b.Download(iDataUpdate);
+}
+
+void VerticalDynamicsB200::StepImplicit(
+	int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT
+) {
+	B200Bridge & b = B200Bridge::Get(m_model);
+	b.Upload(iDataInitial);
+	if (iDataUpdate != iDataInitial) {
+		b.Upload(iDataUpdate);
+	}
+	b.Check(tb200_v_step_implicit(b.Ctx(), iDataInitial, iDataUpdate, dDeltaT));
+	b.Check(tb200_check_errors(b.Ctx()));
+	b.Download(iDataUpdate);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// TimestepSchemeB200
+
+TimestepSchemeB200::TimestepSchemeB200(Model & model, int iScheme) :
+	TimestepScheme(model),
+	m_iScheme(iScheme)
+{
+	if (tb200_scheme_instances(iScheme) < 0) {
+		_EXCEPTIONT("tempest_b200: time scheme not implemented");
+	}
+}
+
+int TimestepSchemeB200::GetComponentDataInstances() const {
+	return tb200_scheme_instances(m_iScheme);
+}
+
+int TimestepSchemeB200::GetTracerDataInstances() const {
+	return tb200_scheme_instances(m_iScheme);
+}
+
+void TimestepSchemeB200::Initialize() {
+}
+
+void TimestepSchemeB200::Step(
+	bool fFirstStep, bool fLastStep, const Time & time, double dDeltaT
+) {
+	B200Bridge & b = B200Bridge::Get(m_model);
+	b.Initialize();
+	// Between steps the host may read and change instance 0 (workflow
+	// processes, Model.cpp:477-481; outputs, :484-509): it is the only
+	// instance that crosses the bus.  The carry-over instance of the Strang
+	// scheme stays on the device.
+	b.Upload(0);
+	b.Check(tb200_step(b.Ctx(), m_iScheme, fFirstStep ? 1 : 0, fLastStep ? 1 : 0, dDeltaT));
+	b.Check(tb200_check_errors(b.Ctx()));
+	b.Download(0);
+}
+
+///////////////////////////////////////////////////////////////////////////////

@@ -1,0 +1,144 @@
+///////////////////////////////////////////////////////////////////////////////
+///
+///	\file    TempestB200.h
+///
+///	Reference-side binding of libtempest_b200: plugin classes a maintainer
+///	adds to the reference tree.  They derive from the reference's own plugin
+///	interfaces (HorizontalDynamics.h:34-174, VerticalDynamics.h:30-134,
+///	TimestepScheme.h:32-124) and are the only translation unit that sees both
+///	the reference headers and the C ABI (include/tempest_b200.h).
+///
+///	  HorizontalDynamicsB200  replaces HorizontalDynamicsFEM   (--hmethod B200)
+///	  VerticalDynamicsB200    replaces VerticalDynamicsFEM     (--vmethod B200)
+///	  TimestepSchemeB200      replaces TimestepSchemeStrang / ARS343 and keeps
+///	                          every state instance on the device for the whole
+///	                          step (--timescheme b200/strang, b200/ars343)
+///
+///	Errors of the library surface as the reference's Exception
+///	(src/base/Exception.h:25-49) carrying tb200_last_error().
+///
+///////////////////////////////////////////////////////////////////////////////
+
+#ifndef _TEMPESTB200_H_
+#define _TEMPESTB200_H_
+
+#include "Model.h"
+#include "GridGLL.h"
+#include "GridPatchGLL.h"
+#include "HorizontalDynamics.h"
+#include "VerticalDynamics.h"
+#include "TimestepScheme.h"
+
+#include "tempest_b200.h"
+
+#include <vector>
+
+///////////////////////////////////////////////////////////////////////////////
+
+///	<summary>
+///		The device context shared by the three plugins of one Model.
+///	</summary>
+class B200Bridge {
+
+public:
+	///	<summary>
+	///		Bridge of a model (created on first use).
+	///	</summary>
+	static B200Bridge & Get(Model & model);
+
+	///	<summary>
+	///		Set the parameters the HorizontalDynamicsFEM constructor takes.
+	///	</summary>
+	void SetHyperviscosity(int nOrder, double dNuScalar, double dNuDiv, double dNuVort);
+
+	///	<summary>
+	///		Create the context, describe the grid, upload geometry and tables.
+	///		Called from the plugins' Initialize(), i.e. after
+	///		Grid::EvaluateGeometricTerms (Model.cpp:347-355).
+	///	</summary>
+	void Initialize();
+
+	///	<summary>
+	///		Host instance -> device, device -> host.
+	///	</summary>
+	void Upload(int iInstance);
+	void Download(int iInstance);
+
+	///	<summary>
+	///		Throw the reference's Exception if a C-ABI call failed.
+	///	</summary>
+	void Check(int iResult);
+
+	tb200_ctx * Ctx() { return m_pCtx; }
+
+private:
+	B200Bridge(Model & model);
+
+	Model & m_model;
+	tb200_ctx * m_pCtx;
+	bool m_fInitialized;
+	int m_nHypervisOrder;
+	double m_dNuScalar, m_dNuDiv, m_dNuVort;
+};
+
+///////////////////////////////////////////////////////////////////////////////
+
+class HorizontalDynamicsB200 : public HorizontalDynamics {
+public:
+	///	<summary>
+	///		Same arguments as HorizontalDynamicsFEM (HorizontalDynamicsFEM.h).
+	///	</summary>
+	HorizontalDynamicsB200(
+		Model & model,
+		int nHorizontalOrder,
+		int nHyperviscosityOrder,
+		double dNuScalar,
+		double dNuDiv,
+		double dNuVort,
+		double dInstepNuDiv = 0.0);
+
+	virtual void Initialize();
+	virtual void StepExplicit(int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT);
+	virtual void StepAfterSubCycle(int iDataInitial, int iDataUpdate, int iDataWorking, const Time & time, double dDeltaT);
+};
+
+class VerticalDynamicsB200 : public VerticalDynamics {
+public:
+	///	<summary>
+	///		Same arguments as VerticalDynamicsFEM (VerticalDynamicsFEM.h).
+	///	</summary>
+	VerticalDynamicsB200(
+		Model & model,
+		int nHorizontalOrder,
+		int nVerticalOrder,
+		int nHypervisOrder = 0,
+		bool fFullyExplicit = false,
+		bool fUseReferenceState = true,
+		bool fForceMassFluxOnLevels = false);
+
+	virtual void Initialize();
+	virtual void StepExplicit(int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT);
+	virtual void StepImplicit(int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT);
+};
+
+class TimestepSchemeB200 : public TimestepScheme {
+public:
+	TimestepSchemeB200(Model & model, int iScheme);
+
+	virtual int GetComponentDataInstances() const;
+	virtual int GetTracerDataInstances() const;
+	virtual void Initialize();
+	///	<summary>
+	///		Instance 0 is uploaded when the host may have changed it (first
+	///		step, or after a workflow / output), the whole step runs on the
+	///		device, instance 0 comes back for Model::Go's outputs.
+	///	</summary>
+	virtual void Step(bool fFirstStep, bool fLastStep, const Time & time, double dDeltaT);
+
+private:
+	int m_iScheme;
+};
+
+///////////////////////////////////////////////////////////////////////////////
+
+#endif

@@ -1,0 +1,152 @@
+///////////////////////////////////////////////////////////////////////////////
+///
+///	\file    b200_driver.cpp
+///
+///	The reference's own driver flow (TempestInitialize.h setup macros, Model::Go,
+///	checksum output manager, error norms) with the B200 plugins selected by
+///	--b200 (none | plugins | scheme):
+///	  none     every plugin is the reference's (CPU)
+///	  plugins  HorizontalDynamicsB200 + VerticalDynamicsB200 under the
+///	           reference's TimestepScheme and host DSS
+///	  scheme   TimestepSchemeB200: the whole step on the device
+///	The test-case classes are the reference's (included, main renamed).
+///
+///////////////////////////////////////////////////////////////////////////////
+
+#define main SWTest2_reference_main
+#include "shallowwater_sphere/SWTest2.cpp"
+#undef main
+#define main BaroclinicWaveJW_reference_main
+#include "nonhydro_sphere/BaroclinicWaveJWTest.cpp"
+#undef main
+
+#include "TempestB200.h"
+#include "GridCSGLL.h"
+#include "VerticalDynamicsStub.h"
+
+int main(int argc, char ** argv) {
+
+	TempestInitialize(&argc, &argv);
+
+try {
+	std::string strCase;
+	std::string strMode;
+	int nPatch;
+	double dZtop;
+	std::string strPert;
+
+	BeginTempestCommandLine("B200Driver");
+		SetDefaultResolution(8);
+		SetDefaultLevels(10);
+		SetDefaultOutputDeltaT("200s");
+		SetDefaultDeltaT("200s");
+		SetDefaultEndTime("600s");
+		SetDefaultHorizontalOrder(4);
+		SetDefaultVerticalOrder(1);
+
+		CommandLineString(strCase, "case", "jw");
+		CommandLineString(strMode, "b200", "scheme");
+		CommandLineInt(nPatch, "npatch", 6);
+		CommandLineDouble(dZtop, "ztop", 10000.0);
+		CommandLineString(strPert, "pert", "Exp");
+
+		ParseCommandLine(argc, argv);
+	EndTempestCommandLine(argv)
+
+	const bool fSW = (strCase == "sw2");
+	Model model(fSW ? EquationSet::ShallowWaterEquations
+	                : EquationSet::PrimitiveNonhydrostaticEquations);
+
+	model.SetDeltaT(_tempestvars.timeDeltaT);
+	model.SetEndTime(_tempestvars.timeEndTime);
+
+	STLStringHelper::ToLower(_tempestvars.strTimestepScheme);
+	const int iScheme =
+		(_tempestvars.strTimestepScheme == "ars343")
+			? TB200_SCHEME_ARS343 : TB200_SCHEME_STRANG_KGU35;
+
+	if (strMode == "none") {
+		_TempestSetupMethodOfLines(model, _tempestvars);
+
+	} else {
+		if (strMode == "scheme") {
+			model.SetTimestepScheme(new TimestepSchemeB200(model, iScheme));
+		} else if (iScheme == TB200_SCHEME_ARS343) {
+			model.SetTimestepScheme(new TimestepSchemeARS343(model));
+		} else {
+			model.SetTimestepScheme(new TimestepSchemeStrang(model));
+		}
+		// same arguments as the "v1" branches of _TempestSetupMethodOfLines
+		// (TempestInitialize.h:296-366)
+		if (_tempestvars.fNoHyperviscosity) {
+			_tempestvars.nHyperviscosityOrder = 0;
+			_tempestvars.dNuScalar = 0.0;
+			_tempestvars.dNuDiv = 0.0;
+			_tempestvars.dNuVort = 0.0;
+		}
+		model.SetHorizontalDynamics(
+			new HorizontalDynamicsB200(
+				model,
+				_tempestvars.nHorizontalOrder,
+				_tempestvars.nHyperviscosityOrder,
+				_tempestvars.dNuScalar,
+				_tempestvars.dNuDiv,
+				_tempestvars.dNuVort,
+				_tempestvars.dInstepNuDiv));
+		if (_tempestvars.nLevels == 1) {
+			model.SetVerticalDynamics(new VerticalDynamicsStub(model));
+		} else {
+			model.SetVerticalDynamics(
+				new VerticalDynamicsB200(
+					model,
+					_tempestvars.nHorizontalOrder,
+					_tempestvars.nVerticalOrder,
+					_tempestvars.nVerticalHyperdiffOrder,
+					_tempestvars.fExplicitVertical,
+					!_tempestvars.fNoReferenceState,
+					_tempestvars.fForceMassFluxOnLevels));
+		}
+	}
+
+	// _TempestSetupCubedSphereModel (TempestInitialize.h:476-586)
+	GridCSGLL * pGrid = new GridCSGLL(model);
+	pGrid->DefineParameters();
+	pGrid->SetParameters(
+		_tempestvars.nLevels,
+		nPatch,
+		_tempestvars.nResolutionX,
+		4,
+		_tempestvars.nHorizontalOrder,
+		_tempestvars.nVerticalOrder,
+		Grid::VerticalDiscretization_FiniteElement,
+		Grid::VerticalStaggering_Lorenz);
+	pGrid->InitializeDataLocal();
+	model.SetGrid(pGrid, nPatch);
+	_TempestSetupOutputManagers(model, _tempestvars);
+
+	if (fSW) {
+		model.SetTestCase(new ShallowWaterTestCase2(2998.104995, 38.61068277, 0.0));
+	} else {
+		STLStringHelper::ToLower(strPert);
+		model.SetTestCase(
+			new BaroclinicWaveJWTest(
+				0.0, dZtop,
+				(strPert == "exp") ?
+					BaroclinicWaveJWTest::PerturbationType_Exp :
+					BaroclinicWaveJWTest::PerturbationType_None));
+	}
+
+	AnnounceBanner("SIMULATION");
+	model.Go();
+
+	AnnounceBanner("RESULTS");
+	model.ComputeErrorNorms();
+	AnnounceBanner();
+
+} catch(Exception & e) {
+	std::cout << e.ToString() << std::endl;
+	return 1;
+}
+	TempestDeinitialize();
+	return 0;
+}

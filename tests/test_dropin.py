@@ -1,0 +1,70 @@
+"""Drop-in boundary: the reference's own driver flow (Model::Go, checksum
+output manager, error norms) run with the B200 plugins of integration/
+(C++ shells deriving from the reference's HorizontalDynamics /
+VerticalDynamics / TimestepScheme) must print the reference's checksums.
+
+oracle/_ref/b200_driver is built in the container that has /root/reference
+(`make -C oracle`); the GPU box runs the prebuilt binary."""
+import os
+import re
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DRIVER = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "b200_driver")
+
+
+def run(mode, *flags):
+    res = subprocess.run([DRIVER, "--b200", mode, "--output_none"] + list(flags),
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:]
+    sums = {}
+    final = res.stdout[res.stdout.rindex("(Final)"):]
+    for m in re.finditer(r"Checksum \((\w+)\): ([-+0-9.eE]+)", final):
+        sums[m.group(1)] = float(m.group(2))
+    norms = re.findall(r"^\s+(\w+)\s+([0-9.e+-]+)\s+([0-9.e+-]+)\s+([0-9.e+-]+)\s*$",
+                       res.stdout, flags=re.M)
+    return sums, norms
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/b200_driver not built")
+def test_driver_reference_mode_runs():
+    sums, norms = run("none", "--case", "sw2", "--resolution", "4", "--levels", "1")
+    assert set(sums) == {"U", "V", "H"} and len(norms) == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["plugins", "scheme"])
+def test_shallow_water_dropin(cuda_library, mode):
+    """Williamson 2, ne=8, 3 steps: checksums and error norms of the reference."""
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "sw2", "--resolution", "8", "--levels", "1", "--endtime", "600s"]
+    ref, rn = run("none", *flags)
+    got, gn = run(mode, *flags)
+    scale = max(abs(v) for v in ref.values())
+    for k in ref:
+        # V sums to rounding noise of U-sized terms: tolerance relative to the largest sum
+        assert abs(got[k] - ref[k]) <= 1e-12 * scale, (k, got, ref)
+    assert [r[0] for r in rn] == [g[0] for g in gn]
+    for r, g in zip(rn, gn):
+        for a, b in zip(r[1:], g[1:]):
+            assert abs(float(a) - float(b)) <= 1e-4 * float(a) + 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,scheme", [("plugins", "strang"), ("scheme", "strang"),
+                                         ("scheme", "ars343")])
+def test_nonhydro_dropin(cuda_library, mode, scheme):
+    """JW baroclinic wave ne=8 L10, 3 steps.  rho and rho-theta (conserved)
+    must match the reference to rounding; U, V, W only to the reference's own
+    last-bit sensitivity on this case."""
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "jw", "--resolution", "8", "--levels", "10", "--dt", "200s",
+             "--endtime", "600s", "--timescheme", scheme]
+    ref, _ = run("none", *flags)
+    got, _ = run(mode, *flags)
+    for k in ("Rho", "RhoTheta"):
+        assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k]), (k, got, ref)
+    assert abs(got["U"] - ref["U"]) <= 1e-5 * abs(ref["U"]), (got, ref)
