@@ -243,11 +243,11 @@ def main():
     nk = 10
     k0 = torch.cuda.Event(enable_timing=True)
     k1 = torch.cuda.Event(enable_timing=True)
-    ctx.hv_step_explicit(2, 3, 1e-9)
+    ctx.hv_step_explicit_combine([0.0, 0.0, 1.0, 0.0], 2, 3, 1e-9)
     torch.cuda.synchronize()
     k0.record()
     for _ in range(nk):
-        ctx.hv_step_explicit(2, 3, 1e-9)
+        ctx.hv_step_explicit_combine([0.0, 0.0, 1.0, 0.0], 2, 3, 1e-9)
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / nk

@@ -160,6 +160,17 @@ int tb200_set_column_op(tb200_ctx * ctx, int op, int nout, int nin,
  * GridPatchCSGLL.cpp:295-574 / GridPatchCartesianGLL.cpp:197-460 outputs). */
 int tb200_upload_geometry(tb200_ctx * ctx, int patch_index, const tb200_geometry * g);
 
+/* Optional: let the kernels evaluate the terrain-following cubed-sphere metric
+ * on the fly instead of reading the stored 3-D arrays
+ * (GridPatchCSGLL::EvaluateGeometricTerms, GridPatchCSGLL.cpp:344-553; same
+ * expressions, same bits).  xnode[W_A], ynode[W_B] = tan of GetANode/GetBNode
+ * (GridPatchCSGLL.cpp:205-213), topography_deriv = GetTopographyDeriv()
+ * [W_A][W_B][2]; reta_* = Grid::GetREtaLevels / GetREtaInterfaces. */
+int tb200_set_terrain_metric(tb200_ctx * ctx, int patch_index, const double * xnode,
+                             const double * ynode, const double * topography_deriv);
+int tb200_set_vertical_coordinate(tb200_ctx * ctx, const double * reta_levels,
+                                  const double * reta_interfaces);
+
 /*
  * Connectivity.  The reference finds coincident nodes through its exchange
  * buffer topology (Grid.cpp:1066-1573, Connectivity.cpp:47-744); here the host
@@ -215,6 +226,11 @@ int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt);
 int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt);
 /* Both of the above in one pass over the state (same results). */
 int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double dt);
+/* Grid::LinearCombineData(coeff, out) (GridPatch.cpp:1433-1520) followed by
+ * both explicit plugins, the combination formed inside the stage kernel:
+ * HorizontalDynamics::StepExplicitCombine (HorizontalDynamics.h:97-106). */
+int tb200_hv_step_explicit_combine(tb200_ctx * ctx, const double * coeff, int ncoeff,
+                                   int in, int out, double dt);
 /* VerticalDynamicsFEM::StepImplicit (VerticalDynamicsFEM.cpp:1230-1638). */
 int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt);
 /* GridGLL::PostProcessSubstage -> ApplyDSS (GridGLL.cpp:571-583,

@@ -208,6 +208,21 @@ void B200Bridge::Initialize() {
 		}
 		Check(tb200_upload_geometry(m_pCtx, ixPatch, &geo));
 
+		// On-the-fly terrain-following metric: m_dXNode / m_dYNode
+		// (GridPatchCSGLL.cpp:205-213) and the topography derivatives
+		if (cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
+			std::vector<double> vecX(box.GetATotalWidth()), vecY(box.GetBTotalWidth());
+			for (int i = 0; i < box.GetATotalWidth(); i++) {
+				vecX[i] = tan(pPatch->GetANode(i));
+			}
+			for (int j = 0; j < box.GetBTotalWidth(); j++) {
+				vecY[j] = tan(pPatch->GetBNode(j));
+			}
+			Check(tb200_set_terrain_metric(
+				m_pCtx, ixPatch, &(vecX[0]), &(vecY[0]),
+				&(pPatch->GetTopographyDeriv()[0][0][0])));
+		}
+
 		const int nWA = box.GetAInteriorWidth();
 		const int nWB = box.GetBInteriorWidth();
 		const long gA0 = box.GetAGlobalInteriorBegin();
@@ -265,6 +280,10 @@ void B200Bridge::Initialize() {
 			vecIb.empty() ? NULL : &(vecIb[0]),
 			vecSrc.empty() ? NULL : &(vecSrc[0]),
 			vecM.empty() ? NULL : &(vecM[0])));
+	}
+	if (cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
+		Check(tb200_set_vertical_coordinate(
+			m_pCtx, &(pGrid->GetREtaLevels()[0]), &(pGrid->GetREtaInterfaces()[0])));
 	}
 	Check(tb200_build_connectivity(m_pCtx));
 	m_fInitialized = true;

@@ -211,6 +211,17 @@ static void DumpGeometry(Model & model) {
 		}
 		Write1D(P(n, "anode"), pPatch->GetANodes());
 		Write1D(P(n, "bnode"), pPatch->GetBNodes());
+		{
+			// m_dXNode / m_dYNode (GridPatchCSGLL.cpp:205-213) are protected:
+			// same expression, same libm
+			DataArray1D<double> dX(pPatch->GetANodes().GetRows());
+			DataArray1D<double> dY(pPatch->GetBNodes().GetRows());
+			for (int i = 0; i < dX.GetRows(); i++) dX[i] = tan(pPatch->GetANode(i));
+			for (int j = 0; j < dY.GetRows(); j++) dY[j] = tan(pPatch->GetBNode(j));
+			Write1D(P(n, "xnode"), dX);
+			Write1D(P(n, "ynode"), dY);
+		}
+		Write3D(P(n, "topographyderiv"), pPatch->GetTopographyDeriv());
 		Write2D(P(n, "lon"), pPatch->GetLongitude());
 		Write2D(P(n, "lat"), pPatch->GetLatitude());
 		Write2D(P(n, "jacobian2d"), pPatch->GetJacobian2D());

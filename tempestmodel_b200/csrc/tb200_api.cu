@@ -455,6 +455,66 @@ extern "C" int tb200_upload_geometry(
 	return 0;
 }
 
+// Terrain-following cubed-sphere metric evaluated on the fly
+// (GridPatchCSGLL::EvaluateGeometricTerms, GridPatchCSGLL.cpp:344-553): the
+// gnomonic node coordinates m_dXNode / m_dYNode (= tan of GetANode / GetBNode,
+// GridPatchCSGLL.cpp:205-213) and GridPatch::GetTopographyDeriv().
+extern "C" int tb200_set_terrain_metric(
+	tb200_ctx * ctx, int patch_index, const double * xnode, const double * ynode,
+	const double * topography_deriv
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	const int np = ctx->lay.np;
+	const size_t nn = ctx->lay.nn;
+	const size_t wa = pi->nea * np + 2 * pi->halo;
+	const size_t wb = pi->neb * np + 2 * pi->halo;
+	if (ctx->d_tx == 0) {
+		if (dalloc(ctx, &ctx->d_tx, (size_t)ctx->lay.nelem * nn)) return 1;
+		if (dalloc(ctx, &ctx->d_ty, (size_t)ctx->lay.nelem * nn)) return 1;
+		if (dalloc(ctx, &ctx->d_tda, (size_t)ctx->lay.nelem * nn)) return 1;
+		if (dalloc(ctx, &ctx->d_tdb, (size_t)ctx->lay.nelem * nn)) return 1;
+	}
+	std::vector<double> hx(wa * wb), hy(wa * wb);
+	for (size_t i = 0; i < wa; i++) {
+		for (size_t j = 0; j < wb; j++) {
+			hx[i * wb + j] = xnode[i];
+			hy[i * wb + j] = ynode[j];
+		}
+	}
+	if (upload_geom_array(ctx, *pi, hx.data(), 1, 1, ctx->d_tx, 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, hy.data(), 1, 1, ctx->d_ty, 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, topography_deriv, 1, 2, ctx->d_tda, ctx->d_tdb, 0)) return 1;
+	pi->has_terrain = true;
+	return 0;
+}
+
+// Grid::GetREtaLevels / GetREtaInterfaces; enables the on-the-fly metric once
+// every local patch has its terrain arrays (TB200_METRIC=stored disables it).
+extern "C" int tb200_set_vertical_coordinate(
+	tb200_ctx * ctx, const double * reta_levels, const double * reta_interfaces
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	const int L = ctx->lay.nlev;
+	std::vector<double> a(reta_levels, reta_levels + L), b(reta_interfaces, reta_interfaces + L + 1);
+	if (dupload(ctx, &ctx->d_reta_n, a)) return 1;
+	if (dupload(ctx, &ctx->d_reta_e, b)) return 1;
+	bool all = true;
+	for (size_t p = 0; p < ctx->patches.size(); p++) {
+		if (ctx->patches[p].elem0 >= 0 && !ctx->patches[p].has_terrain) all = false;
+	}
+	const char * force = getenv("TB200_METRIC");
+	if (force != 0 && strcmp(force, "stored") == 0) all = false;
+	DevGeom & g = ctx->geom;
+	g.analytic = all ? 1 : 0;
+	g.tx = ctx->d_tx; g.ty = ctx->d_ty; g.tda = ctx->d_tda; g.tdb = ctx->d_tdb;
+	g.reta_n = ctx->d_reta_n; g.reta_e = ctx->d_reta_e;
+	g.ztop = ctx->cfg.ztop;
+	g.radius = ctx->cfg.earth_radius;
+	return 0;
+}
+
 extern "C" int tb200_upload_element_area(
 	tb200_ctx * ctx, int patch_index, const double * area_node, const double * area_redge
 ) {
@@ -725,15 +785,27 @@ static int check_ops(tb200_ctx * ctx) {
 	return 0;
 }
 
-static int nh_launch(tb200_ctx * ctx, int in, int out, double dt, bool do_h, bool do_v) {
+static StageBase stage_base_out() {
+	StageBase sb;
+	memset(&sb, 0, sizeof(sb));
+	sb.use_out = 1;
+	return sb;
+}
+
+static int nh_launch(
+	tb200_ctx * ctx, int in, int out, double dt, bool do_h, bool do_v,
+	const StageBase & sb
+) {
 	const DevLayout & lay = ctx->lay;
 	if (check_ops(ctx)) return 1;
 	NHArgs a;
 	a.dt = dt;
 	a.xz = ctx->cfg.cartesian_xz;
 	a.fe_nodes = ctx->cfg.vertical_order;
-	int KB = 256 / lay.nn;
-	if (KB > lay.nlev) KB = lay.nlev;
+	// levels per pass: at most 16 (256 threads), chunks of equal size
+	const int maxkb = std::max(1, 256 / lay.nn);
+	const int nchunk = (lay.nlev + maxkb - 1) / maxkb;
+	const int KB = (lay.nlev + nchunk - 1) / nchunk;
 	const size_t smem = tb_nh_smem_doubles(lay.nlev, lay.nn, KB) * sizeof(double);
 	const dim3 grid((unsigned)lay.nelem), block(KB * lay.nn);
 	if (do_h && do_v) {
@@ -742,21 +814,21 @@ static int nh_launch(tb200_ctx * ctx, int in, int out, double dt, bool do_h, boo
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
 		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
-			ctx->ops, ctx->phys, a, (const double *)ctx->inst[in], ctx->inst[out], KB);
+			ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);
 	} else if (do_h) {
 		auto kfn = k_nh_explicit<4, true, false>;
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
 		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
-			ctx->ops, ctx->phys, a, (const double *)ctx->inst[in], ctx->inst[out], KB);
+			ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);
 	} else {
 		auto kfn = k_nh_explicit<4, false, true>;
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
 		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
-			ctx->ops, ctx->phys, a, (const double *)ctx->inst[in], ctx->inst[out], KB);
+			ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);
 	}
 	TB_KERNEL_CHECK(ctx);
 	return 0;
@@ -781,7 +853,7 @@ extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 			(const double *)ctx->inst[in], ctx->inst[out], dt, ctx->cfg.g);
 		TB_KERNEL_CHECK(ctx);
 	} else {
-		if (nh_launch(ctx, in, out, dt, true, false)) return 1;
+		if (nh_launch(ctx, in, out, dt, true, false, stage_base_out())) return 1;
 	}
 	return tb200_filter_negative_tracers(ctx, out);
 }
@@ -793,7 +865,7 @@ extern "C" int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 	}
 	if (ctx->cfg.fully_explicit) TB_FAIL(ctx, "--explicitvertical is not supported");
 	if (in == out) TB_FAIL(ctx, "VerticalDynamics StepExplicit must have iDataInitial != iDataUpdate");
-	return nh_launch(ctx, in, out, dt, false, true);
+	return nh_launch(ctx, in, out, dt, false, true, stage_base_out());
 }
 
 extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
@@ -807,7 +879,37 @@ extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double d
 		if (tb200_h_step_explicit(ctx, in, out, dt)) return 1;
 		return tb200_v_step_explicit(ctx, in, out, dt);
 	}
-	return nh_launch(ctx, in, out, dt, true, true);
+	return nh_launch(ctx, in, out, dt, true, true, stage_base_out());
+}
+
+// Grid::LinearCombineData(coeff, out) (or CopyData when ncoeff == 0: copy of
+// instance -ncoeff_src) followed by both explicit plugins, in one pass:
+// HorizontalDynamics::StepExplicitCombine (HorizontalDynamics.h:97-106).
+extern "C" int tb200_hv_step_explicit_combine(
+	tb200_ctx * ctx, const double * coeff, int ncoeff, int in, int out, double dt
+) {
+	if (check_inst2(ctx, in, out)) return 1;
+	const int ni = (int)ctx->inst.size();
+	if (out >= ncoeff) TB_FAIL(ctx, "Destination index out of coefficient bounds");
+	if (ncoeff > ni) TB_FAIL(ctx, "Too many elements in coefficient vector.");
+	const bool fusable =
+		(ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && (ctx->lay.nlev > 1)
+		&& (ctx->lay.ntr == 0) && (in != out);
+	if (!fusable) {
+		if (tb200_lincomb(ctx, coeff, ncoeff, out, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
+		return tb200_hv_step_explicit(ctx, in, out, dt);
+	}
+	StageBase sb;
+	memset(&sb, 0, sizeof(sb));
+	sb.cdst = coeff[out];
+	sb.scale_dst = (coeff[out] == 0.0) ? 0 : 1;
+	for (int m = 0; m < ncoeff; m++) {
+		if (m == out || coeff[m] == 0.0) continue;
+		sb.src[sb.nsrc] = ctx->inst[m];
+		sb.coeff[sb.nsrc] = coeff[m];
+		sb.nsrc++;
+	}
+	return nh_launch(ctx, in, out, dt, true, true, sb);
 }
 
 extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt) {

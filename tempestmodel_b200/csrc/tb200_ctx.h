@@ -22,6 +22,8 @@ struct PatchInfo {
 	long long elem0;           // first local element, -1 when owned elsewhere
 	std::vector<int64_t> ids;  // [nea*np][neb*np] global node ids
 	std::vector<SeamEntry> seams;
+	bool has_terrain;
+	PatchInfo() : has_terrain(false) {}
 };
 
 struct HostOp {
@@ -67,6 +69,8 @@ struct tb200_ctx {
 	double * d_area_node;             // [e][L][NN] element area (checksum)
 	double * d_area_redge;            // [e][L+1][NN]
 	double * d_sums;
+	double * d_tx; double * d_ty; double * d_tda; double * d_tdb;
+	double * d_reta_n; double * d_reta_e;
 
 	// averaging groups
 	int ngroups;
@@ -96,6 +100,7 @@ struct tb200_ctx {
 		d_stage(0), stage_doubles(0), d_rowmap(0),
 		d_inv_da(0), d_inv_db(0), d_nu_scale(0),
 		d_area_node(0), d_area_redge(0), d_sums(0),
+		d_tx(0), d_ty(0), d_tda(0), d_tdb(0), d_reta_n(0), d_reta_e(0),
 		ngroups(0), d_members(0), d_flags(0), nseam(0), d_seam_group(0),
 		d_seam_mats(0), rank(0), nranks(1), exch_fn(0), exch_user(0),
 		nsend_total(0), nrecv_total(0), d_send_nodes(0), d_sendbuf(0),

@@ -68,6 +68,32 @@ struct DevGeom {
 	const double * jace;
 	const double * cae[3]; const double * cbe[3]; const double * cxe[3];
 	const double * dre[3];
+	// Terrain-following cubed-sphere metric evaluated on the fly (optional):
+	// gnomonic X, Y and the topography derivatives per column [e][NN], the
+	// eta levels / interfaces, model top and radius
+	// (GridPatchCSGLL::EvaluateGeometricTerms, GridPatchCSGLL.cpp:344-553)
+	int analytic;
+	const double * tx; const double * ty;
+	const double * tda; const double * tdb;
+	const double * reta_n; const double * reta_e;
+	double ztop, radius;
+};
+
+// Column constants and per-level values of the terrain-following metric,
+// evaluated with the reference's expression order and without FMA contraction
+// so that they equal the stored arrays bit for bit.
+struct ColMetric {
+	double a0, a1, b0, b1, j2d;
+	double onepx2, onepy2, xy;
+	double msod;        // (-scale) / dxr
+	double inv_dxr, inv_dxr2, dxr;
+	double dazs, dbzs;
+};
+
+struct LevMetric {
+	double jac;
+	double a2, b2, x2;  // ContraMetricA[2], ContraMetricB[2], ContraMetricXi[2]
+	double dar, dbr;    // DerivR[0], DerivR[1]
 };
 
 struct DevTables {

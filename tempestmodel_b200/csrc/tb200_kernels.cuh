@@ -334,6 +334,71 @@ struct NHArgs {
 	int fe_nodes;       // nodes per vertical finite element (vertorder; 1 for FV)
 };
 
+// Base of the stage result: the current content of the update instance, or a
+// linear combination of instances formed on the fly (Grid::CopyData /
+// LinearCombineData fused into the stage; same operation order as k_lincomb).
+struct StageBase {
+	const double * src[TB_MAXINST];
+	double coeff[TB_MAXINST];
+	int nsrc;
+	double cdst;
+	int scale_dst;
+	int use_out;        // 1: base = out as it is
+};
+
+__device__ __forceinline__ double tb_stage_base(
+	const StageBase & sb, const double * out, size_t off
+) {
+	if (sb.use_out) return out[off];
+	double v = 0.0;
+	if (sb.scale_dst) v = out[off] * sb.cdst;
+	for (int m = 0; m < sb.nsrc; m++) {
+		v += sb.src[m][off] * sb.coeff[m];
+	}
+	return v;
+}
+
+// ---- terrain-following metric on the fly --------------------------------------
+// GridPatchCSGLL::EvaluateGeometricTerms (GridPatchCSGLL.cpp:344-553)
+
+__device__ __forceinline__ ColMetric tb_col_metric(const DevGeom & g, size_t g2) {
+	ColMetric c;
+	c.a0 = g.a0[g2]; c.a1 = g.a1[g2]; c.b0 = g.b0[g2]; c.b1 = g.b1[g2];
+	c.j2d = g.j2d[g2];
+	c.onepx2 = 1.0; c.onepy2 = 1.0; c.xy = 0.0; c.msod = 0.0;
+	c.inv_dxr = 0.0; c.inv_dxr2 = 0.0; c.dxr = 0.0; c.dazs = 0.0; c.dbzs = 0.0;
+	if (g.analytic) {
+		const double X = g.tx[g2], Y = g.ty[g2];
+		const double xx = __dmul_rn(X, X), yy = __dmul_rn(Y, Y);
+		const double d2 = __dadd_rn(__dadd_rn(1.0, xx), yy);
+		c.onepx2 = __dadd_rn(1.0, xx);
+		c.onepy2 = __dadd_rn(1.0, yy);
+		c.xy = __dmul_rn(X, Y);
+		const double aa = __dmul_rn(g.radius, g.radius);
+		const double scale = __ddiv_rn(__ddiv_rn(__ddiv_rn(d2, c.onepx2), c.onepy2), aa);
+		c.dxr = __dadd_rn(g.ztop, -g.zs[g2]);
+		c.msod = __ddiv_rn(-scale, c.dxr);
+		c.inv_dxr = __ddiv_rn(1.0, c.dxr);
+		c.inv_dxr2 = __ddiv_rn(1.0, __dmul_rn(c.dxr, c.dxr));
+		c.dazs = g.tda[g2];
+		c.dbzs = g.tdb[g2];
+	}
+	return c;
+}
+
+__device__ __forceinline__ LevMetric tb_lev_metric(const ColMetric & c, double eta) {
+	LevMetric m;
+	const double w = __dadd_rn(1.0, -eta);
+	m.dar = __dmul_rn(w, c.dazs);
+	m.dbr = __dmul_rn(w, c.dbzs);
+	m.jac = __dmul_rn(c.dxr, c.j2d);
+	m.a2 = __dmul_rn(c.msod, __dadd_rn(__dmul_rn(c.onepy2, m.dar), __dmul_rn(c.xy, m.dbr)));
+	m.b2 = __dmul_rn(c.msod, __dadd_rn(__dmul_rn(c.xy, m.dar), __dmul_rn(c.onepx2, m.dbr)));
+	m.x2 = __dadd_rn(c.inv_dxr2,
+		-__dmul_rn(c.inv_dxr, __dadd_rn(__dmul_rn(m.a2, m.dar), __dmul_rn(m.b2, m.dbr))));
+	return m;
+}
+
 // shared-memory doubles needed by k_nh_explicit
 __host__ __device__ inline size_t tb_nh_smem_doubles(int L, int nn, int kb) {
 	return (size_t)nn * (3 * L + (L + 1) + 3 * L) + (size_t)kb * 7 * nn;
@@ -342,7 +407,7 @@ __host__ __device__ inline size_t tb_nh_smem_doubles(int L, int nn, int kb) {
 template <int NP, bool DO_H, bool DO_V>
 __global__ void k_nh_explicit(
 	DevLayout lay, DevGeom g, DevTables t, DevOps ops, DevPhys ph, NHArgs args,
-	const double * __restrict__ in, double * __restrict__ out, int KB
+	StageBase sb, const double * __restrict__ in, double * out, int KB
 ) {
 	const int NN = NP * NP;
 	const int UIx = 0, VIx = 1, PIx = 2, WIx = 3, RIx = 4;
@@ -365,16 +430,16 @@ __global__ void k_nh_explicit(
 	const int nt = blockDim.x;
 
 	const size_t ebase = (size_t)e * lay.nrows * NN;
-	const double * inU = in + ebase + (size_t)lay.rowoff[UIx] * NN;
-	const double * inV = in + ebase + (size_t)lay.rowoff[VIx] * NN;
-	const double * inP = in + ebase + (size_t)lay.rowoff[PIx] * NN;
-	const double * inW = in + ebase + (size_t)lay.rowoff[WIx] * NN;
-	const double * inR = in + ebase + (size_t)lay.rowoff[RIx] * NN;
-	double * outU = out + ebase + (size_t)lay.rowoff[UIx] * NN;
-	double * outV = out + ebase + (size_t)lay.rowoff[VIx] * NN;
-	double * outP = out + ebase + (size_t)lay.rowoff[PIx] * NN;
-	double * outW = out + ebase + (size_t)lay.rowoff[WIx] * NN;
-	double * outR = out + ebase + (size_t)lay.rowoff[RIx] * NN;
+	const size_t offU = ebase + (size_t)lay.rowoff[UIx] * NN;
+	const size_t offV = ebase + (size_t)lay.rowoff[VIx] * NN;
+	const size_t offP = ebase + (size_t)lay.rowoff[PIx] * NN;
+	const size_t offW = ebase + (size_t)lay.rowoff[WIx] * NN;
+	const size_t offR = ebase + (size_t)lay.rowoff[RIx] * NN;
+	const double * inU = in + offU;
+	const double * inV = in + offV;
+	const double * inP = in + offP;
+	const double * inW = in + offW;
+	const double * inR = in + offR;
 
 	for (int idx = threadIdx.x; idx < L * NN; idx += nt) {
 		sU[idx] = inU[idx];
@@ -390,6 +455,18 @@ __global__ void k_nh_explicit(
 	const size_t g2 = (size_t)e * NN + n;
 	const size_t g3 = (size_t)e * L * NN;
 	const size_t g3e = (size_t)e * (L + 1) * NN;
+	const ColMetric cm = tb_col_metric(g, g2);
+
+	// xi-row of the contravariant metric on interface m of this thread's column
+	auto cxe_at = [&](int m, double & c0, double & c1, double & c2) {
+		if (g.analytic) {
+			const LevMetric lm = tb_lev_metric(cm, g.reta_e[m]);
+			c0 = lm.a2; c1 = lm.b2; c2 = lm.x2;
+		} else {
+			const size_t om = g3e + (size_t)m * NN + n;
+			c0 = g.cxe[0][om]; c1 = g.cxe[1][om]; c2 = g.cxe[2][om];
+		}
+	};
 
 	double * tWn = tile + (size_t)kk * 7 * NN;  // covariant w on levels
 	double * tKE = tWn + NN;
@@ -409,6 +486,7 @@ __global__ void k_nh_explicit(
 		double dConUa = 0.0, dConUb = 0.0, dConUx = 0.0;
 		double dJac = 1.0, dRho = 1.0, dRhoTheta = 1.0;
 		double dAlphaBaseFlux = 0.0, dBetaBaseFlux = 0.0;
+		double dDerivR0 = 0.0, dDerivR1 = 0.0;
 
 		if (DO_H) {
 			dCovUa = sU[o];
@@ -416,13 +494,24 @@ __global__ void k_nh_explicit(
 			// InterpolateREdgeToNode(W) (:817-819, GridPatchGLL.cpp:109-143)
 			dCovUx = tb_col_apply(ops.op[1], sW + n, NN, kc);
 
-			dJac = g.jac[g3 + o];
-			const double m0 = g.ca[0][g3 + o];
-			const double m1 = g.ca[1][g3 + o];
-			const double m2 = g.ca[2][g3 + o];
-			const double m3 = g.cb[1][g3 + o];
-			const double m4 = g.cb[2][g3 + o];
-			const double m5 = g.cx[2][g3 + o];
+			double m0, m1, m2, m3, m4, m5;
+			if (g.analytic) {
+				const LevMetric lm = tb_lev_metric(cm, g.reta_n[kc]);
+				dJac = lm.jac;
+				m0 = cm.a0; m1 = cm.a1; m2 = lm.a2;
+				m3 = cm.b1; m4 = lm.b2; m5 = lm.x2;
+				dDerivR0 = lm.dar; dDerivR1 = lm.dbr;
+			} else {
+				dJac = g.jac[g3 + o];
+				m0 = g.ca[0][g3 + o];
+				m1 = g.ca[1][g3 + o];
+				m2 = g.ca[2][g3 + o];
+				m3 = g.cb[1][g3 + o];
+				m4 = g.cb[2][g3 + o];
+				m5 = g.cx[2][g3 + o];
+				dDerivR0 = g.dr[0][g3 + o];
+				dDerivR1 = g.dr[1][g3 + o];
+			}
 
 			// Contravariant velocities (:916-929)
 			dConUa = m0 * dCovUa + m1 * dCovUb + m2 * dCovUx;
@@ -510,7 +599,7 @@ __global__ void k_nh_explicit(
 
 			// Coriolis (:1330-1338)
 			const double dF = g.f[g2];
-			const double dJ2D = g.j2d[g2];
+			const double dJ2D = cm.j2d;
 			dLocalUpdateUa += dF * dJ2D * dConUb;
 			dLocalUpdateUb -= dF * dJ2D * dConUa;
 
@@ -519,8 +608,8 @@ __global__ void k_nh_explicit(
 			const double dPressureGradientForceUb = dDbP * dRhoTheta / dRho;
 
 			// Gravity (:1363-1364)
-			const double dDaPhi = ph.g * g.dr[0][g3 + o];
-			const double dDbPhi = ph.g * g.dr[1][g3 + o];
+			const double dDaPhi = ph.g * dDerivR0;
+			const double dDbPhi = ph.g * dDerivR1;
 
 			const double dDaUpdate = dPressureGradientForceUa + dDaKE + dDaPhi;
 			const double dDbUpdate = dPressureGradientForceUb + dDbKE + dDbPhi;
@@ -528,8 +617,8 @@ __global__ void k_nh_explicit(
 			dLocalUpdateUb -= dDbUpdate;
 
 			if (active) {
-				uNew = outU[o] + dt * dLocalUpdateUa;
-				vNew = outV[o];
+				uNew = tb_stage_base(sb, out, offU + o) + dt * dLocalUpdateUa;
+				vNew = tb_stage_base(sb, out, offV + o);
 				if (!args.xz) {
 					vNew += dt * dLocalUpdateUb;
 				}
@@ -537,12 +626,14 @@ __global__ void k_nh_explicit(
 				sVn[o] = vNew;
 				sZX[o] = dUCrossZetaX;
 				// Density and rho-theta (:1399-1421)
-				outR[o] -= dt * dInvJacobian * (dDaRhoFluxA + dDbRhoFluxB);
-				outP[o] -= dt * dInvJacobian * (dDaPressureFluxA + dDbPressureFluxB);
+				out[offR + o] = tb_stage_base(sb, out, offR + o)
+					- dt * dInvJacobian * (dDaRhoFluxA + dDbRhoFluxB);
+				out[offP + o] = tb_stage_base(sb, out, offP + o)
+					- dt * dInvJacobian * (dDaPressureFluxA + dDbPressureFluxB);
 			}
 		} else if (active) {
-			uNew = outU[o];
-			vNew = outV[o];
+			uNew = tb_stage_base(sb, out, offU + o);
+			vNew = tb_stage_base(sb, out, offV + o);
 		}
 
 		if (DO_V && active) {
@@ -556,9 +647,9 @@ __global__ void k_nh_explicit(
 				const size_t om = (size_t)m * NN + n;
 				const double ue = tb_col_apply(ops.op[0], sU + n, NN, m);
 				const double ve = tb_col_apply(ops.op[0], sV + n, NN, m);
-				const double xd =
-					g.cxe[0][g3e + om] * ue + g.cxe[1][g3e + om] * ve
-					+ g.cxe[2][g3e + om] * sW[om];
+				double c0, c1, c2;
+				cxe_at(m, c0, c1, c2);
+				const double xd = c0 * ue + c1 * ve + c2 * sW[om];
 				const double w = dt * fabs(xd);
 				uNew += tb_col_apply(ops.op[8], sU + n, NN, k) * w;
 				vNew += tb_col_apply(ops.op[8], sV + n, NN, k) * w;
@@ -568,17 +659,17 @@ __global__ void k_nh_explicit(
 				const size_t om = (size_t)m * NN + n;
 				const double ue = tb_col_apply(ops.op[0], sU + n, NN, m);
 				const double ve = tb_col_apply(ops.op[0], sV + n, NN, m);
-				const double xd =
-					g.cxe[0][g3e + om] * ue + g.cxe[1][g3e + om] * ve
-					+ g.cxe[2][g3e + om] * sW[om];
+				double c0, c1, c2;
+				cxe_at(m, c0, c1, c2);
+				const double xd = c0 * ue + c1 * ve + c2 * sW[om];
 				const double w = dt * fabs(xd);
 				uNew += tb_col_apply(ops.op[9], sU + n, NN, k) * w;
 				vNew += tb_col_apply(ops.op[9], sV + n, NN, k) * w;
 			}
 		}
 		if (active) {
-			outU[o] = uNew;
-			outV[o] = vNew;
+			out[offU + o] = uNew;
+			out[offV + o] = vNew;
 		}
 
 		// Tracers (:1531-1553)
@@ -599,8 +690,14 @@ __global__ void k_nh_explicit(
 				dDaTracerFluxA *= dInvDA;
 				dDbTracerFluxB *= dInvDB;
 				if (active) {
-					out[oT] -= dt * dInvJacobian * (dDaTracerFluxA + dDbTracerFluxB);
+					out[oT] = tb_stage_base(sb, out, oT)
+						- dt * dInvJacobian * (dDaTracerFluxA + dDbTracerFluxB);
 				}
+			}
+		} else if (!sb.use_out) {
+			for (int c = 0; c < lay.ntr; c++) {
+				const size_t oT = ebase + (size_t)(lay.troff + c * L + kc) * NN + n;
+				if (active) out[oT] = tb_stage_base(sb, out, oT);
 			}
 		}
 		__syncthreads();
@@ -608,18 +705,36 @@ __global__ void k_nh_explicit(
 
 	// Vertical velocity on interfaces (:1612-1660)
 	if (DO_H) {
-		for (int idx = threadIdx.x; idx < L * NN; idx += nt) {
+		for (int idx = threadIdx.x; idx < (L + 1) * NN; idx += nt) {
 			const int k = idx / NN;
 			const int nc = idx % NN;
 			if (k == 0) {
 				const double dU0 = tb_col_apply(ops.op[0], sUn + nc, NN, 0);
 				const double dV0 = tb_col_apply(ops.op[0], sVn + nc, NN, 0);
-				const size_t oe = g3e + nc;
-				outW[nc] = -(g.cxe[0][oe] * dU0 + g.cxe[1][oe] * dV0) / g.cxe[2][oe];
-			} else {
+				double c0, c1, c2;
+				if (g.analytic) {
+					const ColMetric cmc = tb_col_metric(g, (size_t)e * NN + nc);
+					const LevMetric lm = tb_lev_metric(cmc, g.reta_e[0]);
+					c0 = lm.a2; c1 = lm.b2; c2 = lm.x2;
+				} else {
+					const size_t oe = g3e + nc;
+					c0 = g.cxe[0][oe]; c1 = g.cxe[1][oe]; c2 = g.cxe[2][oe];
+				}
+				out[offW + nc] = -(c0 * dU0 + c1 * dV0) / c2;
+			} else if (k < L) {
 				const double dUCrossZetaX = tb_col_apply(ops.op[0], sZX + nc, NN, k);
-				outW[idx] += dt * dUCrossZetaX;
+				out[offW + idx] = tb_stage_base(sb, out, offW + idx) + dt * dUCrossZetaX;
+			} else if (!sb.use_out) {
+				out[offW + idx] = tb_stage_base(sb, out, offW + idx);
 			}
+		}
+	} else if (!sb.use_out) {
+		for (int idx = threadIdx.x; idx < (L + 1) * NN; idx += nt) {
+			out[offW + idx] = tb_stage_base(sb, out, offW + idx);
+		}
+		for (int idx = threadIdx.x; idx < L * NN; idx += nt) {
+			out[offP + idx] = tb_stage_base(sb, out, offP + idx);
+			out[offR + idx] = tb_stage_base(sb, out, offR + idx);
 		}
 	}
 }

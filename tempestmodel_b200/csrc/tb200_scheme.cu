@@ -55,6 +55,21 @@ static int lincomb(tb200_ctx * ctx, const std::vector<double> & c, int dst) {
 	return tb200_lincomb(ctx, c.data(), (int)c.size(), dst, ALL);
 }
 
+// CopyData(src -> out) / LinearCombineData(c -> out) + explicit substage, the
+// combination formed inside the stage kernel
+static int substage_from(tb200_ctx * ctx, std::vector<double> c, int in, int out, double dt) {
+	if ((int)c.size() <= out) c.resize(out + 1, 0.0);
+	TRY(tb200_hv_step_explicit_combine(ctx, c.data(), (int)c.size(), in, out, dt));
+	TRY(tb200_dss(ctx, out, ALL));
+	return 0;
+}
+
+static std::vector<double> copy_of(int src) {
+	std::vector<double> c(src + 1, 0.0);
+	c[src] = 1.0;
+	return c;
+}
+
 ///////////////////////////////////////////////////////////////////////////////
 
 static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double dt) {
@@ -100,17 +115,12 @@ static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double 
 
 	} else {
 		// Kinnmark-Gray-Ullrich (3,5), :548-585
-		TRY(tb200_copy(ctx, 0, 1, ALL));
-		TRY(substage(ctx, 0, 1, dt / 5.0));
-		TRY(tb200_copy(ctx, 0, 2, ALL));
-		TRY(substage(ctx, 1, 2, dt / 5.0));
-		TRY(tb200_copy(ctx, 0, 3, ALL));
-		TRY(substage(ctx, 2, 3, dt / 3.0));
-		TRY(tb200_copy(ctx, 0, 2, ALL));
-		TRY(substage(ctx, 3, 2, 2.0 * dt / 3.0));
+		TRY(substage_from(ctx, copy_of(0), 0, 1, dt / 5.0));
+		TRY(substage_from(ctx, copy_of(0), 1, 2, dt / 5.0));
+		TRY(substage_from(ctx, copy_of(0), 2, 3, dt / 3.0));
+		TRY(substage_from(ctx, copy_of(0), 3, 2, 2.0 * dt / 3.0));
 		const std::vector<double> kgu = {-1.0 / 4.0, 5.0 / 4.0, 0.0, 0.0, 0.0};
-		TRY(lincomb(ctx, kgu, 4));
-		TRY(substage(ctx, 2, 4, 3.0 * dt / 4.0));
+		TRY(substage_from(ctx, kgu, 2, 4, 3.0 * dt / 4.0));
 	}
 
 	// hyperdiffusion, :638-641
@@ -202,23 +212,19 @@ static int step_ars343(tb200_ctx * ctx, int first, int last, double dt) {
 	(void)last;
 	static const ARS343Coefficients k = ars343_coefficients();
 	// :161-234
-	TRY(tb200_copy(ctx, 0, 1, ALL));
-	TRY(substage(ctx, 0, 1, k.diag_exp[0] * dt));
+	TRY(substage_from(ctx, copy_of(0), 0, 1, k.diag_exp[0] * dt));
 	TRY(tb200_copy(ctx, 1, 2, ALL));
 	TRY(tb200_v_step_implicit(ctx, 2, 2, k.diag_imp[0] * dt));
 
-	TRY(lincomb(ctx, k.u2, 3));
-	TRY(substage(ctx, 2, 3, k.diag_exp[1] * dt));
+	TRY(substage_from(ctx, k.u2, 2, 3, k.diag_exp[1] * dt));
 	TRY(tb200_copy(ctx, 3, 4, ALL));
 	TRY(tb200_v_step_implicit(ctx, 4, 4, k.diag_imp[1] * dt));
 
-	TRY(lincomb(ctx, k.u3, 5));
-	TRY(substage(ctx, 4, 5, k.diag_exp[2] * dt));
+	TRY(substage_from(ctx, k.u3, 4, 5, k.diag_exp[2] * dt));
 	TRY(tb200_copy(ctx, 5, 6, ALL));
 	TRY(tb200_v_step_implicit(ctx, 6, 6, k.diag_imp[2] * dt));
 
-	TRY(lincomb(ctx, k.u4, 1));
-	TRY(substage(ctx, 6, 1, k.diag_exp[3] * dt));
+	TRY(substage_from(ctx, k.u4, 6, 1, k.diag_exp[3] * dt));
 
 	TRY(tb200_copy(ctx, 1, 0, ALL));
 	TRY(tb200_h_step_after_subcycle(ctx, 1, 0, 2, dt));

@@ -123,6 +123,15 @@ class DeviceContext:
             setattr(g, name, None if a is None else a.ctypes.data)
         self._ck(self.lib.tb200_upload_geometry(self._h, patch, ctypes.byref(g)))
 
+    def set_terrain_metric(self, patch, xnode, ynode, topography_deriv):
+        x, y, t = _f64(xnode), _f64(ynode), _f64(topography_deriv)
+        self._ck(self.lib.tb200_set_terrain_metric(self._h, patch, _ptr(x), _ptr(y),
+                                                   _ptr(t)))
+
+    def set_vertical_coordinate(self, reta_levels, reta_interfaces):
+        a, b = _f64(reta_levels), _f64(reta_interfaces)
+        self._ck(self.lib.tb200_set_vertical_coordinate(self._h, _ptr(a), _ptr(b)))
+
     def upload_element_area(self, patch, area_node, area_redge):
         a, b = _f64(area_node), _f64(area_redge)
         self._ck(self.lib.tb200_upload_element_area(self._h, patch, _ptr(a), _ptr(b)))
@@ -182,6 +191,11 @@ class DeviceContext:
 
     def hv_step_explicit(self, i_in, i_out, dt):
         self._ck(self.lib.tb200_hv_step_explicit(self._h, i_in, i_out, dt))
+
+    def hv_step_explicit_combine(self, coeff, i_in, i_out, dt):
+        c = _f64(coeff)
+        self._ck(self.lib.tb200_hv_step_explicit_combine(self._h, _ptr(c), len(c),
+                                                         i_in, i_out, dt))
 
     def v_step_implicit(self, i_in, i_out, dt):
         self._ck(self.lib.tb200_v_step_implicit(self._h, i_in, i_out, dt))

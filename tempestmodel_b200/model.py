@@ -79,10 +79,19 @@ class Model:
             ctx.upload_geometry(p.index, **geo)
             ctx.upload_element_area(p.index, p.area_node, p.area_redge)
             ctx.set_seam_transforms(p.index, *p.seam_transforms())
+            if self.ncomp == 5:
+                # let the kernels evaluate the terrain-following metric on the fly
+                xn = np.zeros(p.wa)
+                yn = np.zeros(p.wb)
+                xn[1:-1], yn[1:-1] = p.X, p.Y
+                ctx.set_terrain_metric(p.index, xn, yn,
+                                       p._pad(np.stack([p._dazs, p._dbzs], axis=-1)))
             if upload_state:
                 node, redge = self.evaluate_test_case(p)
                 self._host[p.index] = (node, redge)
                 ctx.upload_state(p.index, 0, node, redge, None)
+        if self.ncomp == 5:
+            ctx.set_vertical_coordinate(g.reta_levels, g.reta_interfaces)
         ctx.build_connectivity()
         return self
 

@@ -18,7 +18,7 @@ def S(d, k):
 
 
 def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
-                      nranks=1, exchange=None):
+                      nranks=1, exchange=None, analytic_metric=True):
     npatch = S(d, "grid.npatch")
     np_ = S(d, "grid.np")
     nlev = S(d, "grid.nlev")
@@ -103,6 +103,13 @@ def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
                 ia, ib, sp, m = cubedsphere.seam_transforms(
                     S(d, p + "panel"), nea, neb, ea0, eb0, ne, np_, an, bn)
                 ctx.set_seam_transforms(idx, ia, ib, sp, m)
+    if (analytic_metric and not cartesian and eqn == 2 and "patch0.xnode" in d):
+        for n in range(npatch):
+            if owners[n] == rank:
+                p = "patch%d." % n
+                ctx.set_terrain_metric(S(d, p + "index"), d[p + "xnode"], d[p + "ynode"],
+                                       d[p + "topographyderiv"])
+        ctx.set_vertical_coordinate(d["grid.retalevels"], d["grid.retainterfaces"])
     ctx.build_connectivity()
     ctx.dump = d
     ctx.local_patches = [n for n in range(npatch) if owners[n] == rank]
