@@ -171,6 +171,16 @@ int tb200_set_terrain_metric(tb200_ctx * ctx, int patch_index, const double * xn
 int tb200_set_vertical_coordinate(tb200_ctx * ctx, const double * reta_levels,
                                   const double * reta_interfaces);
 
+/* Fast path of the nonhydrostatic kernels (vertical order 1, terrain-following
+ * metric with level-independent layer depth): the 3-D metric arrays are
+ * replaced by 13 constants per column, checked against the uploaded arrays
+ * (relative deviation <= 1e-13) before the path is enabled.  Returns 1 when the
+ * fast kernels are in use, 0 when the general kernels run (reason: see
+ * tb200_fast_path_reason), -1 on error.  TB200_STAGE_KERNEL=generic disables it. */
+int tb200_fast_path(tb200_ctx * ctx);
+const char * tb200_fast_path_reason(tb200_ctx * ctx);
+double tb200_fast_path_metric_error(tb200_ctx * ctx);
+
 /*
  * Connectivity.  The reference finds coincident nodes through its exchange
  * buffer topology (Grid.cpp:1066-1573, Connectivity.cpp:47-744); here the host

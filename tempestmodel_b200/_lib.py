@@ -95,6 +95,9 @@ _SIGNATURES = {
     "tb200_set_terrain_metric": (c_int, [c_void_p, c_int, c_void_p, c_void_p,
                                          c_void_p]),
     "tb200_set_vertical_coordinate": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "tb200_fast_path": (c_int, [c_void_p]),
+    "tb200_fast_path_reason": (c_char_p, [c_void_p]),
+    "tb200_fast_path_metric_error": (c_double, [c_void_p]),
     "tb200_v_step_implicit": (c_int, [c_void_p, c_int, c_int, c_double]),
     "tb200_dss": (c_int, [c_void_p, c_int, c_int]),
     "tb200_h_step_after_subcycle": (c_int, [c_void_p, c_int, c_int, c_int,

@@ -15,6 +15,7 @@
 #include "tb200_kernels.cuh"
 #include "tb200_dss.cuh"
 #include "tb200_column.cuh"
+#include "tb200_fast.cuh"
 
 #define TB_CHECK(ctx, call) \
 	do { \
@@ -451,7 +452,11 @@ extern "C" int tb200_upload_geometry(
 		if (upload_geom_array(ctx, *pi, gh->contrametricb_redge, L + 1, 3, ge[4], ge[5], ge[6])) return 1;
 		if (upload_geom_array(ctx, *pi, gh->contrametricxi_redge, L + 1, 3, ge[7], ge[8], ge[9])) return 1;
 		if (upload_geom_array(ctx, *pi, gh->derivr_redge, L + 1, 3, ge[10], ge[11], ge[12])) return 1;
+		if (gh->contrametrica != 0 && gh->contrametricxi_redge != 0 && gh->derivr_node != 0) {
+			ctx->geometry3d_uploaded = true;
+		}
 	}
+	ctx->fast_state = 0;
 	return 0;
 }
 
@@ -498,6 +503,9 @@ extern "C" int tb200_set_vertical_coordinate(
 	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
 	const int L = ctx->lay.nlev;
 	std::vector<double> a(reta_levels, reta_levels + L), b(reta_interfaces, reta_interfaces + L + 1);
+	ctx->reta_n_h = a;
+	ctx->reta_e_h = b;
+	ctx->fast_state = 0;
 	if (dupload(ctx, &ctx->d_reta_n, a)) return 1;
 	if (dupload(ctx, &ctx->d_reta_e, b)) return 1;
 	bool all = true;
@@ -774,6 +782,136 @@ extern "C" int tb200_zero(tb200_ctx * ctx, int inst, int mask) {
 	return launch_combine(ctx, ca, inst, row0, row1);
 }
 
+
+///////////////////////////////////////////////////////////////////////////////
+// Fast path set-up (tb200_fast.cuh): operator windows, column constants and
+// their verification against the uploaded reference metric.
+
+// dense window of row `row` of operator h over inputs [first, first + nw):
+// false if the row has a non-zero coefficient outside the window
+static bool op_window(const HostOp & h, int row, int first, int nw, double * w) {
+	for (int q = 0; q < nw; q++) w[q] = 0.0;
+	if (row < 0 || row >= h.nout) return true;
+	for (int l = h.begin[row]; l < h.end[row]; l++) {
+		const double c = h.coeff[(size_t)row * h.width + (l - h.begin[row])];
+		if (l >= first && l < first + nw) {
+			w[l - first] = c;
+		} else if (c != 0.0) {
+			return false;
+		}
+	}
+	return true;
+}
+
+static int fast_prepare(tb200_ctx * ctx) {
+	if (ctx->fast_state != 0) return 0;
+	ctx->fast_state = -1;
+	const DevLayout & lay = ctx->lay;
+	const int L = lay.nlev;
+	const char * force = getenv("TB200_STAGE_KERNEL");
+	if (force != 0 && strcmp(force, "generic") == 0) { ctx->fast_reason = "TB200_STAGE_KERNEL=generic"; return 0; }
+	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || lay.np != 4 || L < 2) {
+		ctx->fast_reason = "not a nonhydrostatic np=4 configuration"; return 0;
+	}
+	if (ctx->cfg.vertical_order != 1) { ctx->fast_reason = "vertical order > 1"; return 0; }
+	if ((int)ctx->reta_n_h.size() != L || (int)ctx->reta_e_h.size() != L + 1) {
+		ctx->fast_reason = "vertical coordinate not set"; return 0;
+	}
+	for (size_t p = 0; p < ctx->patches.size(); p++) {
+		if (ctx->patches[p].elem0 >= 0 && !ctx->patches[p].has_terrain) {
+			ctx->fast_reason = "topography derivatives not set"; return 0;
+		}
+	}
+	for (int q = 0; q < TB_NOPS; q++) {
+		if (q == 5 || q == 6) continue;
+		if (ctx->hops[q].nout == 0) { ctx->fast_reason = "column operators not set"; return 0; }
+	}
+	// operator windows
+	std::vector<double> lev((size_t)(L + 1) * TBF_LW, 0.0);
+	bool ok = true;
+	for (int k = 0; k <= L; k++) {
+		double * row = &lev[(size_t)k * TBF_LW];
+		if (k < L) {
+			ok = ok && op_window(ctx->hops[1], k, k, 2, row + TBF_CW);
+			ok = ok && op_window(ctx->hops[2], k, k - 1, 3, row + TBF_CD);
+			ok = ok && op_window(ctx->hops[8], k, k - 1, 3, row + TBF_CPL);
+			ok = ok && op_window(ctx->hops[9], k, k - 1, 3, row + TBF_CPR);
+			ok = ok && op_window(ctx->hops[4], k, k, 2, row + TBF_DEN);
+			row[TBF_SN] = 1.0 - ctx->reta_n_h[k];
+		}
+		if (k >= 1 && k < L) {
+			ok = ok && op_window(ctx->hops[0], k, k - 1, 3, row + TBF_CILO);
+			if (row[TBF_CILO + 2] != 0.0) ok = false;   // interface k reads levels k-1, k
+			ok = ok && op_window(ctx->hops[3], k, k - 1, 2, row + TBF_DNE);
+		}
+		if (k + 1 < L) {
+			ok = ok && op_window(ctx->hops[0], k + 1, k - 1, 3, row + TBF_CIHI);
+		}
+		if (k >= 1) {
+			ok = ok && op_window(ctx->hops[1], k - 1, k - 1, 2, row + TBF_IEN1);
+		}
+		ok = ok && op_window(ctx->hops[7], k, k - 1, 3, row + TBF_DDE);
+		row[TBF_SE] = 1.0 - ctx->reta_e_h[k];
+		row[TBF_SE1] = (k < L) ? (1.0 - ctx->reta_e_h[k + 1]) : 0.0;
+	}
+	ok = ok && op_window(ctx->hops[0], 0, 0, 3, &lev[TBF_CB0]);
+	if (!ok) { ctx->fast_reason = "a column operator row is wider than the order-1 window"; return 0; }
+	if (ctx->d_lev == 0) {
+		if (dalloc(ctx, &ctx->d_lev, lev.size())) return 1;
+		if (dalloc(ctx, &ctx->d_colc, (size_t)lay.nelem * TBF_NC * lay.nn)) return 1;
+	}
+	TB_CHECK(ctx, cudaMemcpy(ctx->d_lev, lev.data(), lev.size() * sizeof(double), cudaMemcpyHostToDevice));
+	DevGeom g = ctx->geom;
+	g.tda = ctx->d_tda; g.tdb = ctx->d_tdb; g.ztop = ctx->cfg.ztop;
+	const long long ncol = lay.nelem * lay.nn;
+	{
+		auto kfn = k_fast_colc;
+		TB_LAUNCH_FLAT(kfn, dim3((unsigned)((ncol + 255) / 256)), dim3(256), 0, ctx->stream,
+			ncol, g, ctx->cfg.g, ctx->d_colc);
+		TB_KERNEL_CHECK(ctx);
+	}
+	ctx->fast_metric_error = 0.0;
+	if (ctx->geometry3d_uploaded) {
+		const int nb = 148, nt = 128;
+		double * d_errs = 0;
+		if (dalloc(ctx, &d_errs, (size_t)nb * nt)) return 1;
+		auto kfn = k_fast_verify;
+		TB_LAUNCH_FLAT(kfn, dim3(nb), dim3(nt), 0, ctx->stream,
+			lay, ctx->geom, ctx->cfg.g, (const double *)ctx->d_colc, (const double *)ctx->d_lev, d_errs);
+		TB_KERNEL_CHECK(ctx);
+		TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+		std::vector<double> errs((size_t)nb * nt);
+		TB_CHECK(ctx, cudaMemcpy(errs.data(), d_errs, errs.size() * sizeof(double), cudaMemcpyDeviceToHost));
+		double worst = 0.0;
+		for (size_t q = 0; q < errs.size(); q++) worst = std::max(worst, errs[q]);
+		ctx->fast_metric_error = worst;
+		if (!(worst <= 1.0e-13)) {
+			char buf[160];
+			snprintf(buf, 160, "column constants deviate from the uploaded metric by %.3e", worst);
+			ctx->fast_reason = buf;
+			return 0;
+		}
+	}
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->fast_state = 1;
+	ctx->fast_reason = "";
+	return 0;
+}
+
+// 1: fast path in use; 0: generic kernels (tb200_fast_path_reason tells why)
+extern "C" int tb200_fast_path(tb200_ctx * ctx) {
+	if (fast_prepare(ctx)) return -1;
+	return (ctx->fast_state == 1) ? 1 : 0;
+}
+
+extern "C" const char * tb200_fast_path_reason(tb200_ctx * ctx) {
+	return ctx->fast_reason.c_str();
+}
+
+extern "C" double tb200_fast_path_metric_error(tb200_ctx * ctx) {
+	return ctx->fast_metric_error;
+}
+
 ///////////////////////////////////////////////////////////////////////////////
 // Dynamics
 
@@ -798,6 +936,42 @@ static int nh_launch(
 ) {
 	const DevLayout & lay = ctx->lay;
 	if (check_ops(ctx)) return 1;
+	if (fast_prepare(ctx)) return 1;
+	if (ctx->fast_state == 1 && lay.ntr == 0) {
+		FastArgs fa;
+		fa.colc = ctx->d_colc;
+		fa.lev = ctx->d_lev;
+		fa.inv_da = ctx->d_inv_da;
+		fa.inv_db = ctx->d_inv_db;
+		fa.dt = dt;
+		fa.xz = ctx->cfg.cartesian_xz;
+		const size_t smem = tb_fast_stage_smem_doubles(lay.nlev, do_h) * sizeof(double);
+		const dim3 grid((unsigned)lay.nelem), block(TBF_THREADS);
+#ifndef TB200_EMU
+#define TB_FAST_ATTR(kfn) TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#else
+#define TB_FAST_ATTR(kfn)
+#endif
+		if (do_h && do_v) {
+			auto kfn = k_nh_stage_fast<true, true>;
+			TB_FAST_ATTR(kfn);
+			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa, sb,
+				(const double *)ctx->inst[in], ctx->inst[out]);
+		} else if (do_h) {
+			auto kfn = k_nh_stage_fast<true, false>;
+			TB_FAST_ATTR(kfn);
+			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa, sb,
+				(const double *)ctx->inst[in], ctx->inst[out]);
+		} else {
+			auto kfn = k_nh_stage_fast<false, true>;
+			TB_FAST_ATTR(kfn);
+			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa, sb,
+				(const double *)ctx->inst[in], ctx->inst[out]);
+		}
+#undef TB_FAST_ATTR
+		TB_KERNEL_CHECK(ctx);
+		return 0;
+	}
 	NHArgs a;
 	a.dt = dt;
 	a.xz = ctx->cfg.cartesian_xz;

@@ -95,6 +95,15 @@ struct tb200_ctx {
 
 	int64_t launches;
 
+	// fast path (tb200_fast.cuh): 0 = not examined, 1 = enabled, -1 = unavailable
+	int fast_state;
+	std::string fast_reason;          // why the fast path is unavailable
+	double fast_metric_error;         // deviation from the uploaded 3-D metric
+	double * d_colc;                  // [e][TBF_NC][NN] column constants
+	double * d_lev;                   // [L+1][TBF_LW] operator windows
+	std::vector<double> reta_n_h, reta_e_h;
+	bool geometry3d_uploaded;
+
 	tb200_ctx() :
 		stream(0), committed(false), connectivity_built(false),
 		d_stage(0), stage_doubles(0), d_rowmap(0),
@@ -105,7 +114,9 @@ struct tb200_ctx {
 		d_seam_mats(0), rank(0), nranks(1), exch_fn(0), exch_user(0),
 		nsend_total(0), nrecv_total(0), d_send_nodes(0), d_sendbuf(0),
 		d_recvbuf(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0),
-		d_ws(0), ws_cols(0), d_info(0), offd(4), launches(0)
+		d_ws(0), ws_cols(0), d_info(0), offd(4), launches(0),
+		fast_state(0), fast_metric_error(0.0), d_colc(0), d_lev(0),
+		geometry3d_uploaded(false)
 	{
 		for (int i = 0; i < 7; i++) g2d[i] = 0;
 		for (int i = 0; i < 13; i++) { g3n[i] = 0; g3e[i] = 0; }

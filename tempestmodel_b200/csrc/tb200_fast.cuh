@@ -1,0 +1,689 @@
+// Fast path of the explicit stage (FP64, sm_100a): vertical order 1,
+// terrain-following metric with a level-independent layer depth.
+//
+// Same mathematics as k_nh_explicit (tb200_kernels.cuh), reorganised around the
+// B200's two scarce resources for this stencil - FP64 issue slots and HBM
+// bytes:
+//
+//  * one block per element, one thread per (level k, element row i); the
+//    thread owns the four nodes (i, j = 0..3) of its row, i.e. 32 contiguous
+//    bytes of every 128-byte state row -> 16-byte vector loads / stores, whole
+//    element streamed as one contiguous 19 kB block;
+//  * beta-derivatives (sums over j) are register-only; alpha-derivatives (sums
+//    over i) read the (k) tile of a field from shared memory as 16-byte
+//    vectors - five tiles + the V column, one __syncwarp, no block barrier;
+//  * the vertical operators (interpolation / differentiation / penalty, taken
+//    from the host tables, never hard-coded) are pre-windowed on the host to
+//    dense 3-coefficient rows around k and loaded once per thread;
+//  * the 3-D metric arrays of the reference (13 doubles per node) are replaced
+//    by 13 constants per column (TBF_*), exact for every terrain-following
+//    metric of the form  dR/dalpha = s(eta) dzs/dalpha, dR/dxi = ztop - zs
+//    (GridPatchCSGLL.cpp:344-553; GridPatchCartesianGLL.cpp:262-330 with flat
+//    terrain).  The host verifies them against the uploaded reference arrays
+//    before enabling this path (tb200_api.cu: fast_prepare).
+//  * Grid::CopyData / LinearCombineData of the stage base is formed on the fly.
+//
+// Summation order inside every np-sum and column operator follows the
+// reference; products are contracted to FMA by nvcc.  Results agree with the
+// reference to rounding (tests/test_parity.py, 1e-12 of the tendency).
+#ifndef TB200_FAST_CUH
+#define TB200_FAST_CUH
+
+#include "tb200_platform.h"
+#include "tb200_device.h"
+#include "tb200_kernels.cuh"
+
+// ---- per-column constants: colc[(e * TBF_NC + q) * 16 + n] ---------------------
+#define TBF_A0 0       // ContraMetric2DA[0]
+#define TBF_A1 1       // ContraMetric2DA[1] (= ContraMetric2DB[0])
+#define TBF_B1 2       // ContraMetric2DB[1]
+#define TBF_JAC 3      // Jacobian = dxr * Jacobian2D (levels and interfaces)
+#define TBF_INVJAC 4
+#define TBF_FJ 5       // CoriolisF * Jacobian2D
+#define TBF_A2 6       // ContraMetricA[2] = s * A2, A2 = -(a0 dazs + a1 dbzs) / dxr
+#define TBF_B2 7       // ContraMetricB[2] = s * B2
+#define TBF_X0 8       // ContraMetricXi[2] = X0 + s^2 X2, X0 = 1 / dxr^2
+#define TBF_X2 9       //                     X2 = -(A2 dazs + B2 dbzs) / dxr
+#define TBF_GDA 10     // g * dzs/dalpha   (g * DerivR[0] = s * GDA)
+#define TBF_GDB 11
+#define TBF_DXR 12     // DerivR[2]
+#define TBF_NC 13
+
+// ---- per-level operator windows: lev[k * TBF_LW + q], k = 0..L ------------------
+#define TBF_CW 0       // [2] InterpREdgeToNode row k on W[k], W[k+1]
+#define TBF_CD 2       // [3] DiffNodeToNode row k on levels k-1, k, k+1
+#define TBF_CILO 5     // [3] InterpNodeToREdge row k   on levels k-1, k, k+1
+#define TBF_CIHI 8     // [3] InterpNodeToREdge row k+1 on levels k-1, k, k+1
+#define TBF_CPL 11     // [3] penalty (left)  row k on levels k-1, k, k+1
+#define TBF_CPR 14     // [3] penalty (right) row k
+#define TBF_SN 17      // s on level k
+#define TBF_SE 18      // s on interface k
+#define TBF_SE1 19     // s on interface k+1
+#define TBF_CB0 20     // [3] InterpNodeToREdge row 0 on levels 0, 1, 2 (row k = 0 only)
+// column solve (tb200_column_fast.cuh)
+#define TBF_DNE 23     // [2] DiffNodeToREdge row k on levels k-1, k
+#define TBF_DEN 25     // [2] DiffREdgeToNode row k on interfaces k, k+1
+#define TBF_DDE 27     // [3] DiffDiffREdgeToREdge row k on interfaces k-1, k, k+1
+#define TBF_IEN1 30    // [2] InterpREdgeToNode row k-1 on W[k-1], W[k]
+#define TBF_LW 32
+
+#define TBF_RS 18      // shared-memory row stride (doubles): 16 nodes + 2 pad
+
+struct FastArgs {
+	const double * colc;
+	const double * lev;
+	const double * inv_da;
+	const double * inv_db;
+	double dt;
+	int xz;
+};
+
+// 4 consecutive doubles <-> registers (two 16-byte accesses)
+__device__ __forceinline__ void tb_ld4(const double * p, double (&v)[4]) {
+#ifdef TB200_EMU
+	v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+#else
+	const double2 a = *reinterpret_cast<const double2 *>(p);
+	const double2 b = *reinterpret_cast<const double2 *>(p + 2);
+	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+#endif
+}
+
+__device__ __forceinline__ void tb_st4(double * p, const double (&v)[4]) {
+#ifdef TB200_EMU
+	p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; p[3] = v[3];
+#else
+	*reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+	*reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
+#endif
+}
+
+__device__ __forceinline__ void tb_ld2(const double * p, double (&v)[2]) {
+#ifdef TB200_EMU
+	v[0] = p[0]; v[1] = p[1];
+#else
+	const double2 a = *reinterpret_cast<const double2 *>(p);
+	v[0] = a.x; v[1] = a.y;
+#endif
+}
+
+__device__ __forceinline__ void tb_st2(double * p, const double (&v)[2]) {
+#ifdef TB200_EMU
+	p[0] = v[0]; p[1] = v[1];
+#else
+	*reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+#endif
+}
+
+// Stage base of 2 consecutive values (same operation order as k_lincomb)
+__device__ __forceinline__ void tb_stage_base2(
+	const StageBase & sb, const double * out, size_t off, double (&v)[2]
+) {
+	if (sb.use_out) {
+		tb_ld2(out + off, v);
+		return;
+	}
+	if (sb.scale_dst) {
+		tb_ld2(out + off, v);
+		v[0] = v[0] * sb.cdst;
+		v[1] = v[1] * sb.cdst;
+	} else {
+		v[0] = 0.0;
+		v[1] = 0.0;
+	}
+	for (int m = 0; m < sb.nsrc; m++) {
+		double s[2];
+		tb_ld2(sb.src[m] + off, s);
+		const double c = sb.coeff[m];
+		v[0] += s[0] * c;
+		v[1] += s[1] * c;
+	}
+}
+
+// Stage base of 4 consecutive values (same operation order as k_lincomb)
+__device__ __forceinline__ void tb_stage_base4(
+	const StageBase & sb, const double * out, size_t off, double (&v)[4]
+) {
+	if (sb.use_out) {
+		tb_ld4(out + off, v);
+		return;
+	}
+	if (sb.scale_dst) {
+		tb_ld4(out + off, v);
+#pragma unroll
+		for (int j = 0; j < 4; j++) v[j] = v[j] * sb.cdst;
+	} else {
+#pragma unroll
+		for (int j = 0; j < 4; j++) v[j] = 0.0;
+	}
+	for (int m = 0; m < sb.nsrc; m++) {
+		double s[4];
+		tb_ld4(sb.src[m] + off, s);
+		const double c = sb.coeff[m];
+#pragma unroll
+		for (int j = 0; j < 4; j++) v[j] += s[j] * c;
+	}
+}
+
+__host__ __device__ inline size_t tb_fast_stage_smem_doubles(int L, bool do_h) {
+	// sU, sV [L], sW [L+1]; tiles Wn, KE, EX, FaR, FaP, ZX, AU, AV [L]; Un, Vn [3]
+	const size_t rows = do_h ? (size_t)(3 * L + 1 + 8 * L + 6) : (size_t)(3 * L + 1);
+	return rows * TBF_RS;
+}
+
+// alpha-derivative of a field whose level-k tile sits in shared memory, for
+// the node pair j = 2 jh, 2 jh + 1:   out[q] = sum_s tile[s][2 jh + q] * c[s]
+__device__ __forceinline__ void tb_cross_sum2(
+	const double * tile, const double (&c)[4], double (&o)[2]
+) {
+	double r0[2], r1[2], r2[2], r3[2];
+	tb_ld2(tile, r0);
+	tb_ld2(tile + 4, r1);
+	tb_ld2(tile + 8, r2);
+	tb_ld2(tile + 12, r3);
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		double a = 0.0;
+		a += r0[q] * c[0];
+		a += r1[q] * c[1];
+		a += r2[q] * c[2];
+		a += r3[q] * c[3];
+		o[q] = a;
+	}
+}
+
+#define TBF_THREADS 128
+#ifndef TBF_MINBLOCKS
+#define TBF_MINBLOCKS 3
+#endif
+#define TBF_KB (TBF_THREADS / 4)     // levels per pass
+
+template <bool DO_H, bool DO_V>
+__global__ void __launch_bounds__(TBF_THREADS, TBF_MINBLOCKS)
+k_nh_stage_fast(
+	DevLayout lay, DevTables t, DevPhys ph, FastArgs fa, StageBase sb,
+	const double * __restrict__ in, double * out
+) {
+	const int NP = 4, NN = 16, RS = TBF_RS;
+	const int L = lay.nlev;
+	const double dt = fa.dt;
+
+	TB_DYN_SMEM(double, sm);
+	double * sU = sm;                       // [L][RS]   covariant u_alpha
+	double * sV = sU + (size_t)L * RS;      // [L][RS]
+	double * sW = sV + (size_t)L * RS;      // [L+1][RS] covariant w on interfaces
+	double * tWn = sW + (size_t)(L + 1) * RS;
+	double * tKE = tWn + (size_t)L * RS;
+	double * tEX = tKE + (size_t)L * RS;
+	double * tFaR = tEX + (size_t)L * RS;
+	double * tFaP = tFaR + (size_t)L * RS;
+	double * tZX = tFaP + (size_t)L * RS;
+	double * tAU = tZX + (size_t)L * RS;    // vertical-explicit increments of U, V
+	double * tAV = tAU + (size_t)L * RS;
+	double * sUn = tAV + (size_t)L * RS;    // [3][RS] U after the horizontal update, levels 0..2
+	double * sVn = sUn + 3 * RS;
+
+	const long long e = blockIdx.x;
+	const int kq = threadIdx.x >> 2;
+	const int i = threadIdx.x & 3;
+
+	const size_t ebase = (size_t)e * lay.nrows * NN;
+	const size_t offU = ebase + (size_t)lay.rowoff[0] * NN;
+	const size_t offV = ebase + (size_t)lay.rowoff[1] * NN;
+	const size_t offP = ebase + (size_t)lay.rowoff[2] * NN;
+	const size_t offW = ebase + (size_t)lay.rowoff[3] * NN;
+	const size_t offR = ebase + (size_t)lay.rowoff[4] * NN;
+
+	// ---- stage the U, V (levels) and W (interfaces) columns of the element ---------
+	for (int k = kq; k <= L; k += TBF_KB) {
+		double x[4];
+		if (k < L) {
+			tb_ld4(in + offU + (size_t)k * NN + i * NP, x);
+			tb_st4(sU + k * RS + i * NP, x);
+			tb_ld4(in + offV + (size_t)k * NN + i * NP, x);
+			tb_st4(sV + k * RS + i * NP, x);
+		}
+		tb_ld4(in + offW + (size_t)k * NN + i * NP, x);
+		tb_st4(sW + k * RS + i * NP, x);
+	}
+	double p[4], r[4];
+	if (DO_H) {
+		const int k = (kq < L) ? kq : (L - 1);
+		tb_ld4(in + offP + (size_t)k * NN + i * NP, p);
+		tb_ld4(in + offR + (size_t)k * NN + i * NP, r);
+	}
+
+	// constants of my four columns
+	const double * cc = fa.colc + (size_t)e * TBF_NC * NN + i * NP;
+	const double dInvDA = fa.inv_da[e];
+	const double dInvDB = fa.inv_db[e];
+
+	__syncthreads();
+
+	for (int k0 = 0; k0 < L; k0 += TBF_KB) {
+		const int k = k0 + kq;
+		const bool active = (k < L);
+		const int kc = active ? k : (L - 1);
+		const size_t o4 = (size_t)kc * NN + i * NP;    // my 4 nodes inside a component
+		const double * lv = fa.lev + (size_t)kc * TBF_LW;
+		const double sn = lv[TBF_SN];
+		double cA2[4], cB2[4], cX0[4], cX2[4];
+		tb_ld4(cc + TBF_A2 * NN, cA2);
+		tb_ld4(cc + TBF_B2 * NN, cB2);
+		tb_ld4(cc + TBF_X0 * NN, cX0);
+		tb_ld4(cc + TBF_X2 * NN, cX2);
+
+		const int km = (kc > 0) ? kc - 1 : 0;
+		const int kp = (kc < L - 1) ? kc + 1 : L - 1;
+		double u[4], v[4], w0[4], um[4], up[4], vm[4], vp[4], wp[4];
+		tb_ld4(sU + kc * RS + i * NP, u);
+		tb_ld4(sV + kc * RS + i * NP, v);
+		tb_ld4(sW + kc * RS + i * NP, w0);
+		tb_ld4(sU + km * RS + i * NP, um);
+		tb_ld4(sU + kp * RS + i * NP, up);
+		tb_ld4(sV + km * RS + i * NP, vm);
+		tb_ld4(sV + kp * RS + i * NP, vp);
+		tb_ld4(sW + (kc + 1) * RS + i * NP, wp);
+		if (DO_H && k0 > 0) {
+			tb_ld4(in + offP + o4, p);
+			tb_ld4(in + offR + o4, r);
+		}
+
+		// ---- vertical explicit part: upwind penalty on U and V ----------------------
+		// (VerticalDynamicsFEM.cpp:816-828, 998-1023; LinearColumnOperatorFEM.cpp:1863-1887)
+		double addU[4], addV[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) { addU[j] = 0.0; addV[j] = 0.0; }
+		if (DO_V) {
+			const double se0 = lv[TBF_SE], se1 = lv[TBF_SE1];
+			const bool hi = (kc <= L - 2);      // interface k+1 is interior
+			const bool lo = (kc >= 1);          // interface k is interior
+			const double h0 = lv[TBF_CIHI + 0], h1 = lv[TBF_CIHI + 1], h2 = lv[TBF_CIHI + 2];
+			const double l0 = lv[TBF_CILO + 0], l1 = lv[TBF_CILO + 1], l2 = lv[TBF_CILO + 2];
+			const double pl0 = lv[TBF_CPL + 0], pl1 = lv[TBF_CPL + 1], pl2 = lv[TBF_CPL + 2];
+			const double pr0 = lv[TBF_CPR + 0], pr1 = lv[TBF_CPR + 1], pr2 = lv[TBF_CPR + 2];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (hi) {
+					double ue = 0.0, ve = 0.0;
+					ue += h0 * um[j]; ue += h1 * u[j]; ue += h2 * up[j];
+					ve += h0 * vm[j]; ve += h1 * v[j]; ve += h2 * vp[j];
+					const double c0 = se1 * cA2[j], c1 = se1 * cB2[j];
+					const double c2 = cX0[j] + (se1 * se1) * cX2[j];
+					const double xd = c0 * ue + c1 * ve + c2 * wp[j];
+					const double wgt = dt * fabs(xd);
+					double pu = 0.0, pv = 0.0;
+					pu += pl0 * um[j]; pu += pl1 * u[j]; pu += pl2 * up[j];
+					pv += pl0 * vm[j]; pv += pl1 * v[j]; pv += pl2 * vp[j];
+					addU[j] += pu * wgt;
+					addV[j] += pv * wgt;
+				}
+				if (lo) {
+					double ue = 0.0, ve = 0.0;
+					ue += l0 * um[j]; ue += l1 * u[j]; ue += l2 * up[j];
+					ve += l0 * vm[j]; ve += l1 * v[j]; ve += l2 * vp[j];
+					const double c0 = se0 * cA2[j], c1 = se0 * cB2[j];
+					const double c2 = cX0[j] + (se0 * se0) * cX2[j];
+					const double xd = c0 * ue + c1 * ve + c2 * w0[j];
+					const double wgt = dt * fabs(xd);
+					double pu = 0.0, pv = 0.0;
+					pu += pr0 * um[j]; pu += pr1 * u[j]; pu += pr2 * up[j];
+					pv += pr0 * vm[j]; pv += pr1 * v[j]; pv += pr2 * vp[j];
+					addU[j] += pu * wgt;
+					addV[j] += pv * wgt;
+				}
+			}
+		}
+
+		if (!DO_H) {
+			// VerticalDynamicsFEM::StepExplicit alone
+			if (active) {
+				double bu[4], bv[4];
+				tb_stage_base4(sb, out, offU + o4, bu);
+				tb_stage_base4(sb, out, offV + o4, bv);
+#pragma unroll
+				for (int j = 0; j < 4; j++) { bu[j] += addU[j]; bv[j] += addV[j]; }
+				tb_st4(out + offU + o4, bu);
+				tb_st4(out + offV + o4, bv);
+				if (!sb.use_out) {
+					double b[4];
+					tb_stage_base4(sb, out, offP + o4, b); tb_st4(out + offP + o4, b);
+					tb_stage_base4(sb, out, offR + o4, b); tb_st4(out + offR + o4, b);
+					tb_stage_base4(sb, out, offW + o4, b); tb_st4(out + offW + o4, b);
+					if (k == L - 1) {
+						const size_t oL = offW + (size_t)L * NN + i * NP;
+						tb_stage_base4(sb, out, oL, b); tb_st4(out + oL, b);
+					}
+				}
+			}
+			continue;
+		}
+
+		// ---- horizontal part (HorizontalDynamicsFEM.cpp:876-1660) -------------------
+		double cA0[4], cA1[4], cB1[4], cJ[4];
+		tb_ld4(cc + TBF_A0 * NN, cA0);
+		tb_ld4(cc + TBF_A1 * NN, cA1);
+		tb_ld4(cc + TBF_B1 * NN, cB1);
+		tb_ld4(cc + TBF_JAC * NN, cJ);
+
+		double wn[4], conUa[4], conUb[4], conUx[4], ke[4], ex[4], fbR[4], fbP[4];
+		double dxUa[4], dxUb[4], theta[4];
+		{
+			double faR[4], faP[4];
+			const double sn2 = sn * sn;
+			const double cw0 = lv[TBF_CW + 0], cw1 = lv[TBF_CW + 1];
+			const double d0 = lv[TBF_CD + 0], d1 = lv[TBF_CD + 1], d2 = lv[TBF_CD + 2];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				// InterpolateREdgeToNode(W) (:817-819)
+				double x = 0.0;
+				x += cw0 * w0[j];
+				x += cw1 * wp[j];
+				wn[j] = x;
+				const double m2 = sn * cA2[j], m4 = sn * cB2[j];
+				const double m5 = cX0[j] + sn2 * cX2[j];
+				// Contravariant velocities (:916-929)
+				conUa[j] = cA0[j] * u[j] + cA1[j] * v[j] + m2 * x;
+				conUb[j] = cA1[j] * u[j] + cB1[j] * v[j] + m4 * x;
+				conUx[j] = m2 * u[j] + m4 * v[j] + m5 * x;
+				// Specific kinetic energy (:932-935)
+				ke[j] = 0.5 * (conUa[j] * u[j] + conUb[j] * v[j] + conUx[j] * x);
+				// Exner pressure (:949-951, PhysicalConstants.h:397-399)
+				ex[j] = ph.cp * exp(ph.exner_c1 * log(ph.exner_c2 * p[j]));
+				// Fluxes (:1050-1077)
+				const double fa_ = cJ[j] * conUa[j];
+				const double fb_ = cJ[j] * conUb[j];
+				faR[j] = fa_ * r[j];
+				fbR[j] = fb_ * r[j];
+				faP[j] = fa_ * p[j];
+				fbP[j] = fb_ * p[j];
+				theta[j] = p[j] / r[j];
+				// DifferentiateNodeToNode of u_alpha, u_beta (:974-1001)
+				double d = 0.0;
+				d += d0 * um[j]; d += d1 * u[j]; d += d2 * up[j];
+				dxUa[j] = d;
+				d = 0.0;
+				d += d0 * vm[j]; d += d1 * v[j]; d += d2 * vp[j];
+				dxUb[j] = d;
+			}
+			if (active) {
+				tb_st4(tWn + k * RS + i * NP, wn);
+				tb_st4(tKE + k * RS + i * NP, ke);
+				tb_st4(tEX + k * RS + i * NP, ex);
+				tb_st4(tFaR + k * RS + i * NP, faR);
+				tb_st4(tFaP + k * RS + i * NP, faP);
+			}
+		}
+		__syncwarp();
+
+		if (DO_V && active) {
+			tb_st4(tAU + k * RS + i * NP, addU);
+			tb_st4(tAV + k * RS + i * NP, addV);
+		}
+
+		// alpha-derivatives: sums over s of tile[s][j] (rows held by the other
+		// three threads of the level); beta-derivatives: sums over my own row.
+		// Two nodes at a time to bound the live registers.
+		double dxI[4], stI[4];
+#pragma unroll
+		for (int s = 0; s < 4; s++) {
+			dxI[s] = t.dx[s * NP + i];
+			stI[s] = t.st[i * NP + s];
+		}
+#pragma unroll
+		for (int jh = 0; jh < 2; jh++) {
+			double dCovDaUb[2], dCovDaUx[2], dDaP[2], dDaKE[2], dDaRhoFluxA[2], dDaPressureFluxA[2];
+			tb_cross_sum2(sV + kc * RS + 2 * jh, dxI, dCovDaUb);
+			tb_cross_sum2(tWn + kc * RS + 2 * jh, dxI, dCovDaUx);
+			tb_cross_sum2(tEX + kc * RS + 2 * jh, dxI, dDaP);
+			tb_cross_sum2(tKE + kc * RS + 2 * jh, dxI, dDaKE);
+			tb_cross_sum2(tFaR + kc * RS + 2 * jh, stI, dDaRhoFluxA);
+			tb_cross_sum2(tFaP + kc * RS + 2 * jh, stI, dDaPressureFluxA);
+
+			const size_t o2 = o4 + 2 * jh;
+			double cIJ[2], cFJ[2], cGA[2], cGB[2];
+			tb_ld2(cc + TBF_INVJAC * NN + 2 * jh, cIJ);
+			tb_ld2(cc + TBF_FJ * NN + 2 * jh, cFJ);
+			tb_ld2(cc + TBF_GDA * NN + 2 * jh, cGA);
+			tb_ld2(cc + TBF_GDB * NN + 2 * jh, cGB);
+			double bU[2], bV[2], bP[2], bR[2];
+			tb_stage_base2(sb, out, offU + o2, bU);
+			tb_stage_base2(sb, out, offV + o2, bV);
+			tb_stage_base2(sb, out, offP + o2, bP);
+			tb_stage_base2(sb, out, offR + o2, bR);
+
+			double zx[2];
+#pragma unroll
+			for (int q = 0; q < 2; q++) {
+				const int j = 2 * jh + q;
+				double dCovDbUa = 0.0, dCovDbUx = 0.0, dDbP = 0.0, dDbKE = 0.0;
+				double dDbRhoFluxB = 0.0, dDbPressureFluxB = 0.0;
+#pragma unroll
+				for (int s = 0; s < 4; s++) {
+					dCovDbUa += u[s] * t.dx[s * NP + j];
+					dCovDbUx += wn[s] * t.dx[s * NP + j];
+					dDbRhoFluxB -= fbR[s] * t.st[j * NP + s];
+					dDbPressureFluxB -= fbP[s] * t.st[j * NP + s];
+					dDbP += ex[s] * t.dx[s * NP + j];
+					dDbKE += ke[s] * t.dx[s * NP + j];
+				}
+				const double aDaUb = dCovDaUb[q] * dInvDA;
+				const double aDaUx = dCovDaUx[q] * dInvDA;
+				const double aDbUa = dCovDbUa * dInvDB;
+				const double aDbUx = dCovDbUx * dInvDB;
+
+				// U cross relative vorticity (:966-1039)
+				const double dJZetaA = (aDbUx - dxUb[j]);
+				const double dJZetaB = (dxUa[j] - aDaUx);
+				const double dJZetaX = (aDaUb - aDbUa);
+				const double dUCrossZetaA = conUb[j] * dJZetaX - conUx[j] * dJZetaB;
+				const double dUCrossZetaB = conUx[j] * dJZetaA - conUa[j] * dJZetaX;
+				zx[q] = -conUa[j] * aDaUx - conUb[j] * aDbUx;
+
+				// flux divergences; the alpha sums were accumulated with a plus
+				// sign (:1222-1301 subtract term by term)
+				const double aDaRho = -(dDaRhoFluxA[q] * dInvDA);
+				const double aDbRho = dDbRhoFluxB * dInvDB;
+				const double aDaPre = -(dDaPressureFluxA[q] * dInvDA);
+				const double aDbPre = dDbPressureFluxB * dInvDB;
+				const double aDaP = dDaP[q] * dInvDA;
+				const double aDbP = dDbP * dInvDB;
+				const double aDaKE = dDaKE[q] * dInvDA;
+				const double aDbKE = dDbKE * dInvDB;
+
+				double dLocalUpdateUa = 0.0, dLocalUpdateUb = 0.0;
+				dLocalUpdateUa += dUCrossZetaA;
+				dLocalUpdateUb += dUCrossZetaB;
+				// Coriolis (:1330-1338)
+				dLocalUpdateUa += cFJ[q] * conUb[j];
+				dLocalUpdateUb -= cFJ[q] * conUa[j];
+				// Pressure gradient force, RHOTHETA_PI (:1348-1353): theta * grad Pi
+				const double dPGFa = aDaP * theta[j];
+				const double dPGFb = aDbP * theta[j];
+				// Gravity (:1363-1364): g * DerivR
+				const double dDaPhi = sn * cGA[q];
+				const double dDbPhi = sn * cGB[q];
+				dLocalUpdateUa -= dPGFa + aDaKE + dDaPhi;
+				dLocalUpdateUb -= dPGFb + aDbKE + dDbPhi;
+
+				bU[q] = bU[q] + dt * dLocalUpdateUa;
+				if (!fa.xz) bV[q] += dt * dLocalUpdateUb;
+				// Density and rho-theta (:1399-1421)
+				bR[q] = bR[q] - dt * cIJ[q] * (aDaRho + aDbRho);
+				bP[q] = bP[q] - dt * cIJ[q] * (aDaPre + aDbPre);
+			}
+			if (active) {
+				tb_st2(out + offR + o2, bR);
+				tb_st2(out + offP + o2, bP);
+				tb_st2(tZX + k * RS + i * NP + 2 * jh, zx);
+				if (k < 3) {
+					tb_st2(sUn + k * RS + i * NP + 2 * jh, bU);
+					tb_st2(sVn + k * RS + i * NP + 2 * jh, bV);
+				}
+				if (DO_V) {
+					double au[2], av[2];
+					tb_ld2(tAU + k * RS + i * NP + 2 * jh, au);
+					tb_ld2(tAV + k * RS + i * NP + 2 * jh, av);
+					bU[0] += au[0]; bU[1] += au[1];
+					bV[0] += av[0]; bV[1] += av[1];
+				}
+				tb_st2(out + offU + o2, bU);
+				tb_st2(out + offV + o2, bV);
+			}
+		}
+	}
+	if (!DO_H) return;
+	__syncthreads();
+
+	// ---- vertical velocity on interfaces (:1612-1660) ------------------------------
+	for (int k = kq; k <= L; k += TBF_KB) {
+		const size_t o4 = (size_t)k * NN + i * NP;
+		const double * lv = fa.lev + (size_t)k * TBF_LW;
+		double bW[4];
+		if (k == 0) {
+			// bottom boundary: no flow through the surface, with the updated u
+			// extrapolated to the surface
+			const double se0 = lv[TBF_SE];
+			double a[4], b[4], c[4], a2[4], b2[4], c2[4];
+			double cA2[4], cB2[4], cX0[4], cX2[4];
+			tb_ld4(cc + TBF_A2 * NN, cA2);
+			tb_ld4(cc + TBF_B2 * NN, cB2);
+			tb_ld4(cc + TBF_X0 * NN, cX0);
+			tb_ld4(cc + TBF_X2 * NN, cX2);
+			const int l2 = (L > 2) ? 2 : (L - 1);
+			const int l1 = (L > 1) ? 1 : 0;
+			tb_ld4(sUn + i * NP, a); tb_ld4(sUn + l1 * RS + i * NP, b); tb_ld4(sUn + l2 * RS + i * NP, c);
+			tb_ld4(sVn + i * NP, a2); tb_ld4(sVn + l1 * RS + i * NP, b2); tb_ld4(sVn + l2 * RS + i * NP, c2);
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				double dU0 = 0.0, dV0 = 0.0;
+				dU0 += lv[TBF_CB0 + 0] * a[j]; dU0 += lv[TBF_CB0 + 1] * b[j]; dU0 += lv[TBF_CB0 + 2] * c[j];
+				dV0 += lv[TBF_CB0 + 0] * a2[j]; dV0 += lv[TBF_CB0 + 1] * b2[j]; dV0 += lv[TBF_CB0 + 2] * c2[j];
+				const double c0 = se0 * cA2[j], c1 = se0 * cB2[j];
+				const double cx2 = cX0[j] + (se0 * se0) * cX2[j];
+				bW[j] = -(c0 * dU0 + c1 * dV0) / cx2;
+			}
+			tb_st4(out + offW + o4, bW);
+		} else if (k < L) {
+			double zm[4], z0[4];
+			tb_ld4(tZX + (k - 1) * RS + i * NP, zm);
+			tb_ld4(tZX + k * RS + i * NP, z0);
+			tb_stage_base4(sb, out, offW + o4, bW);
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				double x = 0.0;
+				x += lv[TBF_CILO + 0] * zm[j];
+				x += lv[TBF_CILO + 1] * z0[j];
+				bW[j] += dt * x;
+			}
+			tb_st4(out + offW + o4, bW);
+		} else if (!sb.use_out) {
+			tb_stage_base4(sb, out, offW + o4, bW);
+			tb_st4(out + offW + o4, bW);
+		}
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Column constants from the 2-D metric, the topography derivatives and the
+// layer depth dxr = ztop - zs (GridPatchCSGLL.cpp:344-553).
+
+__global__ void k_fast_colc(
+	long long ncol, DevGeom g, double grav, double * colc
+) {
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= ncol) return;
+	const long long e = idx / 16;
+	const int n = (int)(idx % 16);
+	const double a0 = g.a0[idx], a1 = g.a1[idx], b1 = g.b1[idx];
+	const double j2d = g.j2d[idx];
+	const double dazs = (g.tda != 0) ? g.tda[idx] : 0.0;
+	const double dbzs = (g.tdb != 0) ? g.tdb[idx] : 0.0;
+	const double dxr = g.ztop - g.zs[idx];
+	const double jac = dxr * j2d;
+	const double A2 = -(a0 * dazs + a1 * dbzs) / dxr;
+	const double B2 = -(a1 * dazs + b1 * dbzs) / dxr;
+	double * c = colc + (size_t)e * TBF_NC * 16 + n;
+	c[TBF_A0 * 16] = a0;
+	c[TBF_A1 * 16] = a1;
+	c[TBF_B1 * 16] = b1;
+	c[TBF_JAC * 16] = jac;
+	c[TBF_INVJAC * 16] = 1.0 / jac;
+	c[TBF_FJ * 16] = g.f[idx] * j2d;
+	c[TBF_A2 * 16] = A2;
+	c[TBF_B2 * 16] = B2;
+	c[TBF_X0 * 16] = 1.0 / (dxr * dxr);
+	c[TBF_X2 * 16] = -(A2 * dazs + B2 * dbzs) / dxr;
+	c[TBF_GDA * 16] = grav * dazs;
+	c[TBF_GDB * 16] = grav * dbzs;
+	c[TBF_DXR * 16] = dxr;
+}
+
+// Largest deviation of the metric rebuilt from the column constants from the
+// uploaded reference arrays (relative to the natural scale of each entry):
+// one value per thread in errs[], the host takes the maximum.
+__device__ __forceinline__ void tb_fast_dev(double ref, double got, double scale, double & worst) {
+	const double d = fabs(ref - got);
+	const double s = fabs(scale);
+	const double rel = (s > 0.0) ? d / s : d;
+	if (!(rel == rel)) worst = 1.0e300;
+	else if (rel > worst) worst = rel;
+}
+
+__global__ void k_fast_verify(
+	DevLayout lay, DevGeom g, double grav, const double * colc, const double * lev,
+	double * errs
+) {
+	const int L = lay.nlev;
+	const long long ncol = lay.nelem * 16;
+	double worst = 0.0;
+	for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	     idx < ncol; idx += (long long)gridDim.x * blockDim.x
+	) {
+		const long long e = idx / 16;
+		const int n = (int)(idx % 16);
+		const double * c = colc + (size_t)e * TBF_NC * 16 + n;
+		const double a0 = c[TBF_A0 * 16], a1 = c[TBF_A1 * 16], b1 = c[TBF_B1 * 16];
+		const double mag = fabs(a0) + fabs(b1);      // scale of the horizontal metric
+		const double dxr = c[TBF_DXR * 16];
+		for (int k = 0; k <= L; k++) {
+			const size_t oe = ((size_t)e * (L + 1) + k) * 16 + n;
+			const double se = lev[(size_t)k * TBF_LW + TBF_SE];
+			const double x2e = c[TBF_X0 * 16] + se * se * c[TBF_X2 * 16];
+			const double mix = sqrt(mag * x2e);
+			tb_fast_dev(g.jace[oe], c[TBF_JAC * 16], g.jace[oe], worst);
+			tb_fast_dev(g.cae[0][oe], a0, mag, worst);
+			tb_fast_dev(g.cae[1][oe], a1, mag, worst);
+			tb_fast_dev(g.cbe[1][oe], b1, mag, worst);
+			tb_fast_dev(g.cae[2][oe], se * c[TBF_A2 * 16], mix, worst);
+			tb_fast_dev(g.cbe[2][oe], se * c[TBF_B2 * 16], mix, worst);
+			tb_fast_dev(g.cxe[0][oe], se * c[TBF_A2 * 16], mix, worst);
+			tb_fast_dev(g.cxe[1][oe], se * c[TBF_B2 * 16], mix, worst);
+			tb_fast_dev(g.cxe[2][oe], x2e, x2e, worst);
+			tb_fast_dev(g.dre[2][oe], dxr, dxr, worst);
+			if (k < L) {
+				const size_t on = ((size_t)e * L + k) * 16 + n;
+				const double s = lev[(size_t)k * TBF_LW + TBF_SN];
+				const double x2 = c[TBF_X0 * 16] + s * s * c[TBF_X2 * 16];
+				const double mixn = sqrt(mag * x2);
+				tb_fast_dev(g.jac[on], c[TBF_JAC * 16], g.jac[on], worst);
+				tb_fast_dev(g.ca[0][on], a0, mag, worst);
+				tb_fast_dev(g.ca[1][on], a1, mag, worst);
+				tb_fast_dev(g.cb[0][on], a1, mag, worst);
+				tb_fast_dev(g.cb[1][on], b1, mag, worst);
+				tb_fast_dev(g.ca[2][on], s * c[TBF_A2 * 16], mixn, worst);
+				tb_fast_dev(g.cb[2][on], s * c[TBF_B2 * 16], mixn, worst);
+				tb_fast_dev(g.cx[0][on], s * c[TBF_A2 * 16], mixn, worst);
+				tb_fast_dev(g.cx[1][on], s * c[TBF_B2 * 16], mixn, worst);
+				tb_fast_dev(g.cx[2][on], x2, x2, worst);
+				tb_fast_dev(g.dr[2][on], dxr, dxr, worst);
+				// g * DerivR[0,1]
+				tb_fast_dev(grav * g.dr[0][on], s * c[TBF_GDA * 16], grav * g.dr[0][on], worst);
+				tb_fast_dev(grav * g.dr[1][on], s * c[TBF_GDB * 16], grav * g.dr[1][on], worst);
+			}
+		}
+	}
+	errs[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = worst;
+}
+
+#endif

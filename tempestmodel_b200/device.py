@@ -132,6 +132,14 @@ class DeviceContext:
         a, b = _f64(reta_levels), _f64(reta_interfaces)
         self._ck(self.lib.tb200_set_vertical_coordinate(self._h, _ptr(a), _ptr(b)))
 
+    def fast_path(self):
+        """-> (enabled, reason, metric deviation) of the order-1 fast kernels."""
+        r = self.lib.tb200_fast_path(self._h)
+        if r < 0:
+            self._ck(1)
+        return (r == 1, self.lib.tb200_fast_path_reason(self._h).decode(),
+                self.lib.tb200_fast_path_metric_error(self._h))
+
     def upload_element_area(self, patch, area_node, area_redge):
         a, b = _f64(area_node), _f64(area_redge)
         self._ck(self.lib.tb200_upload_element_area(self._h, patch, _ptr(a), _ptr(b)))

@@ -207,19 +207,33 @@ def test_column_kernels_agree(library, monkeypatch):
                 assert np.abs(a - b).max() <= 1e-12 * np.abs(a).max()
 
 
-def test_on_the_fly_metric_equals_stored_metric(library):
-    """The terrain-following metric evaluated inside the kernels reproduces the
-    reference's stored 3-D arrays bit for bit: an explicit stage gives
-    identical results either way."""
+def test_fast_path_equals_general_kernels(library, monkeypatch):
+    """The order-1 fast kernels (column constants instead of the stored 3-D
+    metric, tb200_fast.cuh) and the general kernels reading the reference's
+    arrays give the same explicit stage to rounding; the column constants
+    reproduce the uploaded metric to 1e-13."""
     d = cases.load_case("jw_ne2_l6")
     res = []
-    for analytic in (False, True):
-        ctx = dumpctx.context_from_dump(d, library=library, analytic_metric=analytic)
+    for fast in (False, True):
+        if not fast:
+            monkeypatch.setenv("TB200_STAGE_KERNEL", "generic")
+        else:
+            monkeypatch.delenv("TB200_STAGE_KERNEL", raising=False)
+        ctx = dumpctx.context_from_dump(d, library=library, analytic_metric=True)
+        enabled, reason, dev = ctx.fast_path()
+        assert enabled == fast, reason
+        if fast:
+            assert dev <= 1e-13
         dumpctx.upload_tag(ctx, d, "ic")
         ctx.hv_step_explicit_combine([1.0, 0.0], 0, 1, 50.0)
         res.append(dumpctx.download(ctx, d, 1))
         assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
         ctx.close()
+    ic = {n: (dumpctx.interior(d["ic.patch%d.inst0.node" % n]),
+              dumpctx.interior(d["ic.patch%d.inst0.redge" % n])) for n in res[0]}
     for n in res[0]:
         for loc in (0, 1):
-            assert np.array_equal(res[0][n][loc], res[1][n][loc])
+            a, b = dumpctx.interior(res[0][n][loc]), dumpctx.interior(res[1][n][loc])
+            for c in ([0, 1, 2, 4] if loc == 0 else [3]):
+                tend = np.abs(a[c] - ic[n][loc][c]).max()
+                assert np.abs(a[c] - b[c]).max() <= 1e-12 * tend + 4e-16 * np.abs(a[c]).max()
