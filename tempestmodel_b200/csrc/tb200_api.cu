@@ -120,6 +120,17 @@ extern "C" int tb200_create(const tb200_config * cfg, tb200_ctx ** out) {
 	if (cfg->device >= 0) {
 		TB_CHECK(ctx, cudaSetDevice(cfg->device));
 	}
+	ctx->sm_count = 148;
+#ifndef TB200_EMU
+	{
+		int dev = 0, sms = 0;
+		if (cudaGetDevice(&dev) == cudaSuccess
+			&& cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess
+			&& sms > 0) {
+			ctx->sm_count = sms;
+		}
+	}
+#endif
 
 	DevLayout & lay = ctx->lay;
 	memset(&lay, 0, sizeof(lay));
@@ -834,8 +845,10 @@ static int fast_prepare(tb200_ctx * ctx) {
 		if (k < L) {
 			ok = ok && op_window(ctx->hops[1], k, k, 2, row + TBF_CW);
 			ok = ok && op_window(ctx->hops[2], k, k - 1, 3, row + TBF_CD);
-			ok = ok && op_window(ctx->hops[8], k, k - 1, 3, row + TBF_CPL);
-			ok = ok && op_window(ctx->hops[9], k, k - 1, 3, row + TBF_CPR);
+			// penalty rows: the left operator acts on all but the top level, the
+			// right one on all but the bottom level (VerticalDynamicsFEM.cpp:1009-1023)
+			if (k <= L - 2) ok = ok && op_window(ctx->hops[8], k, k - 1, 3, row + TBF_CPL);
+			if (k >= 1) ok = ok && op_window(ctx->hops[9], k, k - 1, 3, row + TBF_CPR);
 			ok = ok && op_window(ctx->hops[4], k, k, 2, row + TBF_DEN);
 			row[TBF_SN] = 1.0 - ctx->reta_n_h[k];
 		}
@@ -945,6 +958,40 @@ static int nh_launch(
 		fa.inv_db = ctx->d_inv_db;
 		fa.dt = dt;
 		fa.xz = ctx->cfg.cartesian_xz;
+		// stage base = one instance, coefficient 1: pipelined kernel
+		const char * nopipe = getenv("TB200_STAGE_KERNEL");
+		const bool simple = sb.use_out || (sb.nsrc == 1 && sb.coeff[0] == 1.0 && !sb.scale_dst);
+		if (do_h && simple && !(nopipe != 0 && strcmp(nopipe, "fast") == 0)) {
+			const double * base = sb.use_out ? ctx->inst[out] : sb.src[0];
+			const int alias = (base == ctx->inst[in]) ? 1 : 0;
+			const size_t smem = tb_pipe_smem_doubles(lay.nrows, lay.nlev, alias != 0) * sizeof(double);
+			if (smem <= 227 * 1024 - 1024) {
+				int per_sm = (int)((227 * 1024) / (smem + 1024));
+				if (per_sm > 4) per_sm = 4;
+				long long nb = (long long)ctx->sm_count * per_sm;
+				const char * fb = getenv("TB200_PIPE_BLOCKS");   // tests: force the multi-element loop
+				if (fb != 0 && atoi(fb) > 0) nb = atoi(fb);
+				if (nb > lay.nelem) nb = lay.nelem;
+				const dim3 grid((unsigned)nb), block(TBF_THREADS);
+				if (do_v) {
+					auto kfn = k_nh_stage_pipe<true>;
+#ifndef TB200_EMU
+					TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa,
+						(const double *)ctx->inst[in], base, ctx->inst[out], alias);
+				} else {
+					auto kfn = k_nh_stage_pipe<false>;
+#ifndef TB200_EMU
+					TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa,
+						(const double *)ctx->inst[in], base, ctx->inst[out], alias);
+				}
+				TB_KERNEL_CHECK(ctx);
+				return 0;
+			}
+		}
 		const size_t smem = tb_fast_stage_smem_doubles(lay.nlev, do_h) * sizeof(double);
 		const dim3 grid((unsigned)lay.nelem), block(TBF_THREADS);
 #ifndef TB200_EMU

@@ -94,6 +94,7 @@ struct tb200_ctx {
 	int offd;
 
 	int64_t launches;
+	int sm_count;
 
 	// fast path (tb200_fast.cuh): 0 = not examined, 1 = enabled, -1 = unavailable
 	int fast_state;

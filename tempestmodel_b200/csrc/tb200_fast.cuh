@@ -66,6 +66,7 @@
 #define TBF_DDE 27     // [3] DiffDiffREdgeToREdge row k on interfaces k-1, k, k+1
 #define TBF_IEN1 30    // [2] InterpREdgeToNode row k-1 on W[k-1], W[k]
 #define TBF_LW 32
+#define TBF_LWS 34     // row stride of the table in shared memory (bank spread)
 
 #define TBF_RS 18      // shared-memory row stride (doubles): 16 nodes + 2 pad
 
@@ -580,6 +581,473 @@ k_nh_stage_fast(
 		} else if (!sb.use_out) {
 			tb_stage_base4(sb, out, offW + o4, bW);
 			tb_st4(out + offW + o4, bW);
+		}
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Pipelined variant of the fused stage: persistent blocks, the element's input
+// state and stage base prefetched one element ahead with cp.async
+// (global -> shared, no register staging), so that HBM latency is off the
+// critical path and every SM keeps ~4 elements (2 blocks x 2 buffers) of loads
+// in flight.  Rows are 128 bytes (16 nodes); the 16-byte chunk c of row r is
+// stored at chunk c ^ (r & 1): the two levels that share a quarter-warp then
+// hit different bank groups for both access patterns of the kernel (own 32
+// bytes of a row; the whole row, broadcast within the level's four threads).
+// Stage base = one source instance with coefficient 1 (Grid::CopyData), which
+// is every stage of KGU35 but the last, every ARS stage's first half, and the
+// plugin calls on a pre-filled update instance; other combinations take
+// k_nh_stage_fast.
+
+#ifdef TB200_EMU
+__device__ __forceinline__ void tb_cp16(double * dst, const double * src) {
+	dst[0] = src[0]; dst[1] = src[1];
+}
+__device__ __forceinline__ void tb_cp_commit() {}
+template <int N> __device__ __forceinline__ void tb_cp_wait() {}
+#else
+__device__ __forceinline__ void tb_cp16(double * dst, const double * src) {
+	const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tb_cp_commit() {
+	asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void tb_cp_wait() {
+	asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory");
+}
+#endif
+
+// read-only global data (column constants): non-coherent loads
+__device__ __forceinline__ void tb_ld2g(const double * p, double (&v)[2]) {
+#ifdef TB200_EMU
+	v[0] = p[0]; v[1] = p[1];
+#else
+	const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+	v[0] = a.x; v[1] = a.y;
+#endif
+}
+__device__ __forceinline__ void tb_ld4g(const double * p, double (&v)[4]) {
+	double a[2], b[2];
+	tb_ld2g(p, a);
+	tb_ld2g(p + 2, b);
+	v[0] = a[0]; v[1] = a[1]; v[2] = b[0]; v[3] = b[1];
+}
+
+// my four nodes (i, 0..3) of a swizzled row
+__device__ __forceinline__ void tb_ld4s(const double * row, int par, int i, double (&v)[4]) {
+	double a[2], b[2];
+	tb_ld2(row + (((2 * i) ^ par) << 1), a);
+	tb_ld2(row + (((2 * i + 1) ^ par) << 1), b);
+	v[0] = a[0]; v[1] = a[1]; v[2] = b[0]; v[3] = b[1];
+}
+
+__device__ __forceinline__ void tb_st4s(double * row, int par, int i, const double (&v)[4]) {
+	const double a[2] = {v[0], v[1]};
+	const double b[2] = {v[2], v[3]};
+	tb_st2(row + (((2 * i) ^ par) << 1), a);
+	tb_st2(row + (((2 * i + 1) ^ par) << 1), b);
+}
+
+// out[q] = sum_s row[s][2 jh + q] * c[s] on a swizzled row
+__device__ __forceinline__ void tb_cross_sum2s(
+	const double * row, int par, int jh, const double (&c)[4], double (&o)[2]
+) {
+	double r0[2], r1[2], r2[2], r3[2];
+	tb_ld2(row + (((0 + jh) ^ par) << 1), r0);
+	tb_ld2(row + (((2 + jh) ^ par) << 1), r1);
+	tb_ld2(row + (((4 + jh) ^ par) << 1), r2);
+	tb_ld2(row + (((6 + jh) ^ par) << 1), r3);
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		double a = 0.0;
+		a += r0[q] * c[0];
+		a += r1[q] * c[1];
+		a += r2[q] * c[2];
+		a += r3[q] * c[3];
+		o[q] = a;
+	}
+}
+
+__host__ __device__ inline size_t tb_pipe_smem_doubles(int nrows, int L, bool alias) {
+	// in[2], base[2] (unless it aliases in), tiles Wn, KE, EX, FaR, FaP, ZX, Un/Vn[3],
+	// column constants [2], operator windows [L+1]
+	return (size_t)nrows * 16 * (alias ? 2 : 4) + (size_t)(6 * L + 6) * 16
+		+ 2 * TBF_NC * 16 + (size_t)(L + 1) * TBF_LWS;
+}
+
+#ifndef TBP_MINBLOCKS
+#define TBP_MINBLOCKS 2
+#endif
+
+template <bool DO_V>
+__global__ void __launch_bounds__(TBF_THREADS, TBP_MINBLOCKS)
+k_nh_stage_pipe(
+	DevLayout lay, DevTables t, DevPhys ph, FastArgs fa,
+	const double * __restrict__ in, const double * base, double * out, int alias
+) {
+	const int NP = 4, NN = 16;
+	const int L = lay.nlev;
+	const double dt = fa.dt;
+	const int nrows = lay.nrows;
+	const int rU = lay.rowoff[0], rV = lay.rowoff[1], rP = lay.rowoff[2];
+	const int rW = lay.rowoff[3], rR = lay.rowoff[4];
+
+	TB_DYN_SMEM(double, sm);
+	const size_t esz = (size_t)nrows * NN;
+	double * inb0 = sm;
+	double * bsb0 = alias ? sm : (sm + 2 * esz);
+	double * tWn = sm + (alias ? 2 : 4) * esz;
+	double * tKE = tWn + (size_t)L * NN;
+	double * tEX = tKE + (size_t)L * NN;
+	double * tFaR = tEX + (size_t)L * NN;
+	double * tFaP = tFaR + (size_t)L * NN;
+	double * tZX = tFaP + (size_t)L * NN;
+	double * sUn = tZX + (size_t)L * NN;     // [3][16] U after the horizontal update
+	double * sVn = sUn + 3 * NN;
+	double * scc0 = sVn + 3 * NN;            // [2][TBF_NC][16] column constants
+	double * slev = scc0 + 2 * TBF_NC * NN;  // [L+1][TBF_LWS] operator windows
+
+	const int tid = threadIdx.x;
+	const int kq = tid >> 2;
+	const int i = tid & 3;
+	const int nchunk = nrows * 8;
+
+	double dxI[4], stI[4];
+#pragma unroll
+	for (int s = 0; s < 4; s++) {
+		dxI[s] = t.dx[s * NP + i];
+		stI[s] = t.st[i * NP + s];
+	}
+
+	long long e = blockIdx.x;
+	if (e >= lay.nelem) return;
+	{
+		const size_t eb = (size_t)e * esz;
+		for (int q = tid; q < nchunk; q += TBF_THREADS) {
+			const int r = q >> 3, c = q & 7;
+			const int d = ((r << 3) | (c ^ (r & 1))) << 1;
+			tb_cp16(inb0 + d, in + eb + 2 * q);
+			if (!alias) tb_cp16(bsb0 + d, base + eb + 2 * q);
+		}
+		for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
+			tb_cp16(scc0 + 2 * q, fa.colc + (size_t)e * TBF_NC * NN + 2 * q);
+		}
+		for (int q = tid; q < (L + 1) * (TBF_LW / 2); q += TBF_THREADS) {
+			const int r = q / (TBF_LW / 2), c = q % (TBF_LW / 2);
+			tb_cp16(slev + (size_t)r * TBF_LWS + 2 * c, fa.lev + 2 * q);
+		}
+		tb_cp_commit();
+	}
+
+	for (int it = 0; e < lay.nelem; it++, e += gridDim.x) {
+		const int buf = it & 1;
+		const double * inb = inb0 + (size_t)buf * esz;
+		const double * bsb = bsb0 + (size_t)buf * esz;
+		// the data of this element (issued one iteration ago) has landed, and
+		// every thread is done with the previous element
+		tb_cp_wait<0>();
+		__syncthreads();
+		// prefetch the next element of this block into the other buffer
+		{
+			const long long en = e + gridDim.x;
+			if (en < lay.nelem) {
+				const size_t eb = (size_t)en * esz;
+				double * di = inb0 + (size_t)(buf ^ 1) * esz;
+				double * db = bsb0 + (size_t)(buf ^ 1) * esz;
+				for (int q = tid; q < nchunk; q += TBF_THREADS) {
+					const int r = q >> 3, c = q & 7;
+					const int d = ((r << 3) | (c ^ (r & 1))) << 1;
+					tb_cp16(di + d, in + eb + 2 * q);
+					if (!alias) tb_cp16(db + d, base + eb + 2 * q);
+				}
+				double * dc = scc0 + (size_t)(buf ^ 1) * TBF_NC * NN;
+				for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
+					tb_cp16(dc + 2 * q, fa.colc + (size_t)en * TBF_NC * NN + 2 * q);
+				}
+			}
+			tb_cp_commit();
+		}
+
+		const size_t ebase = (size_t)e * esz;
+		const double * cc = scc0 + (size_t)buf * TBF_NC * NN + i * NP;
+		const double dInvDA = __ldg(fa.inv_da + e);
+		const double dInvDB = __ldg(fa.inv_db + e);
+
+		for (int k0 = 0; k0 < L; k0 += TBF_KB) {
+			const int k = k0 + kq;
+			const bool active = (k < L);
+			const int kc = active ? k : (L - 1);
+			const int km = (kc > 0) ? kc - 1 : 0;
+			const int kp = (kc < L - 1) ? kc + 1 : L - 1;
+			const double * lv = slev + (size_t)kc * TBF_LWS;
+			const double sn = lv[TBF_SN];
+			const int tp = kc & 1;                         // tile parity
+
+			double cA2[4], cB2[4], cX0[4], cX2[4];
+			tb_ld4(cc + TBF_A2 * NN, cA2);
+			tb_ld4(cc + TBF_B2 * NN, cB2);
+			tb_ld4(cc + TBF_X0 * NN, cX0);
+			tb_ld4(cc + TBF_X2 * NN, cX2);
+
+			double u[4], wn[4], conUa[4], conUb[4], conUx[4], ke[4], ex[4], fbR[4], fbP[4];
+			double dxUa[4], dxUb[4], theta[4];
+			{
+				double v[4], w0[4], wp[4], p[4], r[4], um[4], up[4], vm[4], vp[4];
+				tb_ld4s(inb + (size_t)(rU + kc) * NN, (rU + kc) & 1, i, u);
+				tb_ld4s(inb + (size_t)(rV + kc) * NN, (rV + kc) & 1, i, v);
+				tb_ld4s(inb + (size_t)(rW + kc) * NN, (rW + kc) & 1, i, w0);
+				tb_ld4s(inb + (size_t)(rW + kc + 1) * NN, (rW + kc + 1) & 1, i, wp);
+				tb_ld4s(inb + (size_t)(rP + kc) * NN, (rP + kc) & 1, i, p);
+				tb_ld4s(inb + (size_t)(rR + kc) * NN, (rR + kc) & 1, i, r);
+				tb_ld4s(inb + (size_t)(rU + km) * NN, (rU + km) & 1, i, um);
+				tb_ld4s(inb + (size_t)(rU + kp) * NN, (rU + kp) & 1, i, up);
+				tb_ld4s(inb + (size_t)(rV + km) * NN, (rV + km) & 1, i, vm);
+				tb_ld4s(inb + (size_t)(rV + kp) * NN, (rV + kp) & 1, i, vp);
+				double cA0[4], cA1[4], cB1[4], cJ[4];
+				tb_ld4(cc + TBF_A0 * NN, cA0);
+				tb_ld4(cc + TBF_A1 * NN, cA1);
+				tb_ld4(cc + TBF_B1 * NN, cB1);
+				tb_ld4(cc + TBF_JAC * NN, cJ);
+				double faR[4], faP[4];
+				const double sn2 = sn * sn;
+				const double cw0 = lv[TBF_CW + 0], cw1 = lv[TBF_CW + 1];
+				const double d0 = lv[TBF_CD + 0], d1 = lv[TBF_CD + 1], d2 = lv[TBF_CD + 2];
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					// InterpolateREdgeToNode(W) (:817-819)
+					double x = 0.0;
+					x += cw0 * w0[j];
+					x += cw1 * wp[j];
+					wn[j] = x;
+					const double m2 = sn * cA2[j], m4 = sn * cB2[j];
+					const double m5 = cX0[j] + sn2 * cX2[j];
+					// Contravariant velocities (:916-929)
+					conUa[j] = cA0[j] * u[j] + cA1[j] * v[j] + m2 * x;
+					conUb[j] = cA1[j] * u[j] + cB1[j] * v[j] + m4 * x;
+					conUx[j] = m2 * u[j] + m4 * v[j] + m5 * x;
+					// Specific kinetic energy (:932-935)
+					ke[j] = 0.5 * (conUa[j] * u[j] + conUb[j] * v[j] + conUx[j] * x);
+					// Exner pressure (:949-951, PhysicalConstants.h:397-399)
+					ex[j] = ph.cp * exp(ph.exner_c1 * log(ph.exner_c2 * p[j]));
+					// Fluxes (:1050-1077)
+					const double fa_ = cJ[j] * conUa[j];
+					const double fb_ = cJ[j] * conUb[j];
+					faR[j] = fa_ * r[j];
+					fbR[j] = fb_ * r[j];
+					faP[j] = fa_ * p[j];
+					fbP[j] = fb_ * p[j];
+					theta[j] = p[j] / r[j];
+					// DifferentiateNodeToNode of u_alpha, u_beta (:974-1001)
+					double d = 0.0;
+					d += d0 * um[j]; d += d1 * u[j]; d += d2 * up[j];
+					dxUa[j] = d;
+					d = 0.0;
+					d += d0 * vm[j]; d += d1 * v[j]; d += d2 * vp[j];
+					dxUb[j] = d;
+				}
+				if (active) {
+					tb_st4s(tWn + (size_t)k * NN, tp, i, wn);
+					tb_st4s(tKE + (size_t)k * NN, tp, i, ke);
+					tb_st4s(tEX + (size_t)k * NN, tp, i, ex);
+					tb_st4s(tFaR + (size_t)k * NN, tp, i, faR);
+					tb_st4s(tFaP + (size_t)k * NN, tp, i, faP);
+				}
+			}
+			__syncwarp();
+
+			const size_t o4 = (size_t)kc * NN + i * NP;
+#pragma unroll
+			for (int jh = 0; jh < 2; jh++) {
+				double dCovDaUb[2], dCovDaUx[2], dDaP[2], dDaKE[2], dDaRhoFluxA[2], dDaPressureFluxA[2];
+				tb_cross_sum2s(inb + (size_t)(rV + kc) * NN, (rV + kc) & 1, jh, dxI, dCovDaUb);
+				tb_cross_sum2s(tWn + (size_t)kc * NN, tp, jh, dxI, dCovDaUx);
+				tb_cross_sum2s(tEX + (size_t)kc * NN, tp, jh, dxI, dDaP);
+				tb_cross_sum2s(tKE + (size_t)kc * NN, tp, jh, dxI, dDaKE);
+				tb_cross_sum2s(tFaR + (size_t)kc * NN, tp, jh, stI, dDaRhoFluxA);
+				tb_cross_sum2s(tFaP + (size_t)kc * NN, tp, jh, stI, dDaPressureFluxA);
+
+				double cIJ[2], cFJ[2], cGA[2], cGB[2];
+				tb_ld2(cc + TBF_INVJAC * NN + 2 * jh, cIJ);
+				tb_ld2(cc + TBF_FJ * NN + 2 * jh, cFJ);
+				tb_ld2(cc + TBF_GDA * NN + 2 * jh, cGA);
+				tb_ld2(cc + TBF_GDB * NN + 2 * jh, cGB);
+				// stage base: my node pair of the four level components
+				const int ch = 2 * i + jh;
+				double bU[2], bV[2], bP[2], bR[2];
+				tb_ld2(bsb + (size_t)(rU + kc) * NN + ((ch ^ ((rU + kc) & 1)) << 1), bU);
+				tb_ld2(bsb + (size_t)(rV + kc) * NN + ((ch ^ ((rV + kc) & 1)) << 1), bV);
+				tb_ld2(bsb + (size_t)(rP + kc) * NN + ((ch ^ ((rP + kc) & 1)) << 1), bP);
+				tb_ld2(bsb + (size_t)(rR + kc) * NN + ((ch ^ ((rR + kc) & 1)) << 1), bR);
+
+				double zx[2];
+#pragma unroll
+				for (int q = 0; q < 2; q++) {
+					const int j = 2 * jh + q;
+					double dCovDbUa = 0.0, dCovDbUx = 0.0, dDbP = 0.0, dDbKE = 0.0;
+					double dDbRhoFluxB = 0.0, dDbPressureFluxB = 0.0;
+#pragma unroll
+					for (int s = 0; s < 4; s++) {
+						dCovDbUa += u[s] * t.dx[s * NP + j];
+						dCovDbUx += wn[s] * t.dx[s * NP + j];
+						dDbRhoFluxB -= fbR[s] * t.st[j * NP + s];
+						dDbPressureFluxB -= fbP[s] * t.st[j * NP + s];
+						dDbP += ex[s] * t.dx[s * NP + j];
+						dDbKE += ke[s] * t.dx[s * NP + j];
+					}
+					const double aDaUb = dCovDaUb[q] * dInvDA;
+					const double aDaUx = dCovDaUx[q] * dInvDA;
+					const double aDbUa = dCovDbUa * dInvDB;
+					const double aDbUx = dCovDbUx * dInvDB;
+
+					// U cross relative vorticity (:966-1039)
+					const double dJZetaA = (aDbUx - dxUb[j]);
+					const double dJZetaB = (dxUa[j] - aDaUx);
+					const double dJZetaX = (aDaUb - aDbUa);
+					const double dUCrossZetaA = conUb[j] * dJZetaX - conUx[j] * dJZetaB;
+					const double dUCrossZetaB = conUx[j] * dJZetaA - conUa[j] * dJZetaX;
+					zx[q] = -conUa[j] * aDaUx - conUb[j] * aDbUx;
+
+					const double aDaRho = -(dDaRhoFluxA[q] * dInvDA);
+					const double aDbRho = dDbRhoFluxB * dInvDB;
+					const double aDaPre = -(dDaPressureFluxA[q] * dInvDA);
+					const double aDbPre = dDbPressureFluxB * dInvDB;
+					const double aDaP = dDaP[q] * dInvDA;
+					const double aDbP = dDbP * dInvDB;
+					const double aDaKE = dDaKE[q] * dInvDA;
+					const double aDbKE = dDbKE * dInvDB;
+
+					double dLocalUpdateUa = 0.0, dLocalUpdateUb = 0.0;
+					dLocalUpdateUa += dUCrossZetaA;
+					dLocalUpdateUb += dUCrossZetaB;
+					// Coriolis (:1330-1338)
+					dLocalUpdateUa += cFJ[q] * conUb[j];
+					dLocalUpdateUb -= cFJ[q] * conUa[j];
+					// Pressure gradient force (:1348-1353), gravity (:1363-1364)
+					const double dPGFa = aDaP * theta[j];
+					const double dPGFb = aDbP * theta[j];
+					const double dDaPhi = sn * cGA[q];
+					const double dDbPhi = sn * cGB[q];
+					dLocalUpdateUa -= dPGFa + aDaKE + dDaPhi;
+					dLocalUpdateUb -= dPGFb + aDbKE + dDbPhi;
+
+					bU[q] = bU[q] + dt * dLocalUpdateUa;
+					if (!fa.xz) bV[q] += dt * dLocalUpdateUb;
+					// Density and rho-theta (:1399-1421)
+					bR[q] = bR[q] - dt * cIJ[q] * (aDaRho + aDbRho);
+					bP[q] = bP[q] - dt * cIJ[q] * (aDaPre + aDbPre);
+				}
+				if (active) {
+					const size_t o2 = o4 + 2 * jh;
+					tb_st2(out + ebase + (size_t)rR * NN + o2, bR);
+					tb_st2(out + ebase + (size_t)rP * NN + o2, bP);
+					tb_st2(tZX + (size_t)k * NN + ((ch ^ tp) << 1), zx);
+					if (k < 3) {
+						tb_st2(sUn + k * NN + 4 * i + 2 * jh, bU);
+						tb_st2(sVn + k * NN + 4 * i + 2 * jh, bV);
+					}
+				}
+				if (DO_V) {
+					// upwind penalty on U and V for this node pair
+					// (VerticalDynamicsFEM.cpp:816-828, 998-1023)
+					const double se0 = lv[TBF_SE], se1 = lv[TBF_SE1];
+					// the windows of the skipped sides (top / bottom level) are zero
+					double u0[2], v0[2], um[2], up[2], vm[2], vp[2], w0[2], wp[2];
+					tb_ld2(inb + (size_t)(rU + kc) * NN + ((ch ^ ((rU + kc) & 1)) << 1), u0);
+					tb_ld2(inb + (size_t)(rV + kc) * NN + ((ch ^ ((rV + kc) & 1)) << 1), v0);
+					tb_ld2(inb + (size_t)(rU + km) * NN + ((ch ^ ((rU + km) & 1)) << 1), um);
+					tb_ld2(inb + (size_t)(rU + kp) * NN + ((ch ^ ((rU + kp) & 1)) << 1), up);
+					tb_ld2(inb + (size_t)(rV + km) * NN + ((ch ^ ((rV + km) & 1)) << 1), vm);
+					tb_ld2(inb + (size_t)(rV + kp) * NN + ((ch ^ ((rV + kp) & 1)) << 1), vp);
+					tb_ld2(inb + (size_t)(rW + kc) * NN + ((ch ^ ((rW + kc) & 1)) << 1), w0);
+					tb_ld2(inb + (size_t)(rW + kc + 1) * NN + ((ch ^ ((rW + kc + 1) & 1)) << 1), wp);
+#pragma unroll
+					for (int q = 0; q < 2; q++) {
+						const int j = 2 * jh + q;
+						double au = 0.0, av = 0.0;
+						{
+							double ue = 0.0, ve = 0.0;
+							ue += lv[TBF_CIHI + 0] * um[q]; ue += lv[TBF_CIHI + 1] * u0[q]; ue += lv[TBF_CIHI + 2] * up[q];
+							ve += lv[TBF_CIHI + 0] * vm[q]; ve += lv[TBF_CIHI + 1] * v0[q]; ve += lv[TBF_CIHI + 2] * vp[q];
+							const double c0 = se1 * cA2[j], c1 = se1 * cB2[j];
+							const double c2 = cX0[j] + (se1 * se1) * cX2[j];
+							const double xd = c0 * ue + c1 * ve + c2 * wp[q];
+							const double wgt = dt * fabs(xd);
+							double pu = 0.0, pv = 0.0;
+							pu += lv[TBF_CPL + 0] * um[q]; pu += lv[TBF_CPL + 1] * u0[q]; pu += lv[TBF_CPL + 2] * up[q];
+							pv += lv[TBF_CPL + 0] * vm[q]; pv += lv[TBF_CPL + 1] * v0[q]; pv += lv[TBF_CPL + 2] * vp[q];
+							au += pu * wgt;
+							av += pv * wgt;
+						}
+						{
+							double ue = 0.0, ve = 0.0;
+							ue += lv[TBF_CILO + 0] * um[q]; ue += lv[TBF_CILO + 1] * u0[q]; ue += lv[TBF_CILO + 2] * up[q];
+							ve += lv[TBF_CILO + 0] * vm[q]; ve += lv[TBF_CILO + 1] * v0[q]; ve += lv[TBF_CILO + 2] * vp[q];
+							const double c0 = se0 * cA2[j], c1 = se0 * cB2[j];
+							const double c2 = cX0[j] + (se0 * se0) * cX2[j];
+							const double xd = c0 * ue + c1 * ve + c2 * w0[q];
+							const double wgt = dt * fabs(xd);
+							double pu = 0.0, pv = 0.0;
+							pu += lv[TBF_CPR + 0] * um[q]; pu += lv[TBF_CPR + 1] * u0[q]; pu += lv[TBF_CPR + 2] * up[q];
+							pv += lv[TBF_CPR + 0] * vm[q]; pv += lv[TBF_CPR + 1] * v0[q]; pv += lv[TBF_CPR + 2] * vp[q];
+							au += pu * wgt;
+							av += pv * wgt;
+						}
+						bU[q] += au;
+						bV[q] += av;
+					}
+				}
+				if (active) {
+					const size_t o2 = o4 + 2 * jh;
+					tb_st2(out + ebase + (size_t)rU * NN + o2, bU);
+					tb_st2(out + ebase + (size_t)rV * NN + o2, bV);
+				}
+			}
+		}
+		__syncthreads();
+
+		// ---- vertical velocity on interfaces (:1612-1660) --------------------------
+		for (int k = kq; k <= L; k += TBF_KB) {
+			const size_t o4 = (size_t)k * NN + i * NP;
+			const double * lv = slev + (size_t)k * TBF_LWS;
+			double bW[4];
+			if (k == 0) {
+				const double se0 = lv[TBF_SE];
+				double a[4], b[4], c[4], a2[4], b2[4], c2[4];
+				double cA2[4], cB2[4], cX0[4], cX2[4];
+				tb_ld4(cc + TBF_A2 * NN, cA2);
+				tb_ld4(cc + TBF_B2 * NN, cB2);
+				tb_ld4(cc + TBF_X0 * NN, cX0);
+				tb_ld4(cc + TBF_X2 * NN, cX2);
+				const int l2 = (L > 2) ? 2 : (L - 1);
+				const int l1 = (L > 1) ? 1 : 0;
+				tb_ld4(sUn + i * NP, a); tb_ld4(sUn + l1 * NN + i * NP, b); tb_ld4(sUn + l2 * NN + i * NP, c);
+				tb_ld4(sVn + i * NP, a2); tb_ld4(sVn + l1 * NN + i * NP, b2); tb_ld4(sVn + l2 * NN + i * NP, c2);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					double dU0 = 0.0, dV0 = 0.0;
+					dU0 += lv[TBF_CB0 + 0] * a[j]; dU0 += lv[TBF_CB0 + 1] * b[j]; dU0 += lv[TBF_CB0 + 2] * c[j];
+					dV0 += lv[TBF_CB0 + 0] * a2[j]; dV0 += lv[TBF_CB0 + 1] * b2[j]; dV0 += lv[TBF_CB0 + 2] * c2[j];
+					const double c0 = se0 * cA2[j], c1 = se0 * cB2[j];
+					const double cx2 = cX0[j] + (se0 * se0) * cX2[j];
+					bW[j] = -(c0 * dU0 + c1 * dV0) / cx2;
+				}
+			} else {
+				tb_ld4s(bsb + (size_t)(rW + k) * NN, (rW + k) & 1, i, bW);
+				if (k < L) {
+					double zm[4], z0[4];
+					tb_ld4s(tZX + (size_t)(k - 1) * NN, (k - 1) & 1, i, zm);
+					tb_ld4s(tZX + (size_t)k * NN, k & 1, i, z0);
+#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						double x = 0.0;
+						x += lv[TBF_CILO + 0] * zm[j];
+						x += lv[TBF_CILO + 1] * z0[j];
+						bW[j] += dt * x;
+					}
+				}
+			}
+			tb_st4(out + ebase + (size_t)rW * NN + o4, bW);
 		}
 	}
 }

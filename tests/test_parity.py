@@ -229,6 +229,19 @@ def test_fast_path_equals_general_kernels(library, monkeypatch):
         res.append(dumpctx.download(ctx, d, 1))
         assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
         ctx.close()
+    # persistent-block loop of the pipelined kernel (several elements per block,
+    # double-buffered prefetch) and the non-pipelined fast kernel: same bits
+    for env, val in (("TB200_PIPE_BLOCKS", "5"), ("TB200_STAGE_KERNEL", "fast")):
+        monkeypatch.setenv(env, val)
+        ctx = dumpctx.context_from_dump(d, library=library, analytic_metric=True)
+        dumpctx.upload_tag(ctx, d, "ic")
+        ctx.hv_step_explicit_combine([1.0, 0.0], 0, 1, 50.0)
+        got = dumpctx.download(ctx, d, 1)
+        ctx.close()
+        monkeypatch.delenv(env)
+        for n in got:
+            for loc in (0, 1):
+                assert np.array_equal(got[n][loc], res[1][n][loc]), env
     ic = {n: (dumpctx.interior(d["ic.patch%d.inst0.node" % n]),
               dumpctx.interior(d["ic.patch%d.inst0.redge" % n])) for n in res[0]}
     for n in res[0]:
