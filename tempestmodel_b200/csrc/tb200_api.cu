@@ -16,6 +16,7 @@
 #include "tb200_dss.cuh"
 #include "tb200_column.cuh"
 #include "tb200_fast.cuh"
+#include "tb200_column_fast.cuh"
 
 #define TB_CHECK(ctx, call) \
 	do { \
@@ -1152,6 +1153,41 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
 	ca.assemble_only = 0;
+
+	// vertical order 1 + terrain-following metric: specialised kernel
+	// (tb200_column_fast.cuh); TB200_COLUMN_KERNEL = thread | warp | window selects
+	// one of the general kernels instead
+	if (fast_prepare(ctx)) return 1;
+	if (ctx->fast_state == 1 && getenv("TB200_COLUMN_KERNEL") == 0) {
+		ColumnFastArgs fa;
+		fa.col_node = ctx->d_col_node;
+		fa.col_dups = ctx->d_col_dups;
+		fa.ws = ctx->d_ws;
+		fa.dt = dt;
+		fa.upwind_coeff = ca.upwind_coeff;
+		fa.info = ctx->d_info;
+		fa.colc = ctx->d_colc;
+		fa.lev = ctx->d_lev;
+		const size_t smem = (size_t)(lay.nlev + 1) * TBF_LW * sizeof(double);
+		auto kfn = k_column_fast;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		// scratch: 10 n doubles per column, columns padded to whole blocks
+		const size_t ws_doubles = (size_t)tb_column_ws_entries(lay.nlev, ctx->offd) * ctx->ws_cols;
+		long long chunk = (long long)(ws_doubles / ((size_t)30 * (lay.nlev + 1))) / TBC_THREADS * TBC_THREADS;
+		if (chunk < TBC_THREADS) TB_FAIL(ctx, "column workspace too small");
+		if (chunk > ctx->ncols) chunk = ((ctx->ncols + TBC_THREADS - 1) / TBC_THREADS) * TBC_THREADS;
+		for (int c0 = 0; c0 < ctx->ncols; c0 += (int)chunk) {
+			fa.col0 = c0;
+			fa.ncols = (int)std::min<long long>(chunk, ctx->ncols - c0);
+			TB_LAUNCH(kfn, dim3((fa.ncols + TBC_THREADS - 1) / TBC_THREADS), dim3(TBC_THREADS),
+				smem, ctx->stream, lay, ctx->phys, fa,
+				(const double *)ctx->inst[in], ctx->inst[out]);
+			TB_KERNEL_CHECK(ctx);
+		}
+		return 0;
+	}
 
 	// one warp per column with all work arrays in shared memory, unless the
 	// column is too tall for it (or TB200_COLUMN_KERNEL=thread asks for the

@@ -185,14 +185,20 @@ def test_error_conventions(library):
 
 
 def test_column_kernels_agree(library, monkeypatch):
-    """The three device implementations of the implicit column solve
-    (thread per column / warp per column / sliding window) build the same
-    matrix and run the same elimination: results agree to rounding."""
+    """The device implementations of the implicit column solve (general:
+    thread per column / warp per column / sliding window; order-1 fast kernel)
+    build the same matrix and run the same elimination: results agree to
+    rounding."""
     d = cases.load_case("jw_ne2_l6")
     res = {}
-    for kind in ("thread", "warp", "window"):
-        monkeypatch.setenv("TB200_COLUMN_KERNEL", kind)
+    for kind in ("thread", "warp", "window", "fast"):
+        if kind == "fast":
+            monkeypatch.delenv("TB200_COLUMN_KERNEL")
+        else:
+            monkeypatch.setenv("TB200_COLUMN_KERNEL", kind)
         ctx = dumpctx.context_from_dump(d, library=library)
+        if kind == "fast":
+            assert ctx.fast_path()[0]
         dumpctx.upload_tag(ctx, d, "dss", instances=[1])
         ctx.copy(1, 2)
         ctx.v_step_implicit(2, 2, 30.0)
@@ -200,7 +206,7 @@ def test_column_kernels_agree(library, monkeypatch):
         res[kind] = dumpctx.download(ctx, d, 2)
         assert_below(dumpctx.compare(ctx, d, 2, "vi", [0, 1, 2, 4], [3]), 1e-12)
         ctx.close()
-    for kind in ("warp", "window"):
+    for kind in ("warp", "window", "fast"):
         for n in res["thread"]:
             for loc in (0, 1):
                 a, b = res["thread"][n][loc], res[kind][n][loc]
