@@ -1455,6 +1455,59 @@ static int hyper_vector(
 	return 0;
 }
 
+static bool hyper_fast_ok(tb200_ctx * ctx) {
+	if (fast_prepare(ctx)) return false;
+	const char * force = getenv("TB200_HYPER_KERNEL");
+	if (force != 0 && strcmp(force, "generic") == 0) return false;
+	return ctx->fast_state == 1 && ctx->lay.ntr == 0;
+}
+
+// out = (base >= 0 ? inst[base] : 0) - dt nu L(inst[fld]), all prognostic fields
+static int hyper_fast(
+	tb200_ctx * ctx, int fld, int base, int out, double dt,
+	double nus, double nud, double nuv, bool scale
+) {
+	const DevLayout & lay = ctx->lay;
+	HyperFastArgs ha;
+	ha.colc = ctx->d_colc;
+	ha.inv_da = ctx->d_inv_da;
+	ha.inv_db = ctx->d_inv_db;
+	ha.nu_scale = ctx->d_nu_scale;
+	ha.dt = dt;
+	ha.nu_scalar = nus;
+	ha.nu_div = nud;
+	ha.nu_vort = nuv;
+	ha.scale_nu = scale ? 1 : 0;
+	ha.xz = ctx->cfg.cartesian_xz;
+	const bool has_base = (base >= 0);
+	const size_t smem = tb_hyper_smem_doubles(lay.nrows, lay.nlev, has_base) * sizeof(double);
+	if (smem > 227 * 1024 - 1024) TB_FAIL(ctx, "column too tall for the fused hyperdiffusion kernel");
+	int per_sm = (int)((227 * 1024) / (smem + 1024));
+	if (per_sm > 2) per_sm = 2;
+	long long nb = (long long)ctx->sm_count * per_sm;
+	const char * fb = getenv("TB200_PIPE_BLOCKS");
+	if (fb != 0 && atoi(fb) > 0) nb = atoi(fb);
+	if (nb > lay.nelem) nb = lay.nelem;
+	const dim3 grid((unsigned)nb), block(TBF_THREADS);
+	if (has_base) {
+		auto kfn = k_hyper_pipe<true>;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
+			(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out]);
+	} else {
+		auto kfn = k_hyper_pipe<false>;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
+			(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out]);
+	}
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
 extern "C" int tb200_h_step_after_subcycle(
 	tb200_ctx * ctx, int in, int out, int work, double dt
 ) {
@@ -1466,7 +1519,10 @@ extern "C" int tb200_h_step_after_subcycle(
 	if (out == work) TB_FAIL(ctx, "Invalid indices -- working and update data must be distinct");
 	const tb200_config & c = ctx->cfg;
 	const int all = TB200_DATA_STATE | TB200_DATA_TRACERS;
-	if (tb200_copy(ctx, in, out, all)) return 1;
+	const bool active = !((c.nu_scalar == 0.0) && (c.nu_div == 0.0) && (c.nu_vort == 0.0));
+	if (!(active && c.hypervis_order == 4 && hyper_fast_ok(ctx))) {
+		if (tb200_copy(ctx, in, out, all)) return 1;
+	}
 	if ((c.nu_scalar == 0.0) && (c.nu_div == 0.0) && (c.nu_vort == 0.0)) {
 	} else if (c.hypervis_order == 0) {
 	} else if (c.hypervis_order == 2) {
@@ -1474,6 +1530,13 @@ extern "C" int tb200_h_step_after_subcycle(
 		if (hyper_vector(ctx, in, out, -dt, c.nu_div, c.nu_vort, false)) return 1;
 		if (tb200_filter_negative_tracers(ctx, out)) return 1;
 		if (tb200_dss(ctx, out, all)) return 1;
+	} else if (c.hypervis_order == 4 && hyper_fast_ok(ctx)) {
+		// both Laplacian applications with ZeroData / CopyData folded in
+		if (hyper_fast(ctx, in, -1, work, 1.0, 1.0, 1.0, 1.0, false)) return 1;
+		if (tb200_dss(ctx, work, all)) return 1;
+		if (hyper_fast(ctx, work, in, out, -dt, c.nu_scalar, c.nu_div, c.nu_vort, true)) return 1;
+		if (tb200_dss(ctx, out, all)) return 1;
+		return 0;
 	} else if (c.hypervis_order == 4) {
 		if (tb200_zero(ctx, work, all)) return 1;
 		if (hyper_scalar(ctx, in, work, 1.0, 1.0, false)) return 1;

@@ -16,7 +16,7 @@
 //    from the host tables, never hard-coded) are pre-windowed on the host to
 //    dense 3-coefficient rows around k and loaded once per thread;
 //  * the 3-D metric arrays of the reference (13 doubles per node) are replaced
-//    by 13 constants per column (TBF_*), exact for every terrain-following
+//    by 15 constants per column (TBF_*), exact for every terrain-following
 //    metric of the form  dR/dalpha = s(eta) dzs/dalpha, dR/dxi = ztop - zs
 //    (GridPatchCSGLL.cpp:344-553; GridPatchCartesianGLL.cpp:262-330 with flat
 //    terrain).  The host verifies them against the uploaded reference arrays
@@ -47,7 +47,9 @@
 #define TBF_GDA 10     // g * dzs/dalpha   (g * DerivR[0] = s * GDA)
 #define TBF_GDB 11
 #define TBF_DXR 12     // DerivR[2]
-#define TBF_NC 13
+#define TBF_J2D 13     // Jacobian2D
+#define TBF_B0 14      // ContraMetric2DB[0]
+#define TBF_NC 15
 
 // ---- per-level operator windows: lev[k * TBF_LW + q], k = 0..L ------------------
 #define TBF_CW 0       // [2] InterpREdgeToNode row k on W[k], W[k+1]
@@ -1053,6 +1055,304 @@ k_nh_stage_pipe(
 }
 
 ///////////////////////////////////////////////////////////////////////////////
+// Hyperdiffusion, one pass over all prognostic fields:
+//   out = base - dt nu L(fld)       (base = 0 when HAS_BASE is false)
+// with L the scalar Laplacian on rho-theta, w, rho
+// (HorizontalDynamicsFEM::ApplyScalarHyperdiffusion, :1867-2203) and the vector
+// Laplacian on (u_alpha, u_beta) (ApplyVectorHyperdiffusion with
+// GridPatchCSGLL::ComputeCurlAndDiv inlined, :2207-2414,
+// GridPatchCSGLL.cpp:1132-1305).  The reference's order-4 sequence
+//   work = 0; work -= L(in); DSS(work); out = in; out -= (-dt) nu_loc L(work); DSS(out)
+// (:2687-2713) becomes two launches of this kernel around the DSS calls, with
+// the ZeroData / CopyData passes folded in: 8 S bytes per node in all
+//  instead of 13 S.  Same persistent, cp.async-pipelined skeleton
+// and the same (level, element row) thread layout as k_nh_stage_pipe.
+
+struct HyperFastArgs {
+	const double * colc;
+	const double * inv_da;
+	const double * inv_db;
+	const double * nu_scale;
+	double dt;
+	double nu_scalar, nu_div, nu_vort;
+	int scale_nu;
+	int xz;
+};
+
+__host__ __device__ inline size_t tb_hyper_smem_doubles(int nrows, int L, bool has_base) {
+	// fld[2] (+ base[2]), tiles GaP, GaR, JUa, Div, Curl [L], GaW [L+1], column constants [2]
+	return (size_t)nrows * 16 * (has_base ? 4 : 2) + (size_t)(6 * L + 1) * 16 + 2 * TBF_NC * 16;
+}
+
+// beta-direction sum over my own row: o = sum_s x[s] * c[s*4 + j] (c = dx) or
+// c[j*4 + s] (c = st)
+#define TB_ROW_DX(x, j) ((((0.0 + (x)[0] * t.dx[0 * 4 + (j)]) + (x)[1] * t.dx[1 * 4 + (j)]) \
+	+ (x)[2] * t.dx[2 * 4 + (j)]) + (x)[3] * t.dx[3 * 4 + (j)])
+#define TB_ROW_ST(x, j) ((((0.0 + (x)[0] * t.st[(j) * 4 + 0]) + (x)[1] * t.st[(j) * 4 + 1]) \
+	+ (x)[2] * t.st[(j) * 4 + 2]) + (x)[3] * t.st[(j) * 4 + 3])
+
+// alpha-direction sum over a swizzled row for all four nodes of my row
+__device__ __forceinline__ void tb_cross_sum4s(
+	const double * row, int par, const double (&c)[4], double (&o)[4]
+) {
+	double lo[2], hi[2];
+	tb_cross_sum2s(row, par, 0, c, lo);
+	tb_cross_sum2s(row, par, 1, c, hi);
+	o[0] = lo[0]; o[1] = lo[1]; o[2] = hi[0]; o[3] = hi[1];
+}
+
+template <bool HAS_BASE>
+__global__ void __launch_bounds__(TBF_THREADS, 2)
+k_hyper_pipe(
+	DevLayout lay, DevTables t, HyperFastArgs ha,
+	const double * __restrict__ fld, const double * base, double * out
+) {
+	const int NP = 4, NN = 16;
+	const int L = lay.nlev;
+	const int nrows = lay.nrows;
+	const int rU = lay.rowoff[0], rV = lay.rowoff[1], rP = lay.rowoff[2];
+	const int rW = lay.rowoff[3], rR = lay.rowoff[4];
+
+	TB_DYN_SMEM(double, sm);
+	const size_t esz = (size_t)nrows * NN;
+	double * fb0 = sm;
+	double * bb0 = sm + 2 * esz;
+	double * tGP = sm + (HAS_BASE ? 4 : 2) * esz;
+	double * tGR = tGP + (size_t)L * NN;
+	double * tJU = tGR + (size_t)L * NN;
+	double * tDV = tJU + (size_t)L * NN;
+	double * tCL = tDV + (size_t)L * NN;
+	double * tGW = tCL + (size_t)L * NN;         // [L+1]
+	double * scc0 = tGW + (size_t)(L + 1) * NN;  // [2][TBF_NC][16]
+
+	const int tid = threadIdx.x;
+	const int kq = tid >> 2;
+	const int i = tid & 3;
+	const int nchunk = nrows * 8;
+
+	double dxI[4], stI[4];
+#pragma unroll
+	for (int s = 0; s < 4; s++) {
+		dxI[s] = t.dx[s * NP + i];
+		stI[s] = t.st[i * NP + s];
+	}
+
+	long long e = blockIdx.x;
+	if (e >= lay.nelem) return;
+	{
+		const size_t eb = (size_t)e * esz;
+		for (int q = tid; q < nchunk; q += TBF_THREADS) {
+			const int r = q >> 3, c = q & 7;
+			const int d = ((r << 3) | (c ^ (r & 1))) << 1;
+			tb_cp16(fb0 + d, fld + eb + 2 * q);
+			if (HAS_BASE) tb_cp16(bb0 + d, base + eb + 2 * q);
+		}
+		for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
+			tb_cp16(scc0 + 2 * q, ha.colc + (size_t)e * TBF_NC * NN + 2 * q);
+		}
+		tb_cp_commit();
+	}
+
+	for (int it = 0; e < lay.nelem; it++, e += gridDim.x) {
+		const int buf = it & 1;
+		const double * fb = fb0 + (size_t)buf * esz;
+		const double * bb = bb0 + (size_t)buf * esz;
+		tb_cp_wait<0>();
+		__syncthreads();
+		{
+			const long long en = e + gridDim.x;
+			if (en < lay.nelem) {
+				const size_t eb = (size_t)en * esz;
+				double * df = fb0 + (size_t)(buf ^ 1) * esz;
+				double * db = bb0 + (size_t)(buf ^ 1) * esz;
+				for (int q = tid; q < nchunk; q += TBF_THREADS) {
+					const int r = q >> 3, c = q & 7;
+					const int d = ((r << 3) | (c ^ (r & 1))) << 1;
+					tb_cp16(df + d, fld + eb + 2 * q);
+					if (HAS_BASE) tb_cp16(db + d, base + eb + 2 * q);
+				}
+				double * dc = scc0 + (size_t)(buf ^ 1) * TBF_NC * NN;
+				for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
+					tb_cp16(dc + 2 * q, ha.colc + (size_t)en * TBF_NC * NN + 2 * q);
+				}
+			}
+			tb_cp_commit();
+		}
+
+		const size_t ebase = (size_t)e * esz;
+		const double * cc = scc0 + (size_t)buf * TBF_NC * NN + i * NP;
+		const double dInvDA = __ldg(ha.inv_da + e);
+		const double dInvDB = __ldg(ha.inv_db + e);
+		const double nus = ha.scale_nu ? __ldg(ha.nu_scale + e) : 1.0;
+		// HorizontalDynamicsFEM.cpp:1970-1975, 2226-2233
+		const double dNuS = ha.scale_nu ? ha.nu_scalar * nus : ha.nu_scalar;
+		const double dNuD = ha.scale_nu ? ha.nu_div * nus : ha.nu_div;
+		const double dNuV = ha.scale_nu ? ha.nu_vort * nus : ha.nu_vort;
+
+		double cA0[4], cA1[4], cB0[4], cB1[4], cJ[4], cIJ[4], cJ2[4];
+		tb_ld4(cc + TBF_A0 * NN, cA0);
+		tb_ld4(cc + TBF_A1 * NN, cA1);
+		tb_ld4(cc + TBF_B0 * NN, cB0);
+		tb_ld4(cc + TBF_B1 * NN, cB1);
+		tb_ld4(cc + TBF_JAC * NN, cJ);
+		tb_ld4(cc + TBF_INVJAC * NN, cIJ);
+		tb_ld4(cc + TBF_J2D * NN, cJ2);
+
+		for (int k0 = 0; k0 <= L; k0 += TBF_KB) {
+			const int k = k0 + kq;
+			const bool wact = (k <= L);             // interface row exists
+			const bool lact = (k < L);              // level rows exist
+			const int kw = wact ? k : L;
+			const int kc = lact ? k : (L - 1);
+			const int tp = kc & 1, tpw = kw & 1;
+
+			// ---- first round: gradients -> fluxes ------------------------------------
+			double gbP[4], gbR[4], gbW[4], jub[4], u[4], v[4];
+			{
+				double x[4], da[4], gaP[4], gaR[4], gaW[4], jua[4];
+				// rho-theta
+				tb_ld4s(fb + (size_t)(rP + kc) * NN, (rP + kc) & 1, i, x);
+				tb_cross_sum4s(fb + (size_t)(rP + kc) * NN, (rP + kc) & 1, dxI, da);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const double dDa = da[j] * dInvDA;
+					const double dDb = TB_ROW_DX(x, j) * dInvDB;
+					gaP[j] = cJ[j] * (cA0[j] * dDa + cA1[j] * dDb);
+					gbP[j] = cJ[j] * (cB0[j] * dDa + cB1[j] * dDb);
+				}
+				// rho
+				tb_ld4s(fb + (size_t)(rR + kc) * NN, (rR + kc) & 1, i, x);
+				tb_cross_sum4s(fb + (size_t)(rR + kc) * NN, (rR + kc) & 1, dxI, da);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const double dDa = da[j] * dInvDA;
+					const double dDb = TB_ROW_DX(x, j) * dInvDB;
+					gaR[j] = cJ[j] * (cA0[j] * dDa + cA1[j] * dDb);
+					gbR[j] = cJ[j] * (cB0[j] * dDa + cB1[j] * dDb);
+				}
+				// w (interfaces; JacobianREdge = Jacobian for this metric)
+				tb_ld4s(fb + (size_t)(rW + kw) * NN, (rW + kw) & 1, i, x);
+				tb_cross_sum4s(fb + (size_t)(rW + kw) * NN, (rW + kw) & 1, dxI, da);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const double dDa = da[j] * dInvDA;
+					const double dDb = TB_ROW_DX(x, j) * dInvDB;
+					gaW[j] = cJ[j] * (cA0[j] * dDa + cA1[j] * dDb);
+					gbW[j] = cJ[j] * (cB0[j] * dDa + cB1[j] * dDb);
+				}
+				// velocities: J2D * contravariant components (GridPatchCSGLL.cpp:1207-1218)
+				tb_ld4s(fb + (size_t)(rU + kc) * NN, (rU + kc) & 1, i, u);
+				tb_ld4s(fb + (size_t)(rV + kc) * NN, (rV + kc) & 1, i, v);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					jua[j] = cJ2[j] * (+cA0[j] * u[j] + cA1[j] * v[j]);
+					jub[j] = cJ2[j] * (+cB0[j] * u[j] + cB1[j] * v[j]);
+				}
+				if (lact) {
+					tb_st4s(tGP + (size_t)k * NN, tp, i, gaP);
+					tb_st4s(tGR + (size_t)k * NN, tp, i, gaR);
+					tb_st4s(tJU + (size_t)k * NN, tp, i, jua);
+				}
+				if (wact) tb_st4s(tGW + (size_t)k * NN, tpw, i, gaW);
+			}
+			__syncwarp();
+
+			// ---- scalar Laplacians (:2126-2165) ----------------------------------------
+			{
+				double ua[4], o[4];
+				const size_t o4 = (size_t)i * NP;
+				tb_cross_sum4s(tGP + (size_t)kc * NN, tp, stI, ua);
+				if (HAS_BASE) tb_ld4s(bb + (size_t)(rP + kc) * NN, (rP + kc) & 1, i, o);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const double dUpdateA = ua[j] * dInvDA;
+					const double dUpdateB = TB_ROW_ST(gbP, j) * dInvDB;
+					const double b = HAS_BASE ? o[j] : 0.0;
+					o[j] = b - ha.dt * cIJ[j] * dNuS * (dUpdateA + dUpdateB);
+				}
+				if (lact) tb_st4(out + ebase + (size_t)(rP + k) * NN + o4, o);
+				tb_cross_sum4s(tGR + (size_t)kc * NN, tp, stI, ua);
+				if (HAS_BASE) tb_ld4s(bb + (size_t)(rR + kc) * NN, (rR + kc) & 1, i, o);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const double dUpdateA = ua[j] * dInvDA;
+					const double dUpdateB = TB_ROW_ST(gbR, j) * dInvDB;
+					const double b = HAS_BASE ? o[j] : 0.0;
+					o[j] = b - ha.dt * cIJ[j] * dNuS * (dUpdateA + dUpdateB);
+				}
+				if (lact) tb_st4(out + ebase + (size_t)(rR + k) * NN + o4, o);
+				tb_cross_sum4s(tGW + (size_t)kw * NN, tpw, stI, ua);
+				if (HAS_BASE) tb_ld4s(bb + (size_t)(rW + kw) * NN, (rW + kw) & 1, i, o);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const double dUpdateA = ua[j] * dInvDA;
+					const double dUpdateB = TB_ROW_ST(gbW, j) * dInvDB;
+					const double b = HAS_BASE ? o[j] : 0.0;
+					o[j] = b - ha.dt * cIJ[j] * dNuS * (dUpdateA + dUpdateB);
+				}
+				if (wact) tb_st4(out + ebase + (size_t)(rW + k) * NN + o4, o);
+			}
+
+			// ---- curl and divergence (GridPatchCSGLL.cpp:1262-1299) --------------------
+			double dv[4], cl[4];
+			{
+				double daUb[4], daJUa[4];
+				tb_cross_sum4s(fb + (size_t)(rV + kc) * NN, (rV + kc) & 1, dxI, daUb);
+				tb_cross_sum4s(tJU + (size_t)kc * NN, tp, dxI, daJUa);
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const double dDaUb = daUb[j] * dInvDA;
+					const double dDbUa = TB_ROW_DX(u, j) * dInvDB;
+					const double dDaJUa = daJUa[j] * dInvDA;
+					const double dDbJUb = TB_ROW_DX(jub, j) * dInvDB;
+					const double dInvJacobian2D = 1.0 / cJ2[j];
+					dv[j] = (dDaJUa + dDbJUb) * dInvJacobian2D;
+					cl[j] = (dDaUb - dDbUa) * dInvJacobian2D;
+				}
+				if (lact) {
+					tb_st4s(tDV + (size_t)k * NN, tp, i, dv);
+					tb_st4s(tCL + (size_t)k * NN, tp, i, cl);
+				}
+			}
+			__syncwarp();
+
+			// ---- vector Laplacian (:2366-2407) -----------------------------------------
+			{
+				double daDiv[4], daCurl[4], oU[4], oV[4];
+				tb_cross_sum4s(tDV + (size_t)kc * NN, tp, stI, daDiv);
+				tb_cross_sum4s(tCL + (size_t)kc * NN, tp, stI, daCurl);
+				if (HAS_BASE) {
+					tb_ld4s(bb + (size_t)(rU + kc) * NN, (rU + kc) & 1, i, oU);
+					tb_ld4s(bb + (size_t)(rV + kc) * NN, (rV + kc) & 1, i, oV);
+				}
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const double dDaDiv = -daDiv[j] * dInvDA;
+					const double dDbDiv = -TB_ROW_ST(dv, j) * dInvDB;
+					const double dDaCurl = -daCurl[j] * dInvDA;
+					const double dDbCurl = -TB_ROW_ST(cl, j) * dInvDB;
+					const double dUpdateUa =
+						+dNuD * dDaDiv
+						- dNuV * cJ2[j] * (cB0[j] * dDaCurl + cB1[j] * dDbCurl);
+					const double dUpdateUb =
+						+dNuD * dDbDiv
+						+ dNuV * cJ2[j] * (cA0[j] * dDaCurl + cA1[j] * dDbCurl);
+					const double bu = HAS_BASE ? oU[j] : 0.0;
+					const double bv = HAS_BASE ? oV[j] : 0.0;
+					oU[j] = bu - ha.dt * dUpdateUa;
+					oV[j] = ha.xz ? bv : (bv - ha.dt * dUpdateUb);
+				}
+				if (lact) {
+					const size_t o4 = (size_t)i * NP;
+					tb_st4(out + ebase + (size_t)(rU + k) * NN + o4, oU);
+					tb_st4(out + ebase + (size_t)(rV + k) * NN + o4, oV);
+				}
+			}
+		}
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
 // Column constants from the 2-D metric, the topography derivatives and the
 // layer depth dxr = ztop - zs (GridPatchCSGLL.cpp:344-553).
 
@@ -1085,6 +1385,8 @@ __global__ void k_fast_colc(
 	c[TBF_GDA * 16] = grav * dazs;
 	c[TBF_GDB * 16] = grav * dbzs;
 	c[TBF_DXR * 16] = dxr;
+	c[TBF_J2D * 16] = j2d;
+	c[TBF_B0 * 16] = g.b0[idx];
 }
 
 // Largest deviation of the metric rebuilt from the column constants from the

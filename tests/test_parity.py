@@ -256,3 +256,33 @@ def test_fast_path_equals_general_kernels(library, monkeypatch):
             for c in ([0, 1, 2, 4] if loc == 0 else [3]):
                 tend = np.abs(a[c] - ic[n][loc][c]).max()
                 assert np.abs(a[c] - b[c]).max() <= 1e-12 * tend + 4e-16 * np.abs(a[c]).max()
+
+
+def test_fused_hyperdiffusion_equals_general_kernels(library, monkeypatch):
+    """The fused order-4 hyperdiffusion passes (k_hyper_pipe, ZeroData / CopyData
+    folded in) against the general per-field kernels, and the persistent-block
+    loop against one element per block."""
+    d = cases.load_case("jw_ne2_l6")
+    res = {}
+    for kind in ("generic", "fused", "loop"):
+        monkeypatch.delenv("TB200_HYPER_KERNEL", raising=False)
+        monkeypatch.delenv("TB200_PIPE_BLOCKS", raising=False)
+        if kind == "generic":
+            monkeypatch.setenv("TB200_HYPER_KERNEL", "generic")
+        if kind == "loop":
+            monkeypatch.setenv("TB200_PIPE_BLOCKS", "5")
+        ctx = dumpctx.context_from_dump(d, library=library)
+        dumpctx.upload_tag(ctx, d, "dss", instances=[1])
+        ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+        assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+        assert_below(dumpctx.compare(ctx, d, 4, "hasc", [0, 1, 2, 4], [3]), 1e-11)
+        res[kind] = (dumpctx.download(ctx, d, 3), dumpctx.download(ctx, d, 4))
+        ctx.close()
+    for inst in (0, 1):
+        for n in res["fused"][inst]:
+            for loc in (0, 1):
+                a = res["fused"][inst][n][loc]
+                assert np.array_equal(a, res["loop"][inst][n][loc])
+                g = res["generic"][inst][n][loc]
+                for c in range(a.shape[0]):
+                    assert np.abs(a[c] - g[c]).max() <= 1e-12 * max(np.abs(g[c]).max(), 1e-300)
