@@ -243,6 +243,11 @@ int tb200_hv_step_explicit_combine(tb200_ctx * ctx, const double * coeff, int nc
                                    int in, int out, double dt);
 /* VerticalDynamicsFEM::StepImplicit (VerticalDynamicsFEM.cpp:1230-1638). */
 int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt);
+/* Grid::CopyData(src -> dst) + VerticalDynamics::StepImplicit(dst, dst, ...) as the
+ * time schemes issue them back to back (TimestepSchemeStrang.cpp:644-650,
+ * TimestepSchemeARS343.cpp:169-172): only the rows the solve does not
+ * overwrite are copied. */
+int tb200_copy_v_step_implicit(tb200_ctx * ctx, int src, int dst, double dt);
 /* GridGLL::PostProcessSubstage -> ApplyDSS (GridGLL.cpp:571-583,
  * GridCSGLL.cpp:435-781, GridCartesianGLL.cpp:508-654). */
 int tb200_dss(tb200_ctx * ctx, int inst, int data_mask);

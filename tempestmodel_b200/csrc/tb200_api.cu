@@ -64,6 +64,28 @@ static int dupload(tb200_ctx * ctx, T ** p, const std::vector<T> & v) {
 	return 0;
 }
 
+// Grid of a persistent kernel: resident blocks per SM (registers and shared
+// memory both counted by the runtime) times the SM count, so that every block
+// of the launch is resident and walks the same number of elements.
+template <typename K>
+static long long persistent_blocks(tb200_ctx * ctx, K kfn, int threads, size_t smem, long long nwork) {
+	int per_sm = 1;
+#ifndef TB200_EMU
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem) != cudaSuccess
+		|| per_sm < 1) {
+		per_sm = 1;
+	}
+#else
+	(void)kfn; (void)threads; (void)smem;
+	per_sm = 2;
+#endif
+	long long nb = (long long)ctx->sm_count * per_sm;
+	const char * fb = getenv("TB200_PIPE_BLOCKS");   // tests: force the multi-element loop
+	if (fb != 0 && atoi(fb) > 0) nb = atoi(fb);
+	if (nb > nwork) nb = nwork;
+	return nb;
+}
+
 static PatchInfo * find_patch(tb200_ctx * ctx, int patch_index) {
 	std::map<int, int>::iterator it = ctx->patch_pos.find(patch_index);
 	if (it == ctx->patch_pos.end()) return 0;
@@ -779,6 +801,8 @@ extern "C" int tb200_lincomb(
 		ca.coeff[ca.nsrc] = coeff[m];
 		ca.nsrc++;
 	}
+	// dest = 1.0 * dest and nothing added: bitwise no-op
+	if (ca.nsrc == 0 && ca.scale_dst && ca.cdst == 1.0) return 0;
 	int row0, row1;
 	mask_rows(ctx, mask, row0, row1);
 	return launch_combine(ctx, ca, dst, row0, row1);
@@ -967,18 +991,13 @@ static int nh_launch(
 			const int alias = (base == ctx->inst[in]) ? 1 : 0;
 			const size_t smem = tb_pipe_smem_doubles(lay.nrows, lay.nlev, alias != 0) * sizeof(double);
 			if (smem <= 227 * 1024 - 1024) {
-				int per_sm = (int)((227 * 1024) / (smem + 1024));
-				if (per_sm > 4) per_sm = 4;
-				long long nb = (long long)ctx->sm_count * per_sm;
-				const char * fb = getenv("TB200_PIPE_BLOCKS");   // tests: force the multi-element loop
-				if (fb != 0 && atoi(fb) > 0) nb = atoi(fb);
-				if (nb > lay.nelem) nb = lay.nelem;
-				const dim3 grid((unsigned)nb), block(TBF_THREADS);
+				const dim3 block(TBF_THREADS);
 				if (do_v) {
 					auto kfn = k_nh_stage_pipe<true>;
 #ifndef TB200_EMU
 					TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
+					const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem));
 					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa,
 						(const double *)ctx->inst[in], base, ctx->inst[out], alias);
 				} else {
@@ -986,6 +1005,7 @@ static int nh_launch(
 #ifndef TB200_EMU
 					TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
+					const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem));
 					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa,
 						(const double *)ctx->inst[in], base, ctx->inst[out], alias);
 				}
@@ -1131,6 +1151,14 @@ extern "C" int tb200_hv_step_explicit_combine(
 		sb.coeff[sb.nsrc] = coeff[m];
 		sb.nsrc++;
 	}
+	if (fast_prepare(ctx)) return 1;
+	const bool simple = (sb.nsrc == 1 && sb.coeff[0] == 1.0 && !sb.scale_dst);
+	if (ctx->fast_state == 1 && !simple && getenv("TB200_STAGE_KERNEL") == 0) {
+		// several sources: a streaming combine, then the pipelined stage kernel on
+		// the pre-filled update instance (same operation order as the fused form)
+		if (tb200_lincomb(ctx, coeff, ncoeff, out, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
+		return nh_launch(ctx, in, out, dt, true, true, stage_base_out());
+	}
 	return nh_launch(ctx, in, out, dt, true, true, sb);
 }
 
@@ -1254,6 +1282,31 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 		TB_KERNEL_CHECK(ctx);
 	}
 	return 0;
+}
+
+// CopyData(src -> dst) followed by StepImplicit(dst, dst): the column solve
+// reads src and writes rho-theta, w, rho of dst (every node is a solved column
+// or the duplicate of one), so only the rows the solve leaves alone (u, v) are
+// copied.
+extern "C" int tb200_copy_v_step_implicit(tb200_ctx * ctx, int src, int dst, double dt) {
+	if (check_inst2(ctx, src, dst)) return 1;
+	const DevLayout & lay = ctx->lay;
+	const bool solve = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && lay.nlev > 1
+		&& !ctx->cfg.fully_explicit;
+	if (src == dst || !solve || lay.ntr > 0 || fast_prepare(ctx) || ctx->fast_state != 1
+		|| getenv("TB200_COLUMN_KERNEL") != 0) {
+		if (tb200_copy(ctx, src, dst, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
+		return tb200_v_step_implicit(ctx, dst, dst, dt);
+	}
+	CombineArgs ca;
+	memset(&ca, 0, sizeof(ca));
+	ca.nsrc = 1;
+	ca.src[0] = ctx->inst[src];
+	ca.coeff[0] = 1.0;
+	ca.scale_dst = 0;
+	// rows of u and v (components 0 and 1 are adjacent)
+	if (launch_combine(ctx, ca, dst, lay.rowoff[0], lay.rowoff[1] + lay.rowlev[1])) return 1;
+	return tb200_v_step_implicit(ctx, src, dst, dt);
 }
 
 // Debugging aid: assemble F and the banded Jacobian of the first launch chunk
@@ -1482,18 +1535,13 @@ static int hyper_fast(
 	const bool has_base = (base >= 0);
 	const size_t smem = tb_hyper_smem_doubles(lay.nrows, lay.nlev, has_base) * sizeof(double);
 	if (smem > 227 * 1024 - 1024) TB_FAIL(ctx, "column too tall for the fused hyperdiffusion kernel");
-	int per_sm = (int)((227 * 1024) / (smem + 1024));
-	if (per_sm > 2) per_sm = 2;
-	long long nb = (long long)ctx->sm_count * per_sm;
-	const char * fb = getenv("TB200_PIPE_BLOCKS");
-	if (fb != 0 && atoi(fb) > 0) nb = atoi(fb);
-	if (nb > lay.nelem) nb = lay.nelem;
-	const dim3 grid((unsigned)nb), block(TBF_THREADS);
+	const dim3 block(TBF_THREADS);
 	if (has_base) {
 		auto kfn = k_hyper_pipe<true>;
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
+		const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem));
 		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
 			(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out]);
 	} else {
@@ -1501,6 +1549,7 @@ static int hyper_fast(
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
+		const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem));
 		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
 			(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out]);
 	}

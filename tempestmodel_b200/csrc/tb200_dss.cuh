@@ -31,50 +31,80 @@ struct DssArgs {
 	int sel_row0;             // first row carried by the exchange
 };
 
+// offset of local node m = e * nn + n inside row 0 of its element
+__device__ __forceinline__ size_t tb_dss_base(const DevLayout & lay, int m) {
+	if (lay.nn == 16) {
+		return (size_t)(m >> 4) * lay.nrows * 16 + (m & 15);
+	}
+	const int e = m / lay.nn;
+	const int n = m % lay.nn;
+	return (size_t)e * lay.nrows * lay.nn + n;
+}
+
 __device__ __forceinline__ double tb_dss_load(
 	const DevLayout & lay, const DssArgs & a, const double * data, int m, int r
 ) {
 	if (m < a.nlocal) {
-		const int e = m / lay.nn;
-		const int n = m % lay.nn;
-		return data[((size_t)e * lay.nrows + r) * lay.nn + n];
+		return data[tb_dss_base(lay, m) + (size_t)r * lay.nn];
 	}
 	return a.recv[(size_t)(m - a.nlocal) * a.nsel + (r - a.sel_row0)];
+}
+
+// member reference resolved once per thread: local nodes -> pointer to row 0,
+// remote nodes -> pointer into the receive buffer
+struct DssRef {
+	const double * p;
+	double * w;        // writable alias for local members, null otherwise
+	int stride;        // doubles per row step
+};
+
+__device__ __forceinline__ DssRef tb_dss_ref(
+	const DevLayout & lay, const DssArgs & a, double * data, int m
+) {
+	DssRef r;
+	if (m < 0) {
+		r.p = 0; r.w = 0; r.stride = 0;
+	} else if (m < a.nlocal) {
+		r.w = data + tb_dss_base(lay, m);
+		r.p = r.w;
+		r.stride = lay.nn;
+	} else {
+		r.p = a.recv + (size_t)(m - a.nlocal) * a.nsel - a.sel_row0;
+		r.w = 0;
+		r.stride = 1;
+	}
+	return r;
 }
 
 __global__ void k_dss_scalar(DevLayout lay, DssArgs a, double * data) {
 	const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (gidx >= a.ngroups) return;
-	const int m0 = a.members[4 * gidx + 0];
-	const int m1 = a.members[4 * gidx + 1];
 	const int m2 = a.members[4 * gidx + 2];
 	const int m3 = a.members[4 * gidx + 3];
+	const DssRef r0 = tb_dss_ref(lay, a, data, a.members[4 * gidx + 0]);
+	const DssRef r1 = tb_dss_ref(lay, a, data, a.members[4 * gidx + 1]);
+	const DssRef r2 = tb_dss_ref(lay, a, data, m2);
+	const DssRef r3 = tb_dss_ref(lay, a, data, m3);
 	const bool seam = (a.flags[gidx] & 1) != 0;
 	for (int r = a.row0 + blockIdx.y; r < a.row1; r += gridDim.y) {
 		if (seam && r >= a.uv_row0 && r < a.uv_row1) continue;
-		const double v0 = tb_dss_load(lay, a, data, m0, r);
-		const double v1 = tb_dss_load(lay, a, data, m1, r);
+		const double v0 = r0.p[(size_t)r * r0.stride];
+		const double v1 = r1.p[(size_t)r * r1.stride];
 		double avg;
 		if (m2 < 0) {
 			avg = 0.5 * (v0 + v1);
 		} else if (m3 < 0) {
-			const double v2 = tb_dss_load(lay, a, data, m2, r);
+			const double v2 = r2.p[(size_t)r * r2.stride];
 			avg = (1.0 / 3.0) * (v0 + v1 + v2);
 		} else {
-			const double v2 = tb_dss_load(lay, a, data, m2, r);
-			const double v3 = tb_dss_load(lay, a, data, m3, r);
+			const double v2 = r2.p[(size_t)r * r2.stride];
+			const double v3 = r3.p[(size_t)r * r3.stride];
 			avg = 0.5 * (0.5 * (v0 + v1) + 0.5 * (v2 + v3));
 		}
-		const int ms[4] = {m0, m1, m2, m3};
-#pragma unroll
-		for (int q = 0; q < 4; q++) {
-			const int m = ms[q];
-			if (m >= 0 && m < a.nlocal) {
-				const int e = m / lay.nn;
-				const int n = m % lay.nn;
-				data[((size_t)e * lay.nrows + r) * lay.nn + n] = avg;
-			}
-		}
+		if (r0.w != 0) r0.w[(size_t)r * r0.stride] = avg;
+		if (r1.w != 0) r1.w[(size_t)r * r1.stride] = avg;
+		if (r2.w != 0) r2.w[(size_t)r * r2.stride] = avg;
+		if (r3.w != 0) r3.w[(size_t)r * r3.stride] = avg;
 	}
 }
 
@@ -130,10 +160,9 @@ __global__ void k_dss_seam_vector(DevLayout lay, DssArgs a, SeamArgs sa, double 
 			au = 0.5 * (0.5 * (tu[0] + tu[1]) + 0.5 * (tu[2] + tu[3]));
 			av = 0.5 * (0.5 * (tv[0] + tv[1]) + 0.5 * (tv[2] + tv[3]));
 		}
-		const int e = m / lay.nn;
-		const int n = m % lay.nn;
-		data[((size_t)e * lay.nrows + a.uv_row0 + k) * lay.nn + n] = au;
-		data[((size_t)e * lay.nrows + a.uv_row0 + sa.nlev_u + k) * lay.nn + n] = av;
+		const size_t b = tb_dss_base(lay, m);
+		data[b + (size_t)(a.uv_row0 + k) * lay.nn] = au;
+		data[b + (size_t)(a.uv_row0 + sa.nlev_u + k) * lay.nn] = av;
 	}
 }
 
@@ -150,9 +179,7 @@ __global__ void k_dss_pack(
 		const int slot = (int)(idx / nsel);
 		const int r = (int)(idx % nsel);
 		const int m = send_nodes[slot];
-		const int e = m / lay.nn;
-		const int n = m % lay.nn;
-		send[idx] = data[((size_t)e * lay.nrows + row0 + r) * lay.nn + n];
+		send[idx] = data[tb_dss_base(lay, m) + (size_t)(row0 + r) * lay.nn];
 	}
 }
 

@@ -123,14 +123,13 @@ static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double 
 		TRY(substage_from(ctx, kgu, 2, 4, 3.0 * dt / 4.0));
 	}
 
-	// hyperdiffusion, :638-641
-	TRY(tb200_copy(ctx, 4, 1, ALL));
+	// hyperdiffusion, :638-641 (the CopyData(4 -> 1) in front of it repeats the
+	// one StepAfterSubCycle starts with, HorizontalDynamicsFEM.cpp:2661)
 	TRY(tb200_h_step_after_subcycle(ctx, 4, 1, 2, dt));
 
-	// vertical step, :644-657
+	// vertical step, :644-657: CopyData(1 -> 0), StepImplicit(0, 0)
 	const double dOffCenterDeltaT = 0.5 * (1.0 + offc) * dt;
-	TRY(tb200_copy(ctx, 1, 0, ALL));
-	TRY(tb200_v_step_implicit(ctx, 0, 0, dOffCenterDeltaT));
+	TRY(tb200_copy_v_step_implicit(ctx, 1, 0, dOffCenterDeltaT));
 	const std::vector<double> oc = {(2.0 - offc) / 2.0, offc / 2.0};
 	TRY(lincomb(ctx, oc, 0));
 	if (!last) {
@@ -213,20 +212,17 @@ static int step_ars343(tb200_ctx * ctx, int first, int last, double dt) {
 	static const ARS343Coefficients k = ars343_coefficients();
 	// :161-234
 	TRY(substage_from(ctx, copy_of(0), 0, 1, k.diag_exp[0] * dt));
-	TRY(tb200_copy(ctx, 1, 2, ALL));
-	TRY(tb200_v_step_implicit(ctx, 2, 2, k.diag_imp[0] * dt));
+	TRY(tb200_copy_v_step_implicit(ctx, 1, 2, k.diag_imp[0] * dt));
 
 	TRY(substage_from(ctx, k.u2, 2, 3, k.diag_exp[1] * dt));
-	TRY(tb200_copy(ctx, 3, 4, ALL));
-	TRY(tb200_v_step_implicit(ctx, 4, 4, k.diag_imp[1] * dt));
+	TRY(tb200_copy_v_step_implicit(ctx, 3, 4, k.diag_imp[1] * dt));
 
 	TRY(substage_from(ctx, k.u3, 4, 5, k.diag_exp[2] * dt));
-	TRY(tb200_copy(ctx, 5, 6, ALL));
-	TRY(tb200_v_step_implicit(ctx, 6, 6, k.diag_imp[2] * dt));
+	TRY(tb200_copy_v_step_implicit(ctx, 5, 6, k.diag_imp[2] * dt));
 
 	TRY(substage_from(ctx, k.u4, 6, 1, k.diag_exp[3] * dt));
 
-	TRY(tb200_copy(ctx, 1, 0, ALL));
+	// (CopyData(1 -> 0) is the first thing StepAfterSubCycle does)
 	TRY(tb200_h_step_after_subcycle(ctx, 1, 0, 2, dt));
 	return 0;
 }
