@@ -63,7 +63,13 @@ enum tb200_scheme {
 	TB200_SCHEME_ARS443 = 4,       /* TimestepSchemeARS443             */
 	TB200_SCHEME_STRANG_RK4 = 5,
 	TB200_SCHEME_STRANG_SSP3 = 6,
-	TB200_SCHEME_STRANG_FE = 7
+	TB200_SCHEME_STRANG_FE = 7,
+	TB200_SCHEME_STRANG_SSPRK53 = 8,
+	TB200_SCHEME_ERK_KGU35 = 9,    /* TimestepSchemeERK (default "erk") */
+	TB200_SCHEME_ERK_FE = 10,
+	TB200_SCHEME_ERK_RK4 = 11,
+	TB200_SCHEME_ERK_SSP3 = 12,
+	TB200_SCHEME_ERK_SSPRK53 = 13
 };
 
 /*
@@ -260,6 +266,10 @@ int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst);
 
 /* TimestepScheme::Step (TimestepSchemeStrang.cpp:450-674,
  * TimestepSchemeARS343.cpp:146-235, ...): one full time step on the device. */
+/* Scheme id of a --timescheme string (TempestInitialize.h:192-291, lower case:
+ * strang[/kgu35|fe|rk4|rk3|ssprk53], erk[/...], ars222, ars232, ars343, ars443);
+ * -1 if the scheme is not implemented. */
+int tb200_scheme_from_name(const char * name);
 int tb200_scheme_instances(int scheme);
 int tb200_step(tb200_ctx * ctx, int scheme, int first_step, int last_step, double dt);
 

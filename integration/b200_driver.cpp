@@ -61,9 +61,11 @@ try {
 	model.SetEndTime(_tempestvars.timeEndTime);
 
 	STLStringHelper::ToLower(_tempestvars.strTimestepScheme);
-	const int iScheme =
-		(_tempestvars.strTimestepScheme == "ars343")
-			? TB200_SCHEME_ARS343 : TB200_SCHEME_STRANG_KGU35;
+	const int iScheme = tb200_scheme_from_name(_tempestvars.strTimestepScheme.c_str());
+	if (iScheme < 0) {
+		_EXCEPTION1("--timescheme \"%s\" is not implemented by libtempest_b200",
+			_tempestvars.strTimestepScheme.c_str());
+	}
 
 	if (strMode == "none") {
 		_TempestSetupMethodOfLines(model, _tempestvars);
@@ -73,8 +75,10 @@ try {
 			model.SetTimestepScheme(new TimestepSchemeB200(model, iScheme));
 		} else if (iScheme == TB200_SCHEME_ARS343) {
 			model.SetTimestepScheme(new TimestepSchemeARS343(model));
-		} else {
+		} else if (iScheme == TB200_SCHEME_STRANG_KGU35) {
 			model.SetTimestepScheme(new TimestepSchemeStrang(model));
+		} else {
+			_EXCEPTIONT("--mode plugins drives the reference's strang or ars343 scheme");
 		}
 		// same arguments as the "v1" branches of _TempestSetupMethodOfLines
 		// (TempestInitialize.h:296-366)

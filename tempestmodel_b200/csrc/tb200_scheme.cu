@@ -6,6 +6,10 @@
 // instances, in the same order with the same coefficients.
 //   TimestepSchemeStrang::Step   reference TimestepSchemeStrang.cpp:450-674
 //   TimestepSchemeARS343::Step   reference TimestepSchemeARS343.cpp:146-235
+//   TimestepSchemeARS222::Step   reference TimestepSchemeARS222.cpp:50-118
+//   TimestepSchemeARS232::Step   reference TimestepSchemeARS232.cpp:51-150
+//   TimestepSchemeARS443::Step   reference TimestepSchemeARS443.cpp:52-191
+//   TimestepSchemeERK::Step      reference TimestepSchemeERK.cpp:143-304
 
 #include <cstring>
 #include <cmath>
@@ -29,15 +33,46 @@
 
 static const int ALL = TB200_DATA_STATE | TB200_DATA_TRACERS;
 
+// --timescheme strings of TempestInitialize.h:192-291 (lower case)
+extern "C" int tb200_scheme_from_name(const char * name) {
+	static const struct { const char * n; int id; } tab[] = {
+		{"strang", TB200_SCHEME_STRANG_KGU35}, {"strang/kgu35", TB200_SCHEME_STRANG_KGU35},
+		{"strang/fe", TB200_SCHEME_STRANG_FE}, {"strang/rk4", TB200_SCHEME_STRANG_RK4},
+		{"strang/rk3", TB200_SCHEME_STRANG_SSP3}, {"strang/ssprk53", TB200_SCHEME_STRANG_SSPRK53},
+		{"erk", TB200_SCHEME_ERK_KGU35}, {"erk/kgu35", TB200_SCHEME_ERK_KGU35},
+		{"erk/fe", TB200_SCHEME_ERK_FE}, {"erk/rk4", TB200_SCHEME_ERK_RK4},
+		{"erk/rk3", TB200_SCHEME_ERK_SSP3}, {"erk/ssprk53", TB200_SCHEME_ERK_SSPRK53},
+		{"ars222", TB200_SCHEME_ARS222}, {"ars232", TB200_SCHEME_ARS232},
+		{"ars343", TB200_SCHEME_ARS343}, {"ars443", TB200_SCHEME_ARS443}};
+	if (name == 0) return -1;
+	for (size_t q = 0; q < sizeof(tab) / sizeof(tab[0]); q++) {
+		if (strcmp(name, tab[q].n) == 0) return tab[q].id;
+	}
+	return -1;
+}
+
 extern "C" int tb200_scheme_instances(int scheme) {
 	switch (scheme) {
 		case TB200_SCHEME_STRANG_KGU35:
 		case TB200_SCHEME_STRANG_RK4:
 		case TB200_SCHEME_STRANG_SSP3:
 		case TB200_SCHEME_STRANG_FE:
+		case TB200_SCHEME_STRANG_SSPRK53:
 			return 5;   // TimestepSchemeStrang.h:61-70
+		case TB200_SCHEME_ERK_KGU35:
+		case TB200_SCHEME_ERK_FE:
+		case TB200_SCHEME_ERK_RK4:
+		case TB200_SCHEME_ERK_SSP3:
+		case TB200_SCHEME_ERK_SSPRK53:
+			return 5;   // TimestepSchemeERK.h:61-70
 		case TB200_SCHEME_ARS343:
 			return 7;   // TimestepSchemeARS343.h:49-58
+		case TB200_SCHEME_ARS222:
+			return 4;   // TimestepSchemeARS222.h:48-57
+		case TB200_SCHEME_ARS232:
+			return 7;   // TimestepSchemeARS232.h:48-57
+		case TB200_SCHEME_ARS443:
+			return 10;  // TimestepSchemeARS443.h:48-57
 		default:
 			return -1;
 	}
@@ -112,6 +147,18 @@ static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double 
 		const std::vector<double> b = {1.0 / 3.0, 0.0, 2.0 / 3.0, 0.0, 0.0};
 		TRY(lincomb(ctx, b, 4));
 		TRY(substage(ctx, 2, 4, (2.0 / 3.0) * dt));
+
+	} else if (scheme == TB200_SCHEME_STRANG_SSPRK53) {
+		// :586-627
+		const double s1 = 0.377268915331368;
+		TRY(substage_from(ctx, copy_of(0), 0, 1, s1 * dt));
+		TRY(substage_from(ctx, copy_of(1), 1, 2, s1 * dt));
+		const std::vector<double> a = {0.355909775063327, 0.0, 0.644090224936674, 0.0};
+		TRY(substage_from(ctx, a, 2, 3, 0.242995220537396 * dt));
+		const std::vector<double> b = {0.367933791638137, 0.0, 0.0, 0.632066208361863};
+		TRY(substage_from(ctx, b, 3, 0, 0.238458932846290 * dt));
+		const std::vector<double> c = {0.762406163401431, 0.0, 0.237593836598569, 0.0, 0.0};
+		TRY(substage_from(ctx, c, 0, 4, 0.287632146308408 * dt));
 
 	} else {
 		// Kinnmark-Gray-Ullrich (3,5), :548-585
@@ -227,14 +274,195 @@ static int step_ars343(tb200_ctx * ctx, int first, int last, double dt) {
 	return 0;
 }
 
+///////////////////////////////////////////////////////////////////////////////
+// TimestepSchemeERK: explicit Runge-Kutta on the horizontal dynamics only
+// (reference TimestepSchemeERK.cpp:143-304; VerticalDynamics is never called).
+
+static int substage_h(tb200_ctx * ctx, const std::vector<double> & c, int in, int out, double dt) {
+	std::vector<double> cc(c);
+	if ((int)cc.size() <= out) cc.resize(out + 1, 0.0);
+	TRY(tb200_lincomb(ctx, cc.data(), (int)cc.size(), out, ALL));
+	TRY(tb200_h_step_explicit(ctx, in, out, dt));
+	TRY(tb200_dss(ctx, out, ALL));
+	return 0;
+}
+
+static int step_erk(tb200_ctx * ctx, int scheme, double dt) {
+	const double half = 0.5 * dt;
+	if (scheme == TB200_SCHEME_ERK_FE) {
+		TRY(substage_h(ctx, copy_of(0), 0, 4, dt));
+	} else if (scheme == TB200_SCHEME_ERK_RK4) {
+		TRY(substage_h(ctx, copy_of(0), 0, 1, half));
+		TRY(substage_h(ctx, copy_of(0), 1, 2, half));
+		TRY(substage_h(ctx, copy_of(0), 2, 3, dt));
+		const std::vector<double> rk4 = {-1.0 / 3.0, 1.0 / 3.0, 2.0 / 3.0, 1.0 / 3.0, 0.0};
+		TRY(substage_h(ctx, rk4, 3, 4, dt / 6.0));
+	} else if (scheme == TB200_SCHEME_ERK_SSP3) {
+		TRY(substage_h(ctx, copy_of(0), 0, 1, dt));
+		const std::vector<double> a = {3.0 / 4.0, 1.0 / 4.0, 0.0};
+		TRY(substage_h(ctx, a, 1, 2, 0.25 * dt));
+		const std::vector<double> b = {1.0 / 3.0, 0.0, 2.0 / 3.0, 0.0, 0.0};
+		TRY(substage_h(ctx, b, 2, 4, (2.0 / 3.0) * dt));
+	} else if (scheme == TB200_SCHEME_ERK_KGU35) {
+		TRY(substage_h(ctx, copy_of(0), 0, 1, dt / 5.0));
+		TRY(substage_h(ctx, copy_of(0), 1, 2, dt / 5.0));
+		TRY(substage_h(ctx, copy_of(0), 2, 3, dt / 3.0));
+		TRY(substage_h(ctx, copy_of(0), 3, 2, 2.0 * dt / 3.0));
+		const std::vector<double> kgu = {-1.0 / 4.0, 5.0 / 4.0, 0.0, 0.0, 0.0};
+		TRY(substage_h(ctx, kgu, 2, 4, 3.0 * dt / 4.0));
+	} else {
+		const double s1 = 0.377268915331368;
+		TRY(substage_h(ctx, copy_of(0), 0, 1, s1 * dt));
+		TRY(substage_h(ctx, copy_of(1), 1, 2, s1 * dt));
+		const std::vector<double> a = {0.355909775063327, 0.0, 0.644090224936674, 0.0};
+		TRY(substage_h(ctx, a, 2, 3, 0.242995220537396 * dt));
+		const std::vector<double> b = {0.367933791638137, 0.0, 0.0, 0.632066208361863};
+		TRY(substage_h(ctx, b, 3, 0, 0.238458932846290 * dt));
+		const std::vector<double> c = {0.762406163401431, 0.0, 0.237593836598569, 0.0, 0.0};
+		TRY(substage_h(ctx, c, 0, 4, 0.287632146308408 * dt));
+	}
+	// :300-303 (the CopyData(4 -> 0) repeats the one StepAfterSubCycle starts with)
+	TRY(tb200_h_step_after_subcycle(ctx, 4, 0, 2, dt));
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// ARS(2,2,2), ARS(2,3,2), ARS(4,4,3) of Ascher, Ruuth & Spiteri (1997).  The
+// stage combinations are the reference's m_du?fCombo vectors
+// (TimestepSchemeARS222.cpp:67-72, ARS232.cpp:68-86, ARS443.cpp:70-108).
+
+// raw[r][.]: combination that forms the base of explicit stage r + 1 from
+// u^n (instance 0) and the explicit / implicit results of the earlier stages
+static void ars_combo(
+	const double * E, const double * I, int ns, int r, std::vector<double> & c, int len
+) {
+	c.assign(len, 0.0);
+	c[0] = 1.0 - E[r * ns + 0] / E[0];
+	c[1] = E[r * ns + 0] / E[0] - I[r * ns + 0] / I[0];
+	c[2] = I[r * ns + 0] / I[0];
+	for (int j = 1; j < r; j++) {
+		c[2 * j + 1] = E[r * ns + j] / E[j * ns + j] - I[r * ns + j] / I[j * ns + j];
+		c[2 * j + 2] = I[r * ns + j] / I[j * ns + j];
+	}
+}
+
+// CopyData(State only) + StepImplicit + DSS, as ARS222 / ARS443 issue them
+// (the reference copies the State twice and never the Tracers, ARS222.cpp:88-89)
+static int implicit_stage_dss(tb200_ctx * ctx, int src, int dst, double dt) {
+	if (ctx->lay.ntr == 0) {
+		TRY(tb200_copy_v_step_implicit(ctx, src, dst, dt));
+	} else {
+		TRY(tb200_copy(ctx, src, dst, TB200_DATA_STATE));
+		TRY(tb200_v_step_implicit(ctx, dst, dst, dt));
+	}
+	TRY(tb200_dss(ctx, dst, ALL));
+	return 0;
+}
+
+static int step_ars222(tb200_ctx * ctx, double dt) {
+	const double gam = 1.0 - 0.5 * std::sqrt(2.0);
+	const double del = 1.0 - 1.0 / (2.0 * gam);
+	const double I[4] = {gam, 0.0, 1.0 - gam, gam};
+	const double E[4] = {gam, 0.0, del, 1.0 - del};
+	std::vector<double> u2;
+	ars_combo(E, I, 2, 1, u2, 4);
+	// stage 1 (:75-93)
+	TRY(substage_from(ctx, copy_of(0), 0, 1, E[0] * dt));
+	TRY(implicit_stage_dss(ctx, 1, 2, I[0] * dt));
+	// stage 2 (:96-110)
+	TRY(substage_from(ctx, u2, 2, 3, E[3] * dt));
+	TRY(tb200_v_step_implicit(ctx, 3, 3, I[3] * dt));
+	TRY(tb200_dss(ctx, 3, ALL));
+	// hyperdiffusion (:113-117)
+	TRY(tb200_copy(ctx, 3, 2, ALL));
+	TRY(tb200_h_step_after_subcycle(ctx, 2, 1, 3, dt));
+	TRY(tb200_copy(ctx, 1, 0, ALL));
+	return 0;
+}
+
+static int step_ars232(tb200_ctx * ctx, double dt) {
+	const double gam = 1.0 - 1.0 / std::sqrt(2.0);
+	const double del = -(2.0 * std::sqrt(2.0)) / 3.0;
+	const double I[9] = {gam, 0., 0., 1.0 - gam, gam, 0., 1.0 - gam, gam, 0.};
+	const double E[9] = {gam, 0., 0., del, 1.0 - del, 0., 0., 1.0 - gam, gam};
+	std::vector<double> u2, u3;
+	ars_combo(E, I, 3, 1, u2, 6);
+	ars_combo(E, I, 3, 2, u3, 7);
+	u3[5] = -E[2 * 3 + 1] / E[1 * 3 + 1];     // :85
+	// stage 1 (:89-105)
+	TRY(substage_from(ctx, copy_of(0), 0, 1, E[0] * dt));
+	TRY(tb200_copy_v_step_implicit(ctx, 1, 2, I[0] * dt));
+	// stage 2 (:108-126): the combination is kept in instance 5
+	TRY(tb200_lincomb(ctx, u2.data(), (int)u2.size(), 5, ALL));
+	TRY(substage_from(ctx, copy_of(5), 2, 3, E[4] * dt));
+	TRY(tb200_copy_v_step_implicit(ctx, 3, 4, I[4] * dt));
+	// stage 3 (:129-137)
+	TRY(substage_from(ctx, u3, 4, 6, E[8] * dt));
+	// hyperdiffusion (:146-150)
+	TRY(tb200_copy(ctx, 6, 2, ALL));
+	TRY(tb200_h_step_after_subcycle(ctx, 2, 1, 6, dt));
+	TRY(tb200_copy(ctx, 1, 0, ALL));
+	return 0;
+}
+
+static int step_ars443(tb200_ctx * ctx, double dt) {
+	const double I[16] = {
+		1. / 2., 0., 0., 0.,
+		1. / 6., 1. / 2., 0., 0.,
+		-1. / 2., 1. / 2., 1. / 2., 0.,
+		3. / 2., -3. / 2., 1. / 2., 1. / 2.};
+	const double E[16] = {
+		1. / 2., 0., 0., 0.,
+		11. / 18., 1. / 18., 0., 0.,
+		5. / 6., -5. / 6., 1. / 2., 0.,
+		1. / 4., 7. / 4., 3. / 4., -7. / 4.};
+	std::vector<double> u2, u3, u4;
+	ars_combo(E, I, 4, 1, u2, 8);
+	ars_combo(E, I, 4, 2, u3, 9);
+	ars_combo(E, I, 4, 3, u4, 10);
+	u3[7] = -E[2 * 4 + 1] / E[1 * 4 + 1];     // :88
+	u4[7] = -E[3 * 4 + 1] / E[1 * 4 + 1];     // :104
+	u4[8] = -E[3 * 4 + 2] / E[2 * 4 + 2];     // :105
+	// stage 1 (:111-127)
+	TRY(substage_from(ctx, copy_of(0), 0, 1, E[0] * dt));
+	TRY(implicit_stage_dss(ctx, 1, 2, I[0] * dt));
+	// stage 2 (:130-148): combination kept in instance 7
+	TRY(tb200_lincomb(ctx, u2.data(), (int)u2.size(), 7, ALL));
+	TRY(substage_from(ctx, copy_of(7), 2, 3, E[5] * dt));
+	TRY(implicit_stage_dss(ctx, 3, 4, I[5] * dt));
+	// stage 3 (:151-169): combination kept in instance 8
+	TRY(tb200_lincomb(ctx, u3.data(), (int)u3.size(), 8, ALL));
+	TRY(substage_from(ctx, copy_of(8), 4, 5, E[10] * dt));
+	TRY(implicit_stage_dss(ctx, 5, 6, I[10] * dt));
+	// stage 4 (:172-185)
+	TRY(substage_from(ctx, u4, 6, 9, E[15] * dt));
+	TRY(tb200_v_step_implicit(ctx, 9, 9, I[15] * dt));
+	TRY(tb200_dss(ctx, 9, ALL));
+	// hyperdiffusion (:187-191)
+	TRY(tb200_copy(ctx, 9, 2, ALL));
+	TRY(tb200_h_step_after_subcycle(ctx, 2, 1, 9, dt));
+	TRY(tb200_copy(ctx, 1, 0, ALL));
+	return 0;
+}
+
 extern "C" int tb200_step(tb200_ctx * ctx, int scheme, int first, int last, double dt) {
 	const int need = tb200_scheme_instances(scheme);
 	if (need < 0) TB_FAIL(ctx, "time scheme not implemented");
 	if ((int)ctx->inst.size() < need) TB_FAIL(ctx, "not enough state instances for this scheme");
-	if (scheme == TB200_SCHEME_ARS343) {
-		return step_ars343(ctx, first, last, dt);
+	switch (scheme) {
+		case TB200_SCHEME_ARS343: return step_ars343(ctx, first, last, dt);
+		case TB200_SCHEME_ARS222: return step_ars222(ctx, dt);
+		case TB200_SCHEME_ARS232: return step_ars232(ctx, dt);
+		case TB200_SCHEME_ARS443: return step_ars443(ctx, dt);
+		case TB200_SCHEME_ERK_KGU35:
+		case TB200_SCHEME_ERK_FE:
+		case TB200_SCHEME_ERK_RK4:
+		case TB200_SCHEME_ERK_SSP3:
+		case TB200_SCHEME_ERK_SSPRK53:
+			return step_erk(ctx, scheme, dt);
+		default:
+			return step_strang(ctx, scheme, first, last, dt);
 	}
-	return step_strang(ctx, scheme, first, last, dt);
 }
 
 ///////////////////////////////////////////////////////////////////////////////

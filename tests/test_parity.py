@@ -108,6 +108,24 @@ def test_shallow_water_steps(library):
     ctx.close()
 
 
+@pytest.mark.parametrize("scheme", ["erk", "erk/rk4", "erk/rk3", "erk/ssprk53", "erk/fe"])
+def test_shallow_water_erk_steps(library, scheme):
+    """TimestepSchemeERK (horizontal dynamics only), two steps."""
+    d = cases.load_case("sw2_ne2_%s" % scheme.replace("/", "_"))
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step(scheme, True, False, 200.0)
+    ctx.step(scheme, False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2]), TOL_STATE)
+    cs = ctx.checksum(0)
+    assert np.allclose(cs, d["cs.checksum"], rtol=1e-12,
+                       atol=1e-12 * np.abs(d["cs.checksum"]).max())
+    ctx.close()
+
+
 def test_nonhydro_stages(library):
     d = cases.load_case("jw_ne2_l6")
     ctx = dumpctx.context_from_dump(d, library=library)
@@ -151,9 +169,10 @@ def test_nonhydro_stages(library):
     ctx.close()
 
 
-@pytest.mark.parametrize("scheme", ["strang", "ars343"])
+@pytest.mark.parametrize("scheme", ["strang", "ars343", "ars222", "ars232", "ars443",
+                                    "strang/ssprk53", "strang/rk4", "strang/rk3"])
 def test_nonhydro_steps(library, scheme):
-    d = cases.load_case("jw_ne2_l6_%s" % scheme)
+    d = cases.load_case("jw_ne2_l6_%s" % scheme.replace("/", "_"))
     ctx = dumpctx.context_from_dump(d, library=library)
     dumpctx.upload_tag(ctx, d, "ic")
     for m in range(1, ctx.cfg.ninstances):
