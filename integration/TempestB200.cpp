@@ -9,6 +9,7 @@
 #include "TempestB200.h"
 
 #include "GridCSGLL.h"
+#include "GridCartesianGLL.h"
 #include "CubedSphereTrans.h"
 #include "EquationSet.h"
 #include "PhysicalConstants.h"
@@ -87,8 +88,21 @@ void B200Bridge::Initialize() {
 		_EXCEPTIONT("tempest_b200 requires a GridGLL");
 	}
 	GridCSGLL * pGridCS = dynamic_cast<GridCSGLL *>(pGrid);
-	if (pGridCS == NULL) {
-		_EXCEPTIONT("tempest_b200: only the cubed-sphere grid is bound so far");
+	GridCartesianGLL * pGridCart = dynamic_cast<GridCartesianGLL *>(pGrid);
+	if ((pGridCS == NULL) && (pGridCart == NULL)) {
+		_EXCEPTIONT("tempest_b200: GridCSGLL or GridCartesianGLL expected");
+	}
+	if (pGridCart != NULL) {
+		// GridPatchCartesianGLL::ApplyBoundaryConditions (no-flux / no-slip
+		// walls) is not implemented on the device
+		for (int d = 0; d < 4; d++) {
+			if (pGrid->GetBoundaryCondition((Direction)d) !=
+			    Grid::BoundaryCondition_Periodic
+			) {
+				_EXCEPTIONT("tempest_b200: only periodic Cartesian boundaries "
+					"are implemented");
+			}
+		}
 	}
 	const EquationSet & eqn = m_model.GetEquationSet();
 	const PhysicalConstants & phys = m_model.GetPhysicalConstants();
@@ -232,7 +246,21 @@ void B200Bridge::Initialize() {
 		std::vector<int> vecIa, vecIb, vecSrc;
 		std::vector<double> vecM;
 		const long m = 2 * nLattice + 1;
-		for (int i = 0; i < nWA; i++) {
+		if (pGridCart != NULL) {
+			// periodic global node index: duplicates across element edges,
+			// patch edges and the periodic boundaries share one id
+			// (GridCartesianGLL.cpp:380-432)
+			const long nUA = (long)(np - 1) * pGrid->GetABaseResolution();
+			const long nUB = (long)(np - 1) * pGrid->GetBBaseResolution();
+			for (int i = 0; i < nWA; i++) {
+			for (int j = 0; j < nWB; j++) {
+				const long uA = UniqueIndex(gA0 + i, np) % nUA;
+				const long uB = UniqueIndex(gB0 + j, np) % nUB;
+				vecIds[(size_t)i * nWB + j] = uA * nUB + uB;
+			}
+			}
+		}
+		for (int i = 0; (pGridCart == NULL) && (i < nWA); i++) {
 		for (int j = 0; j < nWB; j++) {
 			const long s = 2 * UniqueIndex(gA0 + i, np) - nLattice;
 			const long t = 2 * UniqueIndex(gB0 + j, np) - nLattice;

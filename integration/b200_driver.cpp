@@ -19,9 +19,13 @@
 #define main BaroclinicWaveJW_reference_main
 #include "nonhydro_sphere/BaroclinicWaveJWTest.cpp"
 #undef main
+#define main ThermalBubble_reference_main
+#include "nonhydro_xz/ThermalBubbleCartesianTest.cpp"
+#undef main
 
 #include "TempestB200.h"
 #include "GridCSGLL.h"
+#include "GridCartesianGLL.h"
 #include "VerticalDynamicsStub.h"
 
 int main(int argc, char ** argv) {
@@ -37,6 +41,7 @@ try {
 
 	BeginTempestCommandLine("B200Driver");
 		SetDefaultResolution(8);
+		SetDefaultResolutionY(1);
 		SetDefaultLevels(10);
 		SetDefaultOutputDeltaT("200s");
 		SetDefaultDeltaT("200s");
@@ -112,23 +117,52 @@ try {
 		}
 	}
 
-	// _TempestSetupCubedSphereModel (TempestInitialize.h:476-586)
-	GridCSGLL * pGrid = new GridCSGLL(model);
-	pGrid->DefineParameters();
-	pGrid->SetParameters(
-		_tempestvars.nLevels,
-		nPatch,
-		_tempestvars.nResolutionX,
-		4,
-		_tempestvars.nHorizontalOrder,
-		_tempestvars.nVerticalOrder,
-		Grid::VerticalDiscretization_FiniteElement,
-		Grid::VerticalStaggering_Lorenz);
-	pGrid->InitializeDataLocal();
-	model.SetGrid(pGrid, nPatch);
+	ThermalBubbleCartesianTest * pBubble = NULL;
+	if (strCase == "bubble") {
+		// _TempestSetupCartesianModel (TempestInitialize.h:590-706), x-z slice
+		pBubble = new ThermalBubbleCartesianTest(
+			300.0, 0.5, 250.0, 500.0, 350.0, 3.14159265);
+		GridCartesianGLL * pGrid = new GridCartesianGLL(model);
+		pGrid->DefineParameters();
+		pGrid->SetParameters(
+			_tempestvars.nLevels,
+			1,
+			_tempestvars.nResolutionX,
+			_tempestvars.nResolutionY,
+			4,
+			_tempestvars.nHorizontalOrder,
+			_tempestvars.nVerticalOrder,
+			pBubble->m_dGDim,
+			0.0,
+			pBubble->m_iLatBC,
+			true,
+			Grid::VerticalDiscretization_FiniteElement,
+			Grid::VerticalStaggering_Lorenz);
+		pGrid->InitializeDataLocal();
+		model.SetGrid(pGrid);
+		const double XL = std::abs(pBubble->m_dGDim[1] - pBubble->m_dGDim[0]);
+		pGrid->SetReferenceLength((XL < 110000.0) ? XL : 110000.0);
+	} else {
+		// _TempestSetupCubedSphereModel (TempestInitialize.h:476-586)
+		GridCSGLL * pGrid = new GridCSGLL(model);
+		pGrid->DefineParameters();
+		pGrid->SetParameters(
+			_tempestvars.nLevels,
+			nPatch,
+			_tempestvars.nResolutionX,
+			4,
+			_tempestvars.nHorizontalOrder,
+			_tempestvars.nVerticalOrder,
+			Grid::VerticalDiscretization_FiniteElement,
+			Grid::VerticalStaggering_Lorenz);
+		pGrid->InitializeDataLocal();
+		model.SetGrid(pGrid, nPatch);
+	}
 	_TempestSetupOutputManagers(model, _tempestvars);
 
-	if (fSW) {
+	if (pBubble != NULL) {
+		model.SetTestCase(pBubble);
+	} else if (fSW) {
 		model.SetTestCase(new ShallowWaterTestCase2(2998.104995, 38.61068277, 0.0));
 	} else {
 		STLStringHelper::ToLower(strPert);

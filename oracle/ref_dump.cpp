@@ -202,7 +202,8 @@ static void DumpGeometry(Model & model) {
 		WriteScalarI(P(n, "b_global_begin"), box.GetBGlobalInteriorBegin());
 		WriteScalarD(P(n, "delta_a"), pPatch->GetElementDeltaA());
 		WriteScalarD(P(n, "delta_b"), pPatch->GetElementDeltaB());
-		{
+		const bool fCartesian = (dynamic_cast<GridCartesianGLL*>(pGrid) != NULL);
+		if (!fCartesian) {
 			DataArray1D<int> nb(8);
 			for (int d = 0; d < 8; d++) {
 				nb[d] = pPatch->GetNeighborPanel((Direction)d);
@@ -211,7 +212,7 @@ static void DumpGeometry(Model & model) {
 		}
 		Write1D(P(n, "anode"), pPatch->GetANodes());
 		Write1D(P(n, "bnode"), pPatch->GetBNodes());
-		{
+		if (!fCartesian) {
 			// m_dXNode / m_dYNode (GridPatchCSGLL.cpp:205-213) are protected:
 			// same expression, same libm
 			DataArray1D<double> dX(pPatch->GetANodes().GetRows());
@@ -422,6 +423,7 @@ try {
 
 	BeginTempestCommandLine("RefDump");
 		SetDefaultResolution(4);
+		SetDefaultResolutionY(1);
 		SetDefaultLevels(1);
 		SetDefaultOutputDeltaT("200s");
 		SetDefaultDeltaT("200s");

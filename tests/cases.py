@@ -41,6 +41,24 @@ CASES = {
         script="addw:0,20000;dss:0;dump:ic,0;step:2;dump:st,0;checksum:cs"),
 }
 
+# nonhydrostatic Cartesian x-z slice, rising thermal bubble (SURVEY 8c config 2,
+# reduced): periodic GridCartesianGLL, one element across y
+CASES["bubble_r6_l8"] = dict(
+    case="bubble", npatch=1,
+    flags=["--resolution", "6", "--resy", "1", "--levels", "8", "--dt", "10000u",
+           "--nu", "1e4", "--nud", "1e4", "--nuv", "1e4"],
+    script=";".join([
+        "addw:0,100", "dss:0",
+        "dump:ic,0", "copy:0,1", "hexp:0,1,0.01", "dump:h1,1", "vexp:0,1,0.01",
+        "dump:v1,1", "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,0.01",
+        "dump:vi,2", "hasc:1,3,4,0.01", "dump:hasc,3,4"]))
+CASES["bubble_r6_l8_strang"] = dict(
+    case="bubble", npatch=1,
+    flags=["--resolution", "6", "--resy", "1", "--levels", "8", "--dt", "10000u",
+           "--nu", "1e4", "--nud", "1e4", "--nuv", "1e4"],
+    script="addw:0,100;dss:0;dump:ic,0;step:3;dump:st,0;checksum:cs",
+    geometry_from="bubble_r6_l8")
+
 # more time schemes on the same grid and initial state: only the run records are
 # stored, the geometry comes from the strang case (same flags)
 for _scheme in ("ars222", "ars232", "ars443", "strang/ssprk53", "strang/rk4", "strang/rk3"):
@@ -77,12 +95,14 @@ def load_case(name):
     if not refdump.have_ref_dump():
         raise FileNotFoundError("golden file %s missing and oracle/_ref/ref_dump not built" % path)
     c = CASES[name]
-    return refdump.run_ref_dump("/tmp/tb200_%s.bin" % name, c["case"], c["script"], c["flags"])
+    return refdump.run_ref_dump("/tmp/tb200_%s.bin" % name, c["case"], c["script"], c["flags"],
+                                npatch=c.get("npatch", 6))
 
 
 def write_golden(name):
     c = CASES[name]
-    d = refdump.run_ref_dump("/tmp/tb200_%s.bin" % name, c["case"], c["script"], c["flags"])
+    d = refdump.run_ref_dump("/tmp/tb200_%s.bin" % name, c["case"], c["script"], c["flags"],
+                             npatch=c.get("npatch", 6))
     os.makedirs(GOLDEN, exist_ok=True)
     if c.get("geometry_from") is not None:
         base = load_case(c["geometry_from"])

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 import refdump
-from tempestmodel_b200 import DeviceContext, cubedsphere
+from tempestmodel_b200 import DeviceContext, cartesian as cartgrid, cubedsphere
 from tempestmodel_b200._lib import OP_NAMES
 
 EMU_LIBRARY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu",
@@ -103,11 +103,23 @@ def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
                 ia, ib, sp, m = cubedsphere.seam_transforms(
                     S(d, p + "panel"), nea, neb, ea0, eb0, ne, np_, an, bn)
                 ctx.set_seam_transforms(idx, ia, ib, sp, m)
-    if (analytic_metric and not cartesian and eqn == 2 and "patch0.xnode" in d):
+    if cartesian:
+        # one row of patches along alpha (GridCartesianGLL.cpp:146-229)
+        ne_a = sum(S(d, "patch%d.nelem_a" % n) for n in range(npatch))
+        ne_b = S(d, "patch0.nelem_b")
+        for n in range(npatch):
+            p = "patch%d." % n
+            ctx.set_node_ids(S(d, p + "index"), cartgrid.node_ids(
+                S(d, p + "nelem_a"), S(d, p + "nelem_b"),
+                S(d, p + "a_global_begin") // np_, S(d, p + "b_global_begin") // np_,
+                ne_a, ne_b, np_))
+    if (analytic_metric and eqn == 2 and ("patch0.xnode" in d or cartesian)):
         for n in range(npatch):
             if owners[n] == rank:
                 p = "patch%d." % n
-                ctx.set_terrain_metric(S(d, p + "index"), d[p + "xnode"], d[p + "ynode"],
+                xn = d[p + "xnode"] if not cartesian else d[p + "anode"]
+                yn = d[p + "ynode"] if not cartesian else d[p + "bnode"]
+                ctx.set_terrain_metric(S(d, p + "index"), xn, yn,
                                        d[p + "topographyderiv"])
         ctx.set_vertical_coordinate(d["grid.retalevels"], d["grid.retainterfaces"])
     ctx.build_connectivity()

@@ -305,3 +305,47 @@ def test_fused_hyperdiffusion_equals_general_kernels(library, monkeypatch):
                 g = res["generic"][inst][n][loc]
                 for c in range(a.shape[0]):
                     assert np.abs(a[c] - g[c]).max() <= 1e-12 * max(np.abs(g[c]).max(), 1e-300)
+
+
+def test_cartesian_bubble_stages(library):
+    """Config 2 (reduced): periodic Cartesian x-z slice with one element across
+    y (GridCartesianGLL; the DSS averages the two y-edges of the same element),
+    HEVI stages against the reference."""
+    d = cases.load_case("bubble_r6_l8")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert ctx.fast_path()[0], ctx.fast_path()
+    dumpctx.upload_tag(ctx, d, "ic")
+    assert_below(dumpctx.compare(ctx, d, 0, "ic", [0, 1, 2, 4], [3]), 0.0)
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 0.01)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 2, 4], [3]), TOL_STAGE)
+    ctx.v_step_explicit(0, 1, 0.01)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 2, 4], [3]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 0.01)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3]), TOL_IMPLICIT)
+    ctx.h_step_after_subcycle(1, 3, 4, 0.01)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    assert_below(dumpctx.compare(ctx, d, 4, "hasc", [0, 2, 4], [3]), 1e-11)
+    ctx.close()
+
+
+def test_cartesian_bubble_steps(library):
+    d = cases.load_case("bubble_r6_l8_strang")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 0.01)
+    ctx.step("strang", False, False, 0.01)
+    ctx.step("strang", False, False, 0.01)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 2, 4], [3]), TOL_STATE)
+    cs = ctx.checksum(0)
+    ref = d["cs.checksum"]
+    assert abs(cs[4] - ref[4]) <= 1e-13 * abs(ref[4])
+    assert abs(cs[2] - ref[2]) <= 1e-13 * abs(ref[2])
+    ctx.close()
