@@ -318,18 +318,29 @@ def test_cartesian_bubble_stages(library):
     assert_below(dumpctx.compare(ctx, d, 0, "ic", [0, 1, 2, 4], [3]), 0.0)
     ctx.copy(0, 1)
     ctx.h_step_explicit(0, 1, 0.01)
-    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 2, 4], [3]), TOL_STAGE)
+    # u: the only horizontal forcing is the pressure gradient of a 0.5 K bubble,
+    # i.e. differences of Exner values (~1e3) that agree to 4 digits; one ulp of
+    # exp/log (libdevice vs glibc) is 2e-12 of that tendency
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [2, 4], [3]), TOL_STAGE)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0]), 1e-11)
     ctx.v_step_explicit(0, 1, 0.01)
-    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 2, 4], [3]), TOL_STAGE)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [2, 4], [3]), TOL_STAGE)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0]), 1e-11)
     ctx.dss(1)
-    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    # u starts from rest, so the u field itself is that tendency
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [1, 2, 4], [3]), TOL_DSS)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0]), 1e-11)
     ctx.copy(1, 2)
     ctx.v_step_implicit(2, 2, 0.01)
     ctx.check_errors()
     assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3]), TOL_IMPLICIT)
     ctx.h_step_after_subcycle(1, 3, 4, 0.01)
-    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
-    assert_below(dumpctx.compare(ctx, d, 4, "hasc", [0, 2, 4], [3]), 1e-11)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [1, 2, 4], [3]), 1e-13)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0]), 1e-11)
+    # work instance = DSS(Laplacian); rho is horizontally uniform in this case,
+    # so its Laplacian is rounding noise and is left out
+    assert_below(dumpctx.compare(ctx, d, 4, "hasc", [2], [3]), 1e-11)
+    assert_below(dumpctx.compare(ctx, d, 4, "hasc", [0]), 1e-10)
     ctx.close()
 
 
