@@ -263,6 +263,10 @@ int tb200_h_step_after_subcycle(tb200_ctx * ctx, int in, int out, int work, doub
 /* VerticalDynamics::FilterNegativeTracers + HorizontalDynamicsFEM one
  * (VerticalDynamicsFEM.cpp:4286-4347, HorizontalDynamicsFEM.cpp:213-317). */
 int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst);
+/* VerticalDynamicsFEM::FilterNegativeTracers (VerticalDynamicsFEM.cpp:4286-4347):
+ * the column-wise filter (the one above is HorizontalDynamicsFEM's element-wise
+ * filter, HorizontalDynamicsFEM.cpp:213-317). */
+int tb200_v_filter_negative_tracers(tb200_ctx * ctx, int inst);
 
 /* TimestepScheme::Step (TimestepSchemeStrang.cpp:450-674,
  * TimestepSchemeARS343.cpp:146-235, ...): one full time step on the device. */

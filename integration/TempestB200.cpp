@@ -441,6 +441,16 @@ void VerticalDynamicsB200::StepImplicit(
 	b.Download(iDataUpdate);
 }
 
+void VerticalDynamicsB200::FilterNegativeTracers(int iDataUpdate) {
+	if (m_model.GetEquationSet().GetTracers() == 0) {
+		return;
+	}
+	B200Bridge & b = B200Bridge::Get(m_model);
+	b.Upload(iDataUpdate);
+	b.Check(tb200_v_filter_negative_tracers(b.Ctx(), iDataUpdate));
+	b.Download(iDataUpdate);
+}
+
 ///////////////////////////////////////////////////////////////////////////////
 // TimestepSchemeB200
 

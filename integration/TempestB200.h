@@ -119,6 +119,10 @@ public:
 	virtual void Initialize();
 	virtual void StepExplicit(int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT);
 	virtual void StepImplicit(int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT);
+	///	<summary>
+	///		Column-wise positive-definite filter (VerticalDynamics.h:123).
+	///	</summary>
+	virtual void FilterNegativeTracers(int iDataUpdate);
 };
 
 class TimestepSchemeB200 : public TimestepScheme {

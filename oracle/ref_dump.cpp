@@ -56,6 +56,57 @@
 
 ///////////////////////////////////////////////////////////////////////////////
 
+///	<summary>
+///		Test data: the reference's Jablonowski-Williamson case carrying
+///		analytic tracer densities (a smooth field and two narrow cosine bells
+///		with zero background, which the transport drives negative so that the
+///		positive-definite filters act).
+///	</summary>
+class JWTracerTest : public BaroclinicWaveJWTest {
+public:
+	JWTracerTest(
+		double dAlpha, double dZtop, PerturbationType ePert, int nTracers
+	) :
+		BaroclinicWaveJWTest(dAlpha, dZtop, ePert),
+		m_nTracers(nTracers)
+	{ }
+
+	virtual void EvaluatePointwiseState(
+		const PhysicalConstants & phys,
+		const Time & time,
+		double dZ, double dLon, double dLat,
+		double * dState, double * dTracer
+	) const {
+		BaroclinicWaveJWTest::EvaluatePointwiseState(
+			phys, time, dZ, dLon, dLat, dState, dTracer);
+		const double dRho = dState[4];
+		for (int c = 0; c < m_nTracers; c++) {
+			double dQ;
+			if (c == 0) {
+				dQ = 1.0e-3 * (2.0 + sin(dLon) * cos(dLat))
+					* exp(- dZ / 8000.0);
+			} else {
+				// cosine bell centred at (lon0, lat0, z0)
+				const double dLon0 = 0.5 + 1.7 * c;
+				const double dLat0 = 0.6 - 0.5 * c;
+				const double dZ0 = 4000.0 + 3000.0 * c;
+				const double dR = acos(
+					sin(dLat0) * sin(dLat)
+					+ cos(dLat0) * cos(dLat) * cos(dLon - dLon0));
+				const double dRz = fabs(dZ - dZ0) / 6000.0;
+				const double dD = sqrt(dR * dR / (0.9 * 0.9) + dRz * dRz);
+				dQ = (dD < 1.0) ? 0.5e-2 * (1.0 + cos(M_PI * dD)) : 0.0;
+			}
+			dTracer[c] = dRho * dQ;
+		}
+	}
+
+private:
+	int m_nTracers;
+};
+
+///////////////////////////////////////////////////////////////////////////////
+
 static FILE * g_fp = NULL;
 
 static void WriteRecord(
@@ -420,6 +471,7 @@ try {
 	double dZtop;
 	std::string strPert;
 	double dU0, dH0, dAlpha;
+	int nTracers;
 
 	BeginTempestCommandLine("RefDump");
 		SetDefaultResolution(4);
@@ -440,6 +492,7 @@ try {
 		CommandLineDouble(dU0, "u0", 38.61068277);
 		CommandLineDouble(dH0, "h0", 2998.104995);
 		CommandLineDouble(dAlpha, "alpha", 0.0);
+		CommandLineInt(nTracers, "ntracers", 0);
 
 		ParseCommandLine(argc, argv);
 	EndTempestCommandLine(argv)
@@ -457,13 +510,25 @@ try {
 		pModel = new Model(EquationSet::ShallowWaterEquations);
 		pTest = new ShallowWaterTestCase2(dH0, dU0, dAlpha);
 	} else if (strCase == "jw") {
-		pModel = new Model(EquationSet::PrimitiveNonhydrostaticEquations);
 		STLStringHelper::ToLower(strPert);
-		pTest = new BaroclinicWaveJWTest(
-			dAlpha, dZtop,
+		const BaroclinicWaveJWTest::PerturbationType ePert =
 			(strPert == "exp") ?
 				BaroclinicWaveJWTest::PerturbationType_Exp :
-				BaroclinicWaveJWTest::PerturbationType_None);
+				BaroclinicWaveJWTest::PerturbationType_None;
+		if (nTracers > 0) {
+			EquationSet eqn(EquationSet::PrimitiveNonhydrostaticEquations);
+			for (int c = 0; c < nTracers; c++) {
+				char szName[16];
+				snprintf(szName, 16, "RhoQ%d", c);
+				eqn.InsertTracer(szName, szName);
+			}
+			UserDataMeta metaUserData;
+			pModel = new Model(eqn, metaUserData);
+			pTest = new JWTracerTest(dAlpha, dZtop, ePert, nTracers);
+		} else {
+			pModel = new Model(EquationSet::PrimitiveNonhydrostaticEquations);
+			pTest = new BaroclinicWaveJWTest(dAlpha, dZtop, ePert);
+		}
 	} else if (strCase == "bubble") {
 		pModel = new Model(EquationSet::PrimitiveNonhydrostaticEquations);
 		pTest = new ThermalBubbleCartesianTest(

@@ -105,6 +105,7 @@ _SIGNATURES = {
     "tb200_h_step_after_subcycle": (c_int, [c_void_p, c_int, c_int, c_int,
                                             c_double]),
     "tb200_filter_negative_tracers": (c_int, [c_void_p, c_int]),
+    "tb200_v_filter_negative_tracers": (c_int, [c_void_p, c_int]),
     "tb200_scheme_instances": (c_int, [c_int]),
     "tb200_scheme_from_name": (c_int, [c_char_p]),
     "tb200_step": (c_int, [c_void_p, c_int, c_int, c_int, c_double]),

@@ -17,6 +17,7 @@
 #include "tb200_column.cuh"
 #include "tb200_fast.cuh"
 #include "tb200_column_fast.cuh"
+#include "tb200_tracers.cuh"
 
 #define TB_CHECK(ctx, call) \
 	do { \
@@ -1162,12 +1163,64 @@ extern "C" int tb200_hv_step_explicit_combine(
 	return nh_launch(ctx, in, out, dt, true, true, sb);
 }
 
+static int column_solve(tb200_ctx * ctx, int in, int out, double dt);
+static int column_tracers(tb200_ctx * ctx, int in, int out, double dt);
+
 extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt) {
 	if (check_inst2(ctx, in, out)) return 1;
 	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || ctx->lay.nlev == 1) return 0;
 	if (ctx->cfg.fully_explicit) return 0;   // VerticalDynamicsFEM.cpp:1240-1242
 	if (check_ops(ctx)) return 1;
-	if (ctx->lay.ntr > 0) TB_FAIL(ctx, "implicit tracer transport is not implemented yet");
+	const DevLayout & lay = ctx->lay;
+	if (lay.ntr > 0) {
+		// w before the solve is needed by the tracer update (the solve may run
+		// in place): keep a copy [e][L+1][NN]
+		const size_t wrow = (size_t)(lay.nlev + 1) * lay.nn;
+		if (ctx->d_wold == 0) {
+			if (dalloc(ctx, &ctx->d_wold, (size_t)lay.nelem * wrow)) return 1;
+		}
+		TB_CHECK(ctx, cudaMemcpy2DAsync(
+			ctx->d_wold, wrow * sizeof(double),
+			ctx->inst[in] + (size_t)lay.rowoff[3] * lay.nn, (size_t)lay.nrows * lay.nn * sizeof(double),
+			wrow * sizeof(double), (size_t)lay.nelem, cudaMemcpyDeviceToDevice, ctx->stream));
+		if (column_solve(ctx, in, out, dt)) return 1;
+		return column_tracers(ctx, in, out, dt);
+	}
+	return column_solve(ctx, in, out, dt);
+}
+
+// UpdateColumnTracers for every unique column, then the column filter
+// (VerticalDynamicsFEM.cpp:1528-1536, 1637)
+static int column_tracers(tb200_ctx * ctx, int in, int out, double dt) {
+	const DevLayout & lay = ctx->lay;
+	TracerColumnArgs ta;
+	ta.col_node = ctx->d_col_node;
+	ta.col_dups = ctx->d_col_dups;
+	ta.ws = ctx->d_ws;
+	ta.ws_stride = ctx->ws_cols;
+	ta.dt = dt;
+	ta.fe_nodes = ctx->cfg.vertical_order;
+	ta.kl = 2 * ctx->cfg.vertical_order - 1;
+	ta.w_old = ctx->d_wold;
+	ta.info = ctx->d_info;
+	if (tb_tracer_ws_entries(lay.nlev, ta.kl) > tb_column_ws_entries(lay.nlev, ctx->offd)) {
+		TB_FAIL(ctx, "column workspace too small for the tracer update");
+	}
+	for (int c0 = 0; c0 < ctx->ncols; c0 += ctx->ws_cols) {
+		ta.col0 = c0;
+		ta.ncols = std::min(ctx->ws_cols, ctx->ncols - c0);
+		const int block = 64;
+		auto kfn = k_column_tracers;
+		TB_LAUNCH_FLAT(kfn, dim3((ta.ncols + block - 1) / block), dim3(block), 0, ctx->stream,
+			lay, ctx->geom, ctx->ops, ta,
+			(const double *)ctx->inst[in], (const double *)ctx->inst[out],
+			(const double *)ctx->inst[in], ctx->inst[out]);
+		TB_KERNEL_CHECK(ctx);
+	}
+	return tb200_v_filter_negative_tracers(ctx, out);
+}
+
+static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 	const DevLayout & lay = ctx->lay;
 	ColumnArgs ca;
 	ca.col_node = ctx->d_col_node;
@@ -1370,10 +1423,36 @@ extern "C" int tb200_check_errors(tb200_ctx * ctx) {
 	return check_column_info(ctx);
 }
 
+// HorizontalDynamicsFEM::FilterNegativeTracers (element-wise) and
+// VerticalDynamicsFEM::FilterNegativeTracers (column-wise); both need the
+// element areas (tb200_upload_element_area).
+static int filter_tracers(tb200_ctx * ctx, int inst, bool column) {
+	const DevLayout & lay = ctx->lay;
+	if (lay.ntr == 0) return 0;
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid state instance");
+	if (ctx->d_area_node == 0) TB_FAIL(ctx, "element areas not uploaded (tracer filter)");
+	const int block = 128;
+	if (column) {
+		const long long nitems = lay.nelem * lay.nn * lay.ntr;
+		auto kfn = k_filter_tracers_column;
+		TB_LAUNCH_FLAT(kfn, dim3((unsigned)((nitems + block - 1) / block)), dim3(block), 0,
+			ctx->stream, lay, (const double *)ctx->d_area_node, ctx->inst[inst]);
+	} else {
+		const long long nitems = lay.nelem * lay.ntr * lay.nlev;
+		auto kfn = k_filter_tracers_element;
+		TB_LAUNCH_FLAT(kfn, dim3((unsigned)((nitems + block - 1) / block)), dim3(block), 0,
+			ctx->stream, lay, (const double *)ctx->d_area_node, ctx->inst[inst]);
+	}
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
 extern "C" int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst) {
-	if (ctx->lay.ntr == 0) return 0;
-	(void)inst;
-	TB_FAIL(ctx, "FilterNegativeTracers is not implemented yet");
+	return filter_tracers(ctx, inst, false);
+}
+
+extern "C" int tb200_v_filter_negative_tracers(tb200_ctx * ctx, int inst) {
+	return filter_tracers(ctx, inst, true);
 }
 
 ///////////////////////////////////////////////////////////////////////////////

@@ -117,7 +117,8 @@ static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double 
 	} else {
 		const std::vector<double> carry = {1.0, 1.0};
 		TRY(lincomb(ctx, carry, 0));
-		TRY(tb200_filter_negative_tracers(ctx, 0));
+		// pVerticalDynamics->FilterNegativeTracers(0), TimestepSchemeStrang.cpp:480
+		TRY(tb200_v_filter_negative_tracers(ctx, 0));
 	}
 
 	if (scheme == TB200_SCHEME_STRANG_FE) {

@@ -59,6 +59,22 @@ CASES["bubble_r6_l8_strang"] = dict(
     script="addw:0,100;dss:0;dump:ic,0;step:3;dump:st,0;checksum:cs",
     geometry_from="bubble_r6_l8")
 
+# tracers: the JW case carrying three analytic tracer densities (oracle/ref_dump.cpp
+# JWTracerTest): horizontal transport, implicit column transport, both
+# positive-definite filters, DSS and hyperdiffusion of tracers
+CASES["jwtr_ne2_l6"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--ntracers", "3"],
+    script=";".join([
+        "addw:0,20000", "dss:0",
+        "dump:ic,0", "copy:0,1", "hexp:0,1,50", "dump:h1,1", "vexp:0,1,50",
+        "dump:v1,1", "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,30",
+        "dump:vi,2", "hasc:1,3,4,200", "dump:hasc,3,4"]),
+    geometry_from="jw_ne2_l6")
+CASES["jwtr_ne2_l6_strang"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s", "--ntracers", "3"],
+    script="addw:0,20000;dss:0;dump:ic,0;step:3;dump:st,0;checksum:cs",
+    geometry_from="jw_ne2_l6_strang")
+
 # more time schemes on the same grid and initial state: only the run records are
 # stored, the geometry comes from the strang case (same flags)
 for _scheme in ("ars222", "ars232", "ars443", "strang/ssprk53", "strang/rk4", "strang/rk3"):

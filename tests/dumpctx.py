@@ -190,3 +190,36 @@ def compare(ctx, d, inst, tag, comps_node, comps_redge=(), ref_inst=None,
                 den = max(den, np.abs(r).max())
             errs[(loc, c)] = num / den if den > 0 else num
     return errs
+
+
+def download_tracers(ctx, d, inst):
+    """-> {patch n: tracers [nT][W_A][W_B][L]} in the reference layout."""
+    out = {}
+    for n in ctx.local_patches:
+        idx = S(d, "patch%d.index" % n)
+        key = [k for k in d if k.endswith(".patch%d.inst0.tracers" % n)][0]
+        tr = np.zeros_like(d[key])
+        ctx.download_state(idx, inst, None, None, tr, False)
+        out[n] = tr
+    return out
+
+
+def compare_tracers(ctx, d, inst, tag, before=None):
+    """max |dev - ref| per tracer over interior nodes, relative to max |ref|, or -
+    with before = (tag, inst) - to the largest change since that record."""
+    got = download_tracers(ctx, d, inst)
+    ntr = S(d, "grid.ntracers")
+    errs = {}
+    for c in range(ntr):
+        num = den = 0.0
+        for n in ctx.local_patches:
+            ref = interior(d["%s.patch%d.inst%d.tracers" % (tag, n, inst)])[c]
+            dev = interior(got[n])[c]
+            num = max(num, np.abs(dev - ref).max())
+            if before is None:
+                den = max(den, np.abs(ref).max())
+            else:
+                b = interior(d["%s.patch%d.inst%d.tracers" % (before[0], n, before[1])])[c]
+                den = max(den, np.abs(ref - b).max())
+        errs[("tracer", c)] = num / den if den > 0 else num
+    return errs

@@ -360,3 +360,46 @@ def test_cartesian_bubble_steps(library):
     assert abs(cs[4] - ref[4]) <= 1e-13 * abs(ref[4])
     assert abs(cs[2] - ref[2]) <= 1e-13 * abs(ref[2])
     ctx.close()
+
+
+def test_tracer_stages(library):
+    """Tracers: horizontal transport inside StepExplicit with the
+    element filter, DSS, implicit column transport with the column filter
+    (UpdateColumnTracers, both FilterNegativeTracers), hyperdiffusion."""
+    d = cases.load_case("jwtr_ne2_l6")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    assert_below(dumpctx.compare_tracers(ctx, d, 0, "ic"), 0.0)
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "h1", before=("ic", 0)), 1e-11)
+    ctx.v_step_explicit(0, 1, 50.0)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "dss"), 1e-13)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=True), TOL_IMPLICIT)
+    assert_below(dumpctx.compare_tracers(ctx, d, 2, "vi"), 1e-10)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    assert_below(dumpctx.compare_tracers(ctx, d, 3, "hasc"), 1e-12)
+    ctx.close()
+
+
+def test_tracer_steps(library):
+    d = cases.load_case("jwtr_ne2_l6_strang")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    assert_below(dumpctx.compare_tracers(ctx, d, 0, "st"), 1e-9)
+    ctx.close()
