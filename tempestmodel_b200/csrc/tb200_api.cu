@@ -984,32 +984,53 @@ static int nh_launch(
 		fa.inv_db = ctx->d_inv_db;
 		fa.dt = dt;
 		fa.xz = ctx->cfg.cartesian_xz;
-		// stage base = one instance, coefficient 1: pipelined kernel
+		// stage base from at most TBP_MAXSRC instances: pipelined kernel
 		const char * nopipe = getenv("TB200_STAGE_KERNEL");
-		const bool simple = sb.use_out || (sb.nsrc == 1 && sb.coeff[0] == 1.0 && !sb.scale_dst);
-		if (do_h && simple && !(nopipe != 0 && strcmp(nopipe, "fast") == 0)) {
-			const double * base = sb.use_out ? ctx->inst[out] : sb.src[0];
-			const int alias = (base == ctx->inst[in]) ? 1 : 0;
-			const size_t smem = tb_pipe_smem_doubles(lay.nrows, lay.nlev, alias != 0) * sizeof(double);
+		PipeBase pb;
+		memset(&pb, 0, sizeof(pb));
+		bool fits = true;
+		if (sb.use_out) {
+			pb.src[0] = ctx->inst[out]; pb.coeff[0] = 1.0; pb.nsrc = 1;
+		} else {
+			if (sb.scale_dst) {
+				pb.src[0] = ctx->inst[out]; pb.coeff[0] = sb.cdst; pb.nsrc = 1;
+			}
+			for (int m = 0; m < sb.nsrc; m++) {
+				if (pb.nsrc == TBP_MAXSRC) { fits = false; break; }
+				pb.src[pb.nsrc] = sb.src[m]; pb.coeff[pb.nsrc] = sb.coeff[m]; pb.nsrc++;
+			}
+			if (pb.nsrc == 0) fits = false;       // an all-zero base: general kernel
+		}
+		// base = the input instance, copied: read it once
+		if (fits && pb.nsrc == 1 && pb.coeff[0] == 1.0 && pb.src[0] == ctx->inst[in]) {
+			pb.nsrc = 0;
+		}
+		if (do_h && fits && !(nopipe != 0 && strcmp(nopipe, "fast") == 0)) {
+			const size_t smem = tb_pipe_smem_doubles(lay.nrows, lay.nlev, pb.nsrc) * sizeof(double);
 			if (smem <= 227 * 1024 - 1024) {
 				const dim3 block(TBF_THREADS);
+#ifndef TB200_EMU
+#define TB_PIPE_ATTR(kfn) TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#else
+#define TB_PIPE_ATTR(kfn)
+#endif
+#define TB_PIPE_LAUNCH(V, N) { \
+					auto kfn = k_nh_stage_pipe<V, N>; \
+					TB_PIPE_ATTR(kfn); \
+					const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem)); \
+					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa, \
+						(const double *)ctx->inst[in], pb, ctx->inst[out]); }
 				if (do_v) {
-					auto kfn = k_nh_stage_pipe<true>;
-#ifndef TB200_EMU
-					TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
-					const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem));
-					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa,
-						(const double *)ctx->inst[in], base, ctx->inst[out], alias);
+					if (pb.nsrc == 0) TB_PIPE_LAUNCH(true, 0)
+					else if (pb.nsrc == 1) TB_PIPE_LAUNCH(true, 1)
+					else TB_PIPE_LAUNCH(true, 2)
 				} else {
-					auto kfn = k_nh_stage_pipe<false>;
-#ifndef TB200_EMU
-					TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
-					const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem));
-					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa,
-						(const double *)ctx->inst[in], base, ctx->inst[out], alias);
+					if (pb.nsrc == 0) TB_PIPE_LAUNCH(false, 0)
+					else if (pb.nsrc == 1) TB_PIPE_LAUNCH(false, 1)
+					else TB_PIPE_LAUNCH(false, 2)
 				}
+#undef TB_PIPE_LAUNCH
+#undef TB_PIPE_ATTR
 				TB_KERNEL_CHECK(ctx);
 				return 0;
 			}
@@ -1153,8 +1174,9 @@ extern "C" int tb200_hv_step_explicit_combine(
 		sb.nsrc++;
 	}
 	if (fast_prepare(ctx)) return 1;
-	const bool simple = (sb.nsrc == 1 && sb.coeff[0] == 1.0 && !sb.scale_dst);
-	if (ctx->fast_state == 1 && !simple && getenv("TB200_STAGE_KERNEL") == 0) {
+	const int nterms = sb.nsrc + (sb.scale_dst ? 1 : 0);
+	if (ctx->fast_state == 1 && (nterms > TBP_MAXSRC || nterms == 0)
+		&& getenv("TB200_STAGE_KERNEL") == 0) {
 		// several sources: a streaming combine, then the pipelined stage kernel on
 		// the pre-filled update instance (same operation order as the fused form)
 		if (tb200_lincomb(ctx, coeff, ncoeff, out, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;

@@ -671,22 +671,75 @@ __device__ __forceinline__ void tb_cross_sum2s(
 	}
 }
 
-__host__ __device__ inline size_t tb_pipe_smem_doubles(int nrows, int L, bool alias) {
-	// in[2], base[2] (unless it aliases in), tiles Wn, KE, EX, FaR, FaP, ZX, Un/Vn[3],
+#define TBP_MAXSRC 2
+
+// Stage base of the pipelined kernel: up to TBP_MAXSRC instances (the update
+// instance itself counts as one when its coefficient is non-zero), combined in
+// Grid::LinearCombineData's order.
+struct PipeBase {
+	const double * src[TBP_MAXSRC];
+	double coeff[TBP_MAXSRC];
+	int nsrc;          // 0: the base is the input instance itself (first stage)
+};
+
+__host__ __device__ inline size_t tb_pipe_smem_doubles(int nrows, int L, int nsrc) {
+	// in[2], base[nsrc], tiles Wn, KE, EX, FaR, FaP, ZX, Un/Vn[3],
 	// column constants [2], operator windows [L+1]
-	return (size_t)nrows * 16 * (alias ? 2 : 4) + (size_t)(6 * L + 6) * 16
+	// (one source: its buffer is doubled and fetched one element ahead)
+	return (size_t)nrows * 16 * (2 + (nsrc == 1 ? 2 : nsrc)) + (size_t)(6 * L + 6) * 16
 		+ 2 * TBF_NC * 16 + (size_t)(L + 1) * TBF_LWS;
+}
+
+// cp.async of the rows of thread (kq, i) - its four nodes of every component
+// at levels kq, kq + TBF_KB, ... - from one element of a source instance into
+// a swizzled element buffer
+__device__ __forceinline__ void tb_pipe_fetch(
+	const DevLayout & lay, const double * sp, double * dp, int kq, int i, int L
+) {
+	for (int k = kq; k <= L; k += TBF_KB) {
+#pragma unroll
+		for (int cmp = 0; cmp < 5; cmp++) {
+			if (cmp != 3 && k == L) continue;
+			const int r = lay.rowoff[cmp] + k;
+			const int c0 = (2 * i) ^ (r & 1), c1 = (2 * i + 1) ^ (r & 1);
+			tb_cp16(dp + ((r << 3) | c0) * 2, sp + (size_t)r * 16 + 4 * i);
+			tb_cp16(dp + ((r << 3) | c1) * 2, sp + (size_t)r * 16 + 4 * i + 2);
+		}
+	}
+}
+
+// my node pair of the stage base at swizzled element offset off
+template <int NSRC>
+__device__ __forceinline__ void tb_pipe_base2(
+	const PipeBase & pb, const double * inb, const double * b0, const double * b1,
+	int off, double (&v)[2]
+) {
+	if (NSRC == 0) {
+		tb_ld2(inb + off, v);
+		return;
+	}
+	// first term: value * coefficient (= 0 + value * coefficient of
+	// LinearCombineData, and the scaled destination when it leads the list)
+	double s[2];
+	tb_ld2(b0 + off, s);
+	v[0] = s[0] * pb.coeff[0];
+	v[1] = s[1] * pb.coeff[0];
+	if (NSRC == 2) {
+		tb_ld2(b1 + off, s);
+		v[0] += s[0] * pb.coeff[1];
+		v[1] += s[1] * pb.coeff[1];
+	}
 }
 
 #ifndef TBP_MINBLOCKS
 #define TBP_MINBLOCKS 2
 #endif
 
-template <bool DO_V>
+template <bool DO_V, int NSRC>
 __global__ void __launch_bounds__(TBF_THREADS, TBP_MINBLOCKS)
 k_nh_stage_pipe(
 	DevLayout lay, DevTables t, DevPhys ph, FastArgs fa,
-	const double * __restrict__ in, const double * base, double * out, int alias
+	const double * __restrict__ in, PipeBase pb, double * out
 ) {
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
@@ -698,8 +751,11 @@ k_nh_stage_pipe(
 	TB_DYN_SMEM(double, sm);
 	const size_t esz = (size_t)nrows * NN;
 	double * inb0 = sm;
-	double * bsb0 = alias ? sm : (sm + 2 * esz);
-	double * tWn = sm + (alias ? 2 : 4) * esz;
+	// one source: [2][esz], fetched one element ahead like the input;
+	// two sources: [2][esz], one buffer each, fetched at the start of the element
+	double * bsb0 = sm + 2 * esz;
+	const bool ahead = (NSRC == 1);
+	double * tWn = sm + (2 + (NSRC == 1 ? 2 : NSRC)) * esz;
 	double * tKE = tWn + (size_t)L * NN;
 	double * tEX = tKE + (size_t)L * NN;
 	double * tFaR = tEX + (size_t)L * NN;
@@ -730,7 +786,7 @@ k_nh_stage_pipe(
 			const int r = q >> 3, c = q & 7;
 			const int d = ((r << 3) | (c ^ (r & 1))) << 1;
 			tb_cp16(inb0 + d, in + eb + 2 * q);
-			if (!alias) tb_cp16(bsb0 + d, base + eb + 2 * q);
+			if (ahead) tb_cp16(bsb0 + d, pb.src[0] + eb + 2 * q);
 		}
 		for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
 			tb_cp16(scc0 + 2 * q, fa.colc + (size_t)e * TBF_NC * NN + 2 * q);
@@ -745,11 +801,24 @@ k_nh_stage_pipe(
 	for (int it = 0; e < lay.nelem; it++, e += gridDim.x) {
 		const int buf = it & 1;
 		const double * inb = inb0 + (size_t)buf * esz;
-		const double * bsb = bsb0 + (size_t)buf * esz;
 		// the data of this element (issued one iteration ago) has landed, and
 		// every thread is done with the previous element
 		tb_cp_wait<0>();
 		__syncthreads();
+		// stage base.  Every thread fetches exactly the 32 bytes per row it will
+		// combine (its own four nodes).  Two sources: fetched now for this
+		// element, the thread's own cp.async.wait_group is all the
+		// synchronisation the data needs.  One source: fetched below, one
+		// element ahead.
+		const double * bp0 = ahead ? (bsb0 + (size_t)buf * esz) : bsb0;
+		const double * bp1 = bsb0 + esz;
+		if (NSRC == 2) {
+#pragma unroll
+			for (int m = 0; m < NSRC; m++) {
+				tb_pipe_fetch(lay, pb.src[m] + (size_t)e * esz, bsb0 + (size_t)m * esz, kq, i, L);
+			}
+			tb_cp_commit();
+		}
 		// prefetch the next element of this block into the other buffer
 		{
 			const long long en = e + gridDim.x;
@@ -761,7 +830,7 @@ k_nh_stage_pipe(
 					const int r = q >> 3, c = q & 7;
 					const int d = ((r << 3) | (c ^ (r & 1))) << 1;
 					tb_cp16(di + d, in + eb + 2 * q);
-					if (!alias) tb_cp16(db + d, base + eb + 2 * q);
+					if (ahead) tb_cp16(db + d, pb.src[0] + eb + 2 * q);
 				}
 				double * dc = scc0 + (size_t)(buf ^ 1) * TBF_NC * NN;
 				for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
@@ -877,10 +946,11 @@ k_nh_stage_pipe(
 				// stage base: my node pair of the four level components
 				const int ch = 2 * i + jh;
 				double bU[2], bV[2], bP[2], bR[2];
-				tb_ld2(bsb + (size_t)(rU + kc) * NN + ((ch ^ ((rU + kc) & 1)) << 1), bU);
-				tb_ld2(bsb + (size_t)(rV + kc) * NN + ((ch ^ ((rV + kc) & 1)) << 1), bV);
-				tb_ld2(bsb + (size_t)(rP + kc) * NN + ((ch ^ ((rP + kc) & 1)) << 1), bP);
-				tb_ld2(bsb + (size_t)(rR + kc) * NN + ((ch ^ ((rR + kc) & 1)) << 1), bR);
+				if (jh == 0 && NSRC == 2) tb_cp_wait<1>();     // my base chunks have landed
+				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rU + kc) * NN + ((ch ^ ((rU + kc) & 1)) << 1), bU);
+				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rV + kc) * NN + ((ch ^ ((rV + kc) & 1)) << 1), bV);
+				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rP + kc) * NN + ((ch ^ ((rP + kc) & 1)) << 1), bP);
+				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rR + kc) * NN + ((ch ^ ((rR + kc) & 1)) << 1), bR);
 
 				double zx[2];
 #pragma unroll
@@ -1035,7 +1105,13 @@ k_nh_stage_pipe(
 					bW[j] = -(c0 * dU0 + c1 * dV0) / cx2;
 				}
 			} else {
-				tb_ld4s(bsb + (size_t)(rW + k) * NN, (rW + k) & 1, i, bW);
+				{
+					const int par = (rW + k) & 1;
+					double lo[2], hi[2];
+					tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rW + k) * NN + (((2 * i) ^ par) << 1), lo);
+					tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rW + k) * NN + (((2 * i + 1) ^ par) << 1), hi);
+					bW[0] = lo[0]; bW[1] = lo[1]; bW[2] = hi[0]; bW[3] = hi[1];
+				}
 				if (k < L) {
 					double zm[4], z0[4];
 					tb_ld4s(tZX + (size_t)(k - 1) * NN, (k - 1) & 1, i, zm);
