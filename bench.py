@@ -276,12 +276,21 @@ def main():
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM traffic of the same kernel from the committed ncu capture (per node)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)
+        if ctx.fast_path()[0]:
+            traffic = tr["k_nh_stage_pipe<true,0>"]["bytes_per_node"] * local_nodes
+    except Exception:
+        pass
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     fast = ctx.fast_path()
     roofline = {"bound": "hbm",
                 "kernel": "k_nh_stage_pipe<true>" if fast[0] else "k_nh_explicit<4,true,true>",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                 "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
