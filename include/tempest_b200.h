@@ -254,6 +254,9 @@ int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt);
  * TimestepSchemeARS343.cpp:169-172): only the rows the solve does not
  * overwrite are copied. */
 int tb200_copy_v_step_implicit(tb200_ctx * ctx, int src, int dst, double dt);
+/* ... followed by Grid::LinearCombineData({+1 dst, -1 src} -> src): dst = solve(src),
+ * src = dst - src (the tail of TimestepSchemeStrang::Step, :644-672). */
+int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst, double dt);
 /* GridGLL::PostProcessSubstage -> ApplyDSS (GridGLL.cpp:571-583,
  * GridCSGLL.cpp:435-781, GridCartesianGLL.cpp:508-654). */
 int tb200_dss(tb200_ctx * ctx, int inst, int data_mask);

@@ -1271,6 +1271,7 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 		fa.info = ctx->d_info;
 		fa.colc = ctx->d_colc;
 		fa.lev = ctx->d_lev;
+		fa.inc = ctx->column_inc;
 		const size_t smem = (size_t)(lay.nlev + 1) * TBF_LW * sizeof(double);
 		auto kfn = k_column_fast;
 #ifndef TB200_EMU
@@ -1382,6 +1383,43 @@ extern "C" int tb200_copy_v_step_implicit(tb200_ctx * ctx, int src, int dst, dou
 	// rows of u and v (components 0 and 1 are adjacent)
 	if (launch_combine(ctx, ca, dst, lay.rowoff[0], lay.rowoff[1] + lay.rowlev[1])) return 1;
 	return tb200_v_step_implicit(ctx, src, dst, dt);
+}
+
+// CopyData(src -> dst), StepImplicit(dst, dst), LinearCombineData({+1, -1} -> src):
+// dst = solve(src) and src = dst - src, the tail of a Strang step without
+// off-centring (TimestepSchemeStrang.cpp:644-672).  The increment of the solved
+// rows is written by the column kernel itself; u and v are untouched by the
+// solve, their increment is +0.
+extern "C" int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst, double dt) {
+	if (check_inst2(ctx, src, dst)) return 1;
+	const DevLayout & lay = ctx->lay;
+	const bool solve = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && lay.nlev > 1
+		&& !ctx->cfg.fully_explicit;
+	if (src == dst || !solve || lay.ntr > 0 || fast_prepare(ctx) || ctx->fast_state != 1
+		|| getenv("TB200_COLUMN_KERNEL") != 0) {
+		if (tb200_copy_v_step_implicit(ctx, src, dst, dt)) return 1;
+		const double fin[2] = {+1.0, -1.0};
+		std::vector<double> c(std::max(src, dst) + 1, 0.0);
+		c[dst] = fin[0];
+		c[src] = fin[1];
+		return tb200_lincomb(ctx, c.data(), (int)c.size(), src, TB200_DATA_STATE | TB200_DATA_TRACERS);
+	}
+	CombineArgs ca;
+	memset(&ca, 0, sizeof(ca));
+	ca.nsrc = 1;
+	ca.src[0] = ctx->inst[src];
+	ca.coeff[0] = 1.0;
+	ca.scale_dst = 0;
+	const int uv0 = lay.rowoff[0], uv1 = lay.rowoff[1] + lay.rowlev[1];
+	if (launch_combine(ctx, ca, dst, uv0, uv1)) return 1;
+	ctx->column_inc = ctx->inst[src];
+	const int rc = tb200_v_step_implicit(ctx, src, dst, dt);
+	ctx->column_inc = 0;
+	if (rc) return 1;
+	// u, v rows of the increment
+	CombineArgs zero;
+	memset(&zero, 0, sizeof(zero));
+	return launch_combine(ctx, zero, src, uv0, uv1);
 }
 
 // Debugging aid: assemble F and the banded Jacobian of the first launch chunk

@@ -48,6 +48,7 @@ struct ColumnFastArgs {
 	int * info;
 	const double * colc;
 	const double * lev;
+	double * inc;           // optional: receives x_new - x_old (may alias the input)
 };
 
 // rows of one level in LAPACK band form relative to their own diagonal:
@@ -536,6 +537,14 @@ k_column_fast(
 				if (d0 >= 0) out[ob0 + ro] = xnew;
 				if (d1 >= 0) out[ob1 + ro] = xnew;
 				if (d2 >= 0) out[ob2 + ro] = xnew;
+				if (ca.inc != 0) {
+					// Grid::LinearCombineData({+1, -1}) of the new and the old state
+					const double dx = xnew - x0cur[c3];
+					ca.inc[ebase + ro + nd] = dx;
+					if (d0 >= 0) ca.inc[ob0 + ro] = dx;
+					if (d1 >= 0) ca.inc[ob1 + ro] = dx;
+					if (d2 >= 0) ca.inc[ob2 + ro] = dx;
+				}
 			}
 		}
 #pragma unroll

@@ -177,6 +177,12 @@ static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double 
 
 	// vertical step, :644-657: CopyData(1 -> 0), StepImplicit(0, 0)
 	const double dOffCenterDeltaT = 0.5 * (1.0 + offc) * dt;
+	if (offc == 0.0 && !last) {
+		// the off-centring combination is 1 * instance 0: the solve and the final
+		// {+1, -1} combination run as one call
+		TRY(tb200_copy_v_step_implicit_diff(ctx, 1, 0, dOffCenterDeltaT));
+		return 0;
+	}
 	TRY(tb200_copy_v_step_implicit(ctx, 1, 0, dOffCenterDeltaT));
 	const std::vector<double> oc = {(2.0 - offc) / 2.0, offc / 2.0};
 	TRY(lincomb(ctx, oc, 0));

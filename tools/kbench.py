@@ -71,7 +71,8 @@ def main():
         return e0.elapsed_time(e1) / reps
 
     ops = [
-        ("stage(copy0)+HV 2S", lambda: ctx.hv_step_explicit_combine([1.0, 0.0, 0.0, 0.0], 2, 3, 1e-6), 2),
+        ("stage(in=base)+HV 2S", lambda: ctx.hv_step_explicit_combine([0.0, 0.0, 1.0, 0.0], 2, 3, 1e-6), 2),
+        ("stage(copy0)+HV 3S", lambda: ctx.hv_step_explicit_combine([1.0, 0.0, 0.0, 0.0], 2, 3, 1e-6), 3),
         ("stage(2src)+HV 4S", lambda: ctx.hv_step_explicit_combine([-0.25, 1.25, 0.0, 0.0, 0.0], 2, 4, 1e-6), 4),
         ("dss 1.5S", lambda: ctx.dss(3), 1.5),
         ("implicit 2S", lambda: ctx.v_step_implicit(3, 3, dt * 1e-3), 2),
