@@ -181,6 +181,13 @@ extern "C" int tb200_create(const tb200_config * cfg, tb200_ctx ** out) {
 	ctx->phys.p0 = cfg->p0;
 	ctx->phys.exner_c1 = cfg->R / (cfg->cp - cfg->R);
 	ctx->phys.exner_c2 = cfg->R / cfg->p0;
+	{
+		// R / cv == 2/5 (to rounding): the fast kernels take tb_exner's Newton form;
+		// TB200_EXNER=libm keeps exp(c log x)
+		const char * ex = getenv("TB200_EXNER");
+		ctx->phys.exner25 = (fabs(ctx->phys.exner_c1 - 0.4) <= 1.0e-15
+			&& !(ex != 0 && strcmp(ex, "libm") == 0)) ? 1 : 0;
+	}
 
 	// m_nJacobianFOffD (VerticalDynamicsFEM.cpp:188-201, FE discretisation)
 	switch (cfg->vertical_order) {

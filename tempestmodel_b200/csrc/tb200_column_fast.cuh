@@ -352,7 +352,7 @@ k_column_fast(
 			const double sn = lv[TBF_SN];
 			double wn = 0.0;
 			wn += lv[TBF_CW + 0] * W0; wn += lv[TBF_CW + 1] * Wp;
-			exn_0 = ph.cp * exp(ph.exner_c1 * log(ph.exner_c2 * P0));
+			exn_0 = tb_exner(ph, P0);
 			const double cx0 = sn * cA2, cx1 = sn * cB2;
 			const double cx2 = cX0 + (sn * sn) * cX2;
 			const double dConUa = cA0 * U0 + cA1 * V0 + cx0 * wn;

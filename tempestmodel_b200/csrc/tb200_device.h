@@ -105,6 +105,7 @@ struct DevPhys {
 	double g, R, cp, cv, p0;
 	double exner_c1;   // R / (cp - R)
 	double exner_c2;   // R / p0
+	int exner25;       // exponent R / cv is 2/5 (dry air of PhysicalConstants.h): tb_exner
 };
 
 #endif
