@@ -283,6 +283,14 @@ int tb200_step(tb200_ctx * ctx, int scheme, int first_step, int last_step, doubl
 /* ---- diagnostics (Grid::Checksum, GridPatch.cpp:744-835) ----------------- */
 /* Area-weighted sum of every component of an instance over the local patches;
  * sums[ncomp].  element_area_* in the reference layout are supplied once. */
+/* Rayleigh friction: GridPatch::GetRayleighStrength(Node / REdge) [W_A][W_B][L(+1)]
+ * and GridPatch::GetReferenceState(Node / REdge) in the state layout.  Once
+ * uploaded, tb200_h_step_after_subcycle applies
+ * HorizontalDynamicsFEM::ApplyRayleighFriction (:2418-2536) after the
+ * hyperdiffusion (APPLY_RAYLEIGH_WITH_HYPERVIS, Defines.h:74). */
+int tb200_upload_rayleigh(tb200_ctx * ctx, int patch_index,
+                          const double * strength_node, const double * strength_redge,
+                          const double * ref_node, const double * ref_redge);
 int tb200_upload_element_area(tb200_ctx * ctx, int patch_index,
                               const double * area_node, const double * area_redge);
 int tb200_checksum(tb200_ctx * ctx, int inst, double * sums);

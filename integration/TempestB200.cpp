@@ -222,6 +222,16 @@ void B200Bridge::Initialize() {
 		}
 		Check(tb200_upload_geometry(m_pCtx, ixPatch, &geo));
 
+		// Rayleigh friction (Grid::HasRayleighFriction, GridPatch.h:1053-1078)
+		if (pGrid->HasRayleighFriction()) {
+			Check(tb200_upload_rayleigh(
+				m_pCtx, ixPatch,
+				&(pPatch->GetRayleighStrength(DataLocation_Node)[0][0][0]),
+				&(pPatch->GetRayleighStrength(DataLocation_REdge)[0][0][0]),
+				&(pPatch->GetReferenceState(DataLocation_Node)[0][0][0][0]),
+				&(pPatch->GetReferenceState(DataLocation_REdge)[0][0][0][0])));
+		}
+
 		// On-the-fly terrain-following metric: m_dXNode / m_dYNode
 		// (GridPatchCSGLL.cpp:205-213) and the topography derivatives
 		if (cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {

@@ -65,11 +65,33 @@
 class JWTracerTest : public BaroclinicWaveJWTest {
 public:
 	JWTracerTest(
-		double dAlpha, double dZtop, PerturbationType ePert, int nTracers
+		double dAlpha, double dZtop, PerturbationType ePert, int nTracers,
+		double dRayleigh
 	) :
 		BaroclinicWaveJWTest(dAlpha, dZtop, ePert),
-		m_nTracers(nTracers)
+		m_nTracers(nTracers),
+		m_dRayleigh(dRayleigh),
+		m_dSpongeTop(dZtop)
 	{ }
+
+	///	<summary>
+	///		Test data: a sponge layer in the upper 40 % of the domain whose
+	///		strength also varies horizontally.
+	///	</summary>
+	virtual bool HasRayleighFriction() const {
+		return (m_dRayleigh > 0.0);
+	}
+
+	virtual double EvaluateRayleighStrength(
+		double dZ, double dLon, double dLat
+	) const {
+		const double dZ0 = 0.6 * m_dSpongeTop;
+		if (dZ <= dZ0) {
+			return 0.0;
+		}
+		const double dS = sin(0.5 * M_PI * (dZ - dZ0) / (m_dSpongeTop - dZ0));
+		return m_dRayleigh * dS * dS * (1.0 + 0.3 * cos(dLon) * cos(dLat));
+	}
 
 	virtual void EvaluatePointwiseState(
 		const PhysicalConstants & phys,
@@ -103,6 +125,8 @@ public:
 
 private:
 	int m_nTracers;
+	double m_dRayleigh;
+	double m_dSpongeTop;
 };
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -472,6 +496,7 @@ try {
 	std::string strPert;
 	double dU0, dH0, dAlpha;
 	int nTracers;
+	double dRayleigh;
 
 	BeginTempestCommandLine("RefDump");
 		SetDefaultResolution(4);
@@ -493,6 +518,7 @@ try {
 		CommandLineDouble(dH0, "h0", 2998.104995);
 		CommandLineDouble(dAlpha, "alpha", 0.0);
 		CommandLineInt(nTracers, "ntracers", 0);
+		CommandLineDouble(dRayleigh, "rayleigh", 0.0);
 
 		ParseCommandLine(argc, argv);
 	EndTempestCommandLine(argv)
@@ -515,7 +541,7 @@ try {
 			(strPert == "exp") ?
 				BaroclinicWaveJWTest::PerturbationType_Exp :
 				BaroclinicWaveJWTest::PerturbationType_None;
-		if (nTracers > 0) {
+		if ((nTracers > 0) || (dRayleigh > 0.0)) {
 			EquationSet eqn(EquationSet::PrimitiveNonhydrostaticEquations);
 			for (int c = 0; c < nTracers; c++) {
 				char szName[16];
@@ -524,7 +550,7 @@ try {
 			}
 			UserDataMeta metaUserData;
 			pModel = new Model(eqn, metaUserData);
-			pTest = new JWTracerTest(dAlpha, dZtop, ePert, nTracers);
+			pTest = new JWTracerTest(dAlpha, dZtop, ePert, nTracers, dRayleigh);
 		} else {
 			pModel = new Model(EquationSet::PrimitiveNonhydrostaticEquations);
 			pTest = new BaroclinicWaveJWTest(dAlpha, dZtop, ePert);

@@ -111,6 +111,8 @@ _SIGNATURES = {
     "tb200_scheme_from_name": (c_int, [c_char_p]),
     "tb200_step": (c_int, [c_void_p, c_int, c_int, c_int, c_double]),
     "tb200_upload_element_area": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "tb200_upload_rayleigh": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     "tb200_checksum": (c_int, [c_void_p, c_int, c_void_p]),
     "tb200_set_exchange": (c_int, [c_void_p, c_int, c_int, EXCHANGE_FN,
                                    c_void_p]),

@@ -582,6 +582,45 @@ extern "C" int tb200_upload_element_area(
 	return 0;
 }
 
+extern "C" int tb200_upload_state(
+	tb200_ctx * ctx, int patch_index, int inst,
+	const double * node, const double * redge, const double * tracers);
+
+// Rayleigh friction (GridPatch::GetRayleighStrength, GetReferenceState): the
+// strength on levels / interfaces [W_A][W_B][L(+1)] and the reference state in
+// the layout of a state instance.  Optional; StepAfterSubCycle applies the
+// friction once any patch has a non-zero strength (Grid::HasRayleighFriction).
+extern "C" int tb200_upload_rayleigh(
+	tb200_ctx * ctx, int patch_index,
+	const double * strength_node, const double * strength_redge,
+	const double * ref_node, const double * ref_redge
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	const DevLayout & lay = ctx->lay;
+	const int L = lay.nlev;
+	const size_t nn = lay.nn;
+	if (ctx->d_ray_node == 0) {
+		if (dalloc(ctx, &ctx->d_ray_node, (size_t)lay.nelem * L * nn)) return 1;
+		if (dalloc(ctx, &ctx->d_ray_redge, (size_t)lay.nelem * (L + 1) * nn)) return 1;
+		if (dalloc(ctx, &ctx->d_refstate, (size_t)lay.nelem * lay.nrows * nn)) return 1;
+		TB_CHECK(ctx, cudaMemset(ctx->d_ray_node, 0, (size_t)lay.nelem * L * nn * sizeof(double)));
+		TB_CHECK(ctx, cudaMemset(ctx->d_ray_redge, 0, (size_t)lay.nelem * (L + 1) * nn * sizeof(double)));
+		TB_CHECK(ctx, cudaMemset(ctx->d_refstate, 0, (size_t)lay.nelem * lay.nrows * nn * sizeof(double)));
+	}
+	if (upload_geom_array(ctx, *pi, strength_node, L, 1, ctx->d_ray_node, 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, strength_redge, L + 1, 1, ctx->d_ray_redge, 0, 0)) return 1;
+	// the reference state goes through the state path into a scratch "instance"
+	ctx->inst.push_back(ctx->d_refstate);
+	const int slot = (int)ctx->inst.size() - 1;
+	const int rc = tb200_upload_state(ctx, patch_index, slot, ref_node, ref_redge, 0);
+	ctx->inst.pop_back();
+	if (rc) return 1;
+	ctx->has_rayleigh = true;
+	return 0;
+}
+
 ///////////////////////////////////////////////////////////////////////////////
 // State movement
 
@@ -1703,7 +1742,7 @@ static int hyper_fast(
 	return 0;
 }
 
-extern "C" int tb200_h_step_after_subcycle(
+static int h_step_after_subcycle_impl(
 	tb200_ctx * ctx, int in, int out, int work, double dt
 ) {
 	const int ni = (int)ctx->inst.size();
@@ -1744,6 +1783,25 @@ extern "C" int tb200_h_step_after_subcycle(
 	} else {
 		TB_FAIL(ctx, "Invalid viscosity order");
 	}
+	return 0;
+}
+
+// Rayleigh damping after the hyperdiffusion (APPLY_RAYLEIGH_WITH_HYPERVIS,
+// Defines.h:74; HorizontalDynamicsFEM.cpp:2720-2725)
+extern "C" int tb200_h_step_after_subcycle(
+	tb200_ctx * ctx, int in, int out, int work, double dt
+) {
+	if (h_step_after_subcycle_impl(ctx, in, out, work, dt)) return 1;
+	if (!ctx->has_rayleigh) return 0;
+	const DevLayout & lay = ctx->lay;
+	const long long total = lay.nelem * (long long)lay.nrows_state * lay.nn;
+	long long nb = (total + 255) / 256;
+	if (nb > 148 * 16) nb = 148 * 16;
+	auto kfn = k_rayleigh;
+	TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(256), 0, ctx->stream,
+		lay, (const double *)ctx->d_ray_node, (const double *)ctx->d_ray_redge,
+		(const double *)ctx->d_refstate, ctx->inst[out], dt, ctx->cfg.cartesian_xz);
+	TB_KERNEL_CHECK(ctx);
 	return 0;
 }
 

@@ -91,6 +91,8 @@ struct tb200_ctx {
 	int ncols;
 	int * d_col_node; int * d_col_dups;
 	double * d_ws; int ws_cols; int * d_info;
+	double * d_ray_node; double * d_ray_redge; double * d_refstate;   // Rayleigh friction
+	bool has_rayleigh;
 	double * column_inc;              // set while tb200_copy_v_step_implicit_diff runs
 	double * d_wold;                  // w before the implicit solve (tracer update)
 	int offd;
@@ -117,7 +119,8 @@ struct tb200_ctx {
 		d_seam_mats(0), rank(0), nranks(1), exch_fn(0), exch_user(0),
 		nsend_total(0), nrecv_total(0), d_send_nodes(0), d_sendbuf(0),
 		d_recvbuf(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0),
-		d_ws(0), ws_cols(0), d_info(0), column_inc(0), d_wold(0), offd(4), launches(0),
+		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false),
+		column_inc(0), d_wold(0), offd(4), launches(0),
 		fast_state(0), fast_metric_error(0.0), d_colc(0), d_lev(0),
 		geometry3d_uploaded(false)
 	{

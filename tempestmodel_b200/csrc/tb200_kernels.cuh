@@ -936,4 +936,47 @@ k_hyper_vector(
 	}
 }
 
+///////////////////////////////////////////////////////////////////////////////
+// HorizontalDynamicsFEM::ApplyRayleighFriction
+// (reference HorizontalDynamicsFEM.cpp:2418-2536): ten implicit relaxation
+// sub-cycles towards the reference state wherever the strength is non-zero;
+// u, v, rho-theta, w (u, rho-theta, w on x-z slices) - not rho.
+
+__global__ void k_rayleigh(
+	DevLayout lay, const double * ray_node, const double * ray_redge,
+	const double * ref, double * data, double dt, int xz
+) {
+	const int NN = lay.nn;
+	const int L = lay.nlev;
+	const int nRayleighCycles = 10;
+	const double dRayleighFactor = 1.0 / nRayleighCycles;
+	const long long total = lay.nelem * (long long)lay.nrows_state * NN;
+	for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	     idx < total; idx += (long long)gridDim.x * blockDim.x
+	) {
+		const int n = (int)(idx % NN);
+		const long long er = idx / NN;
+		const int row = (int)(er % lay.nrows_state);
+		const long long e = er / lay.nrows_state;
+		int c = 0;
+		while (c + 1 < lay.ncomp && row >= lay.rowoff[c + 1]) c++;
+		// nEffectiveC (:2444-2464)
+		if (c == 4) continue;
+		if (xz && c == 1) continue;
+		const int k = row - lay.rowoff[c];
+		const double dNu = lay.onedge[c]
+			? ray_redge[((size_t)e * (L + 1) + k) * NN + n]
+			: ray_node[((size_t)e * L + k) * NN + n];
+		if (dNu == 0.0) continue;
+		const size_t off = ((size_t)e * lay.nrows + row) * NN + n;
+		const double r = ref[off];
+		double x = data[off];
+		for (int si = 0; si < nRayleighCycles; si++) {
+			const double dNuNode = 1.0 / (1.0 + dRayleighFactor * dt * dNu);
+			x = dNuNode * x + (1.0 - dNuNode) * r;
+		}
+		data[off] = x;
+	}
+}
+
 #endif

@@ -144,6 +144,12 @@ class DeviceContext:
         a, b = _f64(area_node), _f64(area_redge)
         self._ck(self.lib.tb200_upload_element_area(self._h, patch, _ptr(a), _ptr(b)))
 
+    def upload_rayleigh(self, patch, strength_node, strength_redge, ref_node, ref_redge):
+        a, b, c, d = (_f64(strength_node), _f64(strength_redge), _f64(ref_node),
+                      _f64(ref_redge))
+        self._ck(self.lib.tb200_upload_rayleigh(self._h, patch, _ptr(a), _ptr(b), _ptr(c),
+                                                _ptr(d)))
+
     def set_node_ids(self, patch, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         self._ck(self.lib.tb200_set_node_ids(self._h, patch, _ptr(ids)))

@@ -75,6 +75,13 @@ CASES["jwtr_ne2_l6_strang"] = dict(
     script="addw:0,20000;dss:0;dump:ic,0;step:3;dump:st,0;checksum:cs",
     geometry_from="jw_ne2_l6_strang")
 
+# Rayleigh friction: the JW case with a sponge layer (oracle/ref_dump.cpp --rayleigh)
+CASES["jwray_ne2_l6"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s", "--rayleigh", "0.01"],
+    script=";".join(["addw:0,20000", "dss:0", "dump:ic,0", "hasc:0,1,2,200", "dump:hasc,1",
+                     "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
+                     "step:2", "dump:st,0"]))
+
 # more time schemes on the same grid and initial state: only the run records are
 # stored, the geometry comes from the strang case (same flags)
 for _scheme in ("ars222", "ars232", "ars443", "strang/ssprk53", "strang/rk4", "strang/rk3"):

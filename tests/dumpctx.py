@@ -86,6 +86,10 @@ def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
                     contrametricxi_redge=d[p + "contrametricxiredge"],
                     derivr_node=d[p + "derivrnode"], derivr_redge=d[p + "derivrredge"])
             ctx.upload_geometry(idx, **geo)
+            if (p + "rayleighnode") in d and (np.abs(d[p + "rayleighnode"]).max() > 0.0
+                                              or np.abs(d[p + "rayleighredge"]).max() > 0.0):
+                ctx.upload_rayleigh(idx, d[p + "rayleighnode"], d[p + "rayleighredge"],
+                                    d[p + "refstatenode"], d[p + "refstateredge"])
             if eqn == 2 or True:
                 if (p + "elementareanode") in d:
                     ctx.upload_element_area(idx, d[p + "elementareanode"],

@@ -403,3 +403,25 @@ def test_tracer_steps(library):
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     assert_below(dumpctx.compare_tracers(ctx, d, 0, "st"), 1e-9)
     ctx.close()
+
+
+def test_rayleigh_friction(library):
+    """HorizontalDynamicsFEM::ApplyRayleighFriction (sponge layer relaxing u, v,
+    rho-theta, w towards the reference state) at the end of StepAfterSubCycle,
+    alone and inside two strang steps."""
+    d = cases.load_case("jwray_ne2_l6")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.h_step_after_subcycle(0, 1, 2, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 1, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    # the friction changed the state by far more than that
+    ic = dumpctx.interior(d["ic.patch0.inst0.node"])[0]
+    ha = dumpctx.interior(d["hasc.patch0.inst1.node"])[0]
+    assert np.abs(ha - ic).max() > 1e-4 * np.abs(ic).max()
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    ctx.close()
