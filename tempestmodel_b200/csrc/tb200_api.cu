@@ -1613,7 +1613,11 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 	a.sel_row0 = row0;
 	{
 		const int block = 128;
-		int gy = std::min(nsel, 32);
+		int gy = std::min(nsel, 4);
+		{
+			const char * g = getenv("TB200_DSS_GY");
+			if (g != 0 && atoi(g) > 0) gy = std::min(nsel, atoi(g));
+		}
 		auto kfn = k_dss_scalar;
 		TB_LAUNCH_FLAT(kfn, dim3((ctx->ngroups + block - 1) / block, gy), dim3(block), 0,
 			ctx->stream, lay, a, ctx->inst[inst]);

@@ -86,7 +86,13 @@ __global__ void k_dss_scalar(DevLayout lay, DssArgs a, double * data) {
 	const DssRef r2 = tb_dss_ref(lay, a, data, m2);
 	const DssRef r3 = tb_dss_ref(lay, a, data, m3);
 	const bool seam = (a.flags[gidx] & 1) != 0;
-	for (int r = a.row0 + blockIdx.y; r < a.row1; r += gridDim.y) {
+	// blockIdx.y owns a contiguous range of rows: the rows of an element are
+	// adjacent in memory, so a block walks whole DRAM pages
+	const int rows_per = (a.row1 - a.row0 + gridDim.y - 1) / gridDim.y;
+	const int rbeg = a.row0 + blockIdx.y * rows_per;
+	const int rend = (rbeg + rows_per < a.row1) ? (rbeg + rows_per) : a.row1;
+#pragma unroll 4
+	for (int r = rbeg; r < rend; r++) {
 		if (seam && r >= a.uv_row0 && r < a.uv_row1) continue;
 		const double v0 = r0.p[(size_t)r * r0.stride];
 		const double v1 = r1.p[(size_t)r * r1.stride];
