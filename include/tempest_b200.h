@@ -247,6 +247,11 @@ int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double dt);
  * HorizontalDynamics::StepExplicitCombine (HorizontalDynamics.h:97-106). */
 int tb200_hv_step_explicit_combine(tb200_ctx * ctx, const double * coeff, int ncoeff,
                                    int in, int out, double dt);
+/* ... followed by PostProcessSubstage(out) (DSS of state and tracers): the explicit
+ * substage of every time scheme.  On several ranks the halo exchange overlaps the
+ * elements that do not feed it when TB200_OVERLAP=1. */
+int tb200_hv_step_explicit_combine_dss(tb200_ctx * ctx, const double * coeff, int ncoeff,
+                                       int in, int out, double dt);
 /* VerticalDynamicsFEM::StepImplicit (VerticalDynamicsFEM.cpp:1230-1638). */
 int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt);
 /* Grid::CopyData(src -> dst) + VerticalDynamics::StepImplicit(dst, dst, ...) as the

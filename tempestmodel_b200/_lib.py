@@ -93,6 +93,8 @@ _SIGNATURES = {
     "tb200_hv_step_explicit": (c_int, [c_void_p, c_int, c_int, c_double]),
     "tb200_hv_step_explicit_combine": (c_int, [c_void_p, c_void_p, c_int, c_int,
                                                c_int, c_double]),
+    "tb200_hv_step_explicit_combine_dss": (c_int, [c_void_p, c_void_p, c_int, c_int,
+                                               c_int, c_double]),
     "tb200_set_terrain_metric": (c_int, [c_void_p, c_int, c_void_p, c_void_p,
                                          c_void_p]),
     "tb200_set_vertical_coordinate": (c_int, [c_void_p, c_void_p, c_void_p]),

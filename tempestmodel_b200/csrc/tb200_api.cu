@@ -69,7 +69,9 @@ static int dupload(tb200_ctx * ctx, T ** p, const std::vector<T> & v) {
 // memory both counted by the runtime) times the SM count, so that every block
 // of the launch is resident and walks the same number of elements.
 template <typename K>
-static long long persistent_blocks(tb200_ctx * ctx, K kfn, int threads, size_t smem, long long nwork) {
+static long long persistent_blocks(
+	tb200_ctx * ctx, K kfn, int threads, size_t smem, long long nwork, int reserve_sms = 0
+) {
 	int per_sm = 1;
 #ifndef TB200_EMU
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem) != cudaSuccess
@@ -80,11 +82,73 @@ static long long persistent_blocks(tb200_ctx * ctx, K kfn, int threads, size_t s
 	(void)kfn; (void)threads; (void)smem;
 	per_sm = 2;
 #endif
-	long long nb = (long long)ctx->sm_count * per_sm;
+	// reserve_sms: SMs left free for the pack kernel and the collective that run
+	// next to this launch (persistent blocks would otherwise hold every SM)
+	long long nb = (long long)std::max(1, ctx->sm_count - reserve_sms) * per_sm;
 	const char * fb = getenv("TB200_PIPE_BLOCKS");   // tests: force the multi-element loop
 	if (fb != 0 && atoi(fb) > 0) nb = atoi(fb);
 	if (nb > nwork) nb = nwork;
 	return nb;
+}
+
+// Multi-rank overlap of the halo exchange with compute: an element kernel that
+// is followed by a DSS runs first on the elements that own nodes of the send
+// list (same stream as the pack + exchange), and on all other elements on a
+// second stream while the exchange is in flight; dss_rows joins the two before
+// it averages.  part: 0 = every element on ctx->stream; 1 = exchange-feeding
+// elements on ctx->stream; 2 = the rest on ctx->stream2.
+// TB200_OVERLAP=1 turns the exchange / compute overlap on (off by default until
+// it is measured to pay on the target node count)
+static bool overlap_wanted() {
+	const char * ov = getenv("TB200_OVERLAP");
+	return ov != 0 && strcmp(ov, "1") == 0;
+}
+
+static int overlap_reserve() {
+	const char * r = getenv("TB200_OVERLAP_RESERVE");
+	return (r != 0) ? atoi(r) : 8;
+}
+
+static bool split_enabled(const tb200_ctx * ctx) {
+	return ctx->want_split && ctx->nranks > 1 && ctx->d_elist_bnd != 0 && ctx->n_int > 0;
+}
+
+static ElemList elem_list(const tb200_ctx * ctx, int part) {
+	ElemList el;
+	if (part == 1) { el.list = ctx->d_elist_bnd; el.n = ctx->n_bnd; }
+	else if (part == 2) { el.list = ctx->d_elist_int; el.n = ctx->n_int; }
+	else { el.list = 0; el.n = (int)ctx->lay.nelem; }
+	return el;
+}
+
+static int split_fork(tb200_ctx * ctx) {
+#ifndef TB200_EMU
+	if (ctx->stream2 == 0) {
+		TB_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+		TB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+		TB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+	}
+	TB_CHECK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+	TB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+#endif
+	return 0;
+}
+
+static int split_mark(tb200_ctx * ctx) {
+#ifndef TB200_EMU
+	TB_CHECK(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+#endif
+	ctx->split_pending = true;
+	return 0;
+}
+
+static int split_join(tb200_ctx * ctx) {
+	if (!ctx->split_pending) return 0;
+#ifndef TB200_EMU
+	TB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+#endif
+	ctx->split_pending = false;
+	return 0;
 }
 
 static PatchInfo * find_patch(tb200_ctx * ctx, int patch_index) {
@@ -1063,9 +1127,20 @@ static int nh_launch(
 #define TB_PIPE_LAUNCH(V, N) { \
 					auto kfn = k_nh_stage_pipe<V, N>; \
 					TB_PIPE_ATTR(kfn); \
-					const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem)); \
-					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ctx->phys, fa, \
-						(const double *)ctx->inst[in], pb, ctx->inst[out]); }
+					const bool split = split_enabled(ctx); \
+					if (split && split_fork(ctx)) return 1; \
+					for (int part = split ? 1 : 0; part <= (split ? 2 : 0); part++) { \
+						const ElemList el = elem_list(ctx, part); \
+						if (el.n == 0) continue; \
+						const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, el.n, \
+							(part == 2) ? overlap_reserve() : 0)); \
+						TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream, \
+							lay, ctx->tables, ctx->phys, fa, \
+							(const double *)ctx->inst[in], pb, ctx->inst[out], el); \
+						ctx->launches++; \
+					} \
+					ctx->launches--; \
+					if (split && split_mark(ctx)) return 1; }
 				if (do_v) {
 					if (pb.nsrc == 0) TB_PIPE_LAUNCH(true, 0)
 					else if (pb.nsrc == 1) TB_PIPE_LAUNCH(true, 1)
@@ -1190,6 +1265,24 @@ extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double d
 		return tb200_v_step_explicit(ctx, in, out, dt);
 	}
 	return nh_launch(ctx, in, out, dt, true, true, stage_base_out());
+}
+
+// The explicit substage as the time schemes issue it: combination + both
+// explicit plugins + PostProcessSubstage(out) (e.g. TimestepSchemeStrang.cpp:548-553).
+// On several ranks the halo exchange of the DSS overlaps the elements that do
+// not feed it.
+extern "C" int tb200_hv_step_explicit_combine(
+	tb200_ctx * ctx, const double * coeff, int ncoeff, int in, int out, double dt);
+
+extern "C" int tb200_hv_step_explicit_combine_dss(
+	tb200_ctx * ctx, const double * coeff, int ncoeff, int in, int out, double dt
+) {
+	ctx->want_split = overlap_wanted();
+	int rc = tb200_hv_step_explicit_combine(ctx, coeff, ncoeff, in, out, dt);
+	ctx->want_split = false;
+	if (rc == 0) rc = tb200_dss(ctx, out, TB200_DATA_STATE | TB200_DATA_TRACERS);
+	if (split_join(ctx)) return 1;
+	return rc;
 }
 
 // Grid::LinearCombineData(coeff, out) (or CopyData when ncoeff == 0: copy of
@@ -1598,6 +1691,8 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 			TB_FAIL(ctx, "exchange callback failed");
 		}
 	}
+	// elements that do not feed the exchange may still be in flight on stream2
+	if (split_join(ctx)) return 1;
 	if (ctx->ngroups == 0) return 0;
 	DssArgs a;
 	a.members = ctx->d_members;
@@ -1730,17 +1825,37 @@ static int hyper_fast(
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-		const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem));
-		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
-			(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out]);
+		const bool split = split_enabled(ctx);
+		if (split && split_fork(ctx)) return 1;
+		for (int part = split ? 1 : 0; part <= (split ? 2 : 0); part++) {
+			const ElemList el = elem_list(ctx, part);
+			if (el.n == 0) continue;
+			const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, el.n,
+				(part == 2) ? overlap_reserve() : 0));
+			TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream,
+				lay, ctx->tables, ha,
+				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out], el);
+			if (part != 0 && part != 2) ctx->launches++;
+		}
+		if (split && split_mark(ctx)) return 1;
 	} else {
 		auto kfn = k_hyper_pipe<false>;
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-		const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, lay.nelem));
-		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
-			(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out]);
+		const bool split = split_enabled(ctx);
+		if (split && split_fork(ctx)) return 1;
+		for (int part = split ? 1 : 0; part <= (split ? 2 : 0); part++) {
+			const ElemList el = elem_list(ctx, part);
+			if (el.n == 0) continue;
+			const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBF_THREADS, smem, el.n,
+				(part == 2) ? overlap_reserve() : 0));
+			TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream,
+				lay, ctx->tables, ha,
+				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out], el);
+			if (part != 0 && part != 2) ctx->launches++;
+		}
+		if (split && split_mark(ctx)) return 1;
 	}
 	TB_KERNEL_CHECK(ctx);
 	return 0;
@@ -1769,12 +1884,21 @@ static int h_step_after_subcycle_impl(
 		if (tb200_filter_negative_tracers(ctx, out)) return 1;
 		if (tb200_dss(ctx, out, all)) return 1;
 	} else if (c.hypervis_order == 4 && hyper_fast_ok(ctx)) {
-		// both Laplacian applications with ZeroData / CopyData folded in
-		if (hyper_fast(ctx, in, -1, work, 1.0, 1.0, 1.0, 1.0, false)) return 1;
-		if (tb200_dss(ctx, work, all)) return 1;
-		if (hyper_fast(ctx, work, in, out, -dt, c.nu_scalar, c.nu_div, c.nu_vort, true)) return 1;
-		if (tb200_dss(ctx, out, all)) return 1;
-		return 0;
+		// both Laplacian applications with ZeroData / CopyData folded in; each is
+		// followed by a DSS whose exchange overlaps the elements that do not feed it
+		const bool want = overlap_wanted();
+		ctx->want_split = want;
+		int rc = hyper_fast(ctx, in, -1, work, 1.0, 1.0, 1.0, 1.0, false);
+		ctx->want_split = false;
+		if (rc == 0) rc = tb200_dss(ctx, work, all);
+		if (split_join(ctx)) return 1;
+		if (rc) return 1;
+		ctx->want_split = want;
+		rc = hyper_fast(ctx, work, in, out, -dt, c.nu_scalar, c.nu_div, c.nu_vort, true);
+		ctx->want_split = false;
+		if (rc == 0) rc = tb200_dss(ctx, out, all);
+		if (split_join(ctx)) return 1;
+		return rc;
 	} else if (c.hypervis_order == 4) {
 		if (tb200_zero(ctx, work, all)) return 1;
 		if (hyper_scalar(ctx, in, work, 1.0, 1.0, false)) return 1;
@@ -1948,6 +2072,19 @@ extern "C" int tb200_build_connectivity(tb200_ctx * ctx) {
 		ctx->recv_count[r] = (int64_t)rl.size();
 	}
 	ctx->nsend_total = (int)send_nodes.size();
+	if (ctx->nranks > 1) {
+		// elements that own a node of the send list, and the rest
+		std::vector<char> feeds((size_t)ctx->lay.nelem, 0);
+		for (size_t q = 0; q < send_nodes.size(); q++) feeds[send_nodes[q] / nn] = 1;
+		std::vector<int> lb, li;
+		for (long long e = 0; e < ctx->lay.nelem; e++) {
+			(feeds[e] ? lb : li).push_back((int)e);
+		}
+		ctx->n_bnd = (int)lb.size();
+		ctx->n_int = (int)li.size();
+		if (dupload(ctx, &ctx->d_elist_bnd, lb)) return 1;
+		if (dupload(ctx, &ctx->d_elist_int, li)) return 1;
+	}
 	ctx->nrecv_total = slot;
 	if (dupload(ctx, &ctx->d_send_nodes, send_nodes)) return 1;
 

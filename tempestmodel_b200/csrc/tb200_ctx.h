@@ -97,6 +97,13 @@ struct tb200_ctx {
 	double * d_wold;                  // w before the implicit solve (tracer update)
 	int offd;
 
+	// exchange / compute overlap on several ranks
+	cudaStream_t stream2;
+	cudaEvent_t ev_fork, ev_join;
+	int * d_elist_bnd; int n_bnd;     // elements owning nodes of the send list
+	int * d_elist_int; int n_int;     // all other elements
+	bool want_split, split_pending;
+
 	int64_t launches;
 	int sm_count;
 
@@ -111,6 +118,8 @@ struct tb200_ctx {
 
 	tb200_ctx() :
 		stream(0), committed(false), connectivity_built(false),
+		stream2(0), ev_fork(0), ev_join(0), d_elist_bnd(0), n_bnd(0), d_elist_int(0), n_int(0),
+		want_split(false), split_pending(false),
 		d_stage(0), stage_doubles(0), d_rowmap(0),
 		d_inv_da(0), d_inv_db(0), d_nu_scale(0),
 		d_area_node(0), d_area_redge(0), d_sums(0),

@@ -106,6 +106,18 @@ __device__ __forceinline__ double tb_exner(const DevPhys & ph, double rhotheta) 
 	return ph.cp * exp(ph.exner_c1 * log(x));
 }
 
+// Elements a launch works on: all of them (list == 0, n = nelem) or an index
+// list (multi-rank: the elements that feed the halo exchange first, the rest on
+// a second stream while the exchange is in flight).
+struct ElemList {
+	const int * list;
+	int n;
+};
+
+__device__ __forceinline__ long long tb_elem(const ElemList & el, long long w) {
+	return (el.list != 0) ? (long long)el.list[w] : w;
+}
+
 struct FastArgs {
 	const double * colc;
 	const double * lev;
@@ -773,7 +785,7 @@ template <bool DO_V, int NSRC>
 __global__ void __launch_bounds__(TBF_THREADS, TBP_MINBLOCKS)
 k_nh_stage_pipe(
 	DevLayout lay, DevTables t, DevPhys ph, FastArgs fa,
-	const double * __restrict__ in, PipeBase pb, double * out
+	const double * __restrict__ in, PipeBase pb, double * out, ElemList el
 ) {
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
@@ -812,8 +824,9 @@ k_nh_stage_pipe(
 		stI[s] = t.st[i * NP + s];
 	}
 
-	long long e = blockIdx.x;
-	if (e >= lay.nelem) return;
+	long long w = blockIdx.x;          // position in the element list
+	if (w >= el.n) return;
+	long long e = tb_elem(el, w);
 	{
 		const size_t eb = (size_t)e * esz;
 		for (int q = tid; q < nchunk; q += TBF_THREADS) {
@@ -832,7 +845,8 @@ k_nh_stage_pipe(
 		tb_cp_commit();
 	}
 
-	for (int it = 0; e < lay.nelem; it++, e += gridDim.x) {
+	for (int it = 0; w < el.n; it++, w += gridDim.x) {
+		e = tb_elem(el, w);
 		const int buf = it & 1;
 		const double * inb = inb0 + (size_t)buf * esz;
 		// the data of this element (issued one iteration ago) has landed, and
@@ -855,8 +869,8 @@ k_nh_stage_pipe(
 		}
 		// prefetch the next element of this block into the other buffer
 		{
-			const long long en = e + gridDim.x;
-			if (en < lay.nelem) {
+			if (w + gridDim.x < el.n) {
+				const long long en = tb_elem(el, w + gridDim.x);
 				const size_t eb = (size_t)en * esz;
 				double * di = inb0 + (size_t)(buf ^ 1) * esz;
 				double * db = bsb0 + (size_t)(buf ^ 1) * esz;
@@ -1215,7 +1229,7 @@ template <bool HAS_BASE>
 __global__ void __launch_bounds__(TBF_THREADS, 2)
 k_hyper_pipe(
 	DevLayout lay, DevTables t, HyperFastArgs ha,
-	const double * __restrict__ fld, const double * base, double * out
+	const double * __restrict__ fld, const double * base, double * out, ElemList el
 ) {
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
@@ -1247,8 +1261,9 @@ k_hyper_pipe(
 		stI[s] = t.st[i * NP + s];
 	}
 
-	long long e = blockIdx.x;
-	if (e >= lay.nelem) return;
+	long long w = blockIdx.x;          // position in the element list
+	if (w >= el.n) return;
+	long long e = tb_elem(el, w);
 	{
 		const size_t eb = (size_t)e * esz;
 		for (int q = tid; q < nchunk; q += TBF_THREADS) {
@@ -1263,15 +1278,16 @@ k_hyper_pipe(
 		tb_cp_commit();
 	}
 
-	for (int it = 0; e < lay.nelem; it++, e += gridDim.x) {
+	for (int it = 0; w < el.n; it++, w += gridDim.x) {
+		e = tb_elem(el, w);
 		const int buf = it & 1;
 		const double * fb = fb0 + (size_t)buf * esz;
 		const double * bb = bb0 + (size_t)buf * esz;
 		tb_cp_wait<0>();
 		__syncthreads();
 		{
-			const long long en = e + gridDim.x;
-			if (en < lay.nelem) {
+			if (w + gridDim.x < el.n) {
+				const long long en = tb_elem(el, w + gridDim.x);
 				const size_t eb = (size_t)en * esz;
 				double * df = fb0 + (size_t)(buf ^ 1) * esz;
 				double * db = bb0 + (size_t)(buf ^ 1) * esz;

@@ -94,8 +94,7 @@ static int lincomb(tb200_ctx * ctx, const std::vector<double> & c, int dst) {
 // combination formed inside the stage kernel
 static int substage_from(tb200_ctx * ctx, std::vector<double> c, int in, int out, double dt) {
 	if ((int)c.size() <= out) c.resize(out + 1, 0.0);
-	TRY(tb200_hv_step_explicit_combine(ctx, c.data(), (int)c.size(), in, out, dt));
-	TRY(tb200_dss(ctx, out, ALL));
+	TRY(tb200_hv_step_explicit_combine_dss(ctx, c.data(), (int)c.size(), in, out, dt));
 	return 0;
 }
 
