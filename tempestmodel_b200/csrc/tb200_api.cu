@@ -1411,7 +1411,8 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 		fa.colc = ctx->d_colc;
 		fa.lev = ctx->d_lev;
 		fa.inc = ctx->column_inc;
-		const size_t smem = (size_t)(lay.nlev + 1) * TBF_LW * sizeof(double);
+		const size_t smem = (size_t)(lay.nlev + 1) * TBF_LW * sizeof(double)
+			+ (size_t)(TBC_THREADS / 32) * 3 * (lay.nlev + 1) * sizeof(unsigned);
 		auto kfn = k_column_fast;
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -21,10 +21,13 @@
 //    for step: same pivot search, interchange, reciprocal scaling, rank-1
 //    update; rows that are structurally zero in the pivot column enter late;
 //  * finished rows of U and the forward-substituted right-hand side stream to
-//    a scratch laid out [block][step][10][thread] (coalesced, compile-time
-//    offsets); the back substitution reads them once, in dtbsv order, one level
-//    prefetched ahead, and scatters x = x0 - delta to the column and its
-//    duplicates.
+//    a per-warp scratch [entry][lane] (coalesced); the solve is bound by that
+//    traffic, so entries of a row that are zero in every lane of the warp are
+//    not stored (the pivot order this matrix takes leaves 2-4 of the 8
+//    off-diagonal entries of a row of U zero): a warp vote builds the row's mask,
+//    kept in shared memory.  The back substitution reads the rows once, in
+//    dtbsv order, one level prefetched ahead, and scatters x = x0 - delta to
+//    the column and its duplicates.
 #ifndef TB200_COLUMN_FAST_CUH
 #define TB200_COLUMN_FAST_CUH
 
@@ -70,10 +73,13 @@ k_column_fast(
 	DevLayout lay, DevPhys ph, ColumnFastArgs ca,
 	const double * in, double * out   // may alias
 ) {
-	TB_DYN_SMEM(double, slev);          // [L+1][TBF_LW]
+	TB_DYN_SMEM(double, slev);          // [L+1][TBF_LW], then row masks [warps][n]
 	const int L = lay.nlev;
 	const int NN = lay.nn;
 	const int n = 3 * (L + 1);
+	unsigned * smask = reinterpret_cast<unsigned *>(slev + (size_t)(L + 1) * TBF_LW)
+		+ (size_t)(threadIdx.x >> 5) * n;
+	const unsigned FULL = 0xffffffffu;
 	for (int q = threadIdx.x; q < (L + 1) * TBF_LW; q += blockDim.x) {
 		slev[q] = ca.lev[q];
 	}
@@ -107,9 +113,13 @@ k_column_fast(
 
 	// scratch of this block: step j -> [10 j + c][thread], c = 0..8 row j of U,
 	// c = 9 right-hand side
-	const int S = TBC_THREADS;
-	double * sc = ca.ws + (size_t)blockIdx.x * (10 * n) * S + threadIdx.x;
-	double * scp = sc;      // entry of the current elimination step
+	// scratch of this warp: entries [slot][lane]; a step stores the pivot, the
+	// right-hand side and the off-diagonal entries of its mask
+	const int S = 32;
+	double * sc = ca.ws
+		+ ((size_t)blockIdx.x * (TBC_THREADS / 32) + (threadIdx.x >> 5)) * (size_t)(10 * n) * S
+		+ (threadIdx.x & 31);
+	double * scp = sc;      // next free slot
 
 	// ---- sliding input window ------------------------------------------------------
 	// levels k-1, k, k+1 (m, 0, p) and the prefetched level k+2 (q)
@@ -410,12 +420,25 @@ k_column_fast(
 		} else if (info == 0) {
 			info = jstep + 1;
 		}
+		{
+			unsigned m = 0;
 #pragma unroll
-		for (int c = 0; c < 9; c++) {
-			scp[c * S] = B[0][c];
+			for (int c = 1; c < 9; c++) {
+				if (__any_sync(FULL, B[0][c] != 0.0)) m |= (1u << c);
+			}
+			scp[0] = B[0][0];
+			scp[S] = bb[0];
+			int slot = 2;
+#pragma unroll
+			for (int c = 1; c < 9; c++) {
+				if (m & (1u << c)) {
+					scp[slot * S] = B[0][c];
+					slot++;
+				}
+			}
+			scp += slot * S;
+			if ((threadIdx.x & 31) == 0) smask[jstep] = m;
 		}
-		scp[9 * S] = bb[0];
-		scp += 10 * S;
 #pragma unroll
 		for (int r = 0; r < 4; r++) {
 #pragma unroll
@@ -465,6 +488,7 @@ k_column_fast(
 		eliminate();          // j = 3k + 1
 		eliminate();          // j = 3k + 2
 	}
+	__syncwarp();          // the row masks of this warp are complete
 	if (info != 0) {
 		if (live) atomicMax(ca.info, ca.col0 + tcol + 1);
 		return;
@@ -486,25 +510,34 @@ k_column_fast(
 	// level k: steps 3k+2, 3k+1, 3k; the scratch rows and the old state of the
 	// next level to be processed (k-1) are loaded while level k is computed
 	double ucur[3][10], x0cur[3];
-	{
-		const double * q = sc + (size_t)(10 * 3 * L) * S;
+	// rows of level k (steps 3k+2, 3k+1, 3k) from the compacted scratch; scp
+	// walks backwards
+	auto load_level = [&](int k, double (&u)[3][10]) {
 #pragma unroll
-		for (int c3 = 0; c3 < 3; c3++) {
+		for (int c3 = 2; c3 >= 0; c3--) {
+			const unsigned m = smask[3 * k + c3];
+			scp -= (2 + __popc(m)) * S;
+			u[c3][0] = scp[0];
+			u[c3][9] = scp[S];
+			int slot = 2;
 #pragma unroll
-			for (int c = 0; c < 10; c++) ucur[c3][c] = q[(10 * c3 + c) * S];
+			for (int c = 1; c < 9; c++) {
+				if (m & (1u << c)) {
+					u[c3][c] = scp[slot * S];
+					slot++;
+				} else {
+					u[c3][c] = 0.0;
+				}
+			}
 		}
-		x0cur[0] = 0.0; x0cur[2] = 0.0;
-		x0cur[1] = in[ebase + (size_t)(rowW + L) * NN + nd];
-	}
+	};
+	load_level(L, ucur);
+	x0cur[0] = 0.0; x0cur[2] = 0.0;
+	x0cur[1] = in[ebase + (size_t)(rowW + L) * NN + nd];
 	for (int k = L; k >= 0; k--) {
 		double unext[3][10], x0next[3];
 		if (k > 0) {
-			const double * q = sc + (size_t)(10 * 3 * (k - 1)) * S;
-#pragma unroll
-			for (int c3 = 0; c3 < 3; c3++) {
-#pragma unroll
-				for (int c = 0; c < 10; c++) unext[c3][c] = q[(10 * c3 + c) * S];
-			}
+			load_level(k - 1, unext);
 			x0next[0] = in[ebase + (size_t)(rowP + k - 1) * NN + nd];
 			x0next[1] = in[ebase + (size_t)(rowW + k - 1) * NN + nd];
 			x0next[2] = in[ebase + (size_t)(rowR + k - 1) * NN + nd];

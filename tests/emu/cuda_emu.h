@@ -226,6 +226,20 @@ inline int __shfl_down_sync(unsigned m, int v, unsigned delta, int width = 32) {
 	return (int)__shfl_down_sync(m, (double)v, delta, width);
 }
 
+inline int __any_sync(unsigned, int pred) {
+	tbemu::Sched & g = tbemu::G();
+	unsigned t = g.cur, w = t / 32, lane = t % 32;
+	// lanes beyond the block's thread count do not exist: their slots must not vote
+	const unsigned nlanes = (g.nthreads - w * 32 < 32) ? (g.nthreads - w * 32) : 32;
+	g.wbuf[w][lane] = pred ? 1.0 : 0.0;
+	tbemu::Yield(tbemu::AT_WBAR);
+	int r = 0;
+	for (unsigned l = 0; l < nlanes; l++) r |= (g.wbuf[w][l] != 0.0);
+	tbemu::Yield(tbemu::AT_WBAR);
+	return r;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+
 inline double __ldg(const double * p) { return *p; }
 inline int __ldg(const int * p) { return *p; }
 inline double atomicAdd(double * p, double v) { double o = *p; *p += v; return o; }
