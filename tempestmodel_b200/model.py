@@ -50,7 +50,8 @@ class Model:
             vertical_order=grid.vertical_order, ncomp=self.ncomp, ntracers=0,
             ninstances=SCHEME_INSTANCES[self.timescheme],
             eqn_type=EQN_SHALLOW_WATER if sw else EQN_PRIMITIVE_NONHYDRO,
-            cartesian_xz=0, comp_on_redge=onedge, device=device,
+            cartesian_xz=1 if getattr(grid, "xz", False) else 0,
+            comp_on_redge=onedge, device=device,
             g=ph.g, R=ph.R, cp=ph.cp, cv=ph.cv, p0=ph.p0, omega=ph.omega,
             earth_radius=ph.earth_radius, ztop=grid.ztop,
             ref_length=grid.reference_length, hypervis_order=hypervis_order,
@@ -66,8 +67,9 @@ class Model:
     def initialize(self, upload_state=True):
         g, ctx = self.grid, self.ctx
         for p in g.patches:
-            ctx.add_patch(p.index, p.panel, p.nea, p.neb, p.halo, p.delta,
-                          p.delta, self.owners[p.index])
+            ctx.add_patch(p.index, p.panel, p.nea, p.neb, p.halo,
+                          getattr(p, "delta_a", p.delta), getattr(p, "delta_b", p.delta),
+                          self.owners[p.index])
         ctx.commit_layout()
         ctx.set_tables(g.dx, g.stiffness, g.gll_weights)
         for i, name in enumerate(OP_NAMES):
@@ -123,8 +125,12 @@ class Model:
         else:
             st = test.evaluate_pointwise_state(ph, z, lon, lat)
         st = [np.broadcast_to(s, np.broadcast(z, lon).shape) for s in st]
-        ua, ub = G.covec_abp_from_rll(p.XX[:, :, None], p.YY[:, :, None], p.panel,
-                                      st[0] * ph.earth_radius, st[1] * ph.earth_radius)
+        if getattr(g, "is_cartesian", False):
+            # the metric is the identity: covariant = physical components
+            ua, ub = st[0], st[1]
+        else:
+            ua, ub = G.covec_abp_from_rll(p.XX[:, :, None], p.YY[:, :, None], p.panel,
+                                          st[0] * ph.earth_radius, st[1] * ph.earth_radius)
         node[0, 1:-1, 1:-1] = ua
         node[1, 1:-1, 1:-1] = ub
         if test.equation_set == "shallow_water":

@@ -203,3 +203,34 @@ class BaroclinicWaveJWTest:
             r = r / self.pert_r
             st[0] = st[0] + xp.where(r < 1.0, self.up * xp.exp(-r * r), xp.zeros_like(r))
         return st
+
+
+class ThermalBubbleCartesianTest:
+    """Rising thermal bubble on an x-z slice
+    (reference test/nonhydro_xz/ThermalBubbleCartesianTest.cpp:75-285)."""
+
+    equation_set = "primitive_nonhydro"
+    # x0, x1, y0, y1, z0, z1 (:93-99)
+    dims = (0.0, 1000.0, -500.0, 500.0, 0.0, 1000.0)
+    ztop = 1000.0
+
+    def __init__(self, theta_bar=300.0, theta_c=0.5, r_c=250.0, x_c=500.0, z_c=350.0,
+                 pi_c=3.14159265):
+        self.theta_bar, self.theta_c = theta_bar, theta_c
+        self.r_c, self.x_c, self.z_c, self.pi_c = r_c, x_c, z_c, pi_c
+
+    def evaluate_topography(self, phys, x, y):
+        return np.zeros_like(x)
+
+    def evaluate_pointwise_state(self, phys, z, x, y, xp=NUMPY):
+        """-> [u, v, theta, w, rho] (:236-268); u, v are the covariant components
+        themselves on the Cartesian grid."""
+        rp = xp.sqrt((x - self.x_c) * (x - self.x_c) + (z - self.z_c) * (z - self.z_c))
+        tprime = xp.where(rp <= self.r_c,
+                          0.5 * self.theta_c * (1.0 + xp.cos(self.pi_c * rp / self.r_c)),
+                          0.0 * rp)
+        theta = self.theta_bar + tprime
+        exner = -phys.g / (phys.cp * self.theta_bar) * z + 1.0
+        rho = phys.p0 / (phys.R * self.theta_bar) * exner ** (phys.cv / phys.R) + 0.0 * x
+        zero = 0.0 * rho
+        return [zero, zero, theta, zero, rho]

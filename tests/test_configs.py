@@ -52,3 +52,83 @@ def test_config1_sw2_ne20_checksums(cuda_library):
     # V sums to rounding noise of U-sized terms
     assert abs(cs[1] - CONFIG1["V"]) <= 1e-12 * abs(CONFIG1["U"])
     model.ctx.close()
+
+
+def test_cartesian_python_setup_matches_reference():
+    """GridCartesianGLL / ThermalBubbleCartesianTest of the Python driver against
+    the reference's own arrays (golden bubble dump): coordinates, metric, element
+    areas and the initial state."""
+    import cases
+    from tempestmodel_b200.cartesian import GridCartesianGLL
+    d = cases.load_case("bubble_r6_l8")
+    test = TC.ThermalBubbleCartesianTest()
+    grid = GridCartesianGLL(6, 1, 8, test.dims)
+    grid.evaluate_topography(test)
+    p = grid.patches[0]
+    geo = p.evaluate_geometric_terms(p._zs, p._dazs, p._dbzs)
+    I = (slice(1, -1), slice(1, -1))
+    assert np.allclose(d["patch0.anode"][1:-1], p.anode, rtol=0, atol=1e-12)
+    assert np.allclose(d["patch0.bnode"][1:-1], p.bnode, rtol=0, atol=1e-12)
+    for key, name in (("jacobian2d", "jacobian2d"), ("contrametric2da", "contrametric2da"),
+                      ("jacobian", "jacobian"), ("jacobianredge", "jacobian_redge"),
+                      ("contrametrica", "contrametrica"), ("contrametricxi", "contrametricxi"),
+                      ("contrametricxiredge", "contrametricxi_redge"),
+                      ("derivrnode", "derivr_node"), ("derivrredge", "derivr_redge")):
+        ref = d["patch0." + key][I]
+        got = geo[name][I]
+        assert np.abs(got - ref).max() <= 1e-14 * max(np.abs(ref).max(), 1e-300), key
+    assert np.abs(p.area_node[I] - d["patch0.elementareanode"][I]).max() \
+        <= 1e-13 * np.abs(d["patch0.elementareanode"]).max()
+    # initial state (u, v, rho-theta, rho on levels; the golden w carries the
+    # test's added perturbation)
+    node, redge = Model.evaluate_test_case(
+        type("S", (), dict(grid=grid, test=test, ncomp=5, device_setup=False))(), p)
+    ref = d["ic.patch0.inst0.node"]
+    for c in (0, 1, 2, 4):
+        assert np.abs(node[c][I] - ref[c][I]).max() <= 1e-13 * max(np.abs(ref[c]).max(), 1.0), c
+    # one element across the periodic y direction: its two y-edges are duplicates
+    ids = p.node_ids()
+    assert np.array_equal(ids[:, 0], ids[:, 3])
+
+
+def test_cartesian_python_driver_steps(emu_library):
+    """The bubble through Model on the emulation library: three steps run, mass
+    and rho-theta are conserved to rounding."""
+    from tempestmodel_b200.cartesian import GridCartesianGLL
+    test = TC.ThermalBubbleCartesianTest()
+    grid = GridCartesianGLL(6, 1, 8, test.dims)
+    model = Model(grid, test, timescheme="strang", dt=0.01, no_hypervis=True,
+                  library=emu_library)
+    model.initialize()
+    assert model.ctx.fast_path()[0], model.ctx.fast_path()
+    c0 = model.checksum(0)
+    model.step(3, last=True)
+    model.ctx.check_errors()
+    c1 = model.checksum(0)
+    assert abs(c1[4] - c0[4]) <= 1e-13 * abs(c0[4])
+    assert abs(c1[2] - c0[2]) <= 1e-13 * abs(c0[2])
+    assert c1[3] != 0.0          # the bubble has started to rise
+    model.ctx.close()
+
+
+# ThermalBubbleCartesianTest --dt 10000u --endtime 1s --nohypervis --output_none
+# (resx = 36, 72 levels, 100 steps): checksums of the unmodified reference
+CONFIG2 = dict(RhoTheta=3.345218421487319e+11, W=1.698392084434990e+10,
+               Rho=1.114962976498227e+09)
+
+
+@pytest.mark.gpu
+def test_config2_bubble_checksums(cuda_library):
+    from tempestmodel_b200.cartesian import GridCartesianGLL
+    test = TC.ThermalBubbleCartesianTest()
+    grid = GridCartesianGLL(36, 1, 72, test.dims)
+    model = Model(grid, test, timescheme="strang", dt=0.01, no_hypervis=True,
+                  library=cuda_library)
+    model.initialize()
+    model.step(100, last=True)
+    model.ctx.check_errors()
+    cs = model.checksum(0)
+    assert abs(cs[4] - CONFIG2["Rho"]) <= 1e-12 * abs(CONFIG2["Rho"])
+    assert abs(cs[2] - CONFIG2["RhoTheta"]) <= 1e-12 * abs(CONFIG2["RhoTheta"])
+    assert abs(cs[3] - CONFIG2["W"]) <= 1e-6 * abs(CONFIG2["W"])
+    model.ctx.close()
