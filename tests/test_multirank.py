@@ -10,13 +10,13 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(backend, nproc=2, port=29611):
+def _run(backend, nproc=2, port=29611, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "_multirank_worker.py"),
            backend, "jw_ne2_l6_strang", "strang"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                         text=True, timeout=900)
+                         text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert res.returncode == 0, res.stdout[-3000:]
     assert "MULTIRANK worst=" in res.stdout, res.stdout[-3000:]
     return res.stdout
@@ -26,9 +26,23 @@ def test_two_ranks_gloo(emu_library):
     _run("gloo")
 
 
+def test_two_ranks_gloo_overlap(emu_library):
+    """Element-list launches of the persistent kernels (exchange-feeding elements
+    first, the rest on the second stream): same state."""
+    _run("gloo", port=29613, env={"TB200_OVERLAP": "1"})
+
+
 @pytest.mark.gpu
 def test_two_ranks_nccl(cuda_library):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run("nccl", port=29612)
+
+
+@pytest.mark.gpu
+def test_two_ranks_nccl_overlap(cuda_library):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("nccl", port=29614, env={"TB200_OVERLAP": "1"})
