@@ -41,6 +41,16 @@
 		} \
 	} while (0)
 
+// error check of launches that were counted one by one
+#define TB_LAUNCH_CHECK(ctx) \
+	do { \
+		cudaError_t e__ = cudaGetLastError(); \
+		if (e__ != cudaSuccess) { \
+			(ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__); \
+			return 1; \
+		} \
+	} while (0)
+
 static const int kItems = 8;   // (element, level) pairs per block in the slab kernels
 
 template <typename T>
@@ -1139,7 +1149,6 @@ static int nh_launch(
 							(const double *)ctx->inst[in], pb, ctx->inst[out], el); \
 						ctx->launches++; \
 					} \
-					ctx->launches--; \
 					if (split && split_mark(ctx)) return 1; }
 				if (do_v) {
 					if (pb.nsrc == 0) TB_PIPE_LAUNCH(true, 0)
@@ -1152,7 +1161,7 @@ static int nh_launch(
 				}
 #undef TB_PIPE_LAUNCH
 #undef TB_PIPE_ATTR
-				TB_KERNEL_CHECK(ctx);
+				TB_LAUNCH_CHECK(ctx);
 				return 0;
 			}
 		}
@@ -1836,7 +1845,7 @@ static int hyper_fast(
 			TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream,
 				lay, ctx->tables, ha,
 				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out], el);
-			if (part != 0 && part != 2) ctx->launches++;
+			ctx->launches++;
 		}
 		if (split && split_mark(ctx)) return 1;
 	} else {
@@ -1854,11 +1863,11 @@ static int hyper_fast(
 			TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream,
 				lay, ctx->tables, ha,
 				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out], el);
-			if (part != 0 && part != 2) ctx->launches++;
+			ctx->launches++;
 		}
 		if (split && split_mark(ctx)) return 1;
 	}
-	TB_KERNEL_CHECK(ctx);
+	TB_LAUNCH_CHECK(ctx);
 	return 0;
 }
 
