@@ -1718,14 +1718,27 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 	a.sel_row0 = row0;
 	{
 		const int block = 128;
-		int gy = std::min(nsel, 4);
+		static const bool classes = []() {  // TB200_DSS_KERNEL=generic: row-at-a-time kernel for every group
+			const char * e = getenv("TB200_DSS_KERNEL");
+			return !(e != 0 && strcmp(e, "generic") == 0);
+		}();
+		// one batch of TBD_B rows per thread measured best (0.76 ms against
+		// 0.79 ms with 38 rows per thread at ne=120, L=30); the row-at-a-time
+		// kernel wants its prologue amortised over more rows
+		int gy = classes ? (nsel + TBD_B - 1) / TBD_B : std::min(nsel, 4);
 		{
 			const char * g = getenv("TB200_DSS_GY");
 			if (g != 0 && atoi(g) > 0) gy = std::min(nsel, atoi(g));
 		}
-		auto kfn = k_dss_scalar;
-		TB_LAUNCH_FLAT(kfn, dim3((ctx->ngroups + block - 1) / block, gy), dim3(block), 0,
-			ctx->stream, lay, a, ctx->inst[inst]);
+		if (classes) {
+			auto kfn = k_dss_fast;
+			TB_LAUNCH_FLAT(kfn, dim3((ctx->ngroups + block - 1) / block, gy), dim3(block), 0,
+				ctx->stream, lay, a, ctx->inst[inst]);
+		} else {
+			auto kfn = k_dss_scalar;
+			TB_LAUNCH_FLAT(kfn, dim3((ctx->ngroups + block - 1) / block, gy), dim3(block), 0,
+				ctx->stream, lay, a, ctx->inst[inst]);
+		}
 		TB_KERNEL_CHECK(ctx);
 	}
 	if (is_state && ctx->nseam > 0) {
@@ -2120,7 +2133,12 @@ extern "C" int tb200_build_connectivity(tb200_ctx * ctx) {
 					ctx->patches[m.ppos].index, std::make_pair(m.ia, m.ib))];
 			}
 		}
-		if (!gr.seam) continue;
+		if (!gr.seam) {
+			bool local = (gr.mem.size() == 2 || gr.mem.size() == 4);
+			for (size_t q = 0; q < gr.mem.size(); q++) local = local && gr.mem[q].addr >= 0;
+			if (local) flags[gi] = 2;
+			continue;
+		}
 		flags[gi] = 1;
 		seam_group.push_back((int)gi);
 		const size_t base = seam_mats.size();

@@ -21,7 +21,7 @@
 
 struct DssArgs {
 	const int * members;      // [ngroups][4], -1 = unused; >= nlocal: remote slot
-	const int * flags;        // [ngroups] bit0: group spans a panel seam
+	const int * flags;        // [ngroups] bit0: group spans a panel seam; bit1: 2 or 4 members, all local, no seam
 	int ngroups;
 	int nlocal;               // number of local element nodes (nelem * NN)
 	const double * recv;      // [slot][nsel]
@@ -76,9 +76,9 @@ __device__ __forceinline__ DssRef tb_dss_ref(
 	return r;
 }
 
-__global__ void k_dss_scalar(DevLayout lay, DssArgs a, double * data) {
-	const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (gidx >= a.ngroups) return;
+__device__ __forceinline__ void tb_dss_generic(
+	const DevLayout & lay, const DssArgs & a, int gidx, double * data
+) {
 	const int m2 = a.members[4 * gidx + 2];
 	const int m3 = a.members[4 * gidx + 3];
 	const DssRef r0 = tb_dss_ref(lay, a, data, a.members[4 * gidx + 0]);
@@ -111,6 +111,88 @@ __global__ void k_dss_scalar(DevLayout lay, DssArgs a, double * data) {
 		if (r1.w != 0) r1.w[(size_t)r * r1.stride] = avg;
 		if (r2.w != 0) r2.w[(size_t)r * r2.stride] = avg;
 		if (r3.w != 0) r3.w[(size_t)r * r3.stride] = avg;
+	}
+}
+
+__global__ void k_dss_scalar(DevLayout lay, DssArgs a, double * data) {
+	const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (gidx >= a.ngroups) return;
+	tb_dss_generic(lay, a, gidx, data);
+}
+
+// Groups whose 2 or 4 members are all local and off the panel seams (flag
+// bit 1; every group but the seam and rank-boundary ones): the loads of B rows
+// are issued before the first store (the members alias as far as the compiler
+// can tell, so the row-at-a-time loop above serialises on every store) and the
+// member pointers just step by one row.  Groups stay ordered by the address of
+// their first member, so every row of an element is touched within one wave
+// of blocks and comes from DRAM once.
+template <int B>
+__device__ __forceinline__ void tb_dss_local(
+	const DevLayout & lay, const DssArgs & a, int gidx, double * data
+) {
+	const int rows_per = (a.row1 - a.row0 + gridDim.y - 1) / gridDim.y;
+	const int rbeg = a.row0 + blockIdx.y * rows_per;
+	const int rend = (rbeg + rows_per < a.row1) ? (rbeg + rows_per) : a.row1;
+	const int nn = lay.nn;
+	const int4 m = ((const int4 *)a.members)[gidx];
+	const bool four = m.z >= 0;
+	double * p0 = data + tb_dss_base(lay, m.x) + (size_t)rbeg * nn;
+	double * p1 = data + tb_dss_base(lay, m.y) + (size_t)rbeg * nn;
+	double * p2 = four ? data + tb_dss_base(lay, m.z) + (size_t)rbeg * nn : p0;
+	double * p3 = four ? data + tb_dss_base(lay, m.w) + (size_t)rbeg * nn : p1;
+	int r = rbeg;
+	for (; r + B <= rend; r += B) {
+		double v0[B], v1[B], v2[B], v3[B];
+#pragma unroll
+		for (int b = 0; b < B; b++) {
+			v0[b] = p0[b * nn];
+			v1[b] = p1[b * nn];
+			if (four) {
+				v2[b] = p2[b * nn];
+				v3[b] = p3[b * nn];
+			}
+		}
+#pragma unroll
+		for (int b = 0; b < B; b++) {
+			double avg = 0.5 * (v0[b] + v1[b]);
+			if (four) avg = 0.5 * (avg + 0.5 * (v2[b] + v3[b]));
+			p0[b * nn] = avg;
+			p1[b * nn] = avg;
+			if (four) {
+				p2[b * nn] = avg;
+				p3[b * nn] = avg;
+			}
+		}
+		p0 += B * nn; p1 += B * nn; p2 += B * nn; p3 += B * nn;
+	}
+	for (; r < rend; r++) {
+		const double v0 = p0[0], v1 = p1[0];
+		double avg = 0.5 * (v0 + v1);
+		if (four) avg = 0.5 * (avg + 0.5 * (p2[0] + p3[0]));
+		p0[0] = avg;
+		p1[0] = avg;
+		if (four) {
+			p2[0] = avg;
+			p3[0] = avg;
+		}
+		p0 += nn; p1 += nn; p2 += nn; p3 += nn;
+	}
+}
+
+#ifndef TBD_B
+#define TBD_B 4
+#endif
+#ifndef TBD_MINB
+#define TBD_MINB 8
+#endif
+__global__ void __launch_bounds__(128, TBD_MINB) k_dss_fast(DevLayout lay, DssArgs a, double * data) {
+	const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (gidx >= a.ngroups) return;
+	if (a.flags[gidx] & 2) {
+		tb_dss_local<TBD_B>(lay, a, gidx, data);
+	} else {
+		tb_dss_generic(lay, a, gidx, data);
 	}
 }
 

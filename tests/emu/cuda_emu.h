@@ -33,6 +33,8 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 
+struct int4 { int x, y, z, w; };
+
 struct dim3 {
 	unsigned x, y, z;
 	dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
