@@ -894,6 +894,7 @@ extern "C" int tb200_copy(tb200_ctx * ctx, int src, int dst, int mask) {
 		const size_t bytes = (size_t)ctx->lay.nelem * ctx->lay.nrows * ctx->lay.nn * sizeof(double);
 		TB_CHECK(ctx, cudaMemcpyAsync(ctx->inst[dst], ctx->inst[src], bytes,
 			cudaMemcpyDeviceToDevice, ctx->stream));
+		ctx->uvzero_inst = -1;      // not a counted launch
 		return 0;
 	}
 	CombineArgs ca;
@@ -926,6 +927,17 @@ extern "C" int tb200_lincomb(
 	if (ca.nsrc == 0 && ca.scale_dst && ca.cdst == 1.0) return 0;
 	int row0, row1;
 	mask_rows(ctx, mask, row0, row1);
+	// dest += c * (the increment the Strang tail just wrote): its u, v rows are
+	// zero, so those rows of dest stay as they are (Strang carry-over,
+	// TimestepSchemeStrang.cpp:470-482)
+	if (ca.nsrc == 1 && ca.scale_dst && ca.cdst == 1.0 && ctx->uvzero_inst >= 0
+		&& ca.src[0] == ctx->inst[ctx->uvzero_inst] && ctx->launches == ctx->uvzero_launches
+		&& row0 == 0 && ctx->lay.rowoff[0] == 0
+		&& ctx->lay.rowoff[1] == ctx->lay.rowlev[0]
+		&& getenv("TB200_CARRY_FULL") == 0      // test switch: combine every row
+	) {
+		row0 = ctx->lay.rowoff[1] + ctx->lay.rowlev[1];
+	}
 	return launch_combine(ctx, ca, dst, row0, row1);
 }
 
@@ -1568,7 +1580,10 @@ extern "C" int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst
 	// u, v rows of the increment
 	CombineArgs zero;
 	memset(&zero, 0, sizeof(zero));
-	return launch_combine(ctx, zero, src, uv0, uv1);
+	if (launch_combine(ctx, zero, src, uv0, uv1)) return 1;
+	ctx->uvzero_inst = src;
+	ctx->uvzero_launches = ctx->launches;
+	return 0;
 }
 
 // Debugging aid: assemble F and the banded Jacobian of the first launch chunk

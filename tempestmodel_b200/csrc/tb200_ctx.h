@@ -105,6 +105,11 @@ struct tb200_ctx {
 	bool want_split, split_pending;
 
 	int64_t launches;
+	// instance whose u, v rows are known to be zero (the increment written by
+	// tb200_copy_v_step_implicit_diff) as long as `launches` still equals
+	// uvzero_launches, i.e. nothing has run since; -1 = none
+	int uvzero_inst;
+	int64_t uvzero_launches;
 	int sm_count;
 
 	// fast path (tb200_fast.cuh): 0 = not examined, 1 = enabled, -1 = unavailable
@@ -129,7 +134,7 @@ struct tb200_ctx {
 		nsend_total(0), nrecv_total(0), d_send_nodes(0), d_sendbuf(0),
 		d_recvbuf(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0),
 		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false),
-		column_inc(0), d_wold(0), offd(4), launches(0),
+		column_inc(0), d_wold(0), offd(4), launches(0), uvzero_inst(-1), uvzero_launches(0),
 		fast_state(0), fast_metric_error(0.0), d_colc(0), d_lev(0),
 		geometry3d_uploaded(false)
 	{

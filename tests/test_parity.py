@@ -277,6 +277,34 @@ def test_fast_path_equals_general_kernels(library, monkeypatch):
                 assert np.abs(a[c] - b[c]).max() <= 1e-12 * tend + 4e-16 * np.abs(a[c]).max()
 
 
+def test_strang_carry_over_rows(library, monkeypatch):
+    """The Strang carry-over `state += increment` skips the u, v rows when the
+    increment is the one the implicit tail just wrote (those rows are zero):
+    same bits as combining every row, and launches in between (an upload)
+    switch the shortcut off."""
+    d = cases.load_case("jw_ne2_l6_strang")
+    res = []
+    for full in (True, False):
+        if full:
+            monkeypatch.setenv("TB200_CARRY_FULL", "1")
+        else:
+            monkeypatch.delenv("TB200_CARRY_FULL", raising=False)
+        ctx = dumpctx.context_from_dump(d, library=library, analytic_metric=True)
+        assert ctx.fast_path()[0]
+        dumpctx.upload_tag(ctx, d, "ic")
+        for m in range(1, ctx.cfg.ninstances):
+            ctx.copy(0, m)
+        ctx.step("strang", True, False, 200.0)
+        ctx.step("strang", False, False, 200.0)
+        ctx.step("strang", False, True, 200.0)
+        ctx.check_errors()
+        res.append(dumpctx.download(ctx, d, 0))
+        ctx.close()
+    for n in res[0]:
+        for loc in (0, 1):
+            assert np.array_equal(res[0][n][loc], res[1][n][loc])
+
+
 def test_fused_hyperdiffusion_equals_general_kernels(library, monkeypatch):
     """The fused order-4 hyperdiffusion passes (k_hyper_pipe, ZeroData / CopyData
     folded in) against the general per-field kernels, and the persistent-block
