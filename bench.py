@@ -388,7 +388,10 @@ def main():
             "config": {"workload": "JW baroclinic wave ne=%d L%d np=4 %s dt=%gs, %d patches"
                                    % (ne, L, args.timescheme, dt, npatch),
                        "l2": "state per instance %.2f GB >> 126 MB L2"
-                             % (ctx.column_count * (5 * L + 1) * 8 / 1e9)},
+                             % (ctx.column_count * (5 * L + 1) * 8 / 1e9),
+                       "halo_exchange": ("none (one rank)" if world == 1 else
+                                         "peer-memory stores over NVLink" if model.peer_exchange
+                                         else "NCCL all-to-all")},
             "sim_days_per_day": dt / sec_per_step,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),

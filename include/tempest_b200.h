@@ -313,6 +313,22 @@ typedef int (*tb200_exchange_fn)(void * user, double * sendbuf, double * recvbuf
                                  const int64_t * recv_counts, int nranks);
 int tb200_set_exchange(tb200_ctx * ctx, int rank, int nranks,
                        tb200_exchange_fn fn, void * user);
+/* Peer-memory exchange over NVLink / NVSwitch (replaces the callback once
+ * attached): the pack kernel stores every shared node straight into the
+ * receive buffer of the rank that averages it and raises a flag there; the
+ * consumer's stream waits on its flags.  After tb200_build_connectivity every
+ * rank calls tb200_peer_export (allocates its receive area; handle = 64-byte
+ * CUDA IPC handle, recv_offsets[r] = first slot of source rank r,
+ * recv_total = slots in all), the host all-gathers the three, and every rank
+ * calls tb200_peer_attach with handles[nranks][64], my_offset_at[r] = where
+ * rank r expects this rank's slots (= rank r's recv_offsets[this rank]) and
+ * recv_totals[r].  All ranks of one node, one GPU each. */
+int tb200_peer_export(tb200_ctx * ctx, void * handle, int64_t * recv_offsets,
+                      int64_t * recv_total);
+int tb200_peer_attach(tb200_ctx * ctx, const void * handles,
+                      const int64_t * my_offset_at, const int64_t * recv_totals);
+/* Back to the callback exchange (e.g. another rank could not attach). */
+int tb200_peer_detach(tb200_ctx * ctx);
 /* Nodes sent to / received from each rank per exchange (after
  * tb200_build_connectivity); arrays of nranks entries. */
 int tb200_exchange_counts(tb200_ctx * ctx, int64_t * send_nodes, int64_t * recv_nodes);

@@ -119,6 +119,9 @@ _SIGNATURES = {
     "tb200_set_exchange": (c_int, [c_void_p, c_int, c_int, EXCHANGE_FN,
                                    c_void_p]),
     "tb200_exchange_counts": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "tb200_peer_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tb200_peer_attach": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tb200_peer_detach": (c_int, [c_void_p]),
     "tb200_launch_count": (c_int64, [c_void_p]),
     "tb200_column_count": (c_int64, [c_void_p]),
     "tb200_debug_column_assembly": (c_int, [c_void_p, c_int, c_double, c_int,

@@ -281,6 +281,12 @@ extern "C" int tb200_create(const tb200_config * cfg, tb200_ctx ** out) {
 extern "C" int tb200_destroy(tb200_ctx * ctx) {
 	if (ctx == 0) return 0;
 	cudaDeviceSynchronize();
+#ifndef TB200_EMU
+	for (size_t r = 0; r < ctx->peer_base.size(); r++) {
+		if (ctx->peer_base[r] != 0) cudaIpcCloseMemHandle(ctx->peer_base[r]);
+	}
+	if (ctx->peer_area != 0) cudaFree(ctx->peer_area);
+#endif
 	for (size_t i = 0; i < ctx->allocs.size(); i++) {
 		cudaFree(ctx->allocs[i]);
 	}
@@ -1630,8 +1636,14 @@ extern "C" int tb200_debug_column_assembly(
 // VerticalDynamicsFEM.cpp:1461-1481); checked at tb200_sync-like points.
 static int check_column_info(tb200_ctx * ctx) {
 	if (ctx->d_info == 0) return 0;
-	int info = 0;
-	TB_CHECK(ctx, cudaMemcpy(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost));
+	int both[2] = {0, 0};
+	TB_CHECK(ctx, cudaMemcpy(both, ctx->d_info, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+	if (both[1] != 0) {
+		char buf[128];
+		snprintf(buf, 128, "peer-memory exchange: rank %d did not signal within the time limit", both[1] - 1);
+		TB_FAIL(ctx, buf);
+	}
+	const int info = both[0];
 	if (info != 0) {
 		char buf[128];
 		snprintf(buf, 128, "Inversion failure in column %d", info - 1);
@@ -1690,11 +1702,135 @@ static int ensure_buffers(tb200_ctx * ctx, size_t rows) {
 	return 0;
 }
 
+// ---- peer-memory exchange -----------------------------------------------------
+static const size_t kPeerFlagDoubles = 64;     // 512 bytes of flags in front of the buffers
+
+static double * peer_buffer(void * base, int64_t recv_total, size_t rows, int parity) {
+	return (double *)base + kPeerFlagDoubles + (size_t)parity * (size_t)recv_total * rows;
+}
+
+static int peer_exchange(tb200_ctx * ctx, int inst, int row0, int nsel, const double ** recvbuf) {
+	const DevLayout & lay = ctx->lay;
+	if ((size_t)nsel > ctx->peer_rows) TB_FAIL(ctx, "peer exchange: more rows than the buffers hold");
+	const unsigned long long seq = ++ctx->peer_seq;
+	const int parity = (int)(seq & 1);
+	PeerPtrs pp;
+	memset(&pp, 0, sizeof(pp));
+	unsigned wait_mask = 0;
+	bool any_send = false;
+	for (int r = 0; r < ctx->nranks; r++) {
+		if (r == ctx->rank || ctx->peer_base[r] == 0) continue;
+		pp.recv[r] = peer_buffer(ctx->peer_base[r], ctx->peer_recv_total[r], ctx->peer_rows, parity);
+		if (ctx->send_count[r] > 0) {
+			pp.flag[r] = (unsigned long long *)ctx->peer_base[r] + ctx->rank;
+			any_send = true;
+		}
+		if (ctx->recv_count[r] > 0) wait_mask |= (1u << r);
+	}
+	if (ctx->nsend_total > 0) {
+		const long long total = (long long)ctx->nsend_total * nsel;
+		long long nb = (total + 255) / 256;
+		if (nb > 148 * 8) nb = 148 * 8;
+		auto kfn = k_dss_pack_peer;
+		TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(256), 0, ctx->stream,
+			lay, (const int *)ctx->d_send_nodes, (const int *)ctx->d_send_rank,
+			(const int *)ctx->d_send_slot, ctx->nsend_total,
+			(const double *)ctx->inst[inst], pp, row0, nsel);
+		TB_KERNEL_CHECK(ctx);
+	}
+	if (any_send) {
+		auto kfn = k_peer_signal;
+		TB_LAUNCH_FLAT(kfn, dim3(1), dim3(32), 0, ctx->stream, pp, ctx->nranks, ctx->rank, seq);
+		TB_KERNEL_CHECK(ctx);
+	}
+	if (wait_mask != 0) {
+		auto kfn = k_peer_wait;
+		TB_LAUNCH_FLAT(kfn, dim3(1), dim3(32), 0, ctx->stream,
+			(const unsigned long long *)ctx->peer_area, wait_mask, seq,
+			60ull * 1000000000ull, ctx->d_info);
+		TB_KERNEL_CHECK(ctx);
+	}
+	*recvbuf = peer_buffer(ctx->peer_area, ctx->nrecv_total, ctx->peer_rows, parity);
+	return 0;
+}
+
+extern "C" int tb200_peer_export(
+	tb200_ctx * ctx, void * handle, int64_t * recv_offsets, int64_t * recv_total
+) {
+#ifdef TB200_EMU
+	(void)handle; (void)recv_offsets; (void)recv_total;
+	TB_FAIL(ctx, "peer-memory exchange needs the CUDA build");
+#else
+	if (!ctx->connectivity_built) TB_FAIL(ctx, "connectivity not built");
+	if (ctx->nranks < 2) TB_FAIL(ctx, "peer-memory exchange needs more than one rank");
+	if (ctx->nranks > TB200_MAX_PEERS) TB_FAIL(ctx, "peer-memory exchange: too many ranks");
+	if (ctx->peer_area != 0) TB_FAIL(ctx, "peer-memory exchange already exported");
+	const DevLayout & lay = ctx->lay;
+	ctx->peer_rows = (size_t)std::max(lay.nrows_state, lay.nrows - lay.nrows_state);
+	const size_t doubles = kPeerFlagDoubles + 2 * (size_t)ctx->nrecv_total * ctx->peer_rows;
+	TB_CHECK(ctx, cudaMalloc(&ctx->peer_area, doubles * sizeof(double)));
+	TB_CHECK(ctx, cudaMemset(ctx->peer_area, 0, doubles * sizeof(double)));
+	cudaIpcMemHandle_t h;
+	TB_CHECK(ctx, cudaIpcGetMemHandle(&h, ctx->peer_area));
+	static_assert(sizeof(h) == 64, "IPC handle size");
+	memcpy(handle, &h, sizeof(h));
+	int64_t off = 0;
+	for (int r = 0; r < ctx->nranks; r++) {
+		recv_offsets[r] = off;
+		off += ctx->recv_count[r];
+	}
+	*recv_total = ctx->nrecv_total;
+	if (ctx->d_info == 0) {
+		if (dalloc(ctx, &ctx->d_info, 4)) return 1;
+		TB_CHECK(ctx, cudaMemset(ctx->d_info, 0, 4 * sizeof(int)));
+	}
+	return 0;
+#endif
+}
+
+extern "C" int tb200_peer_attach(
+	tb200_ctx * ctx, const void * handles, const int64_t * my_offset_at,
+	const int64_t * recv_totals
+) {
+#ifdef TB200_EMU
+	(void)handles; (void)my_offset_at; (void)recv_totals;
+	TB_FAIL(ctx, "peer-memory exchange needs the CUDA build");
+#else
+	if (ctx->peer_area == 0) TB_FAIL(ctx, "tb200_peer_export first");
+	ctx->peer_base.assign(ctx->nranks, (void *)0);
+	ctx->peer_recv_total.assign(recv_totals, recv_totals + ctx->nranks);
+	for (int r = 0; r < ctx->nranks; r++) {
+		if (r == ctx->rank || (ctx->send_count[r] == 0 && ctx->recv_count[r] == 0)) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char *)handles + (size_t)r * 64, sizeof(h));
+		void * p = 0;
+		TB_CHECK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		ctx->peer_base[r] = p;
+	}
+	std::vector<int> slot(ctx->send_rank.size());
+	for (size_t q = 0; q < slot.size(); q++) {
+		slot[q] = (int)(my_offset_at[ctx->send_rank[q]] + ctx->send_j[q]);
+	}
+	if (dupload(ctx, &ctx->d_send_rank, ctx->send_rank)) return 1;
+	if (dupload(ctx, &ctx->d_send_slot, slot)) return 1;
+	ctx->peer_ready = true;
+	return 0;
+#endif
+}
+
+extern "C" int tb200_peer_detach(tb200_ctx * ctx) {
+	ctx->peer_ready = false;      // back to the callback; mappings are released at destroy
+	return 0;
+}
+
 static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state) {
 	if (row1 <= row0) return 0;
 	const DevLayout & lay = ctx->lay;
 	const int nsel = row1 - row0;
-	if (ctx->nranks > 1) {
+	const double * recvbuf = ctx->d_recvbuf;
+	if (ctx->nranks > 1 && ctx->peer_ready) {
+		if (peer_exchange(ctx, inst, row0, nsel, &recvbuf)) return 1;
+	} else if (ctx->nranks > 1) {
 		if (ensure_buffers(ctx, (size_t)std::max(lay.nrows_state, lay.nrows - lay.nrows_state))) return 1;
 		if (ctx->nsend_total > 0) {
 			const long long total = (long long)ctx->nsend_total * nsel;
@@ -1715,6 +1851,7 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 				sc.data(), rc.data(), ctx->nranks) != 0) {
 			TB_FAIL(ctx, "exchange callback failed");
 		}
+		recvbuf = ctx->d_recvbuf;
 	}
 	// elements that do not feed the exchange may still be in flight on stream2
 	if (split_join(ctx)) return 1;
@@ -1724,7 +1861,7 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 	a.flags = ctx->d_flags;
 	a.ngroups = ctx->ngroups;
 	a.nlocal = (int)(lay.nelem * lay.nn);
-	a.recv = ctx->d_recvbuf;
+	a.recv = recvbuf;
 	a.row0 = row0;
 	a.row1 = row1;
 	a.uv_row0 = is_state ? lay.rowoff[0] : -1;
@@ -2089,6 +2226,8 @@ extern "C" int tb200_build_connectivity(tb200_ctx * ctx) {
 
 	// deterministic slot order on both sides
 	std::vector<int> send_nodes;
+	ctx->send_rank.clear();
+	ctx->send_j.clear();
 	ctx->send_count.assign(ctx->nranks, 0);
 	ctx->recv_count.assign(ctx->nranks, 0);
 	std::map<std::pair<int, std::pair<int, int> >, int> recv_slot;  // (patch index,(ia,ib)) -> slot
@@ -2098,7 +2237,11 @@ extern "C" int tb200_build_connectivity(tb200_ctx * ctx) {
 		std::sort(sl.begin(), sl.end(),
 			[ctx](const Member & x, const Member & y) { return member_less(ctx, x, y); });
 		// a node can be listed once per group only, groups are disjoint: no duplicates
-		for (size_t q = 0; q < sl.size(); q++) send_nodes.push_back((int)sl[q].addr);
+		for (size_t q = 0; q < sl.size(); q++) {
+			send_nodes.push_back((int)sl[q].addr);
+			ctx->send_rank.push_back(r);
+			ctx->send_j.push_back((int)q);
+		}
 		ctx->send_count[r] = (int64_t)sl.size();
 		std::vector<Member> & rl = recv_lists[r];
 		std::sort(rl.begin(), rl.end(),

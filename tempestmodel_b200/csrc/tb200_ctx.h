@@ -85,6 +85,15 @@ struct tb200_ctx {
 	std::vector<int64_t> send_count, recv_count;   // nodes per peer
 	int * d_send_nodes;
 	double * d_sendbuf; double * d_recvbuf;
+	// peer-memory exchange (tb200_peer_export / tb200_peer_attach)
+	std::vector<int> send_rank, send_j;     // per send slot: destination, index in its block
+	int * d_send_rank; int * d_send_slot;
+	void * peer_area;                       // [64 flags][2][nrecv_total * peer_rows]
+	size_t peer_rows;
+	std::vector<void *> peer_base;          // IPC mappings of the peers' areas
+	std::vector<int64_t> peer_recv_total;
+	bool peer_ready;
+	unsigned long long peer_seq;
 	size_t buf_rows;                  // rows per slot the buffers are sized for
 
 	// implicit column solve
@@ -132,7 +141,8 @@ struct tb200_ctx {
 		ngroups(0), d_members(0), d_flags(0), nseam(0), d_seam_group(0),
 		d_seam_mats(0), rank(0), nranks(1), exch_fn(0), exch_user(0),
 		nsend_total(0), nrecv_total(0), d_send_nodes(0), d_sendbuf(0),
-		d_recvbuf(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0),
+		d_recvbuf(0), d_send_rank(0), d_send_slot(0), peer_area(0), peer_rows(0),
+		peer_ready(false), peer_seq(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0),
 		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false),
 		column_inc(0), d_wold(0), offd(4), launches(0), uvzero_inst(-1), uvzero_launches(0),
 		fast_state(0), fast_metric_error(0.0), d_colc(0), d_lev(0),

@@ -271,4 +271,72 @@ __global__ void k_dss_pack(
 	}
 }
 
+// ---- peer-memory exchange (NVLink / NVSwitch P2P) ----------------------------
+// Instead of packing into a send buffer and handing it to a collective, the
+// pack kernel stores every shared node straight into the receive buffer of the
+// rank that averages it (an IPC mapping of the peer's memory); a flag per
+// source rank, raised after the kernel, tells the consumer the slots of this
+// exchange have landed.  Receive buffers alternate by exchange parity: a rank
+// that signals exchange s has finished averaging exchange s - 2 (in-order
+// stream), and nobody can be more than one exchange ahead of a neighbour it
+// waits for.
+#define TB200_MAX_PEERS 16
+
+struct PeerPtrs {
+	double * recv[TB200_MAX_PEERS];               // peer's receive buffer of this parity
+	unsigned long long * flag[TB200_MAX_PEERS];   // peer's flag for this rank
+};
+
+__global__ void k_dss_pack_peer(
+	DevLayout lay, const int * send_nodes, const int * send_rank, const int * send_slot,
+	int nsend, const double * data, PeerPtrs pp, int row0, int nsel
+) {
+	const long long total = (long long)nsend * nsel;
+	for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	     idx < total; idx += (long long)gridDim.x * blockDim.x
+	) {
+		const int slot = (int)(idx / nsel);
+		const int r = (int)(idx % nsel);
+		const int m = send_nodes[slot];
+		pp.recv[send_rank[slot]][(size_t)send_slot[slot] * nsel + r] =
+			data[tb_dss_base(lay, m) + (size_t)(row0 + r) * lay.nn];
+	}
+}
+
+// after the pack kernel (stream order: its stores are performed): lane r tells
+// rank r that exchange seq of this rank is complete
+__global__ void k_peer_signal(PeerPtrs pp, int nranks, int me, unsigned long long seq) {
+	const int r = threadIdx.x;
+	if (r < nranks && r != me && pp.flag[r] != 0) {
+		__threadfence_system();
+		*(volatile unsigned long long *)pp.flag[r] = seq;
+		__threadfence_system();
+	}
+}
+
+// lane q waits until source rank q has signalled exchange seq; gives up after
+// timeout_ns and records the failure (reported by tb200_check_errors)
+__global__ void k_peer_wait(
+	const unsigned long long * flags, unsigned mask, unsigned long long seq,
+	unsigned long long timeout_ns, int * info
+) {
+	const int q = threadIdx.x;
+	if (q >= TB200_MAX_PEERS || !((mask >> q) & 1u)) return;
+#ifndef TB200_EMU
+	if (*(volatile int *)(info + 1) != 0) return;      // a peer is gone: do not wait again
+	unsigned long long t0;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+	const volatile unsigned long long * f = flags + q;
+	while (*f < seq) {
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+		if (t1 - t0 > timeout_ns) {
+			atomicMax(info + 1, q + 1);
+			break;
+		}
+	}
+	__threadfence_system();
+#endif
+}
+
 #endif

@@ -171,6 +171,23 @@ class DeviceContext:
         self._ck(self.lib.tb200_exchange_counts(self._h, _ptr(s), _ptr(r)))
         return s, r
 
+    def peer_export(self, nranks):
+        """(IPC handle bytes, first receive slot per source rank, receive slots)"""
+        h = np.zeros(64, dtype=np.uint8)
+        off = np.zeros(nranks, dtype=np.int64)
+        tot = np.zeros(1, dtype=np.int64)
+        self._ck(self.lib.tb200_peer_export(self._h, _ptr(h), _ptr(off), _ptr(tot)))
+        return h.tobytes(), off.tolist(), int(tot[0])
+
+    def peer_attach(self, handles, my_offset_at, recv_totals):
+        h = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+        off = np.ascontiguousarray(my_offset_at, dtype=np.int64)
+        tot = np.ascontiguousarray(recv_totals, dtype=np.int64)
+        self._ck(self.lib.tb200_peer_attach(self._h, _ptr(h), _ptr(off), _ptr(tot)))
+
+    def peer_detach(self):
+        self._ck(self.lib.tb200_peer_detach(self._h))
+
     # -- state ------------------------------------------------------------------
     def upload_state(self, patch, inst, node=None, redge=None, tracers=None):
         n, e, t = _f64(node), _f64(redge), _f64(tracers)

@@ -4,6 +4,7 @@ owns the grid, the test case and the device context, and advances the state
 with TimestepScheme::Step entirely on the device.
 """
 import math
+import os
 
 import numpy as np
 
@@ -57,6 +58,7 @@ class Model:
             ref_length=grid.reference_length, hypervis_order=hypervis_order,
             nu_scalar=nu_scalar, nu_div=nu_div, nu_vort=nu_vort,
             fully_explicit=0, off_centering=off_centering)
+        self.exchange = exchange
         if nranks > 1:
             self.ctx.set_exchange(rank, nranks, exchange)
         self.steps_taken = 0
@@ -98,6 +100,13 @@ class Model:
         if self.ncomp == 5:
             ctx.set_vertical_coordinate(g.reta_levels, g.reta_interfaces)
         ctx.build_connectivity()
+        # multi-GPU: direct stores into the peers' receive buffers unless
+        # TB200_EXCHANGE=nccl asks for the all-to-all callback
+        self.peer_exchange = False
+        if (self.nranks > 1 and getattr(self.exchange, "cuda", False)
+                and os.environ.get("TB200_EXCHANGE", "peer") == "peer"):
+            from .parallel import enable_peer_exchange
+            self.peer_exchange = enable_peer_exchange(ctx, self.rank, self.nranks)
         return self
 
     def evaluate_test_case(self, p):

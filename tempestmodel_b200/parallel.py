@@ -85,3 +85,38 @@ class Exchange:
             traceback.print_exc()
             self.error = exc
             return 1
+
+
+def enable_peer_exchange(ctx, rank, nranks):
+    """Switch the halo exchange of `ctx` from the callback to direct stores
+    into the peers' receive buffers (CUDA IPC over NVLink / NVSwitch; all ranks
+    on one node).  torch.distributed only carries the 64-byte handles and the
+    slot offsets at set-up.  Collective: every rank must call it after
+    build_connectivity.  Returns False (and leaves the callback in place) when
+    any rank could not map its peers."""
+    import torch
+    import torch.distributed as dist
+    ok = 1
+    try:
+        mine = ctx.peer_export(nranks)
+    except Exception:
+        mine, ok = None, 0
+    gathered = [None] * nranks
+    dist.all_gather_object(gathered, mine)
+    if ok and all(g is not None for g in gathered):
+        try:
+            ctx.peer_attach([g[0] for g in gathered],
+                            [g[1][rank] for g in gathered],
+                            [g[2] for g in gathered])
+        except Exception:
+            ok = 0
+    else:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32,
+                        device="cuda" if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if ok:
+            ctx.peer_detach()
+        return False
+    return True

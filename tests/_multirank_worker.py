@@ -35,6 +35,10 @@ def main():
     ctx = dumpctx.context_from_dump(
         d, library=PRODUCT_LIBRARY if cuda else dumpctx.EMU_LIBRARY,
         owners=owners, rank=rank, nranks=world, exchange=ex)
+    peer = len(sys.argv) > 4 and sys.argv[4] == "peer"
+    if peer:
+        from tempestmodel_b200.parallel import enable_peer_exchange
+        assert enable_peer_exchange(ctx, rank, world), "peer-memory exchange unavailable"
     dumpctx.upload_tag(ctx, d, "ic")
     for m in range(1, ctx.cfg.ninstances):
         ctx.copy(0, m)
@@ -48,7 +52,9 @@ def main():
     s, r = ctx.exchange_counts(world)
     if rank == 0:
         print("MULTIRANK worst=%.3e exchanges=%d send_nodes=%s" % (t.item(), ex.calls, s.tolist()))
-    assert ex.calls > 0 and s.sum() > 0
+    assert s.sum() > 0
+    # peer-memory exchange: the callback is never used
+    assert (ex.calls == 0) if peer else (ex.calls > 0)
     assert t.item() < 1e-10, errs
     dist.destroy_process_group()
 

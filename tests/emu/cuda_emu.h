@@ -200,6 +200,7 @@ inline void __syncthreads() { tbemu::Yield(tbemu::AT_BAR); }
 inline void __syncwarp(unsigned = 0xffffffffu) { tbemu::Yield(tbemu::AT_WBAR); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
+inline void __threadfence_system() {}
 
 inline double __shfl_sync(unsigned, double v, int src, int width = 32) {
 	tbemu::Sched & g = tbemu::G();

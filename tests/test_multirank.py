@@ -10,11 +10,11 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(backend, nproc=2, port=29611, env=None):
+def _run(backend, nproc=2, port=29611, env=None, extra=()):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "_multirank_worker.py"),
-           backend, "jw_ne2_l6_strang", "strang"]
+           backend, "jw_ne2_l6_strang", "strang"] + list(extra)
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert res.returncode == 0, res.stdout[-3000:]
@@ -46,3 +46,14 @@ def test_two_ranks_nccl_overlap(cuda_library):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run("nccl", port=29614, env={"TB200_OVERLAP": "1"})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nproc", [2, 3])
+def test_ranks_peer_memory_exchange(cuda_library, nproc):
+    """Halo exchange by direct stores into the peers' receive buffers (CUDA IPC
+    over NVLink) instead of the all-to-all callback: same state."""
+    import torch
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    _run("nccl", nproc=nproc, port=29615 + nproc, extra=["peer"])
