@@ -271,20 +271,32 @@ def main():
     value = columns / sec_per_step
 
     # ---- dominant kernel: fused explicit stage (combine + H + V explicit) -------
-    # first KGU35 stage: base = input instance (CopyData(0 -> 1) + StepExplicit(0, 1)),
-    # one source read + one instance written = 2 S bytes per node
-    nk = 10
+    # KGU35 stages 2-4 (three of the five stages of a step, the largest share of
+    # the launch list): CopyData(0 -> out) + StepExplicit(in, out), i.e. the
+    # stage base and the input are two instances read and one is written =
+    # 3 S bytes per node.  The other instantiations (first stage:
+    # base = input, 2 S; last stage: two-term base, 4 S) and the DSS kernel are
+    # timed the same way and reported under "kernels".
     k0 = torch.cuda.Event(enable_timing=True)
     k1 = torch.cuda.Event(enable_timing=True)
-    ctx.copy(0, 2)          # instance 2 holds Laplacians after a step: use a valid state
-    ctx.hv_step_explicit_combine([0.0, 0.0, 1.0, 0.0], 2, 3, 1e-6)
-    torch.cuda.synchronize()
-    k0.record()
-    for _ in range(nk):
-        ctx.hv_step_explicit_combine([0.0, 0.0, 1.0, 0.0], 2, 3, 1e-6)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / nk
+
+    def time_op(fn, n):
+        for m in range(1, ctx.cfg.ninstances):
+            ctx.copy(0, m)      # work instances hold Laplacians after a step: valid states
+        fn()
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(n):
+            fn()
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / n
+
+    nk = 10
+    kernel_ms = time_op(lambda: ctx.hv_step_explicit_combine([1.0, 0.0, 0.0, 0.0], 2, 3, 1e-6), nk)
+    first_ms = time_op(lambda: ctx.hv_step_explicit_combine([0.0, 0.0, 1.0, 0.0], 2, 3, 1e-6), nk)
+    last_ms = time_op(lambda: ctx.hv_step_explicit_combine([-0.25, 1.25, 0.0, 0.0, 0.0], 2, 4, 1e-6), nk)
+    dss_ms = time_op(lambda: ctx.dss(3), nk)
     # implicit column solve alone (FP64 pipe / scratch-bandwidth bound)
     ctx.copy(0, 3)
     ctx.v_step_implicit(3, 3, dt * 1e-3)
@@ -297,9 +309,9 @@ def main():
     column_ms = k0.elapsed_time(k1) / 3
     ctx.check_errors()
     local_nodes = ctx.column_count * L
-    # algorithmic bytes of one explicit stage pass with one source instance
+    # algorithmic bytes of one explicit stage pass with two source instances
     # ((n_src + 1) * S * 8 B per node, S = 5)
-    alg_bytes = local_nodes * (1 + 1) * 5 * 8
+    alg_bytes = local_nodes * (2 + 1) * 5 * 8
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -313,19 +325,29 @@ def main():
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             tr = json.load(f)
         if ctx.fast_path()[0]:
-            traffic = tr["k_nh_stage_pipe<true,0>"]["bytes_per_node"] * local_nodes
+            traffic = tr["k_nh_stage_pipe<true,1>"]["bytes_per_node"] * local_nodes
     except Exception:
         pass
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     fast = ctx.fast_path()
     roofline = {"bound": "hbm",
-                "kernel": "k_nh_stage_pipe<true>" if fast[0] else "k_nh_explicit<4,true,true>",
+                "kernel": "k_nh_stage_pipe<true,1>" if fast[0] else "k_nh_explicit<4,true,true>",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                 "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "bytes_per_node": 80,
+                "bytes_per_node": 120,
+                "kernels": {
+                    "k_nh_stage_pipe<true,0> (first stage, 2 S)": {
+                        "ms": first_ms, "achieved": local_nodes * 80 / (first_ms * 1e-3) / 1e9,
+                        "frac": local_nodes * 80 / (first_ms * 1e-3) / 1e9 / peak},
+                    "k_nh_stage_pipe<true,2> (last stage, 4 S)": {
+                        "ms": last_ms, "achieved": local_nodes * 160 / (last_ms * 1e-3) / 1e9,
+                        "frac": local_nodes * 160 / (last_ms * 1e-3) / 1e9 / peak},
+                    "k_dss_fast (1.5 S algorithmic; DRAM floor 2 S)": {
+                        "ms": dss_ms, "achieved": local_nodes * 60 / (dss_ms * 1e-3) / 1e9,
+                        "frac": local_nodes * 60 / (dss_ms * 1e-3) / 1e9 / peak}},
                 "column_solve": {"kernel": "k_column_fast" if fast[0] else "k_column_implicit_window",
                                  "ms": column_ms,
                                  "unique_columns_per_s": ctx.column_count * 9.0 / 16.0 / (column_ms * 1e-3)},
