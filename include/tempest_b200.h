@@ -262,6 +262,13 @@ int tb200_copy_v_step_implicit(tb200_ctx * ctx, int src, int dst, double dt);
 /* ... followed by Grid::LinearCombineData({+1 dst, -1 src} -> src): dst = solve(src),
  * src = dst - src (the tail of TimestepSchemeStrang::Step, :644-672). */
 int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst, double dt);
+/* The same tail when the state to solve already sits in `inst`
+ * (StepAfterSubCycle written straight into it): StepImplicit(inst, inst) in
+ * place, `inc` = new - old state (zero in the u, v rows).  Returns 2 without
+ * doing anything when the fast column kernel does not apply
+ * (tb200_v_step_implicit_inc_available == 0). */
+int tb200_v_step_implicit_inc_available(tb200_ctx * ctx);
+int tb200_v_step_implicit_inc(tb200_ctx * ctx, int inst, int inc, double dt);
 /* GridGLL::PostProcessSubstage -> ApplyDSS (GridGLL.cpp:571-583,
  * GridCSGLL.cpp:435-781, GridCartesianGLL.cpp:508-654). */
 int tb200_dss(tb200_ctx * ctx, int inst, int data_mask);

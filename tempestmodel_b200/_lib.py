@@ -104,6 +104,8 @@ _SIGNATURES = {
     "tb200_v_step_implicit": (c_int, [c_void_p, c_int, c_int, c_double]),
     "tb200_copy_v_step_implicit": (c_int, [c_void_p, c_int, c_int, c_double]),
     "tb200_copy_v_step_implicit_diff": (c_int, [c_void_p, c_int, c_int, c_double]),
+    "tb200_v_step_implicit_inc_available": (c_int, [c_void_p]),
+    "tb200_v_step_implicit_inc": (c_int, [c_void_p, c_int, c_int, c_double]),
     "tb200_dss": (c_int, [c_void_p, c_int, c_int]),
     "tb200_h_step_after_subcycle": (c_int, [c_void_p, c_int, c_int, c_int,
                                             c_double]),

@@ -1592,6 +1592,41 @@ extern "C" int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst
 	return 0;
 }
 
+// Strang tail when the state to be solved already sits in the destination
+// (hyperdiffusion written straight into it): StepImplicit(inst, inst) in place,
+// and `inc` receives Grid::LinearCombineData({+1, -1}) of the new and the old
+// state (zero in the u, v rows).  Returns 2, having done nothing, when the
+// fast column kernel does not apply; the caller then takes the reference's
+// sequence of calls.
+extern "C" int tb200_v_step_implicit_inc_available(tb200_ctx * ctx) {
+	const DevLayout & lay = ctx->lay;
+	const bool solve = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && lay.nlev > 1
+		&& !ctx->cfg.fully_explicit;
+	if (!solve || lay.ntr > 0 || fast_prepare(ctx) || ctx->fast_state != 1
+		|| getenv("TB200_COLUMN_KERNEL") != 0 || getenv("TB200_CARRY_FULL") != 0) {
+		return 0;
+	}
+	return 1;
+}
+
+extern "C" int tb200_v_step_implicit_inc(tb200_ctx * ctx, int inst, int inc, double dt) {
+	if (check_inst2(ctx, inst, inc)) return 1;
+	const DevLayout & lay = ctx->lay;
+	if (inst == inc || !tb200_v_step_implicit_inc_available(ctx)) return 2;
+	ctx->column_inc = ctx->inst[inc];
+	const int rc = tb200_v_step_implicit(ctx, inst, inst, dt);
+	ctx->column_inc = 0;
+	if (rc) return 1;
+	// u, v rows of the increment
+	const int uv0 = lay.rowoff[0], uv1 = lay.rowoff[1] + lay.rowlev[1];
+	CombineArgs zero;
+	memset(&zero, 0, sizeof(zero));
+	if (launch_combine(ctx, zero, inc, uv0, uv1)) return 1;
+	ctx->uvzero_inst = inc;
+	ctx->uvzero_launches = ctx->launches;
+	return 0;
+}
+
 // Debugging aid: assemble F and the banded Jacobian of the first launch chunk
 // without solving and copy the workspace of one column back
 // (cf. USE_JACOBIAN_DEBUG / BootstrapJacobian, VerticalDynamicsFEM.cpp:1163-1226).

@@ -170,12 +170,20 @@ static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double 
 		TRY(substage_from(ctx, kgu, 2, 4, 3.0 * dt / 4.0));
 	}
 
+	const double dOffCenterDeltaT = 0.5 * (1.0 + offc) * dt;
+	if (offc == 0.0 && !last && tb200_v_step_implicit_inc_available(ctx)) {
+		// hyperdiffusion written straight into instance 0 (no CopyData(1 -> 0)),
+		// solve in place, instance 1 receives the {+1, -1} combination
+		TRY(tb200_h_step_after_subcycle(ctx, 4, 0, 2, dt));
+		TRY(tb200_v_step_implicit_inc(ctx, 0, 1, dOffCenterDeltaT));
+		return 0;
+	}
+
 	// hyperdiffusion, :638-641 (the CopyData(4 -> 1) in front of it repeats the
 	// one StepAfterSubCycle starts with, HorizontalDynamicsFEM.cpp:2661)
 	TRY(tb200_h_step_after_subcycle(ctx, 4, 1, 2, dt));
 
 	// vertical step, :644-657: CopyData(1 -> 0), StepImplicit(0, 0)
-	const double dOffCenterDeltaT = 0.5 * (1.0 + offc) * dt;
 	if (offc == 0.0 && !last) {
 		// the off-centring combination is 1 * instance 0: the solve and the final
 		// {+1, -1} combination run as one call
