@@ -1744,6 +1744,18 @@ static double * peer_buffer(void * base, int64_t recv_total, size_t rows, int pa
 	return (double *)base + kPeerFlagDoubles + (size_t)parity * (size_t)recv_total * rows;
 }
 
+// how long a rank waits for a neighbour's flag before reporting it missing:
+// TB200_PEER_TIMEOUT_S seconds, default 120 (ranks may legitimately drift apart,
+// e.g. while one writes output)
+static unsigned long long peer_timeout_ns() {
+	static const unsigned long long ns = []() {
+		const char * e = getenv("TB200_PEER_TIMEOUT_S");
+		const double sec = (e != 0 && atof(e) > 0.0) ? atof(e) : 120.0;
+		return (unsigned long long)(sec * 1e9);
+	}();
+	return ns;
+}
+
 static int peer_exchange(tb200_ctx * ctx, int inst, int row0, int nsel, const double ** recvbuf) {
 	const DevLayout & lay = ctx->lay;
 	if ((size_t)nsel > ctx->peer_rows) TB_FAIL(ctx, "peer exchange: more rows than the buffers hold");
@@ -1782,7 +1794,7 @@ static int peer_exchange(tb200_ctx * ctx, int inst, int row0, int nsel, const do
 		auto kfn = k_peer_wait;
 		TB_LAUNCH_FLAT(kfn, dim3(1), dim3(32), 0, ctx->stream,
 			(const unsigned long long *)ctx->peer_area, wait_mask, seq,
-			60ull * 1000000000ull, ctx->d_info);
+			peer_timeout_ns(), ctx->d_info);
 		TB_KERNEL_CHECK(ctx);
 	}
 	*recvbuf = peer_buffer(ctx->peer_area, ctx->nrecv_total, ctx->peer_rows, parity);

@@ -984,7 +984,7 @@ k_column_implicit_window(
 	const int NN = lay.nn;
 	const int L = lay.nlev;
 	const int n = 3 * (L + 1);
-	const int kl = TBW_KL, kv = TBW_KV;
+	const int kl = TBW_KL;
 
 	const int node = ca.col_node[ca.col0 + tcol];
 	const long long e = node / NN;
