@@ -132,3 +132,70 @@ def test_config2_bubble_checksums(cuda_library):
     assert abs(cs[2] - CONFIG2["RhoTheta"]) <= 1e-12 * abs(CONFIG2["RhoTheta"])
     assert abs(cs[3] - CONFIG2["W"]) <= 1e-6 * abs(CONFIG2["W"])
     model.ctx.close()
+
+
+@pytest.mark.gpu
+def test_config5_jw_ne120_l30_properties(cuda_library):
+    """BASELINE configuration (ne = 120, L = 30, 1.38 M columns) through
+    size-independent properties: conservation of the mass and rho-theta
+    checksums over Strang steps, DSS idempotence, linearity of the stage
+    combination and the host <-> device layout round trip."""
+    import torch
+    if torch.cuda.mem_get_info()[1] < 40e9:
+        pytest.skip("needs a 40 GB device")
+    ne, L = 120, 30
+    grid = G.GridCSGLL(ne, L, npatch=6, ztop=30000.0)
+    model = Model(grid, TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"),
+                  timescheme="strang", dt=200.0 * 20.0 / ne, library=cuda_library)
+    model.device_setup = True
+    model.initialize()
+    model._host = {}
+    ctx = model.ctx
+    assert ctx.fast_path()[0]
+    assert ctx.column_count == 6 * ne * ne * 16
+    cs0 = np.array(model.checksum(0))
+    model.step(3, last=False)
+    ctx.check_errors()
+    cs1 = np.array(model.checksum(0))
+    assert np.all(np.isfinite(cs1))
+    assert abs(cs1[4] - cs0[4]) <= 1e-12 * abs(cs0[4])          # mass
+    assert abs(cs1[2] - cs0[2]) <= 1e-12 * abs(cs0[2])          # rho-theta
+
+    p = model.local[0]
+
+    def patch(inst):
+        node = np.zeros((5, p.wa, p.wb, L))
+        redge = np.zeros((5, p.wa, p.wb, L + 1))
+        ctx.download_state(p.index, inst, node, redge, None, False)
+        return node, redge
+
+    # host <-> device layout round trip: bit-exact
+    n0, e0 = patch(0)
+    ctx.upload_state(p.index, 3, n0, e0, None)
+    n3, e3 = patch(3)
+    assert np.array_equal(n0, n3) and np.array_equal(e0, e3)
+
+    # DSS of an already continuous state changes it by rounding only (1/3 at
+    # the cube corners, covector re-basing on the seams), and is idempotent
+    ctx.copy(0, 2)
+    ctx.dss(2)
+    n2, e2 = patch(2)
+    for c in (0, 1, 2, 4):
+        assert np.abs(n2[c] - n0[c]).max() <= 1e-13 * np.abs(n0[c]).max()
+    assert np.abs(e2[3] - e0[3]).max() <= 1e-13 * max(np.abs(e0[3]).max(), 1e-300)
+    ctx.dss(2)
+    n2b, e2b = patch(2)
+    for c in (2, 4):
+        assert np.abs(n2b[c] - n2[c]).max() <= 1e-15 * np.abs(n2[c]).max()
+    for c in (0, 1):
+        # the covector re-basing at the seams is a rotation and back: rounding
+        assert np.abs(n2b[c] - n2[c]).max() <= 1e-13 * np.abs(n2[c]).max()
+
+    # linearity: 0.25 * instance 0 + 0.75 * instance 2, checksum of checksums
+    ctx.lincomb([0.25, 0.0, 0.75, 0.0], 3)
+    cs2 = np.array(model.checksum(2))
+    cs3 = np.array(model.checksum(3))
+    for c in (2, 4):
+        assert abs(cs3[c] - (0.25 * cs1[c] + 0.75 * cs2[c])) <= 1e-13 * abs(cs1[c])
+    ctx.check_errors()
+    ctx.close()
