@@ -26,6 +26,12 @@ def test_two_ranks_gloo(emu_library):
     _run("gloo")
 
 
+def test_three_ranks_gloo(emu_library):
+    """Two patches per rank: every rank exchanges with two neighbours, so the
+    per-source slot offsets of the receive buffer are non-trivial."""
+    _run("gloo", nproc=3, port=29617)
+
+
 def test_two_ranks_gloo_overlap(emu_library):
     """Element-list launches of the persistent kernels (exchange-feeding elements
     first, the rest on the second stream): same state."""
