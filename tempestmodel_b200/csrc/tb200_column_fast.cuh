@@ -31,6 +31,8 @@
 #ifndef TB200_COLUMN_FAST_CUH
 #define TB200_COLUMN_FAST_CUH
 
+#include <type_traits>
+
 #include "tb200_platform.h"
 #include "tb200_device.h"
 #include "tb200_fast.cuh"
@@ -374,46 +376,53 @@ k_column_fast(
 	};
 
 	// ---- dgbtf2 + forward substitution on the register block -----------------------
-	// B[r][c] = A(j + r, j + c), bb[r] = b(j + r)
-	double B[5][9];
-	double bb[5];
+	// B[r][c] = A(j + r, j + c), bb[r] = b(j + r) with j = 3k fixed over the three
+	// steps of level k: rows 0-2 are the (partly eliminated) rows of level k,
+	// rows 3-5 those of level k+1; step s works on rows s..s+4 and columns
+	// s..s+8 (row 6 of the third step is P(k+2), zero in that pivot column, and
+	// is left out).  The names are static inside a level; the block moves by
+	// three rows and columns once per level.
+	double B[6][11];
+	double bb[6];
 #pragma unroll
-	for (int r = 0; r < 5; r++) {
+	for (int r = 0; r < 6; r++) {
 #pragma unroll
-		for (int c = 0; c < 9; c++) B[r][c] = 0.0;
+		for (int c = 0; c < 11; c++) B[r][c] = 0.0;
 		bb[r] = 0.0;
 	}
 	int info = 0;
 	int jstep = 0;
 
-	// one elimination step on the block, then shift by one row and column
-	auto eliminate = [&]() {
+	// elimination step s of the level
+	auto eliminate = [&](auto sc) {
+		constexpr int s = decltype(sc)::value;
+		constexpr int rlast = (s + 4 < 5) ? (s + 4) : 5;
 		int jp = 0;
-		double amax = fabs(B[0][0]);
+		double amax = fabs(B[s][s]);
 #pragma unroll
-		for (int r = 1; r < 5; r++) {
-			const double v = fabs(B[r][0]);
-			if (v > amax) { amax = v; jp = r; }
+		for (int r = s + 1; r <= rlast; r++) {
+			const double v = fabs(B[r][s]);
+			if (v > amax) { amax = v; jp = r - s; }
 		}
 		// interchange rows j and j + jp (warp-uniform in practice)
 		if (jp != 0) {
-#define TBC_SWAP(R) { _Pragma("unroll") for (int c = 0; c < 9; c++) { const double t0 = B[0][c]; B[0][c] = B[R][c]; B[R][c] = t0; } \
-			const double t1 = bb[0]; bb[0] = bb[R]; bb[R] = t1; }
-			if (jp == 1) TBC_SWAP(1)
-			else if (jp == 2) TBC_SWAP(2)
-			else if (jp == 3) TBC_SWAP(3)
-			else TBC_SWAP(4)
+#define TBC_SWAP(R) { _Pragma("unroll") for (int c = s; c < s + 9; c++) { const double t0 = B[s][c]; B[s][c] = B[R][c]; B[R][c] = t0; } \
+			const double t1 = bb[s]; bb[s] = bb[R]; bb[R] = t1; }
+			if (jp == 1) TBC_SWAP(s + 1)
+			else if (jp == 2) TBC_SWAP(s + 2)
+			else if (jp == 3) TBC_SWAP(s + 3)
+			else TBC_SWAP((s + 4 <= 5) ? (s + 4) : 5)
 #undef TBC_SWAP
 		}
-		if (B[0][0] != 0.0) {
-			const double rcp = 1.0 / B[0][0];
-			const double bj = bb[0];
+		if (B[s][s] != 0.0) {
+			const double rcp = 1.0 / B[s][s];
+			const double bj = bb[s];
 #pragma unroll
-			for (int r = 1; r < 5; r++) {
-				const double mult = B[r][0] * rcp;
+			for (int r = s + 1; r <= rlast; r++) {
+				const double mult = B[r][s] * rcp;
 #pragma unroll
-				for (int c = 1; c < 9; c++) {
-					B[r][c] -= mult * B[0][c];
+				for (int c = s + 1; c < s + 9; c++) {
+					B[r][c] -= mult * B[s][c];
 				}
 				bb[r] -= mult * bj;
 			}
@@ -424,31 +433,21 @@ k_column_fast(
 			unsigned m = 0;
 #pragma unroll
 			for (int c = 1; c < 9; c++) {
-				if (__any_sync(FULL, B[0][c] != 0.0)) m |= (1u << c);
+				if (__any_sync(FULL, B[s][s + c] != 0.0)) m |= (1u << c);
 			}
-			scp[0] = B[0][0];
-			scp[S] = bb[0];
+			scp[0] = B[s][s];
+			scp[S] = bb[s];
 			int slot = 2;
 #pragma unroll
 			for (int c = 1; c < 9; c++) {
 				if (m & (1u << c)) {
-					scp[slot * S] = B[0][c];
+					scp[slot * S] = B[s][s + c];
 					slot++;
 				}
 			}
 			scp += slot * S;
 			if ((threadIdx.x & 31) == 0) smask[jstep] = m;
 		}
-#pragma unroll
-		for (int r = 0; r < 4; r++) {
-#pragma unroll
-			for (int c = 0; c < 8; c++) B[r][c] = B[r + 1][c + 1];
-			B[r][8] = 0.0;
-			bb[r] = bb[r + 1];
-		}
-#pragma unroll
-		for (int c = 0; c < 9; c++) B[4][c] = 0.0;
-		bb[4] = 0.0;
 		jstep++;
 	};
 
@@ -466,27 +465,41 @@ k_column_fast(
 		bb[0] = o.fp; bb[1] = o.fw; bb[2] = o.fr;
 	}
 	for (int k = 0; k <= L; k++) {
-		TbcRows o;
-		const bool more = (k + 1 <= L);
-		if (more) {
+		if (k + 1 <= L) {
+			TbcRows o;
 			advance(k + 1);
 			assemble(k + 1, o);
-			// P(k+1) -> slot 3 (block column b - 1), W(k+1) -> slot 4 (column b)
+			// P(k+1) -> row 3 (block column b - 1), W(k+1) -> row 4 (column b),
+			// R(k+1) -> row 5 (column b + 1); the rest of the rows is zero
 #pragma unroll
 			for (int b = 1; b < 9; b++) B[3][b - 1] = o.p[b];
 #pragma unroll
 			for (int b = 0; b < 9; b++) B[4][b] = o.w[b];
-			bb[3] = o.fp; bb[4] = o.fw;
-		}
-		eliminate();          // j = 3k
-		if (more) {
-			// R(k+1) -> slot 4 (block column b)
 #pragma unroll
-			for (int b = 0; b < 9; b++) B[4][b] = o.r[b];
-			bb[4] = o.fr;
+			for (int b = 0; b < 9; b++) B[5][b + 1] = o.r[b];
+			bb[3] = o.fp; bb[4] = o.fw; bb[5] = o.fr;
+		} else {
+#pragma unroll
+			for (int r = 3; r < 6; r++) {
+#pragma unroll
+				for (int c = 0; c < 11; c++) B[r][c] = 0.0;
+				bb[r] = 0.0;
+			}
 		}
-		eliminate();          // j = 3k + 1
-		eliminate();          // j = 3k + 2
+		B[3][8] = 0.0; B[3][9] = 0.0; B[3][10] = 0.0;
+		B[4][9] = 0.0; B[4][10] = 0.0;
+		B[5][0] = 0.0; B[5][10] = 0.0;
+		eliminate(std::integral_constant<int, 0>());          // j = 3k
+		eliminate(std::integral_constant<int, 1>());          // j = 3k + 1
+		eliminate(std::integral_constant<int, 2>());          // j = 3k + 2
+		// rows and columns 3.. become 0..
+#pragma unroll
+		for (int r = 0; r < 3; r++) {
+#pragma unroll
+			for (int c = 0; c < 8; c++) B[r][c] = B[r + 3][c + 3];
+			B[r][8] = 0.0; B[r][9] = 0.0; B[r][10] = 0.0;
+			bb[r] = bb[r + 3];
+		}
 	}
 	__syncwarp();          // the row masks of this warp are complete
 	if (info != 0) {
