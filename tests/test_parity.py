@@ -305,6 +305,42 @@ def test_strang_carry_over_rows(library, monkeypatch):
             assert np.array_equal(res[0][n][loc], res[1][n][loc])
 
 
+@pytest.mark.parametrize("touch", ["upload", "copy", "lincomb"])
+def test_strang_carry_over_shortcut_is_dropped_when_the_increment_changes(library, monkeypatch, touch):
+    """Anything that runs between two steps (here: instance 1 overwritten by an
+    upload, a full copy or a combination) must switch the u, v shortcut of the
+    carry-over off: same bits as the full combination."""
+    d = cases.load_case("jw_ne2_l6_strang")
+    res = []
+    for full in (True, False):
+        if full:
+            monkeypatch.setenv("TB200_CARRY_FULL", "1")
+        else:
+            monkeypatch.delenv("TB200_CARRY_FULL", raising=False)
+        ctx = dumpctx.context_from_dump(d, library=library, analytic_metric=True)
+        dumpctx.upload_tag(ctx, d, "ic")
+        for m in range(1, ctx.cfg.ninstances):
+            ctx.copy(0, m)
+        ctx.step("strang", True, False, 200.0)
+        ctx.step("strang", False, False, 200.0)
+        if touch == "upload":
+            for n in ctx.local_patches:
+                ctx.upload_state(dumpctx.S(d, "patch%d.index" % n), 1,
+                                 d["ic.patch%d.inst0.node" % n],
+                                 d.get("ic.patch%d.inst0.redge" % n), None)
+        elif touch == "copy":
+            ctx.copy(0, 1)
+        else:
+            ctx.lincomb([1e-3, 1.0], 1)
+        ctx.step("strang", False, True, 200.0)
+        ctx.check_errors()
+        res.append(dumpctx.download(ctx, d, 0))
+        ctx.close()
+    for n in res[0]:
+        for loc in (0, 1):
+            assert np.array_equal(res[0][n][loc], res[1][n][loc])
+
+
 def test_fused_hyperdiffusion_equals_general_kernels(library, monkeypatch):
     """The fused order-4 hyperdiffusion passes (k_hyper_pipe, ZeroData / CopyData
     folded in) against the general per-field kernels, and the persistent-block
