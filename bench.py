@@ -101,6 +101,15 @@ def run_reference_all_cores(ne, levels, steps, dt, timescheme, cores=None):
                 value=value, cores=len(res), per_core=value / len(res))
 
 
+def workload_name(ne, L, scheme, dt, npatch):
+    return ("JW baroclinic wave ne=%d L%d np=4 %s dt=%gs, %d patches"
+            % (ne, L, scheme, dt, npatch))
+
+
+def patches_for(world):
+    return 6 if world <= 1 else 24
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -119,11 +128,13 @@ def reference_arm(args):
               % (args.ref_ne, args.levels, args.timescheme, r["steps"], r["cores"], args.ne))
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "column-steps/s",
-        "n_gpus": 0, "steps": r["steps"], "warmup": 0,
+        "n_gpus": args.gpus, "gpus_used": 0, "steps": r["steps"], "warmup": 0,
         "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "JW baroclinic wave ne=%d L%d np=4 %s (CPU sample ne=%d)"
-                   % (args.ne, args.levels, args.timescheme, args.ref_ne)},
+        # the b200 arm's workload; what the CPU actually ran is in cpu_baseline.sample
+        "config": {"workload": workload_name(args.ne, args.levels, args.timescheme,
+                                             200.0 * 20.0 / args.ne, patches_for(args.gpus)),
+                   "cpu_sample": "ne=%d, dt=%ds" % (args.ref_ne, dt)},
         "sim_days_per_day": dt / r["seconds_per_step"],
         "cpu_baseline": {"value": r["value"], "unit": "column-steps/s", "cores": r["cores"],
                          "kind": "reference", "sample": sample,
@@ -200,7 +211,7 @@ def main():
 
     ne, L = args.ne, args.levels
     dt = 200.0 * 20.0 / ne
-    npatch = 6 if world == 1 else 24
+    npatch = patches_for(world)
     while npatch % world != 0 or ne % int(round((npatch // 6) ** 0.5)) != 0:
         npatch += 6
     owners = assign_patches(npatch, world)
@@ -407,8 +418,7 @@ def main():
             "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "JW baroclinic wave ne=%d L%d np=4 %s dt=%gs, %d patches"
-                                   % (ne, L, args.timescheme, dt, npatch),
+            "config": {"workload": workload_name(ne, L, args.timescheme, dt, npatch),
                        "l2": "state per instance %.2f GB >> 126 MB L2"
                              % (ctx.column_count * (5 * L + 1) * 8 / 1e9),
                        "halo_exchange": ("none (one rank)" if world == 1 else
