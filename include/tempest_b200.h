@@ -321,7 +321,8 @@ typedef int (*tb200_exchange_fn)(void * user, double * sendbuf, double * recvbuf
 int tb200_set_exchange(tb200_ctx * ctx, int rank, int nranks,
                        tb200_exchange_fn fn, void * user);
 /* Peer-memory exchange over NVLink / NVSwitch (replaces the callback once
- * attached): the pack kernel stores every shared node straight into the
+ * attached; stands in for the MPI_Isend / MPI_Irecv / MPI_Waitall of
+ * Grid::Exchange, Grid.cpp:627-685, Connectivity.cpp:941-1120): the pack kernel stores every shared node straight into the
  * receive buffer of the rank that averages it and raises a flag there; the
  * consumer's stream waits on its flags.  After tb200_build_connectivity every
  * rank calls tb200_peer_export (allocates its receive area; handle = 64-byte
