@@ -40,6 +40,7 @@ class Model:
         self.local = [p for p in grid.patches if self.owners[p.index] == rank]
         sw = (test.equation_set == "shallow_water")
         self.ncomp = 3 if sw else 5
+        self.ntracers = int(getattr(test, "ntracers", 0))
         onedge = [0] * 8
         if not sw:
             onedge[3] = 1                       # Lorenz staggering: W on interfaces
@@ -48,7 +49,7 @@ class Model:
         ph = grid.phys
         self.ctx = DeviceContext(
             library=library, np=grid.np, nlev=grid.nlev,
-            vertical_order=grid.vertical_order, ncomp=self.ncomp, ntracers=0,
+            vertical_order=grid.vertical_order, ncomp=self.ncomp, ntracers=self.ntracers,
             ninstances=SCHEME_INSTANCES[self.timescheme],
             eqn_type=EQN_SHALLOW_WATER if sw else EQN_PRIMITIVE_NONHYDRO,
             cartesian_xz=1 if getattr(grid, "xz", False) else 0,
@@ -63,6 +64,7 @@ class Model:
             self.ctx.set_exchange(rank, nranks, exchange)
         self.steps_taken = 0
         self._host = {}
+        self._host_tracers = {}
         self.device_setup = False
 
     # -- setup (Model::SetGrid, SetTestCase and the head of Model::Go) ---------
@@ -96,7 +98,7 @@ class Model:
             if upload_state:
                 node, redge = self.evaluate_test_case(p)
                 self._host[p.index] = (node, redge)
-                ctx.upload_state(p.index, 0, node, redge, None)
+                ctx.upload_state(p.index, 0, node, redge, self._host_tracers.get(p.index))
         if self.ncomp == 5:
             ctx.set_vertical_coordinate(g.reta_levels, g.reta_interfaces)
         ctx.build_connectivity()
@@ -149,6 +151,16 @@ class Model:
             node[2, 1:-1, 1:-1] = st[2] * st[4]
             node[4, 1:-1, 1:-1] = st[4]
             # w on interfaces: zero for the test cases here (dState[3] = 0)
+        if self.ntracers > 0:
+            # tracer densities rho * q on levels (GridPatchCSGLL::EvaluateTestCase,
+            # GridPatchCSGLL.cpp:760-790: dTracer from EvaluatePointwiseState)
+            tr = np.zeros((self.ntracers, p.wa, p.wb, L))
+            shape = np.broadcast(z, lon).shape
+            for c, q in enumerate(test.evaluate_tracers(
+                    ph, np.broadcast_to(z, shape), np.broadcast_to(lon, shape),
+                    np.broadcast_to(lat, shape), st[4])):
+                tr[c, 1:-1, 1:-1] = q
+            self._host_tracers[p.index] = tr
         return node, redge
 
     # -- the step loop (Model::Go, Model.cpp:395-518) ------------------------------
@@ -167,6 +179,14 @@ class Model:
             redge = np.zeros((self.ncomp, p.wa, p.wb, L + 1))
             self.ctx.download_state(p.index, inst, node, redge, None, True)
             out[p.index] = (node, redge)
+        return out
+
+    def download_tracers(self, inst=0):
+        out = {}
+        for p in self.local:
+            tr = np.zeros((self.ntracers, p.wa, p.wb, self.grid.nlev))
+            self.ctx.download_state(p.index, inst, None, None, tr, False)
+            out[p.index] = tr
         return out
 
     def checksum(self, inst=0):

@@ -234,3 +234,33 @@ class ThermalBubbleCartesianTest:
         rho = phys.p0 / (phys.R * self.theta_bar) * exner ** (phys.cv / phys.R) + 0.0 * x
         zero = 0.0 * rho
         return [zero, zero, theta, zero, rho]
+
+
+class BaroclinicWaveJWTracerTest(BaroclinicWaveJWTest):
+    """The JW wave carrying `ntracers` analytic tracer densities rho * q:
+    q_0 a smooth global field decaying with height, q_c (c >= 1) cosine bells.
+    The same closed forms as the oracle's dump hook uses for its tracer
+    fixtures (oracle/ref_dump.cpp, JWTracerTest), i.e. a dry stand-in for the
+    five-tracer configuration 4 of SURVEY 8 (the DCMIP-2016 driver itself
+    needs gfortran)."""
+
+    def __init__(self, ntracers=3, **kw):
+        super().__init__(**kw)
+        self.ntracers = int(ntracers)
+
+    def evaluate_tracers(self, phys, z, lon, lat, rho, xp=NUMPY):
+        out = []
+        for c in range(self.ntracers):
+            if c == 0:
+                q = 1.0e-3 * (2.0 + xp.sin(lon) * xp.cos(lat)) * xp.exp(-z / 8000.0)
+            else:
+                lon0 = 0.5 + 1.7 * c
+                lat0 = 0.6 - 0.5 * c
+                z0 = 4000.0 + 3000.0 * c
+                r = xp.arccos(math.sin(lat0) * xp.sin(lat)
+                              + math.cos(lat0) * xp.cos(lat) * xp.cos(lon - lon0))
+                rz = xp.abs(z - z0) / 6000.0
+                dd = xp.sqrt(r * r / (0.9 * 0.9) + rz * rz)
+                q = xp.where(dd < 1.0, 0.5e-2 * (1.0 + xp.cos(math.pi * dd)), 0.0 * dd)
+            out.append(rho * q)
+        return out

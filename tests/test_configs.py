@@ -199,3 +199,46 @@ def test_config5_jw_ne120_l30_properties(cuda_library):
         assert abs(cs3[c] - (0.25 * cs1[c] + 0.75 * cs2[c])) <= 1e-13 * abs(cs1[c])
     ctx.check_errors()
     ctx.close()
+
+
+def test_python_tracer_case_matches_reference(emu_library):
+    """Tracers through the Python driver (a dry stand-in for the five-tracer
+    configuration 4): the closed-form tracer densities equal the reference's
+    initial arrays, and three Strang steps from the reference's initial state
+    reproduce its tracer fields and state (numpy geometry against the
+    reference's: rounding-level differences, amplified by three steps)."""
+    import cases
+    import dumpctx
+    d = cases.load_case("jwtr_ne2_l6_strang")
+    ntr = dumpctx.S(d, "grid.ntracers")
+    grid = G.GridCSGLL(2, 6, npatch=6, ztop=30000.0)
+    test = TC.BaroclinicWaveJWTracerTest(ntracers=ntr, ztop=30000.0, perturbation="exp")
+    model = Model(grid, test, timescheme="strang", dt=200.0, library=emu_library)
+    model.initialize()
+    ctx = model.ctx
+    for p in model.local:
+        ref = dumpctx.interior(d["ic.patch%d.inst0.tracers" % p.index])
+        got = dumpctx.interior(model._host_tracers[p.index])
+        for c in range(ntr):
+            assert np.abs(got[c] - ref[c]).max() <= 1e-12 * np.abs(ref[c]).max(), (p.index, c)
+    # the reference's initial state (its w was perturbed by the dump script)
+    for p in model.local:
+        key = "ic.patch%d.inst0." % p.index
+        ctx.upload_state(p.index, 0, d[key + "node"], d[key + "redge"], d[key + "tracers"])
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    model.step(3, last=False)
+    ctx.check_errors()
+    got = model.download_tracers(0)
+    for p in model.local:
+        ref = dumpctx.interior(d["st.patch%d.inst0.tracers" % p.index])
+        dev = dumpctx.interior(got[p.index])
+        for c in range(ntr):
+            assert np.abs(dev[c] - ref[c]).max() <= 1e-9 * np.abs(ref[c]).max(), (p.index, c)
+    state = model.download_state(0)
+    for p in model.local:
+        ref = dumpctx.interior(d["st.patch%d.inst0.node" % p.index])
+        dev = dumpctx.interior(state[p.index][0])
+        for c in (2, 4):
+            assert np.abs(dev[c] - ref[c]).max() <= 1e-9 * np.abs(ref[c]).max(), (p.index, c)
+    ctx.close()
