@@ -151,7 +151,7 @@ class Model:
             node[2, 1:-1, 1:-1] = st[2] * st[4]
             node[4, 1:-1, 1:-1] = st[4]
             # w on interfaces: zero for the test cases here (dState[3] = 0)
-        if self.ntracers > 0:
+        if getattr(self, "ntracers", 0) > 0:
             # tracer densities rho * q on levels (GridPatchCSGLL::EvaluateTestCase,
             # GridPatchCSGLL.cpp:760-790: dTracer from EvaluatePointwiseState)
             tr = np.zeros((self.ntracers, p.wa, p.wb, L))
