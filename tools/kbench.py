@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--timescheme", default="strang")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--tracers", type=int, default=0,
+                    help="carry N analytic tracers (general kernels; S = 5 + N)")
     args = ap.parse_args()
 
     import torch
@@ -36,7 +38,12 @@ def main():
     torch.cuda.set_device(0)
     t0 = time.time()
     grid = G.GridCSGLL(ne, L, npatch=6, ztop=30000.0)
-    model = Model(grid, TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"),
+    if args.tracers > 0:
+        test = TC.BaroclinicWaveJWTracerTest(ntracers=args.tracers, ztop=30000.0,
+                                             perturbation="exp")
+    else:
+        test = TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp")
+    model = Model(grid, test,
                   timescheme=args.timescheme, dt=dt, device=0, library=args.lib)
     ctx = model.ctx
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -50,7 +57,7 @@ def main():
     ctx.check_errors()
 
     nodes = ctx.column_count * L
-    S = 5 * 8
+    S = (5 + args.tracers) * 8
 
     ninst = ctx.cfg.ninstances
 
