@@ -50,6 +50,7 @@ def main():
     model.device_setup = True
     model.initialize()
     model._host = {}
+    model._host_tracers = {}
     ctx.sync()
     setup = time.time() - t0
     fast = ctx.fast_path() if hasattr(ctx, "fast_path") else None
