@@ -82,6 +82,17 @@ CASES["jwray_ne2_l6"] = dict(
                      "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
                      "step:2", "dump:st,0"]))
 
+# second-order viscosity (--hypervisorder 2: one Laplacian application + DSS,
+# HorizontalDynamicsFEM.cpp:2671-2684; nu is not scaled with the resolution)
+CASES["jwhv2_ne2_l6"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s",
+                      "--hypervisorder", "2", "--nu", "1.0e7", "--nud", "2.0e7",
+                      "--nuv", "0.5e7"],
+    script=";".join(["addw:0,20000", "dss:0", "dump:ic,0", "hasc:0,1,2,200", "dump:hasc,1",
+                     "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
+                     "step:2", "dump:st,0"]),
+    geometry_from="jw_ne2_l6_strang")
+
 # more time schemes on the same grid and initial state: only the run records are
 # stored, the geometry comes from the strang case (same flags)
 for _scheme in ("ars222", "ars232", "ars443", "strang/ssprk53", "strang/rk4", "strang/rk3"):

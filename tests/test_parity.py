@@ -489,3 +489,23 @@ def test_rayleigh_friction(library):
     ctx.check_errors()
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     ctx.close()
+
+
+def test_second_order_viscosity(library):
+    """--hypervisorder 2 (HorizontalDynamicsFEM.cpp:2671-2684): one scalar and
+    one vector Laplacian application with unscaled coefficients, filter, DSS;
+    alone and inside two Strang steps."""
+    d = cases.load_case("jwhv2_ne2_l6")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert ctx.cfg.hypervis_order == 2
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.h_step_after_subcycle(0, 1, 2, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 1, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    assert_below(tendency_errors(ctx, d, 1, "hasc", "ic", 0, [0, 1, 2, 4], [3]), 1e-8)
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    ctx.close()
