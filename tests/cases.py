@@ -93,6 +93,17 @@ CASES["jwhv2_ne2_l6"] = dict(
                      "step:2", "dump:st,0"]),
     geometry_from="jw_ne2_l6_strang")
 
+# stretched levels (--vstretch cubic): non-uniform vertical operator tables and
+# a level-dependent layer depth (the column-constant fast path must step aside)
+CASES["jw_ne2_l6_cubic"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s", "--vstretch", "cubic"],
+    script=";".join([
+        "addw:0,20000", "dss:0",
+        "dump:ic,0", "copy:0,1", "hexp:0,1,50", "dump:h1,1", "vexp:0,1,50",
+        "dump:v1,1", "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,30",
+        "dump:vi,2", "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
+        "step:2", "dump:st,0"]))
+
 # more time schemes on the same grid and initial state: only the run records are
 # stored, the geometry comes from the strang case (same flags)
 for _scheme in ("ars222", "ars232", "ars443", "strang/ssprk53", "strang/rk4", "strang/rk3"):

@@ -509,3 +509,37 @@ def test_second_order_viscosity(library):
     ctx.check_errors()
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     ctx.close()
+
+
+@pytest.mark.parametrize("analytic", [False, True])
+def test_stretched_levels(library, analytic):
+    """--vstretch cubic: non-uniform level spacing (vertical operator tables of
+    GridGLL.cpp:101-363 with stretched REta).  General kernels on the stored
+    metric and the column-constant fast path (its verification against the
+    uploaded arrays must still pass) against the reference, stage by stage and
+    over two Strang steps."""
+    d = cases.load_case("jw_ne2_l6_cubic")
+    ctx = dumpctx.context_from_dump(d, library=library, analytic_metric=analytic)
+    enabled, reason, dev = ctx.fast_path()
+    assert enabled == analytic, reason
+    if analytic:
+        assert dev <= 1e-13
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.v_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), 1e-14)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3]), 1e-10)
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    ctx.close()
