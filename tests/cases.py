@@ -104,6 +104,16 @@ CASES["jw_ne2_l6_cubic"] = dict(
         "dump:vi,2", "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
         "step:2", "dump:st,0"]))
 
+# fourth-order hyperdiffusion with three different coefficients (scalar,
+# divergence, vorticity): the defaults are all 1e15 and would hide a mix-up
+CASES["jwhv4_ne2_l6"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s",
+                      "--nu", "1.0e15", "--nud", "2.5e15", "--nuv", "0.4e15"],
+    script=";".join(["addw:0,20000", "dss:0", "dump:ic,0", "hasc:0,1,2,200", "dump:hasc,1",
+                     "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
+                     "step:2", "dump:st,0"]),
+    geometry_from="jw_ne2_l6_strang")
+
 # more time schemes on the same grid and initial state: only the run records are
 # stored, the geometry comes from the strang case (same flags)
 for _scheme in ("ars222", "ars232", "ars443", "strang/ssprk53", "strang/rk4", "strang/rk3"):

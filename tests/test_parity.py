@@ -543,3 +543,25 @@ def test_stretched_levels(library, analytic):
     ctx.check_errors()
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     ctx.close()
+
+
+@pytest.mark.parametrize("analytic", [False, True])
+def test_hyperdiffusion_distinct_coefficients(library, analytic):
+    """Order-4 hyperdiffusion with nu (scalars), nud (divergence) and nuv
+    (vorticity) all different - the defaults are equal and would hide a mix-up
+    of the three in the general or in the fused kernels."""
+    d = cases.load_case("jwhv4_ne2_l6")
+    ctx = dumpctx.context_from_dump(d, library=library, analytic_metric=analytic)
+    assert ctx.fast_path()[0] == analytic
+    assert len({ctx.cfg.nu_scalar, ctx.cfg.nu_div, ctx.cfg.nu_vort}) == 3
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.h_step_after_subcycle(0, 1, 2, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 1, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    assert_below(tendency_errors(ctx, d, 1, "hasc", "ic", 0, [0, 1, 2, 4], [3]), 1e-8)
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    ctx.close()
