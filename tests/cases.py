@@ -114,6 +114,15 @@ CASES["jwhv4_ne2_l6"] = dict(
                      "step:2", "dump:st,0"]),
     geometry_from="jw_ne2_l6_strang")
 
+# Williamson 2 with the flow axis tilted (--alpha 0.7): Coriolis parameter and
+# both velocity components non-trivial on every panel
+CASES["sw2_ne2_alpha"] = dict(
+    case="sw2", flags=["--resolution", "2", "--alpha", "0.7"],
+    script=";".join([
+        "dump:ic,0", "copy:0,1", "hexp:0,1,100", "dump:h1,1", "dss:1", "dump:dss,1",
+        "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
+        "step:2", "dump:st,0", "checksum:cs"]))
+
 # more time schemes on the same grid and initial state: only the run records are
 # stored, the geometry comes from the strang case (same flags)
 for _scheme in ("ars222", "ars232", "ars443", "strang/ssprk53", "strang/rk4", "strang/rk3"):

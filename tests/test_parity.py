@@ -565,3 +565,24 @@ def test_hyperdiffusion_distinct_coefficients(library, analytic):
     ctx.check_errors()
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     ctx.close()
+
+
+def test_shallow_water_tilted_flow(library):
+    """Williamson 2 with --alpha 0.7: the Coriolis parameter and both velocity
+    components vary on every panel (the alpha = 0 case leaves the polar panels
+    nearly trivial)."""
+    d = cases.load_case("sw2_ne2_alpha")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 100.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2]), TOL_DSS)
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2]), 1e-12)
+    ctx.close()
