@@ -75,6 +75,12 @@ CASES["jwtr_ne2_l6_strang"] = dict(
     script="addw:0,20000;dss:0;dump:ic,0;step:3;dump:st,0;checksum:cs",
     geometry_from="jw_ne2_l6_strang")
 
+CASES["jwtr_ne2_l6_ars343"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s", "--ntracers", "3",
+                      "--timescheme", "ars343"],
+    script="addw:0,20000;dss:0;dump:ic,0;step:1;dump:s1,0,3,4;step:1;dump:st,0",
+    geometry_from="jw_ne2_l6_strang")
+
 # Rayleigh friction: the JW case with a sponge layer (oracle/ref_dump.cpp --rayleigh)
 CASES["jwray_ne2_l6"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s", "--rayleigh", "0.01"],
