@@ -402,7 +402,9 @@ void HorizontalDynamicsB200::StepAfterSubCycle(
 	b.Check(tb200_h_step_after_subcycle(
 		b.Ctx(), iDataInitial, iDataUpdate, iDataWorking, dDeltaT));
 	b.Download(iDataUpdate);
-	b.Download(iDataWorking);
+	// the working instance is scratch: the reference writes it only in the
+	// order-4 branch (HorizontalDynamicsFEM.cpp:2687-2713) and nothing reads it
+	// afterwards; leave the host copy alone
 }
 
 ///////////////////////////////////////////////////////////////////////////////

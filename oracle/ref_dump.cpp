@@ -26,6 +26,12 @@
 ///	  checksum:TAG          Grid::Checksum of instance 0 -> record
 ///	  addw:INST,AMP         test data: add a smooth non-zero W on interfaces
 ///	  perturb:INST,EPS      test data: relative pseudo-random noise of size EPS
+///	  energy:TAG,INST       Grid::ComputeTotalEnergy / ComputeTotalPotentialEnstrophy /
+///	                        ComputeTotalVerticalMomentum of INST -> record, after
+///	                        refreshing the slots those routines read at the location
+///	                        the state does not live on (W on levels, rho on
+///	                        interfaces) with the reference's own interpolation
+///	(--nogeometry 1 leaves the 3-D metric arrays out of the file: large grids)
 ///
 ///	The test-case classes live in the reference's driver sources next to a
 ///	main(); they are included (not copied) with main renamed.
@@ -211,7 +217,7 @@ static std::string P(int n, const char * sz) {
 
 ///////////////////////////////////////////////////////////////////////////////
 
-static void DumpGeometry(Model & model) {
+static void DumpGeometry(Model & model, bool fArrays3D) {
 	GridGLL * pGrid = dynamic_cast<GridGLL*>(model.GetGrid());
 	const PhysicalConstants & phys = model.GetPhysicalConstants();
 	const EquationSet & eqn = model.GetEquationSet();
@@ -305,6 +311,7 @@ static void DumpGeometry(Model & model) {
 		Write3D(P(n, "contrametric2db"), pPatch->GetContraMetric2DB());
 		Write2D(P(n, "coriolis"), pPatch->GetCoriolisF());
 		Write2D(P(n, "topography"), pPatch->GetTopography());
+		if (!fArrays3D) continue;
 		Write3D(P(n, "jacobian"), pPatch->GetJacobian());
 		Write3D(P(n, "jacobianredge"), pPatch->GetJacobianREdge());
 		Write4D(P(n, "contrametrica"), pPatch->GetContraMetricA());
@@ -471,6 +478,25 @@ static void RunScript(Model & model, const std::string & strScript) {
 				fFirst = false;
 				time += model.GetDeltaT();
 			}
+		} else if (op == "energy") {
+			// GridPatch::ComputeTotalEnergy (GridPatch.cpp:925-1138) reads W on
+			// levels and rho on interfaces, which the Lorenz-staggered state
+			// does not carry: refresh them first (Grid.cpp:843-863)
+			const int iInst = atoi(a[1].c_str());
+			if (eqn.GetType() == EquationSet::PrimitiveNonhydrostaticEquations) {
+				if (pGrid->GetVarLocation(3) == DataLocation_REdge) {
+					pGrid->InterpolateREdgeToNode(3, iInst);
+				}
+				if (pGrid->GetVarLocation(4) == DataLocation_Node) {
+					pGrid->InterpolateNodeToREdge(4, iInst);
+				}
+			}
+			DataArray1D<double> dDiag(3);
+			dDiag[0] = pGrid->ComputeTotalEnergy(iInst);
+			dDiag[1] = pGrid->ComputeTotalPotentialEnstrophy(iInst);
+			dDiag[2] = (eqn.GetType() == EquationSet::PrimitiveNonhydrostaticEquations) ?
+				pGrid->ComputeTotalVerticalMomentum(iInst) : 0.0;
+			Write1D(a[0] + ".energy", dDiag);
 		} else if (op == "checksum") {
 			DataArray1D<double> dSums;
 			pGrid->Checksum(DataType_State, dSums, 0, ChecksumType_Sum);
@@ -497,6 +523,7 @@ try {
 	double dU0, dH0, dAlpha;
 	int nTracers;
 	double dRayleigh;
+	int nNoGeometry;
 
 	BeginTempestCommandLine("RefDump");
 		SetDefaultResolution(4);
@@ -519,6 +546,7 @@ try {
 		CommandLineDouble(dAlpha, "alpha", 0.0);
 		CommandLineInt(nTracers, "ntracers", 0);
 		CommandLineDouble(dRayleigh, "rayleigh", 0.0);
+		CommandLineInt(nNoGeometry, "nogeometry", 0);
 
 		ParseCommandLine(argc, argv);
 	EndTempestCommandLine(argv)
@@ -610,7 +638,7 @@ try {
 	WriteScalarD("run.nu_div", _tempestvars.dNuDiv);
 	WriteScalarD("run.nu_vort", _tempestvars.dNuVort);
 
-	DumpGeometry(model);
+	DumpGeometry(model, nNoGeometry == 0);
 	RunScript(model, strScript);
 
 	fclose(g_fp);

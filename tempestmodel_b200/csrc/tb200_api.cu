@@ -34,6 +34,7 @@
 #define TB_KERNEL_CHECK(ctx) \
 	do { \
 		(ctx)->launches++; \
+		(ctx)->writes++; \
 		cudaError_t e__ = cudaGetLastError(); \
 		if (e__ != cudaSuccess) { \
 			(ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__); \
@@ -275,6 +276,9 @@ extern "C" int tb200_create(const tb200_config * cfg, tb200_ctx ** out) {
 	memset(&ctx->ops, 0, sizeof(ctx->ops));
 	memset(&ctx->geom, 0, sizeof(ctx->geom));
 	memset(&ctx->tables, 0, sizeof(ctx->tables));
+	ctx->carry_full = (getenv("TB200_CARRY_FULL") != 0);
+	TB_CHECK(ctx, cudaMallocHost((void **)&ctx->h_info, 4 * sizeof(int)));
+	memset(ctx->h_info, 0, 4 * sizeof(int));
 	return 0;
 }
 
@@ -290,6 +294,7 @@ extern "C" int tb200_destroy(tb200_ctx * ctx) {
 	for (size_t i = 0; i < ctx->allocs.size(); i++) {
 		cudaFree(ctx->allocs[i]);
 	}
+	if (ctx->h_info != 0) cudaFreeHost(ctx->h_info);
 	delete ctx;
 	return 0;
 }
@@ -900,7 +905,7 @@ extern "C" int tb200_copy(tb200_ctx * ctx, int src, int dst, int mask) {
 		const size_t bytes = (size_t)ctx->lay.nelem * ctx->lay.nrows * ctx->lay.nn * sizeof(double);
 		TB_CHECK(ctx, cudaMemcpyAsync(ctx->inst[dst], ctx->inst[src], bytes,
 			cudaMemcpyDeviceToDevice, ctx->stream));
-		ctx->uvzero_inst = -1;      // not a counted launch
+		ctx->writes++;              // not a kernel launch, still a write
 		return 0;
 	}
 	CombineArgs ca;
@@ -937,10 +942,10 @@ extern "C" int tb200_lincomb(
 	// zero, so those rows of dest stay as they are (Strang carry-over,
 	// TimestepSchemeStrang.cpp:470-482)
 	if (ca.nsrc == 1 && ca.scale_dst && ca.cdst == 1.0 && ctx->uvzero_inst >= 0
-		&& ca.src[0] == ctx->inst[ctx->uvzero_inst] && ctx->launches == ctx->uvzero_launches
+		&& ca.src[0] == ctx->inst[ctx->uvzero_inst] && ctx->writes == ctx->uvzero_writes
 		&& row0 == 0 && ctx->lay.rowoff[0] == 0
 		&& ctx->lay.rowoff[1] == ctx->lay.rowlev[0]
-		&& getenv("TB200_CARRY_FULL") == 0      // test switch: combine every row
+		&& !ctx->carry_full                     // TB200_CARRY_FULL=1 (tests): combine every row
 	) {
 		row0 = ctx->lay.rowoff[1] + ctx->lay.rowlev[1];
 	}
@@ -1166,6 +1171,7 @@ static int nh_launch(
 							lay, ctx->tables, ctx->phys, fa, \
 							(const double *)ctx->inst[in], pb, ctx->inst[out], el); \
 						ctx->launches++; \
+						ctx->writes++; \
 					} \
 					if (split && split_mark(ctx)) return 1; }
 				if (do_v) {
@@ -1588,7 +1594,7 @@ extern "C" int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst
 	memset(&zero, 0, sizeof(zero));
 	if (launch_combine(ctx, zero, src, uv0, uv1)) return 1;
 	ctx->uvzero_inst = src;
-	ctx->uvzero_launches = ctx->launches;
+	ctx->uvzero_writes = ctx->writes;
 	return 0;
 }
 
@@ -1623,7 +1629,7 @@ extern "C" int tb200_v_step_implicit_inc(tb200_ctx * ctx, int inst, int inc, dou
 	memset(&zero, 0, sizeof(zero));
 	if (launch_combine(ctx, zero, inc, uv0, uv1)) return 1;
 	ctx->uvzero_inst = inc;
-	ctx->uvzero_launches = ctx->launches;
+	ctx->uvzero_writes = ctx->writes;
 	return 0;
 }
 
@@ -1692,6 +1698,25 @@ static int check_column_info(tb200_ctx * ctx) {
 extern "C" int tb200_check_errors(tb200_ctx * ctx) {
 	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
 	return check_column_info(ctx);
+}
+
+// Stream-ordered copy of the device-side failure record into pinned host
+// memory (end of every tb200_step), and the test on it that needs no
+// synchronisation (start of every tb200_step): a failed column solve or a peer
+// that stopped signalling stops the run at most two steps later even when the
+// caller never asks (the reference throws at once, VerticalDynamicsFEM.cpp:1461-1481).
+int tb_mirror_errors(tb200_ctx * ctx) {
+	if (ctx->d_info == 0 || ctx->h_info == 0) return 0;
+	TB_CHECK(ctx, cudaMemcpyAsync(ctx->h_info, ctx->d_info, 2 * sizeof(int),
+		cudaMemcpyDeviceToHost, ctx->stream));
+	return 0;
+}
+
+int tb_poll_errors(tb200_ctx * ctx) {
+	if (ctx->h_info == 0) return 0;
+	const volatile int * h = ctx->h_info;
+	if (h[0] == 0 && h[1] == 0) return 0;
+	return tb200_check_errors(ctx);
 }
 
 // HorizontalDynamicsFEM::FilterNegativeTracers (element-wise) and
@@ -2058,6 +2083,7 @@ static int hyper_fast(
 				lay, ctx->tables, ha,
 				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out], el);
 			ctx->launches++;
+			ctx->writes++;
 		}
 		if (split && split_mark(ctx)) return 1;
 	} else {
@@ -2076,6 +2102,7 @@ static int hyper_fast(
 				lay, ctx->tables, ha,
 				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out], el);
 			ctx->launches++;
+			ctx->writes++;
 		}
 		if (split && split_mark(ctx)) return 1;
 	}

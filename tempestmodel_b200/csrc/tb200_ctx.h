@@ -114,11 +114,19 @@ struct tb200_ctx {
 	bool want_split, split_pending;
 
 	int64_t launches;
-	// instance whose u, v rows are known to be zero (the increment written by
-	// tb200_copy_v_step_implicit_diff) as long as `launches` still equals
-	// uvzero_launches, i.e. nothing has run since; -1 = none
+	// Every operation that writes device state bumps `writes`: kernel launches
+	// (TB_KERNEL_CHECK and the counted persistent launches) and the
+	// cudaMemcpyAsync of tb200_copy.  uvzero_inst is the instance whose u, v
+	// rows are known to be zero (the increment written by the Strang tail) as
+	// long as `writes` still equals uvzero_writes, i.e. nothing has written
+	// anything since; -1 = none
+	int64_t writes;
 	int uvzero_inst;
-	int64_t uvzero_launches;
+	int64_t uvzero_writes;
+	bool carry_full;                  // TB200_CARRY_FULL at tb200_create (tests)
+	// pinned host mirror of d_info, refreshed by an asynchronous copy at the end
+	// of every tb200_step: tb200_step refuses to start once it shows a failure
+	int * h_info;
 	int sm_count;
 
 	// fast path (tb200_fast.cuh): 0 = not examined, 1 = enabled, -1 = unavailable
@@ -144,7 +152,8 @@ struct tb200_ctx {
 		d_recvbuf(0), d_send_rank(0), d_send_slot(0), peer_area(0), peer_rows(0),
 		peer_ready(false), peer_seq(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0),
 		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false),
-		column_inc(0), d_wold(0), offd(4), launches(0), uvzero_inst(-1), uvzero_launches(0),
+		column_inc(0), d_wold(0), offd(4), launches(0), writes(0), uvzero_inst(-1), uvzero_writes(0),
+		carry_full(false), h_info(0),
 		fast_state(0), fast_metric_error(0.0), d_colc(0), d_lev(0),
 		geometry3d_uploaded(false)
 	{

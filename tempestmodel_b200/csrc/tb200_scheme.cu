@@ -459,10 +459,10 @@ static int step_ars443(tb200_ctx * ctx, double dt) {
 	return 0;
 }
 
-extern "C" int tb200_step(tb200_ctx * ctx, int scheme, int first, int last, double dt) {
-	const int need = tb200_scheme_instances(scheme);
-	if (need < 0) TB_FAIL(ctx, "time scheme not implemented");
-	if ((int)ctx->inst.size() < need) TB_FAIL(ctx, "not enough state instances for this scheme");
+int tb_mirror_errors(tb200_ctx * ctx);    // tb200_api.cu
+int tb_poll_errors(tb200_ctx * ctx);
+
+static int step_dispatch(tb200_ctx * ctx, int scheme, int first, int last, double dt) {
 	switch (scheme) {
 		case TB200_SCHEME_ARS343: return step_ars343(ctx, first, last, dt);
 		case TB200_SCHEME_ARS222: return step_ars222(ctx, dt);
@@ -477,6 +477,16 @@ extern "C" int tb200_step(tb200_ctx * ctx, int scheme, int first, int last, doub
 		default:
 			return step_strang(ctx, scheme, first, last, dt);
 	}
+}
+
+extern "C" int tb200_step(tb200_ctx * ctx, int scheme, int first, int last, double dt) {
+	const int need = tb200_scheme_instances(scheme);
+	if (need < 0) TB_FAIL(ctx, "time scheme not implemented");
+	if ((int)ctx->inst.size() < need) TB_FAIL(ctx, "not enough state instances for this scheme");
+	// a failure recorded by an earlier step (column solve, peer time-out): stop
+	TRY(tb_poll_errors(ctx));
+	TRY(step_dispatch(ctx, scheme, first, last, dt));
+	return tb_mirror_errors(ctx);
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -520,6 +530,7 @@ extern "C" int tb200_checksum(tb200_ctx * ctx, int inst, double * sums) {
 		ctx->lay, (const double *)ctx->inst[inst], (const double *)ctx->d_area_node,
 		(const double *)ctx->d_area_redge, ctx->d_sums);
 	ctx->launches++;
+	ctx->writes++;
 	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
 	TB_CHECK(ctx, cudaMemcpy(sums, ctx->d_sums, ctx->lay.ncomp * sizeof(double),
 		cudaMemcpyDeviceToHost));

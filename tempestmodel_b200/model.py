@@ -164,14 +164,22 @@ class Model:
         return node, redge
 
     # -- the step loop (Model::Go, Model.cpp:395-518) ------------------------------
-    def step(self, nsteps=1, last=False):
+    def step(self, nsteps=1, last=False, check=True):
+        """`nsteps` calls of TimestepScheme::Step.  Device-side failures (the
+        column solve's "Inversion failure" / NaN, where the reference throws -
+        VerticalDynamicsFEM.cpp:1461-1481 - and a peer that stopped signalling)
+        are raised after the loop (one synchronisation per call, none per step);
+        the library itself refuses to start another step once one is recorded."""
         for s in range(nsteps):
             first = (self.steps_taken == 0)
             is_last = last and (s == nsteps - 1)
             self.ctx.step(SCHEMES[self.timescheme], first, is_last, self.dt)
             self.steps_taken += 1
+        if check:
+            self.ctx.check_errors()
 
     def download_state(self, inst=0):
+        self.ctx.check_errors()
         out = {}
         L = self.grid.nlev
         for p in self.local:
@@ -182,6 +190,7 @@ class Model:
         return out
 
     def download_tracers(self, inst=0):
+        self.ctx.check_errors()
         out = {}
         for p in self.local:
             tr = np.zeros((self.ntracers, p.wa, p.wb, self.grid.nlev))
@@ -190,6 +199,7 @@ class Model:
         return out
 
     def checksum(self, inst=0):
+        self.ctx.check_errors()
         return self.ctx.checksum(inst)
 
     @property

@@ -30,7 +30,15 @@ def test_config3_jw_ne30_l30_checksums(cuda_library):
     # the implicit Jacobian at zero wind
     assert abs(cs[4] - CONFIG3["Rho"]) <= 1e-12 * abs(CONFIG3["Rho"])
     assert abs(cs[2] - CONFIG3["RhoTheta"]) <= 1e-12 * abs(CONFIG3["RhoTheta"])
-    assert abs(cs[0] - CONFIG3["U"]) <= 1e-7 * abs(CONFIG3["U"])
+    # U: 10 x the spread the reference shows against itself under 1e-15
+    # perturbations of this very run (tests/golden/sensitivity.json)
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                           "sensitivity.json")) as f:
+        sp = json.load(f)["jw_ne30_l30_strang_2steps"]
+    assert sp["checksum"][0] == CONFIG3["U"]
+    assert abs(cs[0] - CONFIG3["U"]) <= 10.0 * sp["rel_spread"][0] * abs(CONFIG3["U"]), (cs, sp)
     model.ctx.close()
 
 # SWTest2 --resolution 20 --order 4 --output_none (dt = 200 s, 1 step, strang,

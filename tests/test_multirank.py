@@ -10,11 +10,11 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(backend, nproc=2, port=29611, env=None, extra=()):
+def _run(backend, nproc=2, port=29611, env=None, extra=(), case="jw_ne2_l6_strang"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "_multirank_worker.py"),
-           backend, "jw_ne2_l6_strang", "strang"] + list(extra)
+           backend, case, "strang"] + list(extra)
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert res.returncode == 0, res.stdout[-3000:]
@@ -63,3 +63,25 @@ def test_ranks_peer_memory_exchange(cuda_library, nproc):
     if torch.cuda.device_count() < nproc:
         pytest.skip("needs %d GPUs" % nproc)
     _run("nccl", nproc=nproc, port=29615 + nproc, extra=["peer"])
+
+
+# ---- the decomposition the multi-GPU bench lines use: 24 patches, L = 30 -------
+
+@pytest.mark.parametrize("nproc", [4, 8])
+def test_24_patches_gloo(emu_library, nproc):
+    """ne = 4, L = 30 on 24 patches over 4 and 8 ranks (6 and 3 patches each):
+    every rank has up to seven neighbours, cube corners are shared by three
+    ranks; state after two Strang steps against the single-rank reference."""
+    _run("gloo", nproc=nproc, port=29630 + nproc, case="jw_ne4_l30_p24")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nproc,mode", [(2, "peer"), (4, "peer"), (8, "peer"), (8, "nccl")])
+def test_24_patches_gpus(cuda_library, nproc, mode):
+    """The same on 2, 4 and 8 GPUs (peer-memory exchange, and the NCCL callback
+    at 8): the configuration SCALE measures."""
+    import torch
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    _run("nccl", nproc=nproc, port=29640 + nproc + (1 if mode == "nccl" else 0),
+         extra=["peer"] if mode == "peer" else [], case="jw_ne4_l30_p24")

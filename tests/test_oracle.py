@@ -57,3 +57,36 @@ def test_committed_fixture_matches_fresh_reference_run(tmp_path):
     assert set(fresh) == set(gold)
     for k in gold:
         assert np.array_equal(fresh[k], gold[k], equal_nan=True), k
+
+
+@needs_ref
+@pytest.mark.skipif(not refdump.have_ref_dump(), reason="ref_dump not built")
+def test_committed_l30_fixture_matches_fresh_reference_run(tmp_path):
+    """The L = 30 Strang fixture (run records only; geometry is shared)."""
+    name = "jw_ne2_l30_strang"
+    c = cases.CASES[name]
+    fresh = refdump.run_ref_dump(str(tmp_path / "x.bin"), c["case"], c["script"], c["flags"])
+    with np.load(cases.golden_path(name)) as z:
+        for k in z.files:
+            assert np.array_equal(fresh[k], z[k], equal_nan=True), k
+
+
+@needs_ref
+@pytest.mark.skipif(not refdump.have_ref_dump(), reason="ref_dump not built")
+@pytest.mark.parametrize("key", ["jw_ne8_l10_strang_3steps", "jwtr_ne2_l6_ars343_2steps"])
+def test_reference_sensitivity_is_what_the_json_records(key):
+    """tests/golden/sensitivity.json (the reference's spread against itself
+    under 1e-15 perturbations, which bounds the loosened parity tolerances)
+    re-measured on the reference built here."""
+    import make_sensitivity as ms
+    gold = ms.load()[key]
+    fresh = ms.ENTRIES[key]()
+    if "checksum" in gold:
+        assert np.allclose(fresh["checksum"], gold["checksum"], rtol=1e-13, atol=0)
+        pairs = zip(fresh["abs_spread"], gold["abs_spread"])
+    else:
+        assert np.allclose(fresh["mass"], gold["mass"], rtol=1e-13, atol=0)
+        pairs = zip(fresh["field_rel_spread"] + fresh["mass_rel_spread"],
+                    gold["field_rel_spread"] + gold["mass_rel_spread"])
+    for a, b in pairs:
+        assert a == b, (fresh, gold)     # same binary, same input: deterministic

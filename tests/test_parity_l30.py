@@ -1,0 +1,153 @@
+"""Parity at L = 30, the level count every measured number is quoted on.
+
+The kernels behind the bench line (k_nh_stage_pipe, k_hyper_pipe, k_dss_fast,
+k_column_fast) take a different shape there than at the L = 6 / 8 of the other
+fixtures: 120 active threads of a 128-thread block, one level tile of
+TBF_KB = 32 with two idle level slots, 19.3 kB element rows, the shared-memory
+carve-up of tb_pipe_smem_doubles, a 93-unknown band system in the column solve.
+Fixtures: the unmodified reference at `--levels 30 --ztop 30000 --pert Exp`
+(the flags of bench.py), ne = 2 on 6 patches stage by stage and over two Strang
+steps, and ne = 4 on the 24 patches bench.py uses on 2, 4 and 8 GPUs.
+Tolerances as in test_parity.py (FP64): explicit stages 1e-12 of the largest
+tendency, DSS 1e-14 of the field, implicit stage 1e-10 of the largest change,
+multi-step states 1e-10 of the field.
+"""
+import numpy as np
+import pytest
+
+import cases
+import dumpctx
+from test_parity import (BACKENDS, TOL_DSS, TOL_IMPLICIT, TOL_STAGE, TOL_STATE,
+                         assert_below, tendency_errors)
+
+
+@pytest.fixture(params=BACKENDS)
+def library(request):
+    if request.param == "emu":
+        return request.getfixturevalue("emu_library")
+    return request.getfixturevalue("cuda_library")
+
+
+def test_stages_l30(library):
+    """h1 / v1 / dss / vi / hasc against the reference, fast path enabled."""
+    d = cases.load_case("jw_ne2_l30")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    enabled, reason, dev = ctx.fast_path()
+    assert enabled, reason
+    assert dev <= 1e-13
+    dumpctx.upload_tag(ctx, d, "ic")
+    assert_below(dumpctx.compare(ctx, d, 0, "ic", [0, 1, 2, 4], [3]), 0.0)
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.v_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    # the fused forms the time schemes launch: k_nh_stage_pipe<true, 0 / 1 / 2>
+    a = dumpctx.download(ctx, d, 1)
+    for coeff, out in (([1.0, 0.0, 0.0, 0.0], 3),          # base = input (2 S)
+                       ([0.0, 0.0, 1.0, 0.0], 3),          # base = another instance (3 S)
+                       ([0.75, 0.0, 0.25, 0.0, 0.0], 4)):  # two-term base (4 S)
+        ctx.copy(0, 2)
+        ctx.hv_step_explicit_combine(coeff, 0, out, 50.0)
+        assert_below(tendency_errors(ctx, d, out, "v1", "ic", 0, [0, 1, 2, 4], [3],
+                                     ref_inst=1), TOL_STAGE)
+        if coeff[0] == 1.0:
+            b = dumpctx.download(ctx, d, out)
+            for n in ctx.local_patches:
+                for loc in (0, 1):
+                    ia, ib = dumpctx.interior(a[n][loc]), dumpctx.interior(b[n][loc])
+                    for c in ([0, 1, 2, 4] if loc == 0 else [3]):
+                        assert np.abs(ia[c] - ib[c]).max() <= 4e-16 * np.abs(ia[c]).max()
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    assert_below(tendency_errors(ctx, d, 1, "dss", "ic", 0, [0, 1, 2, 4], [3],
+                                 scale=("v1", 1)), 1e-10)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=True), TOL_IMPLICIT)
+    assert_below(dumpctx.compare(ctx, d, 2, "vi", [0, 1, 2, 4], [3], skip_poles=True), 1e-12)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    assert_below(dumpctx.compare(ctx, d, 4, "hasc", [0, 1, 2, 4], [3]), 1e-11)
+    ctx.close()
+
+
+def test_general_kernels_l30(library, monkeypatch):
+    """The general kernels on the stored 3-D metric at L = 30 (two level chunks
+    of 15 in k_nh_explicit) against the same records."""
+    d = cases.load_case("jw_ne2_l30")
+    monkeypatch.setenv("TB200_STAGE_KERNEL", "generic")
+    monkeypatch.setenv("TB200_HYPER_KERNEL", "generic")
+    monkeypatch.setenv("TB200_COLUMN_KERNEL", "window")
+    ctx = dumpctx.context_from_dump(d, library=library, analytic_metric=False)
+    assert not ctx.fast_path()[0]
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.v_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=True), TOL_IMPLICIT)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    ctx.close()
+
+
+def test_steps_l30(library):
+    """Two Strang / KGU35 steps (the bench scheme) at L = 30: state, increment
+    instance and the reference's checksums."""
+    d = cases.load_case("jw_ne2_l30_strang")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert ctx.fast_path()[0]
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    cs = ctx.checksum(0)
+    ref = d["cs.checksum"]
+    assert abs(cs[4] - ref[4]) <= 1e-13 * abs(ref[4])
+    assert abs(cs[2] - ref[2]) <= 1e-13 * abs(ref[2])
+    assert abs(cs[0] - ref[0]) <= 1e-10 * abs(ref[0])
+    ctx.close()
+
+
+def test_24_patches_l30(library):
+    """ne = 4 on 24 patches (one rank): the decomposition of the multi-GPU bench
+    lines - DSS across patch edges inside a panel, panel seams and cube corners
+    shared by three patches - stage records and two Strang steps."""
+    d = cases.load_case("jw_ne4_l30_p24")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert ctx.fast_path()[0]
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.hv_step_explicit_combine([1.0, 0.0], 0, 1, 50.0)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=True), TOL_IMPLICIT)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    cs = ctx.checksum(0)
+    ref = d["cs.checksum"]
+    assert abs(cs[4] - ref[4]) <= 1e-13 * abs(ref[4])
+    assert abs(cs[2] - ref[2]) <= 1e-13 * abs(ref[2])
+    ctx.close()
