@@ -37,6 +37,10 @@ def parse():
                     help="resolution of the bounded CPU sample (reference arm)")
     ap.add_argument("--cpu-ne", type=int, default=12,
                     help="resolution of the cpu_baseline sample inside the b200 arm")
+    ap.add_argument("--tracers", type=int, default=0,
+                    help="carry N analytic tracers (config 4 dry stand-in: --ne 60 --tracers 5)")
+    ap.add_argument("--lean", action="store_true",
+                    help="upload no 3-D metric arrays (default above ne=120 L30)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -116,22 +120,22 @@ def run_reference_all_cores(ne, levels, steps, dt, timescheme, cores=None):
                 value=value, cores=len(res), per_core=value / len(res))
 
 
-def workload_name(ne, L, scheme, dt, npatch):
-    return ("JW baroclinic wave ne=%d L%d np=4 %s dt=%gs, %d patches"
-            % (ne, L, scheme, dt, npatch))
+def workload_name(ne, L, scheme, dt, npatch, tracers=0):
+    return ("JW baroclinic wave ne=%d L%d np=4 %s dt=%gs%s, %d patches"
+            % (ne, L, scheme, dt, (" + %d tracers" % tracers) if tracers else "", npatch))
 
 
 def patches_for(world):
     return 6 if world <= 1 else 24
 
 
-def bench_config(ne, L, scheme, world):
+def bench_config(ne, L, scheme, world, tracers=0):
     """`config` of the JSON line: identical for both arms (the reference arm
     times a bounded sample of this workload, described in cpu_baseline.sample)."""
     npatch = patches_for(world)
-    return {"workload": workload_name(ne, L, scheme, step_seconds(ne), npatch),
+    return {"workload": workload_name(ne, L, scheme, step_seconds(ne), npatch, tracers),
             "l2": "state per instance %.2f GB >> 126 MB L2"
-                  % (6 * ne * ne * 16 * (5 * L + 1) * 8 / 1e9),
+                  % (6 * ne * ne * 16 * ((5 + tracers) * L + 1) * 8 / 1e9),
             "halo_exchange": "none (one rank)" if world <= 1 else "patch halos between ranks"}
 
 
@@ -160,7 +164,7 @@ def reference_arm(args):
         "ms_per_step": r["seconds_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         # the b200 arm's workload; what the CPU actually ran is in cpu_baseline.sample
-        "config": bench_config(args.ne, args.levels, args.timescheme, args.gpus),
+        "config": bench_config(args.ne, args.levels, args.timescheme, args.gpus, args.tracers),
         "sim_days_per_day": dt / r["seconds_per_step"],
         "cpu_baseline": {"value": r["value"], "unit": "column-steps/s", "cores": r["cores"],
                          "kind": "reference", "sample": sample,
@@ -292,12 +296,19 @@ def main():
     t_setup = time.time()
     grid = G.GridCSGLL(ne, L, npatch=npatch, ztop=30000.0)
     ex = Exchange(cuda=True) if world > 1 else None
-    model = Model(grid, TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"),
-                  timescheme=args.timescheme, dt=dt, device=local_rank,
+    if args.tracers > 0:
+        test = TC.BaroclinicWaveJWTracerTest(ntracers=args.tracers, ztop=30000.0,
+                                             perturbation="exp")
+    else:
+        test = TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp")
+    model = Model(grid, test, timescheme=args.timescheme, dt=dt, device=local_rank,
                   rank=rank, nranks=world, owners=owners, exchange=ex)
     ctx = model.ctx
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     model.device_setup = True
+    # above the headline size the 3-D metric arrays (26 values per node) would not
+    # fit beside the state: the column-constant kernels need the 2-D metric only
+    model.lean_geometry = args.lean or (ne * ne * L > 120 * 120 * 30)
     model.initialize()
     ctx.sync()
     t_setup = time.time() - t_setup
@@ -311,6 +322,8 @@ def main():
     # pinned host copies of instance 0 (reference layout) for the end-to-end leg
     host = {}
     h2d = d2h = 0
+    if args.tracers > 0:
+        args.no_e2e = True       # the end-to-end leg moves the dry state only
     if not args.no_e2e:
         for p in model.local:
             node, redge = model._host[p.index]
@@ -332,7 +345,17 @@ def main():
             dist.all_reduce(cs)
         return cs.cpu().numpy()
 
+    def global_energy():
+        """Grid::ComputeTotalEnergy of instance 0 over all ranks."""
+        if args.tracers > 0 and not ctx.fast_path()[0]:
+            return float("nan")
+        e = torch.tensor([ctx.total_energy(0)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e)
+        return e.item()
+
     cs_ic = global_checksum()
+    energy_ic = global_energy()
 
     # ---- warm-up ------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -366,7 +389,11 @@ def main():
 
     # ---- parity of the state the timed steps produced ---------------------------
     parity = parity_block(global_checksum(), cs_ic, max(args.warmup, 3) + args.steps,
-                          workload_name(ne, L, args.timescheme, dt, 0).split(",")[0], world)
+                          workload_name(ne, L, args.timescheme, dt, 0, args.tracers).split(",")[0],
+                          world)
+    energy = global_energy()
+    parity["total_energy"] = energy
+    parity["energy_drift"] = (energy - energy_ic) / energy_ic
 
     # ---- dominant kernel: fused explicit stage (combine + H + V explicit) -------
     # KGU35 stages 2-4 (three of the five stages of a step, the largest share of
@@ -407,9 +434,10 @@ def main():
     column_ms = k0.elapsed_time(k1) / 3
     ctx.check_errors()
     local_nodes = ctx.column_count * L
+    S = 5 + args.tracers
     # algorithmic bytes of one explicit stage pass with two source instances
-    # ((n_src + 1) * S * 8 B per node, S = 5)
-    alg_bytes = local_nodes * (2 + 1) * 5 * 8
+    # ((n_src + 1) * S * 8 B per node, S = 5 + tracers)
+    alg_bytes = local_nodes * (2 + 1) * S * 8
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -422,12 +450,14 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             tr = json.load(f)
-        if ctx.fast_path()[0]:
+        if ctx.fast_path()[0] and args.tracers == 0:
             traffic = tr["k_nh_stage_pipe<true,1>"]["bytes_per_node"] * local_nodes
     except Exception:
         pass
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     fast = ctx.fast_path()
+    if args.tracers > 0:
+        fast = (False, "tracers take the general kernels", fast[2])
     roofline = {"bound": "hbm",
                 "kernel": "k_nh_stage_pipe<true,1>" if fast[0] else "k_nh_explicit<4,true,true>",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -435,22 +465,23 @@ def main():
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                 "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "bytes_per_node": 120,
+                "bytes_per_node": 3 * S * 8,
                 "kernels": {
                     "k_nh_stage_pipe<true,0> (first stage, 2 S)": {
-                        "ms": first_ms, "achieved": local_nodes * 80 / (first_ms * 1e-3) / 1e9,
-                        "frac": local_nodes * 80 / (first_ms * 1e-3) / 1e9 / peak},
+                        "ms": first_ms, "achieved": local_nodes * 16 * S / (first_ms * 1e-3) / 1e9,
+                        "frac": local_nodes * 16 * S / (first_ms * 1e-3) / 1e9 / peak},
                     "k_nh_stage_pipe<true,2> (last stage, 4 S)": {
-                        "ms": last_ms, "achieved": local_nodes * 160 / (last_ms * 1e-3) / 1e9,
-                        "frac": local_nodes * 160 / (last_ms * 1e-3) / 1e9 / peak},
+                        "ms": last_ms, "achieved": local_nodes * 32 * S / (last_ms * 1e-3) / 1e9,
+                        "frac": local_nodes * 32 * S / (last_ms * 1e-3) / 1e9 / peak},
                     "k_dss_fast (1.5 S algorithmic; DRAM floor 2 S)": {
-                        "ms": dss_ms, "achieved": local_nodes * 60 / (dss_ms * 1e-3) / 1e9,
-                        "frac": local_nodes * 60 / (dss_ms * 1e-3) / 1e9 / peak}},
+                        "ms": dss_ms, "achieved": local_nodes * 12 * S / (dss_ms * 1e-3) / 1e9,
+                        "frac": local_nodes * 12 * S / (dss_ms * 1e-3) / 1e9 / peak}},
                 "column_solve": {"kernel": "k_column_fast" if fast[0] else "k_column_implicit_window",
                                  "ms": column_ms,
                                  "unique_columns_per_s": ctx.column_count * 9.0 / 16.0 / (column_ms * 1e-3)},
-                "step_algorithmic_bytes": columns * L * 35.5 * 5 * 8,
-                "step_frac": columns * L * 35.5 * 5 * 8 / sec_per_step / 1e9 / peak / n_gpus}
+                "step_algorithmic_bytes": columns * L * 35.5 * S * 8,
+                "step_frac": columns * L * 35.5 * S * 8 / sec_per_step / 1e9 / peak / n_gpus,
+                "hbm_bytes_in_use": int(torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0])}
 
     # ---- end to end: host buffers in, host buffers out, every step ------------
     e2e = None
@@ -505,7 +536,7 @@ def main():
             "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": bench_config(ne, L, args.timescheme, world),
+            "config": bench_config(ne, L, args.timescheme, world, args.tracers),
             "halo_exchange": ("none (one rank)" if world == 1 else
                               "peer-memory stores over NVLink" if model.peer_exchange
                               else "NCCL all-to-all"),

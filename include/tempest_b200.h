@@ -306,6 +306,19 @@ int tb200_upload_rayleigh(tb200_ctx * ctx, int patch_index,
 int tb200_upload_element_area(tb200_ctx * ctx, int patch_index,
                               const double * area_node, const double * area_redge);
 int tb200_checksum(tb200_ctx * ctx, int inst, double * sums);
+/* Conservation diagnostics of an instance over the local patches
+ * (Grid::ComputeTotalEnergy, Grid.cpp:529-556 / GridPatch.cpp:925-1138;
+ * Grid::ComputeTotalPotentialEnstrophy, Grid.cpp:560-590 / GridPatch.cpp:1142-1230;
+ * Grid::ComputeTotalVerticalMomentum, Grid.cpp:594-623 / GridPatch.cpp:1234-1288).
+ * W on levels and rho on interfaces, which the reference's routines read and
+ * the Lorenz-staggered state does not carry, are formed with
+ * Grid::InterpolateREdgeToNode / InterpolateNodeToREdge (Grid.cpp:843-863).
+ * Shallow water: the potential enstrophy needs the DSS'd relative vorticity
+ * (GridGLL::ComputeVorticityDivergence, GridGLL.cpp:587-602), built in the
+ * scratch instance `work`; other equation sets ignore `work`. */
+int tb200_total_energy(tb200_ctx * ctx, int inst, double * energy);
+int tb200_total_potential_enstrophy(tb200_ctx * ctx, int inst, int work, double * enstrophy);
+int tb200_total_vertical_momentum(tb200_ctx * ctx, int inst, double * momentum);
 
 /* ---- multi-GPU halo traffic (Grid::Exchange, Grid.cpp:627-685) ----------- */
 /* Patches are partitioned over ranks (one process per GPU).  Per exchange the

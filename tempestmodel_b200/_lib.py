@@ -118,6 +118,9 @@ _SIGNATURES = {
     "tb200_upload_rayleigh": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "tb200_checksum": (c_int, [c_void_p, c_int, c_void_p]),
+    "tb200_total_energy": (c_int, [c_void_p, c_int, c_void_p]),
+    "tb200_total_potential_enstrophy": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "tb200_total_vertical_momentum": (c_int, [c_void_p, c_int, c_void_p]),
     "tb200_set_exchange": (c_int, [c_void_p, c_int, c_int, EXCHANGE_FN,
                                    c_void_p]),
     "tb200_exchange_counts": (c_int, [c_void_p, c_void_p, c_void_p]),

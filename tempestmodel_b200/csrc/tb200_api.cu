@@ -18,6 +18,7 @@
 #include "tb200_fast.cuh"
 #include "tb200_column_fast.cuh"
 #include "tb200_tracers.cuh"
+#include "tb200_diag.cuh"
 
 #define TB_CHECK(ctx, call) \
 	do { \
@@ -409,24 +410,16 @@ extern "C" int tb200_commit_layout(tb200_ctx * ctx) {
 		TB_CHECK(ctx, cudaMemset(ctx->g2d[q], 0, (size_t)nelem * nn * sizeof(double)));
 	}
 	const bool need3d = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO);
-	// the level / interface Jacobians are needed by every equation set
-	// (scalar hyperdiffusion, HorizontalDynamicsFEM.cpp:1913-1916)
-	for (int q = 0; q < (need3d ? 13 : 1); q++) {
-		if (dalloc(ctx, &ctx->g3n[q], (size_t)nelem * L * nn)) return 1;
-		if (dalloc(ctx, &ctx->g3e[q], (size_t)nelem * (L + 1) * nn)) return 1;
-	}
+	// The 3-D metric arrays (26 values per node against 5 of the state) are
+	// allocated when the host uploads them (tb200_upload_geometry).  A host that
+	// supplies only the 2-D metric, the topography derivatives and the vertical
+	// coordinate runs on the column constants / the on-the-fly metric and keeps
+	// that memory for the state: ne = 240, L = 60 holds 5 instances in 67 GB
+	// instead of 136 GB.
 	DevGeom & g = ctx->geom;
 	g.inv_da = ctx->d_inv_da; g.inv_db = ctx->d_inv_db; g.nu_scale = ctx->d_nu_scale;
 	g.j2d = ctx->g2d[0]; g.a0 = ctx->g2d[1]; g.a1 = ctx->g2d[2];
 	g.b0 = ctx->g2d[3]; g.b1 = ctx->g2d[4]; g.f = ctx->g2d[5]; g.zs = ctx->g2d[6];
-	g.jac = ctx->g3n[0];
-	g.jace = ctx->g3e[0];
-	for (int m = 0; m < 3; m++) {
-		g.ca[m] = ctx->g3n[1 + m]; g.cb[m] = ctx->g3n[4 + m];
-		g.cx[m] = ctx->g3n[7 + m]; g.dr[m] = ctx->g3n[10 + m];
-		g.cae[m] = ctx->g3e[1 + m]; g.cbe[m] = ctx->g3e[4 + m];
-		g.cxe[m] = ctx->g3e[7 + m]; g.dre[m] = ctx->g3e[10 + m];
-	}
 	if (dalloc(ctx, &ctx->d_sums, 64)) return 1;
 	if (dalloc(ctx, &ctx->d_info, 4)) return 1;
 	TB_CHECK(ctx, cudaMemset(ctx->d_info, 0, 4 * sizeof(int)));
@@ -530,6 +523,28 @@ extern "C" int tb200_set_column_op(
 
 ///////////////////////////////////////////////////////////////////////////////
 
+// 3-D metric arrays: device storage on first use
+static int ensure_geom3d(tb200_ctx * ctx, int q0, int nq, bool edge) {
+	const DevLayout & lay = ctx->lay;
+	const size_t count = (size_t)lay.nelem * (lay.nlev + (edge ? 1 : 0)) * lay.nn;
+	double ** arr = edge ? ctx->g3e : ctx->g3n;
+	for (int q = q0; q < q0 + nq; q++) {
+		if (arr[q] != 0) continue;
+		if (dalloc(ctx, &arr[q], count)) return 1;
+		TB_CHECK(ctx, cudaMemset(arr[q], 0, count * sizeof(double)));
+	}
+	DevGeom & g = ctx->geom;
+	g.jac = ctx->g3n[0];
+	g.jace = ctx->g3e[0];
+	for (int m = 0; m < 3; m++) {
+		g.ca[m] = ctx->g3n[1 + m]; g.cb[m] = ctx->g3n[4 + m];
+		g.cx[m] = ctx->g3n[7 + m]; g.dr[m] = ctx->g3n[10 + m];
+		g.cae[m] = ctx->g3e[1 + m]; g.cbe[m] = ctx->g3e[4 + m];
+		g.cxe[m] = ctx->g3e[7 + m]; g.dre[m] = ctx->g3e[10 + m];
+	}
+	return 0;
+}
+
 static int upload_geom_array(
 	tb200_ctx * ctx, const PatchInfo & pi, const double * host,
 	int nlev, int nm, double * d0, double * d1, double * d2
@@ -568,9 +583,19 @@ extern "C" int tb200_upload_geometry(
 	if (upload_geom_array(ctx, *pi, gh->contrametric2db, 1, 2, g2[3], g2[4], 0)) return 1;
 	if (upload_geom_array(ctx, *pi, gh->coriolis, 1, 1, g2[5], 0, 0)) return 1;
 	if (upload_geom_array(ctx, *pi, gh->topography, 1, 1, g2[6], 0, 0)) return 1;
+	if (gh->jacobian != 0 && ensure_geom3d(ctx, 0, 1, false)) return 1;
+	if (gh->jacobian_redge != 0 && ensure_geom3d(ctx, 0, 1, true)) return 1;
 	if (upload_geom_array(ctx, *pi, gh->jacobian, L, 1, gn[0], 0, 0)) return 1;
 	if (upload_geom_array(ctx, *pi, gh->jacobian_redge, L + 1, 1, ge[0], 0, 0)) return 1;
 	if (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
+		if (gh->contrametrica != 0 && ensure_geom3d(ctx, 1, 3, false)) return 1;
+		if (gh->contrametricb != 0 && ensure_geom3d(ctx, 4, 3, false)) return 1;
+		if (gh->contrametricxi != 0 && ensure_geom3d(ctx, 7, 3, false)) return 1;
+		if (gh->derivr_node != 0 && ensure_geom3d(ctx, 10, 3, false)) return 1;
+		if (gh->contrametrica_redge != 0 && ensure_geom3d(ctx, 1, 3, true)) return 1;
+		if (gh->contrametricb_redge != 0 && ensure_geom3d(ctx, 4, 3, true)) return 1;
+		if (gh->contrametricxi_redge != 0 && ensure_geom3d(ctx, 7, 3, true)) return 1;
+		if (gh->derivr_redge != 0 && ensure_geom3d(ctx, 10, 3, true)) return 1;
 		if (upload_geom_array(ctx, *pi, gh->contrametrica, L, 3, gn[1], gn[2], gn[3])) return 1;
 		if (upload_geom_array(ctx, *pi, gh->contrametricb, L, 3, gn[4], gn[5], gn[6])) return 1;
 		if (upload_geom_array(ctx, *pi, gh->contrametricxi, L, 3, gn[7], gn[8], gn[9])) return 1;
@@ -1097,6 +1122,19 @@ extern "C" double tb200_fast_path_metric_error(tb200_ctx * ctx) {
 ///////////////////////////////////////////////////////////////////////////////
 // Dynamics
 
+// The general kernels read the stored level / interface Jacobians (and, without
+// the on-the-fly metric, every 3-D metric array): refuse to run them on a
+// context whose host supplied the lean geometry only.
+static int need_metric3d(tb200_ctx * ctx, const char * what) {
+	const bool have_jac = (ctx->g3n[0] != 0 && ctx->g3e[0] != 0);
+	const bool have_all = ctx->geometry3d_uploaded;
+	if (have_jac && (have_all || ctx->geom.analytic
+		|| ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO)) return 0;
+	ctx->err = std::string(what) + ": the 3-D metric arrays were not uploaded "
+		"(lean geometry runs the column-constant kernels only)";
+	return 1;
+}
+
 static int check_ops(tb200_ctx * ctx) {
 	for (int q = 0; q < TB_NOPS; q++) {
 		if (q == 5 || q == 6) continue;   // not used by the hot path
@@ -1216,6 +1254,7 @@ static int nh_launch(
 		TB_KERNEL_CHECK(ctx);
 		return 0;
 	}
+	if (need_metric3d(ctx, "explicit stage (general kernel)")) return 1;
 	NHArgs a;
 	a.dt = dt;
 	a.xz = ctx->cfg.cartesian_xz;
@@ -1387,6 +1426,7 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 // (VerticalDynamicsFEM.cpp:1528-1536, 1637)
 static int column_tracers(tb200_ctx * ctx, int in, int out, double dt) {
 	const DevLayout & lay = ctx->lay;
+	if (need_metric3d(ctx, "tracer column update")) return 1;
 	TracerColumnArgs ta;
 	ta.col_node = ctx->d_col_node;
 	ta.col_dups = ctx->d_col_dups;
@@ -1466,6 +1506,7 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 		return 0;
 	}
 
+	if (need_metric3d(ctx, "implicit column solve (general kernel)")) return 1;
 	// one warp per column with all work arrays in shared memory, unless the
 	// column is too tall for it (or TB200_COLUMN_KERNEL=thread asks for the
 	// thread-per-column implementation)
@@ -1980,6 +2021,13 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 	return 0;
 }
 
+// DSS of rows that hold scalars (no covector re-basing at panel seams):
+// the vorticity of the shallow-water enstrophy diagnostic
+static int tb_dss_scalar_rows(tb200_ctx * ctx, int inst, int row0, int row1) {
+	if (!ctx->connectivity_built) TB_FAIL(ctx, "connectivity not built");
+	return dss_rows(ctx, inst, row0, row1, false);
+}
+
 extern "C" int tb200_dss(tb200_ctx * ctx, int inst, int mask) {
 	if (!ctx->connectivity_built) TB_FAIL(ctx, "connectivity not built");
 	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid state instance");
@@ -1998,6 +2046,7 @@ extern "C" int tb200_dss(tb200_ctx * ctx, int inst, int mask) {
 
 static int hyper_scalar(tb200_ctx * ctx, int in, int out, double dt, double nu, bool scale) {
 	const DevLayout & lay = ctx->lay;
+	if (need_metric3d(ctx, "scalar hyperdiffusion (general kernel)")) return 1;
 	HyperRows hr;
 	memset(&hr, 0, sizeof(hr));
 	int nsel = 0;
@@ -2449,4 +2498,74 @@ extern "C" int tb200_test_band_solve(
 		for (int q = 0; q < n; q++) b[(size_t)c * n + q] = hb[(size_t)q * ncols + c];
 	}
 	return check_column_info(ctx);
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Conservation diagnostics (kernels: tb200_diag.cuh)
+
+
+static int diagnostic(tb200_ctx * ctx, int inst, int what, const double * vort, double * value) {
+	if (ctx->d_area_node == 0) TB_FAIL(ctx, "element areas not uploaded");
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid state instance");
+	const bool sw = (ctx->cfg.eqn_type == TB200_EQN_SHALLOW_WATER);
+	if (!sw) {
+		if (ctx->ops.op[TB200_OP_INTERP_E2N].coeff == 0 || ctx->ops.op[TB200_OP_INTERP_N2E].coeff == 0) {
+			TB_FAIL(ctx, "vertical column operators not set");
+		}
+		if (!ctx->geom.analytic && !ctx->geometry3d_uploaded) {
+			TB_FAIL(ctx, "diagnostics need the 3-D metric arrays or the terrain metric");
+		}
+		if (ctx->d_reta_n == 0) TB_FAIL(ctx, "vertical coordinate not set (tb200_set_vertical_coordinate)");
+	}
+	DiagArgs da;
+	da.g = ctx->cfg.g;
+	da.gamma = ctx->cfg.cp / (ctx->cfg.cp - ctx->cfg.R);              // PhysicalConstants.h:368
+	da.pscale = ctx->cfg.p0 * pow(ctx->cfg.R / ctx->cfg.p0, da.gamma);  // PhysicalConstants.h:375
+	da.shallow = sw ? 1 : 0;
+	da.what = what;
+	da.vort = vort;
+	DevGeom g = ctx->geom;
+	g.reta_n = ctx->d_reta_n; g.reta_e = ctx->d_reta_e; g.ztop = ctx->cfg.ztop;
+	TB_CHECK(ctx, cudaMemsetAsync(ctx->d_sums, 0, 64 * sizeof(double), ctx->stream));
+	auto kfn = k_diagnostic;
+	TB_LAUNCH(kfn, dim3(2 * 148), dim3(128), 0, ctx->stream,
+		ctx->lay, g, ctx->ops, da, (const double *)ctx->inst[inst],
+		(const double *)ctx->d_area_node, (const double *)ctx->d_area_redge, ctx->d_sums);
+	TB_KERNEL_CHECK(ctx);
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	TB_CHECK(ctx, cudaMemcpy(value, ctx->d_sums, sizeof(double), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int tb200_total_energy(tb200_ctx * ctx, int inst, double * energy) {
+	return diagnostic(ctx, inst, 0, 0, energy);
+}
+
+extern "C" int tb200_total_vertical_momentum(tb200_ctx * ctx, int inst, double * momentum) {
+	if (ctx->cfg.eqn_type == TB200_EQN_SHALLOW_WATER) {
+		// GridPatch.cpp:1262-1265
+		TB_FAIL(ctx, "ComputeTotalVerticalMomentum() Not implemented for ShallowWaterEquations");
+	}
+	return diagnostic(ctx, inst, 2, 0, momentum);
+}
+
+extern "C" int tb200_total_potential_enstrophy(
+	tb200_ctx * ctx, int inst, int work, double * enstrophy
+) {
+	if (ctx->cfg.eqn_type != TB200_EQN_SHALLOW_WATER) {
+		return diagnostic(ctx, inst, 1, 0, enstrophy);
+	}
+	// Grid::ComputeVorticityDivergence + DSS of the vorticity (GridGLL.cpp:587-602)
+	const int ni = (int)ctx->inst.size();
+	if (work < 0 || work >= ni || work == inst) {
+		TB_FAIL(ctx, "potential enstrophy of a shallow-water state needs a scratch instance");
+	}
+	const DevLayout & lay = ctx->lay;
+	const long long nitems = lay.nelem * lay.nlev;
+	auto kfn = k_sw_vorticity;
+	TB_LAUNCH(kfn, dim3((unsigned)((nitems + 7) / 8)), dim3(128), 0, ctx->stream,
+		lay, ctx->geom, ctx->tables, (const double *)ctx->inst[inst], ctx->inst[work]);
+	TB_KERNEL_CHECK(ctx);
+	if (tb_dss_scalar_rows(ctx, work, lay.rowoff[0], lay.rowoff[0] + lay.nlev)) return 1;
+	return diagnostic(ctx, inst, 1, ctx->inst[work], enstrophy);
 }

@@ -248,6 +248,24 @@ class DeviceContext:
         self._ck(self.lib.tb200_checksum(self._h, inst, _ptr(s)))
         return s
 
+    def total_energy(self, inst):
+        """Grid::ComputeTotalEnergy over the local patches."""
+        v = np.zeros(1, dtype=np.float64)
+        self._ck(self.lib.tb200_total_energy(self._h, inst, _ptr(v)))
+        return float(v[0])
+
+    def total_potential_enstrophy(self, inst, work=-1):
+        """Grid::ComputeTotalPotentialEnstrophy (shallow water: `work` is a scratch
+        instance for the DSS'd vorticity)."""
+        v = np.zeros(1, dtype=np.float64)
+        self._ck(self.lib.tb200_total_potential_enstrophy(self._h, inst, work, _ptr(v)))
+        return float(v[0])
+
+    def total_vertical_momentum(self, inst):
+        v = np.zeros(1, dtype=np.float64)
+        self._ck(self.lib.tb200_total_vertical_momentum(self._h, inst, _ptr(v)))
+        return float(v[0])
+
     def test_band_solve(self, ab, b, kl, ku):
         ab = np.ascontiguousarray(ab, dtype=np.float64)
         x = np.array(b, dtype=np.float64, order="C", copy=True)

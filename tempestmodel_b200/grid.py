@@ -303,9 +303,11 @@ class GridPatchCSGLL:
         return cs.seam_transforms(self.panel, self.nea, self.neb, self.ea0, self.eb0,
                                   g.ne, g.np, self.anode, self.bnode)
 
-    def evaluate_geometric_terms(self, zs, dazs, dbzs):
+    def evaluate_geometric_terms(self, zs, dazs, dbzs, lean=False):
         """GridPatchCSGLL::EvaluateGeometricTerms (GridPatchCSGLL.cpp:295-574).
-        zs, dazs, dbzs: topography and its (DSS'd) derivatives on interior nodes."""
+        zs, dazs, dbzs: topography and its (DSS'd) derivatives on interior nodes.
+        lean: the 2-D terms and the element areas only (the device rebuilds the
+        3-D metric from column constants)."""
         g = self.grid
         phys = g.phys
         L = g.nlev
@@ -352,6 +354,13 @@ class GridPatchCSGLL:
             dr = np.stack([dar, dbr, dxr], axis=-1)
             return jac, area, ca, cb, cx, dr
 
+        if lean:
+            for name, reta, warea in (("area_node", g.reta_levels, g.reta_levels_area),
+                                      ("area_redge", g.reta_interfaces, g.reta_interfaces_area)):
+                col = ((g.ztop - zs) * j2d * (wi * self.delta) * (wj * self.delta))
+                setattr(self, name, self._pad(col[:, :, None] * warea[None, None, :]))
+            self.zs = zs
+            return out
         jac, area, ca, cb, cx, dr = column(g.reta_levels, g.reta_levels_area)
         out.update(jacobian=self._pad(jac), contrametrica=self._pad(ca),
                    contrametricb=self._pad(cb), contrametricxi=self._pad(cx),

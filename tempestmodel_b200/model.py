@@ -66,6 +66,10 @@ class Model:
         self._host = {}
         self._host_tracers = {}
         self.device_setup = False
+        # lean geometry: upload the 2-D metric, topography derivatives and the
+        # vertical coordinate only (no 3-D metric arrays: 26 values per node);
+        # the column-constant kernels need nothing else
+        self.lean_geometry = False
 
     # -- setup (Model::SetGrid, SetTestCase and the head of Model::Go) ---------
     def initialize(self, upload_state=True):
@@ -84,7 +88,8 @@ class Model:
         for p in g.patches:
             ctx.set_node_ids(p.index, p.node_ids())
         for p in self.local:
-            geo = p.evaluate_geometric_terms(p._zs, p._dazs, p._dbzs)
+            geo = p.evaluate_geometric_terms(p._zs, p._dazs, p._dbzs,
+                                             **({"lean": True} if self.lean_geometry else {}))
             ctx.upload_geometry(p.index, **geo)
             ctx.upload_element_area(p.index, p.area_node, p.area_redge)
             ctx.set_seam_transforms(p.index, *p.seam_transforms())

@@ -173,6 +173,24 @@ CASES["jw_ne4_l30_p24"] = dict(
         "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0", "checksum:cs"]),
     compact=True)
 
+# conservation diagnostics of the reference (Grid::ComputeTotalEnergy,
+# ComputeTotalPotentialEnstrophy, ComputeTotalVerticalMomentum) on the state
+# before and after two steps; only the scalars are stored, geometry and initial
+# state come from the case named in geometry_from (same flags, same script head)
+CASES["jw_ne2_l6_energy"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s"],
+    script="addw:0,20000;dss:0;energy:e0,0;step:2;energy:e2,0;checksum:cs",
+    geometry_from="jw_ne2_l6_strang", scalars_only=True)
+CASES["jw_ne2_l30_energy"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "30", "--ztop", "30000", "--pert", "Exp",
+                      "--dt", "200s"],
+    script="addw:0,20000;dss:0;energy:e0,0;step:2;energy:e2,0;checksum:cs",
+    geometry_from="jw_ne2_l30_strang", scalars_only=True)
+CASES["sw2_ne2_energy"] = dict(
+    case="sw2", flags=["--resolution", "2", "--alpha", "0.7"],
+    script="energy:e0,0;step:2;energy:e2,0;checksum:cs",
+    geometry_from="sw2_ne2_alpha", scalars_only=True)
+
 _SHARED_PREFIXES = ("patch", "op.", "grid.")
 
 
@@ -188,8 +206,10 @@ def load_case(name):
             d = {k: z[k] for k in z.files}
         base = CASES.get(name, {}).get("geometry_from")
         if base is not None:
+            scalars = CASES[name].get("scalars_only")
             for k, v in load_case(base).items():
-                if k.startswith(_SHARED_PREFIXES) and k not in d:
+                if (k.startswith(_SHARED_PREFIXES) or (scalars and k.startswith("ic."))) \
+                        and k not in d:
                     d[k] = v
         return d
     if not refdump.have_ref_dump():
@@ -230,6 +250,8 @@ def write_golden(name):
                              npatch=c.get("npatch", 6))
     if c.get("compact"):
         d = _compact(d)
+    if c.get("scalars_only"):
+        d = {k: v for k, v in d.items() if v.size <= 16 and not k.startswith(_SHARED_PREFIXES)}
     os.makedirs(GOLDEN, exist_ok=True)
     if c.get("geometry_from") is not None:
         base = load_case(c["geometry_from"])

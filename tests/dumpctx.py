@@ -18,7 +18,7 @@ def S(d, k):
 
 
 def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
-                      nranks=1, exchange=None, analytic_metric=True):
+                      nranks=1, exchange=None, analytic_metric=True, lean=False):
     npatch = S(d, "grid.npatch")
     np_ = S(d, "grid.np")
     nlev = S(d, "grid.nlev")
@@ -76,7 +76,10 @@ def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
                 contrametric2db=d[p + "contrametric2db"],
                 coriolis=d[p + "coriolis"], topography=d[p + "topography"],
                 jacobian=d[p + "jacobian"], jacobian_redge=d[p + "jacobianredge"])
-            if eqn == 2:
+            if lean:
+                # lean geometry: no 3-D metric arrays at all
+                del geo["jacobian"], geo["jacobian_redge"]
+            if eqn == 2 and not lean:
                 geo.update(
                     contrametrica=d[p + "contrametrica"],
                     contrametricb=d[p + "contrametricb"],

@@ -633,3 +633,43 @@ def test_tracers_ars343(library):
             ref += (dumpctx.interior(d["st.patch%d.inst0.tracers" % n])[t] * area).sum()
         assert abs(mass - ref) <= (5.0 * sp["mass_rel_spread"][t] + 1e-12) * abs(ref), (t, mass, ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["jw_ne2_l6_energy", "jw_ne2_l30_energy", "sw2_ne2_energy"])
+def test_conservation_diagnostics(library, name):
+    """Grid::ComputeTotalEnergy / ComputeTotalPotentialEnstrophy /
+    ComputeTotalVerticalMomentum on the device against the reference's values
+    (oracle/ref_dump.cpp `energy`) for the initial state (1e-12) and after two
+    Strang steps (the state itself is held to 1e-10)."""
+    d = cases.load_case(name)
+    ctx = dumpctx.context_from_dump(d, library=library)
+    sw = ctx.cfg.ncomp == 3
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+
+    def diag():
+        v = [ctx.total_energy(0), ctx.total_potential_enstrophy(0, 3)]
+        if not sw:
+            v.append(ctx.total_vertical_momentum(0))
+        return v
+
+    for tag, tol in (("e0", 1e-12), ("e2", 1e-10)):
+        ref = d[tag + ".energy"]
+        got = diag()
+        for q, v in enumerate(got):
+            # the vertical momentum sums to a remainder of much larger terms
+            scale = abs(ref[q]) if q < 2 else max(abs(ref[q]), 1e-3 * abs(ref[1]))
+            assert abs(v - ref[q]) <= tol * scale, (tag, q, v, ref[q])
+        if tag == "e0":
+            if sw:
+                for m in range(1, ctx.cfg.ninstances):
+                    ctx.copy(0, m)      # instance 3 served as scratch
+            ctx.step("strang", True, False, 200.0)
+            ctx.step("strang", False, False, 200.0)
+            ctx.check_errors()
+    if sw:
+        from tempestmodel_b200 import TempestError
+        with pytest.raises(TempestError, match="Not implemented for ShallowWaterEquations"):
+            ctx.total_vertical_momentum(0)
+    ctx.close()

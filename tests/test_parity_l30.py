@@ -151,3 +151,37 @@ def test_24_patches_l30(library):
     assert abs(cs[4] - ref[4]) <= 1e-13 * abs(ref[4])
     assert abs(cs[2] - ref[2]) <= 1e-13 * abs(ref[2])
     ctx.close()
+
+
+def test_lean_geometry_l30(library):
+    """A host that uploads the 2-D metric, the topography derivatives and the
+    vertical coordinate only (no 3-D metric arrays: the memory layout of the
+    ne = 240, L = 60 run): same bits as with the full geometry, and the general
+    kernels refuse to run."""
+    from tempestmodel_b200 import TempestError
+    d = cases.load_case("jw_ne2_l30_strang")
+    res = []
+    for lean in (False, True):
+        ctx = dumpctx.context_from_dump(d, library=library, lean=lean)
+        enabled, reason, dev = ctx.fast_path()
+        assert enabled, reason
+        dumpctx.upload_tag(ctx, d, "ic")
+        for m in range(1, ctx.cfg.ninstances):
+            ctx.copy(0, m)
+        ctx.step("strang", True, False, 200.0)
+        ctx.step("strang", False, False, 200.0)
+        ctx.check_errors()
+        assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+        res.append(dumpctx.download(ctx, d, 0))
+        if lean:
+            import os
+            os.environ["TB200_COLUMN_KERNEL"] = "window"
+            try:
+                with pytest.raises(TempestError, match="3-D metric arrays were not uploaded"):
+                    ctx.v_step_implicit(0, 0, 1.0)
+            finally:
+                del os.environ["TB200_COLUMN_KERNEL"]
+        ctx.close()
+    for n in res[0]:
+        for loc in (0, 1):
+            assert np.array_equal(res[0][n][loc], res[1][n][loc])
