@@ -357,6 +357,10 @@ int tb200_exchange_counts(tb200_ctx * ctx, int64_t * send_nodes, int64_t * recv_
 /* ---- introspection for tests and the bench -------------------------------- */
 /* Number of kernels this context has launched since creation. */
 int64_t tb200_launch_count(const tb200_ctx * ctx);
+/* Averaging groups (shared nodes) that the stage and hyperdiffusion kernels
+ * average themselves when a DSS follows them (all members neighbours inside one
+ * patch); 0 when the fused DSS is unavailable.  TB200_DSS_FUSED=0 turns it off. */
+int64_t tb200_fused_group_count(const tb200_ctx * ctx);
 /* Total columns (element-local nodes incl. duplicates) held by this context. */
 int64_t tb200_column_count(const tb200_ctx * ctx);
 /* Direct banded solve used by the implicit step, exposed for pinning against

@@ -129,6 +129,7 @@ _SIGNATURES = {
     "tb200_peer_detach": (c_int, [c_void_p]),
     "tb200_launch_count": (c_int64, [c_void_p]),
     "tb200_column_count": (c_int64, [c_void_p]),
+    "tb200_fused_group_count": (c_int64, [c_void_p]),
     "tb200_debug_column_assembly": (c_int, [c_void_p, c_int, c_double, c_int,
                                             c_void_p, c_int]),
     "tb200_test_band_solve": (c_int, [c_void_p, c_int, c_int, c_int, c_int,

@@ -103,6 +103,26 @@ static long long persistent_blocks(
 	return nb;
 }
 
+// Blocks of a launch with the fused DSS: all resident (they wait for each other's
+// elements), at most one per strip.  The emulation runs blocks one after another:
+// one block, strips in order.
+template <typename K>
+static long long fused_blocks(tb200_ctx * ctx, K kfn, int threads, size_t smem) {
+#ifdef TB200_EMU
+	(void)kfn; (void)threads; (void)smem; (void)ctx;
+	return 1;
+#else
+	int per_sm = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem) != cudaSuccess
+		|| per_sm < 1) {
+		per_sm = 1;
+	}
+	long long nb = (long long)ctx->sm_count * per_sm;
+	if (nb > ctx->nstrips) nb = ctx->nstrips;
+	return nb;
+#endif
+}
+
 // Multi-rank overlap of the halo exchange with compute: an element kernel that
 // is followed by a DSS runs first on the elements that own nodes of the send
 // list (same stream as the pack + exchange), and on all other elements on a
@@ -161,6 +181,35 @@ static int split_join(tb200_ctx * ctx) {
 #endif
 	ctx->split_pending = false;
 	return 0;
+}
+
+// the next launch of a pipelined kernel may average the in-patch groups itself
+static bool fuse_enabled(const tb200_ctx * ctx) {
+	if (!ctx->fuse_ready || !ctx->fuse_want || split_enabled(ctx)) return false;
+	if (ctx->lay.nrows > TBF_AROWS * TBF_THREADS) return false;   // rows per thread of the alpha phase
+	// Off unless TB200_DSS_FUSED=1: measured on the B200 (ne = 120, L = 30) the
+	// fused kernels cut the DRAM traffic of stage + DSS from 8.5 to 5.7 GB but run
+	// 2.7-3.7 ms against 2.0-2.3 ms for stage kernel + separate DSS pass - flag
+	// polls, the alpha phase and its scattered 8-byte stores sit on the critical
+	// path of a kernel that is latency-bound at 8 warps per SM
+	// (profiles/r2_fused_dss_experiment.txt).  Kept, with its bit-for-bit tests,
+	// as the starting point for a cluster / DSMEM variant.
+	const char * e = getenv("TB200_DSS_FUSED");
+	if (e == 0 || strcmp(e, "1") != 0) return false;
+	if (getenv("TB200_PIPE_BLOCKS") != 0) return false;     // tests of the strided walk
+	return true;
+}
+
+static FuseArgs fuse_args(tb200_ctx * ctx) {
+	FuseArgs fz;
+	memset(&fz, 0, sizeof(fz));
+	fz.strip_first = ctx->d_strip_first;
+	fz.strip_len = ctx->d_strip_len;
+	fz.strip_neb = ctx->d_strip_neb;
+	fz.nstrips = ctx->nstrips;
+	fz.done = ctx->d_done;
+	fz.epoch = ctx->fuse_epoch;
+	return fz;
 }
 
 static PatchInfo * find_patch(tb200_ctx * ctx, int patch_index) {
@@ -312,6 +361,10 @@ extern "C" int tb200_sync(tb200_ctx * ctx) {
 
 extern "C" int64_t tb200_launch_count(const tb200_ctx * ctx) {
 	return ctx->launches;
+}
+
+extern "C" int64_t tb200_fused_group_count(const tb200_ctx * ctx) {
+	return ctx->fuse_ready ? (int64_t)(ctx->ngroups - ctx->nrem) : 0;
 }
 
 extern "C" int64_t tb200_column_count(const tb200_ctx * ctx) {
@@ -1187,7 +1240,11 @@ static int nh_launch(
 			pb.nsrc = 0;
 		}
 		if (do_h && fits && !(nopipe != 0 && strcmp(nopipe, "fast") == 0)) {
-			const size_t smem = tb_pipe_smem_doubles(lay.nrows, lay.nlev, pb.nsrc) * sizeof(double);
+			// DSS of `out` follows: the kernel averages the in-patch groups itself
+			bool fuse = do_v && fuse_enabled(ctx);
+			if (fuse && tb_pipe_smem_doubles(lay.nrows, lay.nlev, pb.nsrc, true) * sizeof(double)
+					> 227 * 1024 - 1024) fuse = false;
+			const size_t smem = tb_pipe_smem_doubles(lay.nrows, lay.nlev, pb.nsrc, fuse) * sizeof(double);
 			if (smem <= 227 * 1024 - 1024) {
 				const dim3 block(TBF_THREADS);
 #ifndef TB200_EMU
@@ -1196,8 +1253,22 @@ static int nh_launch(
 #define TB_PIPE_ATTR(kfn)
 #endif
 #define TB_PIPE_LAUNCH(V, N) { \
-					auto kfn = k_nh_stage_pipe<V, N>; \
+					if (fuse) { \
+						auto kfn = k_nh_stage_pipe<V, N, true>; \
+						TB_PIPE_ATTR(kfn); \
+						ctx->fuse_epoch++; \
+						const FuseArgs fz = fuse_args(ctx); \
+						const dim3 grid((unsigned)fused_blocks(ctx, kfn, TBF_THREADS, smem)); \
+						TB_LAUNCH(kfn, grid, block, smem, ctx->stream, \
+							lay, ctx->tables, ctx->phys, fa, \
+							(const double *)ctx->inst[in], pb, ctx->inst[out], elem_list(ctx, 0), fz); \
+						ctx->launches++; \
+						ctx->writes++; \
+						ctx->fuse_done = true; \
+					} else { \
+					auto kfn = k_nh_stage_pipe<V, N, false>; \
 					TB_PIPE_ATTR(kfn); \
+					const FuseArgs fz = fuse_args(ctx); \
 					const bool split = split_enabled(ctx); \
 					if (split && split_fork(ctx)) return 1; \
 					for (int part = split ? 1 : 0; part <= (split ? 2 : 0); part++) { \
@@ -1207,11 +1278,11 @@ static int nh_launch(
 							(part == 2) ? overlap_reserve() : 0)); \
 						TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream, \
 							lay, ctx->tables, ctx->phys, fa, \
-							(const double *)ctx->inst[in], pb, ctx->inst[out], el); \
+							(const double *)ctx->inst[in], pb, ctx->inst[out], el, fz); \
 						ctx->launches++; \
 						ctx->writes++; \
 					} \
-					if (split && split_mark(ctx)) return 1; }
+					if (split && split_mark(ctx)) return 1; } }
 				if (do_v) {
 					if (pb.nsrc == 0) TB_PIPE_LAUNCH(true, 0)
 					else if (pb.nsrc == 1) TB_PIPE_LAUNCH(true, 1)
@@ -1345,14 +1416,21 @@ extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double d
 // not feed it.
 extern "C" int tb200_hv_step_explicit_combine(
 	tb200_ctx * ctx, const double * coeff, int ncoeff, int in, int out, double dt);
+static int dss_instance(tb200_ctx * ctx, int inst, int mask, bool remainder_only);
 
 extern "C" int tb200_hv_step_explicit_combine_dss(
 	tb200_ctx * ctx, const double * coeff, int ncoeff, int in, int out, double dt
 ) {
 	ctx->want_split = overlap_wanted();
+	ctx->fuse_want = true;
+	ctx->fuse_done = false;
 	int rc = tb200_hv_step_explicit_combine(ctx, coeff, ncoeff, in, out, dt);
 	ctx->want_split = false;
-	if (rc == 0) rc = tb200_dss(ctx, out, TB200_DATA_STATE | TB200_DATA_TRACERS);
+	ctx->fuse_want = false;
+	// the stage kernel has averaged the in-patch groups: the rest (patch edges,
+	// seams, strip ends, other ranks) goes through the group kernels
+	if (rc == 0) rc = dss_instance(ctx, out, TB200_DATA_STATE | TB200_DATA_TRACERS, ctx->fuse_done);
+	ctx->fuse_done = false;
 	if (split_join(ctx)) return 1;
 	return rc;
 }
@@ -1936,7 +2014,9 @@ extern "C" int tb200_peer_detach(tb200_ctx * ctx) {
 	return 0;
 }
 
-static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state) {
+static int dss_rows(
+	tb200_ctx * ctx, int inst, int row0, int row1, bool is_state, bool remainder_only = false
+) {
 	if (row1 <= row0) return 0;
 	const DevLayout & lay = ctx->lay;
 	const int nsel = row1 - row0;
@@ -1973,6 +2053,12 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 	a.members = ctx->d_members;
 	a.flags = ctx->d_flags;
 	a.ngroups = ctx->ngroups;
+	if (remainder_only) {
+		// the groups the fused kernels left raw
+		a.members = ctx->d_rem_members;
+		a.flags = ctx->d_rem_flags;
+		a.ngroups = ctx->nrem;
+	}
 	a.nlocal = (int)(lay.nelem * lay.nn);
 	a.recv = recvbuf;
 	a.row0 = row0;
@@ -1981,7 +2067,7 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 	a.uv_row1 = is_state ? (lay.rowoff[1] + lay.rowlev[1]) : -1;
 	a.nsel = nsel;
 	a.sel_row0 = row0;
-	{
+	if (a.ngroups > 0) {
 		const int block = 128;
 		static const bool classes = []() {  // TB200_DSS_KERNEL=generic: row-at-a-time kernel for every group
 			const char * e = getenv("TB200_DSS_KERNEL");
@@ -1997,16 +2083,20 @@ static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state
 		}
 		if (classes) {
 			auto kfn = k_dss_fast;
-			TB_LAUNCH_FLAT(kfn, dim3((ctx->ngroups + block - 1) / block, gy), dim3(block), 0,
+			TB_LAUNCH_FLAT(kfn, dim3((a.ngroups + block - 1) / block, gy), dim3(block), 0,
 				ctx->stream, lay, a, ctx->inst[inst]);
 		} else {
 			auto kfn = k_dss_scalar;
-			TB_LAUNCH_FLAT(kfn, dim3((ctx->ngroups + block - 1) / block, gy), dim3(block), 0,
+			TB_LAUNCH_FLAT(kfn, dim3((a.ngroups + block - 1) / block, gy), dim3(block), 0,
 				ctx->stream, lay, a, ctx->inst[inst]);
 		}
 		TB_KERNEL_CHECK(ctx);
 	}
 	if (is_state && ctx->nseam > 0) {
+		// seam groups index the full group list
+		a.members = ctx->d_members;
+		a.flags = ctx->d_flags;
+		a.ngroups = ctx->ngroups;
 		SeamArgs sa;
 		sa.group = ctx->d_seam_group;
 		sa.mats = ctx->d_seam_mats;
@@ -2028,17 +2118,21 @@ static int tb_dss_scalar_rows(tb200_ctx * ctx, int inst, int row0, int row1) {
 	return dss_rows(ctx, inst, row0, row1, false);
 }
 
-extern "C" int tb200_dss(tb200_ctx * ctx, int inst, int mask) {
+static int dss_instance(tb200_ctx * ctx, int inst, int mask, bool remainder_only) {
 	if (!ctx->connectivity_built) TB_FAIL(ctx, "connectivity not built");
 	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid state instance");
 	const DevLayout & lay = ctx->lay;
 	if (mask & TB200_DATA_STATE) {
-		if (dss_rows(ctx, inst, 0, lay.nrows_state, true)) return 1;
+		if (dss_rows(ctx, inst, 0, lay.nrows_state, true, remainder_only)) return 1;
 	}
 	if ((mask & TB200_DATA_TRACERS) && lay.ntr > 0) {
-		if (dss_rows(ctx, inst, lay.nrows_state, lay.nrows, false)) return 1;
+		if (dss_rows(ctx, inst, lay.nrows_state, lay.nrows, false, remainder_only)) return 1;
 	}
 	return 0;
+}
+
+extern "C" int tb200_dss(tb200_ctx * ctx, int inst, int mask) {
+	return dss_instance(ctx, inst, mask, false);
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -2113,11 +2207,44 @@ static int hyper_fast(
 	ha.scale_nu = scale ? 1 : 0;
 	ha.xz = ctx->cfg.cartesian_xz;
 	const bool has_base = (base >= 0);
-	const size_t smem = tb_hyper_smem_doubles(lay.nrows, lay.nlev, has_base) * sizeof(double);
+	bool fuse = fuse_enabled(ctx);
+	if (fuse && tb_hyper_smem_doubles(lay.nrows, lay.nlev, has_base, true) * sizeof(double)
+			> 227 * 1024 - 1024) fuse = false;
+	const size_t smem = tb_hyper_smem_doubles(lay.nrows, lay.nlev, has_base, fuse) * sizeof(double);
 	if (smem > 227 * 1024 - 1024) TB_FAIL(ctx, "column too tall for the fused hyperdiffusion kernel");
 	const dim3 block(TBF_THREADS);
+	const FuseArgs fz0 = fuse_args(ctx);
+	if (fuse) {
+		// this launch also averages the in-patch groups of `out` (fused DSS)
+		ctx->fuse_epoch++;
+		const FuseArgs fz = fuse_args(ctx);
+		if (has_base) {
+			auto kfn = k_hyper_pipe<true, true>;
+#ifndef TB200_EMU
+			TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+			const dim3 grid((unsigned)fused_blocks(ctx, kfn, TBF_THREADS, smem));
+			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
+				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out],
+				elem_list(ctx, 0), fz);
+		} else {
+			auto kfn = k_hyper_pipe<false, true>;
+#ifndef TB200_EMU
+			TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+			const dim3 grid((unsigned)fused_blocks(ctx, kfn, TBF_THREADS, smem));
+			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
+				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out],
+				elem_list(ctx, 0), fz);
+		}
+		ctx->launches++;
+		ctx->writes++;
+		ctx->fuse_done = true;
+		TB_LAUNCH_CHECK(ctx);
+		return 0;
+	}
 	if (has_base) {
-		auto kfn = k_hyper_pipe<true>;
+		auto kfn = k_hyper_pipe<true, false>;
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
@@ -2130,13 +2257,13 @@ static int hyper_fast(
 				(part == 2) ? overlap_reserve() : 0));
 			TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream,
 				lay, ctx->tables, ha,
-				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out], el);
+				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out], el, fz0);
 			ctx->launches++;
 			ctx->writes++;
 		}
 		if (split && split_mark(ctx)) return 1;
 	} else {
-		auto kfn = k_hyper_pipe<false>;
+		auto kfn = k_hyper_pipe<false, false>;
 #ifndef TB200_EMU
 		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
@@ -2149,7 +2276,7 @@ static int hyper_fast(
 				(part == 2) ? overlap_reserve() : 0));
 			TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream,
 				lay, ctx->tables, ha,
-				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out], el);
+				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out], el, fz0);
 			ctx->launches++;
 			ctx->writes++;
 		}
@@ -2186,15 +2313,20 @@ static int h_step_after_subcycle_impl(
 		// followed by a DSS whose exchange overlaps the elements that do not feed it
 		const bool want = overlap_wanted();
 		ctx->want_split = want;
+		ctx->fuse_want = true;
+		ctx->fuse_done = false;
 		int rc = hyper_fast(ctx, in, -1, work, 1.0, 1.0, 1.0, 1.0, false);
 		ctx->want_split = false;
-		if (rc == 0) rc = tb200_dss(ctx, work, all);
+		if (rc == 0) rc = dss_instance(ctx, work, all, ctx->fuse_done);
 		if (split_join(ctx)) return 1;
-		if (rc) return 1;
+		if (rc) { ctx->fuse_want = false; return 1; }
 		ctx->want_split = want;
+		ctx->fuse_done = false;
 		rc = hyper_fast(ctx, work, in, out, -dt, c.nu_scalar, c.nu_div, c.nu_vort, true);
 		ctx->want_split = false;
-		if (rc == 0) rc = tb200_dss(ctx, out, all);
+		ctx->fuse_want = false;
+		if (rc == 0) rc = dss_instance(ctx, out, all, ctx->fuse_done);
+		ctx->fuse_done = false;
 		if (split_join(ctx)) return 1;
 		return rc;
 	} else if (c.hypervis_order == 4) {
@@ -2271,6 +2403,106 @@ static bool member_less(const tb200_ctx * ctx, const Member & x, const Member & 
 	if (px != py) return px < py;
 	if (x.ib != y.ib) return x.ib < y.ib;
 	return x.ia < y.ia;
+}
+
+// Strips of the fused DSS (tb200_fast.cuh) and the averaging groups it leaves to
+// the group kernels.  A strip is a run of beta-consecutive elements of one
+// alpha-row of a patch; strips are handed to the persistent blocks round-robin,
+// in (patch, alpha-row, chunk) order, so that the strip one alpha-row down - whose
+// values the alpha-edge averaging reads - is walked at the same pace by another
+// block.  Fused are the groups whose members are exactly
+//   (e-1)(i,3), e(i,0)              i = 1, 2, e not first in its strip
+//   (e-neb)(3,j), e(0,j)            j = 1, 2, e not in the first alpha-row
+//   (e-neb-1)(3,3), (e-1)(0,3), (e-neb)(3,0), e(0,0)      both of the above
+// with all members local and on one panel (flag bit 1).
+static int build_fuse(tb200_ctx * ctx, const std::vector<int> & members, const std::vector<int> & flags) {
+	const DevLayout & lay = ctx->lay;
+	ctx->fuse_ready = false;
+	if (lay.np != 4 || ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO) return 0;
+	const long long nelem = lay.nelem;
+	const int nn = lay.nn;
+	// strip length: about 8 strips per resident block, whole chunks of a row
+	const long long nblocks = 2ll * ctx->sm_count;
+	long long target = nelem / (8 * nblocks);
+	target = std::max(4ll, std::min(64ll, target));
+	{
+		const char * e = getenv("TB200_STRIP");      // tests: any strip length
+		if (e != 0 && atoi(e) > 0) target = atoi(e);
+	}
+	std::vector<int> first, len, nebs;
+	std::vector<char> fa(nelem, 0), fb(nelem, 0);
+	std::vector<int> enb(nelem, 0);
+	for (size_t p = 0; p < ctx->patches.size(); p++) {
+		const PatchInfo & pi = ctx->patches[p];
+		if (pi.elem0 < 0) continue;
+		const int nchunk = (int)((pi.neb + target - 1) / target);
+		for (int a = 0; a < pi.nea; a++) {
+			for (int c = 0; c < nchunk; c++) {
+				const int b0 = (int)((long long)pi.neb * c / nchunk);
+				const int b1 = (int)((long long)pi.neb * (c + 1) / nchunk);
+				if (b1 <= b0) continue;
+				const long long e0 = pi.elem0 + (long long)a * pi.neb + b0;
+				first.push_back((int)e0);
+				len.push_back(b1 - b0);
+				nebs.push_back((a > 0) ? pi.neb : 0);
+				for (int b = b0; b < b1; b++) {
+					const long long e = pi.elem0 + (long long)a * pi.neb + b;
+					fa[e] = (a > 0) ? 1 : 0;
+					fb[e] = (b > b0) ? 1 : 0;
+					enb[e] = pi.neb;
+				}
+			}
+		}
+	}
+	// groups the kernels average themselves
+	const int ngroups = (int)flags.size();
+	std::vector<int> rem_members, rem_flags;
+	long long nfused = 0;
+	for (int gi = 0; gi < ngroups; gi++) {
+		bool fused = false;
+		if (flags[gi] & 2) {
+			const int * m = &members[(size_t)gi * 4];
+			const int cnt = (m[2] >= 0) ? 4 : 2;
+			int top = 0;
+			for (int q = 1; q < cnt; q++) if (m[q] / nn > m[top] / nn) top = q;
+			const long long e = m[top] / nn;
+			const int n = m[top] % nn, i = n / 4, j = n % 4;
+			auto has = [&](long long ee, int ii, int jj) {
+				const int addr = (int)(ee * nn + ii * 4 + jj);
+				for (int q = 0; q < cnt; q++) if (m[q] == addr) return true;
+				return false;
+			};
+			if (cnt == 2 && j == 0 && (i == 1 || i == 2)) {
+				fused = fb[e] && has(e - 1, i, 3);
+			} else if (cnt == 2 && i == 0 && (j == 1 || j == 2)) {
+				fused = fa[e] && has(e - enb[e], 3, j);
+			} else if (cnt == 4 && i == 0 && j == 0) {
+				fused = fa[e] && fb[e] && has(e - 1, 0, 3) && has(e - enb[e], 3, 0)
+					&& has(e - enb[e] - 1, 3, 3);
+			}
+		}
+		if (fused) {
+			nfused++;
+		} else {
+			for (int q = 0; q < 4; q++) rem_members.push_back(members[(size_t)gi * 4 + q]);
+			rem_flags.push_back(flags[gi]);
+		}
+	}
+	ctx->nstrips = (int)first.size();
+	ctx->nrem = (int)rem_flags.size();
+	if (ctx->nstrips == 0 || nfused == 0) return 0;
+	if (dupload(ctx, &ctx->d_strip_first, first)) return 1;
+	if (dupload(ctx, &ctx->d_strip_len, len)) return 1;
+	if (dupload(ctx, &ctx->d_strip_neb, nebs)) return 1;
+	if (dupload(ctx, &ctx->d_rem_members, rem_members)) return 1;
+	if (dupload(ctx, &ctx->d_rem_flags, rem_flags)) return 1;
+	if (ctx->d_done == 0) {
+		if (dalloc(ctx, &ctx->d_done, (size_t)nelem)) return 1;
+		TB_CHECK(ctx, cudaMemset(ctx->d_done, 0, (size_t)nelem * sizeof(unsigned)));
+	}
+	ctx->fuse_epoch = 0;
+	ctx->fuse_ready = true;
+	return 0;
 }
 
 extern "C" int tb200_build_connectivity(tb200_ctx * ctx) {
@@ -2449,6 +2681,7 @@ extern "C" int tb200_build_connectivity(tb200_ctx * ctx) {
 	}
 	ctx->ngroups = (int)groups.size();
 	ctx->nseam = (int)seam_group.size();
+	if (build_fuse(ctx, members, flags)) return 1;
 	if (dupload(ctx, &ctx->d_members, members)) return 1;
 	if (dupload(ctx, &ctx->d_flags, flags)) return 1;
 	if (dupload(ctx, &ctx->d_seam_group, seam_group)) return 1;

@@ -96,6 +96,17 @@ struct tb200_ctx {
 	unsigned long long peer_seq;
 	size_t buf_rows;                  // rows per slot the buffers are sized for
 
+	// DSS fused into the pipelined kernels (tb200_fast.cuh: FuseArgs)
+	bool fuse_ready;                  // strips and the list of unfused groups are built
+	int nstrips;
+	int * d_strip_first; int * d_strip_len; int * d_strip_neb;
+	unsigned * d_done;                // [nelem] launch epoch per element
+	unsigned fuse_epoch;
+	int nrem;                         // averaging groups the fused kernels leave raw
+	int * d_rem_members; int * d_rem_flags;
+	bool fuse_want;                   // the caller follows the launch with a DSS of `out`
+	bool fuse_done;                   // ... and the launch did the fused part of it
+
 	// implicit column solve
 	int ncols;
 	int * d_col_node; int * d_col_dups;
@@ -154,6 +165,9 @@ struct tb200_ctx {
 		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false),
 		column_inc(0), d_wold(0), offd(4), launches(0), writes(0), uvzero_inst(-1), uvzero_writes(0),
 		carry_full(false), h_info(0),
+		fuse_ready(false), nstrips(0), d_strip_first(0), d_strip_len(0), d_strip_neb(0),
+		d_done(0), fuse_epoch(0), nrem(0), d_rem_members(0), d_rem_flags(0),
+		fuse_want(false), fuse_done(false),
 		fast_state(0), fast_metric_error(0.0), d_colc(0), d_lev(0),
 		geometry3d_uploaded(false)
 	{

@@ -68,7 +68,8 @@
 #define TBF_DDE 27     // [3] DiffDiffREdgeToREdge row k on interfaces k-1, k, k+1
 #define TBF_IEN1 30    // [2] InterpREdgeToNode row k-1 on W[k-1], W[k]
 #define TBF_LW 32
-#define TBF_LWS 34     // row stride of the table in shared memory (bank spread)
+#define TBF_LWK 24     // entries of a row the explicit stage reads (0 .. TBF_CB0 + 2)
+#define TBF_LWS 26     // row stride of those in shared memory (bank spread: 8 rows, 8 bank pairs)
 
 #define TBF_RS 18      // shared-memory row stride (doubles): 16 nodes + 2 pad
 
@@ -728,12 +729,13 @@ struct PipeBase {
 	int nsrc;          // 0: the base is the input instance itself (first stage)
 };
 
-__host__ __device__ inline size_t tb_pipe_smem_doubles(int nrows, int L, int nsrc) {
+__host__ __device__ inline size_t tb_pipe_smem_doubles(int nrows, int L, int nsrc, bool fuse = false) {
 	// in[2], base[nsrc], tiles Wn, KE, EX, FaR, FaP, ZX, Un/Vn[3],
 	// column constants [2], operator windows [L+1]
 	// (one source: its buffer is doubled and fetched one element ahead)
+	// fused DSS: + beta carry [nrows][2] and corner pair averages [nrows]
 	return (size_t)nrows * 16 * (2 + (nsrc == 1 ? 2 : nsrc)) + (size_t)(6 * L + 6) * 16
-		+ 2 * TBF_NC * 16 + (size_t)(L + 1) * TBF_LWS;
+		+ 2 * TBF_NC * 16 + (size_t)(L + 1) * TBF_LWS + (fuse ? (size_t)nrows * 3 : 0);
 }
 
 // cp.async of the rows of thread (kq, i) - its four nodes of every component
@@ -777,15 +779,283 @@ __device__ __forceinline__ void tb_pipe_base2(
 	}
 }
 
+
+///////////////////////////////////////////////////////////////////////////////
+// Direct stiffness summation fused into the pipelined kernels.
+//
+// GridCSGLL::ApplyDSS (GridCSGLL.cpp:435-781) averages the duplicates of every
+// node shared between elements after each explicit stage and each Laplacian
+// application.  As a separate pass it reads and writes the whole state again
+// (every 32-byte sector of a row holds an edge node): 7 sweeps per Strang step.
+// Here the averaging groups whose members are neighbours inside one patch - all
+// but the patch edges, panel seams and rank boundaries - are averaged by the
+// kernel that produces the values, while they are in registers or L2:
+//
+//  * blocks walk *strips* of beta-consecutive elements (element index e, e+1,
+//    ...).  Thread (k, i) owns the nodes (i, 0..3) of a row; the beta-edge it
+//    shares with the previous element of the strip - node (i, 0) here, (i, 3)
+//    there, i = 1, 2 - is averaged in registers against a value carried in
+//    shared memory (the store of (i, 3) is deferred by one element);
+//  * the alpha-edge row i = 0 and the corners are finished TBF_LAG elements later
+//    (tb_fuse_alpha): own raw row and the row i = 3 of the element one
+//    alpha-row down - processed at the same pace by another block, found in L2 -
+//    are averaged pairwise in alpha, corners then in beta against the pair
+//    average kept from the previous element: the association order of the
+//    reference (alpha pass, then beta pass) and of the averaging-group kernels
+//    (tb200_dss.cuh), hence the same bits;
+//  * an element's "done" stamp (launch epoch) is published after its raw values
+//    are stored; consumers acquire it before they read the neighbour row.  A
+//    block only ever waits for elements of strips that were taken up before its
+//    own, all blocks are resident: no deadlock.  The lag keeps the wait off the
+//    critical path: finishing an element right after it is produced makes every
+//    alpha-row trail the one below by the publish-to-observe latency (2-3 us),
+//    74 rows deep in every round of strips (measured: +1.5 ms per launch).
+//
+// Groups that are not fused (strip ends, patch edges, seams, other ranks) stay
+// raw and go through the averaging-group kernels afterwards (a few per cent).
+
+struct FuseArgs {
+	const int * strip_first;   // [nstrips] first element of the strip
+	const int * strip_len;     // [nstrips] number of beta-consecutive elements
+	const int * strip_neb;     // [nstrips] element stride to the alpha-neighbour row in the patch, 0: none
+	int nstrips;
+	unsigned * done;           // [nelem] epoch of the launch that last produced the element
+	unsigned epoch;
+};
+
+#define TBF_LAG 3              // elements between producing a row and finishing its alpha edge
+
+struct FuseElem {
+	long long e;               // element, -1: none
+	int neb;                   // stride to the alpha-neighbour row (fa)
+	int fa;                    // alpha-neighbour row in the same patch
+	int fb;                    // the strip has a previous element
+	int defer;                 // the strip has a next element
+};
+
+__device__ __forceinline__ void tb_flag_publish(unsigned * p, unsigned v) {
+#ifdef TB200_EMU
+	*p = v;
+#else
+	// release at gpu scope, cumulative over the stores of the other threads of the
+	// block (ordered before it by the barrier): MEMBAR.ALL.GPU + STG.STRONG.  No
+	// __threadfence() here: it would also invalidate the L1 (CCTL.IVALL), which
+	// holds the operator windows of the fused kernels.
+#if defined(TBF_PUB_SC)
+	__threadfence();
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#elif defined(TBF_PUB_ALLFENCE)
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#else
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#endif
+#endif
+}
+
+__device__ __forceinline__ void tb_flag_wait(const unsigned * p, unsigned v) {
+#ifdef TB200_EMU
+	// the emulation runs fused launches on one block, strips in order: the
+	// producer has finished
+	if (*p != v) { fprintf(stderr, "tb200 emu: fused DSS read an element that was not produced\n"); abort(); }
+#else
+	// Relaxed polling: ld.acquire.gpu invalidates the whole L1 on every iteration
+	// (LDG.STRONG + CCTL.IVALL).  The data read afterwards is loaded with ld.cg
+	// (L2, never L1) by the same thread behind the loop's exit branch, so no stale
+	// line can be observed and no acquire fence is needed.
+	unsigned x;
+	do {
+		asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+	} while (x != v);
+#endif
+}
+
+// 4 consecutive doubles from L2 (written by another block a moment ago)
+__device__ __forceinline__ void tb_ld4cg(const double * p, double (&v)[4]) {
+#ifdef TB200_EMU
+	v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+#else
+	const double2 a = __ldcg(reinterpret_cast<const double2 *>(p));
+	const double2 b = __ldcg(reinterpret_cast<const double2 *>(p + 2));
+	v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+#endif
+}
+
+// Walk of one block over its strips: strip s = blockIdx.x, + gridDim.x, ...;
+// the strip's description is read once, at its first element.
+struct FuseWalk {
+	int s, t;                  // strip, position inside it
+	int first, len, neb;
+};
+
+__device__ __forceinline__ void tb_walk_load(const FuseArgs & fz, FuseWalk & wk) {
+	wk.first = __ldg(fz.strip_first + wk.s);
+	wk.len = __ldg(fz.strip_len + wk.s);
+	wk.neb = __ldg(fz.strip_neb + wk.s);
+}
+
+__device__ __forceinline__ FuseElem tb_walk_elem(const FuseWalk & wk) {
+	FuseElem fe;
+	fe.e = (long long)wk.first + wk.t;
+	fe.neb = wk.neb;
+	fe.fa = (wk.neb > 0) ? 1 : 0;
+	fe.fb = (wk.t > 0) ? 1 : 0;
+	fe.defer = (wk.t + 1 < wk.len) ? 1 : 0;
+	return fe;
+}
+
+// advance to the next element of the block; false when there is none
+__device__ __forceinline__ bool tb_walk_next(const FuseArgs & fz, FuseWalk & wk, int stride) {
+	if (wk.t + 1 < wk.len) {
+		wk.t++;
+		return true;
+	}
+	wk.s += stride;
+	wk.t = 0;
+	if (wk.s >= fz.nstrips) return false;
+	tb_walk_load(fz, wk);
+	return true;
+}
+
+// Store the node pair (i, 2 jh), (i, 2 jh + 1) of one row of the element at oute.
+template <bool FUSE>
+__device__ __forceinline__ void tb_out2(
+	const FuseElem & fe, double * carry, double * oute, size_t esz,
+	int row, int i, int jh, const double (&v)[2]
+) {
+	double * p = oute + (size_t)row * 16 + 4 * i + 2 * jh;
+	if (FUSE && (i == 1 || i == 2)) {
+		double w[2] = {v[0], v[1]};
+		if (jh == 0) {
+			if (fe.fb) {
+				// members in group order: (a, b-1)(i, 3), then (a, b)(i, 0)
+				w[0] = 0.5 * (carry[row * 2 + (i - 1)] + w[0]);
+				*(p - esz + 3) = w[0];
+			}
+			tb_st2(p, w);
+		} else if (fe.defer) {
+			carry[row * 2 + (i - 1)] = w[1];
+			p[0] = w[0];
+		} else {
+			tb_st2(p, w);
+		}
+		return;
+	}
+	tb_st2(p, v);
+}
+
+// ... the four nodes (i, 0..3)
+template <bool FUSE>
+__device__ __forceinline__ void tb_out4(
+	const FuseElem & fe, double * carry, double * oute, size_t esz,
+	int row, int i, const double (&v)[4]
+) {
+	const double a[2] = {v[0], v[1]};
+	const double b[2] = {v[2], v[3]};
+	tb_out2<FUSE>(fe, carry, oute, esz, row, i, 0, a);
+	tb_out2<FUSE>(fe, carry, oute, esz, row, i, 1, b);
+}
+
+// Alpha-edge row and corners of element pe, TBF_LAG elements after it was
+// produced, in two parts so that the L2 round trip of the loads overlaps the
+// prefetch of the next element: tb_alpha_load (rows tid, tid + 128 of the own
+// raw row i = 0 and of the row i = 3 one alpha-row down), tb_alpha_finish.
+#define TBF_AROWS 2            // rows per thread: nrows <= 2 * TBF_THREADS
+
+struct AlphaRegs {
+	double x[TBF_AROWS][4];
+	double nb[TBF_AROWS][4];
+};
+
+__device__ __forceinline__ unsigned tb_flag_peek(const unsigned * p) {
+#ifdef TB200_EMU
+	return *p;
+#else
+	unsigned x;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory");
+	return x;
+#endif
+}
+
+// `seen`: the neighbour's stamp as peeked one iteration ago (tb_alpha_peek): in
+// the steady state it already carries this launch's epoch and nothing is polled.
+// The stamp of the element one alpha-row down covers the corner's fourth member
+// (e - neb - 1) too: every alpha-row of a patch is cut into the same strips, so
+// that element precedes e - neb in the same strip of the same block.
+__device__ __forceinline__ void tb_alpha_load(
+	const FuseArgs & fz, const FuseElem & pe, const double * out, size_t esz, int nrows,
+	int tid, unsigned seen, AlphaRegs & ar
+) {
+	if (pe.e < 0 || !pe.fa) return;
+	// (skipping this poll when a peek of the stamp one iteration earlier had
+	// already shown the epoch was measured to return stale rows on the B200,
+	// with every publisher-side fence tried: the poll stays)
+	(void)seen;
+	tb_flag_wait(fz.done + (pe.e - pe.neb), fz.epoch);
+#pragma unroll
+	for (int q = 0; q < TBF_AROWS; q++) {
+		const int r = tid + q * TBF_THREADS;
+		if (r < nrows) {
+			tb_ld4cg(out + (size_t)pe.e * esz + (size_t)r * 16, ar.x[q]);
+			tb_ld4cg(out + (size_t)(pe.e - pe.neb) * esz + (size_t)r * 16 + 12, ar.nb[q]);
+		}
+	}
+}
+
+__device__ __forceinline__ unsigned tb_alpha_peek(const FuseArgs & fz, const FuseElem & pe) {
+	if (pe.e < 0 || !pe.fa) return 0u;
+	return tb_flag_peek(fz.done + (pe.e - pe.neb));
+}
+
+__device__ __forceinline__ void tb_alpha_finish(
+	const FuseElem & pe, double * out, size_t esz, int nrows, double * aprev, int tid,
+	const AlphaRegs & ar
+) {
+	if (pe.e < 0 || !pe.fa) return;
+#pragma unroll
+	for (int q = 0; q < TBF_AROWS; q++) {
+		const int r = tid + q * TBF_THREADS;
+		if (r >= nrows) continue;
+		double * own = out + (size_t)pe.e * esz + (size_t)r * 16;               // (0, 0..3)
+		double * nbp = out + (size_t)(pe.e - pe.neb) * esz + (size_t)r * 16 + 12;   // (3, 0..3) one row down
+		double A[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) A[j] = 0.5 * (ar.nb[q][j] + ar.x[q][j]);
+		if (pe.fb) {
+			// corner: pair average of the previous element, then this one
+			const double C = 0.5 * (aprev[r] + A[0]);
+			const double o[2] = {C, A[1]};
+			tb_st2(own, o);
+			tb_st2(nbp, o);
+			*(own - esz + 3) = C;       // (a, b-1)(0, 3)
+			*(nbp - esz + 3) = C;       // (a-1, b-1)(3, 3)
+		} else {
+			own[1] = A[1];
+			nbp[1] = A[1];
+		}
+		own[2] = A[2];
+		nbp[2] = A[2];
+		if (pe.defer) aprev[r] = A[3];
+	}
+}
+
+__device__ __forceinline__ void tb_fuse_alpha(
+	const FuseArgs & fz, const FuseElem & pe, double * out, size_t esz, int nrows,
+	double * aprev, int tid
+) {
+	AlphaRegs ar;
+	tb_alpha_load(fz, pe, out, esz, nrows, tid, 0u, ar);
+	tb_alpha_finish(pe, out, esz, nrows, aprev, tid, ar);
+}
+
 #ifndef TBP_MINBLOCKS
 #define TBP_MINBLOCKS 2
 #endif
 
-template <bool DO_V, int NSRC>
+template <bool DO_V, int NSRC, bool FUSE>
 __global__ void __launch_bounds__(TBF_THREADS, TBP_MINBLOCKS)
 k_nh_stage_pipe(
 	DevLayout lay, DevTables t, DevPhys ph, FastArgs fa,
-	const double * __restrict__ in, PipeBase pb, double * out, ElemList el
+	const double * __restrict__ in, PipeBase pb, double * out, ElemList el, FuseArgs fz
 ) {
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
@@ -811,6 +1081,8 @@ k_nh_stage_pipe(
 	double * sVn = sUn + 3 * NN;
 	double * scc0 = sVn + 3 * NN;            // [2][TBF_NC][16] column constants
 	double * slev = scc0 + 2 * TBF_NC * NN;  // [L+1][TBF_LWS] operator windows
+	double * carry = slev + (size_t)(L + 1) * TBF_LWS;   // FUSE: [nrows][2] beta carry of rows i = 1, 2
+	double * aprev = carry + (size_t)nrows * 2;   // FUSE: [nrows] alpha pair average of node (0, 3)
 
 	const int tid = threadIdx.x;
 	const int kq = tid >> 2;
@@ -824,9 +1096,32 @@ k_nh_stage_pipe(
 		stI[s] = t.st[i * NP + s];
 	}
 
-	long long w = blockIdx.x;          // position in the element list
-	if (w >= el.n) return;
-	long long e = tb_elem(el, w);
+	// element walk: positions blockIdx.x, + gridDim.x, ... of the element list,
+	// or (FUSE) the strips blockIdx.x, + gridDim.x, ..., each element by element
+	long long w = blockIdx.x;          // position in the element list / strip
+	if (w >= (FUSE ? (long long)fz.nstrips : (long long)el.n)) return;
+	FuseWalk wk;
+	wk.s = (int)w; wk.t = 0; wk.first = 0; wk.len = 0; wk.neb = 0;
+	AlphaRegs areg;
+	FuseElem cur, prev;
+	prev.e = -1; prev.neb = 0; prev.fa = 0; prev.fb = 0; prev.defer = 0;
+	// the alpha edges trail the walk by TBF_LAG elements: a second walker over the
+	// same strips; lag_el = its element once `behind` has reached TBF_LAG, lag_nx
+	// the one after it (its stamp is peeked one iteration ahead)
+	FuseWalk wa = wk;
+	FuseElem lag_el = prev, lag_nx = prev;
+	int behind = 0;
+	unsigned seen = 0u;
+	if (FUSE) {
+		tb_walk_load(fz, wk);
+		cur = tb_walk_elem(wk);
+		wa = wk;
+		lag_nx = cur;
+	} else {
+		cur = prev;
+		cur.e = tb_elem(el, w);
+	}
+	long long e = cur.e;
 	{
 		const size_t eb = (size_t)e * esz;
 		for (int q = tid; q < nchunk; q += TBF_THREADS) {
@@ -838,21 +1133,51 @@ k_nh_stage_pipe(
 		for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
 			tb_cp16(scc0 + 2 * q, fa.colc + (size_t)e * TBF_NC * NN + 2 * q);
 		}
-		for (int q = tid; q < (L + 1) * (TBF_LW / 2); q += TBF_THREADS) {
-			const int r = q / (TBF_LW / 2), c = q % (TBF_LW / 2);
-			tb_cp16(slev + (size_t)r * TBF_LWS + 2 * c, fa.lev + 2 * q);
+		for (int q = tid; q < (L + 1) * (TBF_LWK / 2); q += TBF_THREADS) {
+			const int r = q / (TBF_LWK / 2), c = q % (TBF_LWK / 2);
+			tb_cp16(slev + (size_t)r * TBF_LWS + 2 * c, fa.lev + (size_t)r * TBF_LW + 2 * c);
 		}
 		tb_cp_commit();
 	}
 
-	for (int it = 0; w < el.n; it++, w += gridDim.x) {
-		e = tb_elem(el, w);
+	bool valid = true;
+	for (int it = 0; valid; it++) {
+		e = cur.e;
+		// the element after this one
+		FuseElem nxt = cur;
+		bool has_next;
+		if (FUSE) {
+			has_next = tb_walk_next(fz, wk, (int)gridDim.x);
+			if (has_next) nxt = tb_walk_elem(wk);
+		} else {
+			w += gridDim.x;
+			has_next = (w < el.n);
+			if (has_next) nxt.e = tb_elem(el, w);
+		}
 		const int buf = it & 1;
 		const double * inb = inb0 + (size_t)buf * esz;
 		// the data of this element (issued one iteration ago) has landed, and
 		// every thread is done with the previous element
 		tb_cp_wait<0>();
+#if defined(TBF_PUB_ALLFENCE) && !defined(TB200_EMU)
+		if (FUSE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
 		__syncthreads();
+		if (FUSE) {
+			// the previous element's raw values are stored: publish it; finish the
+			// alpha edge and corners of the element produced TBF_LAG iterations ago
+			// (the row one down was published long since)
+			if (tid == 0 && prev.e >= 0) tb_flag_publish(fz.done + prev.e, fz.epoch);
+			if (behind == TBF_LAG) {
+				// lag_nx becomes the element whose alpha edge is finished now
+				lag_el = lag_nx;
+				tb_alpha_load(fz, lag_el, out, esz, nrows, tid, seen, areg);
+				if (tb_walk_next(fz, wa, (int)gridDim.x)) lag_nx = tb_walk_elem(wa);
+				seen = tb_alpha_peek(fz, lag_nx);
+			} else {
+				lag_el.e = -1;
+			}
+		}
 		// stage base.  Every thread fetches exactly the 32 bytes per row it will
 		// combine (its own four nodes).  Two sources: fetched now for this
 		// element, the thread's own cp.async.wait_group is all the
@@ -869,8 +1194,8 @@ k_nh_stage_pipe(
 		}
 		// prefetch the next element of this block into the other buffer
 		{
-			if (w + gridDim.x < el.n) {
-				const long long en = tb_elem(el, w + gridDim.x);
+			if (has_next) {
+				const long long en = nxt.e;
 				const size_t eb = (size_t)en * esz;
 				double * di = inb0 + (size_t)(buf ^ 1) * esz;
 				double * db = bsb0 + (size_t)(buf ^ 1) * esz;
@@ -887,6 +1212,7 @@ k_nh_stage_pipe(
 			}
 			tb_cp_commit();
 		}
+		if (FUSE) tb_alpha_finish(lag_el, out, esz, nrows, aprev, tid, areg);
 
 		const size_t ebase = (size_t)e * esz;
 		const double * cc = scc0 + (size_t)buf * TBF_NC * NN + i * NP;
@@ -900,7 +1226,8 @@ k_nh_stage_pipe(
 			const int km = (kc > 0) ? kc - 1 : 0;
 			const int kp = (kc < L - 1) ? kc + 1 : L - 1;
 			const double * lv = slev + (size_t)kc * TBF_LWS;
-			const double sn = lv[TBF_SN];
+#define LV(q) lv[(q)]
+			const double sn = LV(TBF_SN);
 			const int tp = kc & 1;                         // tile parity
 
 			double cA2[4], cB2[4], cX0[4], cX2[4];
@@ -930,8 +1257,8 @@ k_nh_stage_pipe(
 				tb_ld4(cc + TBF_JAC * NN, cJ);
 				double faR[4], faP[4];
 				const double sn2 = sn * sn;
-				const double cw0 = lv[TBF_CW + 0], cw1 = lv[TBF_CW + 1];
-				const double d0 = lv[TBF_CD + 0], d1 = lv[TBF_CD + 1], d2 = lv[TBF_CD + 2];
+				const double cw0 = LV(TBF_CW + 0), cw1 = LV(TBF_CW + 1);
+				const double d0 = LV(TBF_CD + 0), d1 = LV(TBF_CD + 1), d2 = LV(TBF_CD + 2);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					// InterpolateREdgeToNode(W) (:817-819)
@@ -975,7 +1302,6 @@ k_nh_stage_pipe(
 			}
 			__syncwarp();
 
-			const size_t o4 = (size_t)kc * NN + i * NP;
 #pragma unroll
 			for (int jh = 0; jh < 2; jh++) {
 				double dCovDaUb[2], dCovDaUx[2], dDaP[2], dDaKE[2], dDaRhoFluxA[2], dDaPressureFluxA[2];
@@ -1058,9 +1384,8 @@ k_nh_stage_pipe(
 					bP[q] = bP[q] - dt * cIJ[q] * (aDaPre + aDbPre);
 				}
 				if (active) {
-					const size_t o2 = o4 + 2 * jh;
-					tb_st2(out + ebase + (size_t)rR * NN + o2, bR);
-					tb_st2(out + ebase + (size_t)rP * NN + o2, bP);
+					tb_out2<FUSE>(cur, carry, out + ebase, esz, rR + k, i, jh, bR);
+					tb_out2<FUSE>(cur, carry, out + ebase, esz, rP + k, i, jh, bP);
 					tb_st2(tZX + (size_t)k * NN + ((ch ^ tp) << 1), zx);
 					if (k < 3) {
 						tb_st2(sUn + k * NN + 4 * i + 2 * jh, bU);
@@ -1070,7 +1395,7 @@ k_nh_stage_pipe(
 				if (DO_V) {
 					// upwind penalty on U and V for this node pair
 					// (VerticalDynamicsFEM.cpp:816-828, 998-1023)
-					const double se0 = lv[TBF_SE], se1 = lv[TBF_SE1];
+					const double se0 = LV(TBF_SE), se1 = LV(TBF_SE1);
 					// the windows of the skipped sides (top / bottom level) are zero
 					double u0[2], v0[2], um[2], up[2], vm[2], vp[2], w0[2], wp[2];
 					tb_ld2(inb + (size_t)(rU + kc) * NN + ((ch ^ ((rU + kc) & 1)) << 1), u0);
@@ -1087,29 +1412,29 @@ k_nh_stage_pipe(
 						double au = 0.0, av = 0.0;
 						{
 							double ue = 0.0, ve = 0.0;
-							ue += lv[TBF_CIHI + 0] * um[q]; ue += lv[TBF_CIHI + 1] * u0[q]; ue += lv[TBF_CIHI + 2] * up[q];
-							ve += lv[TBF_CIHI + 0] * vm[q]; ve += lv[TBF_CIHI + 1] * v0[q]; ve += lv[TBF_CIHI + 2] * vp[q];
+							ue += LV(TBF_CIHI + 0) * um[q]; ue += LV(TBF_CIHI + 1) * u0[q]; ue += LV(TBF_CIHI + 2) * up[q];
+							ve += LV(TBF_CIHI + 0) * vm[q]; ve += LV(TBF_CIHI + 1) * v0[q]; ve += LV(TBF_CIHI + 2) * vp[q];
 							const double c0 = se1 * cA2[j], c1 = se1 * cB2[j];
 							const double c2 = cX0[j] + (se1 * se1) * cX2[j];
 							const double xd = c0 * ue + c1 * ve + c2 * wp[q];
 							const double wgt = dt * fabs(xd);
 							double pu = 0.0, pv = 0.0;
-							pu += lv[TBF_CPL + 0] * um[q]; pu += lv[TBF_CPL + 1] * u0[q]; pu += lv[TBF_CPL + 2] * up[q];
-							pv += lv[TBF_CPL + 0] * vm[q]; pv += lv[TBF_CPL + 1] * v0[q]; pv += lv[TBF_CPL + 2] * vp[q];
+							pu += LV(TBF_CPL + 0) * um[q]; pu += LV(TBF_CPL + 1) * u0[q]; pu += LV(TBF_CPL + 2) * up[q];
+							pv += LV(TBF_CPL + 0) * vm[q]; pv += LV(TBF_CPL + 1) * v0[q]; pv += LV(TBF_CPL + 2) * vp[q];
 							au += pu * wgt;
 							av += pv * wgt;
 						}
 						{
 							double ue = 0.0, ve = 0.0;
-							ue += lv[TBF_CILO + 0] * um[q]; ue += lv[TBF_CILO + 1] * u0[q]; ue += lv[TBF_CILO + 2] * up[q];
-							ve += lv[TBF_CILO + 0] * vm[q]; ve += lv[TBF_CILO + 1] * v0[q]; ve += lv[TBF_CILO + 2] * vp[q];
+							ue += LV(TBF_CILO + 0) * um[q]; ue += LV(TBF_CILO + 1) * u0[q]; ue += LV(TBF_CILO + 2) * up[q];
+							ve += LV(TBF_CILO + 0) * vm[q]; ve += LV(TBF_CILO + 1) * v0[q]; ve += LV(TBF_CILO + 2) * vp[q];
 							const double c0 = se0 * cA2[j], c1 = se0 * cB2[j];
 							const double c2 = cX0[j] + (se0 * se0) * cX2[j];
 							const double xd = c0 * ue + c1 * ve + c2 * w0[q];
 							const double wgt = dt * fabs(xd);
 							double pu = 0.0, pv = 0.0;
-							pu += lv[TBF_CPR + 0] * um[q]; pu += lv[TBF_CPR + 1] * u0[q]; pu += lv[TBF_CPR + 2] * up[q];
-							pv += lv[TBF_CPR + 0] * vm[q]; pv += lv[TBF_CPR + 1] * v0[q]; pv += lv[TBF_CPR + 2] * vp[q];
+							pu += LV(TBF_CPR + 0) * um[q]; pu += LV(TBF_CPR + 1) * u0[q]; pu += LV(TBF_CPR + 2) * up[q];
+							pv += LV(TBF_CPR + 0) * vm[q]; pv += LV(TBF_CPR + 1) * v0[q]; pv += LV(TBF_CPR + 2) * vp[q];
 							au += pu * wgt;
 							av += pv * wgt;
 						}
@@ -1118,9 +1443,8 @@ k_nh_stage_pipe(
 					}
 				}
 				if (active) {
-					const size_t o2 = o4 + 2 * jh;
-					tb_st2(out + ebase + (size_t)rU * NN + o2, bU);
-					tb_st2(out + ebase + (size_t)rV * NN + o2, bV);
+					tb_out2<FUSE>(cur, carry, out + ebase, esz, rU + k, i, jh, bU);
+					tb_out2<FUSE>(cur, carry, out + ebase, esz, rV + k, i, jh, bV);
 				}
 			}
 		}
@@ -1128,11 +1452,10 @@ k_nh_stage_pipe(
 
 		// ---- vertical velocity on interfaces (:1612-1660) --------------------------
 		for (int k = kq; k <= L; k += TBF_KB) {
-			const size_t o4 = (size_t)k * NN + i * NP;
 			const double * lv = slev + (size_t)k * TBF_LWS;
 			double bW[4];
 			if (k == 0) {
-				const double se0 = lv[TBF_SE];
+				const double se0 = LV(TBF_SE);
 				double a[4], b[4], c[4], a2[4], b2[4], c2[4];
 				double cA2[4], cB2[4], cX0[4], cX2[4];
 				tb_ld4(cc + TBF_A2 * NN, cA2);
@@ -1146,8 +1469,8 @@ k_nh_stage_pipe(
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					double dU0 = 0.0, dV0 = 0.0;
-					dU0 += lv[TBF_CB0 + 0] * a[j]; dU0 += lv[TBF_CB0 + 1] * b[j]; dU0 += lv[TBF_CB0 + 2] * c[j];
-					dV0 += lv[TBF_CB0 + 0] * a2[j]; dV0 += lv[TBF_CB0 + 1] * b2[j]; dV0 += lv[TBF_CB0 + 2] * c2[j];
+					dU0 += LV(TBF_CB0 + 0) * a[j]; dU0 += LV(TBF_CB0 + 1) * b[j]; dU0 += LV(TBF_CB0 + 2) * c[j];
+					dV0 += LV(TBF_CB0 + 0) * a2[j]; dV0 += LV(TBF_CB0 + 1) * b2[j]; dV0 += LV(TBF_CB0 + 2) * c2[j];
 					const double c0 = se0 * cA2[j], c1 = se0 * cB2[j];
 					const double cx2 = cX0[j] + (se0 * se0) * cX2[j];
 					bW[j] = -(c0 * dU0 + c1 * dV0) / cx2;
@@ -1167,13 +1490,28 @@ k_nh_stage_pipe(
 #pragma unroll
 					for (int j = 0; j < 4; j++) {
 						double x = 0.0;
-						x += lv[TBF_CILO + 0] * zm[j];
-						x += lv[TBF_CILO + 1] * z0[j];
+						x += LV(TBF_CILO + 0) * zm[j];
+						x += LV(TBF_CILO + 1) * z0[j];
 						bW[j] += dt * x;
 					}
 				}
 			}
-			tb_st4(out + ebase + (size_t)rW * NN + o4, bW);
+			tb_out4<FUSE>(cur, carry, out + ebase, esz, rW + k, i, bW);
+		}
+#undef LV
+		if (FUSE && behind < TBF_LAG) behind++;
+		prev = cur;
+		cur = nxt;
+		valid = has_next;
+	}
+	if (FUSE) {
+		// the last element of this block, then the alpha edges still pending
+		// (oldest first: the corner pair average passes from one to the next)
+		__syncthreads();
+		if (tid == 0 && prev.e >= 0) tb_flag_publish(fz.done + prev.e, fz.epoch);
+		for (int q = 0; q < behind; q++) {
+			tb_fuse_alpha(fz, lag_nx, out, esz, nrows, aprev, tid);
+			if (tb_walk_next(fz, wa, (int)gridDim.x)) lag_nx = tb_walk_elem(wa);
 		}
 	}
 }
@@ -1203,9 +1541,11 @@ struct HyperFastArgs {
 	int xz;
 };
 
-__host__ __device__ inline size_t tb_hyper_smem_doubles(int nrows, int L, bool has_base) {
+__host__ __device__ inline size_t tb_hyper_smem_doubles(int nrows, int L, bool has_base, bool fuse = false) {
 	// fld[2] (+ base[2]), tiles GaP, GaR, JUa, Div, Curl [L], GaW [L+1], column constants [2]
-	return (size_t)nrows * 16 * (has_base ? 4 : 2) + (size_t)(6 * L + 1) * 16 + 2 * TBF_NC * 16;
+	// (+ fused DSS: beta carry [nrows][2], corner pair averages [nrows])
+	return (size_t)nrows * 16 * (has_base ? 4 : 2) + (size_t)(6 * L + 1) * 16 + 2 * TBF_NC * 16
+		+ (fuse ? (size_t)nrows * 3 : 0);
 }
 
 // beta-direction sum over my own row: o = sum_s x[s] * c[s*4 + j] (c = dx) or
@@ -1225,11 +1565,11 @@ __device__ __forceinline__ void tb_cross_sum4s(
 	o[0] = lo[0]; o[1] = lo[1]; o[2] = hi[0]; o[3] = hi[1];
 }
 
-template <bool HAS_BASE>
+template <bool HAS_BASE, bool FUSE>
 __global__ void __launch_bounds__(TBF_THREADS, 2)
 k_hyper_pipe(
 	DevLayout lay, DevTables t, HyperFastArgs ha,
-	const double * __restrict__ fld, const double * base, double * out, ElemList el
+	const double * __restrict__ fld, const double * base, double * out, ElemList el, FuseArgs fz
 ) {
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
@@ -1248,6 +1588,8 @@ k_hyper_pipe(
 	double * tCL = tDV + (size_t)L * NN;
 	double * tGW = tCL + (size_t)L * NN;         // [L+1]
 	double * scc0 = tGW + (size_t)(L + 1) * NN;  // [2][TBF_NC][16]
+	double * carry = scc0 + 2 * TBF_NC * NN;     // FUSE: [nrows][2]
+	double * aprev = carry + (size_t)nrows * 2;  // FUSE: [nrows]
 
 	const int tid = threadIdx.x;
 	const int kq = tid >> 2;
@@ -1261,9 +1603,30 @@ k_hyper_pipe(
 		stI[s] = t.st[i * NP + s];
 	}
 
-	long long w = blockIdx.x;          // position in the element list
-	if (w >= el.n) return;
-	long long e = tb_elem(el, w);
+	long long w = blockIdx.x;          // position in the element list / strip
+	if (w >= (FUSE ? (long long)fz.nstrips : (long long)el.n)) return;
+	FuseWalk wk;
+	wk.s = (int)w; wk.t = 0; wk.first = 0; wk.len = 0; wk.neb = 0;
+	AlphaRegs areg;
+	FuseElem cur, prev;
+	prev.e = -1; prev.neb = 0; prev.fa = 0; prev.fb = 0; prev.defer = 0;
+	// the alpha edges trail the walk by TBF_LAG elements: a second walker over the
+	// same strips; lag_el = its element once `behind` has reached TBF_LAG, lag_nx
+	// the one after it (its stamp is peeked one iteration ahead)
+	FuseWalk wa = wk;
+	FuseElem lag_el = prev, lag_nx = prev;
+	int behind = 0;
+	unsigned seen = 0u;
+	if (FUSE) {
+		tb_walk_load(fz, wk);
+		cur = tb_walk_elem(wk);
+		wa = wk;
+		lag_nx = cur;
+	} else {
+		cur = prev;
+		cur.e = tb_elem(el, w);
+	}
+	long long e = cur.e;
 	{
 		const size_t eb = (size_t)e * esz;
 		for (int q = tid; q < nchunk; q += TBF_THREADS) {
@@ -1278,16 +1641,45 @@ k_hyper_pipe(
 		tb_cp_commit();
 	}
 
-	for (int it = 0; w < el.n; it++, w += gridDim.x) {
-		e = tb_elem(el, w);
+	bool valid = true;
+	for (int it = 0; valid; it++) {
+		e = cur.e;
+		FuseElem nxt = cur;
+		bool has_next;
+		if (FUSE) {
+			has_next = tb_walk_next(fz, wk, (int)gridDim.x);
+			if (has_next) nxt = tb_walk_elem(wk);
+		} else {
+			w += gridDim.x;
+			has_next = (w < el.n);
+			if (has_next) nxt.e = tb_elem(el, w);
+		}
 		const int buf = it & 1;
 		const double * fb = fb0 + (size_t)buf * esz;
 		const double * bb = bb0 + (size_t)buf * esz;
 		tb_cp_wait<0>();
+#if defined(TBF_PUB_ALLFENCE) && !defined(TB200_EMU)
+		if (FUSE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
 		__syncthreads();
+		if (FUSE) {
+			// the previous element's raw values are stored: publish it; finish the
+			// alpha edge and corners of the element produced TBF_LAG iterations ago
+			// (the row one down was published long since)
+			if (tid == 0 && prev.e >= 0) tb_flag_publish(fz.done + prev.e, fz.epoch);
+			if (behind == TBF_LAG) {
+				// lag_nx becomes the element whose alpha edge is finished now
+				lag_el = lag_nx;
+				tb_alpha_load(fz, lag_el, out, esz, nrows, tid, seen, areg);
+				if (tb_walk_next(fz, wa, (int)gridDim.x)) lag_nx = tb_walk_elem(wa);
+				seen = tb_alpha_peek(fz, lag_nx);
+			} else {
+				lag_el.e = -1;
+			}
+		}
 		{
-			if (w + gridDim.x < el.n) {
-				const long long en = tb_elem(el, w + gridDim.x);
+			if (has_next) {
+				const long long en = nxt.e;
 				const size_t eb = (size_t)en * esz;
 				double * df = fb0 + (size_t)(buf ^ 1) * esz;
 				double * db = bb0 + (size_t)(buf ^ 1) * esz;
@@ -1304,6 +1696,7 @@ k_hyper_pipe(
 			}
 			tb_cp_commit();
 		}
+		if (FUSE) tb_alpha_finish(lag_el, out, esz, nrows, aprev, tid, areg);
 
 		const size_t ebase = (size_t)e * esz;
 		const double * cc = scc0 + (size_t)buf * TBF_NC * NN + i * NP;
@@ -1386,7 +1779,6 @@ k_hyper_pipe(
 			// ---- scalar Laplacians (:2126-2165) ----------------------------------------
 			{
 				double ua[4], o[4];
-				const size_t o4 = (size_t)i * NP;
 				tb_cross_sum4s(tGP + (size_t)kc * NN, tp, stI, ua);
 				if (HAS_BASE) tb_ld4s(bb + (size_t)(rP + kc) * NN, (rP + kc) & 1, i, o);
 #pragma unroll
@@ -1396,7 +1788,7 @@ k_hyper_pipe(
 					const double b = HAS_BASE ? o[j] : 0.0;
 					o[j] = b - ha.dt * cIJ[j] * dNuS * (dUpdateA + dUpdateB);
 				}
-				if (lact) tb_st4(out + ebase + (size_t)(rP + k) * NN + o4, o);
+				if (lact) tb_out4<FUSE>(cur, carry, out + ebase, esz, rP + k, i, o);
 				tb_cross_sum4s(tGR + (size_t)kc * NN, tp, stI, ua);
 				if (HAS_BASE) tb_ld4s(bb + (size_t)(rR + kc) * NN, (rR + kc) & 1, i, o);
 #pragma unroll
@@ -1406,7 +1798,7 @@ k_hyper_pipe(
 					const double b = HAS_BASE ? o[j] : 0.0;
 					o[j] = b - ha.dt * cIJ[j] * dNuS * (dUpdateA + dUpdateB);
 				}
-				if (lact) tb_st4(out + ebase + (size_t)(rR + k) * NN + o4, o);
+				if (lact) tb_out4<FUSE>(cur, carry, out + ebase, esz, rR + k, i, o);
 				tb_cross_sum4s(tGW + (size_t)kw * NN, tpw, stI, ua);
 				if (HAS_BASE) tb_ld4s(bb + (size_t)(rW + kw) * NN, (rW + kw) & 1, i, o);
 #pragma unroll
@@ -1416,7 +1808,7 @@ k_hyper_pipe(
 					const double b = HAS_BASE ? o[j] : 0.0;
 					o[j] = b - ha.dt * cIJ[j] * dNuS * (dUpdateA + dUpdateB);
 				}
-				if (wact) tb_st4(out + ebase + (size_t)(rW + k) * NN + o4, o);
+				if (wact) tb_out4<FUSE>(cur, carry, out + ebase, esz, rW + k, i, o);
 			}
 
 			// ---- curl and divergence (GridPatchCSGLL.cpp:1262-1299) --------------------
@@ -1469,11 +1861,24 @@ k_hyper_pipe(
 					oV[j] = ha.xz ? bv : (bv - ha.dt * dUpdateUb);
 				}
 				if (lact) {
-					const size_t o4 = (size_t)i * NP;
-					tb_st4(out + ebase + (size_t)(rU + k) * NN + o4, oU);
-					tb_st4(out + ebase + (size_t)(rV + k) * NN + o4, oV);
+					tb_out4<FUSE>(cur, carry, out + ebase, esz, rU + k, i, oU);
+					tb_out4<FUSE>(cur, carry, out + ebase, esz, rV + k, i, oV);
 				}
 			}
+		}
+		if (FUSE && behind < TBF_LAG) behind++;
+		prev = cur;
+		cur = nxt;
+		valid = has_next;
+	}
+	if (FUSE) {
+		// the last element of this block, then the alpha edges still pending
+		// (oldest first: the corner pair average passes from one to the next)
+		__syncthreads();
+		if (tid == 0 && prev.e >= 0) tb_flag_publish(fz.done + prev.e, fz.epoch);
+		for (int q = 0; q < behind; q++) {
+			tb_fuse_alpha(fz, lag_nx, out, esz, nrows, aprev, tid);
+			if (tb_walk_next(fz, wa, (int)gridDim.x)) lag_nx = tb_walk_elem(wa);
 		}
 	}
 }

@@ -83,6 +83,11 @@ class DeviceContext:
     def column_count(self):
         return int(self.lib.tb200_column_count(self._h))
 
+    @property
+    def fused_group_count(self):
+        """Averaging groups the pipelined kernels average themselves (fused DSS)."""
+        return int(self.lib.tb200_fused_group_count(self._h))
+
     # -- grid -----------------------------------------------------------------
     def set_exchange(self, rank, nranks, fn):
         cb = _lib.EXCHANGE_FN(fn) if fn is not None else _lib.EXCHANGE_FN()
@@ -230,6 +235,14 @@ class DeviceContext:
 
     def v_step_implicit(self, i_in, i_out, dt):
         self._ck(self.lib.tb200_v_step_implicit(self._h, i_in, i_out, dt))
+
+    def hv_step_explicit_combine_dss(self, coeff, i_in, i_out, dt):
+        """The explicit substage of every time scheme: combination, both explicit
+        plugins and PostProcessSubstage(out) (the DSS fused into the stage kernel
+        where the groups allow)."""
+        c = np.ascontiguousarray(coeff, dtype=np.float64)
+        self._ck(self.lib.tb200_hv_step_explicit_combine_dss(self._h, _ptr(c), len(c),
+                                                             i_in, i_out, dt))
 
     def dss(self, inst, mask=DATA_ALL):
         self._ck(self.lib.tb200_dss(self._h, inst, mask))

@@ -41,6 +41,31 @@ def test_config3_jw_ne30_l30_checksums(cuda_library):
     assert abs(cs[0] - CONFIG3["U"]) <= 10.0 * sp["rel_spread"][0] * abs(CONFIG3["U"]), (cs, sp)
     model.ctx.close()
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("npatch", [6, 24])
+def test_fused_dss_same_bits_ne30(cuda_library, monkeypatch, npatch):
+    """Config 3 on the GPU with the DSS fused into the stage / hyperdiffusion
+    kernels (296 resident blocks walking strips concurrently, flags between them)
+    against the separate DSS pass: the same bits after three steps."""
+    res = []
+    for fused in (False, True):
+        monkeypatch.setenv("TB200_DSS_FUSED", "1" if fused else "0")
+        grid = G.GridCSGLL(30, 30, npatch=npatch, ztop=30000.0)
+        model = Model(grid, TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"),
+                      timescheme="strang", dt=200.0, library=cuda_library)
+        model.device_setup = True
+        model.initialize()
+        assert model.ctx.fast_path()[0]
+        assert model.ctx.fused_group_count > 0
+        model.step(3)
+        res.append((model.download_state(0), model.download_state(1)))
+        model.ctx.close()
+    for inst in (0, 1):
+        for idx in res[0][inst]:
+            for loc in (0, 1):
+                assert np.array_equal(res[0][inst][idx][loc], res[1][inst][idx][loc])
+
+
 # SWTest2 --resolution 20 --order 4 --output_none (dt = 200 s, 1 step, strang,
 # hypervis 4, nu = 1e15): checksums after the step
 CONFIG1 = dict(U=7.114413176809416e+22, V=1.651200000000000e+06, H=1.205365996298435e+18)

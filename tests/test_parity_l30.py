@@ -185,3 +185,61 @@ def test_lean_geometry_l30(library):
     for n in res[0]:
         for loc in (0, 1):
             assert np.array_equal(res[0][n][loc], res[1][n][loc])
+
+
+@pytest.mark.parametrize("name,strip", [("jw_ne2_l30_strang", None), ("jw_ne4_l30_p24", None),
+                                        ("jw_ne4_l30_p24", "1"), ("jw_ne2_l6_strang", None)])
+def test_fused_dss_same_bits(library, monkeypatch, name, strip):
+    """DSS fused into the stage and hyperdiffusion kernels (in-patch averaging
+    groups averaged while the values are in registers / L2, the rest by the
+    group kernels) against the separate DSS pass: bit-identical state after two
+    Strang steps, for any strip partition."""
+    d = cases.load_case(name)
+    res = []
+    for fused in (False, True):
+        monkeypatch.setenv("TB200_DSS_FUSED", "1" if fused else "0")
+        if strip is not None:
+            monkeypatch.setenv("TB200_STRIP", strip)
+        ctx = dumpctx.context_from_dump(d, library=library)
+        assert ctx.fast_path()[0]
+        assert ctx.fused_group_count > 0
+        dumpctx.upload_tag(ctx, d, "ic")
+        for m in range(1, ctx.cfg.ninstances):
+            ctx.copy(0, m)
+        ctx.step("strang", True, False, 200.0)
+        ctx.step("strang", False, False, 200.0)
+        ctx.check_errors()
+        res.append([dumpctx.download(ctx, d, m) for m in (0, 1, 2, 4)])
+        ctx.close()
+    for a, b in zip(*res):
+        for n in a:
+            for loc in (0, 1):
+                assert np.array_equal(a[n][loc], b[n][loc])
+
+
+@pytest.mark.parametrize("ne,npatch,strip", [(6, 6, None), (6, 6, "4"), (4, 24, "3")])
+def test_fused_dss_same_bits_larger_patches(library, monkeypatch, ne, npatch, strip):
+    """The same on patches of 6 x 6 elements (every combination of first / inner /
+    last element of a strip and of an alpha-row) through the Python driver: no
+    reference data needed, the fused and the separate DSS must agree bit for bit."""
+    from tempestmodel_b200 import grid as G
+    from tempestmodel_b200 import testcases as TC
+    from tempestmodel_b200.model import Model
+    res = []
+    for fused in (False, True):
+        monkeypatch.setenv("TB200_DSS_FUSED", "1" if fused else "0")
+        if strip is not None:
+            monkeypatch.setenv("TB200_STRIP", strip)
+        grid = G.GridCSGLL(ne, 7, npatch=npatch, ztop=30000.0)
+        model = Model(grid, TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"),
+                      timescheme="strang", dt=300.0, library=library)
+        model.initialize()
+        assert model.ctx.fast_path()[0]
+        assert model.ctx.fused_group_count > 0
+        model.step(2)
+        res.append((model.download_state(0), model.download_state(1), model.checksum(0)))
+        model.ctx.close()
+    for inst in (0, 1):
+        for idx in res[0][inst]:
+            for loc in (0, 1):
+                assert np.array_equal(res[0][inst][idx][loc], res[1][inst][idx][loc])

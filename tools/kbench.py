@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--timescheme", default="strang")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--only", default=None, help="run the operations whose name contains this")
     ap.add_argument("--tracers", type=int, default=0,
                     help="carry N analytic tracers (general kernels; S = 5 + N)")
     args = ap.parse_args()
@@ -83,6 +84,9 @@ def main():
         ("stage(copy0)+HV 3S", lambda: ctx.hv_step_explicit_combine([1.0, 0.0, 0.0, 0.0], 2, 3, 1e-6), 3),
         ("stage(2src)+HV 4S", lambda: ctx.hv_step_explicit_combine([-0.25, 1.25, 0.0, 0.0, 0.0], 2, 4, 1e-6), 4),
         ("dss 1.5S", lambda: ctx.dss(3), 1.5),
+        ("stage 2S + dss (substage)", lambda: ctx.hv_step_explicit_combine_dss([0.0, 0.0, 1.0, 0.0], 2, 3, 1e-6), 3.5),
+        ("stage 3S + dss (substage)", lambda: ctx.hv_step_explicit_combine_dss([1.0, 0.0, 0.0, 0.0], 2, 3, 1e-6), 4.5),
+        ("stage 4S + dss (substage)", lambda: ctx.hv_step_explicit_combine_dss([-0.25, 1.25, 0.0, 0.0, 0.0], 2, 4, 1e-6), 5.5),
         ("implicit 2S", lambda: ctx.v_step_implicit(3, 3, dt * 1e-3), 2),
         ("hyperdiffusion 8S", lambda: ctx.h_step_after_subcycle(4, 1, 2, dt * 1e-3), 8),
         ("lincomb(2src) 3S", lambda: ctx.lincomb([0.5, 0.5], 1), 3),
@@ -93,6 +97,8 @@ def main():
     print("fast path:", fast, flush=True)
     out = {"tag": args.tag, "ne": ne, "L": L, "setup_s": setup, "fast_path": fast, "ops": {}}
     for name, fn, s in ops:
+        if args.only is not None and args.only not in name:
+            continue
         ms = timeit(fn)
         gbs = nodes * s * S / (ms * 1e-3) / 1e9
         out["ops"][name] = {"ms": round(ms, 4), "alg_GBs": round(gbs, 1)}
