@@ -22,6 +22,7 @@
 #define TEMPEST_B200_H
 
 #include <stdint.h>
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -226,6 +227,24 @@ int tb200_download_state(tb200_ctx * ctx, int patch_index, int inst,
                          double * node, double * redge, double * tracers,
                          int fill_derived);
 
+/* The same without waiting for the bus: the copies and layout conversions of
+ * consecutive calls overlap (two staging buffers, a copy stream).  The host
+ * arrays of an upload may be changed, and those of a download read, after
+ * tb200_transfer_sync.  Host memory should be pinned (tb200_host_register)
+ * for the copies to run asynchronously. */
+int tb200_upload_state_async(tb200_ctx * ctx, int patch_index, int inst,
+                             const double * node, const double * redge,
+                             const double * tracers);
+int tb200_download_state_async(tb200_ctx * ctx, int patch_index, int inst,
+                               double * node, double * redge, double * tracers,
+                               int fill_derived);
+int tb200_transfer_sync(tb200_ctx * ctx);
+/* Pin / unpin the host memory state arrays live in: the reference's
+ * DataContainer blocks (src/base/DataContainer.cpp:77-147; one contiguous
+ * allocation per container, GridPatch.cpp:287-480). */
+int tb200_host_register(tb200_ctx * ctx, void * ptr, size_t bytes);
+int tb200_host_unregister(tb200_ctx * ctx, void * ptr);
+
 /* ---- Grid::CopyData / LinearCombineData / ZeroData (Grid.cpp:1585-1632,
  *      GridPatch.cpp:1402-1553) ------------------------------------------- */
 int tb200_copy(tb200_ctx * ctx, int src, int dst, int data_mask);
@@ -353,6 +372,22 @@ int tb200_peer_detach(tb200_ctx * ctx);
 /* Nodes sent to / received from each rank per exchange (after
  * tb200_build_connectivity); arrays of nranks entries. */
 int tb200_exchange_counts(tb200_ctx * ctx, int64_t * send_nodes, int64_t * recv_nodes);
+
+/* ---- timing hooks (FunctionTimer groups) ----------------------- */
+/* The reference times its plugins with FunctionTimer groups
+ * ("HorizontalStepNonhydrostaticPrimitive", HorizontalDynamicsFEM.cpp:708;
+ * "StepAfterSubCycle", :2645; "VerticalStepExplicit", VerticalDynamicsFEM.cpp:630;
+ * "VerticalStepImplicit", :1237; "Communicate", Grid.cpp:636) and prints their
+ * averages at the end of a run (Model.cpp:640-688).  With hooks set, every
+ * entry point that stands for one of those groups calls begin(user, group)
+ * when it starts and - after waiting for its device work - end(user, group),
+ * also inside tb200_step; the C++ shells open and close the reference's own
+ * FunctionTimer in them.  The fused explicit stage (horizontal + vertical
+ * explicit in one kernel) reports under the horizontal group.  NULL hooks
+ * (default): no synchronisation, no calls. */
+typedef void (*tb200_timing_fn)(void * user, const char * group);
+int tb200_set_timing_hooks(tb200_ctx * ctx, tb200_timing_fn begin, tb200_timing_fn end,
+                           void * user);
 
 /* ---- introspection for tests and the bench -------------------------------- */
 /* Number of kernels this context has launched since creation. */

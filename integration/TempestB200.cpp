@@ -18,6 +18,7 @@
 #include <map>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 ///////////////////////////////////////////////////////////////////////////////
 
@@ -324,7 +325,48 @@ void B200Bridge::Initialize() {
 			m_pCtx, &(pGrid->GetREtaLevels()[0]), &(pGrid->GetREtaInterfaces()[0])));
 	}
 	Check(tb200_build_connectivity(m_pCtx));
+
+	// Pin the state containers (one contiguous block each, DataContainer.cpp:77-147):
+	// bus copies then run asynchronously at full rate
+	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+		GridPatch * pPatch = pGrid->GetActivePatch(n);
+		DataContainer * apDC[2] = {
+			&(pPatch->GetDataContainerActiveState()),
+			&(pPatch->GetDataContainerBufferState())};
+		for (int q = 0; q < 2; q++) {
+			if (apDC[q]->GetTotalByteSize() == 0) {
+				continue;
+			}
+			if (tb200_host_register(
+					m_pCtx, apDC[q]->GetPointer(), apDC[q]->GetTotalByteSize()) == 0
+			) {
+				m_vecPinned.push_back(apDC[q]->GetPointer());
+			}
+		}
+	}
+
+	// FunctionTimer groups of the reference around the device calls
+	const char * szTiming = getenv("TB200_TIMING");
+	if ((szTiming != NULL) && (szTiming[0] == '1')) {
+		Check(tb200_set_timing_hooks(
+			m_pCtx, &B200Bridge::TimerBegin, &B200Bridge::TimerEnd, this));
+	}
 	m_fInitialized = true;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+
+void B200Bridge::TimerBegin(void * pUser, const char * szGroup) {
+	B200Bridge * pBridge = static_cast<B200Bridge *>(pUser);
+	pBridge->m_vecTimers.push_back(new FunctionTimer(szGroup));
+}
+
+void B200Bridge::TimerEnd(void * pUser, const char * szGroup) {
+	B200Bridge * pBridge = static_cast<B200Bridge *>(pUser);
+	if (!pBridge->m_vecTimers.empty()) {
+		delete pBridge->m_vecTimers.back();
+		pBridge->m_vecTimers.pop_back();
+	}
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -334,12 +376,13 @@ void B200Bridge::Upload(int iInstance) {
 	const bool fTracers = (m_model.GetEquationSet().GetTracers() != 0);
 	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
 		GridPatch * pPatch = pGrid->GetActivePatch(n);
-		Check(tb200_upload_state(
+		Check(tb200_upload_state_async(
 			m_pCtx, pPatch->GetPatchIndex(), iInstance,
 			&(pPatch->GetDataState(iInstance, DataLocation_Node)[0][0][0][0]),
 			&(pPatch->GetDataState(iInstance, DataLocation_REdge)[0][0][0][0]),
 			fTracers ? &(pPatch->GetDataTracers(iInstance)[0][0][0][0]) : NULL));
 	}
+	Check(tb200_transfer_sync(m_pCtx));
 }
 
 void B200Bridge::Download(int iInstance) {
@@ -347,13 +390,14 @@ void B200Bridge::Download(int iInstance) {
 	const bool fTracers = (m_model.GetEquationSet().GetTracers() != 0);
 	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
 		GridPatch * pPatch = pGrid->GetActivePatch(n);
-		Check(tb200_download_state(
+		Check(tb200_download_state_async(
 			m_pCtx, pPatch->GetPatchIndex(), iInstance,
 			&(pPatch->GetDataState(iInstance, DataLocation_Node)[0][0][0][0]),
 			&(pPatch->GetDataState(iInstance, DataLocation_REdge)[0][0][0][0]),
 			fTracers ? &(pPatch->GetDataTracers(iInstance)[0][0][0][0]) : NULL,
 			1));
 	}
+	Check(tb200_transfer_sync(m_pCtx));
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -468,7 +512,9 @@ void VerticalDynamicsB200::FilterNegativeTracers(int iDataUpdate) {
 
 TimestepSchemeB200::TimestepSchemeB200(Model & model, int iScheme) :
 	TimestepScheme(model),
-	m_iScheme(iScheme)
+	m_iScheme(iScheme),
+	m_fLazy(false),
+	m_fDeviceCurrent(false)
 {
 	if (tb200_scheme_instances(iScheme) < 0) {
 		_EXCEPTIONT("tempest_b200: time scheme not implemented");
@@ -495,10 +541,53 @@ void TimestepSchemeB200::Step(
 	// processes, Model.cpp:477-481; outputs, :484-509): it is the only
 	// instance that crosses the bus.  The carry-over instance of the Strang
 	// scheme stays on the device.
-	b.Upload(0);
+	if (!m_fLazy || !m_fDeviceCurrent) {
+		b.Upload(0);
+	}
 	b.Check(tb200_step(b.Ctx(), m_iScheme, fFirstStep ? 1 : 0, fLastStep ? 1 : 0, dDeltaT));
-	b.Check(tb200_check_errors(b.Ctx()));
-	b.Download(0);
+	m_fDeviceCurrent = true;
+
+	// Who touches instance 0 on the host before the next step?  Model::Go asks
+	// its workflow processes and output managers with the time at the end of
+	// this step (Model.cpp:470-509).
+	Time timeNext = time;
+	timeNext += m_model.GetDeltaT();
+	if (timeNext >= m_model.GetEndTime()) {
+		timeNext = m_model.GetEndTime();
+	}
+	bool fHostReads = (!m_fLazy) || fLastStep;
+	for (size_t q = 0; q < m_vecNextRead.size(); q++) {
+		if ((!m_vecReadFrequency[q].IsZero()) && (!(timeNext < m_vecNextRead[q]))) {
+			fHostReads = true;
+			m_vecNextRead[q] += m_vecReadFrequency[q];
+		}
+	}
+	for (size_t q = 0; q < m_vecProcesses.size(); q++) {
+		if (m_vecProcesses[q]->IsReady(timeNext)) {
+			// its Perform() changes the host copy: upload before the next step
+			fHostReads = true;
+			m_fDeviceCurrent = false;
+		}
+	}
+	if (fHostReads) {
+		b.Check(tb200_check_errors(b.Ctx()));
+		b.Download(0);
+	}
+}
+
+void TimestepSchemeB200::HostReadsEvery(
+	const Time & timeStart, const Time & timeFrequency
+) {
+	m_fLazy = true;
+	Time timeNext = timeStart;
+	timeNext += timeFrequency;
+	m_vecNextRead.push_back(timeNext);
+	m_vecReadFrequency.push_back(timeFrequency);
+}
+
+void TimestepSchemeB200::HostProcess(WorkflowProcess * pProcess) {
+	m_fLazy = true;
+	m_vecProcesses.push_back(pProcess);
 }
 
 ///////////////////////////////////////////////////////////////////////////////

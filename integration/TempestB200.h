@@ -29,6 +29,9 @@
 #include "VerticalDynamics.h"
 #include "TimestepScheme.h"
 
+#include "FunctionTimer.h"
+#include "WorkflowProcess.h"
+
 #include "tempest_b200.h"
 
 #include <vector>
@@ -59,10 +62,18 @@ public:
 	void Initialize();
 
 	///	<summary>
-	///		Host instance -> device, device -> host.
+	///		Host instance -> device, device -> host.  All patches are enqueued
+	///		(bus copies and layout conversions overlap), then the host waits once.
 	///	</summary>
 	void Upload(int iInstance);
 	void Download(int iInstance);
+
+	///	<summary>
+	///		Open / close one of the reference's FunctionTimer groups
+	///		(tb200_set_timing_hooks); installed when TB200_TIMING=1.
+	///	</summary>
+	static void TimerBegin(void * pUser, const char * szGroup);
+	static void TimerEnd(void * pUser, const char * szGroup);
 
 	///	<summary>
 	///		Throw the reference's Exception if a C-ABI call failed.
@@ -77,6 +88,8 @@ private:
 	Model & m_model;
 	tb200_ctx * m_pCtx;
 	bool m_fInitialized;
+	std::vector<void *> m_vecPinned;
+	std::vector<FunctionTimer *> m_vecTimers;
 	int m_nHypervisOrder;
 	double m_dNuScalar, m_dNuDiv, m_dNuVort;
 };
@@ -133,14 +146,39 @@ public:
 	virtual int GetTracerDataInstances() const;
 	virtual void Initialize();
 	///	<summary>
-	///		Instance 0 is uploaded when the host may have changed it (first
-	///		step, or after a workflow / output), the whole step runs on the
-	///		device, instance 0 comes back for Model::Go's outputs.
+	///		The whole step runs on the device.  Between steps the host only
+	///		touches state instance 0, and only when an output manager fires
+	///		(Model.cpp:484-509) or a workflow process is ready (:477-481): the
+	///		instance is downloaded at the end of a step only then (and on the
+	///		last step), and uploaded at the start of a step only when the host
+	///		may have changed it (first step, after a workflow process).
 	///	</summary>
 	virtual void Step(bool fFirstStep, bool fLastStep, const Time & time, double dDeltaT);
 
+	///	<summary>
+	///		Tell the scheme who reads instance 0 on the host between steps.
+	///		An output manager created with output frequency `timeFrequency`
+	///		fires at start + k * frequency (OutputManager::IsOutputNeeded,
+	///		OutputManager.cpp:83-98; a zero frequency only writes the initial
+	///		and final state).  Without any registration the scheme is
+	///		conservative: instance 0 crosses the bus both ways every step.
+	///	</summary>
+	void HostReadsEvery(const Time & timeStart, const Time & timeFrequency);
+
+	///	<summary>
+	///		A workflow process that reads and changes instance 0 on the host
+	///		(e.g. column physics): asked through its own IsReady(); instance 0
+	///		is uploaded again before the step that follows its Perform().
+	///	</summary>
+	void HostProcess(WorkflowProcess * pProcess);
+
 private:
 	int m_iScheme;
+	bool m_fLazy;
+	bool m_fDeviceCurrent;
+	std::vector<Time> m_vecNextRead;
+	std::vector<Time> m_vecReadFrequency;
+	std::vector<WorkflowProcess *> m_vecProcesses;
 };
 
 ///////////////////////////////////////////////////////////////////////////////

@@ -38,6 +38,7 @@ try {
 	int nPatch;
 	double dZtop;
 	std::string strPert;
+	int nEager;
 
 	BeginTempestCommandLine("B200Driver");
 		SetDefaultResolution(8);
@@ -54,6 +55,7 @@ try {
 		CommandLineInt(nPatch, "npatch", 6);
 		CommandLineDouble(dZtop, "ztop", 10000.0);
 		CommandLineString(strPert, "pert", "Exp");
+		CommandLineInt(nEager, "b200eager", 0);
 
 		ParseCommandLine(argc, argv);
 	EndTempestCommandLine(argv)
@@ -77,7 +79,15 @@ try {
 
 	} else {
 		if (strMode == "scheme") {
-			model.SetTimestepScheme(new TimestepSchemeB200(model, iScheme));
+			TimestepSchemeB200 * pScheme = new TimestepSchemeB200(model, iScheme);
+			// the output managers of _TempestSetupOutputManagers all fire every
+			// --outputtime (TempestInitialize.h:413-472): instance 0 only comes
+			// back to the host for them (--b200eager 1: every step)
+			if (nEager == 0) {
+				pScheme->HostReadsEvery(
+					model.GetStartTime(), _tempestvars.timeOutputDeltaT);
+			}
+			model.SetTimestepScheme(pScheme);
 		} else if (iScheme == TB200_SCHEME_ARS343) {
 			model.SetTimestepScheme(new TimestepSchemeARS343(model));
 		} else if (iScheme == TB200_SCHEME_STRANG_KGU35) {

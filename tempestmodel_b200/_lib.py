@@ -117,6 +117,13 @@ _SIGNATURES = {
     "tb200_upload_element_area": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "tb200_upload_rayleigh": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
+    "tb200_upload_state_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tb200_download_state_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                           c_void_p, c_int]),
+    "tb200_transfer_sync": (c_int, [c_void_p]),
+    "tb200_host_register": (c_int, [c_void_p, c_void_p, ctypes.c_size_t]),
+    "tb200_host_unregister": (c_int, [c_void_p, c_void_p]),
+    "tb200_set_timing_hooks": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "tb200_checksum": (c_int, [c_void_p, c_int, c_void_p]),
     "tb200_total_energy": (c_int, [c_void_p, c_int, c_void_p]),
     "tb200_total_potential_enstrophy": (c_int, [c_void_p, c_int, c_int, c_void_p]),

@@ -53,6 +53,31 @@
 		} \
 	} while (0)
 
+// FunctionTimer group of an entry point (tb200_set_timing_hooks): begin at
+// construction, device work awaited and end at destruction.
+struct TimingScope {
+	tb200_ctx * ctx;
+	const char * group;
+	TimingScope(tb200_ctx * c, const char * g) : ctx(c), group(g) {
+		if (ctx->timing_begin != 0) ctx->timing_begin(ctx->timing_user, group);
+	}
+	~TimingScope() {
+		if (ctx->timing_end != 0) {
+			cudaStreamSynchronize(ctx->stream);
+			ctx->timing_end(ctx->timing_user, group);
+		}
+	}
+};
+
+extern "C" int tb200_set_timing_hooks(
+	tb200_ctx * ctx, tb200_timing_fn begin, tb200_timing_fn end, void * user
+) {
+	ctx->timing_begin = begin;
+	ctx->timing_end = end;
+	ctx->timing_user = user;
+	return 0;
+}
+
 static const int kItems = 8;   // (element, level) pairs per block in the slab kernels
 
 template <typename T>
@@ -345,6 +370,16 @@ extern "C" int tb200_destroy(tb200_ctx * ctx) {
 		cudaFree(ctx->allocs[i]);
 	}
 	if (ctx->h_info != 0) cudaFreeHost(ctx->h_info);
+#ifndef TB200_EMU
+	if (ctx->copy_stream != 0) {
+		cudaStreamDestroy(ctx->copy_stream);
+		for (int q = 0; q < 2; q++) {
+			cudaEventDestroy(ctx->ev_stage_free[q]);
+			cudaEventDestroy(ctx->ev_stage_full[q]);
+		}
+		cudaEventDestroy(ctx->ev_compute);
+	}
+#endif
 	delete ctx;
 	return 0;
 }
@@ -787,11 +822,50 @@ extern "C" int tb200_upload_rayleigh(
 ///////////////////////////////////////////////////////////////////////////////
 // State movement
 
-// Interior of one component slice <-> staging copy: (wa-2) rows of
-// (wb-2)*nlev contiguous doubles, pitch wb*nlev; halo entries are not touched
-// on either side.
+// Host <-> device state movement.
+//
+// A host array (reference layout [c][iA][iB][k], one-node halo) crosses the bus
+// as pitched copies of the interior of its valid component slices into / out of
+// a staging buffer of the same shape, and k_transpose_state converts between
+// that and the element-major device layout.  Two staging buffers and a copy
+// stream pipeline the two: while one array is on the bus the previous one is
+// being transposed (upload) or the next one is (download); per-buffer events
+// order producer and consumer, nothing synchronises with the host until the
+// caller asks (tb200_transfer_sync; the plain tb200_upload_state /
+// tb200_download_state do that before they return - an upload only waits for
+// its bus copies, not for the transposes behind them).
+
+static int xfer_setup(tb200_ctx * ctx) {
+	if (ctx->copy_stream != 0) return 0;
+#ifndef TB200_EMU
+	TB_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	for (int q = 0; q < 2; q++) {
+		TB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_stage_free[q], cudaEventDisableTiming));
+		TB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_stage_full[q], cudaEventDisableTiming));
+	}
+	TB_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+#else
+	ctx->copy_stream = (cudaStream_t)1;
+#endif
+	ctx->stage_buf[0] = ctx->d_stage;
+	if (dalloc(ctx, &ctx->stage_buf[1], ctx->stage_doubles)) return 1;
+	// device row of every host component: node array, interface array, tracers
+	const DevLayout & lay = ctx->lay;
+	std::vector<int> maps(64, -1);
+	for (int c = 0; c < lay.ncomp && c < 8; c++) {
+		maps[c] = lay.onedge[c] ? -1 : lay.rowoff[c];
+		maps[8 + c] = lay.onedge[c] ? lay.rowoff[c] : -1;
+	}
+	for (int q = 0; q < lay.ntr && q < 48; q++) maps[16 + q] = lay.troff + q * lay.nlev;
+	TB_CHECK(ctx, cudaMemcpy(ctx->d_rowmap, maps.data(), 64 * sizeof(int), cudaMemcpyHostToDevice));
+	ctx->rowmap_h = maps;
+	return 0;
+}
+
+// pitched copy of the interior of one component slice between the host array
+// and the staging buffer (halo entries are not touched on either side)
 static int copy_interior(
-	tb200_ctx * ctx, const PatchInfo & pi, double * host, size_t comp,
+	tb200_ctx * ctx, const PatchInfo & pi, double * host, double * stage, size_t comp,
 	int host_nlev, bool to_device
 ) {
 	const int np = ctx->lay.np;
@@ -802,64 +876,99 @@ static int copy_interior(
 	const size_t width = (wb - 2 * pi.halo) * host_nlev * sizeof(double);
 	const size_t off = comp * slice + ((size_t)pi.halo * wb + pi.halo) * host_nlev;
 	if (to_device) {
-		TB_CHECK(ctx, cudaMemcpy2DAsync(ctx->d_stage + off, pitch, host + off, pitch,
-			width, wa - 2 * pi.halo, cudaMemcpyHostToDevice, ctx->stream));
+		TB_CHECK(ctx, cudaMemcpy2DAsync(stage + off, pitch, host + off, pitch,
+			width, wa - 2 * pi.halo, cudaMemcpyHostToDevice, ctx->copy_stream));
 	} else {
-		TB_CHECK(ctx, cudaMemcpy2DAsync(host + off, pitch, ctx->d_stage + off, pitch,
-			width, wa - 2 * pi.halo, cudaMemcpyDeviceToHost, ctx->stream));
+		TB_CHECK(ctx, cudaMemcpy2DAsync(host + off, pitch, stage + off, pitch,
+			width, wa - 2 * pi.halo, cudaMemcpyDeviceToHost, ctx->copy_stream));
 	}
 	return 0;
 }
 
+// One host array of one patch.  map0: first entry of the array's row map in
+// d_rowmap (0 node, 8 interfaces, 16 tracers); derived: components whose
+// derived copies the reference keeps at this location (download only).
 static int move_state_array(
 	tb200_ctx * ctx, const PatchInfo & pi, int inst, double * host,
-	int ncomp_host, int host_nlev, const std::vector<int> & rowmap, bool to_device
+	int ncomp_host, int host_nlev, int map0, bool to_device,
+	const std::vector<int> & derived = std::vector<int>()
 ) {
 	if (host == 0) return 0;
+	if (xfer_setup(ctx)) return 1;
 	const int np = ctx->lay.np, nn = ctx->lay.nn;
 	const size_t wa = pi.nea * np + 2 * pi.halo;
 	const size_t wb = pi.neb * np + 2 * pi.halo;
 	const size_t slice = wa * wb * host_nlev;
 	if (slice * ncomp_host > ctx->stage_doubles) TB_FAIL(ctx, "staging buffer too small");
-	// the previous user of the staging buffer / row map must be done
-	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-	TB_CHECK(ctx, cudaMemcpyAsync(ctx->d_rowmap, rowmap.data(), ncomp_host * sizeof(int),
-		cudaMemcpyHostToDevice, ctx->stream));
+	const int slot = (int)(ctx->xfer_jobs++ & 1);
+	double * stage = ctx->stage_buf[slot];
+	const int * rowmap = ctx->d_rowmap + map0;
 	const size_t smem = (size_t)host_nlev * (nn + 1) * sizeof(double);
 	if (to_device) {
+#ifndef TB200_EMU
+		// the transpose that last read this buffer is done
+		TB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage_free[slot], 0));
+#endif
 		for (int c = 0; c < ncomp_host; c++) {
-			if (rowmap[c] < 0) continue;
-			if (copy_interior(ctx, pi, host, c, host_nlev, true)) return 1;
+			if (ctx->rowmap_h[map0 + c] < 0) continue;
+			if (copy_interior(ctx, pi, host, stage, c, host_nlev, true)) return 1;
 		}
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaEventRecord(ctx->ev_stage_full[slot], ctx->copy_stream));
+		TB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_full[slot], 0));
+#endif
 		auto kfn = k_transpose_state<true>;
 		TB_LAUNCH(kfn, dim3(pi.nea * pi.neb), dim3(256), smem, ctx->stream,
-			ctx->lay, ctx->inst[inst], ctx->d_stage, pi.elem0, pi.nea, pi.neb, pi.halo,
-			0, ncomp_host, host_nlev, 0, (const int *)ctx->d_rowmap);
+			ctx->lay, ctx->inst[inst], stage, pi.elem0, pi.nea, pi.neb, pi.halo,
+			0, ncomp_host, host_nlev, 0, rowmap);
 		TB_KERNEL_CHECK(ctx);
-		TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaEventRecord(ctx->ev_stage_free[slot], ctx->stream));
+#endif
 	} else {
+#ifndef TB200_EMU
+		// the bus copy that last read this buffer is done
+		TB_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free[slot], 0));
+#endif
 		auto kfn = k_transpose_state<false>;
 		TB_LAUNCH(kfn, dim3(pi.nea * pi.neb), dim3(256), smem, ctx->stream,
-			ctx->lay, ctx->inst[inst], ctx->d_stage, pi.elem0, pi.nea, pi.neb, pi.halo,
-			0, ncomp_host, host_nlev, 0, (const int *)ctx->d_rowmap);
+			ctx->lay, ctx->inst[inst], stage, pi.elem0, pi.nea, pi.neb, pi.halo,
+			0, ncomp_host, host_nlev, 0, rowmap);
 		TB_KERNEL_CHECK(ctx);
+		for (size_t q = 0; q < derived.size(); q++) {
+			// W on levels / U, V on interfaces (HorizontalDynamicsFEM.cpp:817-831)
+			auto kfd = k_fill_derived;
+			const int c = derived[q];
+			TB_LAUNCH_FLAT(kfd, dim3(pi.nea * pi.neb), dim3(256), 0, ctx->stream,
+				ctx->lay, ctx->ops, (const double *)ctx->inst[inst], stage,
+				pi.elem0, pi.nea, pi.neb, pi.halo, c, c, (map0 == 0) ? 1 : 0, host_nlev);
+			TB_KERNEL_CHECK(ctx);
+		}
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaEventRecord(ctx->ev_stage_full[slot], ctx->stream));
+		TB_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage_full[slot], 0));
+#endif
+		for (int c = 0; c < ncomp_host; c++) {
+			bool take = ctx->rowmap_h[map0 + c] >= 0;
+			for (size_t q = 0; q < derived.size(); q++) take = take || derived[q] == c;
+			if (!take) continue;
+			if (copy_interior(ctx, pi, host, stage, c, host_nlev, false)) return 1;
+		}
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaEventRecord(ctx->ev_stage_free[slot], ctx->copy_stream));
+#endif
 	}
 	return 0;
 }
 
-// copy the interior of component slices from the staged array back to the host
-static int stage_to_host(
-	tb200_ctx * ctx, const PatchInfo & pi, double * host, int host_nlev,
-	const std::vector<int> & comps
-) {
-	for (size_t q = 0; q < comps.size(); q++) {
-		if (copy_interior(ctx, pi, host, comps[q], host_nlev, false)) return 1;
-	}
-	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+extern "C" int tb200_transfer_sync(tb200_ctx * ctx) {
+#ifndef TB200_EMU
+	if (ctx->copy_stream != 0) TB_CHECK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+#endif
 	return 0;
 }
 
-extern "C" int tb200_upload_state(
+extern "C" int tb200_upload_state_async(
 	tb200_ctx * ctx, int patch_index, int inst,
 	const double * node, const double * redge, const double * tracers
 ) {
@@ -868,26 +977,30 @@ extern "C" int tb200_upload_state(
 	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
 	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid instance");
 	const DevLayout & lay = ctx->lay;
-	std::vector<int> rm(lay.ncomp);
-	for (int c = 0; c < lay.ncomp; c++) rm[c] = lay.onedge[c] ? -1 : lay.rowoff[c];
-	if (move_state_array(ctx, *pi, inst, (double *)node, lay.ncomp, lay.nlev, rm, true)) return 1;
+	if (move_state_array(ctx, *pi, inst, (double *)node, lay.ncomp, lay.nlev, 0, true)) return 1;
 	bool anyedge = false;
-	for (int c = 0; c < lay.ncomp; c++) {
-		rm[c] = lay.onedge[c] ? lay.rowoff[c] : -1;
-		anyedge = anyedge || lay.onedge[c];
-	}
+	for (int c = 0; c < lay.ncomp; c++) anyedge = anyedge || lay.onedge[c];
 	if (anyedge) {
-		if (move_state_array(ctx, *pi, inst, (double *)redge, lay.ncomp, lay.nlev + 1, rm, true)) return 1;
+		if (move_state_array(ctx, *pi, inst, (double *)redge, lay.ncomp, lay.nlev + 1, 8, true)) return 1;
 	}
 	if (lay.ntr > 0 && tracers != 0) {
-		std::vector<int> rt(lay.ntr);
-		for (int q = 0; q < lay.ntr; q++) rt[q] = lay.troff + q * lay.nlev;
-		if (move_state_array(ctx, *pi, inst, (double *)tracers, lay.ntr, lay.nlev, rt, true)) return 1;
+		if (lay.ntr > 48) TB_FAIL(ctx, "more than 48 tracers");
+		if (move_state_array(ctx, *pi, inst, (double *)tracers, lay.ntr, lay.nlev, 16, true)) return 1;
 	}
 	return 0;
 }
 
-extern "C" int tb200_download_state(
+extern "C" int tb200_upload_state(
+	tb200_ctx * ctx, int patch_index, int inst,
+	const double * node, const double * redge, const double * tracers
+) {
+	if (tb200_upload_state_async(ctx, patch_index, inst, node, redge, tracers)) return 1;
+	// the host arrays are free once their bus copies are done; the transposes
+	// run on behind them in stream order
+	return tb200_transfer_sync(ctx);
+}
+
+extern "C" int tb200_download_state_async(
 	tb200_ctx * ctx, int patch_index, int inst,
 	double * node, double * redge, double * tracers, int fill_derived
 ) {
@@ -897,55 +1010,45 @@ extern "C" int tb200_download_state(
 	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid instance");
 	const DevLayout & lay = ctx->lay;
 	const bool nh = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO);
-	std::vector<int> rm(lay.ncomp), comps;
+	std::vector<int> derived;
 	if (node != 0) {
-		comps.clear();
-		for (int c = 0; c < lay.ncomp; c++) {
-			rm[c] = lay.onedge[c] ? -1 : lay.rowoff[c];
-			if (!lay.onedge[c]) comps.push_back(c);
-		}
-		if (move_state_array(ctx, *pi, inst, node, lay.ncomp, lay.nlev, rm, false)) return 1;
-		if (fill_derived && nh) {
-			auto kfn = k_fill_derived;
-			TB_LAUNCH_FLAT(kfn, dim3(pi->nea * pi->neb), dim3(256), 0, ctx->stream,
-				lay, ctx->ops, (const double *)ctx->inst[inst], ctx->d_stage,
-				pi->elem0, pi->nea, pi->neb, pi->halo, 3, 3, 1, lay.nlev);
-			TB_KERNEL_CHECK(ctx);
-			comps.push_back(3);
-		}
-		if (stage_to_host(ctx, *pi, node, lay.nlev, comps)) return 1;
+		derived.clear();
+		if (fill_derived && nh) derived.push_back(3);
+		if (move_state_array(ctx, *pi, inst, node, lay.ncomp, lay.nlev, 0, false, derived)) return 1;
 	}
 	bool anyedge = false;
 	for (int c = 0; c < lay.ncomp; c++) anyedge = anyedge || lay.onedge[c];
 	if (redge != 0 && anyedge) {
-		comps.clear();
-		for (int c = 0; c < lay.ncomp; c++) {
-			rm[c] = lay.onedge[c] ? lay.rowoff[c] : -1;
-			if (lay.onedge[c]) comps.push_back(c);
-		}
-		if (move_state_array(ctx, *pi, inst, redge, lay.ncomp, lay.nlev + 1, rm, false)) return 1;
-		if (fill_derived && nh) {
-			for (int c = 0; c < 2; c++) {
-				auto kfn = k_fill_derived;
-				TB_LAUNCH_FLAT(kfn, dim3(pi->nea * pi->neb), dim3(256), 0, ctx->stream,
-					lay, ctx->ops, (const double *)ctx->inst[inst], ctx->d_stage,
-					pi->elem0, pi->nea, pi->neb, pi->halo, c, c, 0, lay.nlev + 1);
-				TB_KERNEL_CHECK(ctx);
-				comps.push_back(c);
-			}
-		}
-		if (stage_to_host(ctx, *pi, redge, lay.nlev + 1, comps)) return 1;
+		derived.clear();
+		if (fill_derived && nh) { derived.push_back(0); derived.push_back(1); }
+		if (move_state_array(ctx, *pi, inst, redge, lay.ncomp, lay.nlev + 1, 8, false, derived)) return 1;
 	}
 	if (lay.ntr > 0 && tracers != 0) {
-		std::vector<int> rt(lay.ntr);
-		comps.clear();
-		for (int q = 0; q < lay.ntr; q++) {
-			rt[q] = lay.troff + q * lay.nlev;
-			comps.push_back(q);
-		}
-		if (move_state_array(ctx, *pi, inst, tracers, lay.ntr, lay.nlev, rt, false)) return 1;
-		if (stage_to_host(ctx, *pi, tracers, lay.nlev, comps)) return 1;
+		if (lay.ntr > 48) TB_FAIL(ctx, "more than 48 tracers");
+		derived.clear();
+		if (move_state_array(ctx, *pi, inst, tracers, lay.ntr, lay.nlev, 16, false, derived)) return 1;
 	}
+	return 0;
+}
+
+extern "C" int tb200_download_state(
+	tb200_ctx * ctx, int patch_index, int inst,
+	double * node, double * redge, double * tracers, int fill_derived
+) {
+	if (tb200_download_state_async(ctx, patch_index, inst, node, redge, tracers, fill_derived)) return 1;
+	return tb200_transfer_sync(ctx);
+}
+
+// Pin / unpin host memory the state arrays live in (the reference's
+// DataContainer blocks, DataContainer.cpp:77-147) so that the bus copies run
+// asynchronously at full rate.  The C++ shells only see the C ABI.
+extern "C" int tb200_host_register(tb200_ctx * ctx, void * p, size_t bytes) {
+	TB_CHECK(ctx, cudaHostRegister(p, bytes, 0));
+	return 0;
+}
+
+extern "C" int tb200_host_unregister(tb200_ctx * ctx, void * p) {
+	TB_CHECK(ctx, cudaHostUnregister(p));
 	return 0;
 }
 
@@ -1369,6 +1472,8 @@ static int check_inst2(tb200_ctx * ctx, int in, int out) {
 }
 
 extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
+	TimingScope ts(ctx, (ctx->cfg.eqn_type == TB200_EQN_SHALLOW_WATER)
+		? "HorizontalStepShallowWater" : "HorizontalStepNonhydrostaticPrimitive");
 	if (check_inst2(ctx, in, out)) return 1;
 	// HorizontalDynamicsFEM.cpp:1793
 	if (in == out) TB_FAIL(ctx, "HorizontalDynamics Step must have iDataInitial != iDataUpdate");
@@ -1387,6 +1492,7 @@ extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 }
 
 extern "C" int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
+	TimingScope ts(ctx, "VerticalStepExplicit");
 	if (check_inst2(ctx, in, out)) return 1;
 	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || ctx->lay.nlev == 1) {
 		return 0;   // VerticalDynamicsStub (TempestInitialize.h:362-364)
@@ -1407,6 +1513,7 @@ extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double d
 		if (tb200_h_step_explicit(ctx, in, out, dt)) return 1;
 		return tb200_v_step_explicit(ctx, in, out, dt);
 	}
+	TimingScope ts(ctx, "HorizontalStepNonhydrostaticPrimitive");
 	return nh_launch(ctx, in, out, dt, true, true, stage_base_out());
 }
 
@@ -1452,6 +1559,7 @@ extern "C" int tb200_hv_step_explicit_combine(
 		if (tb200_lincomb(ctx, coeff, ncoeff, out, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
 		return tb200_hv_step_explicit(ctx, in, out, dt);
 	}
+	TimingScope ts(ctx, "HorizontalStepNonhydrostaticPrimitive");
 	StageBase sb;
 	memset(&sb, 0, sizeof(sb));
 	sb.cdst = coeff[out];
@@ -1533,6 +1641,7 @@ static int column_tracers(tb200_ctx * ctx, int in, int out, double dt) {
 }
 
 static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
+	TimingScope ts(ctx, "VerticalStepImplicit");
 	const DevLayout & lay = ctx->lay;
 	ColumnArgs ca;
 	ca.col_node = ctx->d_col_node;
@@ -2021,6 +2130,9 @@ static int dss_rows(
 	const DevLayout & lay = ctx->lay;
 	const int nsel = row1 - row0;
 	const double * recvbuf = ctx->d_recvbuf;
+	// Grid::Exchange ("Communicate", Grid.cpp:636): one per DSS, also on one rank
+	// (the reference exchanges halos with itself)
+	TimingScope ts(ctx, "Communicate");
 	if (ctx->nranks > 1 && ctx->peer_ready) {
 		if (peer_exchange(ctx, inst, row0, nsel, &recvbuf)) return 1;
 	} else if (ctx->nranks > 1) {
@@ -2349,6 +2461,7 @@ static int h_step_after_subcycle_impl(
 extern "C" int tb200_h_step_after_subcycle(
 	tb200_ctx * ctx, int in, int out, int work, double dt
 ) {
+	TimingScope ts(ctx, "StepAfterSubCycle");
 	if (h_step_after_subcycle_impl(ctx, in, out, work, dt)) return 1;
 	if (!ctx->has_rayleigh) return 0;
 	const DevLayout & lay = ctx->lay;

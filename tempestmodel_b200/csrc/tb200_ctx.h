@@ -59,7 +59,13 @@ struct tb200_ctx {
 	// staging for host <-> device layout conversion
 	double * d_stage;
 	size_t stage_doubles;
-	int * d_rowmap;
+	int * d_rowmap;                   // [64] device row of host component: node 0.., interfaces 8.., tracers 16..
+	std::vector<int> rowmap_h;
+	// pipelined state transfers: copy stream, two staging buffers and their events
+	cudaStream_t copy_stream;
+	double * stage_buf[2];
+	cudaEvent_t ev_stage_free[2], ev_stage_full[2], ev_compute;
+	unsigned long long xfer_jobs;
 
 	// mutable geometry arrays (device), same pointers as in geom
 	double * d_inv_da; double * d_inv_db; double * d_nu_scale;
@@ -124,6 +130,11 @@ struct tb200_ctx {
 	int * d_elist_int; int n_int;     // all other elements
 	bool want_split, split_pending;
 
+	// FunctionTimer hooks (tb200_set_timing_hooks); depth: only the outermost
+	// entry point of a group reports
+	tb200_timing_fn timing_begin, timing_end;
+	void * timing_user;
+
 	int64_t launches;
 	// Every operation that writes device state bumps `writes`: kernel launches
 	// (TB_KERNEL_CHECK and the counted persistent launches) and the
@@ -153,7 +164,7 @@ struct tb200_ctx {
 		stream(0), committed(false), connectivity_built(false),
 		stream2(0), ev_fork(0), ev_join(0), d_elist_bnd(0), n_bnd(0), d_elist_int(0), n_int(0),
 		want_split(false), split_pending(false),
-		d_stage(0), stage_doubles(0), d_rowmap(0),
+		d_stage(0), stage_doubles(0), d_rowmap(0), copy_stream(0), xfer_jobs(0),
 		d_inv_da(0), d_inv_db(0), d_nu_scale(0),
 		d_area_node(0), d_area_redge(0), d_sums(0),
 		d_tx(0), d_ty(0), d_tda(0), d_tdb(0), d_reta_n(0), d_reta_e(0),
@@ -164,6 +175,7 @@ struct tb200_ctx {
 		peer_ready(false), peer_seq(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0),
 		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false),
 		column_inc(0), d_wold(0), offd(4), launches(0), writes(0), uvzero_inst(-1), uvzero_writes(0),
+		timing_begin(0), timing_end(0), timing_user(0),
 		carry_full(false), h_info(0),
 		fuse_ready(false), nstrips(0), d_strip_first(0), d_strip_len(0), d_strip_neb(0),
 		d_done(0), fuse_epoch(0), nrem(0), d_rem_members(0), d_rem_flags(0),
@@ -171,6 +183,9 @@ struct tb200_ctx {
 		fast_state(0), fast_metric_error(0.0), d_colc(0), d_lev(0),
 		geometry3d_uploaded(false)
 	{
+		stage_buf[0] = stage_buf[1] = 0;
+		for (int i = 0; i < 2; i++) { ev_stage_free[i] = 0; ev_stage_full[i] = 0; }
+		ev_compute = 0;
 		for (int i = 0; i < 7; i++) g2d[i] = 0;
 		for (int i = 0; i < 13; i++) { g3n[i] = 0; g3e[i] = 0; }
 	}

@@ -208,6 +208,27 @@ class DeviceContext:
             self._h, patch, inst, _ptr(node), _ptr(redge), _ptr(tracers),
             1 if fill_derived else 0))
 
+    def upload_state_async(self, patch, inst, node=None, redge=None, tracers=None):
+        """Enqueue only: the arrays (C-contiguous float64, ideally pinned) must stay
+        alive and unchanged until transfer_sync()."""
+        for a in (node, redge, tracers):
+            if a is not None:
+                assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.tb200_upload_state_async(self._h, patch, inst, _ptr(node),
+                                                   _ptr(redge), _ptr(tracers)))
+
+    def download_state_async(self, patch, inst, node=None, redge=None, tracers=None,
+                             fill_derived=True):
+        for a in (node, redge, tracers):
+            if a is not None:
+                assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.tb200_download_state_async(
+            self._h, patch, inst, _ptr(node), _ptr(redge), _ptr(tracers),
+            1 if fill_derived else 0))
+
+    def transfer_sync(self):
+        self._ck(self.lib.tb200_transfer_sync(self._h))
+
     def copy(self, src, dst, mask=DATA_ALL):
         self._ck(self.lib.tb200_copy(self._h, src, dst, mask))
 

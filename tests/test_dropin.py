@@ -23,11 +23,13 @@ def reference_spread(key):
         return json.load(f)[key]
 
 
-def run(mode, *flags):
+def run(mode, *flags, env=None, full=False):
     res = subprocess.run([DRIVER, "--b200", mode, "--output_none"] + list(flags),
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                         text=True, timeout=900)
+                         text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert res.returncode == 0, res.stdout[-3000:]
+    if full:
+        return res.stdout
     sums = {}
     final = res.stdout[res.stdout.rindex("(Final)"):]
     for m in re.finditer(r"Checksum \((\w+)\): ([-+0-9.eE]+)", final):
@@ -98,3 +100,43 @@ def test_cartesian_bubble_dropin(cuda_library, mode):
     # whose sign the reference's Jacobian depends on
     sp = reference_spread("bubble_r36_l72_20steps")["rel_spread"]
     assert abs(got["W"] - ref["W"]) <= max(10.0 * sp[3], 1e-12) * abs(ref["W"]), (got, ref, sp)
+
+
+@pytest.mark.gpu
+def test_lazy_instance0_residency(cuda_library):
+    """TimestepSchemeB200 keeps instance 0 on the device between steps unless an
+    output manager fires (SURVEY 8b call-order contract, Model.cpp:477-509): a
+    run that only comes back to the host at the end, one that comes back for an
+    output every second step and the eager run (both ways every step) print the
+    same checksums."""
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "jw", "--resolution", "4", "--levels", "10", "--dt", "200s",
+             "--endtime", "1200s"]
+    eager, _ = run("scheme", "--b200eager", "1", *flags)
+    lazy, _ = run("scheme", *flags)
+    lazy_out, _ = run("scheme", "--outputtime", "400s", *flags)
+    for k in eager:
+        assert lazy[k] == eager[k], (k, lazy, eager)
+        assert lazy_out[k] == eager[k], (k, lazy_out, eager)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["plugins", "scheme"])
+def test_function_timer_groups(cuda_library, mode):
+    """With TB200_TIMING=1 the shells open the reference's FunctionTimer groups
+    around the device calls, so that Model::Go's end-of-run report
+    (Model.cpp:640-688) is filled in as under the reference's own plugins."""
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "jw", "--resolution", "4", "--levels", "10", "--dt", "200s",
+             "--endtime", "600s"]
+    out = run(mode, *flags, env={"TB200_TIMING": "1"}, full=True)
+    ref = run("none", *flags, full=True)
+    counts = {}
+    for text, store in ((out, counts), (ref, {})):
+        for m in re.finditer(r"Time \[(\w+)\]: \d+ \[\d+, \d+\] \((\d+)\)", text):
+            store[m.group(1)] = int(m.group(2))
+        if store is not counts:
+            refcounts = store
+    for group in ("SNHP", "VSIm", "SaSc"):
+        assert counts.get(group, 0) == refcounts[group], (group, counts, refcounts)
+    assert counts.get("Comm", 0) > 0
