@@ -261,6 +261,35 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the cores of the NUMA node its GPU hangs off, before any
+    pinned host buffer is allocated (first touch then places it there): with one
+    rank per GPU the host<->device copies of the end-to-end leg otherwise all
+    cross from node 0.  Returns the node, or None when the topology is unknown."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -283,6 +312,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl")
     n_gpus = world
@@ -552,6 +582,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": e2e,
             "setup_seconds": t_setup,
+            "numa_node": numa,
         }
         print(json.dumps(line))
     if world > 1:

@@ -2035,21 +2035,14 @@ static int peer_exchange(tb200_ctx * ctx, int inst, int row0, int nsel, const do
 		TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(256), 0, ctx->stream,
 			lay, (const int *)ctx->d_send_nodes, (const int *)ctx->d_send_rank,
 			(const int *)ctx->d_send_slot, ctx->nsend_total,
-			(const double *)ctx->inst[inst], pp, row0, nsel);
+			(const double *)ctx->inst[inst], pp, row0, nsel,
+			ctx->d_peer_ticket, ctx->nranks, ctx->rank, seq);
 		TB_KERNEL_CHECK(ctx);
 	}
-	if (any_send) {
-		auto kfn = k_peer_signal;
-		TB_LAUNCH_FLAT(kfn, dim3(1), dim3(32), 0, ctx->stream, pp, ctx->nranks, ctx->rank, seq);
-		TB_KERNEL_CHECK(ctx);
-	}
-	if (wait_mask != 0) {
-		auto kfn = k_peer_wait;
-		TB_LAUNCH_FLAT(kfn, dim3(1), dim3(32), 0, ctx->stream,
-			(const unsigned long long *)ctx->peer_area, wait_mask, seq,
-			peer_timeout_ns(), ctx->d_info);
-		TB_KERNEL_CHECK(ctx);
-	}
+	(void)any_send;
+	(void)wait_mask;
+	// no signal / wait launches: the last block of the pack kernel raises the
+	// flags, the averaging kernel waits for the ranks each of its groups reads from
 	*recvbuf = peer_buffer(ctx->peer_area, ctx->nrecv_total, ctx->peer_rows, parity);
 	return 0;
 }
@@ -2083,6 +2076,10 @@ extern "C" int tb200_peer_export(
 	if (ctx->d_info == 0) {
 		if (dalloc(ctx, &ctx->d_info, 4)) return 1;
 		TB_CHECK(ctx, cudaMemset(ctx->d_info, 0, 4 * sizeof(int)));
+	}
+	if (ctx->d_peer_ticket == 0) {
+		if (dalloc(ctx, &ctx->d_peer_ticket, 1)) return 1;
+		TB_CHECK(ctx, cudaMemset(ctx->d_peer_ticket, 0, sizeof(unsigned)));
 	}
 	return 0;
 #endif
@@ -2179,6 +2176,15 @@ static int dss_rows(
 	a.uv_row1 = is_state ? (lay.rowoff[1] + lay.rowlev[1]) : -1;
 	a.nsel = nsel;
 	a.sel_row0 = row0;
+	a.peer_flags = 0;
+	a.peer_seq = 0;
+	a.peer_timeout_ns = 0;
+	a.info = ctx->d_info;
+	if (ctx->nranks > 1 && ctx->peer_ready) {
+		a.peer_flags = (const unsigned long long *)ctx->peer_area;
+		a.peer_seq = ctx->peer_seq;
+		a.peer_timeout_ns = peer_timeout_ns();
+	}
 	if (a.ngroups > 0) {
 		const int block = 128;
 		static const bool classes = []() {  // TB200_DSS_KERNEL=generic: row-at-a-time kernel for every group
@@ -2759,13 +2765,18 @@ extern "C" int tb200_build_connectivity(tb200_ctx * ctx) {
 					ctx->patches[m.ppos].index, std::make_pair(m.ia, m.ib))];
 			}
 		}
+		// ranks whose nodes this group reads from the receive buffer
+		int rankmask = 0;
+		for (size_t q = 0; q < gr.mem.size(); q++) {
+			if (gr.mem[q].addr < 0) rankmask |= 1 << ctx->patches[gr.mem[q].ppos].owner;
+		}
 		if (!gr.seam) {
 			bool local = (gr.mem.size() == 2 || gr.mem.size() == 4);
 			for (size_t q = 0; q < gr.mem.size(); q++) local = local && gr.mem[q].addr >= 0;
-			if (local) flags[gi] = 2;
+			flags[gi] = (local ? 2 : 0) | (rankmask << 8);
 			continue;
 		}
-		flags[gi] = 1;
+		flags[gi] = 1 | (rankmask << 8);
 		seam_group.push_back((int)gi);
 		const size_t base = seam_mats.size();
 		seam_mats.resize(base + 64, 0.0);

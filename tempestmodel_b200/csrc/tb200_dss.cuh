@@ -21,7 +21,14 @@
 
 struct DssArgs {
 	const int * members;      // [ngroups][4], -1 = unused; >= nlocal: remote slot
-	const int * flags;        // [ngroups] bit0: group spans a panel seam; bit1: 2 or 4 members, all local, no seam
+	const int * flags;        // [ngroups] bit0: group spans a panel seam; bit1: 2 or 4 members, all local, no seam;
+	                          // bits 8..23: ranks that own remote members of the group
+	// peer-memory exchange: the kernel itself waits for the source ranks' flags
+	// (0: the exchange is complete when the kernel starts)
+	const unsigned long long * peer_flags;   // [rank] sequence number of the last exchange that rank delivered
+	unsigned long long peer_seq;
+	unsigned long long peer_timeout_ns;
+	int * info;               // [1]: rank + 1 of a peer that did not deliver in time
 	int ngroups;
 	int nlocal;               // number of local element nodes (nelem * NN)
 	const double * recv;      // [slot][nsel]
@@ -76,11 +83,53 @@ __device__ __forceinline__ DssRef tb_dss_ref(
 	return r;
 }
 
+// value of a member at row r: local memory, or the receive buffer - filled by
+// another GPU's stores while this kernel may already be running, hence read
+// from L2 (ld.cg), never through L1
+__device__ __forceinline__ double tb_dss_get(const DssRef & m, int r) {
+#ifndef TB200_EMU
+	if (m.w == 0) return __ldcg(m.p + (size_t)r * m.stride);
+#endif
+	return m.p[(size_t)r * m.stride];
+}
+
+// Wait until every rank in `mask` has delivered exchange a.peer_seq.  On a
+// time-out the failure is recorded and false returned: the caller poisons the
+// group (NaN) instead of averaging stale halo data.
+__device__ __forceinline__ bool tb_dss_wait_peers(const DssArgs & a, unsigned mask) {
+#ifndef TB200_EMU
+	if (*(volatile int *)(a.info + 1) != 0) return false;     // a peer is gone: do not wait again
+	unsigned long long t0;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+	while (mask != 0) {
+		const int r = __ffs(mask) - 1;
+		unsigned long long f;
+		asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(a.peer_flags + r) : "memory");
+		if (f >= a.peer_seq) {
+			mask &= mask - 1;
+			continue;
+		}
+		unsigned long long t1;
+		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+		if (t1 - t0 > a.peer_timeout_ns) {
+			atomicMax(a.info + 1, r + 1);
+			return false;
+		}
+	}
+#endif
+	return true;
+}
+
 __device__ __forceinline__ void tb_dss_generic(
 	const DevLayout & lay, const DssArgs & a, int gidx, double * data
 ) {
 	const int m2 = a.members[4 * gidx + 2];
 	const int m3 = a.members[4 * gidx + 3];
+	bool delivered = true;
+	{
+		const unsigned mask = ((unsigned)a.flags[gidx] >> 8) & 0xffffu;
+		if (mask != 0 && a.peer_flags != 0) delivered = tb_dss_wait_peers(a, mask);
+	}
 	const DssRef r0 = tb_dss_ref(lay, a, data, a.members[4 * gidx + 0]);
 	const DssRef r1 = tb_dss_ref(lay, a, data, a.members[4 * gidx + 1]);
 	const DssRef r2 = tb_dss_ref(lay, a, data, m2);
@@ -94,19 +143,22 @@ __device__ __forceinline__ void tb_dss_generic(
 #pragma unroll 4
 	for (int r = rbeg; r < rend; r++) {
 		if (seam && r >= a.uv_row0 && r < a.uv_row1) continue;
-		const double v0 = r0.p[(size_t)r * r0.stride];
-		const double v1 = r1.p[(size_t)r * r1.stride];
+		const double v0 = tb_dss_get(r0, r);
+		const double v1 = tb_dss_get(r1, r);
 		double avg;
 		if (m2 < 0) {
 			avg = 0.5 * (v0 + v1);
 		} else if (m3 < 0) {
-			const double v2 = r2.p[(size_t)r * r2.stride];
+			const double v2 = tb_dss_get(r2, r);
 			avg = (1.0 / 3.0) * (v0 + v1 + v2);
 		} else {
-			const double v2 = r2.p[(size_t)r * r2.stride];
-			const double v3 = r3.p[(size_t)r * r3.stride];
+			const double v2 = tb_dss_get(r2, r);
+			const double v3 = tb_dss_get(r3, r);
 			avg = 0.5 * (0.5 * (v0 + v1) + 0.5 * (v2 + v3));
 		}
+		// a peer never delivered: poison the node rather than average stale data
+		// (tb200_check_errors / the next tb200_step report the rank)
+		if (!delivered) avg = nan("");
 		if (r0.w != 0) r0.w[(size_t)r * r0.stride] = avg;
 		if (r1.w != 0) r1.w[(size_t)r * r1.stride] = avg;
 		if (r2.w != 0) r2.w[(size_t)r * r2.stride] = avg;
@@ -287,9 +339,13 @@ struct PeerPtrs {
 	unsigned long long * flag[TB200_MAX_PEERS];   // peer's flag for this rank
 };
 
+// The last block to finish raises this rank's flag at every neighbour (ticket
+// counter; every thread's stores are fenced at system scope before its block
+// takes a ticket): no separate signal launch.
 __global__ void k_dss_pack_peer(
 	DevLayout lay, const int * send_nodes, const int * send_rank, const int * send_slot,
-	int nsend, const double * data, PeerPtrs pp, int row0, int nsel
+	int nsend, const double * data, PeerPtrs pp, int row0, int nsel,
+	unsigned * ticket, int nranks, int me, unsigned long long seq
 ) {
 	const long long total = (long long)nsend * nsel;
 	for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,42 +357,24 @@ __global__ void k_dss_pack_peer(
 		pp.recv[send_rank[slot]][(size_t)send_slot[slot] * nsel + r] =
 			data[tb_dss_base(lay, m) + (size_t)(row0 + r) * lay.nn];
 	}
-}
-
-// after the pack kernel (stream order: its stores are performed): lane r tells
-// rank r that exchange seq of this rank is complete
-__global__ void k_peer_signal(PeerPtrs pp, int nranks, int me, unsigned long long seq) {
-	const int r = threadIdx.x;
-	if (r < nranks && r != me && pp.flag[r] != 0) {
-		__threadfence_system();
-		*(volatile unsigned long long *)pp.flag[r] = seq;
-		__threadfence_system();
-	}
-}
-
-// lane q waits until source rank q has signalled exchange seq; gives up after
-// timeout_ns and records the failure (reported by tb200_check_errors)
-__global__ void k_peer_wait(
-	const unsigned long long * flags, unsigned mask, unsigned long long seq,
-	unsigned long long timeout_ns, int * info
-) {
-	const int q = threadIdx.x;
-	if (q >= TB200_MAX_PEERS || !((mask >> q) & 1u)) return;
 #ifndef TB200_EMU
-	if (*(volatile int *)(info + 1) != 0) return;      // a peer is gone: do not wait again
-	unsigned long long t0;
-	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-	const volatile unsigned long long * f = flags + q;
-	while (*f < seq) {
-		unsigned long long t1;
-		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-		if (t1 - t0 > timeout_ns) {
-			atomicMax(info + 1, q + 1);
-			break;
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned t = atomicAdd(ticket, 1u);
+		if (t == gridDim.x - 1) {
+			*ticket = 0u;
+			__threadfence_system();
+			for (int r = 0; r < nranks; r++) {
+				if (r != me && pp.flag[r] != 0) {
+					asm volatile("st.release.sys.global.u64 [%0], %1;"
+						:: "l"(pp.flag[r]), "l"(seq) : "memory");
+				}
+			}
 		}
 	}
-	__threadfence_system();
 #endif
 }
+
 
 #endif
