@@ -542,9 +542,40 @@ def main():
         hb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(hb)
+        # the bus alone: the same bytes, host -> device then device -> host, as
+        # plain copies between the pinned buffers and a device buffer on all ranks
+        # at once (what is left of e2e after the step itself is this floor)
+        nbytes = sum(a.nbytes + b.nbytes for a, b in host.values())
+        dbuf = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+        hviews = [torch.from_numpy(x.reshape(-1)) for pair in host.values() for x in pair]
+
+        def bus_only():
+            o = 0
+            for hv in hviews:
+                dbuf[o:o + hv.numel()].copy_(hv, non_blocking=True)
+                o += hv.numel()
+            o = 0
+            for hv in hviews:
+                hv.copy_(dbuf[o:o + hv.numel()], non_blocking=True)
+                o += hv.numel()
+            torch.cuda.synchronize()
+        bus_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            bus_only()
+        barrier()
+        tb = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         e2e = {"value": columns / tt.item(), "unit": "column-steps/s",
                "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()),
-               "ms_per_step": tt.item() * 1e3}
+               "ms_per_step": tt.item() * 1e3,
+               "bus_only_ms": tb.item() * 1e3,
+               "bus_bytes_moved": int(2 * nbytes * (1 if world == 1 else 1)),
+               "note": "bus_only_ms: plain pinned-host <-> device copies of the same arrays "
+                       "(halo and unused component slots included) on all ranks at once"}
+        del dbuf
         ctx.check_errors()
 
     # ---- CPU baseline: the unmodified reference on this host, bounded sample --

@@ -2517,9 +2517,25 @@ struct Member {
 	long long addr; // local node address, -1 when remote
 };
 
+// Order of the members of an averaging group = association order of the average
+// (pairs (0, 1) and (2, 3), then the pair of pair averages; tb200_dss.cuh).  It
+// must not depend on how a panel is cut into patches - a run on 24 patches has
+// to reproduce the bits of the run on 6 - and it has to pair the reference's way:
+// GridCSGLL::ApplyDSS averages across alpha first, then across beta
+// (GridCSGLL.cpp:435-781), so the two members of an alpha pair share the
+// element-local column j.  Key: panel, then element-local j (the element ending
+// at the node first: j = np-1), then element-local i likewise; patch index and
+// position only break ties (slot order of the exchange lists).
 static bool member_less(const tb200_ctx * ctx, const Member & x, const Member & y) {
-	const int px = ctx->patches[x.ppos].index, py = ctx->patches[y.ppos].index;
-	if (px != py) return px < py;
+	const PatchInfo & px = ctx->patches[x.ppos];
+	const PatchInfo & py = ctx->patches[y.ppos];
+	if (px.panel != py.panel) return px.panel < py.panel;
+	const int np = ctx->lay.np;
+	const int jx = (x.ib % np == np - 1) ? 0 : 1, jy = (y.ib % np == np - 1) ? 0 : 1;
+	if (jx != jy) return jx < jy;
+	const int ix = (x.ia % np == np - 1) ? 0 : 1, iy = (y.ia % np == np - 1) ? 0 : 1;
+	if (ix != iy) return ix < iy;
+	if (px.index != py.index) return px.index < py.index;
 	if (x.ib != y.ib) return x.ib < y.ib;
 	return x.ia < y.ia;
 }

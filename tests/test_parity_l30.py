@@ -243,3 +243,36 @@ def test_fused_dss_same_bits_larger_patches(library, monkeypatch, ne, npatch, st
         for idx in res[0][inst]:
             for loc in (0, 1):
                 assert np.array_equal(res[0][inst][idx][loc], res[1][inst][idx][loc])
+
+
+def test_state_does_not_depend_on_the_patch_decomposition(library):
+    """6 patches (one rank) against 24 patches: the averaging groups pair their
+    members by position on the panel (alpha pairs first, as GridCSGLL::ApplyDSS
+    does), not by patch index, so the state after three steps is the same bit
+    for bit - what lets bench.py hold a multi-GPU run to the one-GPU checksums."""
+    from tempestmodel_b200 import grid as G
+    from tempestmodel_b200 import testcases as TC
+    from tempestmodel_b200.model import Model
+    ne, L = 4, 7
+    res = []
+    for npatch in (6, 24):
+        grid = G.GridCSGLL(ne, L, npatch=npatch, ztop=30000.0)
+        model = Model(grid, TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"),
+                      timescheme="strang", dt=300.0, library=library)
+        model.initialize()
+        model.step(3)
+        st = model.download_state(0)
+        nodes = {p: np.zeros((5, 4 * ne, 4 * ne, L)) for p in range(6)}
+        redges = {p: np.zeros((5, 4 * ne, 4 * ne, L + 1)) for p in range(6)}
+        for p in grid.patches:
+            node, redge = st[p.index]
+            sl = (slice(None), slice(4 * p.ea0, 4 * (p.ea0 + p.nea)),
+                  slice(4 * p.eb0, 4 * (p.eb0 + p.neb)))
+            nodes[p.panel][sl] = node[:, 1:-1, 1:-1]
+            redges[p.panel][sl] = redge[:, 1:-1, 1:-1]
+        res.append((nodes, redges))
+        model.ctx.close()
+    for panel in range(6):
+        for c in (0, 1, 2, 4):
+            assert np.array_equal(res[0][0][panel][c], res[1][0][panel][c]), (panel, c)
+        assert np.array_equal(res[0][1][panel][3], res[1][1][panel][3]), panel
