@@ -545,19 +545,13 @@ def main():
         # the bus alone: the same bytes, host -> device then device -> host, as
         # plain copies between the pinned buffers and a device buffer on all ranks
         # at once (what is left of e2e after the step itself is this floor)
-        nbytes = sum(a.nbytes + b.nbytes for a, b in host.values())
+        nbytes = h2d
         dbuf = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
-        hviews = [torch.from_numpy(x.reshape(-1)) for pair in host.values() for x in pair]
+        hbuf = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
 
         def bus_only():
-            o = 0
-            for hv in hviews:
-                dbuf[o:o + hv.numel()].copy_(hv, non_blocking=True)
-                o += hv.numel()
-            o = 0
-            for hv in hviews:
-                hv.copy_(dbuf[o:o + hv.numel()], non_blocking=True)
-                o += hv.numel()
+            dbuf.copy_(hbuf, non_blocking=True)
+            hbuf.copy_(dbuf, non_blocking=True)
             torch.cuda.synchronize()
         bus_only()
         barrier()
@@ -572,10 +566,9 @@ def main():
                "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()),
                "ms_per_step": tt.item() * 1e3,
                "bus_only_ms": tb.item() * 1e3,
-               "bus_bytes_moved": int(2 * nbytes * (1 if world == 1 else 1)),
-               "note": "bus_only_ms: plain pinned-host <-> device copies of the same arrays "
-                       "(halo and unused component slots included) on all ranks at once"}
-        del dbuf
+               "note": "bus_only_ms: one plain pinned-host -> device and one device -> host copy "
+                       "of h2d_bytes_per_step / n_gpus per rank, all ranks at once"}
+        del dbuf, hbuf
         ctx.check_errors()
 
     # ---- CPU baseline: the unmodified reference on this host, bounded sample --
