@@ -173,6 +173,18 @@ CASES["jw_ne4_l30_p24"] = dict(
         "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0", "checksum:cs"]),
     compact=True)
 
+# tracers at L = 30 (config 4's level count): stage records and three Strang steps
+CASES["jwtr_ne2_l30"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "30", "--ztop", "30000", "--pert", "Exp",
+                      "--dt", "200s", "--ntracers", "3"],
+    script=";".join([
+        "addw:0,20000", "dss:0",
+        "dump:ic,0", "copy:0,1", "hexp:0,1,50", "dump:h1,1", "vexp:0,1,50",
+        "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,30",
+        "dump:vi,2", "hasc:1,3,4,200", "dump:hasc,3",
+        "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:3", "dump:st,0"]),
+    geometry_from="jw_ne2_l30", compact=True)
+
 # conservation diagnostics of the reference (Grid::ComputeTotalEnergy,
 # ComputeTotalPotentialEnstrophy, ComputeTotalVerticalMomentum) on the state
 # before and after two steps; only the scalars are stored, geometry and initial
@@ -231,6 +243,12 @@ def _compact(d):
         if leaf in ("refstatenode", "refstateredge", "zlevels", "zinterfaces",
                     "rayleighnode", "rayleighredge"):
             continue
+        if ".inst" in k and leaf == "tracers":
+            v = v.copy()
+            v[:, 0, :, :] = 0.0
+            v[:, -1, :, :] = 0.0
+            v[:, :, 0, :] = 0.0
+            v[:, :, -1, :] = 0.0
         if ".inst" in k and leaf in ("node", "redge"):
             v = v.copy()
             v[:, 0, :, :] = 0.0

@@ -276,3 +276,38 @@ def test_state_does_not_depend_on_the_patch_decomposition(library):
         for c in (0, 1, 2, 4):
             assert np.array_equal(res[0][0][panel][c], res[1][0][panel][c]), (panel, c)
         assert np.array_equal(res[0][1][panel][3], res[1][1][panel][3]), panel
+
+
+def test_tracers_l30(library):
+    """Tracer transport at L = 30 (config 4's level count; general kernels):
+    horizontal transport with the element filter, DSS, implicit column
+    transport with the column filter, hyperdiffusion, three Strang steps."""
+    d = cases.load_case("jwtr_ne2_l30")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "h1", before=("ic", 0)), 1e-11)
+    ctx.v_step_explicit(0, 1, 50.0)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "dss"), 1e-13)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=True), TOL_IMPLICIT)
+    assert_below(dumpctx.compare_tracers(ctx, d, 2, "vi"), 1e-10)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    assert_below(dumpctx.compare_tracers(ctx, d, 3, "hasc"), 1e-12)
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    assert_below(dumpctx.compare_tracers(ctx, d, 0, "st"), 1e-9)
+    ctx.close()
