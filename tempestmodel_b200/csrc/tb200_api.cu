@@ -17,6 +17,9 @@
 #include "tb200_column.cuh"
 #include "tb200_fast.cuh"
 #include "tb200_column_fast.cuh"
+#ifndef TB200_EMU
+#include <cuda.h>
+#endif
 #include "tb200_tracers.cuh"
 #include "tb200_diag.cuh"
 
@@ -105,6 +108,57 @@ static int dupload(tb200_ctx * ctx, T ** p, const std::vector<T> & v) {
 // Grid of a persistent kernel: resident blocks per SM (registers and shared
 // memory both counted by the runtime) times the SM count, so that every block
 // of the launch is resident and walks the same number of elements.
+// Tensor map of a state instance: [nelem * nrows][16] doubles, boxes of whole
+// 128-byte rows, 128-byte swizzle (tb200_tma.cuh).  cuTensorMapEncodeTiled is a
+// driver entry point; it is looked up through the runtime.
+static int make_tensor_map(tb200_ctx * ctx, const double * base, TbMap * out) {
+	const DevLayout & lay = ctx->lay;
+	memset(out, 0, sizeof(TbMap));
+	out->base = base;
+	out->nbox = tb_tma_nbox(lay.nrows);
+	out->boxrows = tb_tma_boxrows(lay.nrows);
+#ifndef TB200_EMU
+	typedef CUresult (*encode_fn)(
+		CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+		const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+		CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static encode_fn encode = 0;
+	if (encode == 0) {
+		void * fn = 0;
+		cudaDriverEntryPointQueryResult qres;
+		TB_CHECK(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		if (fn == 0 || qres != cudaDriverEntryPointSuccess) {
+			TB_FAIL(ctx, "cuTensorMapEncodeTiled is not available in this driver");
+		}
+		encode = (encode_fn)fn;
+	}
+	static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+	const cuuint64_t gdim[2] = {16, (cuuint64_t)lay.nelem * (cuuint64_t)lay.nrows};
+	const cuuint64_t gstride[1] = {128};
+	const cuuint32_t box[2] = {16, (cuuint32_t)out->boxrows};
+	const cuuint32_t estride[2] = {1, 1};
+	const CUresult rc = encode(
+		reinterpret_cast<CUtensorMap *>(out->desc), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+		const_cast<double *>(base), gdim, gstride, box, estride,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+		CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (rc != CUDA_SUCCESS) {
+		char buf[96];
+		snprintf(buf, 96, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+		TB_FAIL(ctx, buf);
+	}
+#endif
+	return 0;
+}
+
+// tensor map of the instance a device pointer belongs to
+static const TbMap & tensor_map_of(const tb200_ctx * ctx, const double * p) {
+	for (size_t m = 0; m < ctx->inst.size(); m++) {
+		if (ctx->inst[m] == p) return ctx->tmaps[m];
+	}
+	return ctx->tmaps[0];
+}
+
 template <typename K>
 static long long persistent_blocks(
 	tb200_ctx * ctx, K kfn, int threads, size_t smem, long long nwork, int reserve_sms = 0
@@ -471,6 +525,10 @@ extern "C" int tb200_commit_layout(tb200_ctx * ctx) {
 	for (int m = 0; m < ctx->cfg.ninstances; m++) {
 		if (dalloc(ctx, &ctx->inst[m], inst_doubles)) return 1;
 		TB_CHECK(ctx, cudaMemset(ctx->inst[m], 0, inst_doubles * sizeof(double)));
+	}
+	ctx->tmaps.resize(ctx->cfg.ninstances);
+	for (int m = 0; m < ctx->cfg.ninstances; m++) {
+		if (make_tensor_map(ctx, ctx->inst[m], &ctx->tmaps[m])) return 1;
 	}
 	ctx->stage_doubles = stage;
 	if (dalloc(ctx, &ctx->d_stage, stage)) return 1;
@@ -1348,6 +1406,10 @@ static int nh_launch(
 			if (fuse && tb_pipe_smem_doubles(lay.nrows, lay.nlev, pb.nsrc, true) * sizeof(double)
 					> 227 * 1024 - 1024) fuse = false;
 			const size_t smem = tb_pipe_smem_doubles(lay.nrows, lay.nlev, pb.nsrc, fuse) * sizeof(double);
+			PipeMaps maps;
+			maps.in = tensor_map_of(ctx, ctx->inst[in]);
+			maps.b0 = tensor_map_of(ctx, pb.nsrc > 0 ? pb.src[0] : ctx->inst[in]);
+			maps.b1 = tensor_map_of(ctx, pb.nsrc > 1 ? pb.src[1] : ctx->inst[in]);
 			if (smem <= 227 * 1024 - 1024) {
 				const dim3 block(TBF_THREADS);
 #ifndef TB200_EMU
@@ -1364,7 +1426,7 @@ static int nh_launch(
 						const dim3 grid((unsigned)fused_blocks(ctx, kfn, TBF_THREADS, smem)); \
 						TB_LAUNCH(kfn, grid, block, smem, ctx->stream, \
 							lay, ctx->tables, ctx->phys, fa, \
-							(const double *)ctx->inst[in], pb, ctx->inst[out], elem_list(ctx, 0), fz); \
+							(const double *)ctx->inst[in], pb, ctx->inst[out], elem_list(ctx, 0), fz, maps); \
 						ctx->launches++; \
 						ctx->writes++; \
 						ctx->fuse_done = true; \
@@ -1381,7 +1443,7 @@ static int nh_launch(
 							(part == 2) ? overlap_reserve() : 0)); \
 						TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream, \
 							lay, ctx->tables, ctx->phys, fa, \
-							(const double *)ctx->inst[in], pb, ctx->inst[out], el, fz); \
+							(const double *)ctx->inst[in], pb, ctx->inst[out], el, fz, maps); \
 						ctx->launches++; \
 						ctx->writes++; \
 					} \
@@ -2332,6 +2394,10 @@ static int hyper_fast(
 	if (smem > 227 * 1024 - 1024) TB_FAIL(ctx, "column too tall for the fused hyperdiffusion kernel");
 	const dim3 block(TBF_THREADS);
 	const FuseArgs fz0 = fuse_args(ctx);
+	PipeMaps maps;
+	maps.in = tensor_map_of(ctx, ctx->inst[fld]);
+	maps.b0 = tensor_map_of(ctx, ctx->inst[has_base ? base : fld]);
+	maps.b1 = maps.b0;
 	if (fuse) {
 		// this launch also averages the in-patch groups of `out` (fused DSS)
 		ctx->fuse_epoch++;
@@ -2344,7 +2410,7 @@ static int hyper_fast(
 			const dim3 grid((unsigned)fused_blocks(ctx, kfn, TBF_THREADS, smem));
 			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
 				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out],
-				elem_list(ctx, 0), fz);
+				elem_list(ctx, 0), fz, maps);
 		} else {
 			auto kfn = k_hyper_pipe<false, true>;
 #ifndef TB200_EMU
@@ -2353,7 +2419,7 @@ static int hyper_fast(
 			const dim3 grid((unsigned)fused_blocks(ctx, kfn, TBF_THREADS, smem));
 			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->tables, ha,
 				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out],
-				elem_list(ctx, 0), fz);
+				elem_list(ctx, 0), fz, maps);
 		}
 		ctx->launches++;
 		ctx->writes++;
@@ -2375,7 +2441,7 @@ static int hyper_fast(
 				(part == 2) ? overlap_reserve() : 0));
 			TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream,
 				lay, ctx->tables, ha,
-				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out], el, fz0);
+				(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out], el, fz0, maps);
 			ctx->launches++;
 			ctx->writes++;
 		}
@@ -2394,7 +2460,7 @@ static int hyper_fast(
 				(part == 2) ? overlap_reserve() : 0));
 			TB_LAUNCH(kfn, grid, block, smem, (part == 2) ? ctx->stream2 : ctx->stream,
 				lay, ctx->tables, ha,
-				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out], el, fz0);
+				(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out], el, fz0, maps);
 			ctx->launches++;
 			ctx->writes++;
 		}

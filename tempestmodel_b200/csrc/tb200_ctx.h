@@ -9,6 +9,7 @@
 
 #include "tb200_platform.h"
 #include "tb200_device.h"
+#include "tb200_tma.cuh"
 #include "../../include/tempest_b200.h"
 
 struct SeamEntry {
@@ -54,6 +55,7 @@ struct tb200_ctx {
 	HostOp hops[TB_NOPS];
 
 	std::vector<double *> inst;       // device state instances
+	std::vector<TbMap> tmaps;         // their tensor maps (bulk tensor copies of the pipelined kernels)
 	std::vector<void *> allocs;       // everything to cudaFree
 
 	// staging for host <-> device layout conversion

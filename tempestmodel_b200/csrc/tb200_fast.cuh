@@ -32,6 +32,7 @@
 #include "tb200_platform.h"
 #include "tb200_device.h"
 #include "tb200_kernels.cuh"
+#include "tb200_tma.cuh"
 
 // ---- per-column constants: colc[(e * TBF_NC + q) * 16 + n] ---------------------
 #define TBF_A0 0       // ContraMetric2DA[0]
@@ -720,6 +721,24 @@ __device__ __forceinline__ void tb_cross_sum2s(
 
 #define TBP_MAXSRC 2
 
+// tensor maps of the instances a pipelined kernel streams: input, up to two
+// stage-base sources (hyperdiffusion: field, base)
+struct PipeMaps {
+	TbMap in;
+	TbMap b0;
+	TbMap b1;
+};
+
+// 1024-byte aligned start of the dynamic shared memory
+__device__ __forceinline__ double * tb_smem_aligned(double * raw) {
+#ifdef TB200_EMU
+	return raw;
+#else
+	const unsigned a = (unsigned)__cvta_generic_to_shared(raw);
+	return raw + (((1024u - (a & 1023u)) & 1023u) >> 3);
+#endif
+}
+
 // Stage base of the pipelined kernel: up to TBP_MAXSRC instances (the update
 // instance itself counts as one when its coefficient is non-zero), combined in
 // Grid::LinearCombineData's order.
@@ -734,26 +753,10 @@ __host__ __device__ inline size_t tb_pipe_smem_doubles(int nrows, int L, int nsr
 	// column constants [2], operator windows [L+1]
 	// (one source: its buffer is doubled and fetched one element ahead)
 	// fused DSS: + beta carry [nrows][2] and corner pair averages [nrows]
-	return (size_t)nrows * 16 * (2 + (nsrc == 1 ? 2 : nsrc)) + (size_t)(6 * L + 6) * 16
-		+ 2 * TBF_NC * 16 + (size_t)(L + 1) * TBF_LWS + (fuse ? (size_t)nrows * 3 : 0);
-}
-
-// cp.async of the rows of thread (kq, i) - its four nodes of every component
-// at levels kq, kq + TBF_KB, ... - from one element of a source instance into
-// a swizzled element buffer
-__device__ __forceinline__ void tb_pipe_fetch(
-	const DevLayout & lay, const double * sp, double * dp, int kq, int i, int L
-) {
-	for (int k = kq; k <= L; k += TBF_KB) {
-#pragma unroll
-		for (int cmp = 0; cmp < 5; cmp++) {
-			if (cmp != 3 && k == L) continue;
-			const int r = lay.rowoff[cmp] + k;
-			const int c0 = (2 * i) ^ (r & 1), c1 = (2 * i + 1) ^ (r & 1);
-			tb_cp16(dp + ((r << 3) | c0) * 2, sp + (size_t)r * 16 + 4 * i);
-			tb_cp16(dp + ((r << 3) | c1) * 2, sp + (size_t)r * 16 + 4 * i + 2);
-		}
-	}
+	// + 1 KiB so that the element buffers start on a 1024-byte boundary (128-byte
+	// swizzle of the bulk tensor copies), + 4 transaction barriers
+	return tb_tma_buffer_doubles(nrows) * (2 + (nsrc == 1 ? 2 : nsrc)) + (size_t)(6 * L + 6) * 16
+		+ 2 * TBF_NC * 16 + (size_t)(L + 1) * TBF_LWS + (fuse ? (size_t)nrows * 3 : 0) + 128 + 4;
 }
 
 // my node pair of the stage base at swizzled element offset off
@@ -1055,7 +1058,8 @@ template <bool DO_V, int NSRC, bool FUSE>
 __global__ void __launch_bounds__(TBF_THREADS, TBP_MINBLOCKS)
 k_nh_stage_pipe(
 	DevLayout lay, DevTables t, DevPhys ph, FastArgs fa,
-	const double * __restrict__ in, PipeBase pb, double * out, ElemList el, FuseArgs fz
+	const double * __restrict__ in, PipeBase pb, double * out, ElemList el, FuseArgs fz,
+	const __grid_constant__ PipeMaps maps
 ) {
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
@@ -1064,14 +1068,16 @@ k_nh_stage_pipe(
 	const int rU = lay.rowoff[0], rV = lay.rowoff[1], rP = lay.rowoff[2];
 	const int rW = lay.rowoff[3], rR = lay.rowoff[4];
 
-	TB_DYN_SMEM(double, sm);
-	const size_t esz = (size_t)nrows * NN;
+	TB_DYN_SMEM(double, sm_raw);
+	double * sm = tb_smem_aligned(sm_raw);
+	const size_t esz = (size_t)nrows * NN;               // element stride in global memory
+	const size_t ebuf = tb_tma_buffer_doubles(nrows);    // element buffer in shared memory
 	double * inb0 = sm;
-	// one source: [2][esz], fetched one element ahead like the input;
-	// two sources: [2][esz], one buffer each, fetched at the start of the element
-	double * bsb0 = sm + 2 * esz;
+	// one source: [2][ebuf], fetched one element ahead like the input;
+	// two sources: [2][ebuf], one buffer each, fetched at the start of the element
+	double * bsb0 = sm + 2 * ebuf;
 	const bool ahead = (NSRC == 1);
-	double * tWn = sm + (2 + (NSRC == 1 ? 2 : NSRC)) * esz;
+	double * tWn = sm + (2 + (NSRC == 1 ? 2 : NSRC)) * ebuf;
 	double * tKE = tWn + (size_t)L * NN;
 	double * tEX = tKE + (size_t)L * NN;
 	double * tFaR = tEX + (size_t)L * NN;
@@ -1083,11 +1089,14 @@ k_nh_stage_pipe(
 	double * slev = scc0 + 2 * TBF_NC * NN;  // [L+1][TBF_LWS] operator windows
 	double * carry = slev + (size_t)(L + 1) * TBF_LWS;   // FUSE: [nrows][2] beta carry of rows i = 1, 2
 	double * aprev = carry + (size_t)nrows * 2;   // FUSE: [nrows] alpha pair average of node (0, 3)
+	// transaction barriers: input slot 0 / 1 (+ its base when fetched ahead, column
+	// constants; slot 0 also the operator windows), the two-source base
+	tb_mbar_t * bars = reinterpret_cast<tb_mbar_t *>(
+		(FUSE ? aprev + (size_t)nrows : slev + (size_t)(L + 1) * TBF_LWS));
 
 	const int tid = threadIdx.x;
 	const int kq = tid >> 2;
 	const int i = tid & 3;
-	const int nchunk = nrows * 8;
 
 	double dxI[4], stI[4];
 #pragma unroll
@@ -1122,22 +1131,27 @@ k_nh_stage_pipe(
 		cur.e = tb_elem(el, w);
 	}
 	long long e = cur.e;
-	{
-		const size_t eb = (size_t)e * esz;
-		for (int q = tid; q < nchunk; q += TBF_THREADS) {
-			const int r = q >> 3, c = q & 7;
-			const int d = ((r << 3) | (c ^ (r & 1))) << 1;
-			tb_cp16(inb0 + d, in + eb + 2 * q);
-			if (ahead) tb_cp16(bsb0 + d, pb.src[0] + eb + 2 * q);
+	(void)in;
+	const unsigned ebytes = tb_tma_element_bytes(maps.in);
+	const unsigned cbytes = TBF_NC * NN * sizeof(double);
+	if (tid == 0) {
+		tb_mbar_init(&bars[0], 1);
+		tb_mbar_init(&bars[1], 1);
+		tb_mbar_init(&bars[2], 1);
+		tb_mbar_fence_init();
+	}
+	__syncthreads();
+	if (tid == 0) {
+		// first element, its column constants and the operator windows
+		tb_mbar_expect(&bars[0], ebytes * (ahead ? 2u : 1u) + cbytes
+			+ (unsigned)((L + 1) * TBF_LWK * sizeof(double)));
+		tb_tma_element(inb0, maps.in, e * nrows, nrows, &bars[0]);
+		if (ahead) tb_tma_element(bsb0, maps.b0, e * nrows, nrows, &bars[0]);
+		tb_bulk_1d(scc0, fa.colc + (size_t)e * TBF_NC * NN, cbytes, &bars[0]);
+		for (int r = 0; r <= L; r++) {
+			tb_bulk_1d(slev + (size_t)r * TBF_LWS, fa.lev + (size_t)r * TBF_LW,
+				TBF_LWK * sizeof(double), &bars[0]);
 		}
-		for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
-			tb_cp16(scc0 + 2 * q, fa.colc + (size_t)e * TBF_NC * NN + 2 * q);
-		}
-		for (int q = tid; q < (L + 1) * (TBF_LWK / 2); q += TBF_THREADS) {
-			const int r = q / (TBF_LWK / 2), c = q % (TBF_LWK / 2);
-			tb_cp16(slev + (size_t)r * TBF_LWS + 2 * c, fa.lev + (size_t)r * TBF_LW + 2 * c);
-		}
-		tb_cp_commit();
 	}
 
 	bool valid = true;
@@ -1155,10 +1169,10 @@ k_nh_stage_pipe(
 			if (has_next) nxt.e = tb_elem(el, w);
 		}
 		const int buf = it & 1;
-		const double * inb = inb0 + (size_t)buf * esz;
+		const double * inb = inb0 + (size_t)buf * ebuf;
 		// the data of this element (issued one iteration ago) has landed, and
 		// every thread is done with the previous element
-		tb_cp_wait<0>();
+		tb_mbar_wait(&bars[buf], (unsigned)(it >> 1) & 1u);
 #if defined(TBF_PUB_ALLFENCE) && !defined(TB200_EMU)
 		if (FUSE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
@@ -1178,39 +1192,28 @@ k_nh_stage_pipe(
 				lag_el.e = -1;
 			}
 		}
-		// stage base.  Every thread fetches exactly the 32 bytes per row it will
-		// combine (its own four nodes).  Two sources: fetched now for this
-		// element, the thread's own cp.async.wait_group is all the
-		// synchronisation the data needs.  One source: fetched below, one
-		// element ahead.
-		const double * bp0 = ahead ? (bsb0 + (size_t)buf * esz) : bsb0;
-		const double * bp1 = bsb0 + esz;
-		if (NSRC == 2) {
-#pragma unroll
-			for (int m = 0; m < NSRC; m++) {
-				tb_pipe_fetch(lay, pb.src[m] + (size_t)e * esz, bsb0 + (size_t)m * esz, kq, i, L);
+		// stage base.  Two sources: fetched now for this element (consumed at the
+		// end of its level loop, behind bars[2]).  One source: fetched below, one
+		// element ahead.  One thread issues the bulk copies.
+		const double * bp0 = ahead ? (bsb0 + (size_t)buf * ebuf) : bsb0;
+		const double * bp1 = bsb0 + ebuf;
+		if (tid == 0) {
+			if (NSRC == 2) {
+				tb_mbar_expect(&bars[2], 2u * ebytes);
+				tb_tma_element(bsb0, maps.b0, e * nrows, nrows, &bars[2]);
+				tb_tma_element(bsb0 + ebuf, maps.b1, e * nrows, nrows, &bars[2]);
 			}
-			tb_cp_commit();
-		}
-		// prefetch the next element of this block into the other buffer
-		{
+			// prefetch the next element of this block into the other buffer
 			if (has_next) {
 				const long long en = nxt.e;
-				const size_t eb = (size_t)en * esz;
-				double * di = inb0 + (size_t)(buf ^ 1) * esz;
-				double * db = bsb0 + (size_t)(buf ^ 1) * esz;
-				for (int q = tid; q < nchunk; q += TBF_THREADS) {
-					const int r = q >> 3, c = q & 7;
-					const int d = ((r << 3) | (c ^ (r & 1))) << 1;
-					tb_cp16(di + d, in + eb + 2 * q);
-					if (ahead) tb_cp16(db + d, pb.src[0] + eb + 2 * q);
+				tb_mbar_expect(&bars[buf ^ 1], ebytes * (ahead ? 2u : 1u) + cbytes);
+				tb_tma_element(inb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nrows, nrows, &bars[buf ^ 1]);
+				if (ahead) {
+					tb_tma_element(bsb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nrows, nrows, &bars[buf ^ 1]);
 				}
-				double * dc = scc0 + (size_t)(buf ^ 1) * TBF_NC * NN;
-				for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
-					tb_cp16(dc + 2 * q, fa.colc + (size_t)en * TBF_NC * NN + 2 * q);
-				}
+				tb_bulk_1d(scc0 + (size_t)(buf ^ 1) * TBF_NC * NN,
+					fa.colc + (size_t)en * TBF_NC * NN, cbytes, &bars[buf ^ 1]);
 			}
-			tb_cp_commit();
 		}
 		if (FUSE) tb_alpha_finish(lag_el, out, esz, nrows, aprev, tid, areg);
 
@@ -1240,16 +1243,16 @@ k_nh_stage_pipe(
 			double dxUa[4], dxUb[4], theta[4];
 			{
 				double v[4], w0[4], wp[4], p[4], r[4], um[4], up[4], vm[4], vp[4];
-				tb_ld4s(inb + (size_t)(rU + kc) * NN, (rU + kc) & 1, i, u);
-				tb_ld4s(inb + (size_t)(rV + kc) * NN, (rV + kc) & 1, i, v);
-				tb_ld4s(inb + (size_t)(rW + kc) * NN, (rW + kc) & 1, i, w0);
-				tb_ld4s(inb + (size_t)(rW + kc + 1) * NN, (rW + kc + 1) & 1, i, wp);
-				tb_ld4s(inb + (size_t)(rP + kc) * NN, (rP + kc) & 1, i, p);
-				tb_ld4s(inb + (size_t)(rR + kc) * NN, (rR + kc) & 1, i, r);
-				tb_ld4s(inb + (size_t)(rU + km) * NN, (rU + km) & 1, i, um);
-				tb_ld4s(inb + (size_t)(rU + kp) * NN, (rU + kp) & 1, i, up);
-				tb_ld4s(inb + (size_t)(rV + km) * NN, (rV + km) & 1, i, vm);
-				tb_ld4s(inb + (size_t)(rV + kp) * NN, (rV + kp) & 1, i, vp);
+				tb_ld4s(inb + (size_t)(rU + kc) * NN, (rU + kc) & 7, i, u);
+				tb_ld4s(inb + (size_t)(rV + kc) * NN, (rV + kc) & 7, i, v);
+				tb_ld4s(inb + (size_t)(rW + kc) * NN, (rW + kc) & 7, i, w0);
+				tb_ld4s(inb + (size_t)(rW + kc + 1) * NN, (rW + kc + 1) & 7, i, wp);
+				tb_ld4s(inb + (size_t)(rP + kc) * NN, (rP + kc) & 7, i, p);
+				tb_ld4s(inb + (size_t)(rR + kc) * NN, (rR + kc) & 7, i, r);
+				tb_ld4s(inb + (size_t)(rU + km) * NN, (rU + km) & 7, i, um);
+				tb_ld4s(inb + (size_t)(rU + kp) * NN, (rU + kp) & 7, i, up);
+				tb_ld4s(inb + (size_t)(rV + km) * NN, (rV + km) & 7, i, vm);
+				tb_ld4s(inb + (size_t)(rV + kp) * NN, (rV + kp) & 7, i, vp);
 				double cA0[4], cA1[4], cB1[4], cJ[4];
 				tb_ld4(cc + TBF_A0 * NN, cA0);
 				tb_ld4(cc + TBF_A1 * NN, cA1);
@@ -1305,7 +1308,7 @@ k_nh_stage_pipe(
 #pragma unroll
 			for (int jh = 0; jh < 2; jh++) {
 				double dCovDaUb[2], dCovDaUx[2], dDaP[2], dDaKE[2], dDaRhoFluxA[2], dDaPressureFluxA[2];
-				tb_cross_sum2s(inb + (size_t)(rV + kc) * NN, (rV + kc) & 1, jh, dxI, dCovDaUb);
+				tb_cross_sum2s(inb + (size_t)(rV + kc) * NN, (rV + kc) & 7, jh, dxI, dCovDaUb);
 				tb_cross_sum2s(tWn + (size_t)kc * NN, tp, jh, dxI, dCovDaUx);
 				tb_cross_sum2s(tEX + (size_t)kc * NN, tp, jh, dxI, dDaP);
 				tb_cross_sum2s(tKE + (size_t)kc * NN, tp, jh, dxI, dDaKE);
@@ -1320,11 +1323,11 @@ k_nh_stage_pipe(
 				// stage base: my node pair of the four level components
 				const int ch = 2 * i + jh;
 				double bU[2], bV[2], bP[2], bR[2];
-				if (jh == 0 && NSRC == 2) tb_cp_wait<1>();     // my base chunks have landed
-				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rU + kc) * NN + ((ch ^ ((rU + kc) & 1)) << 1), bU);
-				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rV + kc) * NN + ((ch ^ ((rV + kc) & 1)) << 1), bV);
-				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rP + kc) * NN + ((ch ^ ((rP + kc) & 1)) << 1), bP);
-				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rR + kc) * NN + ((ch ^ ((rR + kc) & 1)) << 1), bR);
+				if (jh == 0 && NSRC == 2) tb_mbar_wait(&bars[2], (unsigned)it & 1u);   // the bases have landed
+				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rU + kc) * NN + ((ch ^ ((rU + kc) & 7)) << 1), bU);
+				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rV + kc) * NN + ((ch ^ ((rV + kc) & 7)) << 1), bV);
+				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rP + kc) * NN + ((ch ^ ((rP + kc) & 7)) << 1), bP);
+				tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rR + kc) * NN + ((ch ^ ((rR + kc) & 7)) << 1), bR);
 
 				double zx[2];
 #pragma unroll
@@ -1398,14 +1401,14 @@ k_nh_stage_pipe(
 					const double se0 = LV(TBF_SE), se1 = LV(TBF_SE1);
 					// the windows of the skipped sides (top / bottom level) are zero
 					double u0[2], v0[2], um[2], up[2], vm[2], vp[2], w0[2], wp[2];
-					tb_ld2(inb + (size_t)(rU + kc) * NN + ((ch ^ ((rU + kc) & 1)) << 1), u0);
-					tb_ld2(inb + (size_t)(rV + kc) * NN + ((ch ^ ((rV + kc) & 1)) << 1), v0);
-					tb_ld2(inb + (size_t)(rU + km) * NN + ((ch ^ ((rU + km) & 1)) << 1), um);
-					tb_ld2(inb + (size_t)(rU + kp) * NN + ((ch ^ ((rU + kp) & 1)) << 1), up);
-					tb_ld2(inb + (size_t)(rV + km) * NN + ((ch ^ ((rV + km) & 1)) << 1), vm);
-					tb_ld2(inb + (size_t)(rV + kp) * NN + ((ch ^ ((rV + kp) & 1)) << 1), vp);
-					tb_ld2(inb + (size_t)(rW + kc) * NN + ((ch ^ ((rW + kc) & 1)) << 1), w0);
-					tb_ld2(inb + (size_t)(rW + kc + 1) * NN + ((ch ^ ((rW + kc + 1) & 1)) << 1), wp);
+					tb_ld2(inb + (size_t)(rU + kc) * NN + ((ch ^ ((rU + kc) & 7)) << 1), u0);
+					tb_ld2(inb + (size_t)(rV + kc) * NN + ((ch ^ ((rV + kc) & 7)) << 1), v0);
+					tb_ld2(inb + (size_t)(rU + km) * NN + ((ch ^ ((rU + km) & 7)) << 1), um);
+					tb_ld2(inb + (size_t)(rU + kp) * NN + ((ch ^ ((rU + kp) & 7)) << 1), up);
+					tb_ld2(inb + (size_t)(rV + km) * NN + ((ch ^ ((rV + km) & 7)) << 1), vm);
+					tb_ld2(inb + (size_t)(rV + kp) * NN + ((ch ^ ((rV + kp) & 7)) << 1), vp);
+					tb_ld2(inb + (size_t)(rW + kc) * NN + ((ch ^ ((rW + kc) & 7)) << 1), w0);
+					tb_ld2(inb + (size_t)(rW + kc + 1) * NN + ((ch ^ ((rW + kc + 1) & 7)) << 1), wp);
 #pragma unroll
 					for (int q = 0; q < 2; q++) {
 						const int j = 2 * jh + q;
@@ -1477,7 +1480,7 @@ k_nh_stage_pipe(
 				}
 			} else {
 				{
-					const int par = (rW + k) & 1;
+					const int par = (rW + k) & 7;
 					double lo[2], hi[2];
 					tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rW + k) * NN + (((2 * i) ^ par) << 1), lo);
 					tb_pipe_base2<NSRC>(pb, inb, bp0, bp1, (rW + k) * NN + (((2 * i + 1) ^ par) << 1), hi);
@@ -1544,8 +1547,8 @@ struct HyperFastArgs {
 __host__ __device__ inline size_t tb_hyper_smem_doubles(int nrows, int L, bool has_base, bool fuse = false) {
 	// fld[2] (+ base[2]), tiles GaP, GaR, JUa, Div, Curl [L], GaW [L+1], column constants [2]
 	// (+ fused DSS: beta carry [nrows][2], corner pair averages [nrows])
-	return (size_t)nrows * 16 * (has_base ? 4 : 2) + (size_t)(6 * L + 1) * 16 + 2 * TBF_NC * 16
-		+ (fuse ? (size_t)nrows * 3 : 0);
+	return tb_tma_buffer_doubles(nrows) * (has_base ? 4 : 2) + (size_t)(6 * L + 1) * 16 + 2 * TBF_NC * 16
+		+ (fuse ? (size_t)nrows * 3 : 0) + 128 + 4;
 }
 
 // beta-direction sum over my own row: o = sum_s x[s] * c[s*4 + j] (c = dx) or
@@ -1569,7 +1572,8 @@ template <bool HAS_BASE, bool FUSE>
 __global__ void __launch_bounds__(TBF_THREADS, 2)
 k_hyper_pipe(
 	DevLayout lay, DevTables t, HyperFastArgs ha,
-	const double * __restrict__ fld, const double * base, double * out, ElemList el, FuseArgs fz
+	const double * __restrict__ fld, const double * base, double * out, ElemList el, FuseArgs fz,
+	const __grid_constant__ PipeMaps maps
 ) {
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
@@ -1577,11 +1581,13 @@ k_hyper_pipe(
 	const int rU = lay.rowoff[0], rV = lay.rowoff[1], rP = lay.rowoff[2];
 	const int rW = lay.rowoff[3], rR = lay.rowoff[4];
 
-	TB_DYN_SMEM(double, sm);
-	const size_t esz = (size_t)nrows * NN;
+	TB_DYN_SMEM(double, sm_raw);
+	double * sm = tb_smem_aligned(sm_raw);
+	const size_t esz = (size_t)nrows * NN;               // element stride in global memory
+	const size_t ebuf = tb_tma_buffer_doubles(nrows);    // element buffer in shared memory
 	double * fb0 = sm;
-	double * bb0 = sm + 2 * esz;
-	double * tGP = sm + (HAS_BASE ? 4 : 2) * esz;
+	double * bb0 = sm + 2 * ebuf;
+	double * tGP = sm + (HAS_BASE ? 4 : 2) * ebuf;
 	double * tGR = tGP + (size_t)L * NN;
 	double * tJU = tGR + (size_t)L * NN;
 	double * tDV = tJU + (size_t)L * NN;
@@ -1590,11 +1596,11 @@ k_hyper_pipe(
 	double * scc0 = tGW + (size_t)(L + 1) * NN;  // [2][TBF_NC][16]
 	double * carry = scc0 + 2 * TBF_NC * NN;     // FUSE: [nrows][2]
 	double * aprev = carry + (size_t)nrows * 2;  // FUSE: [nrows]
+	tb_mbar_t * bars = reinterpret_cast<tb_mbar_t *>(FUSE ? aprev + (size_t)nrows : carry);
 
 	const int tid = threadIdx.x;
 	const int kq = tid >> 2;
 	const int i = tid & 3;
-	const int nchunk = nrows * 8;
 
 	double dxI[4], stI[4];
 #pragma unroll
@@ -1627,18 +1633,20 @@ k_hyper_pipe(
 		cur.e = tb_elem(el, w);
 	}
 	long long e = cur.e;
-	{
-		const size_t eb = (size_t)e * esz;
-		for (int q = tid; q < nchunk; q += TBF_THREADS) {
-			const int r = q >> 3, c = q & 7;
-			const int d = ((r << 3) | (c ^ (r & 1))) << 1;
-			tb_cp16(fb0 + d, fld + eb + 2 * q);
-			if (HAS_BASE) tb_cp16(bb0 + d, base + eb + 2 * q);
-		}
-		for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
-			tb_cp16(scc0 + 2 * q, ha.colc + (size_t)e * TBF_NC * NN + 2 * q);
-		}
-		tb_cp_commit();
+	(void)fld; (void)base;
+	const unsigned ebytes = tb_tma_element_bytes(maps.in);
+	const unsigned cbytes = TBF_NC * NN * sizeof(double);
+	if (tid == 0) {
+		tb_mbar_init(&bars[0], 1);
+		tb_mbar_init(&bars[1], 1);
+		tb_mbar_fence_init();
+	}
+	__syncthreads();
+	if (tid == 0) {
+		tb_mbar_expect(&bars[0], ebytes * (HAS_BASE ? 2u : 1u) + cbytes);
+		tb_tma_element(fb0, maps.in, e * nrows, nrows, &bars[0]);
+		if (HAS_BASE) tb_tma_element(bb0, maps.b0, e * nrows, nrows, &bars[0]);
+		tb_bulk_1d(scc0, ha.colc + (size_t)e * TBF_NC * NN, cbytes, &bars[0]);
 	}
 
 	bool valid = true;
@@ -1655,9 +1663,9 @@ k_hyper_pipe(
 			if (has_next) nxt.e = tb_elem(el, w);
 		}
 		const int buf = it & 1;
-		const double * fb = fb0 + (size_t)buf * esz;
-		const double * bb = bb0 + (size_t)buf * esz;
-		tb_cp_wait<0>();
+		const double * fb = fb0 + (size_t)buf * ebuf;
+		const double * bb = bb0 + (size_t)buf * ebuf;
+		tb_mbar_wait(&bars[buf], (unsigned)(it >> 1) & 1u);
 #if defined(TBF_PUB_ALLFENCE) && !defined(TB200_EMU)
 		if (FUSE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
@@ -1677,24 +1685,16 @@ k_hyper_pipe(
 				lag_el.e = -1;
 			}
 		}
-		{
-			if (has_next) {
-				const long long en = nxt.e;
-				const size_t eb = (size_t)en * esz;
-				double * df = fb0 + (size_t)(buf ^ 1) * esz;
-				double * db = bb0 + (size_t)(buf ^ 1) * esz;
-				for (int q = tid; q < nchunk; q += TBF_THREADS) {
-					const int r = q >> 3, c = q & 7;
-					const int d = ((r << 3) | (c ^ (r & 1))) << 1;
-					tb_cp16(df + d, fld + eb + 2 * q);
-					if (HAS_BASE) tb_cp16(db + d, base + eb + 2 * q);
-				}
-				double * dc = scc0 + (size_t)(buf ^ 1) * TBF_NC * NN;
-				for (int q = tid; q < TBF_NC * 8; q += TBF_THREADS) {
-					tb_cp16(dc + 2 * q, ha.colc + (size_t)en * TBF_NC * NN + 2 * q);
-				}
+		if (tid == 0 && has_next) {
+			// the next element of this block, by bulk tensor copies
+			const long long en = nxt.e;
+			tb_mbar_expect(&bars[buf ^ 1], ebytes * (HAS_BASE ? 2u : 1u) + cbytes);
+			tb_tma_element(fb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nrows, nrows, &bars[buf ^ 1]);
+			if (HAS_BASE) {
+				tb_tma_element(bb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nrows, nrows, &bars[buf ^ 1]);
 			}
-			tb_cp_commit();
+			tb_bulk_1d(scc0 + (size_t)(buf ^ 1) * TBF_NC * NN,
+				ha.colc + (size_t)en * TBF_NC * NN, cbytes, &bars[buf ^ 1]);
 		}
 		if (FUSE) tb_alpha_finish(lag_el, out, esz, nrows, aprev, tid, areg);
 
@@ -1730,8 +1730,8 @@ k_hyper_pipe(
 			{
 				double x[4], da[4], gaP[4], gaR[4], gaW[4], jua[4];
 				// rho-theta
-				tb_ld4s(fb + (size_t)(rP + kc) * NN, (rP + kc) & 1, i, x);
-				tb_cross_sum4s(fb + (size_t)(rP + kc) * NN, (rP + kc) & 1, dxI, da);
+				tb_ld4s(fb + (size_t)(rP + kc) * NN, (rP + kc) & 7, i, x);
+				tb_cross_sum4s(fb + (size_t)(rP + kc) * NN, (rP + kc) & 7, dxI, da);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					const double dDa = da[j] * dInvDA;
@@ -1740,8 +1740,8 @@ k_hyper_pipe(
 					gbP[j] = cJ[j] * (cB0[j] * dDa + cB1[j] * dDb);
 				}
 				// rho
-				tb_ld4s(fb + (size_t)(rR + kc) * NN, (rR + kc) & 1, i, x);
-				tb_cross_sum4s(fb + (size_t)(rR + kc) * NN, (rR + kc) & 1, dxI, da);
+				tb_ld4s(fb + (size_t)(rR + kc) * NN, (rR + kc) & 7, i, x);
+				tb_cross_sum4s(fb + (size_t)(rR + kc) * NN, (rR + kc) & 7, dxI, da);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					const double dDa = da[j] * dInvDA;
@@ -1750,8 +1750,8 @@ k_hyper_pipe(
 					gbR[j] = cJ[j] * (cB0[j] * dDa + cB1[j] * dDb);
 				}
 				// w (interfaces; JacobianREdge = Jacobian for this metric)
-				tb_ld4s(fb + (size_t)(rW + kw) * NN, (rW + kw) & 1, i, x);
-				tb_cross_sum4s(fb + (size_t)(rW + kw) * NN, (rW + kw) & 1, dxI, da);
+				tb_ld4s(fb + (size_t)(rW + kw) * NN, (rW + kw) & 7, i, x);
+				tb_cross_sum4s(fb + (size_t)(rW + kw) * NN, (rW + kw) & 7, dxI, da);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					const double dDa = da[j] * dInvDA;
@@ -1760,8 +1760,8 @@ k_hyper_pipe(
 					gbW[j] = cJ[j] * (cB0[j] * dDa + cB1[j] * dDb);
 				}
 				// velocities: J2D * contravariant components (GridPatchCSGLL.cpp:1207-1218)
-				tb_ld4s(fb + (size_t)(rU + kc) * NN, (rU + kc) & 1, i, u);
-				tb_ld4s(fb + (size_t)(rV + kc) * NN, (rV + kc) & 1, i, v);
+				tb_ld4s(fb + (size_t)(rU + kc) * NN, (rU + kc) & 7, i, u);
+				tb_ld4s(fb + (size_t)(rV + kc) * NN, (rV + kc) & 7, i, v);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					jua[j] = cJ2[j] * (+cA0[j] * u[j] + cA1[j] * v[j]);
@@ -1780,7 +1780,7 @@ k_hyper_pipe(
 			{
 				double ua[4], o[4];
 				tb_cross_sum4s(tGP + (size_t)kc * NN, tp, stI, ua);
-				if (HAS_BASE) tb_ld4s(bb + (size_t)(rP + kc) * NN, (rP + kc) & 1, i, o);
+				if (HAS_BASE) tb_ld4s(bb + (size_t)(rP + kc) * NN, (rP + kc) & 7, i, o);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					const double dUpdateA = ua[j] * dInvDA;
@@ -1790,7 +1790,7 @@ k_hyper_pipe(
 				}
 				if (lact) tb_out4<FUSE>(cur, carry, out + ebase, esz, rP + k, i, o);
 				tb_cross_sum4s(tGR + (size_t)kc * NN, tp, stI, ua);
-				if (HAS_BASE) tb_ld4s(bb + (size_t)(rR + kc) * NN, (rR + kc) & 1, i, o);
+				if (HAS_BASE) tb_ld4s(bb + (size_t)(rR + kc) * NN, (rR + kc) & 7, i, o);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					const double dUpdateA = ua[j] * dInvDA;
@@ -1800,7 +1800,7 @@ k_hyper_pipe(
 				}
 				if (lact) tb_out4<FUSE>(cur, carry, out + ebase, esz, rR + k, i, o);
 				tb_cross_sum4s(tGW + (size_t)kw * NN, tpw, stI, ua);
-				if (HAS_BASE) tb_ld4s(bb + (size_t)(rW + kw) * NN, (rW + kw) & 1, i, o);
+				if (HAS_BASE) tb_ld4s(bb + (size_t)(rW + kw) * NN, (rW + kw) & 7, i, o);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
 					const double dUpdateA = ua[j] * dInvDA;
@@ -1815,7 +1815,7 @@ k_hyper_pipe(
 			double dv[4], cl[4];
 			{
 				double daUb[4], daJUa[4];
-				tb_cross_sum4s(fb + (size_t)(rV + kc) * NN, (rV + kc) & 1, dxI, daUb);
+				tb_cross_sum4s(fb + (size_t)(rV + kc) * NN, (rV + kc) & 7, dxI, daUb);
 				tb_cross_sum4s(tJU + (size_t)kc * NN, tp, dxI, daJUa);
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
@@ -1840,8 +1840,8 @@ k_hyper_pipe(
 				tb_cross_sum4s(tDV + (size_t)kc * NN, tp, stI, daDiv);
 				tb_cross_sum4s(tCL + (size_t)kc * NN, tp, stI, daCurl);
 				if (HAS_BASE) {
-					tb_ld4s(bb + (size_t)(rU + kc) * NN, (rU + kc) & 1, i, oU);
-					tb_ld4s(bb + (size_t)(rV + kc) * NN, (rV + kc) & 1, i, oV);
+					tb_ld4s(bb + (size_t)(rU + kc) * NN, (rU + kc) & 7, i, oU);
+					tb_ld4s(bb + (size_t)(rV + kc) * NN, (rV + kc) & 7, i, oV);
 				}
 #pragma unroll
 				for (int j = 0; j < 4; j++) {

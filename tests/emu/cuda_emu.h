@@ -31,6 +31,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __shared__ static
 
 struct int4 { int x, y, z, w; };
