@@ -756,7 +756,8 @@ __host__ __device__ inline size_t tb_pipe_smem_doubles(int nrows, int L, int nsr
 	// + 1 KiB so that the element buffers start on a 1024-byte boundary (128-byte
 	// swizzle of the bulk tensor copies), + 4 transaction barriers
 	return tb_tma_buffer_doubles(nrows) * (2 + (nsrc == 1 ? 2 : nsrc)) + (size_t)(6 * L + 6) * 16
-		+ 2 * TBF_NC * 16 + (size_t)(L + 1) * TBF_LWS + (fuse ? (size_t)nrows * 3 : 0) + 128 + 4;
+		+ 2 * TBF_NC * 16 + (size_t)(L + 1) * TBF_LWS + (fuse ? (size_t)nrows * 3 : 0) + 128 + 16
+		+ 2 * 4 * 16;
 }
 
 // my node pair of the stage base at swizzled element offset off
@@ -1093,10 +1094,29 @@ k_nh_stage_pipe(
 	// constants; slot 0 also the operator windows), the two-source base
 	tb_mbar_t * bars = reinterpret_cast<tb_mbar_t *>(
 		(FUSE ? aprev + (size_t)nrows : slev + (size_t)(L + 1) * TBF_LWS));
+	// Decoupled warps (single level pass, no fused DSS): no block barrier inside
+	// the element loop.  A warp only waits for the data it reads: the element
+	// (bars[0 / 1], by bulk copy), the (u x zeta)_xi row of the level below its
+	// first one (zdone, from the warp below; kept in zb, double-buffered by
+	// element parity so that a warp running ahead does not overwrite it), and the
+	// issuing thread for every warp to have left a buffer before it is refilled
+	// (empty[0 / 1], four arrivals).  Warps drift up to one element apart instead
+	// of meeting twice per element.
+	tb_mbar_t * empty = bars + 3;              // [2]
+	tb_mbar_t * zdone = bars + 5;              // [3 warp boundaries][2 element parities]
+	double * zb = reinterpret_cast<double *>(bars + 16);   // [2][4][16]
+	// Measured on the B200 (ne = 120, L = 30) and left off: 1.32 / 1.40 / 1.44 ms
+	// against 1.21 / 1.25 / 1.28 ms with the two block barriers per element.
+#if defined(TBF_DECOUPLED) && !defined(TB200_EMU)
+	const bool decoupled = !FUSE && (L <= TBF_KB);
+#else
+	const bool decoupled = false;
+#endif
 
 	const int tid = threadIdx.x;
 	const int kq = tid >> 2;
 	const int i = tid & 3;
+	const int warp = tid >> 5;
 
 	double dxI[4], stI[4];
 #pragma unroll
@@ -1138,6 +1158,9 @@ k_nh_stage_pipe(
 		tb_mbar_init(&bars[0], 1);
 		tb_mbar_init(&bars[1], 1);
 		tb_mbar_init(&bars[2], 1);
+		tb_mbar_init(&empty[0], TBF_THREADS / 32);
+		tb_mbar_init(&empty[1], TBF_THREADS / 32);
+		for (int q = 0; q < 6; q++) tb_mbar_init(&zdone[q], 1);
 		tb_mbar_fence_init();
 	}
 	__syncthreads();
@@ -1173,10 +1196,7 @@ k_nh_stage_pipe(
 		// the data of this element (issued one iteration ago) has landed, and
 		// every thread is done with the previous element
 		tb_mbar_wait(&bars[buf], (unsigned)(it >> 1) & 1u);
-#if defined(TBF_PUB_ALLFENCE) && !defined(TB200_EMU)
-		if (FUSE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
-#endif
-		__syncthreads();
+		if (!decoupled) __syncthreads();
 		if (FUSE) {
 			// the previous element's raw values are stored: publish it; finish the
 			// alpha edge and corners of the element produced TBF_LAG iterations ago
@@ -1197,7 +1217,16 @@ k_nh_stage_pipe(
 		// element ahead.  One thread issues the bulk copies.
 		const double * bp0 = ahead ? (bsb0 + (size_t)buf * ebuf) : bsb0;
 		const double * bp1 = bsb0 + ebuf;
-		if (tid == 0) {
+		// decoupled, one source or none: the prefetch is issued after this warp's
+		// level loop (below), when every warp has long left the other buffer
+#ifdef TBF_ISSUE_LATE
+		const bool issue_late = decoupled && (NSRC != 2);
+#else
+		const bool issue_late = false;
+#endif
+		if (tid == 0 && !issue_late) {
+			// every warp has left the previous element (its buffers are refilled now)
+			if (decoupled && it > 0) tb_mbar_wait(&empty[buf ^ 1], (unsigned)((it - 1) >> 1) & 1u);
 			if (NSRC == 2) {
 				tb_mbar_expect(&bars[2], 2u * ebytes);
 				tb_tma_element(bsb0, maps.b0, e * nrows, nrows, &bars[2]);
@@ -1390,6 +1419,9 @@ k_nh_stage_pipe(
 					tb_out2<FUSE>(cur, carry, out + ebase, esz, rR + k, i, jh, bR);
 					tb_out2<FUSE>(cur, carry, out + ebase, esz, rP + k, i, jh, bP);
 					tb_st2(tZX + (size_t)k * NN + ((ch ^ tp) << 1), zx);
+					if (decoupled && (k & 7) == 7) {
+						tb_st2(zb + ((size_t)(it & 1) * 4 + warp) * NN + 4 * i + 2 * jh, zx);
+					}
 					if (k < 3) {
 						tb_st2(sUn + k * NN + 4 * i + 2 * jh, bU);
 						tb_st2(sVn + k * NN + 4 * i + 2 * jh, bV);
@@ -1451,7 +1483,25 @@ k_nh_stage_pipe(
 				}
 			}
 		}
-		__syncthreads();
+		if (decoupled) {
+			// this warp's tiles are complete; tell the warp above, wait for the one below
+			__syncwarp();
+			if ((tid & 31) == 0 && warp < 3) tb_mbar_arrive(&zdone[warp * 2 + (it & 1)]);
+			if (issue_late && tid == 0 && has_next) {
+				if (it > 0) tb_mbar_wait(&empty[buf ^ 1], (unsigned)((it - 1) >> 1) & 1u);
+				const long long en = nxt.e;
+				tb_mbar_expect(&bars[buf ^ 1], ebytes * (ahead ? 2u : 1u) + cbytes);
+				tb_tma_element(inb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nrows, nrows, &bars[buf ^ 1]);
+				if (ahead) {
+					tb_tma_element(bsb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nrows, nrows, &bars[buf ^ 1]);
+				}
+				tb_bulk_1d(scc0 + (size_t)(buf ^ 1) * TBF_NC * NN,
+					fa.colc + (size_t)en * TBF_NC * NN, cbytes, &bars[buf ^ 1]);
+			}
+			if (warp > 0) tb_mbar_wait(&zdone[(warp - 1) * 2 + (it & 1)], (unsigned)(it >> 1) & 1u);
+		} else {
+			__syncthreads();
+		}
 
 		// ---- vertical velocity on interfaces (:1612-1660) --------------------------
 		for (int k = kq; k <= L; k += TBF_KB) {
@@ -1488,7 +1538,12 @@ k_nh_stage_pipe(
 				}
 				if (k < L) {
 					double zm[4], z0[4];
-					tb_ld4s(tZX + (size_t)(k - 1) * NN, (k - 1) & 1, i, zm);
+					if (decoupled && (k & 7) == 0) {
+						// the level below belongs to the warp below
+						tb_ld4(zb + ((size_t)(it & 1) * 4 + (warp - 1)) * NN + 4 * i, zm);
+					} else {
+						tb_ld4s(tZX + (size_t)(k - 1) * NN, (k - 1) & 1, i, zm);
+					}
 					tb_ld4s(tZX + (size_t)k * NN, k & 1, i, z0);
 #pragma unroll
 					for (int j = 0; j < 4; j++) {
@@ -1500,6 +1555,11 @@ k_nh_stage_pipe(
 				}
 			}
 			tb_out4<FUSE>(cur, carry, out + ebase, esz, rW + k, i, bW);
+		}
+		if (decoupled) {
+			// this warp has left the element (its buffers, tiles and boundary row)
+			__syncwarp();
+			if ((tid & 31) == 0) tb_mbar_arrive(&empty[buf]);
 		}
 #undef LV
 		if (FUSE && behind < TBF_LAG) behind++;

@@ -39,6 +39,7 @@ __device__ __forceinline__ void tb_mbar_init(tb_mbar_t *, int) {}
 __device__ __forceinline__ void tb_mbar_fence_init() {}
 __device__ __forceinline__ void tb_mbar_expect(tb_mbar_t *, unsigned) {}
 __device__ __forceinline__ void tb_mbar_wait(tb_mbar_t *, unsigned) {}
+__device__ __forceinline__ void tb_mbar_arrive(tb_mbar_t *) {}
 
 // element rows [row0, row0 + nrows) of the instance -> swizzled buffer
 __device__ __forceinline__ void tb_tma_element(
@@ -77,6 +78,11 @@ __device__ __forceinline__ void tb_mbar_fence_init() {
 __device__ __forceinline__ void tb_mbar_expect(tb_mbar_t * bar, unsigned bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
 		:: "r"(tb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// plain arrival (release at CTA scope): "this warp is done with ..."
+__device__ __forceinline__ void tb_mbar_arrive(tb_mbar_t * bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tb_smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void tb_mbar_wait(tb_mbar_t * bar, unsigned parity) {
