@@ -352,8 +352,6 @@ def main():
     # pinned host copies of instance 0 (reference layout) for the end-to-end leg
     host = {}
     h2d = d2h = 0
-    if args.tracers > 0:
-        args.no_e2e = True       # the end-to-end leg moves the dry state only
     if not args.no_e2e:
         for p in model.local:
             node, redge = model._host[p.index]
@@ -361,12 +359,19 @@ def main():
             pe = torch.empty(redge.shape, dtype=torch.float64).pin_memory()
             pn.numpy()[...] = node
             pe.numpy()[...] = redge
-            host[p.index] = (pn.numpy(), pe.numpy())
+            pt = None
+            if args.tracers > 0:
+                tr = model._host_tracers[p.index]
+                ptt = torch.empty(tr.shape, dtype=torch.float64).pin_memory()
+                ptt.numpy()[...] = tr
+                pt = ptt.numpy()
+            host[p.index] = (pn.numpy(), pe.numpy(), pt)
             interior = (p.wa - 2) * (p.wb - 2)
-            # U,V,rho-theta,rho on levels + W on interfaces
-            h2d += interior * (4 * L + (L + 1)) * 8
-            d2h += interior * (4 * L + (L + 1)) * 8
+            # U,V,rho-theta,rho (and the tracers) on levels + W on interfaces
+            h2d += interior * ((4 + args.tracers) * L + (L + 1)) * 8
+            d2h += interior * ((4 + args.tracers) * L + (L + 1)) * 8
     model._host = {}
+    model._host_tracers = {}
 
     def global_checksum():
         """Grid::Checksum of instance 0 over all ranks (U, V, rho-theta, W, rho)."""
@@ -486,10 +491,13 @@ def main():
         pass
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     fast = ctx.fast_path()
-    if args.tracers > 0:
-        fast = (False, "tracers take the general kernels", fast[2])
+    if args.tracers > 0 and os.environ.get("TB200_TRACER_KERNEL") == "generic":
+        fast = (False, "TB200_TRACER_KERNEL=generic: tracers (and the state with them) take the general kernels", fast[2])
+    stage_kernel = "k_nh_stage_pipe<true,1>" if fast[0] else "k_nh_explicit<4,true,true>"
+    if fast[0] and args.tracers > 0:
+        stage_kernel += " + k_tracer_stage (state rows / tracer rows of one stage pass)"
     roofline = {"bound": "hbm",
-                "kernel": "k_nh_stage_pipe<true,1>" if fast[0] else "k_nh_explicit<4,true,true>",
+                "kernel": stage_kernel,
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
@@ -521,13 +529,17 @@ def main():
             # every array is enqueued, bus copies and layout conversions overlap,
             # the host waits once for the result
             for p in model.local:
-                pn, pe = host[p.index]
-                ctx.upload_state_async(p.index, 0, pn, pe, None)
+                pn, pe, pt = host[p.index]
+                ctx.upload_state_async(p.index, 0, pn, pe, pt)
             model.step(1, check=False)
             for p in model.local:
-                pn, pe = host[p.index]
-                ctx.download_state_async(p.index, 0, pn, pe, None, False)
+                pn, pe, pt = host[p.index]
+                ctx.download_state_async(p.index, 0, pn, pe, pt, False)
             ctx.transfer_sync()
+        # the kernel timings above left copies of the state in the work instances:
+        # the Strang carry-over (instance 1) restarts from a zero increment, so that
+        # every end-to-end step advances the uploaded state by a regular step
+        ctx.zero(1)
         e2e_step()
         ksteps = max(2, min(args.steps, 5))
         barrier()

@@ -21,7 +21,12 @@
 #include <cuda.h>
 #endif
 #include "tb200_tracers.cuh"
+#include "tb200_tracers_fast.cuh"
 #include "tb200_diag.cuh"
+
+static_assert(TBT_C_JAC == TBF_JAC && TBT_C_A2 == TBF_A2 && TBT_C_B2 == TBF_B2
+	&& TBT_C_X0 == TBF_X0 && TBT_C_X2 == TBF_X2 && TBT_C_NC == TBF_NC
+	&& TBT_L_SE == TBF_SE && TBT_L_LW == TBF_LW, "column-constant indices of tb200_tracers.cuh");
 
 #define TB_CHECK(ctx, call) \
 	do { \
@@ -115,8 +120,8 @@ static int make_tensor_map(tb200_ctx * ctx, const double * base, TbMap * out) {
 	const DevLayout & lay = ctx->lay;
 	memset(out, 0, sizeof(TbMap));
 	out->base = base;
-	out->nbox = tb_tma_nbox(lay.nrows);
-	out->boxrows = tb_tma_boxrows(lay.nrows);
+	out->nbox = tb_tma_nbox(lay.nrows_state);
+	out->boxrows = tb_tma_boxrows(lay.nrows_state);
 #ifndef TB200_EMU
 	typedef CUresult (*encode_fn)(
 		CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -265,6 +270,7 @@ static int split_join(tb200_ctx * ctx) {
 // the next launch of a pipelined kernel may average the in-patch groups itself
 static bool fuse_enabled(const tb200_ctx * ctx) {
 	if (!ctx->fuse_ready || !ctx->fuse_want || split_enabled(ctx)) return false;
+	if (ctx->lay.ntr > 0) return false;                           // tracer rows are averaged by the group kernels
 	if (ctx->lay.nrows > TBF_AROWS * TBF_THREADS) return false;   // rows per thread of the alpha phase
 	// Off unless TB200_DSS_FUSED=1: measured on the B200 (ne = 120, L = 30) the
 	// fused kernels cut the DRAM traffic of stage + DSS from 8.5 to 5.7 GB but run
@@ -1364,14 +1370,87 @@ static StageBase stage_base_out() {
 	return sb;
 }
 
+// Tracers ride the column-constant path too (tb200_tracers_fast.cuh) unless
+// TB200_TRACER_KERNEL=generic asks for the general kernels (tests).
+static bool fast_with_tracers(const tb200_ctx * ctx) {
+	if (ctx->lay.ntr == 0) return true;
+	const char * force = getenv("TB200_TRACER_KERNEL");
+	return !(force != 0 && strcmp(force, "generic") == 0);
+}
+
+// The explicit stage on the column-constant path?  (state rows: k_nh_stage_pipe /
+// k_nh_stage_fast; tracer rows: k_tracer_stage)
+static bool stage_fast_ok(tb200_ctx * ctx) {
+	if (fast_prepare(ctx)) return false;
+	return ctx->fast_state == 1 && fast_with_tracers(ctx);
+}
+
+static int nh_launch_state(
+	tb200_ctx * ctx, int in, int out, double dt, bool do_h, bool do_v,
+	const StageBase & sb
+);
+
+// Tracer rows of an explicit stage on the fast path: stage base, horizontal
+// transport and the element-wise positivity filter in one pass (do_h); the
+// vertical explicit step leaves tracers alone (VerticalDynamicsFEM.cpp:616-1159),
+// only a stage base that is not already in place is formed.
+static int tracer_stage_fast(
+	tb200_ctx * ctx, int in, int out, double dt, bool do_h, const StageBase & sb
+) {
+	const DevLayout & lay = ctx->lay;
+	if (!do_h) {
+		if (sb.use_out) return 0;
+		CombineArgs ca;
+		memset(&ca, 0, sizeof(ca));
+		ca.cdst = sb.cdst;
+		ca.scale_dst = sb.scale_dst;
+		ca.nsrc = sb.nsrc;
+		for (int m = 0; m < sb.nsrc; m++) { ca.src[m] = sb.src[m]; ca.coeff[m] = sb.coeff[m]; }
+		return launch_combine(ctx, ca, out, lay.nrows_state, lay.nrows);
+	}
+	if (ctx->d_area_node == 0) TB_FAIL(ctx, "element areas not uploaded (tracer filter)");
+	TracerFastArgs ta;
+	ta.colc = ctx->d_colc;
+	ta.lev = ctx->d_lev;
+	ta.inv_da = ctx->d_inv_da;
+	ta.inv_db = ctx->d_inv_db;
+	ta.area = ctx->d_area_node;
+	ta.dt = dt;
+	const ElemList el = elem_list(ctx, 0);
+	if (el.n == 0) return 0;
+	auto kfn = k_tracer_stage;
+	TB_LAUNCH(kfn, dim3((unsigned)el.n), dim3(TBT_THREADS), 0, ctx->stream,
+		lay, ctx->tables, ta, sb, (const double *)ctx->inst[in], ctx->inst[out], el);
+	ctx->launches++;
+	ctx->writes++;
+	TB_LAUNCH_CHECK(ctx);
+	return 0;
+}
+
+// One explicit stage (either plugin or both) of state and tracers.  *filtered
+// tells the caller that HorizontalDynamicsFEM::FilterNegativeTracers has been
+// applied to the tracers of `out` already.
 static int nh_launch(
+	tb200_ctx * ctx, int in, int out, double dt, bool do_h, bool do_v,
+	const StageBase & sb, bool * filtered = 0
+) {
+	if (filtered != 0) *filtered = false;
+	if (check_ops(ctx)) return 1;
+	if (fast_prepare(ctx)) return 1;
+	if (nh_launch_state(ctx, in, out, dt, do_h, do_v, sb)) return 1;
+	if (ctx->lay.ntr > 0 && stage_fast_ok(ctx)) {
+		if (tracer_stage_fast(ctx, in, out, dt, do_h, sb)) return 1;
+		if (filtered != 0 && do_h) *filtered = true;
+	}
+	return 0;
+}
+
+static int nh_launch_state(
 	tb200_ctx * ctx, int in, int out, double dt, bool do_h, bool do_v,
 	const StageBase & sb
 ) {
 	const DevLayout & lay = ctx->lay;
-	if (check_ops(ctx)) return 1;
-	if (fast_prepare(ctx)) return 1;
-	if (ctx->fast_state == 1 && lay.ntr == 0) {
+	if (stage_fast_ok(ctx)) {
 		FastArgs fa;
 		fa.colc = ctx->d_colc;
 		fa.lev = ctx->d_lev;
@@ -1403,9 +1482,9 @@ static int nh_launch(
 		if (do_h && fits && !(nopipe != 0 && strcmp(nopipe, "fast") == 0)) {
 			// DSS of `out` follows: the kernel averages the in-patch groups itself
 			bool fuse = do_v && fuse_enabled(ctx);
-			if (fuse && tb_pipe_smem_doubles(lay.nrows, lay.nlev, pb.nsrc, true) * sizeof(double)
+			if (fuse && tb_pipe_smem_doubles(lay.nrows_state, lay.nlev, pb.nsrc, true) * sizeof(double)
 					> 227 * 1024 - 1024) fuse = false;
-			const size_t smem = tb_pipe_smem_doubles(lay.nrows, lay.nlev, pb.nsrc, fuse) * sizeof(double);
+			const size_t smem = tb_pipe_smem_doubles(lay.nrows_state, lay.nlev, pb.nsrc, fuse) * sizeof(double);
 			PipeMaps maps;
 			maps.in = tensor_map_of(ctx, ctx->inst[in]);
 			maps.b0 = tensor_map_of(ctx, pb.nsrc > 0 ? pb.src[0] : ctx->inst[in]);
@@ -1548,7 +1627,9 @@ extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 			(const double *)ctx->inst[in], ctx->inst[out], dt, ctx->cfg.g);
 		TB_KERNEL_CHECK(ctx);
 	} else {
-		if (nh_launch(ctx, in, out, dt, true, false, stage_base_out())) return 1;
+		bool filtered = false;
+		if (nh_launch(ctx, in, out, dt, true, false, stage_base_out(), &filtered)) return 1;
+		if (filtered) return 0;
 	}
 	return tb200_filter_negative_tracers(ctx, out);
 }
@@ -1570,11 +1651,13 @@ extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double d
 		return tb200_h_step_explicit(ctx, in, out, dt);
 	}
 	if (in == out) TB_FAIL(ctx, "HorizontalDynamics Step must have iDataInitial != iDataUpdate");
-	if (ctx->lay.ntr > 0) {
+	if (ctx->lay.ntr > 0 && !stage_fast_ok(ctx)) {
 		// the tracer filter sits between the two plugins in the reference
 		if (tb200_h_step_explicit(ctx, in, out, dt)) return 1;
 		return tb200_v_step_explicit(ctx, in, out, dt);
 	}
+	// (fast path with tracers: the vertical explicit step does not touch tracers,
+	// so the filter commutes with it and is applied by the tracer kernel)
 	TimingScope ts(ctx, "HorizontalStepNonhydrostaticPrimitive");
 	return nh_launch(ctx, in, out, dt, true, true, stage_base_out());
 }
@@ -1616,7 +1699,7 @@ extern "C" int tb200_hv_step_explicit_combine(
 	if (ncoeff > ni) TB_FAIL(ctx, "Too many elements in coefficient vector.");
 	const bool fusable =
 		(ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && (ctx->lay.nlev > 1)
-		&& (ctx->lay.ntr == 0) && (in != out);
+		&& (ctx->lay.ntr == 0 || stage_fast_ok(ctx)) && (in != out);
 	if (!fusable) {
 		if (tb200_lincomb(ctx, coeff, ncoeff, out, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
 		return tb200_hv_step_explicit(ctx, in, out, dt);
@@ -1674,8 +1757,62 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 // (VerticalDynamicsFEM.cpp:1528-1536, 1637)
 static int column_tracers(tb200_ctx * ctx, int in, int out, double dt) {
 	const DevLayout & lay = ctx->lay;
-	if (need_metric3d(ctx, "tracer column update")) return 1;
+	if (fast_prepare(ctx)) return 1;
+	const bool fastm = (ctx->fast_state == 1) && fast_with_tracers(ctx);
+	if (!fastm && need_metric3d(ctx, "tracer column update")) return 1;
+	const char * forcek = getenv("TB200_TRACER_COLUMN_KERNEL");   // "ws": general kernel, column-constant metric
+	if (fastm && !(forcek != 0 && strcmp(forcek, "ws") == 0)) {
+		// tridiagonal kernel, up to 6 tracers per pass
+		TracerColumnFastArgs fa;
+		fa.col_node = ctx->d_col_node;
+		fa.col_dups = ctx->d_col_dups;
+		fa.ncols = ctx->ncols;
+		fa.colc = ctx->d_colc;
+		fa.lev = ctx->d_lev;
+		fa.w_old = ctx->d_wold;
+		fa.dt = dt;
+		fa.info = ctx->d_info;
+		for (int c0 = 0; c0 < lay.ntr; c0 += 6) {
+			fa.c0 = c0;
+			const int nt = std::min(6, lay.ntr - c0);
+			int threads = 64;
+			size_t smem = tb_tracer_column_smem_doubles(lay.nlev, nt, threads) * sizeof(double);
+			if (smem > 100 * 1024) {
+				threads = 32;
+				smem = tb_tracer_column_smem_doubles(lay.nlev, nt, threads) * sizeof(double);
+			}
+			if (smem > 227 * 1024) TB_FAIL(ctx, "column too tall for the tracer column kernel");
+			const dim3 grid((ctx->ncols + threads - 1) / threads), block(threads);
+#ifndef TB200_EMU
+#define TB_TRC_ATTR(kfn) TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#else
+#define TB_TRC_ATTR(kfn)
+#endif
+#define TB_TRC_LAUNCH(N) { \
+				auto kfn = k_column_tracers_fast<N>; \
+				TB_TRC_ATTR(kfn); \
+				TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, fa, \
+					(const double *)ctx->inst[in], (const double *)ctx->inst[out], \
+					(const double *)ctx->inst[in], ctx->inst[out]); }
+			switch (nt) {
+				case 1: TB_TRC_LAUNCH(1) break;
+				case 2: TB_TRC_LAUNCH(2) break;
+				case 3: TB_TRC_LAUNCH(3) break;
+				case 4: TB_TRC_LAUNCH(4) break;
+				case 5: TB_TRC_LAUNCH(5) break;
+				default: TB_TRC_LAUNCH(6) break;
+			}
+#undef TB_TRC_LAUNCH
+#undef TB_TRC_ATTR
+			ctx->launches++;
+			ctx->writes++;
+			TB_LAUNCH_CHECK(ctx);
+		}
+		return tb200_v_filter_negative_tracers(ctx, out);
+	}
 	TracerColumnArgs ta;
+	ta.colc = fastm ? ctx->d_colc : 0;
+	ta.lev = fastm ? ctx->d_lev : 0;
 	ta.col_node = ctx->d_col_node;
 	ta.col_dups = ctx->d_col_dups;
 	ta.ws = ctx->d_ws;
@@ -1823,6 +1960,21 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 	return 0;
 }
 
+// Tracer rows of Grid::LinearCombineData({+1, -1}): inst[old] = inst[upd] - inst[old]
+// (old holds the tracers from before the column update and its filter)
+static int tracer_increment(tb200_ctx * ctx, int upd, int old) {
+	const DevLayout & lay = ctx->lay;
+	if (lay.ntr == 0) return 0;
+	CombineArgs ca;
+	memset(&ca, 0, sizeof(ca));
+	ca.cdst = -1.0;
+	ca.scale_dst = 1;
+	ca.nsrc = 1;
+	ca.src[0] = ctx->inst[upd];
+	ca.coeff[0] = +1.0;
+	return launch_combine(ctx, ca, old, lay.nrows_state, lay.nrows);
+}
+
 // CopyData(src -> dst) followed by StepImplicit(dst, dst): the column solve
 // reads src and writes rho-theta, w, rho of dst (every node is a solved column
 // or the duplicate of one), so only the rows the solve leaves alone (u, v) are
@@ -1832,7 +1984,7 @@ extern "C" int tb200_copy_v_step_implicit(tb200_ctx * ctx, int src, int dst, dou
 	const DevLayout & lay = ctx->lay;
 	const bool solve = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && lay.nlev > 1
 		&& !ctx->cfg.fully_explicit;
-	if (src == dst || !solve || lay.ntr > 0 || fast_prepare(ctx) || ctx->fast_state != 1
+	if (src == dst || !solve || !fast_with_tracers(ctx) || fast_prepare(ctx) || ctx->fast_state != 1
 		|| getenv("TB200_COLUMN_KERNEL") != 0) {
 		if (tb200_copy(ctx, src, dst, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
 		return tb200_v_step_implicit(ctx, dst, dst, dt);
@@ -1845,6 +1997,8 @@ extern "C" int tb200_copy_v_step_implicit(tb200_ctx * ctx, int src, int dst, dou
 	ca.scale_dst = 0;
 	// rows of u and v (components 0 and 1 are adjacent)
 	if (launch_combine(ctx, ca, dst, lay.rowoff[0], lay.rowoff[1] + lay.rowlev[1])) return 1;
+	// the tracer update subtracts from the copy (VerticalDynamicsFEM.cpp:4265-4281)
+	if (launch_combine(ctx, ca, dst, lay.nrows_state, lay.nrows)) return 1;
 	return tb200_v_step_implicit(ctx, src, dst, dt);
 }
 
@@ -1858,7 +2012,7 @@ extern "C" int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst
 	const DevLayout & lay = ctx->lay;
 	const bool solve = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && lay.nlev > 1
 		&& !ctx->cfg.fully_explicit;
-	if (src == dst || !solve || lay.ntr > 0 || fast_prepare(ctx) || ctx->fast_state != 1
+	if (src == dst || !solve || !fast_with_tracers(ctx) || fast_prepare(ctx) || ctx->fast_state != 1
 		|| getenv("TB200_COLUMN_KERNEL") != 0) {
 		if (tb200_copy_v_step_implicit(ctx, src, dst, dt)) return 1;
 		const double fin[2] = {+1.0, -1.0};
@@ -1875,6 +2029,7 @@ extern "C" int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst
 	ca.scale_dst = 0;
 	const int uv0 = lay.rowoff[0], uv1 = lay.rowoff[1] + lay.rowlev[1];
 	if (launch_combine(ctx, ca, dst, uv0, uv1)) return 1;
+	if (launch_combine(ctx, ca, dst, lay.nrows_state, lay.nrows)) return 1;
 	ctx->column_inc = ctx->inst[src];
 	const int rc = tb200_v_step_implicit(ctx, src, dst, dt);
 	ctx->column_inc = 0;
@@ -1883,6 +2038,7 @@ extern "C" int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst
 	CombineArgs zero;
 	memset(&zero, 0, sizeof(zero));
 	if (launch_combine(ctx, zero, src, uv0, uv1)) return 1;
+	if (tracer_increment(ctx, dst, src)) return 1;
 	ctx->uvzero_inst = src;
 	ctx->uvzero_writes = ctx->writes;
 	return 0;
@@ -1898,7 +2054,7 @@ extern "C" int tb200_v_step_implicit_inc_available(tb200_ctx * ctx) {
 	const DevLayout & lay = ctx->lay;
 	const bool solve = (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && lay.nlev > 1
 		&& !ctx->cfg.fully_explicit;
-	if (!solve || lay.ntr > 0 || fast_prepare(ctx) || ctx->fast_state != 1
+	if (!solve || !fast_with_tracers(ctx) || fast_prepare(ctx) || ctx->fast_state != 1
 		|| getenv("TB200_COLUMN_KERNEL") != 0 || getenv("TB200_CARRY_FULL") != 0) {
 		return 0;
 	}
@@ -1909,6 +2065,15 @@ extern "C" int tb200_v_step_implicit_inc(tb200_ctx * ctx, int inst, int inc, dou
 	if (check_inst2(ctx, inst, inc)) return 1;
 	const DevLayout & lay = ctx->lay;
 	if (inst == inc || !tb200_v_step_implicit_inc_available(ctx)) return 2;
+	if (lay.ntr > 0) {
+		// the tracers before the column update: the increment is formed from them
+		CombineArgs keep;
+		memset(&keep, 0, sizeof(keep));
+		keep.nsrc = 1;
+		keep.src[0] = ctx->inst[inst];
+		keep.coeff[0] = 1.0;
+		if (launch_combine(ctx, keep, inc, lay.nrows_state, lay.nrows)) return 1;
+	}
 	ctx->column_inc = ctx->inst[inc];
 	const int rc = tb200_v_step_implicit(ctx, inst, inst, dt);
 	ctx->column_inc = 0;
@@ -1918,6 +2083,7 @@ extern "C" int tb200_v_step_implicit_inc(tb200_ctx * ctx, int inst, int inc, dou
 	CombineArgs zero;
 	memset(&zero, 0, sizeof(zero));
 	if (launch_combine(ctx, zero, inc, uv0, uv1)) return 1;
+	if (tracer_increment(ctx, inst, inc)) return 1;
 	ctx->uvzero_inst = inc;
 	ctx->uvzero_writes = ctx->writes;
 	return 0;
@@ -2366,7 +2532,44 @@ static bool hyper_fast_ok(tb200_ctx * ctx) {
 	if (fast_prepare(ctx)) return false;
 	const char * force = getenv("TB200_HYPER_KERNEL");
 	if (force != 0 && strcmp(force, "generic") == 0) return false;
-	return ctx->fast_state == 1 && ctx->lay.ntr == 0;
+	return ctx->fast_state == 1 && fast_with_tracers(ctx);
+}
+
+// out = (base >= 0 ? inst[base] : 0) - dt nu L(inst[fld]) on the tracer rows
+// (+ the positivity filter of HorizontalDynamicsFEM.cpp:2717 after the last pass)
+static int hyper_tracers_fast(
+	tb200_ctx * ctx, int fld, int base, int out, double dt, double nus, bool scale, bool filter
+) {
+	const DevLayout & lay = ctx->lay;
+	if (lay.ntr == 0) return 0;
+	if (filter && ctx->d_area_node == 0) TB_FAIL(ctx, "element areas not uploaded (tracer filter)");
+	HyperFastArgs ha;
+	memset(&ha, 0, sizeof(ha));
+	ha.colc = ctx->d_colc;
+	ha.inv_da = ctx->d_inv_da;
+	ha.inv_db = ctx->d_inv_db;
+	ha.nu_scale = ctx->d_nu_scale;
+	ha.dt = dt;
+	ha.nu_scalar = nus;
+	ha.scale_nu = scale ? 1 : 0;
+	const ElemList el = elem_list(ctx, 0);
+	if (el.n == 0) return 0;
+	const double * area = filter ? ctx->d_area_node : 0;
+	if (base >= 0) {
+		auto kfn = k_tracer_hyper<true>;
+		TB_LAUNCH(kfn, dim3((unsigned)el.n), dim3(TBT_THREADS), 0, ctx->stream,
+			lay, ctx->tables, ha, area,
+			(const double *)ctx->inst[fld], (const double *)ctx->inst[base], ctx->inst[out], el);
+	} else {
+		auto kfn = k_tracer_hyper<false>;
+		TB_LAUNCH(kfn, dim3((unsigned)el.n), dim3(TBT_THREADS), 0, ctx->stream,
+			lay, ctx->tables, ha, area,
+			(const double *)ctx->inst[fld], (const double *)0, ctx->inst[out], el);
+	}
+	ctx->launches++;
+	ctx->writes++;
+	TB_LAUNCH_CHECK(ctx);
+	return 0;
 }
 
 // out = (base >= 0 ? inst[base] : 0) - dt nu L(inst[fld]), all prognostic fields
@@ -2388,9 +2591,9 @@ static int hyper_fast(
 	ha.xz = ctx->cfg.cartesian_xz;
 	const bool has_base = (base >= 0);
 	bool fuse = fuse_enabled(ctx);
-	if (fuse && tb_hyper_smem_doubles(lay.nrows, lay.nlev, has_base, true) * sizeof(double)
+	if (fuse && tb_hyper_smem_doubles(lay.nrows_state, lay.nlev, has_base, true) * sizeof(double)
 			> 227 * 1024 - 1024) fuse = false;
-	const size_t smem = tb_hyper_smem_doubles(lay.nrows, lay.nlev, has_base, fuse) * sizeof(double);
+	const size_t smem = tb_hyper_smem_doubles(lay.nrows_state, lay.nlev, has_base, fuse) * sizeof(double);
 	if (smem > 227 * 1024 - 1024) TB_FAIL(ctx, "column too tall for the fused hyperdiffusion kernel");
 	const dim3 block(TBF_THREADS);
 	const FuseArgs fz0 = fuse_args(ctx);
@@ -2500,6 +2703,7 @@ static int h_step_after_subcycle_impl(
 		ctx->fuse_want = true;
 		ctx->fuse_done = false;
 		int rc = hyper_fast(ctx, in, -1, work, 1.0, 1.0, 1.0, 1.0, false);
+		if (rc == 0) rc = hyper_tracers_fast(ctx, in, -1, work, 1.0, 1.0, false, false);
 		ctx->want_split = false;
 		if (rc == 0) rc = dss_instance(ctx, work, all, ctx->fuse_done);
 		if (split_join(ctx)) return 1;
@@ -2507,6 +2711,7 @@ static int h_step_after_subcycle_impl(
 		ctx->want_split = want;
 		ctx->fuse_done = false;
 		rc = hyper_fast(ctx, work, in, out, -dt, c.nu_scalar, c.nu_div, c.nu_vort, true);
+		if (rc == 0) rc = hyper_tracers_fast(ctx, work, in, out, -dt, c.nu_scalar, true, true);
 		ctx->want_split = false;
 		ctx->fuse_want = false;
 		if (rc == 0) rc = dss_instance(ctx, out, all, ctx->fuse_done);

@@ -1065,13 +1065,14 @@ k_nh_stage_pipe(
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
 	const double dt = fa.dt;
-	const int nrows = lay.nrows;
+	const int nrows = lay.nrows_state;                   // rows the kernel handles (tracer rows follow)
+	const long long nstride = lay.nrows;                 // rows per element in global memory
 	const int rU = lay.rowoff[0], rV = lay.rowoff[1], rP = lay.rowoff[2];
 	const int rW = lay.rowoff[3], rR = lay.rowoff[4];
 
 	TB_DYN_SMEM(double, sm_raw);
 	double * sm = tb_smem_aligned(sm_raw);
-	const size_t esz = (size_t)nrows * NN;               // element stride in global memory
+	const size_t esz = (size_t)nstride * NN;             // element stride in global memory
 	const size_t ebuf = tb_tma_buffer_doubles(nrows);    // element buffer in shared memory
 	double * inb0 = sm;
 	// one source: [2][ebuf], fetched one element ahead like the input;
@@ -1168,8 +1169,8 @@ k_nh_stage_pipe(
 		// first element, its column constants and the operator windows
 		tb_mbar_expect(&bars[0], ebytes * (ahead ? 2u : 1u) + cbytes
 			+ (unsigned)((L + 1) * TBF_LWK * sizeof(double)));
-		tb_tma_element(inb0, maps.in, e * nrows, nrows, &bars[0]);
-		if (ahead) tb_tma_element(bsb0, maps.b0, e * nrows, nrows, &bars[0]);
+		tb_tma_element(inb0, maps.in, e * nstride, nrows, &bars[0]);
+		if (ahead) tb_tma_element(bsb0, maps.b0, e * nstride, nrows, &bars[0]);
 		tb_bulk_1d(scc0, fa.colc + (size_t)e * TBF_NC * NN, cbytes, &bars[0]);
 		for (int r = 0; r <= L; r++) {
 			tb_bulk_1d(slev + (size_t)r * TBF_LWS, fa.lev + (size_t)r * TBF_LW,
@@ -1229,16 +1230,16 @@ k_nh_stage_pipe(
 			if (decoupled && it > 0) tb_mbar_wait(&empty[buf ^ 1], (unsigned)((it - 1) >> 1) & 1u);
 			if (NSRC == 2) {
 				tb_mbar_expect(&bars[2], 2u * ebytes);
-				tb_tma_element(bsb0, maps.b0, e * nrows, nrows, &bars[2]);
-				tb_tma_element(bsb0 + ebuf, maps.b1, e * nrows, nrows, &bars[2]);
+				tb_tma_element(bsb0, maps.b0, e * nstride, nrows, &bars[2]);
+				tb_tma_element(bsb0 + ebuf, maps.b1, e * nstride, nrows, &bars[2]);
 			}
 			// prefetch the next element of this block into the other buffer
 			if (has_next) {
 				const long long en = nxt.e;
 				tb_mbar_expect(&bars[buf ^ 1], ebytes * (ahead ? 2u : 1u) + cbytes);
-				tb_tma_element(inb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nrows, nrows, &bars[buf ^ 1]);
+				tb_tma_element(inb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nstride, nrows, &bars[buf ^ 1]);
 				if (ahead) {
-					tb_tma_element(bsb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nrows, nrows, &bars[buf ^ 1]);
+					tb_tma_element(bsb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nstride, nrows, &bars[buf ^ 1]);
 				}
 				tb_bulk_1d(scc0 + (size_t)(buf ^ 1) * TBF_NC * NN,
 					fa.colc + (size_t)en * TBF_NC * NN, cbytes, &bars[buf ^ 1]);
@@ -1491,9 +1492,9 @@ k_nh_stage_pipe(
 				if (it > 0) tb_mbar_wait(&empty[buf ^ 1], (unsigned)((it - 1) >> 1) & 1u);
 				const long long en = nxt.e;
 				tb_mbar_expect(&bars[buf ^ 1], ebytes * (ahead ? 2u : 1u) + cbytes);
-				tb_tma_element(inb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nrows, nrows, &bars[buf ^ 1]);
+				tb_tma_element(inb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nstride, nrows, &bars[buf ^ 1]);
 				if (ahead) {
-					tb_tma_element(bsb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nrows, nrows, &bars[buf ^ 1]);
+					tb_tma_element(bsb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nstride, nrows, &bars[buf ^ 1]);
 				}
 				tb_bulk_1d(scc0 + (size_t)(buf ^ 1) * TBF_NC * NN,
 					fa.colc + (size_t)en * TBF_NC * NN, cbytes, &bars[buf ^ 1]);
@@ -1637,13 +1638,14 @@ k_hyper_pipe(
 ) {
 	const int NP = 4, NN = 16;
 	const int L = lay.nlev;
-	const int nrows = lay.nrows;
+	const int nrows = lay.nrows_state;                   // rows the kernel handles (tracer rows follow)
+	const long long nstride = lay.nrows;                 // rows per element in global memory
 	const int rU = lay.rowoff[0], rV = lay.rowoff[1], rP = lay.rowoff[2];
 	const int rW = lay.rowoff[3], rR = lay.rowoff[4];
 
 	TB_DYN_SMEM(double, sm_raw);
 	double * sm = tb_smem_aligned(sm_raw);
-	const size_t esz = (size_t)nrows * NN;               // element stride in global memory
+	const size_t esz = (size_t)nstride * NN;             // element stride in global memory
 	const size_t ebuf = tb_tma_buffer_doubles(nrows);    // element buffer in shared memory
 	double * fb0 = sm;
 	double * bb0 = sm + 2 * ebuf;
@@ -1704,8 +1706,8 @@ k_hyper_pipe(
 	__syncthreads();
 	if (tid == 0) {
 		tb_mbar_expect(&bars[0], ebytes * (HAS_BASE ? 2u : 1u) + cbytes);
-		tb_tma_element(fb0, maps.in, e * nrows, nrows, &bars[0]);
-		if (HAS_BASE) tb_tma_element(bb0, maps.b0, e * nrows, nrows, &bars[0]);
+		tb_tma_element(fb0, maps.in, e * nstride, nrows, &bars[0]);
+		if (HAS_BASE) tb_tma_element(bb0, maps.b0, e * nstride, nrows, &bars[0]);
 		tb_bulk_1d(scc0, ha.colc + (size_t)e * TBF_NC * NN, cbytes, &bars[0]);
 	}
 
@@ -1749,9 +1751,9 @@ k_hyper_pipe(
 			// the next element of this block, by bulk tensor copies
 			const long long en = nxt.e;
 			tb_mbar_expect(&bars[buf ^ 1], ebytes * (HAS_BASE ? 2u : 1u) + cbytes);
-			tb_tma_element(fb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nrows, nrows, &bars[buf ^ 1]);
+			tb_tma_element(fb0 + (size_t)(buf ^ 1) * ebuf, maps.in, en * nstride, nrows, &bars[buf ^ 1]);
 			if (HAS_BASE) {
-				tb_tma_element(bb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nrows, nrows, &bars[buf ^ 1]);
+				tb_tma_element(bb0 + (size_t)(buf ^ 1) * ebuf, maps.b0, en * nstride, nrows, &bars[buf ^ 1]);
 			}
 			tb_bulk_1d(scc0 + (size_t)(buf ^ 1) * TBF_NC * NN,
 				ha.colc + (size_t)en * TBF_NC * NN, cbytes, &bars[buf ^ 1]);

@@ -29,7 +29,21 @@ struct TracerColumnArgs {
 	int kl;                   // 2 vo - 1
 	const double * w_old;     // [e][L+1][NN]: w before the implicit solve
 	int * info;
+	// column-constant metric (tb200_fast.cuh) instead of the stored 3-D arrays:
+	// colc [e][15][NN], lev [L+1][TBF_LW]; 0 = read the arrays of DevGeom
+	const double * colc;
+	const double * lev;
 };
+
+// entries of the column constants / level rows this kernel reads (tb200_fast.cuh)
+#define TBT_C_JAC 3
+#define TBT_C_A2 6
+#define TBT_C_B2 7
+#define TBT_C_X0 8
+#define TBT_C_X2 9
+#define TBT_C_NC 15
+#define TBT_L_SE 18
+#define TBT_L_LW 32
 
 __host__ __device__ inline int tb_tracer_ws_entries(int L, int kl) {
 	return 8 * (L + 1) + (3 * kl + 1) * L;
@@ -78,6 +92,27 @@ __global__ void k_column_tracers(
 	const double * wNew = st_out + ebase + (size_t)lay.rowoff[WIx] * NN + nd;
 	const double * wOld = ta.w_old + g3e;
 
+	// metric of the column: Jacobian on level k / interface m, xi-row of the
+	// contravariant metric on interface m
+	const bool fastm = (ta.colc != 0);
+	const double * ccol = fastm ? (ta.colc + (size_t)e * TBT_C_NC * NN + nd) : 0;
+	const double cJ = fastm ? ccol[TBT_C_JAC * NN] : 0.0;
+	const double cA2 = fastm ? ccol[TBT_C_A2 * NN] : 0.0;
+	const double cB2 = fastm ? ccol[TBT_C_B2 * NN] : 0.0;
+	const double cX0 = fastm ? ccol[TBT_C_X0 * NN] : 0.0;
+	const double cX2 = fastm ? ccol[TBT_C_X2 * NN] : 0.0;
+	auto jac_at = [&](int k) { return fastm ? cJ : g.jac[g3 + (size_t)k * NN]; };
+	auto jace_at = [&](int m) { return fastm ? cJ : g.jace[g3e + (size_t)m * NN]; };
+	auto cxe_at = [&](int m, double & c0, double & c1, double & c2) {
+		if (fastm) {
+			const double se = ta.lev[(size_t)m * TBT_L_LW + TBT_L_SE];
+			c0 = se * cA2; c1 = se * cB2; c2 = cX0 + (se * se) * cX2;
+		} else {
+			const size_t o = g3e + (size_t)m * NN;
+			c0 = g.cxe[0][o]; c1 = g.cxe[1][o]; c2 = g.cxe[2][o];
+		}
+	};
+
 	// SetupReferenceColumn: u, v on interfaces (:1643-1835)
 	for (int k = 0; k < L; k++) {
 		snU(k) = inU[(size_t)k * NN];
@@ -89,8 +124,8 @@ __global__ void k_column_tracers(
 		if (k >= 1 && k < L) {
 			const double ue = tb_ws_apply(opInterpN2E, snU, k);
 			const double ve = tb_ws_apply(opInterpN2E, snV, k);
-			const size_t o = g3e + (size_t)k * NN;
-			const double c0 = g.cxe[0][o], c1 = g.cxe[1][o], c2 = g.cxe[2][o];
+			double c0, c1, c2;
+			cxe_at(k, c0, c1, c2);
 			a = c0 * ue + c1 * ve + c2 * wOld[(size_t)k * NN];
 			b = c0 * ue + c1 * ve + c2 * wNew[(size_t)k * NN];
 		}
@@ -110,9 +145,9 @@ __global__ void k_column_tracers(
 		// TracerMatFIx(n, k): column n, row k -> band row 2 kl + k - n
 #define TB_TMAT(n, k) AB(2 * kl + (k) - (n), (n))
 		for (int k = 0; k < L; k++) {
-			const double jn = g.jac[g3 + (size_t)k * NN];
+			const double jn = jac_at(k);
 			for (int m = opDiffE2N.begin[k]; m < opDiffE2N.end[k]; m++) {
-				const double je = g.jace[g3e + (size_t)m * NN];
+				const double je = jace_at(m);
 				for (int n = opInterpN2E.begin[m]; n < opInterpN2E.end[m]; n++) {
 					TB_TMAT(n, k) +=
 						tb_op_coeff(opDiffE2N, k, m)
@@ -152,12 +187,12 @@ __global__ void k_column_tracers(
 			qe(k) = tb_ws_apply(opInterpN2E, qn, k);
 		}
 		for (int k = 0; k <= L; k++) {
-			mf(k) = g.jace[g3e + (size_t)k * NN] * qe(k) * xdn(k);
+			mf(k) = jace_at(k) * qe(k) * xdn(k);
 		}
 		mf(0) = 0.0;
 		mf(L) = 0.0;
 		for (int k = 0; k < L; k++) {
-			F(k) = tb_ws_apply(opDiffE2N, mf, k) / g.jac[g3 + (size_t)k * NN];
+			F(k) = tb_ws_apply(opDiffE2N, mf, k) / jac_at(k);
 		}
 		// upwind penalty with the weights of the state before the solve
 		// (LinearColumnDiscPenaltyFEM::Apply, LinearColumnOperatorFEM.cpp:1863-1887)
@@ -177,7 +212,8 @@ __global__ void k_column_tracers(
 			const int kLeftBegin = (a - 1) * vo, kLeftEnd = a * vo;
 			const int kRightBegin = a * vo, kRightEnd = (a + 1) * vo;
 			const double xd = xdi(kLeftEnd);
-			const double cx2 = g.cxe[2][g3e + (size_t)kLeftEnd * NN];
+			double cx0_, cx1_, cx2;
+			cxe_at(kLeftEnd, cx0_, cx1_, cx2);
 			double dSignWeight;
 			if (xd > 0.0) {
 				dSignWeight = 1.0 * cx2;

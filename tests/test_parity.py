@@ -427,10 +427,14 @@ def test_cartesian_bubble_steps(library):
     ctx.close()
 
 
-def test_tracer_stages(library):
+@pytest.mark.parametrize("kernels", ["fast", "generic"])
+def test_tracer_stages(library, monkeypatch, kernels):
     """Tracers: horizontal transport inside StepExplicit with the
     element filter, DSS, implicit column transport with the column filter
-    (UpdateColumnTracers, both FilterNegativeTracers), hyperdiffusion."""
+    (UpdateColumnTracers, both FilterNegativeTracers), hyperdiffusion; on the
+    column-constant path and on the general kernels."""
+    if kernels == "generic":
+        monkeypatch.setenv("TB200_TRACER_KERNEL", "generic")
     d = cases.load_case("jwtr_ne2_l6")
     ctx = dumpctx.context_from_dump(d, library=library)
     dumpctx.upload_tag(ctx, d, "ic")

@@ -278,10 +278,15 @@ def test_state_does_not_depend_on_the_patch_decomposition(library):
         assert np.array_equal(res[0][1][panel][3], res[1][1][panel][3]), panel
 
 
-def test_tracers_l30(library):
-    """Tracer transport at L = 30 (config 4's level count; general kernels):
+@pytest.mark.parametrize("kernels", ["fast", "generic"])
+def test_tracers_l30(library, monkeypatch, kernels):
+    """Tracer transport at L = 30 (config 4's level count) on the column-constant
+    path (k_tracer_stage, k_tracer_hyper, k_column_tracers with the column
+    constants) and on the general kernels (TB200_TRACER_KERNEL=generic):
     horizontal transport with the element filter, DSS, implicit column
     transport with the column filter, hyperdiffusion, three Strang steps."""
+    if kernels == "generic":
+        monkeypatch.setenv("TB200_TRACER_KERNEL", "generic")
     d = cases.load_case("jwtr_ne2_l30")
     ctx = dumpctx.context_from_dump(d, library=library)
     dumpctx.upload_tag(ctx, d, "ic")
