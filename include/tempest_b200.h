@@ -301,6 +301,11 @@ int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst);
  * the column-wise filter (the one above is HorizontalDynamicsFEM's element-wise
  * filter, HorizontalDynamicsFEM.cpp:213-317). */
 int tb200_v_filter_negative_tracers(tb200_ctx * ctx, int inst);
+/* Grid::LinearCombineData(coeff -> dst) (GridPatch.cpp:1433-1520) of state and
+ * tracers followed by VerticalDynamics::FilterNegativeTracers(dst), as
+ * TimestepSchemeStrang::Step issues them at the start of a step (:470-482);
+ * the tracer combination is formed inside the filter kernel. */
+int tb200_lincomb_v_filter(tb200_ctx * ctx, const double * coeff, int ncoeff, int dst);
 
 /* TimestepScheme::Step (TimestepSchemeStrang.cpp:450-674,
  * TimestepSchemeARS343.cpp:146-235, ...): one full time step on the device. */

@@ -1729,6 +1729,7 @@ extern "C" int tb200_hv_step_explicit_combine(
 
 static int column_solve(tb200_ctx * ctx, int in, int out, double dt);
 static int column_tracers(tb200_ctx * ctx, int in, int out, double dt);
+static int filter_tracers(tb200_ctx * ctx, int inst, bool column, const CombineArgs * comb, double * inc);
 
 extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt) {
 	if (check_inst2(ctx, in, out)) return 1;
@@ -1772,43 +1773,60 @@ static int column_tracers(tb200_ctx * ctx, int in, int out, double dt) {
 		fa.w_old = ctx->d_wold;
 		fa.dt = dt;
 		fa.info = ctx->d_info;
+		fa.keep = ctx->tracer_keep;
+		const size_t ws_doubles = (size_t)tb_column_ws_entries(lay.nlev, ctx->offd) * ctx->ws_cols;
+		const size_t smem = (size_t)(lay.nlev + 1) * TBF_LW * sizeof(double);
 		for (int c0 = 0; c0 < lay.ntr; c0 += 6) {
 			fa.c0 = c0;
 			const int nt = std::min(6, lay.ntr - c0);
-			int threads = 64;
-			size_t smem = tb_tracer_column_smem_doubles(lay.nlev, nt, threads) * sizeof(double);
-			if (smem > 100 * 1024) {
-				threads = 32;
-				smem = tb_tracer_column_smem_doubles(lay.nlev, nt, threads) * sizeof(double);
-			}
-			if (smem > 227 * 1024) TB_FAIL(ctx, "column too tall for the tracer column kernel");
-			const dim3 grid((ctx->ncols + threads - 1) / threads), block(threads);
+			// columns per launch: what the scratch holds, whole blocks
+			long long chunk = (long long)(ws_doubles / ((size_t)(3 + nt) * lay.nlev))
+				/ TBT_COL_THREADS * TBT_COL_THREADS;
+			if (chunk < TBT_COL_THREADS) TB_FAIL(ctx, "column workspace too small for the tracer update");
+			for (int col0 = 0; col0 < ctx->ncols; col0 += (int)chunk) {
+				fa.col0 = col0;
+				fa.ncols = (int)std::min<long long>(chunk, ctx->ncols - col0);
+				fa.ws = ctx->d_ws;
+				const dim3 grid((fa.ncols + TBT_COL_THREADS - 1) / TBT_COL_THREADS), block(TBT_COL_THREADS);
 #ifndef TB200_EMU
 #define TB_TRC_ATTR(kfn) TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
 #else
 #define TB_TRC_ATTR(kfn)
 #endif
 #define TB_TRC_LAUNCH(N) { \
-				auto kfn = k_column_tracers_fast<N>; \
-				TB_TRC_ATTR(kfn); \
-				TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, fa, \
-					(const double *)ctx->inst[in], (const double *)ctx->inst[out], \
-					(const double *)ctx->inst[in], ctx->inst[out]); }
-			switch (nt) {
-				case 1: TB_TRC_LAUNCH(1) break;
-				case 2: TB_TRC_LAUNCH(2) break;
-				case 3: TB_TRC_LAUNCH(3) break;
-				case 4: TB_TRC_LAUNCH(4) break;
-				case 5: TB_TRC_LAUNCH(5) break;
-				default: TB_TRC_LAUNCH(6) break;
-			}
+					auto kfn = k_column_tracers_fast<N>; \
+					TB_TRC_ATTR(kfn); \
+					TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, fa, \
+						(const double *)ctx->inst[in], (const double *)ctx->inst[out], \
+						(const double *)ctx->inst[in], ctx->inst[out]); }
+				switch (nt) {
+					case 1: TB_TRC_LAUNCH(1) break;
+					case 2: TB_TRC_LAUNCH(2) break;
+					case 3: TB_TRC_LAUNCH(3) break;
+					case 4: TB_TRC_LAUNCH(4) break;
+					case 5: TB_TRC_LAUNCH(5) break;
+					default: TB_TRC_LAUNCH(6) break;
+				}
 #undef TB_TRC_LAUNCH
 #undef TB_TRC_ATTR
-			ctx->launches++;
-			ctx->writes++;
-			TB_LAUNCH_CHECK(ctx);
+				ctx->launches++;
+				ctx->writes++;
+				TB_LAUNCH_CHECK(ctx);
+			}
 		}
-		return tb200_v_filter_negative_tracers(ctx, out);
+		return filter_tracers(ctx, out, true, 0, ctx->tracer_inc);
+	}
+	if (ctx->tracer_keep != 0) {
+		// the tracers from before the update, for the increment formed after the filter
+		CombineArgs keep;
+		memset(&keep, 0, sizeof(keep));
+		keep.nsrc = 1;
+		keep.src[0] = ctx->inst[out];
+		keep.coeff[0] = 1.0;
+		int kdst = -1;
+		for (int m = 0; m < (int)ctx->inst.size(); m++) if (ctx->inst[m] == ctx->tracer_keep) kdst = m;
+		if (kdst < 0) TB_FAIL(ctx, "invalid tracer keep instance");
+		if (launch_combine(ctx, keep, kdst, lay.nrows_state, lay.nrows)) return 1;
 	}
 	TracerColumnArgs ta;
 	ta.colc = fastm ? ctx->d_colc : 0;
@@ -1836,7 +1854,7 @@ static int column_tracers(tb200_ctx * ctx, int in, int out, double dt) {
 			(const double *)ctx->inst[in], ctx->inst[out]);
 		TB_KERNEL_CHECK(ctx);
 	}
-	return tb200_v_filter_negative_tracers(ctx, out);
+	return filter_tracers(ctx, out, true, 0, ctx->tracer_inc);
 }
 
 static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
@@ -1960,21 +1978,6 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 	return 0;
 }
 
-// Tracer rows of Grid::LinearCombineData({+1, -1}): inst[old] = inst[upd] - inst[old]
-// (old holds the tracers from before the column update and its filter)
-static int tracer_increment(tb200_ctx * ctx, int upd, int old) {
-	const DevLayout & lay = ctx->lay;
-	if (lay.ntr == 0) return 0;
-	CombineArgs ca;
-	memset(&ca, 0, sizeof(ca));
-	ca.cdst = -1.0;
-	ca.scale_dst = 1;
-	ca.nsrc = 1;
-	ca.src[0] = ctx->inst[upd];
-	ca.coeff[0] = +1.0;
-	return launch_combine(ctx, ca, old, lay.nrows_state, lay.nrows);
-}
-
 // CopyData(src -> dst) followed by StepImplicit(dst, dst): the column solve
 // reads src and writes rho-theta, w, rho of dst (every node is a solved column
 // or the duplicate of one), so only the rows the solve leaves alone (u, v) are
@@ -2031,14 +2034,18 @@ extern "C" int tb200_copy_v_step_implicit_diff(tb200_ctx * ctx, int src, int dst
 	if (launch_combine(ctx, ca, dst, uv0, uv1)) return 1;
 	if (launch_combine(ctx, ca, dst, lay.nrows_state, lay.nrows)) return 1;
 	ctx->column_inc = ctx->inst[src];
+	// tracers: src still holds the values from before the update; the column
+	// filter leaves dst - src there
+	ctx->tracer_keep = 0;
+	ctx->tracer_inc = (lay.ntr > 0) ? ctx->inst[src] : 0;
 	const int rc = tb200_v_step_implicit(ctx, src, dst, dt);
 	ctx->column_inc = 0;
+	ctx->tracer_inc = 0;
 	if (rc) return 1;
 	// u, v rows of the increment
 	CombineArgs zero;
 	memset(&zero, 0, sizeof(zero));
 	if (launch_combine(ctx, zero, src, uv0, uv1)) return 1;
-	if (tracer_increment(ctx, dst, src)) return 1;
 	ctx->uvzero_inst = src;
 	ctx->uvzero_writes = ctx->writes;
 	return 0;
@@ -2065,25 +2072,21 @@ extern "C" int tb200_v_step_implicit_inc(tb200_ctx * ctx, int inst, int inc, dou
 	if (check_inst2(ctx, inst, inc)) return 1;
 	const DevLayout & lay = ctx->lay;
 	if (inst == inc || !tb200_v_step_implicit_inc_available(ctx)) return 2;
-	if (lay.ntr > 0) {
-		// the tracers before the column update: the increment is formed from them
-		CombineArgs keep;
-		memset(&keep, 0, sizeof(keep));
-		keep.nsrc = 1;
-		keep.src[0] = ctx->inst[inst];
-		keep.coeff[0] = 1.0;
-		if (launch_combine(ctx, keep, inc, lay.nrows_state, lay.nrows)) return 1;
-	}
+	// tracers: the column kernel leaves the values from before the update in
+	// `inc`, the column filter turns them into new - old
+	ctx->tracer_keep = (lay.ntr > 0) ? ctx->inst[inc] : 0;
+	ctx->tracer_inc = ctx->tracer_keep;
 	ctx->column_inc = ctx->inst[inc];
 	const int rc = tb200_v_step_implicit(ctx, inst, inst, dt);
 	ctx->column_inc = 0;
+	ctx->tracer_keep = 0;
+	ctx->tracer_inc = 0;
 	if (rc) return 1;
 	// u, v rows of the increment
 	const int uv0 = lay.rowoff[0], uv1 = lay.rowoff[1] + lay.rowlev[1];
 	CombineArgs zero;
 	memset(&zero, 0, sizeof(zero));
 	if (launch_combine(ctx, zero, inc, uv0, uv1)) return 1;
-	if (tracer_increment(ctx, inst, inc)) return 1;
 	ctx->uvzero_inst = inc;
 	ctx->uvzero_writes = ctx->writes;
 	return 0;
@@ -2178,7 +2181,9 @@ int tb_poll_errors(tb200_ctx * ctx) {
 // HorizontalDynamicsFEM::FilterNegativeTracers (element-wise) and
 // VerticalDynamicsFEM::FilterNegativeTracers (column-wise); both need the
 // element areas (tb200_upload_element_area).
-static int filter_tracers(tb200_ctx * ctx, int inst, bool column) {
+static int filter_tracers(
+	tb200_ctx * ctx, int inst, bool column, const CombineArgs * comb = 0, double * inc = 0
+) {
 	const DevLayout & lay = ctx->lay;
 	if (lay.ntr == 0) return 0;
 	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid state instance");
@@ -2187,8 +2192,13 @@ static int filter_tracers(tb200_ctx * ctx, int inst, bool column) {
 	if (column) {
 		const long long nitems = lay.nelem * lay.nn * lay.ntr;
 		auto kfn = k_filter_tracers_column;
+		CombineArgs none;
+		memset(&none, 0, sizeof(none));
 		TB_LAUNCH_FLAT(kfn, dim3((unsigned)((nitems + block - 1) / block)), dim3(block), 0,
-			ctx->stream, lay, (const double *)ctx->d_area_node, ctx->inst[inst]);
+			ctx->stream, lay, (const double *)ctx->d_area_node, ctx->inst[inst],
+			(comb != 0) ? *comb : none, (comb != 0) ? 1 : 0, inc);
+		ctx->launches++;
+		ctx->writes++;
 	} else {
 		const long long nitems = lay.nelem * lay.ntr * lay.nlev;
 		auto kfn = k_filter_tracers_element;
@@ -2205,6 +2215,30 @@ extern "C" int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst) {
 
 extern "C" int tb200_v_filter_negative_tracers(tb200_ctx * ctx, int inst) {
 	return filter_tracers(ctx, inst, true);
+}
+
+// Grid::LinearCombineData(coeff -> dst) of state and tracers followed by
+// VerticalDynamics::FilterNegativeTracers(dst): the carry-over at the start of a
+// Strang step (TimestepSchemeStrang.cpp:470-482).  The combination of the tracer
+// rows is formed inside the filter kernel.
+extern "C" int tb200_lincomb_v_filter(tb200_ctx * ctx, const double * coeff, int ncoeff, int dst) {
+	const DevLayout & lay = ctx->lay;
+	if (lay.ntr == 0 || ctx->d_area_node == 0) {
+		if (tb200_lincomb(ctx, coeff, ncoeff, dst, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
+		return tb200_v_filter_negative_tracers(ctx, dst);
+	}
+	if (tb200_lincomb(ctx, coeff, ncoeff, dst, TB200_DATA_STATE)) return 1;
+	CombineArgs ca;
+	memset(&ca, 0, sizeof(ca));
+	ca.cdst = coeff[dst];
+	ca.scale_dst = (coeff[dst] == 0.0) ? 0 : 1;
+	for (int m = 0; m < ncoeff; m++) {
+		if (m == dst || coeff[m] == 0.0) continue;
+		ca.src[ca.nsrc] = ctx->inst[m];
+		ca.coeff[ca.nsrc] = coeff[m];
+		ca.nsrc++;
+	}
+	return filter_tracers(ctx, dst, true, &ca, 0);
 }
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -2287,7 +2321,7 @@ extern "C" int tb200_peer_export(
 	if (ctx->nranks > TB200_MAX_PEERS) TB_FAIL(ctx, "peer-memory exchange: too many ranks");
 	if (ctx->peer_area != 0) TB_FAIL(ctx, "peer-memory exchange already exported");
 	const DevLayout & lay = ctx->lay;
-	ctx->peer_rows = (size_t)std::max(lay.nrows_state, lay.nrows - lay.nrows_state);
+	ctx->peer_rows = (size_t)lay.nrows;
 	const size_t doubles = kPeerFlagDoubles + 2 * (size_t)ctx->nrecv_total * ctx->peer_rows;
 	TB_CHECK(ctx, cudaMalloc(&ctx->peer_area, doubles * sizeof(double)));
 	TB_CHECK(ctx, cudaMemset(ctx->peer_area, 0, doubles * sizeof(double)));
@@ -2361,7 +2395,7 @@ static int dss_rows(
 	if (ctx->nranks > 1 && ctx->peer_ready) {
 		if (peer_exchange(ctx, inst, row0, nsel, &recvbuf)) return 1;
 	} else if (ctx->nranks > 1) {
-		if (ensure_buffers(ctx, (size_t)std::max(lay.nrows_state, lay.nrows - lay.nrows_state))) return 1;
+		if (ensure_buffers(ctx, (size_t)lay.nrows)) return 1;
 		if (ctx->nsend_total > 0) {
 			const long long total = (long long)ctx->nsend_total * nsel;
 			long long nb = (total + 255) / 256;
@@ -2468,6 +2502,11 @@ static int dss_instance(tb200_ctx * ctx, int inst, int mask, bool remainder_only
 	if (!ctx->connectivity_built) TB_FAIL(ctx, "connectivity not built");
 	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid state instance");
 	const DevLayout & lay = ctx->lay;
+	if ((mask & TB200_DATA_STATE) && (mask & TB200_DATA_TRACERS) && lay.ntr > 0 && !remainder_only) {
+		// state and tracers in one exchange and one averaging pass (the reference
+		// exchanges them together as well, Grid::Exchange: Grid.cpp:627-685)
+		return dss_rows(ctx, inst, 0, lay.nrows, true, false);
+	}
 	if (mask & TB200_DATA_STATE) {
 		if (dss_rows(ctx, inst, 0, lay.nrows_state, true, remainder_only)) return 1;
 	}

@@ -115,9 +115,9 @@ static int step_strang(tb200_ctx * ctx, int scheme, int first, int last, double 
 		TRY(tb200_v_step_implicit(ctx, 0, 0, half));
 	} else {
 		const std::vector<double> carry = {1.0, 1.0};
-		TRY(lincomb(ctx, carry, 0));
-		// pVerticalDynamics->FilterNegativeTracers(0), TimestepSchemeStrang.cpp:480
-		TRY(tb200_v_filter_negative_tracers(ctx, 0));
+		// LinearCombineData + pVerticalDynamics->FilterNegativeTracers(0),
+		// TimestepSchemeStrang.cpp:470-480
+		TRY(tb200_lincomb_v_filter(ctx, carry.data(), (int)carry.size(), 0));
 	}
 
 	if (scheme == TB200_SCHEME_STRANG_FE) {

@@ -16,6 +16,7 @@
 #include "tb200_platform.h"
 #include "tb200_device.h"
 #include "tb200_column.cuh"
+#include "tb200_kernels.cuh"
 
 struct TracerColumnArgs {
 	const int * col_node;
@@ -291,9 +292,16 @@ __global__ void k_filter_tracers_element(
 	}
 }
 
-// VerticalDynamicsFEM::FilterNegativeTracers: per (node, tracer), within the column
+// VerticalDynamicsFEM::FilterNegativeTracers: per (node, tracer), within the column.
+// Optionally fused with what the time schemes put around it:
+//  - combine: Grid::LinearCombineData(ca) of the tracer rows first (the Strang
+//    carry-over, TimestepSchemeStrang.cpp:470-482), in k_lincomb's operation order;
+//  - inc: Grid::LinearCombineData({+1, -1}) afterwards, inc = filtered - inc (the
+//    tail of the Strang step, :658-672; inc holds the tracers from before the
+//    column update).
 __global__ void k_filter_tracers_column(
-	DevLayout lay, const double * area_node, double * data
+	DevLayout lay, const double * area_node, double * data,
+	CombineArgs ca, int combine, double * inc
 ) {
 	const int NN = lay.nn;
 	const int L = lay.nlev;
@@ -305,12 +313,26 @@ __global__ void k_filter_tracers_column(
 	const long long ec = item / NN;
 	const int c = (int)(ec % lay.ntr);
 	const long long e = ec / lay.ntr;
-	double * p = data + ((size_t)e * lay.nrows + lay.troff + c * L) * NN + n;
+	const size_t off0 = ((size_t)e * lay.nrows + lay.troff + c * L) * NN + n;
+	double * p = data + off0;
 	const double * a = area_node + (size_t)e * L * NN + n;
 	double dTotalMass = 0.0;
 	double dNonNegativeMass = 0.0;
 	for (int k = 0; k < L; k++) {
-		const double v = p[(size_t)k * NN];
+		double v;
+		if (combine) {
+			const size_t off = off0 + (size_t)k * NN;
+			v = 0.0;
+			if (ca.scale_dst) {
+				v = data[off] * ca.cdst;
+			}
+			for (int m = 0; m < ca.nsrc; m++) {
+				v += ca.src[m][off] * ca.coeff[m];
+			}
+			p[(size_t)k * NN] = v;
+		} else {
+			v = p[(size_t)k * NN];
+		}
 		const double dPointwiseMass = v * a[(size_t)k * NN];
 		dTotalMass += dPointwiseMass;
 		if (v >= 0.0) {
@@ -320,7 +342,14 @@ __global__ void k_filter_tracers_column(
 	const double dR = dTotalMass / dNonNegativeMass;
 	for (int k = 0; k < L; k++) {
 		const double v = p[(size_t)k * NN];
-		p[(size_t)k * NN] = (v > 0.0) ? v * dR : 0.0;
+		const double vf = (v > 0.0) ? v * dR : 0.0;
+		p[(size_t)k * NN] = vf;
+		if (inc != 0) {
+			double * q = inc + off0 + (size_t)k * NN;
+			double w = q[0] * -1.0;
+			w += vf * 1.0;
+			q[0] = w;
+		}
 	}
 }
 

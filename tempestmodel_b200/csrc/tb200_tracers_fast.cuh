@@ -90,7 +90,7 @@ struct TracerFastArgs {
 
 // Stage base (Grid::CopyData / LinearCombineData) + horizontal transport + the
 // element-wise positivity filter of every tracer of an element.
-__global__ void __launch_bounds__(TBT_THREADS, 4)
+__global__ void __launch_bounds__(TBT_THREADS, 3)
 k_tracer_stage(
 	DevLayout lay, DevTables t, TracerFastArgs ta, StageBase sb,
 	const double * __restrict__ in, double * out, ElemList el
@@ -157,11 +157,23 @@ k_tracer_stage(
 			tb_ld4g(ta.area + ((size_t)e * L + kc) * NN + i * 4, area);
 		}
 
+		// the loads of tracer c + 1 are issued before the arithmetic of tracer c
+		// (a thread only ever touches its own 32 bytes of a row, so the stage-base
+		// loads may pass the stores of the previous tracer)
+		const size_t oT0 = ebase + (size_t)lay.troff * NN + o4;
+		const size_t tstep = (size_t)L * NN;
+		double qn[4], bn[4];
+		tb_ld4(in + oT0, qn);
+		tb_stage_base4(sb, out, oT0, bn);
 		for (int c = 0; c < lay.ntr; c++) {
-			const size_t oT = ebase + (size_t)(lay.troff + c * L) * NN + o4;
+			const size_t oT = oT0 + (size_t)c * tstep;
 			double q[4], b[4];
-			tb_ld4(in + oT, q);
-			tb_stage_base4(sb, out, oT, b);
+#pragma unroll
+			for (int j = 0; j < 4; j++) { q[j] = qn[j]; b[j] = bn[j]; }
+			if (c + 1 < lay.ntr) {
+				tb_ld4(in + oT + tstep, qn);
+				tb_stage_base4(sb, out, oT + tstep, bn);
+			}
 			double fA[4], fB[4], dDa[4];
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
@@ -280,7 +292,8 @@ k_tracer_hyper(
 // reciprocal scaling, rank-1 update) and the forward substitution of dgbtrs on
 // all NT right-hand sides at once - NT independent dependency chains per
 // thread.  Only the rows of U and the substituted right-hand sides are kept
-// (shared memory, [entry][thread]); the back substitution (dtbsv) marches up,
+// (block-private scratch in global memory, [entry][thread]: coalesced, written
+// once and read once); the back substitution (dtbsv) marches up,
 // subtracts the solution from the update instance and copies it to the
 // duplicates of the column (:4265-4281, 1544-1633).
 
@@ -293,35 +306,39 @@ struct TracerColumnFastArgs {
 	const double * w_old;     // [e][L+1][NN]: w before the implicit solve
 	double dt;
 	int c0;                   // first tracer of this pass
+	int col0;                 // first column of this launch
+	double * ws;              // scratch: (3 + NT) * L doubles per column of the launch
+	double * keep;            // instance that receives the tracers from before the update, or 0
 	int * info;
 };
 
-__host__ __device__ inline size_t tb_tracer_column_smem_doubles(int L, int nt, int threads) {
-	return (size_t)(L + 1) * TBF_LW + (size_t)(3 + nt) * L * threads;
-}
+#define TBT_COL_THREADS 128
 
 template <int NT>
-__global__ void k_column_tracers_fast(
+__global__ void __launch_bounds__(TBT_COL_THREADS)
+k_column_tracers_fast(
 	DevLayout lay, TracerColumnFastArgs ta,
 	const double * st_in,     // state before the solve (u, v)
 	const double * st_out,    // state after the solve (w)
 	const double * tr_in,     // instance holding the initial tracers
 	double * tr_out           // instance whose tracers are updated
 ) {
-	TB_DYN_SMEM(double, slev);          // [L+1][TBF_LW], then U [3][L][T], Y [NT][L][T]
+	TB_DYN_SMEM(double, slev);          // [L+1][TBF_LW]
 	const int L = lay.nlev;
 	const int NN = lay.nn;
-	const int T = blockDim.x;
+	const int T = TBT_COL_THREADS;
 	for (int q = threadIdx.x; q < (L + 1) * TBF_LW; q += T) {
 		slev[q] = ta.lev[q];
 	}
 	__syncthreads();
-	double * sU = slev + (size_t)(L + 1) * TBF_LW + threadIdx.x;   // sU[(r * L + j) * T]
-	double * sY = sU + (size_t)3 * L * T;                          // sY[(c * L + j) * T]
+	// scratch of this block: U [3][L][T], Y [NT][L][T]
+	double * sU = ta.ws + (size_t)blockIdx.x * (size_t)(3 + NT) * L * T + threadIdx.x;   // sU[(r * L + j) * T]
+	double * sY = sU + (size_t)3 * L * T;                                            // sY[(c * L + j) * T]
 
 	int tcol = blockIdx.x * T + threadIdx.x;
 	const bool live = (tcol < ta.ncols);
 	if (!live) tcol = ta.ncols - 1;
+	tcol += ta.col0;
 	const int node = ta.col_node[tcol];
 	const long long e = node / NN;
 	const int nd = node % NN;
@@ -547,7 +564,14 @@ __global__ void k_column_tracers_fast(
 			if (live && ta.c0 + c < ntr) {
 				const size_t row = (size_t)(lay.troff + (ta.c0 + c) * L + j) * NN;
 				double * own = tr_out + ebase + row + nd;
-				const double v = own[0] - b;
+				const double old = own[0];
+				const double v = old - b;
+				if (ta.keep != 0) {
+					ta.keep[ebase + row + nd] = old;
+					if (d0 >= 0) ta.keep[ob0 + row] = tr_out[ob0 + row];
+					if (d1 >= 0) ta.keep[ob1 + row] = tr_out[ob1 + row];
+					if (d2 >= 0) ta.keep[ob2 + row] = tr_out[ob2 + row];
+				}
 				own[0] = v;
 				if (d0 >= 0) tr_out[ob0 + row] = v;
 				if (d1 >= 0) tr_out[ob1 + row] = v;
