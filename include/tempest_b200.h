@@ -301,6 +301,15 @@ int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst);
  * the column-wise filter (the one above is HorizontalDynamicsFEM's element-wise
  * filter, HorizontalDynamicsFEM.cpp:213-317). */
 int tb200_v_filter_negative_tracers(tb200_ctx * ctx, int inst);
+/* HeldSuarezPhysics::Perform (src/atm/HeldSuarezPhysics.cpp:62-301) as a device
+ * workflow step on instance 0: boundary-layer friction of u, v and Newtonian
+ * relaxation of rho-theta, one streaming pass.  Inputs per column, [iA][iB] in the
+ * reference layout with halo: GridPatch::GetLatitude() and the product
+ * dataREdge[R][..][0] * dataREdge[T][..][0] of instance 0 the reference takes its
+ * "surface pressure" from (:112-115; the dynamics never changes those slots). */
+int tb200_upload_held_suarez(tb200_ctx * ctx, int patch_index,
+                             const double * latitude, const double * surface_product);
+int tb200_held_suarez(tb200_ctx * ctx, double dt);
 /* Grid::LinearCombineData(coeff -> dst) (GridPatch.cpp:1433-1520) of state and
  * tracers followed by VerticalDynamics::FilterNegativeTracers(dst), as
  * TimestepSchemeStrang::Step issues them at the start of a step (:470-482);

@@ -514,7 +514,8 @@ TimestepSchemeB200::TimestepSchemeB200(Model & model, int iScheme) :
 	TimestepScheme(model),
 	m_iScheme(iScheme),
 	m_fLazy(false),
-	m_fDeviceCurrent(false)
+	m_fDeviceCurrent(false),
+	m_fHostCopy(false)
 {
 	if (tb200_scheme_instances(iScheme) < 0) {
 		_EXCEPTIONT("tempest_b200: time scheme not implemented");
@@ -573,6 +574,7 @@ void TimestepSchemeB200::Step(
 		b.Check(tb200_check_errors(b.Ctx()));
 		b.Download(0);
 	}
+	m_fHostCopy = fHostReads;
 }
 
 void TimestepSchemeB200::HostReadsEvery(
@@ -591,3 +593,53 @@ void TimestepSchemeB200::HostProcess(WorkflowProcess * pProcess) {
 }
 
 ///////////////////////////////////////////////////////////////////////////////
+
+///////////////////////////////////////////////////////////////////////////////
+// HeldSuarezPhysicsB200
+
+HeldSuarezPhysicsB200::HeldSuarezPhysicsB200(
+	Model & model, const Time & timeFrequency, TimestepSchemeB200 * pScheme
+) :
+	WorkflowProcess(model, timeFrequency),
+	m_pScheme(pScheme),
+	m_fUploaded(false)
+{ }
+
+void HeldSuarezPhysicsB200::Perform(const Time & time) {
+	B200Bridge & b = B200Bridge::Get(m_model);
+	b.Initialize();
+	Grid * pGrid = m_model.GetGrid();
+	if (!m_fUploaded) {
+		// latitude and the slots the reference takes its surface pressure from
+		// (HeldSuarezPhysics.cpp:95-115): rho and the theta slot on the lowest
+		// interface of instance 0, which the dynamics never writes
+		for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
+			GridPatch * pPatch = pGrid->GetActivePatch(n);
+			const DataArray2D<double> & dataLatitude = pPatch->GetLatitude();
+			const DataArray4D<double> & dataREdge =
+				pPatch->GetDataState(0, DataLocation_REdge);
+			DataArray2D<double> dProduct(dataLatitude.GetRows(), dataLatitude.GetColumns());
+			for (int i = 0; i < dProduct.GetRows(); i++) {
+			for (int j = 0; j < dProduct.GetColumns(); j++) {
+				dProduct[i][j] = dataREdge[4][i][j][0] * dataREdge[2][i][j][0];
+			}
+			}
+			b.Check(tb200_upload_held_suarez(
+				b.Ctx(), pPatch->GetPatchIndex(), &(dataLatitude[0][0]), &(dProduct[0][0])));
+		}
+		m_fUploaded = true;
+	}
+	const double dDeltaT = m_timeFrequency.GetSeconds();
+	if (m_pScheme == NULL) {
+		// host time scheme: instance 0 lives on the host between plugin calls
+		b.Upload(0);
+		b.Check(tb200_held_suarez(b.Ctx(), dDeltaT));
+		b.Download(0);
+	} else {
+		b.Check(tb200_held_suarez(b.Ctx(), dDeltaT));
+		if (m_pScheme->HostCopyIsCurrent()) {
+			b.Download(0);
+		}
+	}
+	WorkflowProcess::Perform(time);
+}

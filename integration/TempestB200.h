@@ -172,13 +172,43 @@ public:
 	///	</summary>
 	void HostProcess(WorkflowProcess * pProcess);
 
+	///	<summary>
+	///		Did the last Step() leave a copy of instance 0 on the host (an
+	///		output manager is about to read it)?  A workflow process that
+	///		changes instance 0 on the device refreshes that copy.
+	///	</summary>
+	bool HostCopyIsCurrent() const { return m_fHostCopy; }
+
 private:
 	int m_iScheme;
 	bool m_fLazy;
 	bool m_fDeviceCurrent;
+	bool m_fHostCopy;
 	std::vector<Time> m_vecNextRead;
 	std::vector<Time> m_vecReadFrequency;
 	std::vector<WorkflowProcess *> m_vecProcesses;
+};
+
+///////////////////////////////////////////////////////////////////////////////
+
+///	<summary>
+///		HeldSuarezPhysics (src/atm/HeldSuarezPhysics.h:27-45) as a device
+///		workflow step: same constructor, same Perform(), the forcing is applied
+///		to instance 0 where it lives.  With TimestepSchemeB200 (pScheme given)
+///		that is the device between steps - no bus traffic unless an output
+///		manager is about to read the host copy; under a host time scheme the
+///		instance is uploaded before and downloaded after.
+///	</summary>
+class HeldSuarezPhysicsB200 : public WorkflowProcess {
+public:
+	HeldSuarezPhysicsB200(
+		Model & model, const Time & timeFrequency, TimestepSchemeB200 * pScheme = NULL);
+
+	virtual void Perform(const Time & time);
+
+private:
+	TimestepSchemeB200 * m_pScheme;
+	bool m_fUploaded;
 };
 
 ///////////////////////////////////////////////////////////////////////////////

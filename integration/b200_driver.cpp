@@ -24,6 +24,7 @@
 #undef main
 
 #include "TempestB200.h"
+#include "HeldSuarezPhysics.h"
 #include "GridCSGLL.h"
 #include "GridCartesianGLL.h"
 #include "VerticalDynamicsStub.h"
@@ -39,6 +40,7 @@ try {
 	double dZtop;
 	std::string strPert;
 	int nEager;
+	int nHeldSuarez;
 
 	BeginTempestCommandLine("B200Driver");
 		SetDefaultResolution(8);
@@ -56,6 +58,7 @@ try {
 		CommandLineDouble(dZtop, "ztop", 10000.0);
 		CommandLineString(strPert, "pert", "Exp");
 		CommandLineInt(nEager, "b200eager", 0);
+		CommandLineInt(nHeldSuarez, "heldsuarez", 0);
 
 		ParseCommandLine(argc, argv);
 	EndTempestCommandLine(argv)
@@ -74,12 +77,14 @@ try {
 			_tempestvars.strTimestepScheme.c_str());
 	}
 
+	TimestepSchemeB200 * pSchemeB200 = NULL;
 	if (strMode == "none") {
 		_TempestSetupMethodOfLines(model, _tempestvars);
 
 	} else {
 		if (strMode == "scheme") {
 			TimestepSchemeB200 * pScheme = new TimestepSchemeB200(model, iScheme);
+			pSchemeB200 = pScheme;
 			// the output managers of _TempestSetupOutputManagers all fire every
 			// --outputtime (TempestInitialize.h:413-472): instance 0 only comes
 			// back to the host for them (--b200eager 1: every step)
@@ -182,6 +187,18 @@ try {
 				(strPert == "exp") ?
 					BaroclinicWaveJWTest::PerturbationType_Exp :
 					BaroclinicWaveJWTest::PerturbationType_None));
+	}
+
+	// --heldsuarez 1: Held-Suarez forcing every step (HeldSuarezTest.cpp:373-377),
+	// the reference's host process under --b200 none, the device step otherwise
+	if ((nHeldSuarez != 0) && (!fSW) && (pBubble == NULL)) {
+		if (strMode == "none") {
+			model.AttachWorkflowProcess(
+				new HeldSuarezPhysics(model, model.GetDeltaT()));
+		} else {
+			model.AttachWorkflowProcess(
+				new HeldSuarezPhysicsB200(model, model.GetDeltaT(), pSchemeB200));
+		}
 	}
 
 	AnnounceBanner("SIMULATION");

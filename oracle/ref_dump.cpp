@@ -23,6 +23,8 @@
 ///	  copy:SRC,DST          Grid::CopyData (State and Tracers)
 ///	  lincomb:DST,c0,c1,..  Grid::LinearCombineData (State and Tracers)
 ///	  step:N                N calls of TimestepScheme::Step (first = first call)
+///	  hs:SECONDS            HeldSuarezPhysics::Perform with that forcing interval
+///	                        (a WorkflowProcess: acts on instance 0)
 ///	  checksum:TAG          Grid::Checksum of instance 0 -> record
 ///	  addw:INST,AMP         test data: add a smooth non-zero W on interfaces
 ///	  perturb:INST,EPS      test data: relative pseudo-random noise of size EPS
@@ -53,6 +55,7 @@
 #include "GridPatchGLL.h"
 #include "HorizontalDynamicsFEM.h"
 #include "VerticalDynamicsFEM.h"
+#include "HeldSuarezPhysics.h"
 
 #include <cstdio>
 #include <cstdint>
@@ -497,6 +500,12 @@ static void RunScript(Model & model, const std::string & strScript) {
 			dDiag[2] = (eqn.GetType() == EquationSet::PrimitiveNonhydrostaticEquations) ?
 				pGrid->ComputeTotalVerticalMomentum(iInst) : 0.0;
 			Write1D(a[0] + ".energy", dDiag);
+		} else if (op == "hs") {
+			const double dSeconds = atof(a[0].c_str());
+			const int iSec = static_cast<int>(dSeconds);
+			const int iMicro = static_cast<int>((dSeconds - iSec) * 1.0e6 + 0.5);
+			HeldSuarezPhysics hs(model, Time(0, 0, 0, iSec, iMicro, Time::CalendarNoLeap, Time::TypeDelta));
+			hs.Perform(time);
 		} else if (op == "checksum") {
 			DataArray1D<double> dSums;
 			pGrid->Checksum(DataType_State, dSums, 0, ChecksumType_Sum);

@@ -112,6 +112,8 @@ _SIGNATURES = {
     "tb200_filter_negative_tracers": (c_int, [c_void_p, c_int]),
     "tb200_v_filter_negative_tracers": (c_int, [c_void_p, c_int]),
     "tb200_lincomb_v_filter": (c_int, [c_void_p, POINTER(c_double), c_int, c_int]),
+    "tb200_upload_held_suarez": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "tb200_held_suarez": (c_int, [c_void_p, c_double]),
     "tb200_scheme_instances": (c_int, [c_int]),
     "tb200_scheme_from_name": (c_int, [c_char_p]),
     "tb200_step": (c_int, [c_void_p, c_int, c_int, c_int, c_double]),

@@ -23,6 +23,7 @@
 #include "tb200_tracers.cuh"
 #include "tb200_tracers_fast.cuh"
 #include "tb200_diag.cuh"
+#include "tb200_physics.cuh"
 
 static_assert(TBT_C_JAC == TBF_JAC && TBT_C_A2 == TBF_A2 && TBT_C_B2 == TBF_B2
 	&& TBT_C_X0 == TBF_X0 && TBT_C_X2 == TBF_X2 && TBT_C_NC == TBF_NC
@@ -880,6 +881,61 @@ extern "C" int tb200_upload_rayleigh(
 	ctx->inst.pop_back();
 	if (rc) return 1;
 	ctx->has_rayleigh = true;
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Column physics (tb200_physics.cuh)
+
+// Per-column inputs of HeldSuarezPhysics::Perform (HeldSuarezPhysics.cpp:95-115):
+// GridPatch::GetLatitude() and the product dataREdge[R][0] * dataREdge[T][0] of
+// instance 0, both [iA][iB] in the reference's layout with halo.
+extern "C" int tb200_upload_held_suarez(
+	tb200_ctx * ctx, int patch_index, const double * latitude, const double * surface_product
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	if (latitude == 0 || surface_product == 0) TB_FAIL(ctx, "Held-Suarez: latitude and surface product needed");
+	const DevLayout & lay = ctx->lay;
+	if (ctx->d_hs_lat == 0) {
+		if (dalloc(ctx, &ctx->d_hs_lat, (size_t)lay.nelem * lay.nn)) return 1;
+		if (dalloc(ctx, &ctx->d_hs_sp, (size_t)lay.nelem * lay.nn)) return 1;
+	}
+	if (upload_geom_array(ctx, *pi, latitude, 1, 1, ctx->d_hs_lat, 0, 0)) return 1;
+	if (upload_geom_array(ctx, *pi, surface_product, 1, 1, ctx->d_hs_sp, 0, 0)) return 1;
+	return 0;
+}
+
+// HeldSuarezPhysics::Perform on instance 0 (the reference's workflow processes
+// always act on instance 0, Model.cpp:477-481)
+extern "C" int tb200_held_suarez(tb200_ctx * ctx, double dt) {
+	const DevLayout & lay = ctx->lay;
+	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO) {
+		TB_FAIL(ctx, "Held-Suarez physics needs the nonhydrostatic equation set");
+	}
+	if (ctx->d_hs_lat == 0) TB_FAIL(ctx, "Held-Suarez inputs not uploaded (tb200_upload_held_suarez)");
+	for (int c = 0; c < 5; c++) {
+		if (c != 3 && lay.onedge[c]) TB_FAIL(ctx, "Held-Suarez physics: Lorenz staggering only");
+	}
+	HeldSuarezArgs a;
+	a.latitude = ctx->d_hs_lat;
+	a.surface_product = ctx->d_hs_sp;
+	a.dt = dt;
+	// PhysicalConstants.h:361-375
+	a.kappa = ctx->cfg.R / ctx->cfg.cp;
+	a.gamma = ctx->cfg.cp / (ctx->cfg.cp - ctx->cfg.R);
+	a.pressure_scaling = ctx->cfg.p0 * pow(ctx->cfg.R / ctx->cfg.p0, a.gamma);
+	a.R = ctx->cfg.R;
+	a.p0 = ctx->cfg.p0;
+	const long long total = lay.nelem * (long long)lay.nlev * lay.nn;
+	long long nb = (total + 255) / 256;
+	if (nb > 148 * 16) nb = 148 * 16;
+	auto kfn = k_held_suarez;
+	TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(256), 0, ctx->stream, lay, a, ctx->inst[0]);
+	ctx->launches++;
+	ctx->writes++;
+	TB_KERNEL_CHECK(ctx);
 	return 0;
 }
 

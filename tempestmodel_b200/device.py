@@ -155,6 +155,17 @@ class DeviceContext:
         self._ck(self.lib.tb200_upload_rayleigh(self._h, patch, _ptr(a), _ptr(b), _ptr(c),
                                                 _ptr(d)))
 
+    def upload_held_suarez(self, patch, latitude, surface_product):
+        """Per-column inputs of HeldSuarezPhysics::Perform: latitude and the product
+        of the rho and rho-theta slots on the lowest interface of instance 0
+        (HeldSuarezPhysics.cpp:95-115), [iA][iB] with halo."""
+        a, b = _f64(latitude), _f64(surface_product)
+        self._ck(self.lib.tb200_upload_held_suarez(self._h, patch, _ptr(a), _ptr(b)))
+
+    def held_suarez(self, dt):
+        """HeldSuarezPhysics::Perform on instance 0 (device workflow step)."""
+        self._ck(self.lib.tb200_held_suarez(self._h, dt))
+
     def set_node_ids(self, patch, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         self._ck(self.lib.tb200_set_node_ids(self._h, patch, _ptr(ids)))

@@ -203,6 +203,14 @@ CASES["sw2_ne2_energy"] = dict(
     script="energy:e0,0;step:2;energy:e2,0;checksum:cs",
     geometry_from="sw2_ne2_alpha", scalars_only=True)
 
+# Held-Suarez forcing as a workflow step: HeldSuarezPhysics::Perform
+# on the JW state, two applications with different intervals
+CASES["jw_ne2_l30_hs"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "30", "--ztop", "30000", "--pert", "Exp",
+                      "--dt", "200s"],
+    script="addw:0,20000;dss:0;dump:ic,0;hs:1800;dump:hs1,0;hs:250.5;dump:hs2,0",
+    geometry_from="jw_ne2_l30", compact=True, surface_product=True)
+
 _SHARED_PREFIXES = ("patch", "op.", "grid.")
 
 
@@ -266,6 +274,14 @@ def write_golden(name):
     c = CASES[name]
     d = refdump.run_ref_dump("/tmp/tb200_%s.bin" % name, c["case"], c["script"], c["flags"],
                              npatch=c.get("npatch", 6))
+    if c.get("surface_product"):
+        # the slots HeldSuarezPhysics takes its surface pressure from: rho and
+        # rho-theta on the lowest interface (invalid location, dropped by _compact)
+        n = 0
+        while "ic.patch%d.inst0.redge" % n in d:
+            e = d["ic.patch%d.inst0.redge" % n]
+            d["hs.patch%d.surface_product" % n] = e[4, :, :, 0] * e[2, :, :, 0]
+            n += 1
     if c.get("compact"):
         d = _compact(d)
     if c.get("scalars_only"):

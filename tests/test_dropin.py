@@ -140,3 +140,31 @@ def test_function_timer_groups(cuda_library, mode):
     for group in ("SNHP", "VSIm", "SaSc"):
         assert counts.get(group, 0) == refcounts[group], (group, counts, refcounts)
     assert counts.get("Comm", 0) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,outputtime", [("plugins", None), ("scheme", None),
+                                             ("scheme", "400s")])
+def test_held_suarez_dropin(cuda_library, mode, outputtime):
+    """Held-Suarez forcing as a workflow process: the reference's
+    HeldSuarezPhysics on the host arrays under --b200 none against
+    HeldSuarezPhysicsB200, which applies it to instance 0 on the device (under
+    TimestepSchemeB200 without any bus traffic, also when an output manager reads
+    the host copy every second step).  JW ne=4 L10, 6 steps of 200 s; the forcing
+    changes rho-theta, so that checksum is no longer a conserved number: it is
+    compared with the reference run like the others."""
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "jw", "--resolution", "4", "--levels", "10", "--dt", "200s",
+             "--endtime", "1200s", "--heldsuarez", "1"]
+    if outputtime is not None:
+        flags += ["--outputtime", outputtime]
+    ref, _ = run("none", *flags)
+    plain, _ = run("none", *[f for f in flags if f not in ("--heldsuarez", "1")], "--heldsuarez", "0")
+    got, _ = run(mode, *flags)
+    # the forcing is seen at all (friction + relaxation change the sums) ...
+    assert abs(ref["RhoTheta"] - plain["RhoTheta"]) > 1e-9 * abs(plain["RhoTheta"])
+    # ... and the device applies the same one
+    assert abs(got["Rho"] - ref["Rho"]) <= 1e-12 * abs(ref["Rho"]), (got, ref)
+    assert abs(got["RhoTheta"] - ref["RhoTheta"]) <= 1e-11 * abs(ref["RhoTheta"]), (got, ref)
+    change = abs(ref["U"] - plain["U"])
+    assert abs(got["U"] - ref["U"]) <= 1e-3 * change + 1e-6 * abs(ref["U"]), (got, ref, plain)
