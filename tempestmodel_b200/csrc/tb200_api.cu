@@ -1474,9 +1474,42 @@ static int tracer_stage_fast(
 	ta.dt = dt;
 	const ElemList el = elem_list(ctx, 0);
 	if (el.n == 0) return 0;
-	auto kfn = k_tracer_stage;
-	TB_LAUNCH(kfn, dim3((unsigned)el.n), dim3(TBT_THREADS), 0, ctx->stream,
-		lay, ctx->tables, ta, sb, (const double *)ctx->inst[in], ctx->inst[out], el);
+	// stage base of at most two terms: pipelined kernel (bulk copies one element
+	// ahead); TB200_TRACER_STAGE_KERNEL=plain keeps the block-per-element kernel
+	TracerBase tbse;
+	memset(&tbse, 0, sizeof(tbse));
+	bool fits = true;
+	if (sb.use_out) {
+		tbse.src[0] = ctx->inst[out]; tbse.coeff[0] = 1.0; tbse.nsrc = 1; tbse.exact = 1;
+	} else {
+		if (sb.scale_dst) {
+			tbse.src[0] = ctx->inst[out]; tbse.coeff[0] = sb.cdst; tbse.nsrc = 1; tbse.first_is_dst = 1;
+		}
+		for (int m = 0; m < sb.nsrc; m++) {
+			if (tbse.nsrc == 2) { fits = false; break; }
+			tbse.src[tbse.nsrc] = sb.src[m]; tbse.coeff[tbse.nsrc] = sb.coeff[m]; tbse.nsrc++;
+		}
+		if (tbse.nsrc == 0) fits = false;
+		if (fits && tbse.nsrc == 1 && !tbse.first_is_dst && tbse.coeff[0] == 1.0
+			&& tbse.src[0] == ctx->inst[in]) {
+			tbse.nsrc = 0;        // base = the input tracers: read once
+		}
+	}
+	const size_t smem = tb_tracer_pipe_smem_doubles(lay.nlev, lay.ntr, tbse.nsrc) * sizeof(double) + 1024;
+	const char * force = getenv("TB200_TRACER_STAGE_KERNEL");
+	if (fits && smem <= 227 * 1024 - 1024 && !(force != 0 && strcmp(force, "plain") == 0)) {
+		auto kfn = k_tracer_stage_pipe;
+#ifndef TB200_EMU
+		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+		const dim3 grid((unsigned)persistent_blocks(ctx, kfn, TBT_THREADS, smem, el.n));
+		TB_LAUNCH(kfn, grid, dim3(TBT_THREADS), smem, ctx->stream,
+			lay, ctx->tables, ta, tbse, (const double *)ctx->inst[in], ctx->inst[out], el);
+	} else {
+		auto kfn = k_tracer_stage;
+		TB_LAUNCH(kfn, dim3((unsigned)el.n), dim3(TBT_THREADS), 0, ctx->stream,
+			lay, ctx->tables, ta, sb, (const double *)ctx->inst[in], ctx->inst[out], el);
+	}
 	ctx->launches++;
 	ctx->writes++;
 	TB_LAUNCH_CHECK(ctx);

@@ -90,7 +90,7 @@ struct TracerFastArgs {
 
 // Stage base (Grid::CopyData / LinearCombineData) + horizontal transport + the
 // element-wise positivity filter of every tracer of an element.
-__global__ void __launch_bounds__(TBT_THREADS, 3)
+__global__ void __launch_bounds__(TBT_THREADS, 4)
 k_tracer_stage(
 	DevLayout lay, DevTables t, TracerFastArgs ta, StageBase sb,
 	const double * __restrict__ in, double * out, ElemList el
@@ -157,23 +157,11 @@ k_tracer_stage(
 			tb_ld4g(ta.area + ((size_t)e * L + kc) * NN + i * 4, area);
 		}
 
-		// the loads of tracer c + 1 are issued before the arithmetic of tracer c
-		// (a thread only ever touches its own 32 bytes of a row, so the stage-base
-		// loads may pass the stores of the previous tracer)
-		const size_t oT0 = ebase + (size_t)lay.troff * NN + o4;
-		const size_t tstep = (size_t)L * NN;
-		double qn[4], bn[4];
-		tb_ld4(in + oT0, qn);
-		tb_stage_base4(sb, out, oT0, bn);
 		for (int c = 0; c < lay.ntr; c++) {
-			const size_t oT = oT0 + (size_t)c * tstep;
+			const size_t oT = ebase + (size_t)(lay.troff + c * L) * NN + o4;
 			double q[4], b[4];
-#pragma unroll
-			for (int j = 0; j < 4; j++) { q[j] = qn[j]; b[j] = bn[j]; }
-			if (c + 1 < lay.ntr) {
-				tb_ld4(in + oT + tstep, qn);
-				tb_stage_base4(sb, out, oT + tstep, bn);
-			}
+			tb_ld4(in + oT, q);
+			tb_stage_base4(sb, out, oT, b);
 			double fA[4], fB[4], dDa[4];
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
@@ -202,6 +190,210 @@ k_tracer_stage(
 			if (ta.area != 0) tb_filter_level(b, area);
 			if (active) tb_st4(out + oT, b);
 		}
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Pipelined variant of k_tracer_stage: persistent blocks, everything an element
+// needs - its u, v, w rows, its tracer rows, the tracer rows of the stage-base
+// sources, column constants and element areas - arrives by bulk asynchronous
+// copies (cp.async.bulk, contiguous runs of 128-byte rows, completion on an
+// mbarrier) one element ahead, so that a whole element per block is always in
+// flight and no warp waits on a global load.  Same arithmetic as k_tracer_stage.
+
+struct TracerBase {
+	const double * src[2];    // instances the base is combined from (Grid::LinearCombineData order)
+	double coeff[2];
+	int nsrc;                 // 0: base = the input tracers (CopyData of the input instance)
+	int first_is_dst;         // src[0] is the update instance itself (scaled by coeff[0])
+	int exact;                // one source taken as it is (the update instance was pre-filled)
+};
+
+__host__ __device__ inline size_t tb_tracer_pipe_buffer_doubles(int L, int ntr, int nsrc) {
+	// u, v [2 L], w [L + 1], tracers [ntr L], base [nsrc][ntr L], column constants, areas [L]
+	return ((size_t)(3 * L + 1) + (size_t)ntr * L * (1 + nsrc) + TBF_NC + L) * 16;
+}
+__host__ __device__ inline size_t tb_tracer_pipe_smem_doubles(int L, int ntr, int nsrc) {
+	return 2 * tb_tracer_pipe_buffer_doubles(L, ntr, nsrc) + 16 + 4;
+}
+
+__global__ void __launch_bounds__(TBT_THREADS, 2)
+k_tracer_stage_pipe(
+	DevLayout lay, DevTables t, TracerFastArgs ta, TracerBase tbse,
+	const double * __restrict__ in, double * out, ElemList el
+) {
+	const int NN = 16;
+	const int L = lay.nlev;
+	const int ntr = lay.ntr;
+	const int nsrc = tbse.nsrc;
+	TB_DYN_SMEM(double, sm_raw);
+	double * sm = tb_smem_aligned(sm_raw);
+	const size_t bufd = tb_tracer_pipe_buffer_doubles(L, ntr, nsrc);
+	tb_mbar_t * bars = reinterpret_cast<tb_mbar_t *>(sm + 2 * bufd);
+
+	const int tid = threadIdx.x;
+	const int kq = tid >> 2;
+	const int i = tid & 3;
+	const size_t esz = (size_t)lay.nrows * NN;
+	const size_t trows = (size_t)ntr * L * NN;        // doubles of the tracer rows of an element
+	const unsigned bytes = (unsigned)(bufd * sizeof(double));
+
+	double stI[4];
+#pragma unroll
+	for (int s = 0; s < 4; s++) stI[s] = t.st[i * 4 + s];
+
+	long long w = blockIdx.x;
+	if (w >= el.n) return;
+	if (tid == 0) {
+		tb_mbar_init(&bars[0], 1);
+		tb_mbar_init(&bars[1], 1);
+		tb_mbar_fence_init();
+	}
+	__syncthreads();
+
+	// buffer layout (doubles): u [L], v [L], w [L+1], tracers, base 0, base 1, colc, area
+	const size_t oU = 0, oV = (size_t)L * NN, oW = (size_t)2 * L * NN;
+	const size_t oT = oW + (size_t)(L + 1) * NN;
+	const size_t oB = oT + trows;
+	const size_t oC = oB + (size_t)nsrc * trows;
+	const size_t oA = oC + (size_t)TBF_NC * NN;
+
+	auto fetch = [&](long long e, int buf) {
+		double * d = sm + (size_t)buf * bufd;
+		const double * ge = in + (size_t)e * esz;
+		tb_mbar_expect(&bars[buf], bytes);
+		tb_bulk_1d(d + oU, ge + (size_t)lay.rowoff[0] * NN, (unsigned)(L * NN * 8), &bars[buf]);
+		tb_bulk_1d(d + oV, ge + (size_t)lay.rowoff[1] * NN, (unsigned)(L * NN * 8), &bars[buf]);
+		tb_bulk_1d(d + oW, ge + (size_t)lay.rowoff[3] * NN, (unsigned)((L + 1) * NN * 8), &bars[buf]);
+		tb_bulk_1d(d + oT, ge + (size_t)lay.troff * NN, (unsigned)(trows * 8), &bars[buf]);
+		for (int m = 0; m < nsrc; m++) {
+			tb_bulk_1d(d + oB + (size_t)m * trows,
+				tbse.src[m] + (size_t)e * esz + (size_t)lay.troff * NN, (unsigned)(trows * 8), &bars[buf]);
+		}
+		tb_bulk_1d(d + oC, ta.colc + (size_t)e * TBF_NC * NN, (unsigned)(TBF_NC * NN * 8), &bars[buf]);
+		tb_bulk_1d(d + oA, ta.area + (size_t)e * L * NN, (unsigned)(L * NN * 8), &bars[buf]);
+	};
+
+	long long e = tb_elem(el, w);
+	if (tid == 0) fetch(e, 0);
+
+	for (int it = 0; ; it++) {
+		w += gridDim.x;
+		const bool has_next = (w < el.n);
+		const long long en = has_next ? tb_elem(el, w) : 0;
+		const int buf = it & 1;
+		// this element has landed, and every thread is done with the other buffer
+		tb_mbar_wait(&bars[buf], (unsigned)(it >> 1) & 1u);
+		__syncthreads();
+		if (tid == 0 && has_next) fetch(en, buf ^ 1);
+
+		const double * d = sm + (size_t)buf * bufd;
+		const double * cc = d + oC + i * 4;
+		const double dInvDA = __ldg(ta.inv_da + e);
+		const double dInvDB = __ldg(ta.inv_db + e);
+		const double dt = ta.dt;
+		double cA0[4], cA1[4], cB1[4], cJ[4], cIJ[4], cA2[4], cB2[4];
+		tb_ld4(cc + TBF_A0 * NN, cA0);
+		tb_ld4(cc + TBF_A1 * NN, cA1);
+		tb_ld4(cc + TBF_B1 * NN, cB1);
+		tb_ld4(cc + TBF_JAC * NN, cJ);
+		tb_ld4(cc + TBF_INVJAC * NN, cIJ);
+		tb_ld4(cc + TBF_A2 * NN, cA2);
+		tb_ld4(cc + TBF_B2 * NN, cB2);
+		double * oute = out + (size_t)e * esz + (size_t)lay.troff * NN;
+
+		for (int k0 = 0; k0 < L; k0 += TBT_KB) {
+			const int k = k0 + kq;
+			const bool active = (k < L);
+			const int kc = active ? k : (L - 1);
+			const size_t o4 = (size_t)kc * NN + i * 4;
+			const double * lv = ta.lev + (size_t)kc * TBF_LW;
+			const double sn = __ldg(lv + TBF_SN);
+			const double cw0 = __ldg(lv + TBF_CW + 0), cw1 = __ldg(lv + TBF_CW + 1);
+
+			double u[4], v[4], w0[4], wp[4];
+			tb_ld4(d + oU + o4, u);
+			tb_ld4(d + oV + o4, v);
+			tb_ld4(d + oW + o4, w0);
+			tb_ld4(d + oW + o4 + NN, wp);
+
+			// mass fluxes per unit tracer density (:916-929, 1050-1077)
+			double fa[4], fb[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				double x = 0.0;
+				x += cw0 * w0[j];
+				x += cw1 * wp[j];
+				const double m2 = sn * cA2[j], m4 = sn * cB2[j];
+				const double conUa = cA0[j] * u[j] + cA1[j] * v[j] + m2 * x;
+				const double conUb = cA1[j] * u[j] + cB1[j] * v[j] + m4 * x;
+				fa[j] = cJ[j] * conUa;
+				fb[j] = cJ[j] * conUb;
+			}
+			double area[4];
+			tb_ld4(d + oA + o4, area);
+
+			for (int c = 0; c < ntr; c++) {
+				const size_t oc = (size_t)c * L * NN + o4;
+				double q[4], b[4];
+				tb_ld4(d + oT + oc, q);
+				// stage base in Grid::LinearCombineData's order (k_lincomb)
+				if (nsrc == 0) {
+#pragma unroll
+					for (int j = 0; j < 4; j++) b[j] = q[j];
+				} else if (tbse.exact) {
+					tb_ld4(d + oB + oc, b);
+				} else {
+					int m0 = 0;
+					if (tbse.first_is_dst) {
+						double s0[4];
+						tb_ld4(d + oB + oc, s0);
+#pragma unroll
+						for (int j = 0; j < 4; j++) b[j] = s0[j] * tbse.coeff[0];
+						m0 = 1;
+					} else {
+#pragma unroll
+						for (int j = 0; j < 4; j++) b[j] = 0.0;
+					}
+					for (int m = m0; m < nsrc; m++) {
+						double s1[4];
+						tb_ld4(d + oB + (size_t)m * trows + oc, s1);
+						const double cf = tbse.coeff[m];
+#pragma unroll
+						for (int j = 0; j < 4; j++) b[j] += s1[j] * cf;
+					}
+				}
+				double fA[4], fB[4], dDa[4];
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					fA[j] = fa[j] * q[j];
+					fB[j] = fb[j] * q[j];
+				}
+				// :1536-1545: dDaTracerFluxA -= flux(s, j) * stiffness(i, s)
+#pragma unroll
+				for (int j = 0; j < 4; j++) dDa[j] = 0.0;
+#pragma unroll
+				for (int s = 0; s < 4; s++) {
+					double r[4];
+					tb_row_from(fA, s, r);
+#pragma unroll
+					for (int j = 0; j < 4; j++) dDa[j] -= r[j] * stI[s];
+				}
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					double dDb = 0.0;
+#pragma unroll
+					for (int s = 0; s < 4; s++) dDb -= fB[s] * t.st[j * 4 + s];
+					const double dDaTracerFluxA = dDa[j] * dInvDA;
+					const double dDbTracerFluxB = dDb * dInvDB;
+					b[j] = b[j] - dt * cIJ[j] * (dDaTracerFluxA + dDbTracerFluxB);
+				}
+				tb_filter_level(b, area);
+				if (active) tb_st4(oute + oc, b);
+			}
+		}
+		if (!has_next) break;
+		e = en;
 	}
 }
 
@@ -361,6 +553,7 @@ k_column_tracers_fast(
 	const double cA2 = ccol[TBF_A2 * NN], cB2 = ccol[TBF_B2 * NN];
 	const double cX0 = ccol[TBF_X0 * NN], cX2 = ccol[TBF_X2 * NN];
 	const double dInvDeltaT = 1.0 / ta.dt;
+	const double cIJ = 1.0 / cJ;
 
 	// interface m (1 <= m <= L-1) from levels m-1, m: xi-dot before (xi) and after
 	// (xn) the solve, jump factor sign(xi-dot) g^{xi xi} (w_new - w_old)
@@ -438,7 +631,9 @@ k_column_tracers_fast(
 		const double i00 = lv[TBF_CILO + 0], i01 = lv[TBF_CILO + 1];   // InterpNodeToREdge(r; r-1, r)
 		const double i10 = lv1[TBF_CILO + 0], i11 = lv1[TBF_CILO + 1]; // InterpNodeToREdge(r+1; r, r+1)
 		double sub = 0.0, diag = 0.0, sup = 0.0;
-		const double e0 = d0 * cJ / cJ, e1 = d1 * cJ / cJ;
+		// (the reference forms coeff * J(interface) / J(level): the two Jacobians
+		// are the same number for this metric)
+		const double e0 = d0, e1 = d1;
 		if (r >= 1) {
 			sub += e0 * i00 * xi0;
 			diag += e0 * i01 * xi0;
@@ -467,7 +662,7 @@ k_column_tracers_fast(
 			}
 			double f = 0.0;
 			f += d0 * mf0[c]; f += d1 * mf1;
-			f = f / cJ;
+			f = f * cIJ;
 			mf0[c] = mf1;
 			double aux = 0.0;
 			if (inner) {
@@ -552,12 +747,13 @@ k_column_tracers_fast(
 		const double u0 = sU[(size_t)(0 * L + j) * T];
 		const double u1 = sU[(size_t)(1 * L + j) * T];
 		const double u2 = sU[(size_t)(2 * L + j) * T];
+		const double ru0 = 1.0 / u0;       // one reciprocal for the NT right-hand sides
 #pragma unroll
 		for (int c = 0; c < NT; c++) {
 			double b = sY[(size_t)(c * L + j) * T];
 			b -= x2[c] * u2;
 			b -= x1[c] * u1;
-			if (b != 0.0) b = b / u0;
+			b = b * ru0;
 			x2[c] = x1[c];
 			x1[c] = b;
 			if (!(b == b)) bad = true;

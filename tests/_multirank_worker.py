@@ -42,11 +42,17 @@ def main():
     dumpctx.upload_tag(ctx, d, "ic")
     for m in range(1, ctx.cfg.ninstances):
         ctx.copy(0, m)
-    ctx.step(scheme, True, False, 200.0)
-    ctx.step(scheme, False, False, 200.0)
+    nsteps = int(os.environ.get("TB_WORKER_STEPS", "2"))
+    for s in range(nsteps):
+        ctx.step(scheme, s == 0, False, 200.0)
     ctx.check_errors()
     errs = dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3])
     worst = max(errs.values())
+    if dumpctx.S(d, "grid.ntracers") > 0:
+        # tracers travel in the same exchange as the state (one DSS pass)
+        terrs = dumpctx.compare_tracers(ctx, d, 0, "st")
+        assert max(terrs.values()) < 1e-9, terrs
+        errs.update(terrs)
     t = torch.tensor([worst], dtype=torch.float64, device="cuda" if cuda else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     s, r = ctx.exchange_counts(world)

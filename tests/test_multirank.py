@@ -32,6 +32,12 @@ def test_three_ranks_gloo(emu_library):
     _run("gloo", nproc=3, port=29617)
 
 
+def test_two_ranks_gloo_tracers(emu_library):
+    """Tracers on two ranks: state and tracer rows cross in one exchange per DSS
+    (three Strang steps of the golden tracer case)."""
+    _run("gloo", port=29619, case="jwtr_ne2_l6_strang", env={"TB_WORKER_STEPS": "3"})
+
+
 def test_two_ranks_gloo_overlap(emu_library):
     """Element-list launches of the persistent kernels (exchange-feeding elements
     first, the rest on the second stream): same state."""
@@ -63,6 +69,17 @@ def test_ranks_peer_memory_exchange(cuda_library, nproc):
     if torch.cuda.device_count() < nproc:
         pytest.skip("needs %d GPUs" % nproc)
     _run("nccl", nproc=nproc, port=29615 + nproc, extra=["peer"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_two_ranks_tracers_gpus(cuda_library, mode):
+    """Tracers on two GPUs, peer-memory exchange and NCCL callback."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("nccl", port=29621 + (1 if mode == "nccl" else 0), case="jwtr_ne2_l6_strang",
+         env={"TB_WORKER_STEPS": "3"}, extra=["peer"] if mode == "peer" else [])
 
 
 # ---- the decomposition the multi-GPU bench lines use: 24 patches, L = 30 -------

@@ -316,3 +316,27 @@ def test_tracers_l30(library, monkeypatch, kernels):
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     assert_below(dumpctx.compare_tracers(ctx, d, 0, "st"), 1e-9)
     ctx.close()
+
+
+def test_tracer_stage_kernels_agree(library, monkeypatch):
+    """The pipelined tracer stage kernel (persistent blocks, bulk copies one
+    element ahead) against the block-per-element kernel
+    (TB200_TRACER_STAGE_KERNEL=plain): same arithmetic, to rounding of the
+    compiler's FMA contraction (bit-identical on the emulation)."""
+    d = cases.load_case("jwtr_ne2_l30")
+    res = []
+    for plain in (False, True):
+        if plain:
+            monkeypatch.setenv("TB200_TRACER_STAGE_KERNEL", "plain")
+        ctx = dumpctx.context_from_dump(d, library=library)
+        dumpctx.upload_tag(ctx, d, "ic")
+        for m in range(1, ctx.cfg.ninstances):
+            ctx.copy(0, m)
+        ctx.step("strang", True, False, 200.0)
+        ctx.step("strang", False, False, 200.0)
+        ctx.check_errors()
+        res.append(dumpctx.download_tracers(ctx, d, 0))
+        ctx.close()
+    for n in res[0]:
+        a, b = np.asarray(res[0][n]), np.asarray(res[1][n])
+        assert np.abs(a - b).max() <= 1e-14 * np.abs(b).max(), n

@@ -21,3 +21,5 @@ PY
 done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 600 --csv --log-file $out/r2j_launches_cfg4.csv python bench.py --ne 60 --tracers 5 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $out/r2j_ncu_bench.log 2>&1
 python tools/launch_summary.py $out/r2j_launches_cfg4.csv 2>&1 | tail -30
+timeout 600 python -m pytest tests/test_physics.py tests/test_dropin.py -m gpu -q -k "held_suarez" 2>&1 | tail -8 > $out/r2j_pytest_hs.txt
+cat $out/r2j_pytest_hs.txt
