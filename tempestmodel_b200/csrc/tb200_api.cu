@@ -933,8 +933,6 @@ extern "C" int tb200_held_suarez(tb200_ctx * ctx, double dt) {
 	if (nb > 148 * 16) nb = 148 * 16;
 	auto kfn = k_held_suarez;
 	TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(256), 0, ctx->stream, lay, a, ctx->inst[0]);
-	ctx->launches++;
-	ctx->writes++;
 	TB_KERNEL_CHECK(ctx);
 	return 0;
 }
@@ -2286,8 +2284,6 @@ static int filter_tracers(
 		TB_LAUNCH_FLAT(kfn, dim3((unsigned)((nitems + block - 1) / block)), dim3(block), 0,
 			ctx->stream, lay, (const double *)ctx->d_area_node, ctx->inst[inst],
 			(comb != 0) ? *comb : none, (comb != 0) ? 1 : 0, inc);
-		ctx->launches++;
-		ctx->writes++;
 	} else {
 		const long long nitems = lay.nelem * lay.ntr * lay.nlev;
 		auto kfn = k_filter_tracers_element;
