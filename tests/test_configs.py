@@ -275,3 +275,71 @@ def test_python_tracer_case_matches_reference(emu_library):
         for c in (2, 4):
             assert np.abs(dev[c] - ref[c]).max() <= 1e-9 * np.abs(ref[c]).max(), (p.index, c)
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tracers", [0, 3])
+def test_device_evaluated_initial_state_equals_host_evaluated(cuda_library, tracers):
+    """Model.device_setup evaluates the closed-form initial state on the GPU (the
+    path the large bench grids take); the numpy path is the one checked against
+    the reference's arrays (test_grid.py, test_python_tracer_case_matches_reference).  Both
+    must give the same state: exp / log / pow / trigonometric functions of the
+    device library against numpy's, 1e-13 of the field."""
+    states = []
+    for dev in (False, True):
+        grid = G.GridCSGLL(4, 10, npatch=6, ztop=30000.0)
+        test = (TC.BaroclinicWaveJWTracerTest(ntracers=tracers, ztop=30000.0, perturbation="exp")
+                if tracers else TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"))
+        model = Model(grid, test, timescheme="strang", dt=200.0, library=cuda_library)
+        model.device_setup = dev
+        model.initialize()
+        st = model.download_state(0)
+        tr = model.download_tracers(0) if tracers else {}
+        states.append((st, tr))
+        model.ctx.close()
+    for idx in states[0][0]:
+        for loc in (0, 1):
+            a, b = states[0][0][idx][loc], states[1][0][idx][loc]
+            for c in range(a.shape[0]):
+                scale = max(np.abs(a[c]).max(), 1e-300)
+                assert np.abs(a[c] - b[c]).max() <= 1e-13 * scale, (idx, loc, c)
+        if tracers:
+            a, b = states[0][1][idx], states[1][1][idx]
+            for c in range(a.shape[0]):
+                assert np.abs(a[c] - b[c]).max() <= 1e-13 * np.abs(a[c]).max(), (idx, c)
+
+
+def test_cubed_sphere_python_setup_matches_reference():
+    """GridCSGLL / BaroclinicWaveJWTest of the Python driver (numpy) against the
+    reference's own arrays (golden jw_ne2_l30 dump): 2-D and 3-D metric, element
+    areas, and the initial state on levels (GridPatchCSGLL.cpp:295-574, 578-920;
+    BaroclinicWaveJWTest.cpp:297-413).  The device-evaluated initial state of the
+    bench runs is held to this numpy path by
+    test_device_evaluated_initial_state_equals_host_evaluated."""
+    import cases
+    import dumpctx
+    d = cases.load_case("jw_ne2_l30")
+    grid = G.GridCSGLL(2, 30, npatch=6, ztop=30000.0)
+    test = TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp")
+    grid.evaluate_topography(test)
+    I = (slice(1, -1), slice(1, -1))
+    for p in grid.patches:
+        n = p.index
+        geo = p.evaluate_geometric_terms(p._zs, p._dazs, p._dbzs)
+        for key, name in (("jacobian2d", "jacobian2d"), ("contrametric2da", "contrametric2da"),
+                          ("contrametric2db", "contrametric2db"),
+                          ("jacobian", "jacobian"), ("jacobianredge", "jacobian_redge"),
+                          ("contrametrica", "contrametrica"), ("contrametricb", "contrametricb"),
+                          ("contrametricxi", "contrametricxi"),
+                          ("contrametricxiredge", "contrametricxi_redge"),
+                          ("derivrnode", "derivr_node"), ("derivrredge", "derivr_redge")):
+            ref = d["patch%d.%s" % (n, key)][I]
+            got = geo[name][I]
+            assert np.abs(got - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1e-300), (n, key)
+        ref = d["patch%d.elementareanode" % n][I]
+        assert np.abs(p.area_node[I] - ref).max() <= 1e-13 * np.abs(ref).max(), n
+        node, redge = Model.evaluate_test_case(
+            type("S", (), dict(grid=grid, test=test, ncomp=5, device_setup=False))(), p)
+        ref = d["ic.patch%d.inst0.node" % n]
+        for c in (0, 1, 2, 4):
+            assert np.abs(node[c][I] - ref[c][I]).max() <= 1e-12 * max(np.abs(ref[c]).max(), 1.0), (n, c)
