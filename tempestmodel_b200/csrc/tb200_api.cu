@@ -1983,15 +1983,34 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 #endif
 		// scratch: 10 n doubles per column, columns padded to whole blocks
 		const size_t ws_doubles = (size_t)tb_column_ws_entries(lay.nlev, ctx->offd) * ctx->ws_cols;
+		const size_t per_block = (size_t)30 * (lay.nlev + 1) * TBC_THREADS;
+		const long long nbatches_all = (ctx->ncols + TBC_THREADS - 1) / TBC_THREADS;
+		// Persistent blocks (default): every resident block walks the batches
+		// blockIdx.x, + gridDim.x, ... and reuses its own scratch slot, so that
+		// the rows of U of a finished batch are overwritten in L2 instead of being
+		// written back.  TB200_COLUMN_PERSISTENT=0: one block per batch, chunked
+		// launches sized by the scratch (round-1 behaviour).
+		const char * pers = getenv("TB200_COLUMN_PERSISTENT");
+		long long grid_p = persistent_blocks(ctx, kfn, TBC_THREADS, smem, nbatches_all);
+		if (!(pers != 0 && strcmp(pers, "0") == 0) && (size_t)grid_p * per_block <= ws_doubles) {
+			fa.col0 = 0;
+			fa.ncols = ctx->ncols;
+			TB_LAUNCH(kfn, dim3((unsigned)grid_p), dim3(TBC_THREADS),
+				smem, ctx->stream, lay, ctx->phys, fa,
+				(const double *)ctx->inst[in], ctx->inst[out], (int)nbatches_all);
+			TB_KERNEL_CHECK(ctx);
+			return 0;
+		}
 		long long chunk = (long long)(ws_doubles / ((size_t)30 * (lay.nlev + 1))) / TBC_THREADS * TBC_THREADS;
 		if (chunk < TBC_THREADS) TB_FAIL(ctx, "column workspace too small");
 		if (chunk > ctx->ncols) chunk = ((ctx->ncols + TBC_THREADS - 1) / TBC_THREADS) * TBC_THREADS;
 		for (int c0 = 0; c0 < ctx->ncols; c0 += (int)chunk) {
 			fa.col0 = c0;
 			fa.ncols = (int)std::min<long long>(chunk, ctx->ncols - c0);
-			TB_LAUNCH(kfn, dim3((fa.ncols + TBC_THREADS - 1) / TBC_THREADS), dim3(TBC_THREADS),
+			const int nb = (fa.ncols + TBC_THREADS - 1) / TBC_THREADS;
+			TB_LAUNCH(kfn, dim3(nb), dim3(TBC_THREADS),
 				smem, ctx->stream, lay, ctx->phys, fa,
-				(const double *)ctx->inst[in], ctx->inst[out]);
+				(const double *)ctx->inst[in], ctx->inst[out], nb);
 			TB_KERNEL_CHECK(ctx);
 		}
 		return 0;

@@ -70,24 +70,22 @@ __device__ __forceinline__ double tb_signw(double xd, double cx2) {
 	return 0.0;
 }
 
-__global__ void __launch_bounds__(TBC_THREADS)
-k_column_fast(
-	DevLayout lay, DevPhys ph, ColumnFastArgs ca,
-	const double * in, double * out   // may alias
+// One batch of TBC_THREADS columns: batch `vblock` of the launch, scratch slot
+// `pblock` (the block's own: a block that walks several batches reuses it, so
+// that the rows of U it wrote for the previous batch - read back and dead by
+// then - are overwritten while they still sit in L2 instead of being written
+// back to DRAM).
+__device__ __forceinline__ void tb_column_fast_batch(
+	const DevLayout & lay, const DevPhys & ph, const ColumnFastArgs & ca,
+	const double * in, double * out, const double * slev, unsigned * smask,
+	int vblock, int pblock
 ) {
-	TB_DYN_SMEM(double, slev);          // [L+1][TBF_LW], then row masks [warps][n]
 	const int L = lay.nlev;
 	const int NN = lay.nn;
 	const int n = 3 * (L + 1);
-	unsigned * smask = reinterpret_cast<unsigned *>(slev + (size_t)(L + 1) * TBF_LW)
-		+ (size_t)(threadIdx.x >> 5) * n;
 	const unsigned FULL = 0xffffffffu;
-	for (int q = threadIdx.x; q < (L + 1) * TBF_LW; q += blockDim.x) {
-		slev[q] = ca.lev[q];
-	}
-	__syncthreads();
 
-	int tcol = blockIdx.x * blockDim.x + threadIdx.x;
+	int tcol = vblock * blockDim.x + threadIdx.x;
 	const bool live = (tcol < ca.ncols);
 	if (!live) tcol = ca.ncols - 1;      // keep the warp converged; no stores
 
@@ -119,7 +117,7 @@ k_column_fast(
 	// right-hand side and the off-diagonal entries of its mask
 	const int S = 32;
 	double * sc = ca.ws
-		+ ((size_t)blockIdx.x * (TBC_THREADS / 32) + (threadIdx.x >> 5)) * (size_t)(10 * n) * S
+		+ ((size_t)pblock * (TBC_THREADS / 32) + (threadIdx.x >> 5)) * (size_t)(10 * n) * S
 		+ (threadIdx.x & 31);
 	double * scp = sc;      // next free slot
 
@@ -601,6 +599,29 @@ k_column_fast(
 		}
 	}
 	if (nan_seen) atomicMax(ca.info, ca.col0 + tcol + 1);
+}
+
+
+__global__ void __launch_bounds__(TBC_THREADS)
+k_column_fast(
+	DevLayout lay, DevPhys ph, ColumnFastArgs ca,
+	const double * in, double * out,  // may alias
+	int nbatches
+) {
+	TB_DYN_SMEM(double, slev);          // [L+1][TBF_LW], then row masks [warps][n]
+	const int L = lay.nlev;
+	const int n = 3 * (L + 1);
+	unsigned * smask = reinterpret_cast<unsigned *>(slev + (size_t)(L + 1) * TBF_LW)
+		+ (size_t)(threadIdx.x >> 5) * n;
+	for (int q = threadIdx.x; q < (L + 1) * TBF_LW; q += blockDim.x) {
+		slev[q] = ca.lev[q];
+	}
+	__syncthreads();
+	// warps are independent from here on (no block barrier in a batch)
+	for (int vb = blockIdx.x; vb < nbatches; vb += gridDim.x) {
+		tb_column_fast_batch(lay, ph, ca, in, out, slev, smask, vb, blockIdx.x);
+		__syncwarp();
+	}
 }
 
 #endif

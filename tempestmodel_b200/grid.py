@@ -447,7 +447,14 @@ class GridCSGLL:
         allv = np.concatenate(grads)
         uniq, inv = np.unique(allid, return_inverse=True)
         cnt = np.bincount(inv).astype(np.float64)
-        avg = np.stack([np.bincount(inv, weights=allv[:, c]) / cnt for c in range(3)], axis=1)
+        # the 2 - 4 contributions of a node are summed in ascending order of their
+        # values, not in the order the patches are listed: the metric (and with it
+        # the state) must not depend on how a panel is cut into patches
+        avg = np.empty((len(uniq), 3))
+        for c in range(3):
+            order = np.lexsort((allv[:, c], inv))
+            starts = np.searchsorted(inv[order], np.arange(len(uniq)))
+            avg[:, c] = np.add.reduceat(allv[order, c], starts) / cnt
         off = 0
         for p, (ea, eb) in zip(self.patches, meta):
             n = p.XX.size

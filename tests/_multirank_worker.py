@@ -53,14 +53,22 @@ def main():
         terrs = dumpctx.compare_tracers(ctx, d, 0, "st")
         assert max(terrs.values()) < 1e-9, terrs
         errs.update(terrs)
+    dump = os.environ.get("TB_WORKER_DUMP")
+    if dump:
+        # raw state of the local patches, for bit-for-bit comparisons between runs
+        # on different numbers of ranks
+        got = dumpctx.download(ctx, d, 0)
+        np.savez(dump + ".rank%d.npz" % rank,
+                 **{"p%d.%s" % (n, loc): got[n][q] for n in got for q, loc in ((0, "node"), (1, "redge"))})
     t = torch.tensor([worst], dtype=torch.float64, device="cuda" if cuda else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     s, r = ctx.exchange_counts(world)
     if rank == 0:
         print("MULTIRANK worst=%.3e exchanges=%d send_nodes=%s" % (t.item(), ex.calls, s.tolist()))
-    assert s.sum() > 0
-    # peer-memory exchange: the callback is never used
-    assert (ex.calls == 0) if peer else (ex.calls > 0)
+    if world > 1:
+        assert s.sum() > 0
+        # peer-memory exchange: the callback is never used
+        assert (ex.calls == 0) if peer else (ex.calls > 0)
     assert t.item() < 1e-10, errs
     dist.destroy_process_group()
 

@@ -3,7 +3,11 @@ bench.py's headline workload (JW baroclinic wave ne = 120, L = 30, strang,
 dt = 33.333333 s) after every step: tests/golden/bench_checksums.json, which
 bench.py's `parity` block compares the device state with.
 
-    python tests/make_bench_checksums.py [nsteps]
+    python tests/make_bench_checksums.py [nsteps [npatch]]
+
+(npatch = 24, the decomposition of the multi-GPU bench lines, is stored under
+"reference_npatch24": the reference's own result depends on the decomposition
+at the level of its sensitivity to rounding)
 
 About 35 GB of host memory and 45 minutes on one core (10 minutes of serial
 set-up, 75 s per step), which is why the numbers are committed rather than
@@ -22,18 +26,25 @@ OUT = os.path.join(refdump.GOLDEN, "bench_checksums.json")
 
 if __name__ == "__main__":
     nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 28
+    npatch = int(sys.argv[2]) if len(sys.argv) > 2 else 6
     script = "copy:0,3;energy:e0,3;checksum:c0"
     for i in range(1, nsteps + 1):
         script += ";step:1;checksum:c%d" % i
     script += ";copy:0,3;energy:e%d,3" % nsteps
-    d = refdump.run_ref_dump("/tmp/ref120.bin", "jw", script,
+    d = refdump.run_ref_dump("/tmp/ref120_p%d.bin" % npatch, "jw", script,
                              ["--resolution", "120", "--levels", "30", "--dt", "33333333u",
-                              "--nogeometry", "1"], timeout=4 * 3600)
+                              "--nogeometry", "1"], npatch=npatch, timeout=4 * 3600)
     table = {}
     if os.path.exists(OUT):
         with open(OUT) as f:
             table = json.load(f)
     entry = table.setdefault(KEY, {})
+    if npatch != 6:
+        entry["reference_npatch%d" % npatch] = {
+            str(i): d["c%d.checksum" % i].tolist() for i in range(nsteps + 1)}
+        with open(OUT, "w") as f:
+            json.dump(table, f, indent=1, sort_keys=True)
+        sys.exit(0)
     entry["reference"] = {str(i): d["c%d.checksum" % i].tolist() for i in range(nsteps + 1)}
     entry["reference_energy"] = {"0": d["e0.energy"].tolist(),
                                  str(nsteps): d["e%d.energy" % nsteps].tolist()}

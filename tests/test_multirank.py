@@ -82,6 +82,54 @@ def test_two_ranks_tracers_gpus(cuda_library, mode):
          env={"TB_WORKER_STEPS": "3"}, extra=["peer"] if mode == "peer" else [])
 
 
+def _states(tag):
+    import glob
+    import numpy as np
+    out = {}
+    for f in glob.glob("/tmp/tb200_mr_%s.rank*.npz" % tag):
+        with np.load(f) as z:
+            for k in z.files:
+                out[k] = z[k]
+        os.remove(f)
+    return out
+
+
+def test_ranks_do_not_change_the_bits(emu_library):
+    """The same 24 patches on one rank and on four: the state after two Strang
+    steps is the same bit for bit (members of an averaging group are ordered by
+    their position on the panel, remote members enter the average exactly as
+    local ones do, every rank solves its own copy of a shared column from
+    identical inputs).  What does change the last bit is the decomposition
+    itself - which copy of a shared column a patch solves - see bench.py."""
+    import numpy as np
+    res = []
+    for nproc, port in ((1, 29651), (4, 29652)):
+        _run("gloo", nproc=nproc, port=port, case="jw_ne4_l30_p24",
+             env={"TB_WORKER_DUMP": "/tmp/tb200_mr_w%d" % nproc})
+        res.append(_states("w%d" % nproc))
+    assert len(res[0]) == 48 and set(res[0]) == set(res[1])
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+
+
+@pytest.mark.gpu
+def test_ranks_do_not_change_the_bits_gpus(cuda_library):
+    """The same on GPUs: one device against four (peer-memory exchange)."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    res = []
+    for nproc, port in ((1, 29653), (4, 29654)):
+        _run("nccl", nproc=nproc, port=port, case="jw_ne4_l30_p24",
+             extra=["peer"] if nproc > 1 else [],
+             env={"TB_WORKER_DUMP": "/tmp/tb200_mr_g%d" % nproc})
+        res.append(_states("g%d" % nproc))
+    assert len(res[0]) == 48 and set(res[0]) == set(res[1])
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+
+
 # ---- the decomposition the multi-GPU bench lines use: 24 patches, L = 30 -------
 
 @pytest.mark.parametrize("nproc", [4, 8])
