@@ -4,7 +4,7 @@
 # dry stand-in on the column-constant path)
 out=gpurun_out
 mkdir -p $out
-timeout 900 python -m pytest tests/test_multirank.py -m gpu -q -k "tracers or (24_patches and 8)" 2>&1 | tail -6 > $out/r2k_pytest_multirank.txt
+timeout 900 python -m pytest tests/test_multirank.py -m gpu -q -k "tracers or bits or (24_patches and 8)" 2>&1 | tail -6 > $out/r2k_pytest_multirank.txt
 cat $out/r2k_pytest_multirank.txt
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29701 bench.py --gpus 8 --steps 20 --warmup 5 2> $out/r2k_bench_n8.err | grep "^{" > $out/r2k_bench_n8.json
