@@ -24,6 +24,7 @@
 #include "tb200_tracers_fast.cuh"
 #include "tb200_diag.cuh"
 #include "tb200_physics.cuh"
+#include "tb200_setup.cuh"
 
 static_assert(TBT_C_JAC == TBF_JAC && TBT_C_A2 == TBF_A2 && TBT_C_B2 == TBF_B2
 	&& TBT_C_X0 == TBF_X0 && TBT_C_X2 == TBF_X2 && TBT_C_NC == TBF_NC
@@ -881,6 +882,110 @@ extern "C" int tb200_upload_rayleigh(
 	ctx->inst.pop_back();
 	if (rc) return 1;
 	ctx->has_rayleigh = true;
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Device-side set-up (tb200_setup.cuh)
+
+// 2-D metric, Coriolis parameter, longitude and latitude of a cubed-sphere patch
+// from X = tan(alpha), Y = tan(beta) (tb200_set_terrain_metric): what
+// GridPatchCSGLL::EvaluateGeometricTerms leaves in GetJacobian2D(),
+// GetContraMetric2DA/B(), GetCoriolisF(), GetLongitude(), GetLatitude().
+extern "C" int tb200_evaluate_geometry_cs(
+	tb200_ctx * ctx, int patch_index, double radius, double omega
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	if (ctx->d_tx == 0) TB_FAIL(ctx, "node coordinates not set (tb200_set_terrain_metric)");
+	const DevLayout & lay = ctx->lay;
+	if (ctx->d_hs_lat == 0) {
+		if (dalloc(ctx, &ctx->d_hs_lat, (size_t)lay.nelem * lay.nn)) return 1;
+		if (dalloc(ctx, &ctx->d_hs_sp, (size_t)lay.nelem * lay.nn)) return 1;
+	}
+	if (ctx->d_lon == 0) {
+		if (dalloc(ctx, &ctx->d_lon, (size_t)lay.nelem * lay.nn)) return 1;
+	}
+	CsGeomOut o;
+	o.j2d = ctx->g2d[0]; o.a0 = ctx->g2d[1]; o.a1 = ctx->g2d[2];
+	o.b0 = ctx->g2d[3]; o.b1 = ctx->g2d[4]; o.coriolis = ctx->g2d[5];
+	o.lon = ctx->d_lon; o.lat = ctx->d_hs_lat;
+	const long long nelem = (long long)pi->nea * pi->neb;
+	const long long total = nelem * lay.nn;
+	auto kfn = k_cs_geometry_2d;
+	TB_LAUNCH_FLAT(kfn, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ctx->stream,
+		lay.nn, (long long)pi->elem0, nelem, pi->panel, radius, omega,
+		(const double *)ctx->d_tx, (const double *)ctx->d_ty, o);
+	TB_KERNEL_CHECK(ctx);
+	pi->has_lonlat = true;
+	return 0;
+}
+
+static JWParams jw_params(const tb200_ctx * ctx, const tb200_jw_test * t) {
+	JWParams P;
+	P.eta0 = t->eta0; P.tropopause_eta = t->tropopause_eta; P.t0 = t->t0;
+	P.delta_t = t->delta_t; P.lapse_rate = t->lapse_rate; P.u0 = t->u0; P.up = t->up;
+	P.pert_lon = t->pert_lon; P.pert_lat = t->pert_lat; P.pert_r = t->pert_r;
+	P.perturbation = t->perturbation;
+	P.g = ctx->cfg.g; P.R = ctx->cfg.R; P.p0 = ctx->cfg.p0;
+	P.omega = t->omega; P.radius = t->radius;
+	// PhysicalConstants.h:361-375
+	P.gamma = ctx->cfg.cp / (ctx->cfg.cp - ctx->cfg.R);
+	P.pressure_scaling = ctx->cfg.p0 * pow(ctx->cfg.R / ctx->cfg.p0, P.gamma);
+	P.ztop = ctx->cfg.ztop;
+	return P;
+}
+
+// BaroclinicWaveJWTest::EvaluateTopography on the nodes of a patch (into the
+// topography array of the geometry); needs tb200_evaluate_geometry_cs.
+extern "C" int tb200_evaluate_jw_topography(
+	tb200_ctx * ctx, int patch_index, const tb200_jw_test * test
+) {
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	if (!pi->has_lonlat) TB_FAIL(ctx, "longitude / latitude not evaluated (tb200_evaluate_geometry_cs)");
+	const DevLayout & lay = ctx->lay;
+	const long long nelem = (long long)pi->nea * pi->neb;
+	const long long total = nelem * lay.nn;
+	auto kfn = k_jw_topography;
+	TB_LAUNCH_FLAT(kfn, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ctx->stream,
+		lay.nn, (long long)pi->elem0, nelem, jw_params(ctx, test),
+		(const double *)ctx->d_hs_lat, ctx->g2d[6]);
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
+// GridPatchCSGLL::EvaluateTestCase for BaroclinicWaveJWTest: the initial state of
+// a patch written straight into instance `inst` (tracers are not touched).
+extern "C" int tb200_evaluate_jw_state(
+	tb200_ctx * ctx, int patch_index, int inst, const tb200_jw_test * test
+) {
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid instance");
+	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO) TB_FAIL(ctx, "the JW test needs the nonhydrostatic equation set");
+	if (!pi->has_lonlat) TB_FAIL(ctx, "longitude / latitude not evaluated (tb200_evaluate_geometry_cs)");
+	if (ctx->d_reta_n == 0) TB_FAIL(ctx, "vertical coordinate not set (tb200_set_vertical_coordinate)");
+	const DevLayout & lay = ctx->lay;
+	const long long nelem = (long long)pi->nea * pi->neb;
+	const long long total = nelem * (long long)(lay.nlev + 1) * lay.nn;
+	long long nb = (total + 127) / 128;
+	if (nb > 148 * 32) nb = 148 * 32;
+	TB_CHECK(ctx, cudaMemset(ctx->d_info + 2, 0, sizeof(int)));
+	auto kfn = k_jw_state;
+	TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(128), 0, ctx->stream,
+		lay, (long long)pi->elem0, nelem, pi->panel, jw_params(ctx, test),
+		(const double *)ctx->d_tx, (const double *)ctx->d_ty,
+		(const double *)ctx->d_lon, (const double *)ctx->d_hs_lat,
+		(const double *)ctx->g2d[6], (const double *)ctx->d_reta_n,
+		ctx->inst[inst], ctx->d_info + 2);
+	TB_KERNEL_CHECK(ctx);
+	int failed = 0;
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	TB_CHECK(ctx, cudaMemcpy(&failed, ctx->d_info + 2, sizeof(int), cudaMemcpyDeviceToHost));
+	// BaroclinicWaveJWTest.cpp:337-339
+	if (failed != 0) TB_FAIL(ctx, "Maximum number of iterations exceeded.");
 	return 0;
 }
 
