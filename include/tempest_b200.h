@@ -301,6 +301,41 @@ int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst);
  * the column-wise filter (the one above is HorizontalDynamicsFEM's element-wise
  * filter, HorizontalDynamicsFEM.cpp:213-317). */
 int tb200_v_filter_negative_tracers(tb200_ctx * ctx, int inst);
+/* ---- device-side set-up of cubed-sphere runs ------------------------
+ * The 2-D metric and the initial state evaluated on the device instead of being
+ * built on the host and copied over the bus.  Needs tb200_set_terrain_metric
+ * (X = tan alpha, Y = tan beta per node), tb200_set_vertical_coordinate and, for
+ * the state, the topography (tb200_evaluate_jw_topography or tb200_upload_geometry). */
+
+/* What GridPatchCSGLL::EvaluateGeometricTerms (src/atm/GridPatchCSGLL.cpp:295-343)
+ * leaves in GetJacobian2D(), GetContraMetric2DA/B(), GetCoriolisF(), GetLongitude()
+ * and GetLatitude() (CubedSphereTrans::RLLFromXYP, CubedSphereTrans.cpp:200-266);
+ * the latitude also feeds tb200_held_suarez. */
+int tb200_evaluate_geometry_cs(tb200_ctx * ctx, int patch_index, double radius, double omega);
+
+/* Debugging aid (cf. tb200_debug_column_assembly): a per-column array in the device's
+ * element-major order [element][np * np]; which = 0 Jacobian2D, 1, 2 ContraMetric2DA,
+ * 3, 4 ContraMetric2DB, 5 CoriolisF, 6 topography, 7 longitude, 8 latitude. */
+int tb200_debug_column_field(tb200_ctx * ctx, int which, double * out);
+
+/* Parameters of BaroclinicWaveJWTest (test/nonhydro_sphere/BaroclinicWaveJWTest.cpp:41-134)
+ * and the constants of the sphere it takes from PhysicalConstants. */
+typedef struct {
+	double eta0, tropopause_eta, t0, delta_t, lapse_rate, u0, up;
+	double pert_lon, pert_lat, pert_r;
+	int perturbation;        /* 1: PerturbationType_Exp, 0: none */
+	double omega, radius;    /* PhysicalConstants::GetOmega(), GetEarthRadius() */
+} tb200_jw_test;
+
+/* BaroclinicWaveJWTest::EvaluateTopography (:170-204) on the nodes of a patch. */
+int tb200_evaluate_jw_topography(tb200_ctx * ctx, int patch_index, const tb200_jw_test * test);
+/* GridPatchCSGLL::EvaluateTestCase (GridPatchCSGLL.cpp:578-920) with
+ * BaroclinicWaveJWTest::EvaluatePointwiseState (:297-413): covariant u_alpha, u_beta,
+ * rho theta, rho on levels and w = 0 on interfaces of state instance `inst`.  Fails with
+ * the reference's "Maximum number of iterations exceeded." when the Newton
+ * iteration for eta does not converge. */
+int tb200_evaluate_jw_state(tb200_ctx * ctx, int patch_index, int inst, const tb200_jw_test * test);
+
 /* HeldSuarezPhysics::Perform (src/atm/HeldSuarezPhysics.cpp:62-301) as a device
  * workflow step on instance 0: boundary-layer friction of u, v and Newtonian
  * relaxation of rho-theta, one streaming pass.  Inputs per column, [iA][iB] in the

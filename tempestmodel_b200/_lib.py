@@ -59,6 +59,14 @@ class Geometry(Structure):
     _fields_ = [(name, c_void_p) for name in GEOMETRY_FIELDS]
 
 
+class JWTest(Structure):
+    """tb200_jw_test: parameters of BaroclinicWaveJWTest."""
+    _fields_ = [(n, c_double) for n in ("eta0", "tropopause_eta", "t0", "delta_t",
+                                         "lapse_rate", "u0", "up", "pert_lon", "pert_lat",
+                                         "pert_r")] \
+        + [("perturbation", c_int), ("omega", c_double), ("radius", c_double)]
+
+
 EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p,
                                POINTER(c_int64), POINTER(c_int64), c_int)
 
@@ -112,6 +120,10 @@ _SIGNATURES = {
     "tb200_filter_negative_tracers": (c_int, [c_void_p, c_int]),
     "tb200_v_filter_negative_tracers": (c_int, [c_void_p, c_int]),
     "tb200_lincomb_v_filter": (c_int, [c_void_p, POINTER(c_double), c_int, c_int]),
+    "tb200_evaluate_geometry_cs": (c_int, [c_void_p, c_int, c_double, c_double]),
+    "tb200_debug_column_field": (c_int, [c_void_p, c_int, c_void_p]),
+    "tb200_evaluate_jw_topography": (c_int, [c_void_p, c_int, POINTER(JWTest)]),
+    "tb200_evaluate_jw_state": (c_int, [c_void_p, c_int, c_int, POINTER(JWTest)]),
     "tb200_upload_held_suarez": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "tb200_held_suarez": (c_int, [c_void_p, c_double]),
     "tb200_scheme_instances": (c_int, [c_int]),

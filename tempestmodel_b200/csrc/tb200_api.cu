@@ -922,6 +922,22 @@ extern "C" int tb200_evaluate_geometry_cs(
 	return 0;
 }
 
+// Read-back of a per-column array in the device's element-major order
+// [element][np * np] (tests of the device-side set-up): 0 Jacobian2D,
+// 1, 2 ContraMetric2DA, 3, 4 ContraMetric2DB, 5 Coriolis, 6 topography,
+// 7 longitude, 8 latitude.
+extern "C" int tb200_debug_column_field(tb200_ctx * ctx, int which, double * out) {
+	const DevLayout & lay = ctx->lay;
+	const double * src = 0;
+	if (which >= 0 && which < 7) src = ctx->g2d[which];
+	else if (which == 7) src = ctx->d_lon;
+	else if (which == 8) src = ctx->d_hs_lat;
+	if (src == 0) TB_FAIL(ctx, "column field not available");
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	TB_CHECK(ctx, cudaMemcpy(out, src, (size_t)lay.nelem * lay.nn * sizeof(double), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
 static JWParams jw_params(const tb200_ctx * ctx, const tb200_jw_test * t) {
 	JWParams P;
 	P.eta0 = t->eta0; P.tropopause_eta = t->tropopause_eta; P.t0 = t->t0;

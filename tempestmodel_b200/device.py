@@ -155,6 +155,40 @@ class DeviceContext:
         self._ck(self.lib.tb200_upload_rayleigh(self._h, patch, _ptr(a), _ptr(b), _ptr(c),
                                                 _ptr(d)))
 
+    # -- device-side set-up (tb200_setup.cuh) ------------------------------------
+    def evaluate_geometry_cs(self, patch, radius, omega):
+        """2-D metric, Coriolis parameter, longitude / latitude of a cubed-sphere
+        patch from the node coordinates already on the device."""
+        self._ck(self.lib.tb200_evaluate_geometry_cs(self._h, patch, radius, omega))
+
+    def column_field(self, which, nelem, nn=16):
+        """Per-column device array [element][np * np] (0 Jacobian2D, 1, 2
+        ContraMetric2DA, 3, 4 ContraMetric2DB, 5 Coriolis, 6 topography, 7 longitude,
+        8 latitude): read-back for tests."""
+        out = np.zeros((nelem, nn))
+        self._ck(self.lib.tb200_debug_column_field(self._h, which, _ptr(out)))
+        return out
+
+    @staticmethod
+    def _jw(test, phys):
+        from ._lib import JWTest
+        return JWTest(eta0=test.eta0, tropopause_eta=test.tropopause_eta, t0=test.t0,
+                      delta_t=test.delta_t, lapse_rate=test.lapse_rate, u0=test.u0,
+                      up=test.up, pert_lon=test.pert_lon, pert_lat=test.pert_lat,
+                      pert_r=test.pert_r, perturbation=1 if test.perturbation == "exp" else 0,
+                      omega=phys.omega, radius=phys.earth_radius)
+
+    def evaluate_jw_topography(self, patch, test, phys):
+        import ctypes
+        self._ck(self.lib.tb200_evaluate_jw_topography(self._h, patch,
+                                                       ctypes.byref(self._jw(test, phys))))
+
+    def evaluate_jw_state(self, patch, inst, test, phys):
+        """Initial state of BaroclinicWaveJWTest written straight into `inst`."""
+        import ctypes
+        self._ck(self.lib.tb200_evaluate_jw_state(self._h, patch, inst,
+                                                  ctypes.byref(self._jw(test, phys))))
+
     def upload_held_suarez(self, patch, latitude, surface_product):
         """Per-column inputs of HeldSuarezPhysics::Perform: latitude and the product
         of the rho and rho-theta slots on the lowest interface of instance 0

@@ -66,6 +66,7 @@ class Model:
         self._host = {}
         self._host_tracers = {}
         self.device_setup = False
+        self._device_state = []
         # lean geometry: upload the 2-D metric, topography derivatives and the
         # vertical coordinate only (no 3-D metric arrays: 26 values per node);
         # the column-constant kernels need nothing else
@@ -90,9 +91,6 @@ class Model:
         for p in self.local:
             geo = p.evaluate_geometric_terms(p._zs, p._dazs, p._dbzs,
                                              **({"lean": True} if self.lean_geometry else {}))
-            ctx.upload_geometry(p.index, **geo)
-            ctx.upload_element_area(p.index, p.area_node, p.area_redge)
-            ctx.set_seam_transforms(p.index, *p.seam_transforms())
             if self.ncomp == 5:
                 # let the kernels evaluate the terrain-following metric on the fly
                 xn = np.zeros(p.wa)
@@ -100,12 +98,31 @@ class Model:
                 xn[1:-1], yn[1:-1] = p.X, p.Y
                 ctx.set_terrain_metric(p.index, xn, yn,
                                        p._pad(np.stack([p._dazs, p._dbzs], axis=-1)))
-            if upload_state:
+            if upload_state and self._device_jw():
+                # longitude / latitude (and the 2-D metric) on the device; the host
+                # arrays uploaded next stay the metric in use, so that a run does not
+                # depend on where its initial state was evaluated
+                ctx.evaluate_geometry_cs(p.index, g.phys.earth_radius, g.phys.omega)
+            ctx.upload_geometry(p.index, **geo)
+            ctx.upload_element_area(p.index, p.area_node, p.area_redge)
+            ctx.set_seam_transforms(p.index, *p.seam_transforms())
+            if upload_state and self._device_jw():
+                self._device_state.append(p)
+            elif upload_state:
                 node, redge = self.evaluate_test_case(p)
                 self._host[p.index] = (node, redge)
                 ctx.upload_state(p.index, 0, node, redge, self._host_tracers.get(p.index))
         if self.ncomp == 5:
             ctx.set_vertical_coordinate(g.reta_levels, g.reta_interfaces)
+        for p in self._device_state:
+            # initial state evaluated where it lives (k_jw_state, tb200_setup.cuh);
+            # the host copy in the reference layout is read back for callers that
+            # want one (bench.py's end-to-end leg)
+            ctx.evaluate_jw_state(p.index, 0, self.test, g.phys)
+            node = np.zeros((self.ncomp, p.wa, p.wb, g.nlev))
+            redge = np.zeros((self.ncomp, p.wa, p.wb, g.nlev + 1))
+            ctx.download_state(p.index, 0, node, redge, None, False)
+            self._host[p.index] = (node, redge)
         ctx.build_connectivity()
         # multi-GPU: direct stores into the peers' receive buffers unless
         # TB200_EXCHANGE=nccl asks for the all-to-all callback
@@ -115,6 +132,15 @@ class Model:
             from .parallel import enable_peer_exchange
             self.peer_exchange = enable_peer_exchange(ctx, self.rank, self.nranks)
         return self
+
+    def _device_jw(self):
+        """device_setup on a cubed sphere with the Jablonowski-Williamson case (or
+        the tracer stand-in built on it): the state is evaluated by k_jw_state."""
+        from .testcases import BaroclinicWaveJWTest
+        return (self.device_setup and isinstance(self.test, BaroclinicWaveJWTest)
+                and self.ntracers == 0
+                and not getattr(self.grid, "is_cartesian", False) and self.ncomp == 5
+                and os.environ.get("TB200_SETUP", "device") == "device")
 
     def evaluate_test_case(self, p):
         """GridPatchCSGLL::EvaluateTestCase (GridPatchCSGLL.cpp:578-920) for
