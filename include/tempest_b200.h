@@ -315,7 +315,8 @@ int tb200_evaluate_geometry_cs(tb200_ctx * ctx, int patch_index, double radius, 
 
 /* Debugging aid (cf. tb200_debug_column_assembly): a per-column array in the device's
  * element-major order [element][np * np]; which = 0 Jacobian2D, 1, 2 ContraMetric2DA,
- * 3, 4 ContraMetric2DB, 5 CoriolisF, 6 topography, 7 longitude, 8 latitude. */
+ * 3, 4 ContraMetric2DB, 5 CoriolisF, 6 topography, 7 longitude, 8 latitude,
+ * 9 accumulated precipitation of tb200_kessler. */
 int tb200_debug_column_field(tb200_ctx * ctx, int which, double * out);
 
 /* Parameters of BaroclinicWaveJWTest (test/nonhydro_sphere/BaroclinicWaveJWTest.cpp:41-134)
@@ -345,6 +346,13 @@ int tb200_evaluate_jw_state(tb200_ctx * ctx, int patch_index, int inst, const tb
 int tb200_upload_held_suarez(tb200_ctx * ctx, int patch_index,
                              const double * latitude, const double * surface_product);
 int tb200_held_suarez(tb200_ctx * ctx, double dt);
+/* KesslerPhysics::Perform (test/dcmip2016/KesslerPhysics.cpp:84-285, calling KESSLER,
+ * test/dcmip2016/interface/kessler.f90:62-185) on instance 0: warm-rain microphysics per
+ * column on rho theta, rho and the first three tracers (rho qv, rho qc, rho qr);
+ * precipitation accumulates per column (UserData2D[0]; tb200_debug_column_field(9)).
+ * PARITY UNPINNED - the reference kernel is Fortran and cannot be built in this image;
+ * the device kernel is held to the C restatement oracle/kessler_port.c. */
+int tb200_kessler(tb200_ctx * ctx, double dt);
 /* Grid::LinearCombineData(coeff -> dst) (GridPatch.cpp:1433-1520) of state and
  * tracers followed by VerticalDynamics::FilterNegativeTracers(dst), as
  * TimestepSchemeStrang::Step issues them at the start of a step (:470-482);

@@ -126,6 +126,7 @@ _SIGNATURES = {
     "tb200_evaluate_jw_state": (c_int, [c_void_p, c_int, c_int, POINTER(JWTest)]),
     "tb200_upload_held_suarez": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "tb200_held_suarez": (c_int, [c_void_p, c_double]),
+    "tb200_kessler": (c_int, [c_void_p, c_double]),
     "tb200_scheme_instances": (c_int, [c_int]),
     "tb200_scheme_from_name": (c_int, [c_char_p]),
     "tb200_step": (c_int, [c_void_p, c_int, c_int, c_int, c_double]),

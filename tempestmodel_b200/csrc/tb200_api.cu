@@ -925,13 +925,14 @@ extern "C" int tb200_evaluate_geometry_cs(
 // Read-back of a per-column array in the device's element-major order
 // [element][np * np] (tests of the device-side set-up): 0 Jacobian2D,
 // 1, 2 ContraMetric2DA, 3, 4 ContraMetric2DB, 5 Coriolis, 6 topography,
-// 7 longitude, 8 latitude.
+// 7 longitude, 8 latitude, 9 accumulated precipitation (Kessler).
 extern "C" int tb200_debug_column_field(tb200_ctx * ctx, int which, double * out) {
 	const DevLayout & lay = ctx->lay;
 	const double * src = 0;
 	if (which >= 0 && which < 7) src = ctx->g2d[which];
 	else if (which == 7) src = ctx->d_lon;
 	else if (which == 8) src = ctx->d_hs_lat;
+	else if (which == 9) src = ctx->d_precip;
 	if (src == 0) TB_FAIL(ctx, "column field not available");
 	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
 	TB_CHECK(ctx, cudaMemcpy(out, src, (size_t)lay.nelem * lay.nn * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1055,6 +1056,49 @@ extern "C" int tb200_held_suarez(tb200_ctx * ctx, double dt) {
 	auto kfn = k_held_suarez;
 	TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(256), 0, ctx->stream, lay, a, ctx->inst[0]);
 	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
+// KesslerPhysics::Perform on instance 0 (state and the first three tracers:
+// rho qv, rho qc, rho qr); accumulates the precipitation per column
+// (GridPatch::GetUserData2D()[0], read back with tb200_debug_column_field(9)).
+extern "C" int tb200_kessler(tb200_ctx * ctx, double dt) {
+	const DevLayout & lay = ctx->lay;
+	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO) {
+		TB_FAIL(ctx, "Kessler physics needs the nonhydrostatic equation set");
+	}
+	if (lay.ntr < 3) TB_FAIL(ctx, "Kessler physics needs three tracers (rho qv, rho qc, rho qr)");
+	if (lay.nlev < 2) TB_FAIL(ctx, "Kessler physics needs at least two levels");
+	for (int c = 0; c < 5; c++) {
+		if (c != 3 && lay.onedge[c]) TB_FAIL(ctx, "Kessler physics: Lorenz staggering only");
+	}
+	if (ctx->d_reta_n == 0) TB_FAIL(ctx, "vertical coordinate not set (tb200_set_vertical_coordinate)");
+	if (ctx->d_precip == 0) {
+		if (dalloc(ctx, &ctx->d_precip, (size_t)lay.nelem * lay.nn)) return 1;
+		TB_CHECK(ctx, cudaMemset(ctx->d_precip, 0, (size_t)lay.nelem * lay.nn * sizeof(double)));
+	}
+	KesslerArgs a;
+	a.zs = ctx->g2d[6];
+	a.reta_n = ctx->d_reta_n;
+	a.ztop = ctx->cfg.ztop;
+	a.dt = dt;
+	a.gamma = ctx->cfg.cp / (ctx->cfg.cp - ctx->cfg.R);
+	a.pressure_scaling = ctx->cfg.p0 * pow(ctx->cfg.R / ctx->cfg.p0, a.gamma);
+	a.R = ctx->cfg.R;
+	a.precip = ctx->d_precip;
+	a.ws = ctx->d_ws;
+	const size_t ws_doubles = (size_t)tb_column_ws_entries(lay.nlev, ctx->offd) * ctx->ws_cols;
+	const long long total = lay.nelem * (long long)lay.nn;
+	long long chunk = (long long)(ws_doubles / ((size_t)9 * lay.nlev)) / 128 * 128;
+	if (chunk < 128) TB_FAIL(ctx, "column workspace too small for the Kessler step");
+	for (long long c0 = 0; c0 < total; c0 += chunk) {
+		a.col0 = c0;
+		a.ncols = std::min(chunk, total - c0);
+		auto kfn = k_kessler;
+		TB_LAUNCH_FLAT(kfn, dim3((unsigned)((a.ncols + 127) / 128)), dim3(128), 0, ctx->stream,
+			lay, a, ctx->inst[0]);
+		TB_KERNEL_CHECK(ctx);
+	}
 	return 0;
 }
 

@@ -126,6 +126,7 @@ struct tb200_ctx {
 	// Held-Suarez forcing (tb200_physics.cuh): latitude and the surface product per column
 	double * d_hs_lat; double * d_hs_sp;
 	double * d_lon;       // longitude per column (device-side set-up)
+	double * d_precip;    // accumulated precipitation per column (Kessler)
 	double * d_ws; int ws_cols; int * d_info;
 	double * d_ray_node; double * d_ray_redge; double * d_refstate;   // Rayleigh friction
 	bool has_rayleigh;
@@ -182,7 +183,7 @@ struct tb200_ctx {
 		d_seam_mats(0), rank(0), nranks(1), exch_fn(0), exch_user(0),
 		nsend_total(0), nrecv_total(0), d_send_nodes(0), d_sendbuf(0),
 		d_recvbuf(0), d_send_rank(0), d_send_slot(0), peer_area(0), peer_rows(0),
-		peer_ready(false), peer_seq(0), d_peer_ticket(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0), tracer_keep(0), tracer_inc(0), d_hs_lat(0), d_hs_sp(0), d_lon(0),
+		peer_ready(false), peer_seq(0), d_peer_ticket(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0), tracer_keep(0), tracer_inc(0), d_hs_lat(0), d_hs_sp(0), d_lon(0), d_precip(0),
 		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false),
 		column_inc(0), d_wold(0), offd(4), launches(0), writes(0), uvzero_inst(-1), uvzero_writes(0),
 		timing_begin(0), timing_end(0), timing_user(0),

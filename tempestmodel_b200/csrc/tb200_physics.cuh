@@ -112,4 +112,166 @@ __global__ void k_held_suarez(DevLayout lay, HeldSuarezArgs a, double * data) {
 	}
 }
 
+///////////////////////////////////////////////////////////////////////////////
+// Kessler warm-rain microphysics as a device workflow step.
+//
+//   KesslerPhysics::Perform   test/dcmip2016/KesslerPhysics.cpp:84-285
+//   KESSLER                   test/dcmip2016/interface/kessler.f90:62-185
+//
+// PARITY UNPINNED: the reference's kernel is Fortran and the image has no
+// Fortran compiler, so it cannot be run here; the device kernel is held to a C
+// restatement of the same source (oracle/kessler_port.c, which states how the
+// mixed-precision declarations of the Fortran are read).  One thread per
+// element-local column (the reference visits every node of a patch, duplicates
+// included); the column arrays live in a coalesced scratch [entry][thread].
+// Tracers 0, 1, 2 are rho qv, rho qc, rho qr.
+
+struct KesslerArgs {
+	const double * zs;           // topography [e][NN]
+	const double * reta_n;       // REta of the levels
+	double ztop;
+	double dt;
+	double pressure_scaling, gamma, R;
+	double * precip;             // accumulated precipitation [e][NN] (UserData2D[0])
+	double * ws;                 // scratch: 9 * L doubles per column of the launch
+	long long col0, ncols;       // columns (element-local nodes) of this launch
+};
+
+// assignment to a default-real (single precision) Fortran variable
+__device__ __forceinline__ double tb_f32(double x) { return (double)(float)x; }
+
+__global__ void k_kessler(DevLayout lay, KesslerArgs a, double * data) {
+	const int NN = lay.nn;
+	const int nz = lay.nlev;
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.ncols) return;
+	const long long col = a.col0 + t;
+	const long long e = col / NN;
+	const int n = (int)(col % NN);
+	const size_t ebase = (size_t)e * lay.nrows * NN + n;
+	double * pT = data + ebase + (size_t)lay.rowoff[2] * NN;
+	double * pR = data + ebase + (size_t)lay.rowoff[4] * NN;
+	double * pQv = data + ebase + (size_t)(lay.troff + 0 * nz) * NN;
+	double * pQc = data + ebase + (size_t)(lay.troff + 1 * nz) * NN;
+	double * pQr = data + ebase + (size_t)(lay.troff + 2 * nz) * NN;
+	const double zs = a.zs[(size_t)e * NN + n];
+
+	// scratch [entry][thread of the launch]
+	const size_t S = (size_t)a.ncols;
+	double * w0 = a.ws + t;
+#define TB_KW(q, k) w0[((size_t)(q) * nz + (k)) * S]
+	enum { THETA = 0, QV, QC, QR, RHOD, PK, VELQR, SED, PC };
+#define TB_KZ(k) (zs + a.reta_n[k] * (a.ztop - zs))
+
+	const double f2x = 17.27;
+	const double f5 = 237.3 * f2x * 2500000.0 / 1003.0;
+	const double xk = .2875;
+	const double psl = 1000.0;
+	const double rhoqr = 1000.0;
+	const double e1364 = (double)0.1364f, e875 = (double).875f;
+	const double e2046 = (double).2046f, e525 = (double).525f, c001 = (double).001f;
+
+	// KesslerPhysics.cpp:143-221
+	for (int k = 0; k < nz; k++) {
+		const double dRho = pR[(size_t)k * NN];
+		const double rqv = pQv[(size_t)k * NN], rqc = pQc[(size_t)k * NN], rqr = pQr[(size_t)k * NN];
+		const double dRhoD = dRho - rqv - rqc - rqr;
+		const double thetav = pT[(size_t)k * NN] / dRho;
+		const double dPressure = a.pressure_scaling * exp(log(dRho * thetav) * a.gamma);
+		const double dTv = dPressure / (dRho * a.R);
+		double qv = rqv / dRho; if (qv < 0.0) qv = 0.0;
+		double qc = rqc / dRho; if (qc < 0.0) qc = 0.0;
+		double qr = rqr / dRho; if (qr < 0.0) qr = 0.0;
+		TB_KW(THETA, k) = thetav / (1.0 + 0.61 * qv);
+		TB_KW(QV, k) = qv;
+		TB_KW(QC, k) = qc;
+		TB_KW(QR, k) = qr;
+		TB_KW(RHOD, k) = dRhoD;
+		TB_KW(PK, k) = dTv / thetav;
+	}
+
+	// kessler.f90:101-185
+	const double rho1 = TB_KW(RHOD, 0);
+	for (int k = 0; k < nz; k++) {
+		const double rho = TB_KW(RHOD, k), pk = TB_KW(PK, k);
+		const double r = tb_f32(0.001 * rho);
+		const double rhalf = tb_f32(sqrt(rho1 / rho));
+		TB_KW(PC, k) = tb_f32(3.8 / (pow(pk, (double)1.f / xk) * psl));
+		TB_KW(VELQR, k) = tb_f32(36.34 * pow(TB_KW(QR, k) * r, e1364) * rhalf);
+	}
+	double dt_max = a.dt;
+	for (int k = 0; k < nz - 1; k++) {
+		const double v = TB_KW(VELQR, k);
+		if (v != 0.0) {
+			dt_max = fmin(dt_max, 0.8 * (TB_KZ(k + 1) - TB_KZ(k)) / v);
+		}
+	}
+	const int rainsplit = (int)ceil(a.dt / dt_max);
+	const double dt0 = a.dt / (double)rainsplit;
+
+	double precl = 0.0;
+	for (int nt = 1; nt <= rainsplit; nt++) {
+		precl = precl + rho1 * TB_KW(QR, 0) * TB_KW(VELQR, 0) / rhoqr;
+
+		for (int k = 0; k < nz - 1; k++) {
+			const double r0 = tb_f32(0.001 * TB_KW(RHOD, k)), r1 = tb_f32(0.001 * TB_KW(RHOD, k + 1));
+			TB_KW(SED, k) = tb_f32(dt0 * (r1 * TB_KW(QR, k + 1) * TB_KW(VELQR, k + 1)
+				- r0 * TB_KW(QR, k) * TB_KW(VELQR, k)) / (r0 * (TB_KZ(k + 1) - TB_KZ(k))));
+		}
+		TB_KW(SED, nz - 1) = tb_f32(-dt0 * TB_KW(QR, nz - 1) * TB_KW(VELQR, nz - 1)
+			/ ((double).5f * (TB_KZ(nz - 1) - TB_KZ(nz - 2))));
+
+		for (int k = 0; k < nz; k++) {
+			double qc = TB_KW(QC, k), qr = TB_KW(QR, k), qv = TB_KW(QV, k), theta = TB_KW(THETA, k);
+			const double pk = TB_KW(PK, k), pc = TB_KW(PC, k);
+			const double r = tb_f32(0.001 * TB_KW(RHOD, k));
+			const double qrprod = qc - (qc - dt0 * fmax(c001 * (qc - .001), 0.0))
+				/ (1.0 + dt0 * 2.2 * pow(qr, e875));
+			qc = fmax(qc - qrprod, 0.0);
+			qr = fmax(qr + qrprod + TB_KW(SED, k), 0.0);
+
+			const double pt = pk * theta;
+			const double qvs = pc * exp(f2x * (pt - 273.0) / (pt - 36.0));
+			const double prod = (qv - qvs) / (1.0 + qvs * f5 / ((pt - 36.0) * (pt - 36.0)));
+
+			const double rq = r * qr;
+			const double ern = fmin(fmin(
+				dt0 * (((1.6 + 124.9 * pow(rq, e2046)) * pow(rq, e525))
+					/ (2550000.0 * pc / (3.8 * qvs) + 540000.0))
+					* (fmax(qvs - qv, 0.0) / (r * qvs)),
+				fmax(-prod - qc, 0.0)), qr);
+
+			theta = theta + 2500000.0 / (1003.0 * pk) * (fmax(prod, -qc) - ern);
+			qv = fmax(qv - fmax(prod, -qc) + ern, 0.0);
+			qc = qc + fmax(prod, -qc);
+			qr = qr - ern;
+			TB_KW(THETA, k) = theta; TB_KW(QV, k) = qv; TB_KW(QC, k) = qc; TB_KW(QR, k) = qr;
+		}
+
+		if (nt != rainsplit) {
+			for (int k = 0; k < nz; k++) {
+				const double rho = TB_KW(RHOD, k);
+				const double r = tb_f32(0.001 * rho);
+				const double rhalf = tb_f32(sqrt(rho1 / rho));
+				TB_KW(VELQR, k) = tb_f32(36.34 * pow(TB_KW(QR, k) * r, e1364) * rhalf);
+			}
+		}
+	}
+	precl = precl / (double)rainsplit;
+
+	// KesslerPhysics.cpp:235-279
+	a.precip[(size_t)e * NN + n] += precl * a.dt;
+	for (int k = 0; k < nz; k++) {
+		const double qv = TB_KW(QV, k), qc = TB_KW(QC, k), qr = TB_KW(QR, k);
+		const double rho = TB_KW(RHOD, k) / (1.0 - qv - qc - qr);
+		pR[(size_t)k * NN] = rho;
+		pQv[(size_t)k * NN] = qv * rho;
+		pQc[(size_t)k * NN] = qc * rho;
+		pQr[(size_t)k * NN] = qr * rho;
+		pT[(size_t)k * NN] = rho * TB_KW(THETA, k) * (1.0 + 0.61 * qv);
+	}
+#undef TB_KW
+#undef TB_KZ
+}
+
 #endif

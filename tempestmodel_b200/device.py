@@ -200,6 +200,11 @@ class DeviceContext:
         """HeldSuarezPhysics::Perform on instance 0 (device workflow step)."""
         self._ck(self.lib.tb200_held_suarez(self._h, dt))
 
+    def kessler(self, dt):
+        """KesslerPhysics::Perform on instance 0 (device workflow step; parity
+        unpinned, see include/tempest_b200.h)."""
+        self._ck(self.lib.tb200_kessler(self._h, dt))
+
     def set_node_ids(self, patch, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         self._ck(self.lib.tb200_set_node_ids(self._h, patch, _ptr(ids)))
