@@ -219,6 +219,18 @@ def parity_block(cs, cs_ic, nsteps, key, world):
         out["vs_reference"] = dict(zip(COMPONENTS, [float(v) for v in rel]))
         out["vs_reference"]["source"] = table.get("reference_source", "")
         ok = ok and rel[4] <= 1e-12 and rel[2] <= 1e-12 and rel[0] <= table.get("u_bound", 1e-6)
+    ref24 = table.get("reference_npatch24", {}).get(str(nsteps))
+    if ref24 is not None and ref is not None:
+        # the unmodified reference run on 24 patches instead of 6: how far the
+        # reference itself moves with the decomposition (the multi-GPU lines run
+        # 24 patches), and this run against it
+        ref24 = np.asarray(ref24)
+        out["reference_24_vs_6_patches"] = dict(zip(
+            COMPONENTS, [float(v) for v in np.abs(ref24 - ref) / np.maximum(np.abs(ref), 1e-300)]))
+        if world > 1:
+            out["vs_reference_24_patches"] = dict(zip(
+                COMPONENTS, [float(v) for v in
+                             np.abs(np.asarray(cs) - ref24) / np.maximum(np.abs(ref24), 1e-300)]))
     dev = table.get("device_one_gpu", {}).get(str(nsteps))
     if dev is not None:
         dev = np.asarray(dev)
