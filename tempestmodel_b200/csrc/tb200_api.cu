@@ -2707,6 +2707,7 @@ static int dss_rows(
 	a.uv_row1 = is_state ? (lay.rowoff[1] + lay.rowlev[1]) : -1;
 	a.nsel = nsel;
 	a.sel_row0 = row0;
+	a.rows_fastest = 0;
 	a.peer_flags = 0;
 	a.peer_seq = 0;
 	a.peer_timeout_ns = 0;
@@ -2730,13 +2731,27 @@ static int dss_rows(
 			const char * g = getenv("TB200_DSS_GY");
 			if (g != 0 && atoi(g) > 0) gy = std::min(nsel, atoi(g));
 		}
+		// block order: consecutive blocks walk the row chunks of the same groups,
+		// i.e. an element's contiguous block of rows is streamed by blocks that run
+		// together (ne = 120, L = 30: 0.757 -> 0.711 ms per pass, two batches of
+		// TBD_B rows per block; TB200_DSS_ORDER=groups: groups fastest, one batch)
+		static const bool rows_fastest = []() {
+			const char * e = getenv("TB200_DSS_ORDER");
+			return !(e != 0 && strcmp(e, "groups") == 0);
+		}();
+		const int gx = (a.ngroups + block - 1) / block;
+		if (rows_fastest && classes && gx <= 65535 && getenv("TB200_DSS_GY") == 0) {
+			gy = (nsel + 2 * TBD_B - 1) / (2 * TBD_B);
+		}
+		a.rows_fastest = (rows_fastest && gx <= 65535) ? 1 : 0;
+		const dim3 grid = a.rows_fastest ? dim3(gy, gx) : dim3(gx, gy);
 		if (classes) {
 			auto kfn = k_dss_fast;
-			TB_LAUNCH_FLAT(kfn, dim3((a.ngroups + block - 1) / block, gy), dim3(block), 0,
+			TB_LAUNCH_FLAT(kfn, grid, dim3(block), 0,
 				ctx->stream, lay, a, ctx->inst[inst]);
 		} else {
 			auto kfn = k_dss_scalar;
-			TB_LAUNCH_FLAT(kfn, dim3((a.ngroups + block - 1) / block, gy), dim3(block), 0,
+			TB_LAUNCH_FLAT(kfn, grid, dim3(block), 0,
 				ctx->stream, lay, a, ctx->inst[inst]);
 		}
 		TB_KERNEL_CHECK(ctx);

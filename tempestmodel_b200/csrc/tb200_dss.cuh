@@ -36,6 +36,7 @@ struct DssArgs {
 	int uv_row0, uv_row1;     // rows of (U,V) skipped for seam groups (vector path)
 	int nsel;                 // rows per remote slot in this exchange
 	int sel_row0;             // first row carried by the exchange
+	int rows_fastest;         // 1: blockIdx.x walks the row chunks, blockIdx.y the groups
 };
 
 // offset of local node m = e * nn + n inside row 0 of its element
@@ -120,6 +121,19 @@ __device__ __forceinline__ bool tb_dss_wait_peers(const DssArgs & a, unsigned ma
 	return true;
 }
 
+// block coordinates: which batch of groups, which chunk of rows.  With
+// rows_fastest consecutive blocks work on the successive row chunks of the same
+// groups, i.e. walk an element's contiguous block of rows together.
+__device__ __forceinline__ int tb_dss_group_block(const DssArgs & a) {
+	return a.rows_fastest ? blockIdx.y : blockIdx.x;
+}
+__device__ __forceinline__ int tb_dss_row_block(const DssArgs & a) {
+	return a.rows_fastest ? blockIdx.x : blockIdx.y;
+}
+__device__ __forceinline__ int tb_dss_row_blocks(const DssArgs & a) {
+	return a.rows_fastest ? gridDim.x : gridDim.y;
+}
+
 __device__ __forceinline__ void tb_dss_generic(
 	const DevLayout & lay, const DssArgs & a, int gidx, double * data
 ) {
@@ -137,8 +151,8 @@ __device__ __forceinline__ void tb_dss_generic(
 	const bool seam = (a.flags[gidx] & 1) != 0;
 	// blockIdx.y owns a contiguous range of rows: the rows of an element are
 	// adjacent in memory, so a block walks whole DRAM pages
-	const int rows_per = (a.row1 - a.row0 + gridDim.y - 1) / gridDim.y;
-	const int rbeg = a.row0 + blockIdx.y * rows_per;
+	const int rows_per = (a.row1 - a.row0 + tb_dss_row_blocks(a) - 1) / tb_dss_row_blocks(a);
+	const int rbeg = a.row0 + tb_dss_row_block(a) * rows_per;
 	const int rend = (rbeg + rows_per < a.row1) ? (rbeg + rows_per) : a.row1;
 #pragma unroll 4
 	for (int r = rbeg; r < rend; r++) {
@@ -167,7 +181,7 @@ __device__ __forceinline__ void tb_dss_generic(
 }
 
 __global__ void k_dss_scalar(DevLayout lay, DssArgs a, double * data) {
-	const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int gidx = tb_dss_group_block(a) * blockDim.x + threadIdx.x;
 	if (gidx >= a.ngroups) return;
 	tb_dss_generic(lay, a, gidx, data);
 }
@@ -183,8 +197,8 @@ template <int B>
 __device__ __forceinline__ void tb_dss_local(
 	const DevLayout & lay, const DssArgs & a, int gidx, double * data
 ) {
-	const int rows_per = (a.row1 - a.row0 + gridDim.y - 1) / gridDim.y;
-	const int rbeg = a.row0 + blockIdx.y * rows_per;
+	const int rows_per = (a.row1 - a.row0 + tb_dss_row_blocks(a) - 1) / tb_dss_row_blocks(a);
+	const int rbeg = a.row0 + tb_dss_row_block(a) * rows_per;
 	const int rend = (rbeg + rows_per < a.row1) ? (rbeg + rows_per) : a.row1;
 	const int nn = lay.nn;
 	const int4 m = ((const int4 *)a.members)[gidx];
@@ -239,7 +253,7 @@ __device__ __forceinline__ void tb_dss_local(
 #define TBD_MINB 8
 #endif
 __global__ void __launch_bounds__(128, TBD_MINB) k_dss_fast(DevLayout lay, DssArgs a, double * data) {
-	const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int gidx = tb_dss_group_block(a) * blockDim.x + threadIdx.x;
 	if (gidx >= a.ngroups) return;
 	if (a.flags[gidx] & 2) {
 		tb_dss_local<TBD_B>(lay, a, gidx, data);
