@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--tag", default="")
     ap.add_argument("--only", default=None, help="run the operations whose name contains this")
     ap.add_argument("--tracers", type=int, default=0,
-                    help="carry N analytic tracers (general kernels; S = 5 + N)")
+                    help="carry N analytic tracers (S = 5 + N)")
     args = ap.parse_args()
 
     import torch
