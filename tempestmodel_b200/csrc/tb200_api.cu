@@ -2160,6 +2160,10 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 		if (!(pers != 0 && strcmp(pers, "0") == 0) && (size_t)grid_p * per_block <= ws_doubles) {
 			fa.col0 = 0;
 			fa.ncols = ctx->ncols;
+			// (Measured and dropped: an access-policy window marking part of the scratch
+			// as persisting in L2 - cudaLimitPersistingL2CacheSize at its maximum - made
+			// this solve 2x slower, 5.7 ms, and every other kernel of the step with it:
+			// the carve-out is taken from the L2 the streams of the step live in.)
 			TB_LAUNCH(kfn, dim3((unsigned)grid_p), dim3(TBC_THREADS),
 				smem, ctx->stream, lay, ctx->phys, fa,
 				(const double *)ctx->inst[in], ctx->inst[out], (int)nbatches_all);

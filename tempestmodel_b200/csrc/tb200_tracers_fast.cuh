@@ -743,14 +743,38 @@ k_column_tracers_fast(
 	bool bad = (info != 0);
 #pragma unroll
 	for (int c = 0; c < NT; c++) { x1[c] = 0.0; x2[c] = 0.0; }
+	// rows of U, substituted right-hand sides and the values to be updated of level
+	// j - 1 are loaded while level j is computed
+	double nu0 = sU[(size_t)(0 * L + (L - 1)) * T];
+	double nu1 = sU[(size_t)(1 * L + (L - 1)) * T];
+	double nu2 = sU[(size_t)(2 * L + (L - 1)) * T];
+	double ny[NT], nown[NT];
+#pragma unroll
+	for (int c = 0; c < NT; c++) {
+		const int cc = (ta.c0 + c < ntr) ? (ta.c0 + c) : (ntr - 1);
+		ny[c] = sY[(size_t)(c * L + (L - 1)) * T];
+		nown[c] = tr_out[ebase + (size_t)(lay.troff + cc * L + (L - 1)) * NN + nd];
+	}
 	for (int j = L - 1; j >= 0; j--) {
-		const double u0 = sU[(size_t)(0 * L + j) * T];
-		const double u1 = sU[(size_t)(1 * L + j) * T];
-		const double u2 = sU[(size_t)(2 * L + j) * T];
+		const double u0 = nu0, u1 = nu1, u2 = nu2;
+		double y[NT], oldv[NT];
+#pragma unroll
+		for (int c = 0; c < NT; c++) { y[c] = ny[c]; oldv[c] = nown[c]; }
+		if (j > 0) {
+			nu0 = sU[(size_t)(0 * L + j - 1) * T];
+			nu1 = sU[(size_t)(1 * L + j - 1) * T];
+			nu2 = sU[(size_t)(2 * L + j - 1) * T];
+#pragma unroll
+			for (int c = 0; c < NT; c++) {
+				const int cc = (ta.c0 + c < ntr) ? (ta.c0 + c) : (ntr - 1);
+				ny[c] = sY[(size_t)(c * L + j - 1) * T];
+				nown[c] = tr_out[ebase + (size_t)(lay.troff + cc * L + j - 1) * NN + nd];
+			}
+		}
 		const double ru0 = 1.0 / u0;       // one reciprocal for the NT right-hand sides
 #pragma unroll
 		for (int c = 0; c < NT; c++) {
-			double b = sY[(size_t)(c * L + j) * T];
+			double b = y[c];
 			b -= x2[c] * u2;
 			b -= x1[c] * u1;
 			b = b * ru0;
@@ -760,7 +784,7 @@ k_column_tracers_fast(
 			if (live && ta.c0 + c < ntr) {
 				const size_t row = (size_t)(lay.troff + (ta.c0 + c) * L + j) * NN;
 				double * own = tr_out + ebase + row + nd;
-				const double old = own[0];
+				const double old = oldv[c];
 				const double v = old - b;
 				if (ta.keep != 0) {
 					ta.keep[ebase + row + nd] = old;
