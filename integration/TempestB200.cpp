@@ -41,8 +41,13 @@ B200Bridge::B200Bridge(Model & model) :
 	m_nHypervisOrder(0),
 	m_dNuScalar(0.0),
 	m_dNuDiv(0.0),
-	m_dNuVort(0.0)
+	m_dNuVort(0.0),
+	m_fFullyExplicit(false)
 { }
+
+void B200Bridge::SetFullyExplicit(bool fFullyExplicit) {
+	m_fFullyExplicit = fFullyExplicit;
+}
 
 void B200Bridge::SetHyperviscosity(
 	int nOrder, double dNuScalar, double dNuDiv, double dNuVort
@@ -138,7 +143,7 @@ void B200Bridge::Initialize() {
 	cfg.nu_scalar = m_dNuScalar;
 	cfg.nu_div = m_dNuDiv;
 	cfg.nu_vort = m_dNuVort;
-	cfg.fully_explicit = 0;
+	cfg.fully_explicit = m_fFullyExplicit ? 1 : 0;
 	cfg.off_centering = 0.0;
 
 	int iResult = tb200_create(&cfg, &m_pCtx);
@@ -465,9 +470,8 @@ VerticalDynamicsB200::VerticalDynamicsB200(
 ) :
 	VerticalDynamics(model)
 {
-	if (fFullyExplicit) {
-		_EXCEPTIONT("tempest_b200: --explicitvertical is not supported");
-	}
+	// --explicitvertical (VerticalDynamicsFEM.cpp:748-793, 1240-1242)
+	B200Bridge::Get(model).SetFullyExplicit(fFullyExplicit);
 }
 
 void VerticalDynamicsB200::Initialize() {

@@ -55,6 +55,12 @@ public:
 	void SetHyperviscosity(int nOrder, double dNuScalar, double dNuDiv, double dNuVort);
 
 	///	<summary>
+	///		The fFullyExplicit argument of the VerticalDynamicsFEM constructor
+	///		(--explicitvertical).
+	///	</summary>
+	void SetFullyExplicit(bool fFullyExplicit);
+
+	///	<summary>
 	///		Create the context, describe the grid, upload geometry and tables.
 	///		Called from the plugins' Initialize(), i.e. after
 	///		Grid::EvaluateGeometricTerms (Model.cpp:347-355).
@@ -92,6 +98,7 @@ private:
 	std::vector<FunctionTimer *> m_vecTimers;
 	int m_nHypervisOrder;
 	double m_dNuScalar, m_dNuDiv, m_dNuVort;
+	bool m_fFullyExplicit;
 };
 
 ///////////////////////////////////////////////////////////////////////////////

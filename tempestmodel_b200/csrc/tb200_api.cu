@@ -1886,14 +1886,49 @@ extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 	return tb200_filter_negative_tracers(ctx, out);
 }
 
+// Fully explicit vertical step: BuildF of every element-local column of `in`
+// (k_column_implicit in its explicit mode), out -= dt * F.
+static int explicit_vertical_columns(tb200_ctx * ctx, int in, int out, double dt) {
+	const DevLayout & lay = ctx->lay;
+	if (check_ops(ctx)) return 1;
+	if (need_metric3d(ctx, "explicit vertical step")) return 1;
+	ColumnArgs ca;
+	ca.col_node = 0;
+	ca.col_dups = 0;
+	ca.ws = ctx->d_ws;
+	ca.ws_stride = ctx->ws_cols;
+	ca.dt = dt;
+	ca.offd = ctx->offd;
+	ca.fe_nodes = ctx->cfg.vertical_order;
+	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
+	ca.info = ctx->d_info;
+	ca.assemble_only = 3;
+	const long long total = lay.nelem * (long long)lay.nn;
+	for (long long c0 = 0; c0 < total; c0 += ctx->ws_cols) {
+		ca.col0 = (int)c0;
+		ca.ncols = (int)std::min<long long>(ctx->ws_cols, total - c0);
+		auto kfn = k_column_implicit;
+		TB_LAUNCH_FLAT(kfn, dim3((ca.ncols + 63) / 64), dim3(64), 0, ctx->stream,
+			lay, ctx->geom, ctx->ops, ctx->phys, ca,
+			(const double *)ctx->inst[in], ctx->inst[out]);
+		TB_KERNEL_CHECK(ctx);
+	}
+	return 0;
+}
+
 extern "C" int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
 	TimingScope ts(ctx, "VerticalStepExplicit");
 	if (check_inst2(ctx, in, out)) return 1;
 	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || ctx->lay.nlev == 1) {
 		return 0;   // VerticalDynamicsStub (TempestInitialize.h:362-364)
 	}
-	if (ctx->cfg.fully_explicit) TB_FAIL(ctx, "--explicitvertical is not supported");
 	if (in == out) TB_FAIL(ctx, "VerticalDynamics StepExplicit must have iDataInitial != iDataUpdate");
+	if (ctx->cfg.fully_explicit) {
+		// --explicitvertical (VerticalDynamicsFEM.cpp:748-793): rho theta, w and rho are
+		// advanced with the column tendencies as well; general kernels
+		if (ctx->lay.ntr > 0) TB_FAIL(ctx, "--explicitvertical with tracers is not supported");
+		if (explicit_vertical_columns(ctx, in, out, dt)) return 1;
+	}
 	return nh_launch(ctx, in, out, dt, false, true, stage_base_out());
 }
 
@@ -1903,8 +1938,9 @@ extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double d
 		return tb200_h_step_explicit(ctx, in, out, dt);
 	}
 	if (in == out) TB_FAIL(ctx, "HorizontalDynamics Step must have iDataInitial != iDataUpdate");
-	if (ctx->lay.ntr > 0 && !stage_fast_ok(ctx)) {
-		// the tracer filter sits between the two plugins in the reference
+	if ((ctx->lay.ntr > 0 && !stage_fast_ok(ctx)) || ctx->cfg.fully_explicit) {
+		// the tracer filter sits between the two plugins in the reference;
+		// --explicitvertical adds the column tendencies in the vertical plugin
 		if (tb200_h_step_explicit(ctx, in, out, dt)) return 1;
 		return tb200_v_step_explicit(ctx, in, out, dt);
 	}
@@ -1951,7 +1987,8 @@ extern "C" int tb200_hv_step_explicit_combine(
 	if (ncoeff > ni) TB_FAIL(ctx, "Too many elements in coefficient vector.");
 	const bool fusable =
 		(ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && (ctx->lay.nlev > 1)
-		&& (ctx->lay.ntr == 0 || stage_fast_ok(ctx)) && (in != out);
+		&& (ctx->lay.ntr == 0 || stage_fast_ok(ctx)) && (in != out)
+		&& !ctx->cfg.fully_explicit;
 	if (!fusable) {
 		if (tb200_lincomb(ctx, coeff, ncoeff, out, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
 		return tb200_hv_step_explicit(ctx, in, out, dt);
@@ -2739,10 +2776,17 @@ static int dss_rows(
 		// i.e. an element's contiguous block of rows is streamed by blocks that run
 		// together (ne = 120, L = 30: 0.757 -> 0.711 ms per pass, two batches of
 		// TBD_B rows per block; TB200_DSS_ORDER=groups: groups fastest, one batch)
-		static const bool rows_fastest = []() {
+		// On several ranks the passes are short and interleaved with the exchange:
+		// measured on 8 GPUs the old order wins there (2.60 against 2.64 ms per step,
+		// twice each), so the new one is the default on one rank only
+		// (TB200_DSS_ORDER=rows / groups forces either).
+		static const int order_env = []() {
 			const char * e = getenv("TB200_DSS_ORDER");
-			return !(e != 0 && strcmp(e, "groups") == 0);
+			if (e != 0 && strcmp(e, "groups") == 0) return 0;
+			if (e != 0 && strcmp(e, "rows") == 0) return 1;
+			return -1;
 		}();
+		const bool rows_fastest = (order_env >= 0) ? (order_env == 1) : (ctx->nranks == 1);
 		const int gx = (a.ngroups + block - 1) / block;
 		if (rows_fastest && classes && gx <= 65535 && getenv("TB200_DSS_GY") == 0) {
 			gy = (nsel + 2 * TBD_B - 1) / (2 * TBD_B);

@@ -34,7 +34,8 @@ struct ColumnArgs {
 	int fe_nodes;           // nodes per vertical finite element
 	double upwind_coeff;    // m_dUpwindCoeff
 	int * info;             // device flag: first failing column + 1
-	int assemble_only;      // debugging: stop before the solve
+	int assemble_only;      // debugging: 1 stop before the solve, 2 after it;
+	                        // 3: fully explicit vertical step (update -= dt F)
 };
 
 // number of workspace entries per column
@@ -193,7 +194,9 @@ __global__ void k_column_implicit(
 	const int offd = ca.offd;
 	const int ldab = 3 * offd + 1;
 
-	const int node = ca.col_node[ca.col0 + tcol];
+	// (col_node == 0: every element-local node is its own column - the fully
+	// explicit vertical step visits all of them, VerticalDynamicsFEM.cpp:723-724)
+	const int node = (ca.col_node != 0) ? ca.col_node[ca.col0 + tcol] : (ca.col0 + tcol);
 	const long long e = node / NN;
 	const int nd = node % NN;
 	const size_t ebase = (size_t)e * lay.nrows * NN;
@@ -494,6 +497,22 @@ __global__ void k_column_implicit(
 #undef TB_MAT
 
 	if (ca.assemble_only == 1) return;
+
+	if (ca.assemble_only == 3) {
+		// VerticalDynamicsFEM::StepExplicit with m_fFullyExplicit (:748-793):
+		// Evaluate(column state) = BuildF, update -= dt * F on rho theta, w, rho
+		double * oP = out + ebase + nd + (size_t)lay.rowoff[PIx] * NN;
+		double * oW = out + ebase + nd + (size_t)lay.rowoff[WIx] * NN;
+		double * oR = out + ebase + nd + (size_t)lay.rowoff[RIx] * NN;
+		for (int k = 0; k < L; k++) {
+			oP[(size_t)k * NN] -= ca.dt * F(3 * k + FP);
+			oR[(size_t)k * NN] -= ca.dt * F(3 * k + FR);
+		}
+		for (int k = 0; k <= L; k++) {
+			oW[(size_t)k * NN] -= ca.dt * F(3 * k + FW);
+		}
+		return;
+	}
 
 	// ---- direct solve and update (:1457-1536) -------------------------------
 	const int r = tb_dgbsv(n, offd, offd, DG, F);

@@ -211,6 +211,18 @@ CASES["jw_ne2_l30_hs"] = dict(
     script="addw:0,20000;dss:0;dump:ic,0;hs:1800;dump:hs1,0;hs:250.5;dump:hs2,0",
     geometry_from="jw_ne2_l30", compact=True, surface_product=True)
 
+# --explicitvertical: VerticalDynamicsFEM::StepExplicit also advances
+# rho theta, w, rho with the column tendencies (VerticalDynamicsFEM.cpp:748-793),
+# StepImplicit does nothing (:1240-1242); one stage and two Strang steps at a
+# time step the explicit vertical allows
+CASES["jw_ne2_l6_explicitv"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "1s", "--explicitvertical"],
+    script=";".join([
+        "addw:0,20000", "dss:0", "dump:ic,0", "copy:0,1", "hexp:0,1,1", "vexp:0,1,1",
+        "dump:v1,1", "copy:1,2", "vimp:2,2,1", "dump:vi,2",
+        "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0"]),
+    geometry_from="jw_ne2_l6", compact=True)
+
 _SHARED_PREFIXES = ("patch", "op.", "grid.")
 
 

@@ -18,7 +18,8 @@ def S(d, k):
 
 
 def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
-                      nranks=1, exchange=None, analytic_metric=True, lean=False):
+                      nranks=1, exchange=None, analytic_metric=True, lean=False,
+                      fully_explicit=0):
     npatch = S(d, "grid.npatch")
     np_ = S(d, "grid.np")
     nlev = S(d, "grid.nlev")
@@ -41,7 +42,7 @@ def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
         nu_scalar=0.0 if S(d, "run.nohypervis") else S(d, "run.nu_scalar"),
         nu_div=0.0 if S(d, "run.nohypervis") else S(d, "run.nu_div"),
         nu_vort=0.0 if S(d, "run.nohypervis") else S(d, "run.nu_vort"),
-        fully_explicit=0, off_centering=0.0,
+        fully_explicit=fully_explicit, off_centering=0.0,
     )
     ctx = DeviceContext(library=library, **cfg)
     if nranks > 1:

@@ -168,3 +168,19 @@ def test_held_suarez_dropin(cuda_library, mode, outputtime):
     assert abs(got["RhoTheta"] - ref["RhoTheta"]) <= 1e-11 * abs(ref["RhoTheta"]), (got, ref)
     change = abs(ref["U"] - plain["U"])
     assert abs(got["U"] - ref["U"]) <= 1e-3 * change + 1e-6 * abs(ref["U"]), (got, ref, plain)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["plugins", "scheme"])
+def test_explicit_vertical_dropin(cuda_library, mode):
+    """--explicitvertical through the reference's driver flow: the
+    vertical plugin advances rho theta, w and rho explicitly, StepImplicit is a
+    no-op.  JW ne=4 L10, dt = 1 s, 5 steps."""
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "jw", "--resolution", "4", "--levels", "10", "--dt", "1s",
+             "--endtime", "5s", "--explicitvertical"]
+    ref, _ = run("none", *flags)
+    got, _ = run(mode, *flags)
+    for k in ("Rho", "RhoTheta"):
+        assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k]), (k, got, ref)
+    assert abs(got["U"] - ref["U"]) <= 1e-10 * abs(ref["U"]), (got, ref)

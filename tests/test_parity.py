@@ -677,3 +677,28 @@ def test_conservation_diagnostics(library, name):
         with pytest.raises(TempestError, match="Not implemented for ShallowWaterEquations"):
             ctx.total_vertical_momentum(0)
     ctx.close()
+
+
+def test_explicit_vertical(library):
+    """--explicitvertical (SURVEY 8 f-4): VerticalDynamicsFEM::StepExplicit advances
+    rho theta, w and rho with the column tendencies as well
+    (VerticalDynamicsFEM.cpp:748-793), StepImplicit does nothing (:1240-1242).
+    One explicit stage, the no-op implicit step and two Strang steps against the
+    reference run with the same flag (general kernels)."""
+    d = cases.load_case("jw_ne2_l6_explicitv")
+    ctx = dumpctx.context_from_dump(d, library=library, fully_explicit=1)
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 1.0)
+    ctx.v_step_explicit(0, 1, 1.0)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 1.0)
+    assert_below(dumpctx.compare(ctx, d, 2, "vi", [0, 1, 2, 4], [3]), TOL_DSS)
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 1.0)
+    ctx.step("strang", False, False, 1.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    ctx.close()
