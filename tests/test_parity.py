@@ -691,10 +691,18 @@ def test_explicit_vertical(library):
     ctx.copy(0, 1)
     ctx.h_step_explicit(0, 1, 1.0)
     ctx.v_step_explicit(0, 1, 1.0)
-    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1], []), TOL_STAGE)
+    # rho theta, w, rho carry the column tendencies (BuildF): like the implicit
+    # residual they are small differences of large terms (hydrostatic balance),
+    # held to the implicit stage's tolerance
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [2, 4], [3]), TOL_IMPLICIT)
     ctx.copy(1, 2)
     ctx.v_step_implicit(2, 2, 1.0)
-    assert_below(dumpctx.compare(ctx, d, 2, "vi", [0, 1, 2, 4], [3]), TOL_DSS)
+    # StepImplicit is a no-op: the same bits as before it, and the reference's state
+    before, after = dumpctx.download(ctx, d, 1), dumpctx.download(ctx, d, 2)
+    for n in before:
+        assert np.array_equal(before[n][0], after[n][0]) and np.array_equal(before[n][1], after[n][1])
+    assert_below(dumpctx.compare(ctx, d, 2, "vi", [0, 1, 2, 4], [3]), TOL_STATE)
     for m in range(1, ctx.cfg.ninstances):
         ctx.copy(0, m)
     ctx.step("strang", True, False, 1.0)
