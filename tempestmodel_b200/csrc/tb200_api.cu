@@ -1026,6 +1026,7 @@ extern "C" int tb200_upload_held_suarez(
 	}
 	if (upload_geom_array(ctx, *pi, latitude, 1, 1, ctx->d_hs_lat, 0, 0)) return 1;
 	if (upload_geom_array(ctx, *pi, surface_product, 1, 1, ctx->d_hs_sp, 0, 0)) return 1;
+	pi->has_held_suarez = true;
 	return 0;
 }
 
@@ -1036,7 +1037,12 @@ extern "C" int tb200_held_suarez(tb200_ctx * ctx, double dt) {
 	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO) {
 		TB_FAIL(ctx, "Held-Suarez physics needs the nonhydrostatic equation set");
 	}
-	if (ctx->d_hs_lat == 0) TB_FAIL(ctx, "Held-Suarez inputs not uploaded (tb200_upload_held_suarez)");
+	for (size_t p = 0; p < ctx->patches.size(); p++) {
+		// (the latitude array alone may exist from tb200_evaluate_geometry_cs)
+		if (ctx->patches[p].elem0 >= 0 && !ctx->patches[p].has_held_suarez) {
+			TB_FAIL(ctx, "Held-Suarez inputs not uploaded (tb200_upload_held_suarez)");
+		}
+	}
 	for (int c = 0; c < 5; c++) {
 		if (c != 3 && lay.onedge[c]) TB_FAIL(ctx, "Held-Suarez physics: Lorenz staggering only");
 	}

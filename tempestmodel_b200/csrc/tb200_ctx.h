@@ -25,7 +25,8 @@ struct PatchInfo {
 	std::vector<SeamEntry> seams;
 	bool has_terrain;
 	bool has_lonlat;      // tb200_evaluate_geometry_cs has run for this patch
-	PatchInfo() : has_terrain(false), has_lonlat(false) {}
+	bool has_held_suarez; // tb200_upload_held_suarez has run for this patch
+	PatchInfo() : has_terrain(false), has_lonlat(false), has_held_suarez(false) {}
 };
 
 struct HostOp {
