@@ -301,6 +301,30 @@ int tb200_filter_negative_tracers(tb200_ctx * ctx, int inst);
  * the column-wise filter (the one above is HorizontalDynamicsFEM's element-wise
  * filter, HorizontalDynamicsFEM.cpp:213-317). */
 int tb200_v_filter_negative_tracers(tb200_ctx * ctx, int inst);
+/* ---- output-side interpolation -----------------------------------------
+ * Grid::ReduceInterpolate (src/atm/Grid.cpp:866-990) -> GridPatchCSGLL::InterpolateData
+ * (src/atm/GridPatchCSGLL.cpp:1365-1780) of state instance `inst` on the device: the
+ * state (data_type TB200_DATA_STATE; only_location -1 every component, 0 those on
+ * levels, 1 those on interfaces = eOnlyVariablesAt) or the tracers
+ * (TB200_DATA_TRACERS) at npts points and nout REta values.  Per point: its patch,
+ * the element it lies in (indices inside the patch, :1605-1627), the np coefficients
+ * of PolynomialInterp::LagrangianPolynomialCoeffs along alpha and beta on that
+ * element's nodes (:1631-1641), alpha and beta themselves (wind conversion).  Per
+ * location the LinearColumnInterpFEM operator as a dense [nout][levels or
+ * interfaces] matrix with its [begin, end) windows (null = identity, nout = that
+ * count).  convert_to_primitive: w divided by DerivR[2], the covariant wind
+ * converted to zonal / meridional components (CubedSphereTrans::CoVecTransRLLFromABP,
+ * :1655-1690, 1735-1776).  The reference state is included (fIncludeReferenceState).
+ * out: host array [components or tracers][nout][npts]; points of patches that are
+ * not local stay zero (the reference sums the ranks' arrays). */
+int tb200_interpolate(tb200_ctx * ctx, int inst, int data_type, int only_location,
+                      int npts, const int * patch_index, const int * elem_a, const int * elem_b,
+                      const double * ca, const double * cb,
+                      const double * alpha, const double * beta, int nout,
+                      const double * vop_node, const int * vbegin_node, const int * vend_node,
+                      const double * vop_redge, const int * vbegin_redge, const int * vend_redge,
+                      int convert_to_primitive, double * out);
+
 /* ---- device-side set-up of cubed-sphere runs ------------------------
  * The 2-D metric and the initial state evaluated on the device instead of being
  * built on the host and copied over the bus.  Needs tb200_set_terrain_metric

@@ -25,6 +25,11 @@
 ///	  step:N                N calls of TimestepScheme::Step (first = first call)
 ///	  hs:SECONDS            HeldSuarezPhysics::Perform with that forcing interval
 ///	                        (a WorkflowProcess: acts on instance 0)
+///	  interp:TAG,NLON,NLAT,NZ,PRIM  Grid::ReduceInterpolate of instance 0 (state at
+///	                        both locations, tracers) to an NLON x NLAT latitude-longitude
+///	                        grid and NZ uniform REta levels, as OutputManagerReference
+///	                        does (OutputManagerReference.cpp:180-222, 585-612);
+///	                        PRIM = fConvertToPrimitive
 ///	  checksum:TAG          Grid::Checksum of instance 0 -> record
 ///	  addw:INST,AMP         test data: add a smooth non-zero W on interfaces
 ///	  perturb:INST,EPS      test data: relative pseudo-random noise of size EPS
@@ -56,6 +61,7 @@
 #include "HorizontalDynamicsFEM.h"
 #include "VerticalDynamicsFEM.h"
 #include "HeldSuarezPhysics.h"
+#include "LinearColumnOperatorFEM.h"
 
 #include <cstdio>
 #include <cstdint>
@@ -506,6 +512,61 @@ static void RunScript(Model & model, const std::string & strScript) {
 			const int iMicro = static_cast<int>((dSeconds - iSec) * 1.0e6 + 0.5);
 			HeldSuarezPhysics hs(model, Time(0, 0, 0, iSec, iMicro, Time::CalendarNoLeap, Time::TypeDelta));
 			hs.Perform(time);
+		} else if (op == "interp") {
+			const int nLon = atoi(a[1].c_str());
+			const int nLat = atoi(a[2].c_str());
+			const int nZ = atoi(a[3].c_str());
+			const bool fPrim = (atoi(a[4].c_str()) != 0);
+			const int nPts = nLon * nLat;
+			DataArray1D<double> dLonDeg(nPts), dLatDeg(nPts);
+			int ix = 0;
+			for (int j = 0; j < nLat; j++) {
+			for (int i = 0; i < nLon; i++) {
+				dLonDeg[ix] = 360.0 * (static_cast<double>(i) + 0.5) / static_cast<double>(nLon);
+				dLatDeg[ix] = -90.0 + 180.0 * (static_cast<double>(j) + 0.5) / static_cast<double>(nLat);
+				ix++;
+			}
+			}
+			DataArray1D<double> dAlpha(nPts), dBeta(nPts);
+			DataArray1D<int> iPatch(nPts);
+			pGrid->ConvertReferenceToPatchCoord(dLonDeg, dLatDeg, dAlpha, dBeta, iPatch);
+			DataArray1D<double> dREta(nZ);
+			for (int k = 0; k < nZ; k++) {
+				dREta[k] = (static_cast<double>(k) + 0.5) / static_cast<double>(nZ);
+			}
+			const int nComp = eqn.GetComponents();
+			DataArray3D<double> dNode(nComp, nZ, nPts);
+			DataArray3D<double> dREdge(nComp, nZ, nPts);
+			pGrid->ReduceInterpolate(
+				DataType_State, dREta, dAlpha, dBeta, iPatch, dNode,
+				DataLocation_Node, true, fPrim);
+			pGrid->ReduceInterpolate(
+				DataType_State, dREta, dAlpha, dBeta, iPatch, dREdge,
+				DataLocation_REdge, true, fPrim);
+			Write1D(a[0] + ".alpha", dAlpha);
+			Write1D(a[0] + ".beta", dBeta);
+			Write1I(a[0] + ".ipatch", iPatch);
+			Write1D(a[0] + ".reta", dREta);
+			Write3D(a[0] + ".node", dNode);
+			Write3D(a[0] + ".redge", dREdge);
+			if (eqn.GetTracers() != 0) {
+				DataArray3D<double> dTr(eqn.GetTracers(), nZ, nPts);
+				pGrid->ReduceInterpolate(
+					DataType_Tracers, dREta, dAlpha, dBeta, iPatch, dTr,
+					DataLocation_None, true, fPrim);
+				Write3D(a[0] + ".tracers", dTr);
+			}
+			// the vertical operators GridPatchCSGLL::InterpolateData builds (:1470-1487)
+			GridGLL * pGridGLL = dynamic_cast<GridGLL*>(pGrid);
+			LinearColumnInterpFEM opN, opE;
+			opN.Initialize(
+				LinearColumnInterpFEM::InterpSource_Levels, pGridGLL->GetVerticalOrder(),
+				pGrid->GetREtaLevels(), pGrid->GetREtaInterfaces(), dREta);
+			opE.Initialize(
+				LinearColumnInterpFEM::InterpSource_Interfaces, pGridGLL->GetVerticalOrder(),
+				pGrid->GetREtaLevels(), pGrid->GetREtaInterfaces(), dREta);
+			WriteOp(a[0] + ".vop_node", opN);
+			WriteOp(a[0] + ".vop_redge", opE);
 		} else if (op == "checksum") {
 			DataArray1D<double> dSums;
 			pGrid->Checksum(DataType_State, dSums, 0, ChecksumType_Sum);

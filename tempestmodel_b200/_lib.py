@@ -121,6 +121,8 @@ _SIGNATURES = {
     "tb200_v_filter_negative_tracers": (c_int, [c_void_p, c_int]),
     "tb200_lincomb_v_filter": (c_int, [c_void_p, POINTER(c_double), c_int, c_int]),
     "tb200_evaluate_geometry_cs": (c_int, [c_void_p, c_int, c_double, c_double]),
+    "tb200_interpolate": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7
+                          + [c_int] + [c_void_p] * 6 + [c_int, c_void_p]),
     "tb200_debug_column_field": (c_int, [c_void_p, c_int, c_void_p]),
     "tb200_evaluate_jw_topography": (c_int, [c_void_p, c_int, POINTER(JWTest)]),
     "tb200_evaluate_jw_state": (c_int, [c_void_p, c_int, c_int, POINTER(JWTest)]),

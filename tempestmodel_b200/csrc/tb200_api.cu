@@ -25,6 +25,7 @@
 #include "tb200_diag.cuh"
 #include "tb200_physics.cuh"
 #include "tb200_setup.cuh"
+#include "tb200_output.cuh"
 
 static_assert(TBT_C_JAC == TBF_JAC && TBT_C_A2 == TBF_A2 && TBT_C_B2 == TBF_B2
 	&& TBT_C_X0 == TBF_X0 && TBT_C_X2 == TBF_X2 && TBT_C_NC == TBF_NC
@@ -1003,6 +1004,142 @@ extern "C" int tb200_evaluate_jw_state(
 	TB_CHECK(ctx, cudaMemcpy(&failed, ctx->d_info + 2, sizeof(int), cudaMemcpyDeviceToHost));
 	// BaroclinicWaveJWTest.cpp:337-339
 	if (failed != 0) TB_FAIL(ctx, "Maximum number of iterations exceeded.");
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// Output-side interpolation (tb200_output.cuh)
+
+namespace {
+struct DevTemp {
+	std::vector<void *> p;
+	~DevTemp() { for (size_t q = 0; q < p.size(); q++) cudaFree(p[q]); }
+	template <typename T> T * up(tb200_ctx * ctx, const T * host, size_t n, bool * ok) {
+		void * d = 0;
+		if (cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) { *ok = false; return 0; }
+		p.push_back(d);
+		if (host != 0 && n > 0
+			&& cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { *ok = false; }
+		(void)ctx;
+		return (T *)d;
+	}
+};
+}
+
+// Grid::ReduceInterpolate (Grid.cpp:866-990) / GridPatchCSGLL::InterpolateData
+// (GridPatchCSGLL.cpp:1365-1780) of instance `inst`: data_type TB200_DATA_STATE or
+// TB200_DATA_TRACERS; only_location -1 all components, 0 those on levels, 1 those
+// on interfaces (eOnlyVariablesAt); per point its patch, element (elem_a, elem_b:
+// element indices inside the patch), the np Lagrangian coefficients along alpha
+// and beta of that element's GLL nodes, and its alpha, beta (primitive wind);
+// per location the column operator (dense [nout][nin] with [begin, end) windows;
+// a null operator = identity, nout = nin).  out: [ncomp or ntracers][nout][npts],
+// zero for points of patches that are not local (the reference sums over ranks)
+// and for components that were not asked for.
+extern "C" int tb200_interpolate(
+	tb200_ctx * ctx, int inst, int data_type, int only_location,
+	int npts, const int * patch_index, const int * elem_a, const int * elem_b,
+	const double * ca, const double * cb, const double * alpha, const double * beta,
+	int nout,
+	const double * vop_node, const int * vbegin_node, const int * vend_node,
+	const double * vop_redge, const int * vbegin_redge, const int * vend_redge,
+	int convert_to_primitive, double * out
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid instance");
+	const DevLayout & lay = ctx->lay;
+	const bool tracers = (data_type == TB200_DATA_TRACERS);
+	if (!tracers && data_type != TB200_DATA_STATE) TB_FAIL(ctx, "Invalid DataType");
+	const int ncomp = tracers ? lay.ntr : lay.ncomp;
+	if (npts <= 0 || nout <= 0 || ncomp == 0) return 0;
+	if (lay.nlev + 1 > TB_INTERP_MAXLEV) TB_FAIL(ctx, "too many levels for the interpolation kernel");
+	const int np = lay.np;
+	std::vector<int> elem(npts), panel(npts);
+	for (int i = 0; i < npts; i++) {
+		PatchInfo * pi = find_patch(ctx, patch_index[i]);
+		elem[i] = -1;
+		panel[i] = 0;
+		if (pi == 0) TB_FAIL(ctx, "unknown patch");
+		panel[i] = pi->panel;
+		if (pi->elem0 < 0) continue;
+		if (elem_a[i] < 0 || elem_a[i] >= pi->nea || elem_b[i] < 0 || elem_b[i] >= pi->neb) {
+			TB_FAIL(ctx, "Point out of range");          // GridPatchCSGLL.cpp:1596-1602
+		}
+		elem[i] = (int)(pi->elem0 + (long long)elem_a[i] * pi->neb + elem_b[i]);
+	}
+	// identity operators when none is given
+	std::vector<double> idn, ide;
+	std::vector<int> bn, en, be, ee;
+	const int L = lay.nlev;
+	auto identity = [&](int n, std::vector<double> & m, std::vector<int> & b, std::vector<int> & e) {
+		m.assign((size_t)n * n, 0.0); b.resize(n); e.resize(n);
+		for (int q = 0; q < n; q++) { m[(size_t)q * n + q] = 1.0; b[q] = q; e[q] = q + 1; }
+	};
+	if (vop_node == 0) {
+		if (nout != L && !tracers) { /* checked per component below */ }
+		identity(L, idn, bn, en);
+	}
+	if (vop_redge == 0) identity(L + 1, ide, be, ee);
+	bool ok = true;
+	DevTemp tmp;
+	int * d_elem = tmp.up(ctx, elem.data(), (size_t)npts, &ok);
+	int * d_panel = tmp.up(ctx, panel.data(), (size_t)npts, &ok);
+	double * d_ca = tmp.up(ctx, ca, (size_t)npts * np, &ok);
+	double * d_cb = tmp.up(ctx, cb, (size_t)npts * np, &ok);
+	double * d_alpha = tmp.up(ctx, alpha, (size_t)npts, &ok);
+	double * d_beta = tmp.up(ctx, beta, (size_t)npts, &ok);
+	const int nout_n = (vop_node != 0) ? nout : L;
+	const int nout_e = (vop_redge != 0) ? nout : (L + 1);
+	double * d_vn = tmp.up(ctx, vop_node != 0 ? vop_node : idn.data(), (size_t)nout_n * L, &ok);
+	int * d_bn = tmp.up(ctx, vop_node != 0 ? vbegin_node : bn.data(), (size_t)nout_n, &ok);
+	int * d_en = tmp.up(ctx, vop_node != 0 ? vend_node : en.data(), (size_t)nout_n, &ok);
+	double * d_ve = tmp.up(ctx, vop_redge != 0 ? vop_redge : ide.data(), (size_t)nout_e * (L + 1), &ok);
+	int * d_be = tmp.up(ctx, vop_redge != 0 ? vbegin_redge : be.data(), (size_t)nout_e, &ok);
+	int * d_ee = tmp.up(ctx, vop_redge != 0 ? vend_redge : ee.data(), (size_t)nout_e, &ok);
+	const size_t per_comp = (size_t)nout * npts;
+	double * d_out = tmp.up(ctx, (const double *)0, per_comp * ncomp, &ok);
+	if (!ok) TB_FAIL(ctx, "interpolation: device allocation failed");
+	TB_CHECK(ctx, cudaMemset(d_out, 0, per_comp * ncomp * sizeof(double)));
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+
+	for (int c = 0; c < ncomp; c++) {
+		const int onedge = tracers ? 0 : lay.onedge[c];
+		if (!tracers && only_location >= 0 && only_location != onedge) continue;
+		if ((onedge ? nout_e : nout_n) != nout) {
+			TB_FAIL(ctx, "InterpData dimension mismatch (1)");      // Grid.cpp:938-940
+		}
+		InterpArgs a;
+		a.npts = npts; a.nout = nout;
+		a.elem = d_elem; a.ca = d_ca; a.cb = d_cb;
+		a.vop = onedge ? d_ve : d_vn;
+		a.vbegin = onedge ? d_be : d_bn;
+		a.vend = onedge ? d_ee : d_en;
+		a.nin = onedge ? (L + 1) : L;
+		a.row0 = tracers ? (lay.troff + c * L) : lay.rowoff[c];
+		// w -> primitive (:1655-1690): divided by DerivR[2] at the element's first node
+		a.divide_derivr = (!tracers && convert_to_primitive && c == 3
+			&& ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) ? 1 : 0;
+		a.derivr = onedge ? ctx->geom.dre[2] : ctx->geom.dr[2];
+		a.zs = ctx->g2d[6];
+		a.ztop = ctx->cfg.ztop;
+		a.out = d_out + per_comp * c;
+		auto kfn = k_interpolate_component;
+		TB_LAUNCH_FLAT(kfn, dim3((npts + 63) / 64), dim3(64), 0, ctx->stream,
+			lay, a, (const double *)ctx->inst[inst]);
+		TB_KERNEL_CHECK(ctx);
+	}
+	if (!tracers && convert_to_primitive && lay.ncomp >= 2
+		&& (only_location < 0 || only_location == lay.onedge[0])) {
+		const long long total = (long long)npts * nout;
+		auto kfn = k_interpolate_wind;
+		TB_LAUNCH_FLAT(kfn, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, ctx->stream,
+			npts, nout, (const int *)d_elem, (const int *)d_panel,
+			(const double *)d_alpha, (const double *)d_beta, ctx->cfg.earth_radius,
+			d_out, d_out + per_comp);
+		TB_KERNEL_CHECK(ctx);
+	}
+	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+	TB_CHECK(ctx, cudaMemcpy(out, d_out, per_comp * ncomp * sizeof(double), cudaMemcpyDeviceToHost));
 	return 0;
 }
 

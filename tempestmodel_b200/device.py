@@ -161,6 +161,32 @@ class DeviceContext:
         patch from the node coordinates already on the device."""
         self._ck(self.lib.tb200_evaluate_geometry_cs(self._h, patch, radius, omega))
 
+    def interpolate(self, inst, data_type, only_location, patch, elem_a, elem_b, ca, cb,
+                    alpha, beta, nout, vop_node=None, vop_redge=None, primitive=True):
+        """Grid::ReduceInterpolate on the device (tb200_output.cuh).  vop_*: (dense
+        matrix, begin, end) of the LinearColumnInterpFEM operator or None (identity).
+        Returns [components or tracers][nout][npts]."""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        patch, elem_a, elem_b = i32(patch), i32(elem_a), i32(elem_b)
+        ca, cb, alpha, beta = _f64(ca), _f64(cb), _f64(alpha), _f64(beta)
+        npts = len(patch)
+        ncomp = self.cfg.ntracers if data_type == _lib.DATA_TRACERS else self.cfg.ncomp
+        out = np.zeros((ncomp, nout, npts))
+        keep = []
+
+        def op(v):
+            if v is None:
+                return None, None, None
+            m, b, e = _f64(v[0]), i32(v[1]), i32(v[2])
+            keep.extend([m, b, e])
+            return _ptr(m), _ptr(b), _ptr(e)
+        vn, ve = op(vop_node), op(vop_redge)
+        self._ck(self.lib.tb200_interpolate(
+            self._h, inst, data_type, only_location, npts, _ptr(patch), _ptr(elem_a),
+            _ptr(elem_b), _ptr(ca), _ptr(cb), _ptr(alpha), _ptr(beta), nout,
+            vn[0], vn[1], vn[2], ve[0], ve[1], ve[2], 1 if primitive else 0, _ptr(out)))
+        return out
+
     def column_field(self, which, nelem, nn=16):
         """Per-column device array [element][np * np] (0 Jacobian2D, 1, 2
         ContraMetric2DA, 3, 4 ContraMetric2DB, 5 Coriolis, 6 topography, 7 longitude,

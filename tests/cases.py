@@ -223,6 +223,14 @@ CASES["jw_ne2_l6_explicitv"] = dict(
         "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0"]),
     geometry_from="jw_ne2_l6", compact=True)
 
+# output-side interpolation: Grid::ReduceInterpolate of the state and
+# tracers to a latitude-longitude grid and uniform REta levels, with and without
+# the conversion to primitive variables
+CASES["jwtr_ne2_l6_interp"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--ntracers", "3"],
+    script="addw:0,20000;dss:0;dump:ic,0;interp:raw,12,7,5,0;interp:prim,12,7,5,1",
+    geometry_from="jw_ne2_l6", compact=True)
+
 _SHARED_PREFIXES = ("patch", "op.", "grid.")
 
 
