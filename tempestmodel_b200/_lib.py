@@ -119,7 +119,7 @@ _SIGNATURES = {
                                             c_double]),
     "tb200_filter_negative_tracers": (c_int, [c_void_p, c_int]),
     "tb200_v_filter_negative_tracers": (c_int, [c_void_p, c_int]),
-    "tb200_lincomb_v_filter": (c_int, [c_void_p, POINTER(c_double), c_int, c_int]),
+    "tb200_lincomb_v_filter": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "tb200_evaluate_geometry_cs": (c_int, [c_void_p, c_int, c_double, c_double]),
     "tb200_interpolate": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7
                           + [c_int] + [c_void_p] * 6 + [c_int, c_void_p]),

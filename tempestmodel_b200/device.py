@@ -312,6 +312,20 @@ class DeviceContext:
         c = _f64(coeff)
         self._ck(self.lib.tb200_lincomb(self._h, _ptr(c), len(c), dst, mask))
 
+    def lincomb_v_filter(self, coeff, dst):
+        """Grid::LinearCombineData(coeff -> dst) of state and tracers followed by
+        VerticalDynamics::FilterNegativeTracers(dst) (start of a Strang step)."""
+        c = _f64(coeff)
+        self._ck(self.lib.tb200_lincomb_v_filter(self._h, _ptr(c), len(c), dst))
+
+    def filter_negative_tracers(self, inst):
+        """HorizontalDynamicsFEM::FilterNegativeTracers (element-wise)."""
+        self._ck(self.lib.tb200_filter_negative_tracers(self._h, inst))
+
+    def v_filter_negative_tracers(self, inst):
+        """VerticalDynamicsFEM::FilterNegativeTracers (column-wise)."""
+        self._ck(self.lib.tb200_v_filter_negative_tracers(self._h, inst))
+
     def zero(self, inst, mask=DATA_ALL):
         self._ck(self.lib.tb200_zero(self._h, inst, mask))
 

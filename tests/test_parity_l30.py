@@ -345,3 +345,29 @@ def test_tracer_stage_kernels_agree(library, monkeypatch):
     for n in res[0]:
         a, b = np.asarray(res[0][n]), np.asarray(res[1][n])
         assert np.abs(a - b).max() <= 1e-14 * np.abs(b).max(), n
+
+
+def test_carry_over_with_fused_tracer_filter(library):
+    """tb200_lincomb_v_filter (the start of a Strang step: instance 0 += increment,
+    then the column filter of the tracers, with the tracer combination formed
+    inside the filter kernel) against the two separate calls: the same bits."""
+    d = cases.load_case("jwtr_ne2_l30")
+    res = []
+    for fused in (False, True):
+        ctx = dumpctx.context_from_dump(d, library=library)
+        dumpctx.upload_tag(ctx, d, "ic")
+        # an "increment" with negative tracer values in instance 1
+        ctx.copy(0, 1)
+        ctx.lincomb([0.0, -0.37], 1)
+        ctx.h_step_explicit(0, 1, 400.0)
+        if fused:
+            ctx.lincomb_v_filter([1.0, 1.0], 0)
+        else:
+            ctx.lincomb([1.0, 1.0], 0)
+            ctx.v_filter_negative_tracers(0)
+        res.append((dumpctx.download(ctx, d, 0), dumpctx.download_tracers(ctx, d, 0)))
+        ctx.close()
+    for n in res[0][0]:
+        assert np.array_equal(res[0][0][n][0], res[1][0][n][0])
+        assert np.array_equal(res[0][0][n][1], res[1][0][n][1])
+        assert np.array_equal(np.asarray(res[0][1][n]), np.asarray(res[1][1][n]))
