@@ -67,6 +67,9 @@ class Model:
         self._host_tracers = {}
         self.device_setup = False
         self._device_state = []
+        # workflow processes (Model::AttachWorkflowProcess, Model.cpp:232-240): run on
+        # instance 0 after every step, on the device
+        self.workflow = []
         # lean geometry: upload the 2-D metric, topography derivatives and the
         # vertical coordinate only (no 3-D metric arrays: 26 values per node);
         # the column-constant kernels need nothing else
@@ -132,6 +135,30 @@ class Model:
             from .parallel import enable_peer_exchange
             self.peer_exchange = enable_peer_exchange(ctx, self.rank, self.nranks)
         return self
+
+    # -- workflow processes: column physics as device steps (Model.cpp:477-481) ------
+    def attach_held_suarez(self):
+        """HeldSuarezPhysics with the model's time step as its frequency
+        (HeldSuarezTest.cpp:373-377).  The per-column inputs come from the set-up:
+        latitude, and the product of the rho and rho-theta slots of the lowest
+        interface, which the reference fills from the test case at set-up and never
+        updates (HeldSuarezPhysics.cpp:112-115)."""
+        g, ph = self.grid, self.grid.phys
+        for p in self.local:
+            zs = p._zs[:, :, None]
+            st = self.test.evaluate_pointwise_state(ph, zs, p.lon[:, :, None], p.lat[:, :, None])
+            st = [np.broadcast_to(x, zs.shape) for x in st]
+            # EquationSet::ConvertComponents: the theta slot holds rho theta
+            prod = (st[4] * (st[2] * st[4]))[:, :, 0]
+            self.ctx.upload_held_suarez(p.index, p._pad(p.lat), p._pad(prod))
+        self.workflow.append(("HeldSuarezPhysics", lambda: self.ctx.held_suarez(self.dt)))
+
+    def attach_kessler(self):
+        """KesslerPhysics with the model's time step as its frequency
+        (test/dcmip2016: tracers 0, 1, 2 = rho qv, rho qc, rho qr)."""
+        if self.ntracers < 3:
+            raise ValueError("Kessler physics needs three tracers (rho qv, rho qc, rho qr)")
+        self.workflow.append(("KesslerPhysics", lambda: self.ctx.kessler(self.dt)))
 
     def _device_jw(self):
         """device_setup on a cubed sphere with the Jablonowski-Williamson case (or
@@ -206,6 +233,10 @@ class Model:
             is_last = last and (s == nsteps - 1)
             self.ctx.step(SCHEMES[self.timescheme], first, is_last, self.dt)
             self.steps_taken += 1
+            # WorkflowProcess::Perform of every attached process (all are ready every
+            # step: their frequency is the time step)
+            for _name, perform in self.workflow:
+                perform()
         if check:
             self.ctx.check_errors()
 

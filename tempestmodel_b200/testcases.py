@@ -264,3 +264,26 @@ class BaroclinicWaveJWTracerTest(BaroclinicWaveJWTest):
                 q = xp.where(dd < 1.0, 0.5e-2 * (1.0 + xp.cos(math.pi * dd)), 0.0 * dd)
             out.append(rho * q)
         return out
+
+
+class BaroclinicWaveJWMoistTest(BaroclinicWaveJWTracerTest):
+    """The JW wave with moisture: tracers 0, 1, 2 are rho qv, rho qc, rho qr (the
+    Kessler categories), the rest the analytic tracers of the stand-in case.  The
+    specific humidity is the DCMIP-2016 profile q0 exp(-(lat / latw)^4)
+    exp(-((eta - 1) p0 / pw)^2) with eta taken as the isothermal-atmosphere value
+    exp(-z / H): test data for the moist configuration 4, not a reference test."""
+
+    def __init__(self, ntracers=5, q0=0.018, **kw):
+        super().__init__(ntracers=ntracers, **kw)
+        if self.ntracers < 3:
+            raise ValueError("the moist case carries at least rho qv, rho qc, rho qr")
+        self.q0 = q0
+
+    def evaluate_tracers(self, phys, z, lon, lat, rho, xp=NUMPY):
+        rest = super().evaluate_tracers(phys, z, lon, lat, rho, xp)
+        eta = xp.exp(-z / 8000.0)
+        latw = 2.0 * math.pi / 9.0
+        pw = 34000.0
+        q = self.q0 * xp.exp(-(lat / latw) ** 4) * xp.exp(-((eta - 1.0) * phys.p0 / pw) ** 2)
+        zero = 0.0 * q
+        return [rho * q, rho * zero, rho * zero] + rest[3:]
