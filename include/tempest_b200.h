@@ -39,6 +39,10 @@ typedef struct tb200_ctx tb200_ctx;
 /* DataType selector (src/atm/DataType.h): bit mask */
 #define TB200_DATA_STATE 1
 #define TB200_DATA_TRACERS 2
+/* derived output fields (tb200_compute_output_fields, tb200_interpolate) */
+#define TB200_DATA_TEMPERATURE 4
+#define TB200_DATA_VORTICITY 8
+#define TB200_DATA_DIVERGENCE 16
 
 /* Vertical column operators of GridGLL (src/atm/GridGLL.h:357-448) */
 enum tb200_column_op {
@@ -317,6 +321,13 @@ int tb200_v_filter_negative_tracers(tb200_ctx * ctx, int inst);
  * :1655-1690, 1735-1776).  The reference state is included (fIncludeReferenceState).
  * out: host array [components or tracers][nout][npts]; points of patches that are
  * not local stay zero (the reference sums the ranks' arrays). */
+/* Grid::ComputeVorticityDivergence (GridPatchCSGLL::ComputeCurlAndDiv,
+ * src/atm/GridPatchCSGLL.cpp:1132-1361) and Grid::ComputeTemperature
+ * (src/atm/GridPatch.cpp:641-700) of state instance `inst`: relative vorticity and
+ * divergence of the horizontal wind element by element, temperature (nonhydrostatic
+ * equations) on levels, kept on the device for tb200_interpolate with data_type
+ * TB200_DATA_VORTICITY / _DIVERGENCE / _TEMPERATURE (one component, on levels). */
+int tb200_compute_output_fields(tb200_ctx * ctx, int inst);
 int tb200_interpolate(tb200_ctx * ctx, int inst, int data_type, int only_location,
                       int npts, const int * patch_index, const int * elem_a, const int * elem_b,
                       const double * ca, const double * cb,

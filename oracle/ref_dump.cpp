@@ -556,6 +556,24 @@ static void RunScript(Model & model, const std::string & strScript) {
 					DataLocation_None, true, fPrim);
 				Write3D(a[0] + ".tracers", dTr);
 			}
+			// derived fields of instance 0 (OutputManagerReference.cpp:640-700)
+			{
+				pGrid->ComputeVorticityDivergence(0);
+				DataArray3D<double> dV(1, nZ, nPts), dD(1, nZ, nPts);
+				pGrid->ReduceInterpolate(
+					DataType_Vorticity, dREta, dAlpha, dBeta, iPatch, dV);
+				pGrid->ReduceInterpolate(
+					DataType_Divergence, dREta, dAlpha, dBeta, iPatch, dD);
+				Write3D(a[0] + ".vorticity", dV);
+				Write3D(a[0] + ".divergence", dD);
+				if (eqn.GetType() == EquationSet::PrimitiveNonhydrostaticEquations) {
+					pGrid->ComputeTemperature(0);
+					DataArray3D<double> dT(1, nZ, nPts);
+					pGrid->ReduceInterpolate(
+						DataType_Temperature, dREta, dAlpha, dBeta, iPatch, dT);
+					Write3D(a[0] + ".temperature", dT);
+				}
+			}
 			// the vertical operators GridPatchCSGLL::InterpolateData builds (:1470-1487)
 			GridGLL * pGridGLL = dynamic_cast<GridGLL*>(pGrid);
 			LinearColumnInterpFEM opN, opE;

@@ -18,6 +18,9 @@ EQN_PRIMITIVE_NONHYDRO = 2
 DATA_STATE = 1
 DATA_TRACERS = 2
 DATA_ALL = 3
+DATA_TEMPERATURE = 4
+DATA_VORTICITY = 8
+DATA_DIVERGENCE = 16
 
 OP_NAMES = ["interp_n2e", "interp_e2n", "diff_n2n", "diff_n2e", "diff_e2n",
             "diff_e2e", "diffdiff_n2n", "diffdiff_e2e", "penalty_left",
@@ -121,6 +124,7 @@ _SIGNATURES = {
     "tb200_v_filter_negative_tracers": (c_int, [c_void_p, c_int]),
     "tb200_lincomb_v_filter": (c_int, [c_void_p, c_void_p, c_int, c_int]),
     "tb200_evaluate_geometry_cs": (c_int, [c_void_p, c_int, c_double, c_double]),
+    "tb200_compute_output_fields": (c_int, [c_void_p, c_int]),
     "tb200_interpolate": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7
                           + [c_int] + [c_void_p] * 6 + [c_int, c_void_p]),
     "tb200_debug_column_field": (c_int, [c_void_p, c_int, c_void_p]),

@@ -1026,6 +1026,59 @@ struct DevTemp {
 };
 }
 
+// Derived output fields of an instance, kept on the device (tb200_output.cuh):
+// GridGLL::ComputeVorticityDivergence (GridGLL.cpp:587-601) = ComputeCurlAndDiv on
+// every patch + ApplyDSS of vorticity and divergence; Grid::ComputeTemperature.
+static int dss_rows(tb200_ctx * ctx, int inst, int row0, int row1, bool is_state, bool remainder_only);
+
+extern "C" int tb200_compute_output_fields(tb200_ctx * ctx, int inst) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid instance");
+	if (!ctx->connectivity_built) TB_FAIL(ctx, "connectivity not built");
+	const DevLayout & lay = ctx->lay;
+	if (lay.ncomp < 2) TB_FAIL(ctx, "Insufficient components for vorticity calculation");
+	if (lay.np != 4) TB_FAIL(ctx, "output fields: np = 4 only");
+	const int L = lay.nlev;
+	if (3 * L > lay.nrows && ctx->nranks > 1) {
+		TB_FAIL(ctx, "output fields: exchange buffers too small for this layout");
+	}
+	const size_t n = (size_t)lay.nelem * 3 * L * lay.nn;
+	if (ctx->d_outfield == 0 && dalloc(ctx, &ctx->d_outfield, n)) return 1;
+	if (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
+		for (int c = 2; c < 5; c++) {
+			if (c != 3 && lay.onedge[c]) TB_FAIL(ctx, "output temperature: rho theta and rho on levels only");
+		}
+		const double gamma = ctx->cfg.cp / (ctx->cfg.cp - ctx->cfg.R);
+		const double pscale = ctx->cfg.p0 * pow(ctx->cfg.R / ctx->cfg.p0, gamma);
+		long long nb = ((long long)lay.nelem * L * lay.nn + 255) / 256;
+		if (nb > 148 * 16) nb = 148 * 16;
+		auto kfn = k_output_temperature;
+		TB_LAUNCH_FLAT(kfn, dim3((unsigned)nb), dim3(256), 0, ctx->stream,
+			lay, pscale, gamma, ctx->cfg.R, (const double *)ctx->inst[inst], ctx->d_outfield);
+		TB_KERNEL_CHECK(ctx);
+	}
+	{
+		const long long nitems = lay.nelem * L;
+		auto kfn = k_output_curl_div<4, kItems>;
+		TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
+			ctx->stream, lay, ctx->geom, ctx->tables, (const double *)ctx->inst[inst],
+			ctx->d_outfield);
+		TB_KERNEL_CHECK(ctx);
+	}
+	// ApplyDSS(0, DataType_Vorticity / DataType_Divergence): the field array is laid
+	// out like an instance of 3 L rows per element, so the averaging (and exchange)
+	// kernels run on it with that row count; scalars, no seam re-basing
+	const DevLayout saved = ctx->lay;
+	ctx->lay.nrows = 3 * L;
+	ctx->lay.nrows_state = 3 * L;
+	ctx->inst.push_back(ctx->d_outfield);
+	const int slot = (int)ctx->inst.size() - 1;
+	const int rc = dss_rows(ctx, slot, 0, 2 * L, false, false);
+	ctx->inst.pop_back();
+	ctx->lay = saved;
+	return rc;
+}
+
 // Grid::ReduceInterpolate (Grid.cpp:866-990) / GridPatchCSGLL::InterpolateData
 // (GridPatchCSGLL.cpp:1365-1780) of instance `inst`: data_type TB200_DATA_STATE or
 // TB200_DATA_TRACERS; only_location -1 all components, 0 those on levels, 1 those
@@ -1049,8 +1102,16 @@ extern "C" int tb200_interpolate(
 	if (inst < 0 || inst >= (int)ctx->inst.size()) TB_FAIL(ctx, "invalid instance");
 	const DevLayout & lay = ctx->lay;
 	const bool tracers = (data_type == TB200_DATA_TRACERS);
-	if (!tracers && data_type != TB200_DATA_STATE) TB_FAIL(ctx, "Invalid DataType");
-	const int ncomp = tracers ? lay.ntr : lay.ncomp;
+	// derived fields (tb200_compute_output_fields): one component on levels
+	int derived = -1;
+	if (data_type == TB200_DATA_TEMPERATURE) derived = 0;
+	if (data_type == TB200_DATA_VORTICITY) derived = 1;
+	if (data_type == TB200_DATA_DIVERGENCE) derived = 2;
+	if (derived >= 0 && ctx->d_outfield == 0) {
+		TB_FAIL(ctx, "output fields not computed (tb200_compute_output_fields)");
+	}
+	if (!tracers && derived < 0 && data_type != TB200_DATA_STATE) TB_FAIL(ctx, "Invalid DataType");
+	const int ncomp = (derived >= 0) ? 1 : (tracers ? lay.ntr : lay.ncomp);
 	if (npts <= 0 || nout <= 0 || ncomp == 0) return 0;
 	if (lay.nlev + 1 > TB_INTERP_MAXLEV) TB_FAIL(ctx, "too many levels for the interpolation kernel");
 	const int np = lay.np;
@@ -1102,9 +1163,10 @@ extern "C" int tb200_interpolate(
 	TB_CHECK(ctx, cudaMemset(d_out, 0, per_comp * ncomp * sizeof(double)));
 	TB_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
 
+	const bool on_levels_only = tracers || (derived >= 0);
 	for (int c = 0; c < ncomp; c++) {
-		const int onedge = tracers ? 0 : lay.onedge[c];
-		if (!tracers && only_location >= 0 && only_location != onedge) continue;
+		const int onedge = on_levels_only ? 0 : lay.onedge[c];
+		if (!on_levels_only && only_location >= 0 && only_location != onedge) continue;
 		if ((onedge ? nout_e : nout_n) != nout) {
 			TB_FAIL(ctx, "InterpData dimension mismatch (1)");      // Grid.cpp:938-940
 		}
@@ -1115,9 +1177,12 @@ extern "C" int tb200_interpolate(
 		a.vbegin = onedge ? d_be : d_bn;
 		a.vend = onedge ? d_ee : d_en;
 		a.nin = onedge ? (L + 1) : L;
-		a.row0 = tracers ? (lay.troff + c * L) : lay.rowoff[c];
+		// derived array: rows 0.. vorticity, L.. divergence, 2L.. temperature
+		const int drow[3] = {2 * L, 0, L};
+		a.row0 = (derived >= 0) ? drow[derived] : (tracers ? (lay.troff + c * L) : lay.rowoff[c]);
+		a.estride = (derived >= 0) ? 3 * L : lay.nrows;
 		// w -> primitive (:1655-1690): divided by DerivR[2] at the element's first node
-		a.divide_derivr = (!tracers && convert_to_primitive && c == 3
+		a.divide_derivr = (!on_levels_only && convert_to_primitive && c == 3
 			&& ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) ? 1 : 0;
 		a.derivr = onedge ? ctx->geom.dre[2] : ctx->geom.dr[2];
 		a.zs = ctx->g2d[6];
@@ -1125,10 +1190,11 @@ extern "C" int tb200_interpolate(
 		a.out = d_out + per_comp * c;
 		auto kfn = k_interpolate_component;
 		TB_LAUNCH_FLAT(kfn, dim3((npts + 63) / 64), dim3(64), 0, ctx->stream,
-			lay, a, (const double *)ctx->inst[inst]);
+			lay, a, (derived >= 0) ? (const double *)ctx->d_outfield
+			                       : (const double *)ctx->inst[inst]);
 		TB_KERNEL_CHECK(ctx);
 	}
-	if (!tracers && convert_to_primitive && lay.ncomp >= 2
+	if (!on_levels_only && convert_to_primitive && lay.ncomp >= 2
 		&& (only_location < 0 || only_location == lay.onedge[0])) {
 		const long long total = (long long)npts * nout;
 		auto kfn = k_interpolate_wind;

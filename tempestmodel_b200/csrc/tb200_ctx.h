@@ -128,6 +128,7 @@ struct tb200_ctx {
 	double * d_hs_lat; double * d_hs_sp;
 	double * d_lon;       // longitude per column (device-side set-up)
 	double * d_precip;    // accumulated precipitation per column (Kessler)
+	double * d_outfield;  // vorticity, divergence, temperature on levels [e][3 L][NN]
 	double * d_ws; int ws_cols; int * d_info;
 	double * d_ray_node; double * d_ray_redge; double * d_refstate;   // Rayleigh friction
 	bool has_rayleigh;
@@ -199,6 +200,7 @@ struct tb200_ctx {
 		for (int i = 0; i < 2; i++) { ev_stage_free[i] = 0; ev_stage_full[i] = 0; }
 		ev_compute = 0;
 		for (int i = 0; i < 7; i++) g2d[i] = 0;
+		d_outfield = 0;
 		for (int i = 0; i < 13; i++) { g3n[i] = 0; g3e[i] = 0; }
 	}
 };

@@ -30,6 +30,7 @@ struct InterpArgs {
 	const int * vend;          // [nout]
 	int nin;                   // levels (L) or interfaces (L + 1) of the rows
 	int row0;                  // first row of the component inside an element
+	long long estride;         // rows per element of the array the rows are read from
 	const double * derivr;     // w -> primitive: DerivR[2] at the rows' location
 	                           // [e][nin][NN], or 0
 	const double * zs;         // ... or ztop - zs (terrain-following, uniform levels)
@@ -50,7 +51,7 @@ __global__ void k_interpolate_component(DevLayout lay, InterpArgs a, const doubl
 	double col[TB_INTERP_MAXLEV];
 	const double * ca = a.ca + (size_t)i * np;
 	const double * cb = a.cb + (size_t)i * np;
-	const double * src = data + ((size_t)e * lay.nrows + a.row0) * NN;
+	const double * src = data + ((size_t)e * a.estride + a.row0) * NN;
 	for (int k = 0; k < a.nin; k++) {
 		double v = 0.0;
 		double dr = 1.0;
@@ -123,6 +124,86 @@ __global__ void k_interpolate_wind(
 	}
 	out_u[idx] = dUlon;
 	out_v[idx] = dUlat;
+}
+
+// ---- derived output fields on levels, one array shaped like a small instance ----------
+// field[((e * 3 L) + row) * NN + n]: rows 0 .. L-1 vorticity, L .. 2L-1 divergence,
+// 2L .. 3L-1 temperature (so that the averaging kernels of the DSS apply to it)
+
+// GridPatch::ComputeTemperature (GridPatch.cpp:641-700, FORMULATION_RHOTHETA_PI):
+// T = p / (rho R), p = PressureFromRhoTheta(rho theta)
+__global__ void k_output_temperature(
+	DevLayout lay, double pressure_scaling, double gamma, double R,
+	const double * data, double * field
+) {
+	const int NN = lay.nn;
+	const int L = lay.nlev;
+	const long long total = lay.nelem * (long long)L * NN;
+	for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	     idx < total; idx += (long long)gridDim.x * blockDim.x
+	) {
+		const long long e = idx / ((long long)L * NN);
+		const int r = (int)(idx % ((long long)L * NN));
+		const size_t ebase = (size_t)e * lay.nrows * NN;
+		const double rt = data[ebase + (size_t)lay.rowoff[2] * NN + r];
+		const double rho = data[ebase + (size_t)lay.rowoff[4] * NN + r];
+		const double dPressure = pressure_scaling * exp(log(rt) * gamma);
+		field[((size_t)e * 3 * L + 2 * L) * NN + r] = dPressure / (rho * R);
+	}
+}
+
+// GridPatchCSGLL::ComputeCurlAndDiv (GridPatchCSGLL.cpp:1132-1305) per (element,
+// level): one thread per node, the element's tile in shared memory.  ITEMS
+// (element, level) pairs per block.
+template <int NP, int ITEMS>
+__global__ void __launch_bounds__(NP * NP * ITEMS)
+k_output_curl_div(
+	DevLayout lay, DevGeom g, DevTables t, const double * data, double * field
+) {
+	const int NN = NP * NP;
+	__shared__ double sUa[ITEMS][NN];
+	__shared__ double sUb[ITEMS][NN];
+	__shared__ double sJa[ITEMS][NN];    // Jacobian2D * contravariant u^alpha
+	__shared__ double sJb[ITEMS][NN];
+	const int L = lay.nlev;
+	const int it = threadIdx.x / NN;
+	const int n = threadIdx.x % NN;
+	const int i = n / NP, j = n % NP;
+	const long long nitems = lay.nelem * L;
+	long long item = (long long)blockIdx.x * ITEMS + it;
+	const bool active = (item < nitems);
+	if (!active) item = nitems - 1;
+	const long long e = item / L;
+	const int k = (int)(item % L);
+	const size_t ebase = (size_t)e * lay.nrows * NN;
+	const size_t g2 = (size_t)e * NN + n;
+	const double dUa = data[ebase + (size_t)(lay.rowoff[0] + k) * NN + n];
+	const double dUb = data[ebase + (size_t)(lay.rowoff[1] + k) * NN + n];
+	const double conUa = + g.a0[g2] * dUa + g.a1[g2] * dUb;
+	const double conUb = + g.b0[g2] * dUa + g.b1[g2] * dUb;
+	sUa[it][n] = dUa;
+	sUb[it][n] = dUb;
+	sJa[it][n] = g.j2d[g2] * conUa;
+	sJb[it][n] = g.j2d[g2] * conUb;
+	__syncthreads();
+	double dDaUb = 0.0, dDbUa = 0.0, dDaJUa = 0.0, dDbJUb = 0.0;
+#pragma unroll
+	for (int s = 0; s < NP; s++) {
+		dDaUb += sUb[it][s * NP + j] * t.dx[s * NP + i];
+		dDbUa += sUa[it][i * NP + s] * t.dx[s * NP + j];
+		dDaJUa += sJa[it][s * NP + j] * t.dx[s * NP + i];
+		dDbJUb += sJb[it][i * NP + s] * t.dx[s * NP + j];
+	}
+	dDaUb *= g.inv_da[e];
+	dDbUa *= g.inv_db[e];
+	dDaJUa *= g.inv_da[e];
+	dDbJUb *= g.inv_db[e];
+	const double dInvJacobian2D = 1.0 / g.j2d[g2];
+	if (active) {
+		const size_t o = ((size_t)e * 3 * L + k) * NN + n;
+		field[o + (size_t)L * NN] = (dDaJUa + dDbJUb) * dInvJacobian2D;
+		field[o] = (dDaUb - dDbUa) * dInvJacobian2D;
+	}
 }
 
 #endif

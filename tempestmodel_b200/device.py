@@ -161,6 +161,11 @@ class DeviceContext:
         patch from the node coordinates already on the device."""
         self._ck(self.lib.tb200_evaluate_geometry_cs(self._h, patch, radius, omega))
 
+    def compute_output_fields(self, inst):
+        """Temperature, relative vorticity and divergence of an instance on levels,
+        kept on the device for interpolate()."""
+        self._ck(self.lib.tb200_compute_output_fields(self._h, inst))
+
     def interpolate(self, inst, data_type, only_location, patch, elem_a, elem_b, ca, cb,
                     alpha, beta, nout, vop_node=None, vop_redge=None, primitive=True):
         """Grid::ReduceInterpolate on the device (tb200_output.cuh).  vop_*: (dense
@@ -171,6 +176,8 @@ class DeviceContext:
         ca, cb, alpha, beta = _f64(ca), _f64(cb), _f64(alpha), _f64(beta)
         npts = len(patch)
         ncomp = self.cfg.ntracers if data_type == _lib.DATA_TRACERS else self.cfg.ncomp
+        if data_type in (_lib.DATA_TEMPERATURE, _lib.DATA_VORTICITY, _lib.DATA_DIVERGENCE):
+            ncomp = 1
         out = np.zeros((ncomp, nout, npts))
         keep = []
 

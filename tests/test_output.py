@@ -109,3 +109,32 @@ def test_interpolate_identity_operator_returns_the_levels(library):
     for c in (0, 2, 4):
         assert np.abs(out[c, :, 0] - ref[c]).max() <= 1e-13 * np.abs(ref[c]).max(), c
     ctx.close()
+
+
+def test_interpolate_derived_fields(emu_library):
+    """Relative vorticity, divergence (GridPatchCSGLL::ComputeCurlAndDiv) and
+    temperature (GridPatch::ComputeTemperature) computed on the device and
+    interpolated, against the reference's ComputeVorticityDivergence /
+    ComputeTemperature + ReduceInterpolate.  Vorticity and divergence are
+    differences of u-sized terms: held to 1e-11 of the field.  Emulation backend
+    (written after the GPU budget of the round was spent)."""
+    from tempestmodel_b200._lib import DATA_DIVERGENCE, DATA_TEMPERATURE, DATA_VORTICITY
+    d = cases.load_case("jwtr_ne2_l6_interp")
+    ctx = dumpctx.context_from_dump(d, library=emu_library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    alpha, beta, ipatch, ea, eb, ca, cb = locate(d, "raw")
+    nout = len(d["raw.reta"])
+    vn, ve = vop(d, "raw", "vop_node"), vop(d, "raw", "vop_redge")
+    with pytest.raises(Exception, match="output fields not computed"):
+        ctx.interpolate(0, DATA_VORTICITY, -1, ipatch, ea, eb, ca, cb, alpha, beta, nout,
+                        vop_node=vn, vop_redge=ve)
+    ctx.compute_output_fields(0)
+    for kind, key, tol in ((DATA_VORTICITY, "vorticity", 1e-11),
+                           (DATA_DIVERGENCE, "divergence", 1e-11),
+                           (DATA_TEMPERATURE, "temperature", 1e-12)):
+        got = ctx.interpolate(0, kind, -1, ipatch, ea, eb, ca, cb, alpha, beta, nout,
+                              vop_node=vn, vop_redge=ve)
+        ref = d["raw." + key]
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), key
+    ctx.close()
