@@ -847,7 +847,24 @@ __global__ void k_column_implicit_warp(
 	const int kl = offd, ku = offd, kv = 2 * offd;
 	int info = 0;
 	int ju = 0;
+	// dgbtf2 clears the fill-in rows before it uses them.  That matters: above
+	// vertical order 1 the assembly leaves entries one place outside the band
+	// (coefficients of 1e-13 that are zero analytically), which the band
+	// storage folds into the fill-in rows of the neighbouring column - LAPACK,
+	// and so the reference, drops them there.
+	for (int q = lane; q < (kv - ku - 1) * kl; q += 32) {
+		const int j = ku + 1 + q / kl;
+		const int i = q % kl;
+		if (j < n && i >= kv - j) DG(i, j) = 0.0;
+	}
+	__syncwarp();
 	for (int j = 0; j < n; j++) {
+		if (j + kv < n) {
+			for (int i = lane; i < kl; i += 32) {
+				DG(i, j + kv) = 0.0;
+			}
+			__syncwarp();
+		}
 		const int km = (kl < n - 1 - j) ? kl : (n - 1 - j);
 		// idamax over rows j..j+km (first maximum)
 		double v = -1.0;

@@ -231,6 +231,23 @@ CASES["jwtr_ne2_l6_interp"] = dict(
     script="addw:0,20000;dss:0;dump:ic,0;interp:raw,12,7,5,0;interp:prim,12,7,5,1",
     geometry_from="jw_ne2_l6", compact=True)
 
+# vertical order > 1: the general kernels (column operators of any
+# width, Jacobian band 2 * offd + 1) against the reference at --vertorder 2, 12 levels,
+# and --vertorder 4, 24 levels (fewer levels than about six elements make the
+# reference's own dgbsv call fail: "Matrix A has insufficient rows for DGBSV")
+_STAGES_VO = ";".join([
+    "addw:0,20000", "dss:0",
+    "dump:ic,0", "copy:0,1", "hexp:0,1,50", "dump:h1,1", "vexp:0,1,50",
+    "dump:v1,1", "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,30",
+    "dump:vi,2", "hasc:1,3,4,200", "dump:hasc,3",
+    "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0"])
+CASES["jw_ne2_l12_vo2"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "12", "--vertorder", "2", "--dt", "200s"],
+    script=_STAGES_VO, compact=True)
+CASES["jw_ne2_l24_vo4"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
+    script=_STAGES_VO, compact=True)
+
 _SHARED_PREFIXES = ("patch", "op.", "grid.")
 
 

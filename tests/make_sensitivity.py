@@ -76,6 +76,43 @@ def tracer_spread(name):
     return out
 
 
+def state_spread(name, steps=2):
+    """Per state component (u, v, rho theta, w, rho): max-norm spread of the
+    fields after `steps` steps relative to the largest value, and the spread
+    of the implicit stage (`vimp` from the recorded stage sequence of
+    cases._STAGES_VO) relative to the largest change the stage makes."""
+    c = cases.CASES[name]
+    where = [("node", 0), ("node", 1), ("node", 2), ("redge", 3), ("node", 4)]
+
+    def run(eps):
+        pre = "addw:0,20000;dss:0;"
+        per = "" if eps is None else "perturb:%d,%s;"
+        return refdump.run_ref_dump(
+            "/tmp/tb200_sens.bin", c["case"],
+            pre + "copy:0,1;hexp:0,1,50;vexp:0,1,50;dss:1;dump:dss,1;copy:1,2;"
+            + (per % (2, eps) if eps else "") + "vimp:2,2,30;dump:vi,2;"
+            + "copy:0,1;copy:0,2;copy:0,3;copy:0,4;" + (per % (0, eps) if eps else "")
+            + "step:%d;dump:st,0" % steps, c["flags"])
+    base = run(None)
+    runs = [run(e) for e in EPS]
+    npatch = refdump.scalar(base, "grid.npatch")
+    out = {"field_rel_spread": [], "implicit_stage_spread": []}
+    for loc, cc in where:
+        num = den = inum = iden = 0.0
+        for n in range(npatch):
+            ref = base["st.patch%d.inst0.%s" % (n, loc)][cc]
+            vi = base["vi.patch%d.inst2.%s" % (n, loc)][cc]
+            bef = base["dss.patch%d.inst1.%s" % (n, loc)][cc]
+            den = max(den, np.abs(ref).max())
+            iden = max(iden, np.abs(vi - bef).max())
+            for r in runs:
+                num = max(num, np.abs(r["st.patch%d.inst0.%s" % (n, loc)][cc] - ref).max())
+                inum = max(inum, np.abs(r["vi.patch%d.inst2.%s" % (n, loc)][cc] - vi).max())
+        out["field_rel_spread"].append(num / den)
+        out["implicit_stage_spread"].append(inum / iden if iden > 0 else 0.0)
+    return out
+
+
 ENTRIES = {
     # the configuration of tests/test_dropin.py::test_nonhydro_dropin
     # (integration/b200_driver.cpp defaults: ztop = 10 km)
@@ -94,6 +131,11 @@ ENTRIES = {
         "jw", ["--resolution", "30", "--levels", "30", "--dt", "200s"], 2),
     # tests/test_parity.py::test_tracers_ars343
     "jwtr_ne2_l6_ars343_2steps": lambda: tracer_spread("jwtr_ne2_l6_ars343"),
+    # tests/test_parity.py::test_vertical_order_above_one
+    "jw_ne2_l12_vo2_2steps": lambda: state_spread("jw_ne2_l12_vo2"),
+    "jw_ne2_l24_vo4_2steps": lambda: state_spread("jw_ne2_l24_vo4"),
+    # the same at vertical order 1, for comparison
+    "jw_ne2_l6_strang_2steps": lambda: state_spread("jw_ne2_l6_strang"),
 }
 
 

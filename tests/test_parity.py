@@ -11,6 +11,8 @@ of the component.  The implicit column solve goes through a different LAPACK
 build than the reference's (OpenBLAS, FMA kernels), so it is held to 1e-10 of
 the largest change of the component; multi-step states to 1e-10 of the field.
 """
+import json
+import os
 import numpy as np
 import pytest
 
@@ -709,4 +711,56 @@ def test_explicit_vertical(library):
     ctx.step("strang", False, False, 1.0)
     ctx.check_errors()
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["jw_ne2_l12_vo2", "jw_ne2_l24_vo4"])
+def test_vertical_order_above_one(library, name):
+    """--vertorder 2 and 4: column operators wider than three
+    entries, Jacobian band of half-width 2 vo + ..., upwind penalties across the
+    vertical elements - the general kernels (the column-constant path is order 1
+    only and must decline), stage by stage and over two Strang steps against the
+    reference."""
+    if name == "jw_ne2_l24_vo4" and "emu" not in os.path.basename(library):
+        # order 2 passed on the B200 (profiles/r2_pytest_gpu_final.txt); the
+        # order-4 case was added after the round's GPU minutes were spent
+        pytest.skip("order 4 is pinned on the emulation build only so far")
+    d = cases.load_case(name)
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert not ctx.fast_path()[0]
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.v_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    # The implicit stage starts from the reference's own record, and it and the
+    # final state are bounded by 10 x the spread the reference shows against
+    # itself under 1-ulp perturbations of its input (tests/make_sensitivity.py
+    # -> sensitivity.json): above order 1 the column solve amplifies last-bit
+    # differences 3e5 (order 2) to 1e8 (order 4) times.
+    with open(os.path.join(cases.GOLDEN, "sensitivity.json")) as f:
+        sp = json.load(f)[name + "_2steps"]
+
+    def bounded(errs, spread, floor):
+        for (loc, c), v in errs.items():
+            assert v <= max(floor, 10.0 * spread[c]), (loc, c, v, spread[c])
+    dumpctx.upload_tag(ctx, d, "dss", instances=[1])
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    bounded(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3], skip_poles=True),
+            sp["implicit_stage_spread"], TOL_IMPLICIT)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    bounded(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]),
+            sp["field_rel_spread"], TOL_STATE)
     ctx.close()
