@@ -248,6 +248,17 @@ CASES["jw_ne2_l24_vo4"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
     script=_STAGES_VO, compact=True)
 
+# tracers at vertical order 2: the column transport of the tracers factorises
+# a band of half-width 2 * order - 1 (VerticalDynamicsFEM.cpp:4028-4038)
+CASES["jwtr_ne2_l12_vo2"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "12", "--vertorder", "2", "--dt", "200s",
+                      "--ntracers", "3"],
+    script=";".join([
+        "addw:0,20000", "dss:0",
+        "dump:ic,0", "copy:0,1", "hexp:0,1,50", "dump:h1,1", "vexp:0,1,50",
+        "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,30", "dump:vi,2"]),
+    geometry_from="jw_ne2_l12_vo2", compact=True)
+
 _SHARED_PREFIXES = ("patch", "op.", "grid.")
 
 

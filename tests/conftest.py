@@ -39,3 +39,13 @@ def cuda_library():
     assert os.path.exists(PRODUCT_LIBRARY), "libtempest_b200.so missing: run __graft_entry__.build()"
     assert _cuda_available(), "no CUDA device"
     return PRODUCT_LIBRARY
+
+
+def added_after_the_gpu_budget(library):
+    """Cases added after the round's GPU minutes were spent: they are pinned on
+    the emulation build of the same kernel sources, and their product-library
+    variant is skipped (not silently passed) until it has run on hardware once -
+    TB200_RUN_UNVERIFIED=1 runs it."""
+    if "emu" not in os.path.basename(library) and not os.environ.get("TB200_RUN_UNVERIFIED"):
+        pytest.skip("added after the GPU budget of the round was spent: emulation build only so far "
+                    "(TB200_RUN_UNVERIFIED=1 runs it)")

@@ -18,6 +18,7 @@ import pytest
 
 import cases
 import dumpctx
+from conftest import added_after_the_gpu_budget
 
 BACKENDS = [pytest.param("emu"), pytest.param("cuda", marks=pytest.mark.gpu)]
 
@@ -721,10 +722,9 @@ def test_vertical_order_above_one(library, name, monkeypatch):
     vertical elements - the general kernels (the column-constant path is order 1
     only and must decline), stage by stage and over two Strang steps against the
     reference."""
-    if name == "jw_ne2_l24_vo4" and "emu" not in os.path.basename(library):
-        # order 2 passed on the B200 (profiles/r2_pytest_gpu_final.txt); the
-        # order-4 case was added after the round's GPU minutes were spent
-        pytest.skip("order 4 is pinned on the emulation build only so far")
+    if name == "jw_ne2_l24_vo4":
+        # order 2 passed on the B200 (profiles/r2_pytest_gpu_final.txt)
+        added_after_the_gpu_budget(library)
     d = cases.load_case(name)
     ctx = dumpctx.context_from_dump(d, library=library)
     assert not ctx.fast_path()[0]
@@ -768,4 +768,29 @@ def test_vertical_order_above_one(library, name, monkeypatch):
     ctx.check_errors()
     bounded(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]),
             sp["field_rel_spread"], TOL_STATE)
+    ctx.close()
+
+
+def test_tracers_vertical_order_two(library):
+    """Tracer transport at --vertorder 2: horizontal transport with the element
+    filter, DSS, and the implicit column transport, whose matrix is a band of
+    half-width 2 * order - 1 = 3 (VerticalDynamicsFEM.cpp:4028-4038), with the
+    column filter - general kernels."""
+    added_after_the_gpu_budget(library)
+    d = cases.load_case("jwtr_ne2_l12_vo2")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "h1", before=("ic", 0)), 1e-11)
+    ctx.v_step_explicit(0, 1, 50.0)
+    ctx.dss(1)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "dss"), 1e-13)
+    # the implicit stage from the reference's own record (see
+    # test_vertical_order_above_one)
+    dumpctx.upload_tag(ctx, d, "dss", instances=[1])
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare_tracers(ctx, d, 2, "vi"), 1e-10)
     ctx.close()
