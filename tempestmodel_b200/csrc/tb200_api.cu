@@ -2122,6 +2122,32 @@ static int explicit_vertical_columns(tb200_ctx * ctx, int in, int out, double dt
 			(const double *)ctx->inst[in], ctx->inst[out]);
 		TB_KERNEL_CHECK(ctx);
 	}
+	if (lay.ntr == 0) return 0;
+	// UpdateColumnTracers in its explicit branches (:802-810, 4048-4171): the column
+	// flux of every tracer with xi-dot of the initial state, out -= dt * F; the
+	// column filter belongs to StepImplicit (:1637), which does nothing here
+	TracerColumnArgs ta;
+	memset(&ta, 0, sizeof(ta));
+	ta.ws = ctx->d_ws;
+	ta.ws_stride = ctx->ws_cols;
+	ta.dt = dt;
+	ta.fe_nodes = ctx->cfg.vertical_order;
+	ta.kl = 2 * ctx->cfg.vertical_order - 1;
+	ta.info = ctx->d_info;
+	ta.fully_explicit = 1;
+	if (tb_tracer_ws_entries(lay.nlev, ta.kl) > tb_column_ws_entries(lay.nlev, ctx->offd)) {
+		TB_FAIL(ctx, "column workspace too small for the tracer update");
+	}
+	for (long long c0 = 0; c0 < total; c0 += ctx->ws_cols) {
+		ta.col0 = (int)c0;
+		ta.ncols = (int)std::min<long long>(ctx->ws_cols, total - c0);
+		auto kfn = k_column_tracers;
+		TB_LAUNCH_FLAT(kfn, dim3((ta.ncols + 63) / 64), dim3(64), 0, ctx->stream,
+			lay, ctx->geom, ctx->ops, ta,
+			(const double *)ctx->inst[in], (const double *)ctx->inst[in],
+			(const double *)ctx->inst[in], ctx->inst[out]);
+		TB_KERNEL_CHECK(ctx);
+	}
 	return 0;
 }
 
@@ -2135,7 +2161,6 @@ extern "C" int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 	if (ctx->cfg.fully_explicit) {
 		// --explicitvertical (VerticalDynamicsFEM.cpp:748-793): rho theta, w and rho are
 		// advanced with the column tendencies as well; general kernels
-		if (ctx->lay.ntr > 0) TB_FAIL(ctx, "--explicitvertical with tracers is not supported");
 		if (explicit_vertical_columns(ctx, in, out, dt)) return 1;
 	}
 	return nh_launch(ctx, in, out, dt, false, true, stage_base_out());
@@ -2338,6 +2363,7 @@ static int column_tracers(tb200_ctx * ctx, int in, int out, double dt) {
 	ta.kl = 2 * ctx->cfg.vertical_order - 1;
 	ta.w_old = ctx->d_wold;
 	ta.info = ctx->d_info;
+	ta.fully_explicit = 0;
 	if (tb_tracer_ws_entries(lay.nlev, ta.kl) > tb_column_ws_entries(lay.nlev, ctx->offd)) {
 		TB_FAIL(ctx, "column workspace too small for the tracer update");
 	}

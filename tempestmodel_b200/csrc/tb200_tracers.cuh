@@ -34,6 +34,10 @@ struct TracerColumnArgs {
 	// colc [e][15][NN], lev [L+1][TBF_LW]; 0 = read the arrays of DevGeom
 	const double * colc;
 	const double * lev;
+	// --explicitvertical (VerticalDynamicsFEM.cpp:802-810): every element-local
+	// node is a column (col_node = 0), xi-dot from the initial w, no matrix
+	// beyond the identity / dt, no jump terms, no duplicates to copy to
+	int fully_explicit;
 };
 
 // entries of the column constants / level rows this kernel reads (tb200_fast.cuh)
@@ -65,7 +69,8 @@ __global__ void k_column_tracers(
 	const int kl = ta.kl;
 	const int ldab = 3 * kl + 1;
 
-	const int node = ta.col_node[ta.col0 + tcol];
+	const bool expl = (ta.fully_explicit != 0);
+	const int node = expl ? (ta.col0 + tcol) : ta.col_node[ta.col0 + tcol];
 	const long long e = node / NN;
 	const int nd = node % NN;
 	const size_t ebase = (size_t)e * lay.nrows * NN;
@@ -91,7 +96,8 @@ __global__ void k_column_tracers(
 	const double * inU = st_in + ebase + (size_t)lay.rowoff[UIx] * NN + nd;
 	const double * inV = st_in + ebase + (size_t)lay.rowoff[VIx] * NN + nd;
 	const double * wNew = st_out + ebase + (size_t)lay.rowoff[WIx] * NN + nd;
-	const double * wOld = ta.w_old + g3e;
+	// (explicit: the initial w throughout, :4048-4061)
+	const double * wOld = expl ? (st_in + ebase + (size_t)lay.rowoff[WIx] * NN + nd) : (ta.w_old + g3e);
 
 	// metric of the column: Jacobian on level k / interface m, xi-row of the
 	// contravariant metric on interface m
@@ -136,7 +142,7 @@ __global__ void k_column_tracers(
 
 	const int vo = ta.fe_nodes;
 	const int nfe = L / vo;
-	const int * dups = ta.col_dups + (size_t)(ta.col0 + tcol) * 3;
+	const int * dups = expl ? 0 : (ta.col_dups + (size_t)(ta.col0 + tcol) * 3);
 
 	for (int c = 0; c < lay.ntr; c++) {
 		// ---- matrix (:3953-4016) ---------------------------------------------------
@@ -145,7 +151,8 @@ __global__ void k_column_tracers(
 		}
 		// TracerMatFIx(n, k): column n, row k -> band row 2 kl + k - n
 #define TB_TMAT(n, k) AB(2 * kl + (k) - (n), (n))
-		for (int k = 0; k < L; k++) {
+		// (only with implicit advection, :3908)
+		for (int k = 0; k < (expl ? 0 : L); k++) {
 			const double jn = jac_at(k);
 			for (int m = opDiffE2N.begin[k]; m < opDiffE2N.end[k]; m++) {
 				const double je = jace_at(m);
@@ -159,7 +166,7 @@ __global__ void k_column_tracers(
 				}
 			}
 		}
-		for (int a = 1; a < nfe; a++) {
+		for (int a = 1; a < (expl ? 0 : nfe); a++) {
 			const int kLeftBegin = (a - 1) * vo, kLeftEnd = a * vo;
 			const int kRightBegin = a * vo, kRightEnd = (a + 1) * vo;
 			const double dWeight = fabs(xdi(kLeftEnd));
@@ -208,8 +215,8 @@ __global__ void k_column_tracers(
 			}
 			F(k) -= aux;
 		}
-		// jump terms from the change of w (:4178-4228)
-		for (int a = 1; a < nfe; a++) {
+		// jump terms from the change of w (:4178-4228; implicit advection only)
+		for (int a = 1; a < (expl ? 0 : nfe); a++) {
 			const int kLeftBegin = (a - 1) * vo, kLeftEnd = a * vo;
 			const int kRightBegin = a * vo, kRightEnd = (a + 1) * vo;
 			const double xd = xdi(kLeftEnd);
@@ -250,7 +257,7 @@ __global__ void k_column_tracers(
 		for (int k = 0; k < L; k++) {
 			const double v = own[(size_t)k * NN] - F(k);
 			own[(size_t)k * NN] = v;
-			for (int q = 0; q < 3; q++) {
+			for (int q = 0; q < (expl ? 0 : 3); q++) {
 				const int tgt = dups[q];
 				if (tgt < 0) continue;
 				tr_out[(size_t)(tgt / NN) * lay.nrows * NN + (tgt % NN)

@@ -223,6 +223,17 @@ CASES["jw_ne2_l6_explicitv"] = dict(
         "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0"]),
     geometry_from="jw_ne2_l6", compact=True)
 
+# the same with tracers: UpdateColumnTracers in its explicit branches
+# (VerticalDynamicsFEM.cpp:802-810, 4048-4171)
+CASES["jwtr_ne2_l6_explicitv"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "1s", "--explicitvertical",
+                      "--ntracers", "3"],
+    script=";".join([
+        "addw:0,20000", "dss:0", "dump:ic,0", "copy:0,1", "hexp:0,1,1", "dump:h1,1",
+        "vexp:0,1,1", "dump:v1,1",
+        "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0"]),
+    geometry_from="jw_ne2_l6", compact=True)
+
 # output-side interpolation: Grid::ReduceInterpolate of the state and
 # tracers to a latitude-longitude grid and uniform REta levels, with and without
 # the conversion to primitive variables

@@ -794,3 +794,33 @@ def test_tracers_vertical_order_two(library):
     ctx.check_errors()
     assert_below(dumpctx.compare_tracers(ctx, d, 2, "vi"), 1e-10)
     ctx.close()
+
+
+def test_explicit_vertical_tracers(library):
+    """--explicitvertical with tracers: UpdateColumnTracers in its explicit branches
+    (VerticalDynamicsFEM.cpp:802-810, 4048-4171) - the column flux of every tracer
+    with xi-dot of the initial state, no matrix beyond the identity, no column
+    filter (it belongs to the skipped StepImplicit, :1637).  The vertical stage
+    against the reference relative to the change it makes, then two Strang
+    steps."""
+    added_after_the_gpu_budget(library)
+    d = cases.load_case("jwtr_ne2_l6_explicitv")
+    ctx = dumpctx.context_from_dump(d, library=library, fully_explicit=1)
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 1.0)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "h1", before=("ic", 0)), 1e-11)
+    # the vertical stage alone, from the reference's record of the horizontal one
+    dumpctx.upload_tag(ctx, d, "h1", instances=[1])
+    ctx.v_step_explicit(0, 1, 1.0)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "v1", before=("h1", 1)), 1e-11)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1], []), TOL_STAGE)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 1.0)
+    ctx.step("strang", False, False, 1.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    assert_below(dumpctx.compare_tracers(ctx, d, 0, "st"), 1e-12)
+    ctx.close()
