@@ -411,6 +411,18 @@ int tb200_step(tb200_ctx * ctx, int scheme, int first_step, int last_step, doubl
  * uploaded, tb200_h_step_after_subcycle applies
  * HorizontalDynamicsFEM::ApplyRayleighFriction (:2418-2536) after the
  * hyperdiffusion (APPLY_RAYLEIGH_WITH_HYPERVIS, Defines.h:74). */
+/* GridPatch::GetReferenceState(Node / REdge) of a local patch alone (zero until
+ * uploaded, as in a test case without TestCase::HasReferenceState). */
+int tb200_upload_reference_state(tb200_ctx * ctx, int patch_index,
+                                 const double * ref_node, const double * ref_redge);
+/* Uniform diffusion (Grid::HasUniformDiffusion, Grid.cpp:399-415, coefficients from
+ * TestCase::GetUniformDiffusionCoeffs): second-order diffusion of the state minus the
+ * reference state - horizontally at the end of HorizontalDynamicsFEM::StepExplicit
+ * (:1817-1858: u, v; rho theta; w), in the column in VerticalDynamicsFEM::StepExplicit
+ * (u, v, :1058-1106) and BuildF (rho theta, w, :2594-2636; not in the Jacobian).
+ * General kernels; with tracers the step fails as the reference does (:3914-3917).
+ * Both zero = off (the default). */
+int tb200_set_uniform_diffusion(tb200_ctx * ctx, double scalar_coeff, double vector_coeff);
 int tb200_upload_rayleigh(tb200_ctx * ctx, int patch_index,
                           const double * strength_node, const double * strength_redge,
                           const double * ref_node, const double * ref_redge);

@@ -238,6 +238,15 @@ void B200Bridge::Initialize() {
 				&(pPatch->GetReferenceState(DataLocation_REdge)[0][0][0][0])));
 		}
 
+		// Uniform diffusion acts on the state minus the reference state
+		// (Grid::HasUniformDiffusion, Grid.h:872-874)
+		if (pGrid->HasUniformDiffusion()) {
+			Check(tb200_upload_reference_state(
+				m_pCtx, ixPatch,
+				&(pPatch->GetReferenceState(DataLocation_Node)[0][0][0][0]),
+				&(pPatch->GetReferenceState(DataLocation_REdge)[0][0][0][0])));
+		}
+
 		// On-the-fly terrain-following metric: m_dXNode / m_dYNode
 		// (GridPatchCSGLL.cpp:205-213) and the topography derivatives
 		if (cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
@@ -330,6 +339,12 @@ void B200Bridge::Initialize() {
 			m_pCtx, &(pGrid->GetREtaLevels()[0]), &(pGrid->GetREtaInterfaces()[0])));
 	}
 	Check(tb200_build_connectivity(m_pCtx));
+	if (pGrid->HasUniformDiffusion()) {
+		Check(tb200_set_uniform_diffusion(
+			m_pCtx,
+			pGrid->GetScalarUniformDiffusionCoeff(),
+			pGrid->GetVectorUniformDiffusionCoeff()));
+	}
 
 	// Pin the state containers (one contiguous block each, DataContainer.cpp:77-147):
 	// bus copies then run asynchronously at full rate

@@ -23,6 +23,33 @@
 #include "nonhydro_xz/ThermalBubbleCartesianTest.cpp"
 #undef main
 
+///	<summary>
+///		The reference's thermal bubble with uniform diffusion switched on
+///		(--diffs / --diffv; its own coefficients are zero,
+///		ThermalBubbleCartesianTest.cpp:144-150 - the other Cartesian cases of
+///		test/nonhydro_xz run with 75 or 300 m^2/s).
+///	</summary>
+class ThermalBubbleDiffusionTest : public ThermalBubbleCartesianTest {
+public:
+	ThermalBubbleDiffusionTest(double dDiffS, double dDiffV) :
+		ThermalBubbleCartesianTest(300.0, 0.5, 250.0, 500.0, 350.0, 3.14159265),
+		m_dDiffS(dDiffS),
+		m_dDiffV(dDiffV)
+	{ }
+
+	virtual void GetUniformDiffusionCoeffs(
+		double & dScalarUniformDiffusionCoeff,
+		double & dVectorUniformDiffusionCoeff
+	) const {
+		dScalarUniformDiffusionCoeff = m_dDiffS;
+		dVectorUniformDiffusionCoeff = m_dDiffV;
+	}
+
+private:
+	double m_dDiffS;
+	double m_dDiffV;
+};
+
 #include "TempestB200.h"
 #include "HeldSuarezPhysics.h"
 #include "GridCSGLL.h"
@@ -41,6 +68,8 @@ try {
 	std::string strPert;
 	int nEager;
 	int nHeldSuarez;
+	double dDiffS;
+	double dDiffV;
 
 	BeginTempestCommandLine("B200Driver");
 		SetDefaultResolution(8);
@@ -59,6 +88,8 @@ try {
 		CommandLineString(strPert, "pert", "Exp");
 		CommandLineInt(nEager, "b200eager", 0);
 		CommandLineInt(nHeldSuarez, "heldsuarez", 0);
+		CommandLineDouble(dDiffS, "diffs", 0.0);
+		CommandLineDouble(dDiffV, "diffv", 0.0);
 
 		ParseCommandLine(argc, argv);
 	EndTempestCommandLine(argv)
@@ -135,8 +166,7 @@ try {
 	ThermalBubbleCartesianTest * pBubble = NULL;
 	if (strCase == "bubble") {
 		// _TempestSetupCartesianModel (TempestInitialize.h:590-706), x-z slice
-		pBubble = new ThermalBubbleCartesianTest(
-			300.0, 0.5, 250.0, 500.0, 350.0, 3.14159265);
+		pBubble = new ThermalBubbleDiffusionTest(dDiffS, dDiffV);
 		GridCartesianGLL * pGrid = new GridCartesianGLL(model);
 		pGrid->DefineParameters();
 		pGrid->SetParameters(

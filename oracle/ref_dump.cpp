@@ -81,13 +81,27 @@ class JWTracerTest : public BaroclinicWaveJWTest {
 public:
 	JWTracerTest(
 		double dAlpha, double dZtop, PerturbationType ePert, int nTracers,
-		double dRayleigh
+		double dRayleigh, double dDiffS = 0.0, double dDiffV = 0.0
 	) :
 		BaroclinicWaveJWTest(dAlpha, dZtop, ePert),
 		m_nTracers(nTracers),
 		m_dRayleigh(dRayleigh),
-		m_dSpongeTop(dZtop)
+		m_dSpongeTop(dZtop),
+		m_dDiffS(dDiffS),
+		m_dDiffV(dDiffV)
 	{ }
+
+	///	<summary>
+	///		Test data: uniform diffusion coefficients (TestCase.h:78-84; the
+	///		Cartesian cases of test/nonhydro_xz set them to 75 or 300 m^2/s).
+	///	</summary>
+	virtual void GetUniformDiffusionCoeffs(
+		double & dScalarUniformDiffusionCoeff,
+		double & dVectorUniformDiffusionCoeff
+	) const {
+		dScalarUniformDiffusionCoeff = m_dDiffS;
+		dVectorUniformDiffusionCoeff = m_dDiffV;
+	}
 
 	///	<summary>
 	///		Test data: a sponge layer in the upper 40 % of the domain whose
@@ -142,6 +156,34 @@ private:
 	int m_nTracers;
 	double m_dRayleigh;
 	double m_dSpongeTop;
+	double m_dDiffS;
+	double m_dDiffV;
+};
+
+///	<summary>
+///		Test data: the reference's thermal bubble with uniform diffusion
+///		switched on (its own coefficients are zero,
+///		ThermalBubbleCartesianTest.cpp:144-150).
+///	</summary>
+class BubbleDiffusionTest : public ThermalBubbleCartesianTest {
+public:
+	BubbleDiffusionTest(double dDiffS, double dDiffV) :
+		ThermalBubbleCartesianTest(300.0, 0.5, 250.0, 500.0, 350.0, 3.14159265),
+		m_dDiffS(dDiffS),
+		m_dDiffV(dDiffV)
+	{ }
+
+	virtual void GetUniformDiffusionCoeffs(
+		double & dScalarUniformDiffusionCoeff,
+		double & dVectorUniformDiffusionCoeff
+	) const {
+		dScalarUniformDiffusionCoeff = m_dDiffS;
+		dVectorUniformDiffusionCoeff = m_dDiffV;
+	}
+
+private:
+	double m_dDiffS;
+	double m_dDiffV;
 };
 
 ///////////////////////////////////////////////////////////////////////////////
@@ -245,6 +287,10 @@ static void DumpGeometry(Model & model, bool fArrays3D) {
 		(dynamic_cast<GridCartesianGLL*>(pGrid) != NULL) ? 1 : 0);
 	WriteScalarD("grid.ztop", pGrid->GetZtop());
 	WriteScalarD("grid.reflength", pGrid->GetReferenceLength());
+	WriteScalarD("grid.diffs",
+		pGrid->HasUniformDiffusion() ? pGrid->GetScalarUniformDiffusionCoeff() : 0.0);
+	WriteScalarD("grid.diffv",
+		pGrid->HasUniformDiffusion() ? pGrid->GetVectorUniformDiffusionCoeff() : 0.0);
 	{
 		DataArray1D<int> loc(eqn.GetComponents());
 		for (int c = 0; c < eqn.GetComponents(); c++) {
@@ -612,6 +658,8 @@ try {
 	int nTracers;
 	double dRayleigh;
 	int nNoGeometry;
+	double dDiffS;
+	double dDiffV;
 
 	BeginTempestCommandLine("RefDump");
 		SetDefaultResolution(4);
@@ -635,6 +683,8 @@ try {
 		CommandLineInt(nTracers, "ntracers", 0);
 		CommandLineDouble(dRayleigh, "rayleigh", 0.0);
 		CommandLineInt(nNoGeometry, "nogeometry", 0);
+		CommandLineDouble(dDiffS, "diffs", 0.0);
+		CommandLineDouble(dDiffV, "diffv", 0.0);
 
 		ParseCommandLine(argc, argv);
 	EndTempestCommandLine(argv)
@@ -657,7 +707,7 @@ try {
 			(strPert == "exp") ?
 				BaroclinicWaveJWTest::PerturbationType_Exp :
 				BaroclinicWaveJWTest::PerturbationType_None;
-		if ((nTracers > 0) || (dRayleigh > 0.0)) {
+		if ((nTracers > 0) || (dRayleigh > 0.0) || (dDiffS != 0.0) || (dDiffV != 0.0)) {
 			EquationSet eqn(EquationSet::PrimitiveNonhydrostaticEquations);
 			for (int c = 0; c < nTracers; c++) {
 				char szName[16];
@@ -666,15 +716,15 @@ try {
 			}
 			UserDataMeta metaUserData;
 			pModel = new Model(eqn, metaUserData);
-			pTest = new JWTracerTest(dAlpha, dZtop, ePert, nTracers, dRayleigh);
+			pTest = new JWTracerTest(
+				dAlpha, dZtop, ePert, nTracers, dRayleigh, dDiffS, dDiffV);
 		} else {
 			pModel = new Model(EquationSet::PrimitiveNonhydrostaticEquations);
 			pTest = new BaroclinicWaveJWTest(dAlpha, dZtop, ePert);
 		}
 	} else if (strCase == "bubble") {
 		pModel = new Model(EquationSet::PrimitiveNonhydrostaticEquations);
-		pTest = new ThermalBubbleCartesianTest(
-			300.0, 0.5, 250.0, 500.0, 350.0, 3.14159265);
+		pTest = new BubbleDiffusionTest(dDiffS, dDiffV);
 	} else {
 		_EXCEPTIONT("--case must be sw2, jw or bubble");
 	}

@@ -139,6 +139,8 @@ _SIGNATURES = {
     "tb200_upload_element_area": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "tb200_upload_rayleigh": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
+    "tb200_upload_reference_state": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "tb200_set_uniform_diffusion": (c_int, [c_void_p, c_double, c_double]),
     "tb200_upload_state_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tb200_download_state_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
                                            c_void_p, c_int]),

@@ -855,6 +855,47 @@ extern "C" int tb200_upload_state(
 // strength on levels / interfaces [W_A][W_B][L(+1)] and the reference state in
 // the layout of a state instance.  Optional; StepAfterSubCycle applies the
 // friction once any patch has a non-zero strength (Grid::HasRayleighFriction).
+// zero reference state until one is uploaded (a test case without one,
+// TestCase::HasReferenceState, leaves the reference's arrays zero as well)
+static int refstate_alloc(tb200_ctx * ctx) {
+	if (ctx->d_refstate != 0) return 0;
+	const DevLayout & lay = ctx->lay;
+	const size_t n = (size_t)lay.nelem * lay.nrows * lay.nn;
+	if (dalloc(ctx, &ctx->d_refstate, n)) return 1;
+	TB_CHECK(ctx, cudaMemset(ctx->d_refstate, 0, n * sizeof(double)));
+	return 0;
+}
+
+// GridPatch::GetReferenceState(Node / REdge) of a local patch, in the state layout
+extern "C" int tb200_upload_reference_state(
+	tb200_ctx * ctx, int patch_index, const double * ref_node, const double * ref_redge
+) {
+	if (!ctx->committed) TB_FAIL(ctx, "commit the layout first");
+	PatchInfo * pi = find_patch(ctx, patch_index);
+	if (pi == 0 || pi->elem0 < 0) TB_FAIL(ctx, "not a local patch");
+	if (refstate_alloc(ctx)) return 1;
+	// through the state path into a scratch "instance"
+	ctx->inst.push_back(ctx->d_refstate);
+	const int slot = (int)ctx->inst.size() - 1;
+	const int rc = tb200_upload_state(ctx, patch_index, slot, ref_node, ref_redge, 0);
+	ctx->inst.pop_back();
+	return rc;
+}
+
+// Grid::HasUniformDiffusion with TestCase::GetUniformDiffusionCoeffs (Grid.cpp:399-415)
+extern "C" int tb200_set_uniform_diffusion(
+	tb200_ctx * ctx, double scalar_coeff, double vector_coeff
+) {
+	ctx->uniform_s = scalar_coeff;
+	ctx->uniform_v = vector_coeff;
+	ctx->fast_state = 0;        // the column-constant path declines (fast_prepare)
+	return 0;
+}
+
+static inline bool uniform_on(const tb200_ctx * ctx) {
+	return ctx->uniform_s != 0.0 || ctx->uniform_v != 0.0;
+}
+
 extern "C" int tb200_upload_rayleigh(
 	tb200_ctx * ctx, int patch_index,
 	const double * strength_node, const double * strength_redge,
@@ -869,19 +910,12 @@ extern "C" int tb200_upload_rayleigh(
 	if (ctx->d_ray_node == 0) {
 		if (dalloc(ctx, &ctx->d_ray_node, (size_t)lay.nelem * L * nn)) return 1;
 		if (dalloc(ctx, &ctx->d_ray_redge, (size_t)lay.nelem * (L + 1) * nn)) return 1;
-		if (dalloc(ctx, &ctx->d_refstate, (size_t)lay.nelem * lay.nrows * nn)) return 1;
 		TB_CHECK(ctx, cudaMemset(ctx->d_ray_node, 0, (size_t)lay.nelem * L * nn * sizeof(double)));
 		TB_CHECK(ctx, cudaMemset(ctx->d_ray_redge, 0, (size_t)lay.nelem * (L + 1) * nn * sizeof(double)));
-		TB_CHECK(ctx, cudaMemset(ctx->d_refstate, 0, (size_t)lay.nelem * lay.nrows * nn * sizeof(double)));
 	}
 	if (upload_geom_array(ctx, *pi, strength_node, L, 1, ctx->d_ray_node, 0, 0)) return 1;
 	if (upload_geom_array(ctx, *pi, strength_redge, L + 1, 1, ctx->d_ray_redge, 0, 0)) return 1;
-	// the reference state goes through the state path into a scratch "instance"
-	ctx->inst.push_back(ctx->d_refstate);
-	const int slot = (int)ctx->inst.size() - 1;
-	const int rc = tb200_upload_state(ctx, patch_index, slot, ref_node, ref_redge, 0);
-	ctx->inst.pop_back();
-	if (rc) return 1;
+	if (tb200_upload_reference_state(ctx, patch_index, ref_node, ref_redge)) return 1;
 	ctx->has_rayleigh = true;
 	return 0;
 }
@@ -1667,6 +1701,7 @@ static int fast_prepare(tb200_ctx * ctx) {
 		ctx->fast_reason = "not a nonhydrostatic np=4 configuration"; return 0;
 	}
 	if (ctx->cfg.vertical_order != 1) { ctx->fast_reason = "vertical order > 1"; return 0; }
+	if (uniform_on(ctx)) { ctx->fast_reason = "uniform diffusion (general kernels)"; return 0; }
 	if ((int)ctx->reta_n_h.size() != L || (int)ctx->reta_e_h.size() != L + 1) {
 		ctx->fast_reason = "vertical coordinate not set"; return 0;
 	}
@@ -2073,6 +2108,10 @@ static int check_inst2(tb200_ctx * ctx, int in, int out) {
 	return 0;
 }
 
+static int uniform_diffusion_horizontal(tb200_ctx * ctx, int in, int out, double dt);
+static int uniform_diffusion_vertical_uv(tb200_ctx * ctx, int in, int out, double dt);
+static int stale_column_update(tb200_ctx * ctx, int in);
+
 extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
 	TimingScope ts(ctx, (ctx->cfg.eqn_type == TB200_EQN_SHALLOW_WATER)
 		? "HorizontalStepShallowWater" : "HorizontalStepNonhydrostaticPrimitive");
@@ -2092,7 +2131,19 @@ extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 		if (nh_launch(ctx, in, out, dt, true, false, stage_base_out(), &filtered)) return 1;
 		if (filtered) return 0;
 	}
+	if (uniform_on(ctx) && uniform_diffusion_horizontal(ctx, in, out, dt)) return 1;
 	return tb200_filter_negative_tracers(ctx, out);
+}
+
+// uniform diffusion terms of BuildF (VerticalDynamicsFEM.cpp:2594-2636)
+static int column_uniform_args(tb200_ctx * ctx, ColumnArgs & ca) {
+	if (!uniform_on(ctx)) return 0;
+	if (refstate_alloc(ctx)) return 1;
+	const double ztop = ctx->cfg.ztop;
+	ca.ref = ctx->d_refstate;
+	ca.uni_s = ctx->uniform_s / (ztop * ztop);
+	ca.uni_v = ctx->uniform_v / (ztop * ztop);
+	return 0;
 }
 
 // Fully explicit vertical step: BuildF of every element-local column of `in`
@@ -2112,6 +2163,7 @@ static int explicit_vertical_columns(tb200_ctx * ctx, int in, int out, double dt
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
 	ca.assemble_only = 3;
+	if (column_uniform_args(ctx, ca)) return 1;
 	const long long total = lay.nelem * (long long)lay.nn;
 	for (long long c0 = 0; c0 < total; c0 += ctx->ws_cols) {
 		ca.col0 = (int)c0;
@@ -2163,7 +2215,9 @@ extern "C" int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 		// advanced with the column tendencies as well; general kernels
 		if (explicit_vertical_columns(ctx, in, out, dt)) return 1;
 	}
-	return nh_launch(ctx, in, out, dt, false, true, stage_base_out());
+	if (nh_launch(ctx, in, out, dt, false, true, stage_base_out())) return 1;
+	if (uniform_on(ctx)) return uniform_diffusion_vertical_uv(ctx, in, out, dt);
+	return 0;
 }
 
 extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
@@ -2172,7 +2226,7 @@ extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double d
 		return tb200_h_step_explicit(ctx, in, out, dt);
 	}
 	if (in == out) TB_FAIL(ctx, "HorizontalDynamics Step must have iDataInitial != iDataUpdate");
-	if ((ctx->lay.ntr > 0 && !stage_fast_ok(ctx)) || ctx->cfg.fully_explicit) {
+	if ((ctx->lay.ntr > 0 && !stage_fast_ok(ctx)) || ctx->cfg.fully_explicit || uniform_on(ctx)) {
 		// the tracer filter sits between the two plugins in the reference;
 		// --explicitvertical adds the column tendencies in the vertical plugin
 		if (tb200_h_step_explicit(ctx, in, out, dt)) return 1;
@@ -2222,7 +2276,7 @@ extern "C" int tb200_hv_step_explicit_combine(
 	const bool fusable =
 		(ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) && (ctx->lay.nlev > 1)
 		&& (ctx->lay.ntr == 0 || stage_fast_ok(ctx)) && (in != out)
-		&& !ctx->cfg.fully_explicit;
+		&& !ctx->cfg.fully_explicit && !uniform_on(ctx);
 	if (!fusable) {
 		if (tb200_lincomb(ctx, coeff, ncoeff, out, TB200_DATA_STATE | TB200_DATA_TRACERS)) return 1;
 		return tb200_hv_step_explicit(ctx, in, out, dt);
@@ -2274,7 +2328,8 @@ extern "C" int tb200_v_step_implicit(tb200_ctx * ctx, int in, int out, double dt
 		if (column_solve(ctx, in, out, dt)) return 1;
 		return column_tracers(ctx, in, out, dt);
 	}
-	return column_solve(ctx, in, out, dt);
+	if (column_solve(ctx, in, out, dt)) return 1;
+	return stale_column_update(ctx, in);
 }
 
 // UpdateColumnTracers for every unique column, then the column filter
@@ -2396,6 +2451,7 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
 	ca.assemble_only = 0;
+	if (column_uniform_args(ctx, ca)) return 1;
 
 	// vertical order 1 + terrain-following metric: specialised kernel
 	// (tb200_column_fast.cuh); TB200_COLUMN_KERNEL = thread | warp | window selects
@@ -2479,6 +2535,8 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 	const char * force = getenv("TB200_COLUMN_KERNEL");
 	bool use_window = (ctx->offd == TBW_KL);
 	if (force != 0 && strcmp(force, "thread") == 0) { wpb = 0; use_window = false; }
+	// (the uniform diffusion terms of BuildF are in the thread-per-column kernel only)
+	if (uniform_on(ctx)) { wpb = 0; use_window = false; force = "thread"; }
 	if (force != 0 && strcmp(force, "warp") == 0) use_window = false;
 	if (force == 0 || strcmp(force, "warp") != 0) { if (use_window) wpb = 0; }
 	if (use_window) {
@@ -2661,6 +2719,7 @@ extern "C" int tb200_debug_column_assembly(
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
 	ca.assemble_only = mode;
+	if (column_uniform_args(ctx, ca)) return 1;
 	ca.col0 = 0;
 	ca.ncols = std::min(ctx->ws_cols, ctx->ncols);
 	if (col < 0 || col >= ca.ncols) TB_FAIL(ctx, "column out of range");
@@ -3090,7 +3149,12 @@ extern "C" int tb200_dss(tb200_ctx * ctx, int inst, int mask) {
 ///////////////////////////////////////////////////////////////////////////////
 // Hyperdiffusion (HorizontalDynamicsFEM::StepAfterSubCycle, :2637-2726)
 
-static int hyper_scalar(tb200_ctx * ctx, int in, int out, double dt, double nu, bool scale) {
+// component >= 0: that state component alone (iComponent, :1988-1996), ref != 0: the
+// reference state is removed from the field first (fRemoveRefState)
+static int hyper_scalar(
+	tb200_ctx * ctx, int in, int out, double dt, double nu, bool scale,
+	int component = -1, const double * ref = 0
+) {
 	const DevLayout & lay = ctx->lay;
 	if (need_metric3d(ctx, "scalar hyperdiffusion (general kernel)")) return 1;
 	HyperRows hr;
@@ -3098,13 +3162,14 @@ static int hyper_scalar(tb200_ctx * ctx, int in, int out, double dt, double nu, 
 	int nsel = 0;
 	// components 2.. of the state (:1983-1993), then every tracer
 	for (int c = 2; c < lay.ncomp; c++) {
+		if (component >= 0 && c != component) continue;
 		hr.row0[hr.nranges] = lay.rowoff[c];
 		hr.row1[hr.nranges] = lay.rowoff[c] + lay.rowlev[c];
 		hr.onedge[hr.nranges] = lay.onedge[c];
 		nsel += lay.rowlev[c];
 		hr.nranges++;
 	}
-	if (lay.ntr > 0) {
+	if (lay.ntr > 0 && component < 0) {
 		hr.row0[hr.nranges] = lay.troff;
 		hr.row1[hr.nranges] = lay.nrows;
 		hr.onedge[hr.nranges] = 0;
@@ -3115,7 +3180,21 @@ static int hyper_scalar(tb200_ctx * ctx, int in, int out, double dt, double nu, 
 	auto kfn = k_hyper_scalar<4, kItems>;
 	TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
 		ctx->stream, lay, ctx->geom, ctx->tables, hr, nsel,
-		(const double *)ctx->inst[in], ctx->inst[out], dt, nu, scale ? 1 : 0);
+		(const double *)ctx->inst[in], ctx->inst[out], dt, nu, scale ? 1 : 0, ref);
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
+static int hyper_vector_from(
+	tb200_ctx * ctx, const double * in, int out, double dt, double nud, double nuv, bool scale
+) {
+	const DevLayout & lay = ctx->lay;
+	const long long nitems = lay.nelem * lay.nlev;
+	auto kfn = k_hyper_vector<4, kItems>;
+	TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
+		ctx->stream, lay, ctx->geom, ctx->tables,
+		in, ctx->inst[out], dt, nud, nuv, scale ? 1 : 0,
+		ctx->cfg.cartesian_xz);
 	TB_KERNEL_CHECK(ctx);
 	return 0;
 }
@@ -3123,13 +3202,84 @@ static int hyper_scalar(tb200_ctx * ctx, int in, int out, double dt, double nu, 
 static int hyper_vector(
 	tb200_ctx * ctx, int in, int out, double dt, double nud, double nuv, bool scale
 ) {
+	return hyper_vector_from(ctx, (const double *)ctx->inst[in], out, dt, nud, nuv, scale);
+}
+
+// Uniform diffusion at the end of HorizontalDynamicsFEM::StepExplicit (:1817-1858):
+// second-order diffusion of the velocity, of rho theta and of w, each minus the same
+// operator on the reference state.
+static int uniform_diffusion_horizontal(tb200_ctx * ctx, int in, int out, double dt) {
+	if (ctx->lay.ntr > 0) {
+		// (the reference's implicit column update of the tracers throws "Not
+		// implemented" with uniform diffusion, VerticalDynamicsFEM.cpp:3914-3917)
+		TB_FAIL(ctx, "uniform diffusion with tracers is not implemented");
+	}
+	if (refstate_alloc(ctx)) return 1;
+	const double nuv = ctx->uniform_v;
+	const double nus = ctx->uniform_s;
+	if (hyper_vector(ctx, in, out, dt, -nuv, -nuv, false)) return 1;
+	if (hyper_vector_from(ctx, (const double *)ctx->d_refstate, out, dt, nuv, nuv, false)) return 1;
+	if (ctx->cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) {
+		if (hyper_scalar(ctx, in, out, dt, nus, false, 2, ctx->d_refstate)) return 1;
+		if (hyper_scalar(ctx, in, out, dt, nuv, false, 3, ctx->d_refstate)) return 1;
+	}
+	return 0;
+}
+
+// Uniform diffusion of u and v in the column (VerticalDynamicsFEM::StepExplicit,
+// :1058-1106), after the vertical advection of the velocity.
+//
+// What the reference differentiates there is its work array m_dStateNode[UIx/VIx],
+// which StepExplicit fills only under --explicitvertical (SetupReferenceColumn,
+// :751-756; the copy at the head of the column loop is commented out, :724-745).
+// Otherwise the array still holds the column SetupReferenceColumn saw last: the
+// last column of the most recent StepImplicit - the last interior node of the last
+// active patch, u and v of that call's initial instance (:1334-1345) - or zeros
+// before the first StepImplicit.  Every node then gets dt nu / ztop^2 (DD of that one
+// column - DD of its own reference column).  Restated as it is: the results are
+// the reference's.
+static int stale_column_alloc(tb200_ctx * ctx) {
+	if (ctx->d_stale_uv != 0) return 0;
+	const size_t n = (size_t)2 * ctx->lay.nlev;
+	if (dalloc(ctx, &ctx->d_stale_uv, n)) return 1;
+	TB_CHECK(ctx, cudaMemset(ctx->d_stale_uv, 0, n * sizeof(double)));
+	return 0;
+}
+
+// after StepImplicit(in, .): remember u, v of its last column
+static int stale_column_update(tb200_ctx * ctx, int in) {
+	if (!uniform_on(ctx) || ctx->cfg.fully_explicit) return 0;
+	if (stale_column_alloc(ctx)) return 1;
+	const PatchInfo * last = 0;
+	for (size_t p = 0; p < ctx->patches.size(); p++) {
+		const PatchInfo & pi = ctx->patches[p];
+		if (pi.elem0 >= 0 && (last == 0 || pi.index > last->index)) last = &pi;
+	}
+	if (last == 0) return 0;
 	const DevLayout & lay = ctx->lay;
-	const long long nitems = lay.nelem * lay.nlev;
-	auto kfn = k_hyper_vector<4, kItems>;
-	TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
-		ctx->stream, lay, ctx->geom, ctx->tables,
-		(const double *)ctx->inst[in], ctx->inst[out], dt, nud, nuv, scale ? 1 : 0,
-		ctx->cfg.cartesian_xz);
+	// element (nea - 1, neb - 1) of the patch, node (np - 1, np - 1)
+	const long long e = last->elem0 + (long long)last->nea * last->neb - 1;
+	const long long node = e * lay.nn + (lay.nn - 1);
+	auto kfn = k_stale_column_uv;
+	TB_LAUNCH_FLAT(kfn, dim3(1), dim3(64), 0, ctx->stream,
+		lay, (const double *)ctx->inst[in], node, ctx->d_stale_uv);
+	TB_KERNEL_CHECK(ctx);
+	return 0;
+}
+
+static int uniform_diffusion_vertical_uv(tb200_ctx * ctx, int in, int out, double dt) {
+	const DevLayout & lay = ctx->lay;
+	if (check_ops(ctx)) return 1;
+	if (refstate_alloc(ctx)) return 1;
+	if (stale_column_alloc(ctx)) return 1;
+	const double ztop = ctx->cfg.ztop;
+	const double coeff = ctx->uniform_v / (ztop * ztop);
+	const long long total = lay.nelem * (long long)lay.nn;
+	auto kfn = k_uniform_diffusion_uv;
+	TB_LAUNCH_FLAT(kfn, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, ctx->stream,
+		lay, ctx->ops, (const double *)ctx->inst[in], (const double *)ctx->d_refstate,
+		ctx->inst[out], dt, coeff,
+		ctx->cfg.fully_explicit ? (const double *)0 : (const double *)ctx->d_stale_uv);
 	TB_KERNEL_CHECK(ctx);
 	return 0;
 }

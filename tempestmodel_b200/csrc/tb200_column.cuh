@@ -36,6 +36,11 @@ struct ColumnArgs {
 	int * info;             // device flag: first failing column + 1
 	int assemble_only;      // debugging: 1 stop before the solve, 2 after it;
 	                        // 3: fully explicit vertical step (update -= dt F)
+	// uniform diffusion (BuildF :2594-2636; k_column_implicit only): reference state in
+	// the state layout and the coefficients divided by ztop^2; 0 = off
+	const double * ref = 0;
+	double uni_s = 0.0;
+	double uni_v = 0.0;
 };
 
 // number of workspace entries per column
@@ -330,6 +335,28 @@ __global__ void k_column_implicit(
 		const double dCurlTerm = -dConUa * dUa(k) - dConUb * dUb(k);
 		f += (dkee(k) + dCurlTerm);
 		F(3 * k + FW) = f;
+	}
+	// uniform diffusion of rho theta and w minus their reference (:2101-2160,
+	// 2594-2636; the Jacobian does not carry it)
+	if (ca.ref != 0) {
+		const DevOp & opDDN2N = ops.op[6];
+		const double * rP = ca.ref + ebase + (size_t)lay.rowoff[PIx] * NN + nd;
+		const double * rW = ca.ref + ebase + (size_t)lay.rowoff[WIx] * NN + nd;
+		for (int k = 0; k < L; k++) {
+			aux(k) = rP[(size_t)k * NN];
+		}
+		for (int k = 0; k < L; k++) {
+			const double dd = tb_ws_apply(opDDN2N, snP, k);
+			const double dUniform = dd - tb_ws_apply(opDDN2N, aux, k);
+			F(3 * k + FP) -= ca.uni_s * dUniform;
+		}
+		for (int k = 0; k <= L; k++) {
+			aux(k) = rW[(size_t)k * NN];
+		}
+		for (int k = 1; k < L; k++) {
+			const double dUniform = ddW(k) - tb_ws_apply(opDDE2E, aux, k);
+			F(3 * k + FW) -= ca.uni_v * dUniform;
+		}
 	}
 	// vertical upwinding (:2640-2713)
 	const int vo = ca.fe_nodes;

@@ -132,6 +132,10 @@ struct tb200_ctx {
 	double * d_ws; int ws_cols; int * d_info;
 	double * d_ray_node; double * d_ray_redge; double * d_refstate;   // Rayleigh friction
 	bool has_rayleigh;
+	// uniform diffusion (Grid::HasUniformDiffusion, Grid.cpp:399-415): scalar and
+	// vector coefficients; acts on the state minus the reference state (d_refstate)
+	double uniform_s; double uniform_v;
+	double * d_stale_uv;   // [2][nlev]: see uniform_diffusion_vertical_uv (tb200_api.cu)
 	double * column_inc;              // set while tb200_copy_v_step_implicit_diff runs
 	double * d_wold;                  // w before the implicit solve (tracer update)
 	int offd;
@@ -186,7 +190,7 @@ struct tb200_ctx {
 		nsend_total(0), nrecv_total(0), d_send_nodes(0), d_sendbuf(0),
 		d_recvbuf(0), d_send_rank(0), d_send_slot(0), peer_area(0), peer_rows(0),
 		peer_ready(false), peer_seq(0), d_peer_ticket(0), buf_rows(0), ncols(0), d_col_node(0), d_col_dups(0), tracer_keep(0), tracer_inc(0), d_hs_lat(0), d_hs_sp(0), d_lon(0), d_precip(0),
-		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false),
+		d_ws(0), ws_cols(0), d_info(0), d_ray_node(0), d_ray_redge(0), d_refstate(0), has_rayleigh(false), uniform_s(0.0), uniform_v(0.0), d_stale_uv(0),
 		column_inc(0), d_wold(0), offd(4), launches(0), writes(0), uvzero_inst(-1), uvzero_writes(0),
 		timing_begin(0), timing_end(0), timing_user(0),
 		carry_full(false), h_info(0),

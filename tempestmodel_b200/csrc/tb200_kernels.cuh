@@ -740,6 +740,50 @@ __global__ void k_nh_explicit(
 }
 
 ///////////////////////////////////////////////////////////////////////////////
+// Uniform diffusion of u and v in the column (VerticalDynamicsFEM::StepExplicit,
+// VerticalDynamicsFEM.cpp:1058-1106): second derivative on levels of the velocity and
+// of the reference velocity, update += dt coeff (DD u - DD u_ref), coeff = nu / ztop^2.
+// One thread per element-local node.  stale != 0: the "state" column is that one
+// column [2][L] for every node (what the reference's work array holds outside
+// --explicitvertical, see uniform_diffusion_vertical_uv in tb200_api.cu).
+__global__ void k_stale_column_uv(
+	DevLayout lay, const double * __restrict__ in, long long node, double * __restrict__ stale
+) {
+	const int NN = lay.nn;
+	const int L = lay.nlev;
+	const size_t ebase = (size_t)(node / NN) * lay.nrows * NN + (size_t)(node % NN);
+	for (int q = threadIdx.x; q < 2 * L; q += blockDim.x) {
+		const int c = q / L, k = q % L;
+		stale[q] = in[ebase + (size_t)(lay.rowoff[c] + k) * NN];
+	}
+}
+
+__global__ void k_uniform_diffusion_uv(
+	DevLayout lay, DevOps ops, const double * __restrict__ in,
+	const double * __restrict__ ref, double * __restrict__ out,
+	double dt, double coeff, const double * __restrict__ stale
+) {
+	const int NN = lay.nn;
+	const int L = lay.nlev;
+	const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (node >= lay.nelem * (long long)NN) return;
+	const long long e = node / NN;
+	const int n = (int)(node % NN);
+	const size_t ebase = (size_t)e * lay.nrows * NN + n;
+	const DevOp & opDDN2N = ops.op[6];
+	for (int c = 0; c < 2; c++) {
+		const size_t o = ebase + (size_t)lay.rowoff[c] * NN;
+		for (int k = 0; k < L; k++) {
+			const double dDiffDiffState = (stale != 0)
+				? tb_col_apply(opDDN2N, stale + (size_t)c * L, 1, k)
+				: tb_col_apply(opDDN2N, in + o, NN, k);
+			const double dDiffDiffRef = tb_col_apply(opDDN2N, ref + o, NN, k);
+			out[o + (size_t)k * NN] += dt * coeff * (dDiffDiffState - dDiffDiffRef);
+		}
+	}
+}
+
+///////////////////////////////////////////////////////////////////////////////
 // HorizontalDynamicsFEM::ApplyScalarHyperdiffusion
 // (reference HorizontalDynamicsFEM.cpp:1867-2203) on rows [row0,row1) of every
 // element, each row being one (component, level) slab; jac_sel picks the
@@ -757,7 +801,8 @@ __global__ void __launch_bounds__(NP * NP * ITEMS)
 k_hyper_scalar(
 	DevLayout lay, DevGeom g, DevTables t, HyperRows hr, int nrows_sel,
 	const double * __restrict__ in, double * __restrict__ out,
-	double dt, double nu, int scale_nu
+	double dt, double nu, int scale_nu,
+	const double * __restrict__ ref   // fRemoveRefState (:2060-2070): subtracted from the field; 0 = no
 ) {
 	const int NN = NP * NP;
 	__shared__ double sPsi[ITEMS][NN];
@@ -795,7 +840,11 @@ k_hyper_scalar(
 		? g.jace[((size_t)e * (L + 1) + klev) * NN + n]
 		: g.jac[((size_t)e * L + klev) * NN + n];
 
-	sPsi[it][n] = in[off];
+	double dBufferState = in[off];
+	if (ref != 0) {
+		dBufferState -= ref[off];
+	}
+	sPsi[it][n] = dBufferState;
 	__syncthreads();
 
 	// Pointwise gradient (:2073-2107)

@@ -155,6 +155,17 @@ class DeviceContext:
         self._ck(self.lib.tb200_upload_rayleigh(self._h, patch, _ptr(a), _ptr(b), _ptr(c),
                                                 _ptr(d)))
 
+    def upload_reference_state(self, patch, ref_node, ref_redge):
+        """GridPatch::GetReferenceState of a local patch (state layout)."""
+        a, b = _f64(ref_node), _f64(ref_redge)
+        self._ck(self.lib.tb200_upload_reference_state(self._h, patch, _ptr(a), _ptr(b)))
+
+    def set_uniform_diffusion(self, scalar_coeff, vector_coeff):
+        """TestCase::GetUniformDiffusionCoeffs -> Grid::HasUniformDiffusion: uniform
+        second-order diffusion of the state minus the reference state."""
+        self._ck(self.lib.tb200_set_uniform_diffusion(self._h, float(scalar_coeff),
+                                                      float(vector_coeff)))
+
     # -- device-side set-up (tb200_setup.cuh) ------------------------------------
     def evaluate_geometry_cs(self, patch, radius, omega):
         """2-D metric, Coriolis parameter, longitude / latitude of a cubed-sphere

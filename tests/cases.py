@@ -59,6 +59,25 @@ CASES["bubble_r6_l8_strang"] = dict(
     script="addw:0,100;dss:0;dump:ic,0;step:3;dump:st,0;checksum:cs",
     geometry_from="bubble_r6_l8")
 
+# uniform diffusion (TestCase::GetUniformDiffusionCoeffs -> Grid::HasUniformDiffusion;
+# the Cartesian cases of test/nonhydro_xz use it): the bubble and the JW case with
+# distinct scalar and vector coefficients, stage by stage and over Strang steps
+_STAGES_DIFF = [
+    "dump:ic,0", "copy:0,1", "hexp:0,1,%(dt)s", "dump:h1,1", "vexp:0,1,%(dt)s",
+    "dump:v1,1", "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,%(dt)s", "dump:vi,2",
+    "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0", "checksum:cs"]
+CASES["bubble_r6_l8_diff"] = dict(
+    case="bubble", npatch=1,
+    flags=["--resolution", "6", "--resy", "1", "--levels", "8", "--dt", "10000u",
+           "--nu", "1e4", "--nud", "1e4", "--nuv", "1e4", "--diffs", "300", "--diffv", "150"],
+    script=";".join(["addw:0,100", "dss:0"] + [s % dict(dt="0.01") for s in _STAGES_DIFF]),
+    compact=True, keep=("refstatenode", "refstateredge"))
+CASES["jw_ne2_l6_diff"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s",
+                      "--diffs", "2e5", "--diffv", "1e5"],
+    script=";".join(["addw:0,20000", "dss:0"] + [s % dict(dt="50") for s in _STAGES_DIFF]),
+    compact=True, keep=("refstatenode", "refstateredge"))
+
 # tracers: the JW case carrying three analytic tracer densities (oracle/ref_dump.cpp
 # JWTracerTest): horizontal transport, implicit column transport, both
 # positive-definite filters, DSS and hyperdiffusion of tracers
@@ -298,7 +317,7 @@ def load_case(name):
                                 npatch=c.get("npatch", 6))
 
 
-def _compact(d):
+def _compact(d, keep=()):
     """Keep what the device path reads and the tests compare: zero the halo and
     the component slots that are not located at the array (the reference keeps
     every component at both locations, GridPatch.cpp:341-357; only the valid
@@ -308,7 +327,7 @@ def _compact(d):
     for k, v in d.items():
         leaf = k.rsplit(".", 1)[-1]
         if leaf in ("refstatenode", "refstateredge", "zlevels", "zinterfaces",
-                    "rayleighnode", "rayleighredge"):
+                    "rayleighnode", "rayleighredge") and leaf not in keep:
             continue
         if ".inst" in k and leaf == "tracers":
             v = v.copy()
@@ -342,7 +361,7 @@ def write_golden(name):
             d["hs.patch%d.surface_product" % n] = e[4, :, :, 0] * e[2, :, :, 0]
             n += 1
     if c.get("compact"):
-        d = _compact(d)
+        d = _compact(d, keep=c.get("keep", ()))
     if c.get("scalars_only"):
         d = {k: v for k, v in d.items() if v.size <= 16 and not k.startswith(_SHARED_PREFIXES)}
     os.makedirs(GOLDEN, exist_ok=True)

@@ -94,6 +94,8 @@ def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
                                               or np.abs(d[p + "rayleighredge"]).max() > 0.0):
                 ctx.upload_rayleigh(idx, d[p + "rayleighnode"], d[p + "rayleighredge"],
                                     d[p + "refstatenode"], d[p + "refstateredge"])
+            if "grid.diffs" in d and (float(np.ravel(d["grid.diffs"])[0]) != 0.0 or float(np.ravel(d["grid.diffv"])[0]) != 0.0):
+                ctx.upload_reference_state(idx, d[p + "refstatenode"], d[p + "refstateredge"])
             if eqn == 2 or True:
                 if (p + "elementareanode") in d:
                     ctx.upload_element_area(idx, d[p + "elementareanode"],
@@ -131,6 +133,8 @@ def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
                                        d[p + "topographyderiv"])
         ctx.set_vertical_coordinate(d["grid.retalevels"], d["grid.retainterfaces"])
     ctx.build_connectivity()
+    if "grid.diffs" in d and (float(np.ravel(d["grid.diffs"])[0]) != 0.0 or float(np.ravel(d["grid.diffv"])[0]) != 0.0):
+        ctx.set_uniform_diffusion(float(np.ravel(d["grid.diffs"])[0]), float(np.ravel(d["grid.diffv"])[0]))
     ctx.dump = d
     ctx.local_patches = [n for n in range(npatch) if owners[n] == rank]
     return ctx

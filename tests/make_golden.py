@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import cases  # noqa: E402
 
 if __name__ == "__main__":
-    for name in cases.CASES:
+    # `make_golden.py NAME ...` regenerates the named cases, no argument all of them
+    for name in (sys.argv[1:] or cases.CASES):
         p = cases.write_golden(name)
         print(p, os.path.getsize(p))

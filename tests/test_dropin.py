@@ -103,6 +103,29 @@ def test_cartesian_bubble_dropin(cuda_library, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["plugins", "scheme"])
+def test_uniform_diffusion_dropin(cuda_library, mode):
+    """The bubble with uniform diffusion (--diffs 300 --diffv 150, the coefficients
+    of the reference's other Cartesian cases) through the driver flow: the shells
+    hand Grid::HasUniformDiffusion, the coefficients and the reference state to the
+    device."""
+    from conftest import added_after_the_gpu_budget
+    added_after_the_gpu_budget(cuda_library)
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "bubble", "--resolution", "12", "--resy", "1", "--levels", "24",
+             "--dt", "10000u", "--endtime", "100000u", "--nohypervis",
+             "--diffs", "300", "--diffv", "150"]
+    ref, _ = run("none", *flags)
+    got, _ = run(mode, *flags)
+    for k in ("Rho", "RhoTheta"):
+        assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k]), (k, got, ref)
+    assert abs(got["W"] - ref["W"]) <= 1e-9 * abs(ref["W"]), (got, ref)
+    # and the diffusion is not in the noise of that comparison
+    plain, _ = run("none", *[f for f in flags[:-4]])
+    assert abs(plain["W"] - ref["W"]) > 1e-6 * abs(ref["W"]), (plain, ref)
+
+
+@pytest.mark.gpu
 def test_lazy_instance0_residency(cuda_library):
     """TimestepSchemeB200 keeps instance 0 on the device between steps unless an
     output manager fires (SURVEY 8b call-order contract, Model.cpp:477-509): a

@@ -824,3 +824,51 @@ def test_explicit_vertical_tracers(library):
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     assert_below(dumpctx.compare_tracers(ctx, d, 0, "st"), 1e-12)
     ctx.close()
+
+
+@pytest.mark.parametrize("name,dt,comps", [("bubble_r6_l8_diff", 0.01, [0, 2, 4]),
+                                           ("jw_ne2_l6_diff", 50.0, [0, 1, 2, 4])])
+def test_uniform_diffusion(library, name, dt, comps):
+    """Uniform diffusion (Grid::HasUniformDiffusion; the Cartesian cases of
+    test/nonhydro_xz run with it): second-order diffusion of the state minus the
+    reference state - horizontally at the end of HorizontalDynamicsFEM::StepExplicit
+    (:1817-1858), in the column for u, v (VerticalDynamicsFEM::StepExplicit,
+    :1058-1106) and inside BuildF for rho theta and w (:2594-2636).  Stage by
+    stage and over two Strang steps; switching the diffusion off on the device
+    must break the agreement (the terms are not in the noise)."""
+    added_after_the_gpu_budget(library)
+    d = cases.load_case(name)
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert not ctx.fast_path()[0]
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, dt)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, comps, [3]), 1e-11)
+    ctx.v_step_explicit(0, 1, dt)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, comps, [3]), 1e-11)
+    dumpctx.upload_tag(ctx, d, "dss", instances=[1])
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, dt)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=(name != "bubble_r6_l8_diff")), TOL_IMPLICIT)
+    step_dt = 0.01 if name.startswith("bubble") else 200.0
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, step_dt)
+    ctx.step("strang", False, False, step_dt)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", comps, [3]), TOL_STATE)
+    cs = ctx.checksum(0)
+    ref = d["cs.checksum"]
+    assert abs(cs[4] - ref[4]) <= 1e-13 * abs(ref[4])
+    # control: without the diffusion the stages are off by far more than the bounds
+    ctx.set_uniform_diffusion(0.0, 0.0)
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, dt)
+    off = tendency_errors(ctx, d, 1, "h1", "ic", 0, [2], [3])
+    # (rho theta of the JW case starts on its reference state: no diffusion at all)
+    assert max(off.values()) > 1e-6, off
+    ctx.close()
