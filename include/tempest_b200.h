@@ -421,6 +421,8 @@ int tb200_upload_reference_state(tb200_ctx * ctx, int patch_index,
  * (:1817-1858: u, v; rho theta; w), in the column in VerticalDynamicsFEM::StepExplicit
  * (u, v, :1058-1106) and BuildF (rho theta, w, :2594-2636; not in the Jacobian).
  * General kernels; with tracers the step fails as the reference does (:3914-3917).
+ * The column terms remove the reference state, as with the default fUseReferenceState
+ * of the VerticalDynamicsFEM constructor (--norefstate is not restated).
  * Both zero = off (the default). */
 int tb200_set_uniform_diffusion(tb200_ctx * ctx, double scalar_coeff, double vector_coeff);
 int tb200_upload_rayleigh(tb200_ctx * ctx, int patch_index,

@@ -42,8 +42,13 @@ B200Bridge::B200Bridge(Model & model) :
 	m_dNuScalar(0.0),
 	m_dNuDiv(0.0),
 	m_dNuVort(0.0),
-	m_fFullyExplicit(false)
+	m_fFullyExplicit(false),
+	m_fUseReferenceState(true)
 { }
+
+void B200Bridge::SetUseReferenceState(bool fUseReferenceState) {
+	m_fUseReferenceState = fUseReferenceState;
+}
 
 void B200Bridge::SetFullyExplicit(bool fFullyExplicit) {
 	m_fFullyExplicit = fFullyExplicit;
@@ -340,6 +345,13 @@ void B200Bridge::Initialize() {
 	}
 	Check(tb200_build_connectivity(m_pCtx));
 	if (pGrid->HasUniformDiffusion()) {
+		// (--norefstate leaves the column's reference arrays zero while the
+		// horizontal part still removes the reference state,
+		// VerticalDynamicsFEM.cpp:1756: not restated)
+		if (!m_fUseReferenceState) {
+			_EXCEPTIONT("B200 plugins: uniform diffusion with --norefstate "
+				"is not supported");
+		}
 		Check(tb200_set_uniform_diffusion(
 			m_pCtx,
 			pGrid->GetScalarUniformDiffusionCoeff(),
@@ -487,6 +499,7 @@ VerticalDynamicsB200::VerticalDynamicsB200(
 {
 	// --explicitvertical (VerticalDynamicsFEM.cpp:748-793, 1240-1242)
 	B200Bridge::Get(model).SetFullyExplicit(fFullyExplicit);
+	B200Bridge::Get(model).SetUseReferenceState(fUseReferenceState);
 }
 
 void VerticalDynamicsB200::Initialize() {

@@ -61,6 +61,12 @@ public:
 	void SetFullyExplicit(bool fFullyExplicit);
 
 	///	<summary>
+	///		The fUseReferenceState argument of the VerticalDynamicsFEM
+	///		constructor (false under --norefstate).
+	///	</summary>
+	void SetUseReferenceState(bool fUseReferenceState);
+
+	///	<summary>
 	///		Create the context, describe the grid, upload geometry and tables.
 	///		Called from the plugins' Initialize(), i.e. after
 	///		Grid::EvaluateGeometricTerms (Model.cpp:347-355).
@@ -99,6 +105,7 @@ private:
 	int m_nHypervisOrder;
 	double m_dNuScalar, m_dNuDiv, m_dNuVort;
 	bool m_fFullyExplicit;
+	bool m_fUseReferenceState;
 };
 
 ///////////////////////////////////////////////////////////////////////////////

@@ -287,6 +287,8 @@ static void DumpGeometry(Model & model, bool fArrays3D) {
 		(dynamic_cast<GridCartesianGLL*>(pGrid) != NULL) ? 1 : 0);
 	WriteScalarD("grid.ztop", pGrid->GetZtop());
 	WriteScalarD("grid.reflength", pGrid->GetReferenceLength());
+	WriteScalarI("grid.vdisc_fv",
+		(pGrid->GetVerticalDiscretization() == Grid::VerticalDiscretization_FiniteVolume) ? 1 : 0);
 	WriteScalarD("grid.diffs",
 		pGrid->HasUniformDiffusion() ? pGrid->GetScalarUniformDiffusionCoeff() : 0.0);
 	WriteScalarD("grid.diffv",
@@ -745,6 +747,10 @@ try {
 		model.SetEndTime(_tempestvars.timeEndTime);
 		_TempestSetupMethodOfLines(model, _tempestvars);
 
+		// --vdisc (TempestInitialize.h:486-497)
+		STLStringHelper::ToLower(_tempestvars.strVerticalDiscretization);
+		const bool fFiniteVolume = (_tempestvars.strVerticalDiscretization == "fv");
+
 		GridCSGLL * pGrid = new GridCSGLL(model);
 		pGrid->DefineParameters();
 		pGrid->SetParameters(
@@ -754,7 +760,9 @@ try {
 			4,
 			_tempestvars.nHorizontalOrder,
 			_tempestvars.nVerticalOrder,
-			Grid::VerticalDiscretization_FiniteElement,
+			fFiniteVolume
+				? Grid::VerticalDiscretization_FiniteVolume
+				: Grid::VerticalDiscretization_FiniteElement,
 			Grid::VerticalStaggering_Lorenz);
 		pGrid->InitializeDataLocal();
 		model.SetGrid(pGrid, nPatch);
