@@ -411,6 +411,12 @@ int tb200_step(tb200_ctx * ctx, int scheme, int first_step, int last_step, doubl
  * uploaded, tb200_h_step_after_subcycle applies
  * HorizontalDynamicsFEM::ApplyRayleighFriction (:2418-2536) after the
  * hyperdiffusion (APPLY_RAYLEIGH_WITH_HYPERVIS, Defines.h:74). */
+/* --vdisc FV (Grid::VerticalDiscretization_FiniteVolume; the default is the finite-
+ * element discretisation): the column operators passed to tb200_set_column_op are
+ * then the reference's finite-volume ones; on this side every level becomes its own
+ * element for the penalty terms and the Jacobian band is the narrower one of
+ * VerticalDynamicsFEM.cpp:174-185.  General kernels.  Call before the first step. */
+int tb200_set_vertical_discretization(tb200_ctx * ctx, int finite_volume);
 /* GridPatch::GetReferenceState(Node / REdge) of a local patch alone (zero until
  * uploaded, as in a test case without TestCase::HasReferenceState). */
 int tb200_upload_reference_state(tb200_ctx * ctx, int patch_index,

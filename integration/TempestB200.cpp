@@ -344,6 +344,11 @@ void B200Bridge::Initialize() {
 			m_pCtx, &(pGrid->GetREtaLevels()[0]), &(pGrid->GetREtaInterfaces()[0])));
 	}
 	Check(tb200_build_connectivity(m_pCtx));
+	if (pGrid->GetVerticalDiscretization() ==
+	    Grid::VerticalDiscretization_FiniteVolume
+	) {
+		Check(tb200_set_vertical_discretization(m_pCtx, 1));
+	}
 	if (pGrid->HasUniformDiffusion()) {
 		// (--norefstate leaves the column's reference arrays zero while the
 		// horizontal part still removes the reference state,

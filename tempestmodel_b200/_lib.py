@@ -141,6 +141,7 @@ _SIGNATURES = {
                                       c_void_p]),
     "tb200_upload_reference_state": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "tb200_set_uniform_diffusion": (c_int, [c_void_p, c_double, c_double]),
+    "tb200_set_vertical_discretization": (c_int, [c_void_p, c_int]),
     "tb200_upload_state_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tb200_download_state_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
                                            c_void_p, c_int]),

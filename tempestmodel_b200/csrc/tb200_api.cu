@@ -411,6 +411,8 @@ extern "C" int tb200_create(const tb200_config * cfg, tb200_ctx ** out) {
 		case 5: ctx->offd = 30; break;
 		default: TB_FAIL(ctx, "unsupported vertical order");
 	}
+	ctx->fe_nodes = cfg->vertical_order;
+	ctx->finite_volume = 0;
 	memset(&ctx->ops, 0, sizeof(ctx->ops));
 	memset(&ctx->geom, 0, sizeof(ctx->geom));
 	memset(&ctx->tables, 0, sizeof(ctx->tables));
@@ -880,6 +882,41 @@ extern "C" int tb200_upload_reference_state(
 	const int rc = tb200_upload_state(ctx, patch_index, slot, ref_node, ref_redge, 0);
 	ctx->inst.pop_back();
 	return rc;
+}
+
+// --vdisc FV (Grid::VerticalDiscretization_FiniteVolume): the column operators the
+// caller supplies are the finite-volume ones (even orders only,
+// LinearColumnOperatorFEM.cpp:227); here only the counts change - every level is
+// its own element for the penalty terms (VerticalDynamicsFEM.cpp:646-650, 2649-2654)
+// and the declared Jacobian band is narrower (:174-185).  The workspace was sized
+// for the finite-element band at tb200_create, which is the wider one.
+extern "C" int tb200_set_vertical_discretization(tb200_ctx * ctx, int finite_volume) {
+	int fe_offd = 0;
+	switch (ctx->cfg.vertical_order) {
+		case 1: fe_offd = 4; break;
+		case 2: fe_offd = 9; break;
+		case 3: fe_offd = 15; break;
+		case 4: fe_offd = 22; break;
+		case 5: fe_offd = 30; break;
+		default: TB_FAIL(ctx, "unsupported vertical order");
+	}
+	if (!finite_volume) {
+		ctx->finite_volume = 0;
+		ctx->fe_nodes = ctx->cfg.vertical_order;
+		ctx->offd = fe_offd;
+	} else {
+		int offd = 0;
+		if (ctx->cfg.vertical_order <= 2) offd = 4;
+		else if (ctx->cfg.vertical_order == 4) offd = 7;
+		else if (ctx->cfg.vertical_order == 6) offd = 10;
+		else TB_FAIL(ctx, "UNIMPLEMENTED: At this vertical order");
+		if (offd > fe_offd) TB_FAIL(ctx, "column workspace too small for this band");
+		ctx->finite_volume = 1;
+		ctx->fe_nodes = 1;
+		ctx->offd = offd;
+	}
+	ctx->fast_state = 0;
+	return 0;
 }
 
 // Grid::HasUniformDiffusion with TestCase::GetUniformDiffusionCoeffs (Grid.cpp:399-415)
@@ -1701,6 +1738,7 @@ static int fast_prepare(tb200_ctx * ctx) {
 		ctx->fast_reason = "not a nonhydrostatic np=4 configuration"; return 0;
 	}
 	if (ctx->cfg.vertical_order != 1) { ctx->fast_reason = "vertical order > 1"; return 0; }
+	if (ctx->finite_volume) { ctx->fast_reason = "finite-volume vertical discretisation"; return 0; }
 	if (uniform_on(ctx)) { ctx->fast_reason = "uniform diffusion (general kernels)"; return 0; }
 	if ((int)ctx->reta_n_h.size() != L || (int)ctx->reta_e_h.size() != L + 1) {
 		ctx->fast_reason = "vertical coordinate not set"; return 0;
@@ -2069,7 +2107,7 @@ static int nh_launch_state(
 	NHArgs a;
 	a.dt = dt;
 	a.xz = ctx->cfg.cartesian_xz;
-	a.fe_nodes = ctx->cfg.vertical_order;
+	a.fe_nodes = ctx->fe_nodes;
 	// levels per pass: at most 16 (256 threads), chunks of equal size
 	const int maxkb = std::max(1, 256 / lay.nn);
 	const int nchunk = (lay.nlev + maxkb - 1) / maxkb;
@@ -2159,7 +2197,7 @@ static int explicit_vertical_columns(tb200_ctx * ctx, int in, int out, double dt
 	ca.ws_stride = ctx->ws_cols;
 	ca.dt = dt;
 	ca.offd = ctx->offd;
-	ca.fe_nodes = ctx->cfg.vertical_order;
+	ca.fe_nodes = ctx->fe_nodes;
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
 	ca.assemble_only = 3;
@@ -2183,7 +2221,7 @@ static int explicit_vertical_columns(tb200_ctx * ctx, int in, int out, double dt
 	ta.ws = ctx->d_ws;
 	ta.ws_stride = ctx->ws_cols;
 	ta.dt = dt;
-	ta.fe_nodes = ctx->cfg.vertical_order;
+	ta.fe_nodes = ctx->fe_nodes;
 	ta.kl = 2 * ctx->cfg.vertical_order - 1;
 	ta.info = ctx->d_info;
 	ta.fully_explicit = 1;
@@ -2414,7 +2452,7 @@ static int column_tracers(tb200_ctx * ctx, int in, int out, double dt) {
 	ta.ws = ctx->d_ws;
 	ta.ws_stride = ctx->ws_cols;
 	ta.dt = dt;
-	ta.fe_nodes = ctx->cfg.vertical_order;
+	ta.fe_nodes = ctx->fe_nodes;
 	ta.kl = 2 * ctx->cfg.vertical_order - 1;
 	ta.w_old = ctx->d_wold;
 	ta.info = ctx->d_info;
@@ -2446,7 +2484,7 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 	ca.ws_stride = ctx->ws_cols;
 	ca.dt = dt;
 	ca.offd = ctx->offd;
-	ca.fe_nodes = ctx->cfg.vertical_order;
+	ca.fe_nodes = ctx->fe_nodes;
 	// m_dUpwindCoeff (VerticalDynamicsFEM.cpp:520-521)
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
@@ -2533,7 +2571,7 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 	// default: thread per column with a sliding band window in shared memory
 	// (vertical order 1); TB200_COLUMN_KERNEL = thread | warp | window overrides
 	const char * force = getenv("TB200_COLUMN_KERNEL");
-	bool use_window = (ctx->offd == TBW_KL);
+	bool use_window = (ctx->offd == TBW_KL) && (ctx->cfg.vertical_order == 1) && !ctx->finite_volume;
 	if (force != 0 && strcmp(force, "thread") == 0) { wpb = 0; use_window = false; }
 	// (the uniform diffusion terms of BuildF are in the thread-per-column kernel only)
 	if (uniform_on(ctx)) { wpb = 0; use_window = false; force = "thread"; }
@@ -2715,7 +2753,7 @@ extern "C" int tb200_debug_column_assembly(
 	ca.ws_stride = ctx->ws_cols;
 	ca.dt = dt;
 	ca.offd = ctx->offd;
-	ca.fe_nodes = ctx->cfg.vertical_order;
+	ca.fe_nodes = ctx->fe_nodes;
 	ca.upwind_coeff = (1.0 / 2.0) * pow(1.0 / static_cast<double>(lay.nlev), 1.0);
 	ca.info = ctx->d_info;
 	ca.assemble_only = mode;

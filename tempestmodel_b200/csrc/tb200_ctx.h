@@ -139,6 +139,8 @@ struct tb200_ctx {
 	double * column_inc;              // set while tb200_copy_v_step_implicit_diff runs
 	double * d_wold;                  // w before the implicit solve (tracer update)
 	int offd;
+	int fe_nodes;          // levels per vertical element: the order (FE), 1 (FV)
+	int finite_volume;     // Grid::VerticalDiscretization_FiniteVolume
 
 	// exchange / compute overlap on several ranks
 	cudaStream_t stream2;

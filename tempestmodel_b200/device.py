@@ -160,6 +160,10 @@ class DeviceContext:
         a, b = _f64(ref_node), _f64(ref_redge)
         self._ck(self.lib.tb200_upload_reference_state(self._h, patch, _ptr(a), _ptr(b)))
 
+    def set_vertical_discretization(self, finite_volume):
+        """--vdisc FV: the column operators supplied are the finite-volume ones."""
+        self._ck(self.lib.tb200_set_vertical_discretization(self._h, int(bool(finite_volume))))
+
     def set_uniform_diffusion(self, scalar_coeff, vector_coeff):
         """TestCase::GetUniformDiffusionCoeffs -> Grid::HasUniformDiffusion: uniform
         second-order diffusion of the state minus the reference state."""

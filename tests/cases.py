@@ -278,6 +278,12 @@ CASES["jw_ne2_l24_vo4"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
     script=_STAGES_VO, compact=True)
 
+# --vdisc FV (finite-volume column operators; even orders only): order 2, 12 levels
+CASES["jw_ne2_l12_fv2"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "12", "--vertorder", "2", "--vdisc", "FV",
+                      "--dt", "200s"],
+    script=_STAGES_VO, compact=True)
+
 # tracers at vertical order 2: the column transport of the tracers factorises
 # a band of half-width 2 * order - 1 (VerticalDynamicsFEM.cpp:4028-4038)
 CASES["jwtr_ne2_l12_vo2"] = dict(

@@ -872,3 +872,40 @@ def test_uniform_diffusion(library, name, dt, comps):
     # (rho theta of the JW case starts on its reference state: no diffusion at all)
     assert max(off.values()) > 1e-6, off
     ctx.close()
+
+
+def test_finite_volume_vertical_discretisation(library, monkeypatch):
+    """--vdisc FV --vertorder 2: the reference's finite-volume column operators
+    (uploaded like the finite-element ones), every level its own element for the
+    penalty terms and the narrower declared Jacobian band
+    (VerticalDynamicsFEM.cpp:174-185, 646-650, 2649-2654); stage by stage and
+    over two Strang steps."""
+    added_after_the_gpu_budget(library)
+    d = cases.load_case("jw_ne2_l12_fv2")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert not ctx.fast_path()[0]
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.v_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=True), TOL_IMPLICIT)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    if "emu" in os.path.basename(library):
+        monkeypatch.setenv("TB200_COLUMN_KERNEL", "thread")   # (speed of the emulation)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    ctx.close()
