@@ -163,6 +163,13 @@ try {
 		}
 	}
 
+	// --vdisc (TempestInitialize.h:486-497)
+	STLStringHelper::ToLower(_tempestvars.strVerticalDiscretization);
+	const Grid::VerticalDiscretization eVerticalDiscretization =
+		(_tempestvars.strVerticalDiscretization == "fv")
+			? Grid::VerticalDiscretization_FiniteVolume
+			: Grid::VerticalDiscretization_FiniteElement;
+
 	ThermalBubbleCartesianTest * pBubble = NULL;
 	if (strCase == "bubble") {
 		// _TempestSetupCartesianModel (TempestInitialize.h:590-706), x-z slice
@@ -181,7 +188,7 @@ try {
 			0.0,
 			pBubble->m_iLatBC,
 			true,
-			Grid::VerticalDiscretization_FiniteElement,
+			eVerticalDiscretization,
 			Grid::VerticalStaggering_Lorenz);
 		pGrid->InitializeDataLocal();
 		model.SetGrid(pGrid);
@@ -198,7 +205,7 @@ try {
 			4,
 			_tempestvars.nHorizontalOrder,
 			_tempestvars.nVerticalOrder,
-			Grid::VerticalDiscretization_FiniteElement,
+			eVerticalDiscretization,
 			Grid::VerticalStaggering_Lorenz);
 		pGrid->InitializeDataLocal();
 		model.SetGrid(pGrid, nPatch);

@@ -126,6 +126,23 @@ def test_uniform_diffusion_dropin(cuda_library, mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("vdisc", ["FE", "FV"])
+def test_vertical_order_two_dropin(cuda_library, vdisc):
+    """--vertorder 2 with the finite-element and the finite-volume column operators
+    through the driver flow (the shells pass Grid::GetVerticalOrder and
+    GetVerticalDiscretization on): conserved sums of the reference."""
+    from conftest import added_after_the_gpu_budget
+    added_after_the_gpu_budget(cuda_library)
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "jw", "--resolution", "4", "--levels", "12", "--vertorder", "2",
+             "--vdisc", vdisc, "--dt", "200s", "--endtime", "600s"]
+    ref, _ = run("none", *flags)
+    got, _ = run("scheme", *flags)
+    for k in ("Rho", "RhoTheta"):
+        assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k]), (k, got, ref)
+
+
+@pytest.mark.gpu
 def test_lazy_instance0_residency(cuda_library):
     """TimestepSchemeB200 keeps instance 0 on the device between steps unless an
     output manager fires (SURVEY 8b call-order contract, Model.cpp:477-509): a
