@@ -83,7 +83,8 @@ enum tb200_scheme {
  * (src/atm/TempestInitialize.h:112-144,185-409; PhysicalConstants.h).
  */
 typedef struct {
-	int np;              /* GridGLL::GetHorizontalOrder (nodes per element edge) */
+	int np;              /* GridGLL::GetHorizontalOrder (nodes per element edge):
+	                      * 3, 4, 5 or 6; the column-constant kernels are np = 4 */
 	int nlev;            /* Grid::GetRElements                                   */
 	int vertical_order;  /* GridGLL::GetVerticalOrder                            */
 	int ncomp;           /* EquationSet::GetComponents (3 SW, 5 nonhydro)        */

@@ -91,6 +91,16 @@ extern "C" int tb200_set_timing_hooks(
 
 static const int kItems = 8;   // (element, level) pairs per block in the slab kernels
 
+// the general element kernels are templates on the horizontal order
+#define TB_NP_SWITCH(np, ...) \
+	switch (np) { \
+		case 3: { constexpr int NPV = 3; __VA_ARGS__ } break; \
+		case 4: { constexpr int NPV = 4; __VA_ARGS__ } break; \
+		case 5: { constexpr int NPV = 5; __VA_ARGS__ } break; \
+		case 6: { constexpr int NPV = 6; __VA_ARGS__ } break; \
+		default: TB_FAIL(ctx, "horizontal order not instantiated"); \
+	}
+
 template <typename T>
 static int dalloc(tb200_ctx * ctx, T ** p, size_t count) {
 	void * q = 0;
@@ -325,8 +335,10 @@ extern "C" int tb200_create(const tb200_config * cfg, tb200_ctx ** out) {
 	tb200_ctx * ctx = new tb200_ctx();
 	*out = ctx;
 	ctx->cfg = *cfg;
-	if (cfg->np != 4) {
-		TB_FAIL(ctx, "only np = 4 kernels are instantiated in this build");
+	// (--order: the general kernels are instantiated for these orders; the
+	// column-constant path is np = 4 only)
+	if (cfg->np != 3 && cfg->np != 4 && cfg->np != 5 && cfg->np != 6) {
+		TB_FAIL(ctx, "only np = 3, 4, 5, 6 kernels are instantiated in this build");
 	}
 	if (cfg->nlev < 1 || cfg->ncomp < 1 || cfg->ncomp > TB_MAXC) {
 		TB_FAIL(ctx, "invalid nlev / ncomp");
@@ -538,7 +550,7 @@ extern "C" int tb200_commit_layout(tb200_ctx * ctx) {
 		TB_CHECK(ctx, cudaMemset(ctx->inst[m], 0, inst_doubles * sizeof(double)));
 	}
 	ctx->tmaps.resize(ctx->cfg.ninstances);
-	for (int m = 0; m < ctx->cfg.ninstances; m++) {
+	for (int m = 0; m < ctx->cfg.ninstances && lay.np == 4; m++) {
 		if (make_tensor_map(ctx, ctx->inst[m], &ctx->tmaps[m])) return 1;
 	}
 	ctx->stage_doubles = stage;
@@ -2114,27 +2126,29 @@ static int nh_launch_state(
 	const int KB = (lay.nlev + nchunk - 1) / nchunk;
 	const size_t smem = tb_nh_smem_doubles(lay.nlev, lay.nn, KB) * sizeof(double);
 	const dim3 grid((unsigned)lay.nelem), block(KB * lay.nn);
+#ifndef TB200_EMU
+#define TB_NH_ATTR(k) TB_CHECK(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#else
+#define TB_NH_ATTR(k) (void)0
+#endif
 	if (do_h && do_v) {
-		auto kfn = k_nh_explicit<4, true, true>;
-#ifndef TB200_EMU
-		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
-		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
-			ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);
+		TB_NP_SWITCH(lay.np,
+			auto kfn = k_nh_explicit<NPV, true, true>;
+			TB_NH_ATTR(kfn);
+			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
+				ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);)
 	} else if (do_h) {
-		auto kfn = k_nh_explicit<4, true, false>;
-#ifndef TB200_EMU
-		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
-		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
-			ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);
+		TB_NP_SWITCH(lay.np,
+			auto kfn = k_nh_explicit<NPV, true, false>;
+			TB_NH_ATTR(kfn);
+			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
+				ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);)
 	} else {
-		auto kfn = k_nh_explicit<4, false, true>;
-#ifndef TB200_EMU
-		TB_CHECK(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
-		TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
-			ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);
+		TB_NP_SWITCH(lay.np,
+			auto kfn = k_nh_explicit<NPV, false, true>;
+			TB_NH_ATTR(kfn);
+			TB_LAUNCH(kfn, grid, block, smem, ctx->stream, lay, ctx->geom, ctx->tables,
+				ctx->ops, ctx->phys, a, sb, (const double *)ctx->inst[in], ctx->inst[out], KB);)
 	}
 	TB_KERNEL_CHECK(ctx);
 	return 0;
@@ -2159,10 +2173,11 @@ extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 	const DevLayout & lay = ctx->lay;
 	if (ctx->cfg.eqn_type == TB200_EQN_SHALLOW_WATER) {
 		const long long nitems = lay.nelem * lay.nlev;
-		auto kfn = k_sw_explicit<4, kItems>;
-		TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
-			ctx->stream, lay, ctx->geom, ctx->tables,
-			(const double *)ctx->inst[in], ctx->inst[out], dt, ctx->cfg.g);
+		TB_NP_SWITCH(lay.np,
+			auto kfn = k_sw_explicit<NPV, kItems>;
+			TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(NPV * NPV * kItems), 0,
+				ctx->stream, lay, ctx->geom, ctx->tables,
+				(const double *)ctx->inst[in], ctx->inst[out], dt, ctx->cfg.g);)
 		TB_KERNEL_CHECK(ctx);
 	} else {
 		bool filtered = false;
@@ -3215,10 +3230,11 @@ static int hyper_scalar(
 		hr.nranges++;
 	}
 	const long long nitems = lay.nelem * nsel;
-	auto kfn = k_hyper_scalar<4, kItems>;
-	TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
-		ctx->stream, lay, ctx->geom, ctx->tables, hr, nsel,
-		(const double *)ctx->inst[in], ctx->inst[out], dt, nu, scale ? 1 : 0, ref);
+	TB_NP_SWITCH(lay.np,
+		auto kfn = k_hyper_scalar<NPV, kItems>;
+		TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(NPV * NPV * kItems), 0,
+			ctx->stream, lay, ctx->geom, ctx->tables, hr, nsel,
+			(const double *)ctx->inst[in], ctx->inst[out], dt, nu, scale ? 1 : 0, ref);)
 	TB_KERNEL_CHECK(ctx);
 	return 0;
 }
@@ -3228,11 +3244,12 @@ static int hyper_vector_from(
 ) {
 	const DevLayout & lay = ctx->lay;
 	const long long nitems = lay.nelem * lay.nlev;
-	auto kfn = k_hyper_vector<4, kItems>;
-	TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
-		ctx->stream, lay, ctx->geom, ctx->tables,
-		in, ctx->inst[out], dt, nud, nuv, scale ? 1 : 0,
-		ctx->cfg.cartesian_xz);
+	TB_NP_SWITCH(lay.np,
+		auto kfn = k_hyper_vector<NPV, kItems>;
+		TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(NPV * NPV * kItems), 0,
+			ctx->stream, lay, ctx->geom, ctx->tables,
+			in, ctx->inst[out], dt, nud, nuv, scale ? 1 : 0,
+			ctx->cfg.cartesian_xz);)
 	TB_KERNEL_CHECK(ctx);
 	return 0;
 }

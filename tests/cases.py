@@ -278,6 +278,22 @@ CASES["jw_ne2_l24_vo4"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
     script=_STAGES_VO, compact=True)
 
+# --order 3 and 5 (horizontal order np other than 4: the general kernels are
+# templates on np): shallow water and the JW case, stages and two Strang steps
+for _np in (3, 5, 6):
+    CASES["sw2_ne2_np%d" % _np] = dict(
+        case="sw2", flags=["--resolution", "2", "--order", str(_np)],
+        script=";".join([
+            "dump:ic,0", "copy:0,1", "hexp:0,1,100", "dump:h1,1", "dss:1", "dump:dss,1",
+            "copy:1,4", "hasc:4,1,2,200", "dump:hasc,1,2",
+            "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
+            "step:2", "dump:st,0", "checksum:cs"]), compact=True)
+    if _np == 6:
+        continue
+    CASES["jw_ne2_l6_np%d" % _np] = dict(
+        case="jw", flags=["--resolution", "2", "--levels", "6", "--order", str(_np), "--dt", "200s"],
+        script=_STAGES_VO, compact=True)
+
 # --vdisc FV (finite-volume column operators; even orders only): order 2, 12 levels
 CASES["jw_ne2_l12_fv2"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "12", "--vertorder", "2", "--vdisc", "FV",

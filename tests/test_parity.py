@@ -909,3 +909,70 @@ def test_finite_volume_vertical_discretisation(library, monkeypatch):
     ctx.check_errors()
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     ctx.close()
+
+
+@pytest.mark.parametrize("order", [3, 5, 6])
+def test_shallow_water_other_horizontal_orders(library, order):
+    """--order 3, 5, 6 (np other than 4): the general element kernels are templates
+    on np, DSS and connectivity work on node groups of any size.  Stages and two
+    Strang steps of Williamson 2 against the reference."""
+    added_after_the_gpu_budget(library)
+    d = cases.load_case("sw2_ne2_np%d" % order)
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert ctx.cfg.np == order
+    dumpctx.upload_tag(ctx, d, "ic")
+    assert_below(dumpctx.compare(ctx, d, 0, "ic", [0, 1, 2]), 0.0)
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 100.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2]), TOL_DSS)
+    ctx.copy(1, 4)
+    ctx.h_step_after_subcycle(4, 1, 2, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 1, "hasc", [0, 1, 2]), 1e-13)
+    assert_below(dumpctx.compare(ctx, d, 2, "hasc", [0, 1, 2]), 1e-12)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, 5):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2]), 1e-13)
+    cs = ctx.checksum(0)
+    ref = d["cs.checksum"]
+    assert abs(cs[2] - ref[2]) <= 1e-13 * abs(ref[2])
+    ctx.close()
+
+
+@pytest.mark.parametrize("order", [3, 5])
+def test_nonhydro_other_horizontal_orders(library, order):
+    """--order 3 and 5 on the JW case: explicit stages, DSS, the implicit column
+    solve, hyperdiffusion and two Strang steps (general kernels; the
+    column-constant path is np = 4 only and declines)."""
+    added_after_the_gpu_budget(library)
+    d = cases.load_case("jw_ne2_l6_np%d" % order)
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert ctx.cfg.np == order and not ctx.fast_path()[0]
+    dumpctx.upload_tag(ctx, d, "ic")
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.v_step_explicit(0, 1, 50.0)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [0, 1, 2, 4], [3]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0, 1, 2, 4], [3]), TOL_DSS)
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 30.0)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3],
+                                 skip_poles=True), TOL_IMPLICIT)
+    ctx.h_step_after_subcycle(1, 3, 4, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0, 1, 2, 4], [3]), 1e-13)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 200.0)
+    ctx.step("strang", False, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
+    ctx.close()
