@@ -38,6 +38,12 @@ def test_two_ranks_gloo_tracers(emu_library):
     _run("gloo", port=29619, case="jwtr_ne2_l6_strang", env={"TB_WORKER_STEPS": "3"})
 
 
+def test_two_ranks_gloo_order5(emu_library):
+    """np = 5 on two ranks: pack / exchange / unpack of the halo nodes with node
+    groups that are not the 16-node elements of the column-constant path."""
+    _run("gloo", port=29621, case="jw_ne2_l6_np5")
+
+
 def test_two_ranks_gloo_overlap(emu_library):
     """Element-list launches of the persistent kernels (exchange-feeding elements
     first, the rest on the second stream): same state."""
