@@ -4017,9 +4017,10 @@ extern "C" int tb200_total_potential_enstrophy(
 	}
 	const DevLayout & lay = ctx->lay;
 	const long long nitems = lay.nelem * lay.nlev;
-	auto kfn = k_sw_vorticity;
-	TB_LAUNCH(kfn, dim3((unsigned)((nitems + 7) / 8)), dim3(128), 0, ctx->stream,
-		lay, ctx->geom, ctx->tables, (const double *)ctx->inst[inst], ctx->inst[work]);
+	TB_NP_SWITCH(lay.np,
+		auto kfn = k_sw_vorticity<NPV>;
+		TB_LAUNCH(kfn, dim3((unsigned)((nitems + 7) / 8)), dim3(NPV * NPV * 8), 0, ctx->stream,
+			lay, ctx->geom, ctx->tables, (const double *)ctx->inst[inst], ctx->inst[work]);)
 	TB_KERNEL_CHECK(ctx);
 	if (tb_dss_scalar_rows(ctx, work, lay.rowoff[0], lay.rowoff[0] + lay.nlev)) return 1;
 	return diagnostic(ctx, inst, 1, ctx->inst[work], enstrophy);

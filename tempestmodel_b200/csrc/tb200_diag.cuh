@@ -153,12 +153,13 @@ __global__ void k_diagnostic(
 // relative vorticity of a shallow-water state, element by element
 // (GridPatchCSGLL::ComputeVorticityDivergence, GridPatchCSGLL.cpp:1309-1460),
 // into row 0.. of `out` (an instance used as scratch)
-__global__ void k_sw_vorticity(
+template <int NP>
+__global__ void __launch_bounds__(NP * NP * 8) k_sw_vorticity(
 	DevLayout lay, DevGeom g, DevTables t, const double * in, double * out
 ) {
-	const int NP = 4, NN = 16;
-	__shared__ double sUa[8][16];
-	__shared__ double sUb[8][16];
+	const int NN = NP * NP;
+	__shared__ double sUa[8][NN];
+	__shared__ double sUb[8][NN];
 	const int it = threadIdx.x / NN;
 	const int n = threadIdx.x % NN;
 	const int i = n / NP, j = n % NP;

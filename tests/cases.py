@@ -284,8 +284,8 @@ for _np in (3, 5, 6):
     CASES["sw2_ne2_np%d" % _np] = dict(
         case="sw2", flags=["--resolution", "2", "--order", str(_np)],
         script=";".join([
-            "dump:ic,0", "copy:0,1", "hexp:0,1,100", "dump:h1,1", "dss:1", "dump:dss,1",
-            "copy:1,4", "hasc:4,1,2,200", "dump:hasc,1,2",
+            "dump:ic,0", "energy:e0,0", "copy:0,1", "hexp:0,1,100", "dump:h1,1", "dss:1",
+            "dump:dss,1", "copy:1,4", "hasc:4,1,2,200", "dump:hasc,1,2",
             "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
             "step:2", "dump:st,0", "checksum:cs"]), compact=True)
     if _np == 6:

@@ -922,6 +922,11 @@ def test_shallow_water_other_horizontal_orders(library, order):
     assert ctx.cfg.np == order
     dumpctx.upload_tag(ctx, d, "ic")
     assert_below(dumpctx.compare(ctx, d, 0, "ic", [0, 1, 2]), 0.0)
+    # total energy and potential enstrophy of the initial state (instance 3 is scratch)
+    ref = d["e0.energy"]
+    got = [ctx.total_energy(0), ctx.total_potential_enstrophy(0, 3)]
+    for q in range(2):
+        assert abs(got[q] - ref[q]) <= 1e-12 * abs(ref[q]), (q, got, ref)
     ctx.copy(0, 1)
     ctx.h_step_explicit(0, 1, 100.0)
     assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2]), TOL_STAGE)
