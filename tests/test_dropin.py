@@ -143,6 +143,24 @@ def test_vertical_order_two_dropin(cuda_library, vdisc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case,order", [("sw2", 3), ("jw", 5)])
+def test_horizontal_order_dropin(cuda_library, case, order):
+    """--order 3 (shallow water) and 5 (JW) through the driver flow: the shells
+    pass Grid::GetHorizontalOrder on and the general kernels of that order run."""
+    from conftest import added_after_the_gpu_budget
+    added_after_the_gpu_budget(cuda_library)
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", case, "--resolution", "4", "--order", str(order), "--endtime", "600s"]
+    flags += ["--levels", "1"] if case == "sw2" else ["--levels", "10", "--dt", "200s"]
+    ref, _ = run("none", *flags)
+    got, _ = run("scheme", *flags)
+    for k in (("H",) if case == "sw2" else ("Rho", "RhoTheta")):
+        assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k]), (k, got, ref)
+    if case == "sw2":
+        assert abs(got["U"] - ref["U"]) <= 1e-12 * abs(ref["U"]), (got, ref)
+
+
+@pytest.mark.gpu
 def test_lazy_instance0_residency(cuda_library):
     """TimestepSchemeB200 keeps instance 0 on the device between steps unless an
     output manager fires (SURVEY 8b call-order contract, Model.cpp:477-509): a
