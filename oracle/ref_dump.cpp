@@ -161,6 +161,45 @@ private:
 };
 
 ///	<summary>
+///		Test data: Williamson 2 carrying analytic tracer densities (a smooth
+///		field and a cosine bell), for the tracer transport of
+///		HorizontalDynamicsFEM::StepShallowWater (:449-453, 612-640).
+///	</summary>
+class SWTracerTest : public ShallowWaterTestCase2 {
+public:
+	SWTracerTest(double dH0, double dU0, double dAlpha, int nTracers) :
+		ShallowWaterTestCase2(dH0, dU0, dAlpha),
+		m_nTracers(nTracers)
+	{ }
+
+	virtual void EvaluatePointwiseState(
+		const PhysicalConstants & phys,
+		const Time & time,
+		double dZ, double dLon, double dLat,
+		double * dState, double * dTracer
+	) const {
+		ShallowWaterTestCase2::EvaluatePointwiseState(
+			phys, time, dZ, dLon, dLat, dState, dTracer);
+		for (int c = 0; c < m_nTracers; c++) {
+			if (c == 0) {
+				dTracer[c] = dState[2] * 1.0e-3 * (2.0 + sin(dLon) * cos(dLat));
+			} else {
+				const double dLon0 = 0.5 + 1.7 * c;
+				const double dLat0 = 0.6 - 0.5 * c;
+				const double dR = acos(
+					sin(dLat0) * sin(dLat)
+					+ cos(dLat0) * cos(dLat) * cos(dLon - dLon0));
+				dTracer[c] = (dR < 0.9)
+					? dState[2] * 0.5e-2 * (1.0 + cos(M_PI * dR / 0.9)) : 0.0;
+			}
+		}
+	}
+
+private:
+	int m_nTracers;
+};
+
+///	<summary>
 ///		Test data: the reference's thermal bubble with uniform diffusion
 ///		switched on (its own coefficients are zero,
 ///		ThermalBubbleCartesianTest.cpp:144-150).
@@ -701,8 +740,20 @@ try {
 	TestCase * pTest;
 
 	if (strCase == "sw2") {
-		pModel = new Model(EquationSet::ShallowWaterEquations);
-		pTest = new ShallowWaterTestCase2(dH0, dU0, dAlpha);
+		if (nTracers > 0) {
+			EquationSet eqn(EquationSet::ShallowWaterEquations);
+			for (int c = 0; c < nTracers; c++) {
+				char szName[16];
+				snprintf(szName, 16, "HQ%d", c);
+				eqn.InsertTracer(szName, szName);
+			}
+			UserDataMeta metaUserData;
+			pModel = new Model(eqn, metaUserData);
+			pTest = new SWTracerTest(dH0, dU0, dAlpha, nTracers);
+		} else {
+			pModel = new Model(EquationSet::ShallowWaterEquations);
+			pTest = new ShallowWaterTestCase2(dH0, dU0, dAlpha);
+		}
 	} else if (strCase == "jw") {
 		STLStringHelper::ToLower(strPert);
 		const BaroclinicWaveJWTest::PerturbationType ePert =

@@ -278,6 +278,16 @@ CASES["jw_ne2_l24_vo4"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
     script=_STAGES_VO, compact=True)
 
+# shallow-water tracers (oracle/ref_dump.cpp SWTracerTest): transport inside
+# StepShallowWater, the element filter, DSS and hyperdiffusion of the tracers
+CASES["sw2tr_ne2"] = dict(
+    case="sw2", flags=["--resolution", "2", "--alpha", "0.7", "--ntracers", "2"],
+    script=";".join([
+        "dump:ic,0", "copy:0,1", "hexp:0,1,100", "dump:h1,1", "dss:1", "dump:dss,1",
+        "copy:1,4", "hasc:4,1,2,200", "dump:hasc,1",
+        "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4",
+        "step:3", "dump:st,0", "checksum:cs"]), compact=True)
+
 # --order 3 and 5 (horizontal order np other than 4: the general kernels are
 # templates on np): shallow water and the JW case, stages and two Strang steps
 for _np in (3, 5, 6):

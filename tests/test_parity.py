@@ -981,3 +981,34 @@ def test_nonhydro_other_horizontal_orders(library, order):
     ctx.check_errors()
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2, 4], [3]), TOL_STATE)
     ctx.close()
+
+
+def test_shallow_water_tracers(library):
+    """Tracer transport of HorizontalDynamicsFEM::StepShallowWater (:449-453, 612-640)
+    with the element filter, DSS and hyperdiffusion of the tracers: Williamson 2
+    on a tilted axis carrying a smooth tracer and a cosine bell, one stage and
+    three Strang steps."""
+    added_after_the_gpu_budget(library)
+    d = cases.load_case("sw2tr_ne2")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    dumpctx.upload_tag(ctx, d, "ic")
+    assert_below(dumpctx.compare_tracers(ctx, d, 0, "ic"), 0.0)
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 100.0)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0, 1, 2]), TOL_STAGE)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "h1", before=("ic", 0)), 1e-11)
+    ctx.dss(1)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "dss"), 1e-13)
+    ctx.copy(1, 4)
+    ctx.h_step_after_subcycle(4, 1, 2, 200.0)
+    assert_below(dumpctx.compare(ctx, d, 1, "hasc", [0, 1, 2]), 1e-13)
+    assert_below(dumpctx.compare_tracers(ctx, d, 1, "hasc"), 1e-12)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, 5):
+        ctx.copy(0, m)
+    for s in range(3):
+        ctx.step("strang", s == 0, False, 200.0)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2]), 1e-13)
+    assert_below(dumpctx.compare_tracers(ctx, d, 0, "st"), 1e-12)
+    ctx.close()
