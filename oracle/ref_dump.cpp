@@ -701,6 +701,7 @@ try {
 	int nNoGeometry;
 	double dDiffS;
 	double dDiffV;
+	int nXZ;
 
 	BeginTempestCommandLine("RefDump");
 		SetDefaultResolution(4);
@@ -724,6 +725,7 @@ try {
 		CommandLineInt(nTracers, "ntracers", 0);
 		CommandLineDouble(dRayleigh, "rayleigh", 0.0);
 		CommandLineInt(nNoGeometry, "nogeometry", 0);
+		CommandLineInt(nXZ, "xz", 1);
 		CommandLineDouble(dDiffS, "diffs", 0.0);
 		CommandLineDouble(dDiffV, "diffv", 0.0);
 
@@ -786,8 +788,10 @@ try {
 	if (strCase == "bubble") {
 		ThermalBubbleCartesianTest * pBubble =
 			dynamic_cast<ThermalBubbleCartesianTest*>(pTest);
+		// --xz 0: a three-dimensional periodic box (as
+		// ThermalBubbleCartesian3DTest sets its grid up) instead of the x-z slice
 		TempestSetupCartesianModel(
-			model, pBubble->m_dGDim, 0.0, pBubble->m_iLatBC, true);
+			model, pBubble->m_dGDim, 0.0, pBubble->m_iLatBC, (nXZ != 0));
 		const double XL = std::abs(pBubble->m_dGDim[1] - pBubble->m_dGDim[0]);
 		model.GetGrid()->SetReferenceLength((XL < 110000.0) ? XL : 110000.0);
 

@@ -278,6 +278,22 @@ CASES["jw_ne2_l24_vo4"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
     script=_STAGES_VO, compact=True)
 
+# three-dimensional periodic Cartesian box (GridCartesianGLL with fCartesianXZ =
+# false, as ThermalBubbleCartesian3DTest sets its grid up): the bubble on 4 x 3
+# elements; the flow stays uniform in y, what is exercised is the connectivity and
+# the DSS across y and the v rows
+CASES["bubble3d_r4x3_l6"] = dict(
+    case="bubble", npatch=1,
+    flags=["--resolution", "4", "--resy", "3", "--levels", "6", "--dt", "10000u",
+           "--nu", "1e4", "--nud", "1e4", "--nuv", "1e4", "--xz", "0"],
+    script=";".join([
+        "addw:0,100", "dss:0",
+        "dump:ic,0", "copy:0,1", "hexp:0,1,0.01", "dump:h1,1", "vexp:0,1,0.01",
+        "dump:v1,1", "dss:1", "dump:dss,1", "copy:1,2", "vimp:2,2,0.01",
+        "dump:vi,2", "hasc:1,3,4,0.01", "dump:hasc,3",
+        "copy:0,1", "copy:0,2", "copy:0,3", "copy:0,4", "step:2", "dump:st,0"]),
+    compact=True)
+
 # shallow-water tracers (oracle/ref_dump.cpp SWTracerTest): transport inside
 # StepShallowWater, the element filter, DSS and hyperdiffusion of the tracers
 CASES["sw2tr_ne2"] = dict(

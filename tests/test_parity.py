@@ -1012,3 +1012,54 @@ def test_shallow_water_tracers(library):
     assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 1, 2]), 1e-13)
     assert_below(dumpctx.compare_tracers(ctx, d, 0, "st"), 1e-12)
     ctx.close()
+
+
+def test_cartesian_box_three_dimensional(library):
+    """GridCartesianGLL as a three-dimensional periodic box (fCartesianXZ false,
+    4 x 3 elements): stages and two Strang steps of the bubble.  The flow is
+    uniform in y - v and its tendency are rounding noise, compared on u's scale -
+    what is exercised is the connectivity and the DSS across y."""
+    added_after_the_gpu_budget(library)
+    d = cases.load_case("bubble3d_r4x3_l6")
+    ctx = dumpctx.context_from_dump(d, library=library)
+    assert ctx.cfg.cartesian_xz == 0
+    dumpctx.upload_tag(ctx, d, "ic")
+
+    def v_on_u_scale(inst, tag):
+        got = dumpctx.download(ctx, d, inst)
+        num = den = 0.0
+        for n in ctx.local_patches:
+            ref = dumpctx.interior(d["%s.patch%d.inst%d.node" % (tag, n, inst)])
+            dev = dumpctx.interior(got[n][0])
+            ic = dumpctx.interior(d["ic.patch%d.inst0.node" % n])
+            num = max(num, np.abs(dev[1] - ref[1]).max())
+            den = max(den, np.abs(ref[0] - ic[0]).max())
+        return num / den
+
+    ctx.copy(0, 1)
+    ctx.h_step_explicit(0, 1, 0.01)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [2, 4], [3]), TOL_STAGE)
+    assert_below(tendency_errors(ctx, d, 1, "h1", "ic", 0, [0]), 1e-11)
+    assert v_on_u_scale(1, "h1") <= 1e-11
+    ctx.v_step_explicit(0, 1, 0.01)
+    assert_below(tendency_errors(ctx, d, 1, "v1", "ic", 0, [2, 4], [3]), TOL_STAGE)
+    ctx.dss(1)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [2, 4], [3]), TOL_DSS)
+    assert_below(dumpctx.compare(ctx, d, 1, "dss", [0]), 1e-11)
+    assert v_on_u_scale(1, "dss") <= 1e-11
+    ctx.copy(1, 2)
+    ctx.v_step_implicit(2, 2, 0.01)
+    ctx.check_errors()
+    assert_below(tendency_errors(ctx, d, 2, "vi", "dss", 1, [2, 4], [3]), TOL_IMPLICIT)
+    ctx.h_step_after_subcycle(1, 3, 4, 0.01)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [2, 4], [3]), 1e-13)
+    assert_below(dumpctx.compare(ctx, d, 3, "hasc", [0]), 1e-11)
+    dumpctx.upload_tag(ctx, d, "ic")
+    for m in range(1, ctx.cfg.ninstances):
+        ctx.copy(0, m)
+    ctx.step("strang", True, False, 0.01)
+    ctx.step("strang", False, False, 0.01)
+    ctx.check_errors()
+    assert_below(dumpctx.compare(ctx, d, 0, "st", [0, 2, 4], [3]), TOL_STATE)
+    assert v_on_u_scale(0, "st") <= 1e-10
+    ctx.close()
