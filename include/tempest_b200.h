@@ -74,7 +74,10 @@ enum tb200_scheme {
 	TB200_SCHEME_ERK_FE = 10,
 	TB200_SCHEME_ERK_RK4 = 11,
 	TB200_SCHEME_ERK_SSP3 = 12,
-	TB200_SCHEME_ERK_SSPRK53 = 13
+	TB200_SCHEME_ERK_SSPRK53 = 13,
+	TB200_SCHEME_GARK2 = 14,       /* TimestepSchemeGARK2   ("gark2")    */
+	TB200_SCHEME_SSP3332 = 15,     /* TimestepSchemeSSP3332 ("ssp3_332") */
+	TB200_SCHEME_ARK232 = 16       /* TimestepSchemeARK232  ("ark232")   */
 };
 
 /*
@@ -400,6 +403,9 @@ int tb200_lincomb_v_filter(tb200_ctx * ctx, const double * coeff, int ncoeff, in
 /* Scheme id of a --timescheme string (TempestInitialize.h:192-291, lower case:
  * strang[/kgu35|fe|rk4|rk3|ssprk53], erk[/...], ars222, ars232, ars343, ars443);
  * -1 if the scheme is not implemented. */
+/* VerticalDynamicsFEM::StepImplicitTermsExplicitly (VerticalDynamicsFEM.cpp:439-612;
+ * TimestepSchemeARK232): out -= dt * BuildF(in) on rho theta, w, rho of every node. */
+int tb200_v_step_implicit_terms_explicitly(tb200_ctx * ctx, int in, int out, double dt);
 int tb200_scheme_from_name(const char * name);
 int tb200_scheme_instances(int scheme);
 int tb200_step(tb200_ctx * ctx, int scheme, int first_step, int last_step, double dt);

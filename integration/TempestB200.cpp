@@ -521,6 +521,17 @@ void VerticalDynamicsB200::StepExplicit(
 	b.Download(iDataUpdate);
 }
 
+void VerticalDynamicsB200::StepImplicitTermsExplicitly(
+	int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT
+) {
+	B200Bridge & b = B200Bridge::Get(m_model);
+	b.Upload(iDataInitial);
+	b.Upload(iDataUpdate);
+	b.Check(tb200_v_step_implicit_terms_explicitly(
+		b.Ctx(), iDataInitial, iDataUpdate, dDeltaT));
+	b.Download(iDataUpdate);
+}
+
 void VerticalDynamicsB200::StepImplicit(
 	int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT
 ) {

@@ -146,6 +146,8 @@ public:
 	virtual void Initialize();
 	virtual void StepExplicit(int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT);
 	virtual void StepImplicit(int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT);
+	virtual void StepImplicitTermsExplicitly(
+		int iDataInitial, int iDataUpdate, const Time & time, double dDeltaT);
 	///	<summary>
 	///		Column-wise positive-definite filter (VerticalDynamics.h:123).
 	///	</summary>

@@ -29,7 +29,8 @@ OP_NAMES = ["interp_n2e", "interp_e2n", "diff_n2n", "diff_n2e", "diff_e2n",
 SCHEMES = {"strang": 0, "strang/kgu35": 0, "ars343": 1, "ars232": 2,
            "ars222": 3, "ars443": 4, "strang/rk4": 5, "strang/rk3": 6,
            "strang/fe": 7, "strang/ssprk53": 8, "erk": 9, "erk/kgu35": 9,
-           "erk/fe": 10, "erk/rk4": 11, "erk/rk3": 12, "erk/ssprk53": 13}
+           "erk/fe": 10, "erk/rk4": 11, "erk/rk3": 12, "erk/ssprk53": 13,
+           "gark2": 14, "ssp3_332": 15, "ark232": 16}
 
 
 class Config(Structure):
@@ -135,6 +136,7 @@ _SIGNATURES = {
     "tb200_kessler": (c_int, [c_void_p, c_double]),
     "tb200_scheme_instances": (c_int, [c_int]),
     "tb200_scheme_from_name": (c_int, [c_char_p]),
+    "tb200_v_step_implicit_terms_explicitly": (c_int, [c_void_p, c_int, c_int, c_double]),
     "tb200_step": (c_int, [c_void_p, c_int, c_int, c_int, c_double]),
     "tb200_upload_element_area": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "tb200_upload_rayleigh": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,

@@ -2273,6 +2273,19 @@ extern "C" int tb200_v_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 	return 0;
 }
 
+// VerticalDynamicsFEM::StepImplicitTermsExplicitly (VerticalDynamicsFEM.cpp:439-612):
+// the column tendencies BuildF of every node of `in`, out -= dt * F (rho theta, w,
+// rho); used by TimestepSchemeARK232.
+extern "C" int tb200_v_step_implicit_terms_explicitly(tb200_ctx * ctx, int in, int out, double dt) {
+	TimingScope ts(ctx, "VerticalStepImplicit");
+	if (check_inst2(ctx, in, out)) return 1;
+	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || ctx->lay.nlev == 1) return 0;
+	if (ctx->lay.ntr > 0) {
+		TB_FAIL(ctx, "StepImplicitTermsExplicitly with tracers is not implemented");
+	}
+	return explicit_vertical_columns(ctx, in, out, dt);
+}
+
 extern "C" int tb200_hv_step_explicit(tb200_ctx * ctx, int in, int out, double dt) {
 	if (check_inst2(ctx, in, out)) return 1;
 	if (ctx->cfg.eqn_type != TB200_EQN_PRIMITIVE_NONHYDRO || ctx->lay.nlev == 1) {

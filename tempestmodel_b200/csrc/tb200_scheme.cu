@@ -43,7 +43,9 @@ extern "C" int tb200_scheme_from_name(const char * name) {
 		{"erk/fe", TB200_SCHEME_ERK_FE}, {"erk/rk4", TB200_SCHEME_ERK_RK4},
 		{"erk/rk3", TB200_SCHEME_ERK_SSP3}, {"erk/ssprk53", TB200_SCHEME_ERK_SSPRK53},
 		{"ars222", TB200_SCHEME_ARS222}, {"ars232", TB200_SCHEME_ARS232},
-		{"ars343", TB200_SCHEME_ARS343}, {"ars443", TB200_SCHEME_ARS443}};
+		{"ars343", TB200_SCHEME_ARS343}, {"ars443", TB200_SCHEME_ARS443},
+		{"gark2", TB200_SCHEME_GARK2}, {"ssp3_332", TB200_SCHEME_SSP3332},
+		{"ark232", TB200_SCHEME_ARK232}};
 	if (name == 0) return -1;
 	for (size_t q = 0; q < sizeof(tab) / sizeof(tab[0]); q++) {
 		if (strcmp(name, tab[q].n) == 0) return tab[q].id;
@@ -73,6 +75,12 @@ extern "C" int tb200_scheme_instances(int scheme) {
 			return 7;   // TimestepSchemeARS232.h:48-57
 		case TB200_SCHEME_ARS443:
 			return 10;  // TimestepSchemeARS443.h:48-57
+		case TB200_SCHEME_GARK2:
+			return 5;   // TimestepSchemeGARK2.h:48-57
+		case TB200_SCHEME_SSP3332:
+			return 9;   // TimestepSchemeSSP3332.h:48-57
+		case TB200_SCHEME_ARK232:
+			return 8;   // TimestepSchemeARK232.h:51-60
 		default:
 			return -1;
 	}
@@ -459,6 +467,175 @@ static int step_ars443(tb200_ctx * ctx, double dt) {
 	return 0;
 }
 
+///////////////////////////////////////////////////////////////////////////////
+// TimestepSchemeGARK2 (second-order IMEX GARK, Sandu & Guenther 2013, example 7;
+// reference TimestepSchemeGARK2.cpp:25-141).  The reference copies the State twice
+// and never the Tracers before its first implicit stage (:107-108); so does this.
+
+static int step_gark2(tb200_ctx * ctx, double dt) {
+	const double gam = 1.0 - 0.5 * std::sqrt(2.0);
+	const double alpha = 0.5;
+	const double Imp[2][2] = {{gam, 0.0}, {1.0 - gam, gam}};
+	const double Exp[2][2] = {{0.0, 0.0}, {1.0, 0.0}};
+	const double EI[2][2] = {{0.0, 0.0}, {1.0, 0.0}};
+	const double IE[2][2] = {{gam, 0.0}, {alpha, 1.0 - alpha}};
+	std::vector<double> u2f(4, 0.0), u3f(5, 0.0);
+	u2f[0] = 1.0 - Exp[1][0] / IE[0][0];
+	u2f[1] = Exp[1][0] / IE[0][0] - EI[1][0] / Imp[0][0];
+	u2f[2] = EI[1][0] / Imp[0][0];
+	u3f[0] = 1.0 - IE[1][0] / IE[0][0];
+	u3f[1] = IE[1][0] / IE[0][0] - Imp[1][0] / Imp[0][0];
+	u3f[2] = Imp[1][0] / Imp[0][0];
+	// stage 1 (:96-112)
+	TRY(substage_from(ctx, copy_of(0), 0, 1, IE[0][0] * dt));
+	TRY(tb200_copy(ctx, 1, 2, TB200_DATA_STATE));
+	TRY(tb200_v_step_implicit(ctx, 2, 2, Imp[0][0] * dt));
+	TRY(tb200_dss(ctx, 2, ALL));
+	// (:115-116)
+	TRY(lincomb(ctx, u2f, 3));
+	// stage 2 (:120-134)
+	TRY(substage_from(ctx, u3f, 3, 4, IE[1][1] * dt));
+	TRY(tb200_v_step_implicit(ctx, 4, 4, Imp[1][1] * dt));
+	TRY(tb200_dss(ctx, 4, ALL));
+	// hyperdiffusion (:137-141)
+	TRY(tb200_copy(ctx, 4, 2, ALL));
+	TRY(tb200_h_step_after_subcycle(ctx, 2, 1, 4, dt));
+	TRY(tb200_copy(ctx, 1, 0, ALL));
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// TimestepSchemeSSP3332 (Pareschi & Russo SSP3(3,3,2); reference
+// TimestepSchemeSSP3332.cpp:25-181).  Every implicit stage copies the State only.
+
+static int step_ssp3332(tb200_ctx * ctx, double dt) {
+	const double gam = 1.0 - 1.0 / sqrt(2.0);
+	const double Imp[4][4] = {
+		{gam, 0., 0., 0.},
+		{(1.0 - 2.0 * gam), gam, 0., 0.},
+		{0.5 - gam, 0.0, gam, 0.},
+		{1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0, 0.}};
+	const double Exp[4][4] = {
+		{0.0, 0., 0., 0.},
+		{1.0, 0., 0., 0.},
+		{0.25, 0.25, 0., 0.},
+		{1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0, 0.}};
+	std::vector<double> u2f(8, 0.0), u3f(9, 0.0), u4f(9, 0.0);
+	// (:62-105, the same expressions in the same order)
+	u2f[0] = 1.0 - Imp[1][0] / Imp[0][0];
+	u2f[2] = Imp[1][0] / Imp[0][0];
+	u3f[0] = 1.0 + Imp[1][0] / Imp[0][0] *
+	               Exp[2][0] / Exp[1][0] -
+	               Exp[2][0] / Exp[1][0] -
+	               Imp[2][0] / Imp[0][0];
+	u3f[2] = Imp[2][0] / Imp[0][0] -
+	         Imp[1][0] / Imp[0][0] *
+	         Exp[2][0] / Exp[1][0];
+	u3f[3] = Exp[2][0] / Exp[1][0];
+	u4f[0] = 1.0 - Exp[3][0] / Imp[0][0];
+	u4f[2] = Imp[3][0] / Imp[0][0];
+	u4f[3] = Exp[3][0] / Exp[1][0] -
+	         Imp[3][1] / Imp[1][1];
+	u4f[4] = Imp[3][1] / Imp[1][1];
+	u4f[5] = Exp[3][1] / Exp[2][1] -
+	         Imp[3][2] / Imp[2][2];
+	u4f[6] = Imp[3][2] / Imp[2][2];
+	u4f[7] = -Exp[3][0] / Exp[1][0];
+	u4f[8] = -Exp[3][1] / Exp[2][1];
+	// stage 1: implicit only (:109-115)
+	TRY(tb200_copy(ctx, 0, 2, TB200_DATA_STATE));
+	TRY(tb200_v_step_implicit(ctx, 2, 2, Imp[0][0] * dt));
+	TRY(tb200_dss(ctx, 2, ALL));
+	// stage 2 (:118-137): the combination is kept in instance 7
+	TRY(lincomb(ctx, u2f, 7));
+	TRY(substage_from(ctx, copy_of(7), 2, 3, Exp[1][0] * dt));
+	TRY(tb200_copy(ctx, 3, 4, TB200_DATA_STATE));
+	TRY(tb200_v_step_implicit(ctx, 4, 4, Imp[1][1] * dt));
+	TRY(tb200_dss(ctx, 4, ALL));
+	// stage 3 (:140-159): combination kept in instance 8
+	TRY(lincomb(ctx, u3f, 8));
+	TRY(substage_from(ctx, copy_of(8), 4, 5, Exp[2][1] * dt));
+	TRY(tb200_copy(ctx, 5, 6, TB200_DATA_STATE));
+	TRY(tb200_v_step_implicit(ctx, 6, 6, Imp[2][2] * dt));
+	TRY(tb200_dss(ctx, 6, ALL));
+	// final stage (:162-170)
+	TRY(substage_from(ctx, u4f, 6, 1, Exp[3][2] * dt));
+	// hyperdiffusion (:173-177)
+	TRY(tb200_copy(ctx, 1, 2, ALL));
+	TRY(tb200_h_step_after_subcycle(ctx, 2, 1, 3, dt));
+	TRY(tb200_copy(ctx, 1, 0, ALL));
+	return 0;
+}
+
+///////////////////////////////////////////////////////////////////////////////
+// TimestepSchemeARK232 (reference TimestepSchemeARK232.cpp:25-226): the first
+// explicit stage in two sub-cycles that overwrite instance 0 on the way (:184-189),
+// the implicit terms of the first stage evaluated explicitly
+// (VerticalDynamicsFEM::StepImplicitTermsExplicitly, VerticalDynamicsFEM.cpp:439-612).
+
+static int step_ark232(tb200_ctx * ctx, double dt) {
+	const double gam = 1.0 - 1.0 / std::sqrt(2.0);
+	const double del = 1.0 / (2.0 * std::sqrt(2.0));
+	const double alpha = 1.0 / 6.0 *
+	                     (3.0 + 2.0 * std::sqrt(2.0));
+	const double Imp[3][3] = {
+		{gam, gam, 0.},
+		{del, del, gam},
+		{del, del, gam}};
+	const double Exp[3][3] = {
+		{2.0 * gam, 0., 0.},
+		{1.0 - alpha, alpha, 0.},
+		{del, del, gam}};
+	std::vector<double> u2f(7, 0.0), u3f(8, 0.0);
+	u2f[0] = 1.0 - Exp[1][0] / Exp[0][0];
+	u2f[1] = Exp[1][0] / Exp[0][0] -
+	         Imp[1][0] / Imp[0][0];
+	u2f[2] = Imp[1][0] / Imp[0][0] -
+	         Imp[1][1] / Imp[0][1];
+	u2f[3] = Imp[1][1] / Imp[0][1];
+	u3f[0] = 1.0 - Exp[2][0] / Exp[0][0];
+	u3f[1] = Exp[2][0] / Exp[0][0] -
+	         Imp[2][0] / Imp[0][0];
+	u3f[2] = Imp[2][0] / Imp[0][0] -
+	         Imp[2][1] / Imp[0][1];
+	u3f[3] = Imp[2][1] / Imp[0][1];
+	u3f[4] = Exp[2][1] / Exp[1][1] -
+	         Imp[2][2] / Imp[1][2];
+	u3f[5] = Imp[2][2] / Imp[1][2];
+	u3f[6] = -Exp[2][1] / Exp[1][1];
+	// SubcycleStageExplicit(ExpCf[0][0], iNS = 2, 0 -> 1) (:170-192)
+	{
+		const int iNS = 2;
+		for (int n = 0; n < iNS; n++) {
+			TRY(substage_from(ctx, copy_of(0), 0, 1, Exp[0][0] * dt / iNS));
+			if (n < iNS - 1) {
+				TRY(tb200_copy(ctx, 1, 0, ALL));
+			}
+		}
+	}
+	// SubcycleStageImplicitExplicitly(ImpCf[0][0], iNS = 1, 1 -> 2) (:196-226)
+	TRY(tb200_copy(ctx, 1, 2, ALL));
+	TRY(tb200_v_step_implicit_terms_explicitly(ctx, 1, 2, Imp[0][0] * dt / 1));
+	TRY(tb200_dss(ctx, 2, ALL));
+	// (:121-127)
+	TRY(tb200_copy(ctx, 2, 3, TB200_DATA_STATE));
+	TRY(tb200_v_step_implicit(ctx, 3, 3, Imp[0][1] * dt));
+	TRY(tb200_dss(ctx, 3, ALL));
+	// stage 2 (:130-149): combination kept in instance 6
+	TRY(lincomb(ctx, u2f, 6));
+	TRY(substage_from(ctx, copy_of(6), 3, 4, Exp[1][1] * dt));
+	TRY(tb200_copy(ctx, 4, 5, TB200_DATA_STATE));
+	TRY(tb200_v_step_implicit(ctx, 5, 5, Imp[1][2] * dt));
+	TRY(tb200_dss(ctx, 5, ALL));
+	// stage 3 (:152-160)
+	TRY(substage_from(ctx, u3f, 5, 7, Exp[2][2] * dt));
+	// hyperdiffusion (:163-167)
+	TRY(tb200_copy(ctx, 7, 2, ALL));
+	TRY(tb200_h_step_after_subcycle(ctx, 7, 1, 3, dt));
+	TRY(tb200_copy(ctx, 1, 0, ALL));
+	return 0;
+}
+
 int tb_mirror_errors(tb200_ctx * ctx);    // tb200_api.cu
 int tb_poll_errors(tb200_ctx * ctx);
 
@@ -468,6 +645,9 @@ static int step_dispatch(tb200_ctx * ctx, int scheme, int first, int last, doubl
 		case TB200_SCHEME_ARS222: return step_ars222(ctx, dt);
 		case TB200_SCHEME_ARS232: return step_ars232(ctx, dt);
 		case TB200_SCHEME_ARS443: return step_ars443(ctx, dt);
+		case TB200_SCHEME_GARK2: return step_gark2(ctx, dt);
+		case TB200_SCHEME_SSP3332: return step_ssp3332(ctx, dt);
+		case TB200_SCHEME_ARK232: return step_ark232(ctx, dt);
 		case TB200_SCHEME_ERK_KGU35:
 		case TB200_SCHEME_ERK_FE:
 		case TB200_SCHEME_ERK_RK4:

@@ -278,6 +278,15 @@ CASES["jw_ne2_l24_vo4"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
     script=_STAGES_VO, compact=True)
 
+# the remaining IMEX schemes that run with these plugins (TimestepSchemeGARK2,
+# SSP3332, ARK232; ARS343b only works with HighSpeedDynamics)
+for _s in ("gark2", "ssp3_332", "ark232"):
+    CASES["jw_ne2_l6_%s" % _s] = dict(
+        case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s",
+                          "--timescheme", _s],
+        script="addw:0,20000;dss:0;dump:ic,0;step:2;dump:st,0;checksum:cs",
+        geometry_from="jw_ne2_l6_strang")
+
 # three-dimensional periodic Cartesian box (GridCartesianGLL with fCartesianXZ =
 # false, as ThermalBubbleCartesian3DTest sets its grid up): the bubble on 4 x 3
 # elements; the flow stays uniform in y, what is exercised is the connectivity and

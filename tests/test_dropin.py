@@ -161,6 +161,23 @@ def test_horizontal_order_dropin(cuda_library, case, order):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode,scheme", [("plugins", "ark232"), ("scheme", "ark232"),
+                                         ("scheme", "gark2"), ("scheme", "ssp3_332")])
+def test_more_schemes_dropin(cuda_library, mode, scheme):
+    """GARK2, SSP3(3,3,2) and ARK232 through the driver flow; under the reference's
+    own ARK232 the vertical shell also serves StepImplicitTermsExplicitly."""
+    from conftest import added_after_the_gpu_budget
+    added_after_the_gpu_budget(cuda_library)
+    assert os.path.exists(DRIVER), "oracle/_ref/b200_driver missing"
+    flags = ["--case", "jw", "--resolution", "4", "--levels", "10", "--dt", "200s",
+             "--endtime", "400s", "--timescheme", scheme]
+    ref, _ = run("none", *flags)
+    got, _ = run(mode, *flags)
+    for k in ("Rho", "RhoTheta"):
+        assert abs(got[k] - ref[k]) <= 1e-12 * abs(ref[k]), (k, got, ref)
+
+
+@pytest.mark.gpu
 def test_lazy_instance0_residency(cuda_library):
     """TimestepSchemeB200 keeps instance 0 on the device between steps unless an
     output manager fires (SURVEY 8b call-order contract, Model.cpp:477-509): a

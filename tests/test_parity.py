@@ -174,8 +174,11 @@ def test_nonhydro_stages(library):
 
 
 @pytest.mark.parametrize("scheme", ["strang", "ars343", "ars222", "ars232", "ars443",
-                                    "strang/ssprk53", "strang/rk4", "strang/rk3"])
+                                    "strang/ssprk53", "strang/rk4", "strang/rk3",
+                                    "gark2", "ssp3_332", "ark232"])
 def test_nonhydro_steps(library, scheme):
+    if scheme in ("gark2", "ssp3_332", "ark232"):
+        added_after_the_gpu_budget(library)
     d = cases.load_case("jw_ne2_l6_%s" % scheme.replace("/", "_"))
     ctx = dumpctx.context_from_dump(d, library=library)
     dumpctx.upload_tag(ctx, d, "ic")
