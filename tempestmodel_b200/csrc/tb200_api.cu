@@ -1120,7 +1120,6 @@ extern "C" int tb200_compute_output_fields(tb200_ctx * ctx, int inst) {
 	if (!ctx->connectivity_built) TB_FAIL(ctx, "connectivity not built");
 	const DevLayout & lay = ctx->lay;
 	if (lay.ncomp < 2) TB_FAIL(ctx, "Insufficient components for vorticity calculation");
-	if (lay.np != 4) TB_FAIL(ctx, "output fields: np = 4 only");
 	const int L = lay.nlev;
 	if (3 * L > lay.nrows && ctx->nranks > 1) {
 		TB_FAIL(ctx, "output fields: exchange buffers too small for this layout");
@@ -1142,10 +1141,11 @@ extern "C" int tb200_compute_output_fields(tb200_ctx * ctx, int inst) {
 	}
 	{
 		const long long nitems = lay.nelem * L;
-		auto kfn = k_output_curl_div<4, kItems>;
-		TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(16 * kItems), 0,
-			ctx->stream, lay, ctx->geom, ctx->tables, (const double *)ctx->inst[inst],
-			ctx->d_outfield);
+		TB_NP_SWITCH(lay.np,
+			auto kfn = k_output_curl_div<NPV, kItems>;
+			TB_LAUNCH(kfn, dim3((unsigned)((nitems + kItems - 1) / kItems)), dim3(NPV * NPV * kItems), 0,
+				ctx->stream, lay, ctx->geom, ctx->tables, (const double *)ctx->inst[inst],
+				ctx->d_outfield);)
 		TB_KERNEL_CHECK(ctx);
 	}
 	// ApplyDSS(0, DataType_Vorticity / DataType_Divergence): the field array is laid
