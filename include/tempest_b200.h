@@ -56,7 +56,10 @@ enum tb200_column_op {
 	TB200_OP_DIFFDIFF_E2E = 7, /* m_opDiffDiffREdgeToREdge */
 	TB200_OP_PENALTY_LEFT = 8, /* m_opPenaltyNodeToNode.GetLeftOp()  */
 	TB200_OP_PENALTY_RIGHT = 9,/* m_opPenaltyNodeToNode.GetRightOp() */
-	TB200_OP_COUNT = 10
+	TB200_OP_DIFF_N2N_ZB = 10, /* m_opDiffNodeToNodeZeroBoundaries (no accessor in the
+	                            * reference: GridGLL::DifferentiateNodeToNode(in, out,
+	                            * true) applied to unit vectors); --vmassfluxlevels only */
+	TB200_OP_COUNT = 11
 };
 
 /* Time schemes (src/atm/TimestepScheme*.cpp) */
@@ -424,6 +427,11 @@ int tb200_step(tb200_ctx * ctx, int scheme, int first_step, int last_step, doubl
  * element for the penalty terms and the Jacobian band is the narrower one of
  * VerticalDynamicsFEM.cpp:174-185.  General kernels.  Call before the first step. */
 int tb200_set_vertical_discretization(tb200_ctx * ctx, int finite_volume);
+/* --vmassfluxlevels (fForceMassFluxOnLevels of the VerticalDynamicsFEM constructor):
+ * BuildF forms the mass and rho-theta fluxes on levels and differentiates them with
+ * TB200_OP_DIFF_N2N_ZB (VerticalDynamicsFEM.cpp:2229-2243, 2301-2315); the Jacobian
+ * stays that of the interface fluxes, as in the reference.  General kernels. */
+int tb200_set_mass_flux_on_levels(tb200_ctx * ctx, int on);
 /* GridPatch::GetReferenceState(Node / REdge) of a local patch alone (zero until
  * uploaded, as in a test case without TestCase::HasReferenceState). */
 int tb200_upload_reference_state(tb200_ctx * ctx, int patch_index,

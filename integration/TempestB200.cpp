@@ -43,11 +43,16 @@ B200Bridge::B200Bridge(Model & model) :
 	m_dNuDiv(0.0),
 	m_dNuVort(0.0),
 	m_fFullyExplicit(false),
-	m_fUseReferenceState(true)
+	m_fUseReferenceState(true),
+	m_fMassFluxOnLevels(false)
 { }
 
 void B200Bridge::SetUseReferenceState(bool fUseReferenceState) {
 	m_fUseReferenceState = fUseReferenceState;
+}
+
+void B200Bridge::SetMassFluxOnLevels(bool fMassFluxOnLevels) {
+	m_fMassFluxOnLevels = fMassFluxOnLevels;
 }
 
 void B200Bridge::SetFullyExplicit(bool fFullyExplicit) {
@@ -179,7 +184,8 @@ void B200Bridge::Initialize() {
 		&(pGrid->GetGLLWeights1D()[0])));
 
 	if (cfg.nlev > 1) {
-		const LinearColumnOperator * apOps[TB200_OP_COUNT] = {
+		// (the operators the reference exposes; TB200_OP_DIFF_N2N_ZB follows below)
+		const LinearColumnOperator * apOps[TB200_OP_DIFF_N2N_ZB] = {
 			&(pGrid->GetOpInterpNodeToREdge()),
 			&(pGrid->GetOpInterpREdgeToNode()),
 			&(pGrid->GetOpDiffNodeToNode()),
@@ -190,7 +196,8 @@ void B200Bridge::Initialize() {
 			&(pGrid->GetOpDiffDiffREdgeToREdge()),
 			&(pGrid->GetOpPenaltyNodeToNode().GetLeftOp()),
 			&(pGrid->GetOpPenaltyNodeToNode().GetRightOp())};
-		for (int o = 0; o < TB200_OP_COUNT; o++) {
+		const int nAccessibleOps = (int)(sizeof(apOps) / sizeof(apOps[0]));
+		for (int o = 0; o < nAccessibleOps; o++) {
 			const DataArray2D<double> & dCoeff = apOps[o]->GetCoeffs();
 			if (dCoeff.GetRows() == 0) {
 				continue;
@@ -201,6 +208,43 @@ void B200Bridge::Initialize() {
 				&(apOps[o]->GetIxBegin()[0]),
 				&(apOps[o]->GetIxEnd()[0])));
 		}
+	}
+
+	// --vmassfluxlevels: BuildF differentiates level fluxes with
+	// m_opDiffNodeToNodeZeroBoundaries (GridGLL.h:413), which has no accessor;
+	// GridGLL::DifferentiateNodeToNode(., ., true) applied to the unit vectors
+	// returns its coefficients exactly
+	if (m_fMassFluxOnLevels && (cfg.eqn_type == TB200_EQN_PRIMITIVE_NONHYDRO) &&
+	    (pGrid->GetRElements() > 1)
+	) {
+		const int nL = pGrid->GetRElements();
+		std::vector<double> vecCoeff((size_t)nL * nL, 0.0);
+		std::vector<int> vecBegin(nL, 0), vecEnd(nL, 0);
+		DataArray1D<double> dIn(nL);
+		DataArray1D<double> dOut(nL);
+		for (int l = 0; l < nL; l++) {
+			dIn.Zero();
+			dOut.Zero();
+			dIn[l] = 1.0;
+			pGrid->DifferentiateNodeToNode(&(dIn[0]), &(dOut[0]), true);
+			for (int k = 0; k < nL; k++) {
+				vecCoeff[(size_t)k * nL + l] = dOut[k];
+			}
+		}
+		for (int k = 0; k < nL; k++) {
+			bool fAny = false;
+			for (int l = 0; l < nL; l++) {
+				if (vecCoeff[(size_t)k * nL + l] != 0.0) {
+					if (!fAny) vecBegin[k] = l;
+					vecEnd[k] = l + 1;
+					fAny = true;
+				}
+			}
+		}
+		Check(tb200_set_column_op(
+			m_pCtx, TB200_OP_DIFF_N2N_ZB, nL, nL,
+			&(vecCoeff[0]), &(vecBegin[0]), &(vecEnd[0])));
+		Check(tb200_set_mass_flux_on_levels(m_pCtx, 1));
 	}
 
 	// Geometry, node ids, seam transforms per patch
@@ -505,6 +549,7 @@ VerticalDynamicsB200::VerticalDynamicsB200(
 	// --explicitvertical (VerticalDynamicsFEM.cpp:748-793, 1240-1242)
 	B200Bridge::Get(model).SetFullyExplicit(fFullyExplicit);
 	B200Bridge::Get(model).SetUseReferenceState(fUseReferenceState);
+	B200Bridge::Get(model).SetMassFluxOnLevels(fForceMassFluxOnLevels);
 }
 
 void VerticalDynamicsB200::Initialize() {

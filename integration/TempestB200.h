@@ -67,6 +67,12 @@ public:
 	void SetUseReferenceState(bool fUseReferenceState);
 
 	///	<summary>
+	///		The fForceMassFluxOnLevels argument of the VerticalDynamicsFEM
+	///		constructor (--vmassfluxlevels).
+	///	</summary>
+	void SetMassFluxOnLevels(bool fMassFluxOnLevels);
+
+	///	<summary>
 	///		Create the context, describe the grid, upload geometry and tables.
 	///		Called from the plugins' Initialize(), i.e. after
 	///		Grid::EvaluateGeometricTerms (Model.cpp:347-355).
@@ -106,6 +112,7 @@ private:
 	double m_dNuScalar, m_dNuDiv, m_dNuVort;
 	bool m_fFullyExplicit;
 	bool m_fUseReferenceState;
+	bool m_fMassFluxOnLevels;
 };
 
 ///////////////////////////////////////////////////////////////////////////////

@@ -229,6 +229,9 @@ private:
 
 static FILE * g_fp = NULL;
 
+// --vmassfluxlevels (recorded with the geometry)
+static int g_nMassFluxLevels = 0;
+
 static void WriteRecord(
 	const std::string & strName,
 	int iType, // 0 = double, 1 = int32
@@ -364,6 +367,42 @@ static void DumpGeometry(Model & model, bool fArrays3D) {
 	WriteOp("op.diffdiff_e2e", pGrid->GetOpDiffDiffREdgeToREdge());
 	WriteOp("op.penalty_left", pGrid->GetOpPenaltyNodeToNode().GetLeftOp());
 	WriteOp("op.penalty_right", pGrid->GetOpPenaltyNodeToNode().GetRightOp());
+	{
+		// m_opDiffNodeToNodeZeroBoundaries (GridGLL.h:413, used by BuildF under
+		// --vmassfluxlevels) has no accessor: recover its coefficients by applying
+		// GridGLL::DifferentiateNodeToNode(., ., true) to the unit vectors
+		const int nL = pGrid->GetRElements();
+		DataArray2D<double> dC(nL, nL);
+		DataArray1D<int> iBegin(nL);
+		DataArray1D<int> iEnd(nL);
+		DataArray1D<double> dIn(nL);
+		DataArray1D<double> dOut(nL);
+		for (int l = 0; l < nL; l++) {
+			dIn.Zero();
+			dOut.Zero();
+			dIn[l] = 1.0;
+			pGrid->DifferentiateNodeToNode(&(dIn[0]), &(dOut[0]), true);
+			for (int k = 0; k < nL; k++) {
+				dC[k][l] = dOut[k];
+			}
+		}
+		for (int k = 0; k < nL; k++) {
+			iBegin[k] = 0;
+			iEnd[k] = 0;
+			bool fAny = false;
+			for (int l = 0; l < nL; l++) {
+				if (dC[k][l] != 0.0) {
+					if (!fAny) iBegin[k] = l;
+					iEnd[k] = l + 1;
+					fAny = true;
+				}
+			}
+		}
+		Write2D("op.diff_n2n_zb.coeff", dC);
+		Write1I("op.diff_n2n_zb.begin", iBegin);
+		Write1I("op.diff_n2n_zb.end", iEnd);
+		WriteScalarI("grid.massfluxlevels", g_nMassFluxLevels);
+	}
 
 	for (int n = 0; n < pGrid->GetActivePatchCount(); n++) {
 		GridPatchGLL * pPatch =
@@ -731,6 +770,8 @@ try {
 
 		ParseCommandLine(argc, argv);
 	EndTempestCommandLine(argv)
+
+	g_nMassFluxLevels = _tempestvars.fForceMassFluxOnLevels ? 1 : 0;
 
 	g_fp = fopen(strOut.c_str(), "wb");
 	if (g_fp == NULL) {

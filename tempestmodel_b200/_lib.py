@@ -24,7 +24,7 @@ DATA_DIVERGENCE = 16
 
 OP_NAMES = ["interp_n2e", "interp_e2n", "diff_n2n", "diff_n2e", "diff_e2n",
             "diff_e2e", "diffdiff_n2n", "diffdiff_e2e", "penalty_left",
-            "penalty_right"]
+            "penalty_right", "diff_n2n_zb"]
 
 SCHEMES = {"strang": 0, "strang/kgu35": 0, "ars343": 1, "ars232": 2,
            "ars222": 3, "ars443": 4, "strang/rk4": 5, "strang/rk3": 6,
@@ -144,6 +144,7 @@ _SIGNATURES = {
     "tb200_upload_reference_state": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "tb200_set_uniform_diffusion": (c_int, [c_void_p, c_double, c_double]),
     "tb200_set_vertical_discretization": (c_int, [c_void_p, c_int]),
+    "tb200_set_mass_flux_on_levels": (c_int, [c_void_p, c_int]),
     "tb200_upload_state_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tb200_download_state_async": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
                                            c_void_p, c_int]),

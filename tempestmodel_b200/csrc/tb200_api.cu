@@ -425,6 +425,7 @@ extern "C" int tb200_create(const tb200_config * cfg, tb200_ctx ** out) {
 	}
 	ctx->fe_nodes = cfg->vertical_order;
 	ctx->finite_volume = 0;
+	ctx->mass_flux_levels = 0;
 	memset(&ctx->ops, 0, sizeof(ctx->ops));
 	memset(&ctx->geom, 0, sizeof(ctx->geom));
 	memset(&ctx->tables, 0, sizeof(ctx->tables));
@@ -928,6 +929,12 @@ extern "C" int tb200_set_vertical_discretization(tb200_ctx * ctx, int finite_vol
 		ctx->offd = offd;
 	}
 	ctx->fast_state = 0;
+	return 0;
+}
+
+extern "C" int tb200_set_mass_flux_on_levels(tb200_ctx * ctx, int on) {
+	ctx->mass_flux_levels = on ? 1 : 0;
+	ctx->fast_state = 0;        // the column-constant path declines (fast_prepare)
 	return 0;
 }
 
@@ -1751,6 +1758,7 @@ static int fast_prepare(tb200_ctx * ctx) {
 	}
 	if (ctx->cfg.vertical_order != 1) { ctx->fast_reason = "vertical order > 1"; return 0; }
 	if (ctx->finite_volume) { ctx->fast_reason = "finite-volume vertical discretisation"; return 0; }
+	if (ctx->mass_flux_levels) { ctx->fast_reason = "--vmassfluxlevels (general kernels)"; return 0; }
 	if (uniform_on(ctx)) { ctx->fast_reason = "uniform diffusion (general kernels)"; return 0; }
 	if ((int)ctx->reta_n_h.size() != L || (int)ctx->reta_e_h.size() != L + 1) {
 		ctx->fast_reason = "vertical coordinate not set"; return 0;
@@ -1761,7 +1769,7 @@ static int fast_prepare(tb200_ctx * ctx) {
 		}
 	}
 	for (int q = 0; q < TB_NOPS; q++) {
-		if (q == 5 || q == 6) continue;
+		if (q == 5 || q == 6 || q == 10) continue;
 		if (ctx->hops[q].nout == 0) { ctx->fast_reason = "column operators not set"; return 0; }
 	}
 	// operator windows
@@ -1870,8 +1878,14 @@ static int need_metric3d(tb200_ctx * ctx, const char * what) {
 
 static int check_ops(tb200_ctx * ctx) {
 	for (int q = 0; q < TB_NOPS; q++) {
-		if (q == 5 || q == 6) continue;   // not used by the hot path
+		if (q == 5 || q == 6 || q == 10) continue;   // not used by the hot path
 		if (ctx->ops.op[q].coeff == 0) TB_FAIL(ctx, "vertical column operators not set");
+	}
+	if (ctx->mass_flux_levels && ctx->ops.op[10].coeff == 0) {
+		TB_FAIL(ctx, "--vmassfluxlevels needs the zero-boundaries DiffNodeToNode operator");
+	}
+	if ((ctx->uniform_s != 0.0 || ctx->uniform_v != 0.0) && ctx->ops.op[6].coeff == 0) {
+		TB_FAIL(ctx, "uniform diffusion needs the DiffDiffNodeToNode operator");
 	}
 	return 0;
 }
@@ -2190,6 +2204,7 @@ extern "C" int tb200_h_step_explicit(tb200_ctx * ctx, int in, int out, double dt
 
 // uniform diffusion terms of BuildF (VerticalDynamicsFEM.cpp:2594-2636)
 static int column_uniform_args(tb200_ctx * ctx, ColumnArgs & ca) {
+	ca.mass_flux_levels = ctx->mass_flux_levels;
 	if (!uniform_on(ctx)) return 0;
 	if (refstate_alloc(ctx)) return 1;
 	const double ztop = ctx->cfg.ztop;
@@ -2602,7 +2617,7 @@ static int column_solve(tb200_ctx * ctx, int in, int out, double dt) {
 	bool use_window = (ctx->offd == TBW_KL) && (ctx->cfg.vertical_order == 1) && !ctx->finite_volume;
 	if (force != 0 && strcmp(force, "thread") == 0) { wpb = 0; use_window = false; }
 	// (the uniform diffusion terms of BuildF are in the thread-per-column kernel only)
-	if (uniform_on(ctx)) { wpb = 0; use_window = false; force = "thread"; }
+	if (uniform_on(ctx) || ctx->mass_flux_levels) { wpb = 0; use_window = false; force = "thread"; }
 	if (force != 0 && strcmp(force, "warp") == 0) use_window = false;
 	if (force == 0 || strcmp(force, "warp") != 0) { if (use_window) wpb = 0; }
 	if (use_window) {

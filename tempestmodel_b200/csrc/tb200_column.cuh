@@ -41,6 +41,8 @@ struct ColumnArgs {
 	const double * ref = 0;
 	double uni_s = 0.0;
 	double uni_v = 0.0;
+	// --vmassfluxlevels (BuildF :2229-2243, 2301-2315; k_column_implicit only)
+	int mass_flux_levels = 0;
 };
 
 // number of workspace entries per column
@@ -299,17 +301,29 @@ __global__ void k_column_implicit(
 		F(q) = 0.0;
 	}
 	mfe(0) = 0.0; mfe(L) = 0.0; pfe(0) = 0.0; pfe(L) = 0.0;
-	for (int k = 1; k < L; k++) {
-		const double je = g.jace[g3e + (size_t)k * NN];
-		mfe(k) = je * seR(k) * xde(k);
-		pfe(k) = je * seP(k) * xde(k);
+	if (!ca.mass_flux_levels) {
+		for (int k = 1; k < L; k++) {
+			const double je = g.jace[g3e + (size_t)k * NN];
+			mfe(k) = je * seR(k) * xde(k);
+			pfe(k) = je * seP(k) * xde(k);
+		}
+	} else {
+		// fluxes on levels, differentiated with zero boundary fluxes
+		for (int k = 0; k < L; k++) {
+			const double jn = g.jac[g3 + (size_t)k * NN];
+			mfe(k) = jn * snR(k) * xdn(k);
+			pfe(k) = jn * snP(k) * xdn(k);
+		}
 	}
-	for (int k = 0; k < L; k++) {
-		const double invj = 1.0 / g.jac[g3 + (size_t)k * NN];
-		dmfn(k) = tb_ws_apply(opDiffE2N, mfe, k);
-		dpfn(k) = tb_ws_apply(opDiffE2N, pfe, k);
-		F(3 * k + FR) = dmfn(k) * invj;
-		F(3 * k + FP) += dpfn(k) * invj;
+	{
+		const DevOp & opFlux = ca.mass_flux_levels ? ops.op[10] : opDiffE2N;
+		for (int k = 0; k < L; k++) {
+			const double invj = 1.0 / g.jac[g3 + (size_t)k * NN];
+			dmfn(k) = tb_ws_apply(opFlux, mfe, k);
+			dpfn(k) = tb_ws_apply(opFlux, pfe, k);
+			F(3 * k + FR) = dmfn(k) * invj;
+			F(3 * k + FP) += dpfn(k) * invj;
+		}
 	}
 	// kinetic energy on levels (:2433-2467)
 	for (int k = 0; k < L; k++) {

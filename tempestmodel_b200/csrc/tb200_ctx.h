@@ -141,6 +141,7 @@ struct tb200_ctx {
 	int offd;
 	int fe_nodes;          // levels per vertical element: the order (FE), 1 (FV)
 	int finite_volume;     // Grid::VerticalDiscretization_FiniteVolume
+	int mass_flux_levels;  // --vmassfluxlevels
 
 	// exchange / compute overlap on several ranks
 	cudaStream_t stream2;

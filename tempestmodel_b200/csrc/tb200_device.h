@@ -23,7 +23,7 @@
 
 #define TB_MAXC 8
 #define TB_MAXNP 8
-#define TB_NOPS 10
+#define TB_NOPS 11
 
 struct DevLayout {
 	int np, nn;

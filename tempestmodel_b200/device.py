@@ -164,6 +164,10 @@ class DeviceContext:
         """--vdisc FV: the column operators supplied are the finite-volume ones."""
         self._ck(self.lib.tb200_set_vertical_discretization(self._h, int(bool(finite_volume))))
 
+    def set_mass_flux_on_levels(self, on):
+        """--vmassfluxlevels: BuildF forms the mass and rho-theta fluxes on levels."""
+        self._ck(self.lib.tb200_set_mass_flux_on_levels(self._h, int(bool(on))))
+
     def set_uniform_diffusion(self, scalar_coeff, vector_coeff):
         """TestCase::GetUniformDiffusionCoeffs -> Grid::HasUniformDiffusion: uniform
         second-order diffusion of the state minus the reference state."""

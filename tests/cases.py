@@ -278,6 +278,11 @@ CASES["jw_ne2_l24_vo4"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
     script=_STAGES_VO, compact=True)
 
+# --vmassfluxlevels: BuildF with the mass and rho-theta fluxes formed on levels
+CASES["jw_ne2_l6_mfl"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "6", "--dt", "200s", "--vmassfluxlevels"],
+    script=_STAGES_VO, compact=True)
+
 # the remaining IMEX schemes that run with these plugins (TimestepSchemeGARK2,
 # SSP3332, ARK232; ARS343b only works with HighSpeedDynamics)
 for _s in ("gark2", "ssp3_332", "ark232"):

@@ -133,6 +133,8 @@ def context_from_dump(d, library=None, ninstances=None, owners=None, rank=0,
                                        d[p + "topographyderiv"])
         ctx.set_vertical_coordinate(d["grid.retalevels"], d["grid.retainterfaces"])
     ctx.build_connectivity()
+    if "grid.massfluxlevels" in d and int(np.ravel(d["grid.massfluxlevels"])[0]) != 0:
+        ctx.set_mass_flux_on_levels(True)
     if "grid.vdisc_fv" in d and int(np.ravel(d["grid.vdisc_fv"])[0]) != 0:
         ctx.set_vertical_discretization(True)
     if "grid.diffs" in d and (float(np.ravel(d["grid.diffs"])[0]) != 0.0 or float(np.ravel(d["grid.diffv"])[0]) != 0.0):
