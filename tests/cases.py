@@ -274,6 +274,9 @@ _STAGES_VO = ";".join([
 CASES["jw_ne2_l12_vo2"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "12", "--vertorder", "2", "--dt", "200s"],
     script=_STAGES_VO, compact=True)
+CASES["jw_ne2_l24_vo3"] = dict(
+    case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "3", "--dt", "200s"],
+    script=_STAGES_VO, compact=True)
 CASES["jw_ne2_l24_vo4"] = dict(
     case="jw", flags=["--resolution", "2", "--levels", "24", "--vertorder", "4", "--dt", "200s"],
     script=_STAGES_VO, compact=True)

@@ -133,6 +133,7 @@ ENTRIES = {
     "jwtr_ne2_l6_ars343_2steps": lambda: tracer_spread("jwtr_ne2_l6_ars343"),
     # tests/test_parity.py::test_vertical_order_above_one
     "jw_ne2_l12_vo2_2steps": lambda: state_spread("jw_ne2_l12_vo2"),
+    "jw_ne2_l24_vo3_2steps": lambda: state_spread("jw_ne2_l24_vo3"),
     "jw_ne2_l24_vo4_2steps": lambda: state_spread("jw_ne2_l24_vo4"),
     # the same at vertical order 1, for comparison
     "jw_ne2_l6_strang_2steps": lambda: state_spread("jw_ne2_l6_strang"),
