@@ -17,7 +17,8 @@ SCHEME_INSTANCES = {"strang": 5, "strang/kgu35": 5, "strang/rk4": 5,
                     "strang/rk3": 5, "strang/fe": 5, "strang/ssprk53": 5,
                     "erk": 5, "erk/kgu35": 5, "erk/fe": 5, "erk/rk4": 5,
                     "erk/rk3": 5, "erk/ssprk53": 5,
-                    "ars343": 7, "ars222": 4, "ars232": 7, "ars443": 10}
+                    "ars343": 7, "ars222": 4, "ars232": 7, "ars443": 10,
+                    "gark2": 5, "ssp3_332": 9, "ark232": 8}
 
 
 class Model:

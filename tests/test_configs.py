@@ -420,3 +420,21 @@ def test_python_driver_workflow_processes(emu_library):
         dry0 = before_s[idx][0][4] - before_t[idx][:3].sum(axis=0)
         dry1 = after_s[idx][0][4] - after_t[idx][:3].sum(axis=0)
         assert np.abs(dry1 - dry0).max() <= 1e-13 * np.abs(dry0).max()
+
+
+@pytest.mark.parametrize("scheme", ["gark2", "ssp3_332", "ark232"])
+def test_python_driver_more_schemes(emu_library, scheme):
+    """The Python driver with the schemes added last (instance counts of
+    TimestepSchemeGARK2 / SSP3332 / ARK232): three steps of the JW case at ne = 2,
+    mass conserved to rounding, no failed column."""
+    grid = G.GridCSGLL(2, 6, npatch=6, ztop=30000.0)
+    model = Model(grid, TC.BaroclinicWaveJWTest(ztop=30000.0, perturbation="exp"),
+                  timescheme=scheme, dt=200.0, library=emu_library)
+    model.initialize()
+    m0 = model.checksum(0)[4]
+    model.step(3, last=False)
+    model.ctx.check_errors()
+    cs = model.checksum(0)
+    assert np.all(np.isfinite(cs))
+    assert abs(cs[4] - m0) <= 1e-13 * abs(m0)
+    model.ctx.close()
