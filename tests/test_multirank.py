@@ -44,6 +44,11 @@ def test_two_ranks_gloo_order5(emu_library):
     _run("gloo", port=29621, case="jw_ne2_l6_np5")
 
 
+def test_two_ranks_gloo_finite_volume_order2(emu_library):
+    """--vdisc FV --vertorder 2 on two ranks (general kernels, 12 levels)."""
+    _run("gloo", port=29623, case="jw_ne2_l12_fv2")
+
+
 def test_two_ranks_gloo_overlap(emu_library):
     """Element-list launches of the persistent kernels (exchange-feeding elements
     first, the rest on the second stream): same state."""
